@@ -1,0 +1,98 @@
+"""CPU: pin the oracle (oracle/lidf_oracle.py) against outputs of the reference's own code
+(tests/golden/*.npz, made by tests/golden/make_golden.py) and against torchvision's roi_align."""
+import pytest
+import torch
+
+from conftest import GOLDEN_CASES, load_golden, rel_err
+from oracle import lidf_oracle as O
+
+TOL = 2e-5   # fp32 oracle vs fp32 reference: same ops, only summation-order noise
+
+
+@pytest.mark.parametrize("name", GOLDEN_CASES)
+def test_oracle_matches_reference_outputs(name):
+    d, cfg, off, prob, part, ref, extra = load_golden(name)
+    out = O.lidf_query(d, cfg, off, prob, part, dedup_rays=True, pcl_label_float=extra.get("pcl_label_float"))
+    for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "pred_pos"):
+        assert out[k].shape == ref[k].shape, k
+        assert rel_err(out[k], ref[k]) < TOL, (k, rel_err(out[k], ref[k]))
+    assert torch.equal(out["max_pair_id"], ref["max_pair_id"])
+    if "roi_feat_per_ray" in ref:
+        ray = d["miss_ray_intersect_idx"]
+        assert rel_err(out["intersect_rgb_feat"], ref["roi_feat_per_ray"][ray]) < TOL
+
+
+def test_oracle_per_pair_roi_equals_per_ray_roi():
+    d, cfg, off, prob, part, ref, _ = load_golden("ief_rel_sigmoid_1x16x20")
+    a = O.get_embedding(d, cfg, dedup_rays=False)["intersect_rgb_feat"]
+    b = O.get_embedding(d, cfg, dedup_rays=True)["intersect_rgb_feat"]
+    assert torch.equal(a, b)
+
+
+def test_fp64_oracle_error_budget():
+    """fp32 reference vs fp64 oracle: the reference itself is only ~1e-5 accurate; the 1e-3 bar has room."""
+    d, cfg, off, prob, part, ref, _ = load_golden("ief_ragged_2x24x32")
+    out = O.lidf_query(O.cast_tree(d, torch.float64), cfg, O.cast_tree(off, torch.float64),
+                       O.cast_tree(prob, torch.float64), part, dedup_rays=True)
+    for k in ("pred_offset", "pred_prob_end", "pair_pred_pos"):
+        assert rel_err(ref[k], out[k]) < 1e-4, k
+
+
+def test_roi_align_restatement_vs_torchvision():
+    tv = pytest.importorskip("torchvision.ops")
+    g = torch.Generator().manual_seed(0)
+    for (B, C, H, W) in [(2, 5, 13, 17), (1, 3, 6, 7), (1, 2, 3, 4)]:
+        feat = torch.randn(B, C, H, W, generator=g)
+        ys, xs = torch.meshgrid(torch.arange(H), torch.arange(W), indexing="ij")
+        pix = torch.stack((xs.reshape(-1), ys.reshape(-1)), -1)
+        for b in range(B):
+            ul = pix - 4; br = pix + 4
+            ul = torch.stack((ul[:, 0].clamp(0, W - 1), ul[:, 1].clamp(0, H - 1)), -1)
+            br = torch.stack((br[:, 0].clamp(0, W - 1), br[:, 1].clamp(0, H - 1)), -1)
+            boxes = torch.cat((torch.full((pix.shape[0], 1), b), ul, br), -1).float()
+            want = tv.roi_align(feat, boxes, output_size=2, spatial_scale=1.0, aligned=True)
+            got = O.roi_align_aligned(feat, boxes, 2, 1.0)
+            assert torch.allclose(got, want, atol=1e-5, rtol=1e-5)
+    # fractional boxes too (not produced by the reference, but the restatement is general)
+    feat = torch.randn(1, 4, 20, 24, generator=g)
+    xy = torch.rand(64, 2, generator=g) * torch.tensor([20.0, 16.0])
+    wh = torch.rand(64, 2, generator=g) * 7.5
+    boxes = torch.cat((torch.zeros(64, 1), xy, xy + wh), -1)
+    want = tv.roi_align(feat, boxes, output_size=2, spatial_scale=1.0, aligned=True)
+    assert torch.allclose(O.roi_align_aligned(feat, boxes, 2, 1.0), want, atol=1e-5, rtol=1e-5)
+
+
+def test_scatter_semantics():
+    src = torch.tensor([1.0, 3.0, 3.0, -2.0, 0.5])
+    idx = torch.tensor([0, 0, 0, 2, 2])
+    mx, arg = O.scatter_max(src, idx, dim_size=4)
+    assert mx.tolist() == [3.0, 0.0, 0.5, 0.0]
+    assert arg.tolist() == [1, 5, 4, 5]          # first max wins; empty segment -> src.numel()
+    sm = O.scatter_softmax(src, idx)
+    assert abs(float(sm[:3].sum()) - 1) < 1e-6 and abs(float(sm[3:].sum()) - 1) < 1e-6
+
+
+def test_embed_layout_and_dims():
+    x = torch.tensor([[0.1, -0.2, 0.3]])
+    e = O.embed(x, 8)
+    assert e.shape == (1, 51) and O.embed_out_dim(8) == 51 and O.embed_out_dim(4) == 27
+    assert torch.allclose(e[0, 3:6], torch.sin(x[0])) and torch.allclose(e[0, 6:9], torch.cos(x[0]))
+    assert torch.allclose(e[0, 45:48], torch.sin(128 * x[0])) and torch.allclose(e[0, 48:51], torch.cos(128 * x[0]))
+    assert O.embed(x, 8, enabled=False) is x
+
+
+def test_refine_tail_matches_reference():
+    d, cfg, off, prob, part, ref, extra = load_golden("ief_ragged_2x24x32")
+    rdec = {k[len("refine_dec."):]: v for k, v in extra.items() if k.startswith("refine_dec.")}
+    evid = extra["refine.end_voxel_id"].long()
+    vb = d["voxel_bound"][evid]
+    center = (vb[:, :3] + vb[:, 3:]) / 2
+    rgb = O.roi_align_aligned(d["full_rgb_feat"], torch.cat((d["miss_bid"].unsqueeze(-1).float(),
+                              (d["miss_img_ind"] - 4).clamp(min=0).float(),
+                              torch.stack(((d["miss_img_ind"][:, 0] + 4).clamp(max=d["full_rgb_feat"].shape[3] - 1),
+                                           (d["miss_img_ind"][:, 1] + 4).clamp(max=d["full_rgb_feat"].shape[2] - 1)), -1).float()), -1))
+    rcfg = dict(O.REFINE_CFG, offset_range=tuple(float(v) for v in extra["refine.offset_range"]),
+                n_iter=extra["refine.n_iter"])
+    out = O.refine_decoder_tail(ref["pred_pos"], d["miss_ray_dir"], center, extra["refine.occ_voxel_feat"][evid],
+                                rgb.reshape(rgb.shape[0], -1), rcfg, rdec)
+    assert rel_err(out, ref["pred_pos_refine"]) < TOL
