@@ -1,0 +1,325 @@
+#!/usr/bin/env python
+"""bench.py -- LIDF query-points/sec on synthetic batches (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c3] [--engine auto] [--impl ours|reference]
+
+One "step" = one pass of the hot path: device-resident (full_rgb_feat, occ_voxel_feat, rays,
+voxel-major pair list, enter/leave distances, decoder weights) -> the six outputs of LIDF.get_pred written.
+Workload at every N: BASELINE config 3 per GPU -- 8 images of 640x480 rays x 64 pairs/ray = 157,286,400 query points,
+shipped decoders (IEF n_iter 2 + IMNet), i.e. weak scaling by image (no data-path collective).
+
+Printed JSON (one line, rank 0): value = whole-job points/s with inputs resident in HBM (CUDA-event timed, max over
+ranks); e2e = same metric through ``lidf_query.forward_host`` with pinned HOST buffers (H2D + D2H inside the timed
+region); roofline = nominal decoder FLOPs / decoder-kernel time vs the measured bf16 peak; cpu_baseline = the oracle
+port of the reference (stock torch CPU ops + torchvision roi_align) on the host cores, on a bounded sample.
+
+``--impl reference`` times that same CPU port as the reference arm (the reference is a Python/PyTorch program with no
+compiled artefact; /root/reference is not available on the GPU box).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import torch
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, REPO)
+
+WORKLOADS = {          # name: (B per GPU, H, W, N)   -- BASELINE.json configs
+    "c1": (1, 64, 64, 16),
+    "c2": (4, 240, 320, 64),
+    "c3": (8, 480, 640, 64),
+    "c4": (4, 480, 640, 64),
+    "tiny": (1, 48, 64, 16),
+}
+FLOP_IMNET = 279168            # 2*MAC of the reference Linear stack, per query point
+FLOP_IEF2 = 574784
+FLOP_PER_POINT = {"IEF": FLOP_IEF2 + FLOP_IMNET, "IMNET": 2 * FLOP_IMNET}
+EXEC_MAC_TC = 921600           # MAC-equivalents the tcgen05 engine executes per point (3 bf16 products / MAC)
+
+
+def load_peaks():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            pk = json.load(f)
+        return dict(bf16_tflops=pk["bf16_tflops"], bf16_tflops_sustained=pk["bf16_tflops_sustained"],
+                    hbm_gbs=pk["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+    return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
+
+
+class ClockSampler:
+    """nvidia-smi sampling during the timed region (B200_PROFILING.md clocks line)."""
+
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index: int):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.th = threading.Thread(target=self._read, daemon=True)
+            self.th.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm = [int(r[0]) for r in self.rows if len(r) >= 6 and r[0].isdigit()]
+        mx = [int(r[1]) for r in self.rows if len(r) >= 6 and r[1].isdigit()]
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = sorted({n for r in self.rows if len(r) >= 6 for n, v in zip(names, r[2:6]) if v.lower().startswith("active")})
+        return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=max(mx) if mx else None, reasons=reasons,
+                    samples=len(sm))
+
+
+def make_decoders(device, offdec="IEF"):
+    """'trained-like' decoders with the reference's state_dict keys, as modules."""
+    from implicit_depth_b200.models import implicit_net as N
+    g = torch.Generator().manual_seed(99)
+    off = N.IEF(device, 385, 1, gf_dim=64, n_iter=2) if offdec == "IEF" else N.IMNet(385, 1, gf_dim=64)
+    prob = N.IMNet(385, 1, gf_dim=64)
+    for mod in (off, prob):
+        for name, p in mod.named_parameters():
+            with torch.no_grad():
+                if p.dim() == 2:
+                    p.copy_(torch.randn(p.shape, generator=g) / (p.shape[1] ** 0.5))
+                else:
+                    p.copy_(torch.randn(p.shape, generator=g) * 0.1)
+    return off.to(device).eval(), prob.to(device).eval()
+
+
+def cpu_reference_points_per_s(workload, offdec, budget_pairs, steps=1, warmup=0, threads=None):
+    """The reference's op chain on the host cores: oracle port + torchvision roi_align, per pair, fp32.
+    Sample = the first ``budget_pairs`` pairs worth of rays of image 0 of the same synthetic workload."""
+    from implicit_depth_b200.synthetic import make_inputs
+    from oracle import lidf_oracle as O
+    try:
+        import torchvision.ops as tv_ops
+        roi_fn = lambda feat, boxes, out, scale: tv_ops.roi_align(feat, boxes, output_size=out, spatial_scale=scale, aligned=True)
+        roi_name = "torchvision.ops.roi_align"
+    except Exception:
+        roi_fn, roi_name = None, "oracle roi_align restatement"
+    threads = threads or os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    B, H, W, N = WORKLOADS[workload]
+    rows = max(1, min(H, budget_pairs // (W * N)))
+    d = make_inputs(1, rows, W, N, seed=1234)          # one image strip of `rows` x W rays, N pairs each
+    g = torch.Generator().manual_seed(99)
+    cfg = dict(O.DEFAULT_CFG, offdec_type=offdec)
+    off = O.init_decoder(offdec, 385, mode="trained", generator=g)
+    prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
+    P = d["occ_vox_intersect_idx"].shape[0]
+    times = []
+    with torch.no_grad():
+        for i in range(warmup + steps):
+            t0 = time.perf_counter()
+            O.lidf_query_chunked(d, cfg, off, prob, d["part_size"], chunk_pairs=1 << 18, roi_fn=roi_fn)
+            if i >= warmup:
+                times.append(time.perf_counter() - t0)
+    t = sum(times) / len(times)
+    sample = f"{rows}x{W} rays x {N} pairs = {P} points of the {workload} workload, {steps} pass(es), {roi_name}"
+    return P / t, t, threads, sample, P
+
+
+def run_reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    pts, t, threads, sample, P = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs,
+                                                            steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    B, H, W, N = WORKLOADS[args.workload]
+    line = dict(impl="reference", metric="lidf_query_points_per_sec", value=pts, unit="points/s", n_gpus=args.gpus,
+                steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"{args.workload}: {H}x{W} rays x {N} pairs/ray, decoders {args.offdec}+IMNET "
+                                     f"(bounded sample of it, see cpu_baseline.sample)"),
+                cpu_baseline=dict(value=pts, unit="points/s", cores=threads, kind="port", sample=sample),
+                e2e=dict(value=pts, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c3", choices=sorted(WORKLOADS))
+    ap.add_argument("--engine", default="auto", choices=["auto", "simt_fp32", "tc_bf16x3", "tc_bf16x1"])
+    ap.add_argument("--offdec", default="IEF", choices=["IEF", "IMNET"])
+    ap.add_argument("--cpu-sample-pairs", type=int, default=1 << 19)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the stock torch op chain (oracle port) on the GPU over a bounded sample")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        return run_reference_arm(args)
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the lidf_query path has no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    from implicit_depth_b200.synthetic import make_inputs
+
+    B, H, W, N = WORKLOADS[args.workload]
+    d = make_inputs(B, H, W, N, seed=1234 + rank, device=dev)      # this rank's images; pair list voxel-major
+    off, prob = make_decoders(dev, args.offdec)
+    P = int(d["occ_vox_intersect_idx"].shape[0]); R = int(d["miss_ray_dir"].shape[0])
+    kw = dict(part_size=d["part_size"], mlp_impl=args.engine)
+    ins = [d[k] for k in lidf_query.INPUT_KEYS]
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step():
+        return lidf_query.forward(*ins, off, prob, **kw)
+
+    for _ in range(max(3, args.warmup)):
+        out = step()
+    del out
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    lidf_query.launch_count(reset=True)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    mlp_ms = []
+    e0.record()
+    for _ in range(args.steps):
+        out = step()
+        del out
+    e1.record()
+    barrier()
+    launches = lidf_query.launch_count()
+    total_ms = e0.elapsed_time(e1)
+    # decoder-kernel time: CUDA events recorded by the library around that launch, on the launching stream
+    for _ in range(min(3, args.steps)):
+        step()
+        mlp_ms.append(lidf_query.last_mlp_ms())
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t) / args.steps
+    value = P * world / (ms_per_step * 1e-3)
+
+    # ---- e2e: the same call with pinned HOST buffers, H2D + D2H inside the timed region ----------------------
+    e2e = None
+    if not args.no_e2e:
+        host = {k: d[k].cpu().pin_memory() for k in lidf_query.INPUT_KEYS}
+        out_host, h2d, d2h = lidf_query.forward_host(host, off, prob, dev, **kw)         # warm-up, allocates pinned outputs
+        lidf_query.forward_host(host, off, prob, dev, out_host=out_host, **kw)
+        barrier()
+        n_e2e = max(1, min(args.steps, 3))
+        t0 = time.perf_counter()
+        for _ in range(n_e2e):
+            lidf_query.forward_host(host, off, prob, dev, out_host=out_host, **kw)
+        torch.cuda.synchronize()
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = dict(value=P * world / float(te), unit="points/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                   ms_per_step=float(te) * 1e3)
+        del host, out_host
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = load_peaks()
+    k_ms = statistics.median(mlp_ms)
+    flop_pt = FLOP_PER_POINT[args.offdec]
+    achieved = P * flop_pt / (k_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]           # the kernel is ~the whole of a long step -> sustained figure
+    roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                    kernel="k_mlp_simt" if args.engine == "simt_fp32" else "k_mlp_tc", kernel_ms=k_ms,
+                    kernel_share_of_step=k_ms / ms_per_step, flop_per_point_nominal=flop_pt,
+                    executed_tflops=(P * 2 * EXEC_MAC_TC / (k_ms * 1e-3) / 1e12) if args.engine != "simt_fp32" else None,
+                    peak_source=peaks["source"] + ", bf16_tflops_sustained")
+    cpu = None
+    if not args.no_cpu_baseline:
+        pts, tcpu, threads, sample, _ = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs)
+        cpu = dict(value=pts, unit="points/s", cores=threads, kind="port", sample=sample, seconds=tcpu)
+    line = dict(metric="lidf_query_points_per_sec", value=value, unit="points/s", n_gpus=world, steps=args.steps,
+                warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16x3 (split bf16 operands, fp32 accumulate)" if args.engine != "simt_fp32" else "f32",
+                data="synthetic",
+                config=dict(workload=f"{args.workload}: {B} images/GPU of {H}x{W} rays x {N} pairs/ray = {P} points/GPU, "
+                                     f"decoders {args.offdec}(n_iter 2)+IMNET, trained-like random weights",
+                            engine=args.engine, l2="inputs (>3 GB/step) exceed the 126 MB L2; no explicit flush",
+                            pair_order="reference voxel-major (regroup inside the timed region)"),
+                clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+    if args.torch_gpu_baseline:
+        line["torch_gpu_baseline"] = torch_gpu_baseline(d, off, prob, args, dev)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def torch_gpu_baseline(d, off, prob, args, dev, rays=1 << 14):
+    """Extra, not part of the contract: the reference's stock op chain (oracle port, torch CUDA ops, fp32, TF32 off)
+    on the same GPU over the first ``rays`` rays -- the 'reference PyTorch decoder' BASELINE.json's 10x target names."""
+    from oracle import lidf_oracle as O
+    import torchvision.ops as tv_ops
+    m = d["miss_ray_intersect_idx"] < rays
+    sub = dict(d)
+    for k in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist"):
+        sub[k] = d[k][m]
+    P = int(sub["occ_vox_intersect_idx"].shape[0])
+    cfg = dict(O.DEFAULT_CFG, offdec_type=args.offdec)
+    offd = {k: v.detach() for k, v in off.state_dict().items()}
+    probd = {k: v.detach() for k, v in prob.state_dict().items()}
+    roi_fn = lambda feat, boxes, out, scale: tv_ops.roi_align(feat, boxes, output_size=out, spatial_scale=scale, aligned=True)
+    torch.backends.cuda.matmul.allow_tf32 = False
+    with torch.no_grad():
+        for _ in range(2):
+            O.lidf_query_chunked(sub, cfg, offd, probd, d["part_size"], chunk_pairs=1 << 20, roi_fn=roi_fn)
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            O.lidf_query_chunked(sub, cfg, offd, probd, d["part_size"], chunk_pairs=1 << 20, roi_fn=roi_fn)
+        e1.record()
+        torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return dict(value=P / (ms * 1e-3), unit="points/s", sample=f"{rays} rays = {P} points, chunk 2^20 pairs", ms=ms)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,275 @@
+// lidf_prep.cuh -- pair regroup (voxel-major -> ray-major CSR), ROIAlign per ray, ray termination.
+#pragma once
+#include "lidf_common.cuh"
+
+// ------------------------------------------------------------------------------------------------
+// Pair regroup.  The reference's pair list is torch.nonzero of a [V,R] mask (pipeline.py:283-285),
+// i.e. sorted by voxel then ray.  The decoder kernels and the ray termination want all pairs of a
+// ray adjacent, so we build a CSR by ray: ray_start[R+1] and perm[P] (sorted slot -> original pair).
+// Outputs are always written back at the ORIGINAL pair index, so results are order-independent.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_count_pairs(const int64_t* __restrict__ pair_ray, int64_t P, int64_t R, int* __restrict__ cnt,
+                              int* __restrict__ err) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  int64_t r = pair_ray[i];
+  if (r < 0 || r >= R) { atomicOr(err, 1); return; }
+  atomicAdd(cnt + r, 1);
+}
+
+// exclusive scan of int32 counts, 3 kernels (block partials, scan of partials, add back)
+#define LIDF_SCAN_BLOCK 1024
+#define LIDF_SCAN_ITEMS 4
+__global__ void k_scan_partial(const int* __restrict__ in, int64_t n, int* __restrict__ out, int* __restrict__ block_sums) {
+  __shared__ int warp_sums[32];
+  const int64_t base = ((int64_t)blockIdx.x * LIDF_SCAN_BLOCK + threadIdx.x) * LIDF_SCAN_ITEMS;
+  int v[LIDF_SCAN_ITEMS];
+  int tsum = 0;
+#pragma unroll
+  for (int j = 0; j < LIDF_SCAN_ITEMS; ++j) { v[j] = (base + j < n) ? in[base + j] : 0; tsum += v[j]; }
+  int inc = tsum;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+  if (lane == 31) warp_sums[warp] = inc;
+  __syncthreads();
+  if (warp == 0) {
+    int w = warp_sums[lane];
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+    warp_sums[lane] = w;
+  }
+  __syncthreads();
+  int excl = inc - tsum + (warp ? warp_sums[warp - 1] : 0);
+#pragma unroll
+  for (int j = 0; j < LIDF_SCAN_ITEMS; ++j) { if (base + j < n) out[base + j] = excl; excl += v[j]; }
+  if (threadIdx.x == LIDF_SCAN_BLOCK - 1) block_sums[blockIdx.x] = excl;
+}
+// single block: exclusive scan of block_sums in place (nb <= a few thousand)
+__global__ void k_scan_blocksums(int* __restrict__ block_sums, int nb) {
+  __shared__ int carry;
+  __shared__ int warp_sums[32];
+  if (threadIdx.x == 0) carry = 0;
+  __syncthreads();
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int b0 = 0; b0 < nb; b0 += 1024) {
+    int i = b0 + threadIdx.x;
+    int v = i < nb ? block_sums[i] : 0;
+    int inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      int w = warp_sums[lane];
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { int t = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += t; }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    int excl = inc - v + (warp ? warp_sums[warp - 1] : 0) + carry;
+    if (i < nb) block_sums[i] = excl;
+    __syncthreads();
+    if (threadIdx.x == 1023) carry = excl + v;
+    __syncthreads();
+  }
+}
+__global__ void k_scan_add(int* __restrict__ out, int64_t n, const int* __restrict__ block_sums, int* __restrict__ total_slot) {
+  const int64_t base = ((int64_t)blockIdx.x * LIDF_SCAN_BLOCK + threadIdx.x) * LIDF_SCAN_ITEMS;
+  const int add = block_sums[blockIdx.x];
+#pragma unroll
+  for (int j = 0; j < LIDF_SCAN_ITEMS; ++j)
+    if (base + j < n) out[base + j] += add;
+  (void)total_slot;
+}
+
+// perm fill: slot = ray_start[ray] + (running cursor); cursor array must be zero on entry
+__global__ void k_fill_perm(const int64_t* __restrict__ pair_ray, int64_t P, const int* __restrict__ ray_start,
+                            int* __restrict__ cursor, int* __restrict__ perm) {
+  int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  int r = (int)pair_ray[i];
+  int slot = ray_start[r] + atomicAdd(cursor + r, 1);
+  perm[slot] = (int)i;
+}
+// Make each ray's segment ascending in original pair index (the atomics above fill it in arbitrary order),
+// so that every floating-point reduction over a ray runs in a reproducible order.
+// One warp per ray; segments up to 128 pairs are sorted in registers (bitonic network, shuffles for
+// strides < 32), longer ones by odd-even transposition in place.
+template <int NPL>
+__device__ __forceinline__ void warp_bitonic_sort(int (&v)[NPL], int lane) {
+  constexpr int N = 32 * NPL;
+#pragma unroll
+  for (int k = 2; k <= N; k <<= 1) {
+#pragma unroll
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      if (j >= 32) {
+        const int qj = j >> 5;
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+          if ((q & qj) == 0) {
+            const bool up = (((q << 5) + lane) & k) == 0;
+            const int a = v[q], b = v[q | qj];
+            if ((a > b) == up) { v[q] = b; v[q | qj] = a; }
+          }
+        }
+      } else {
+#pragma unroll
+        for (int q = 0; q < NPL; ++q) {
+          const int o = __shfl_xor_sync(0xffffffffu, v[q], j);
+          const bool up = (((q << 5) + lane) & k) == 0;
+          const bool lower = (lane & j) == 0;
+          v[q] = (lower == up) ? min(v[q], o) : max(v[q], o);
+        }
+      }
+    }
+  }
+}
+template <int NPL>
+__device__ __forceinline__ void sort_segment_regs(int* __restrict__ perm, int s, int n, int lane) {
+  int v[NPL];
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) v[q] = (q * 32 + lane < n) ? perm[s + q * 32 + lane] : 0x7fffffff;
+  warp_bitonic_sort<NPL>(v, lane);
+#pragma unroll
+  for (int q = 0; q < NPL; ++q) if (q * 32 + lane < n) perm[s + q * 32 + lane] = v[q];
+}
+__global__ void k_sort_segments(const int* __restrict__ ray_start, int64_t R, int* __restrict__ perm) {
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= R) return;
+  const int s = ray_start[ray], e = ray_start[ray + 1];
+  const int n = e - s;
+  if (n <= 1) return;
+  if (n <= 32) { sort_segment_regs<1>(perm, s, n, lane); return; }
+  if (n <= 64) { sort_segment_regs<2>(perm, s, n, lane); return; }
+  if (n <= 128) { sort_segment_regs<4>(perm, s, n, lane); return; }
+  for (int pass = 0; pass < n; ++pass) {   // long segment (rare): odd-even transposition, n passes
+    const int off = pass & 1;
+    for (int i = off + 2 * lane; i + 1 < n; i += 64) {
+      int a = perm[s + i], b = perm[s + i + 1];
+      if (a > b) { perm[s + i] = b; perm[s + i + 1] = a; }
+    }
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// ROIAlign per ray: torchvision.ops.roi_align(feat, boxes, output_size=2, spatial_scale=1, sampling_ratio=-1,
+// aligned=True) with boxes = (bid, clamp(x-h), clamp(y-h), clamp(x+h), clamp(y+h)), h = roi_inp_bbox//2
+// (reference src/models/pipeline.py:374-389).  The feature depends only on the ray, so it is evaluated once per ray
+// (the reference recomputes it for every pair).  Output [R,128] in (c, ph, pw) order (pipeline.py:389).
+// One lane per ray (consecutive rays = consecutive x -> coalesced rows), warps loop over channels.
+// ------------------------------------------------------------------------------------------------
+struct RoiAxis {  // per axis, per output bin: sample taps
+  float start, bin;
+  int grid;
+};
+
+__device__ __forceinline__ void roi_tap(float p, int size, int& lo, int& hi, float& l, float& h, bool& dead) {
+  // torchvision bilinear_interpolate, one axis
+  dead = (p < -1.0f) || (p > (float)size);
+  if (p <= 0.f) p = 0.f;
+  lo = (int)p;
+  if (lo >= size - 1) { hi = lo = size - 1; p = (float)lo; } else { hi = lo + 1; }
+  l = p - (float)lo;
+  h = 1.0f - l;
+}
+
+#define LIDF_ROI_THREADS 256
+__global__ void __launch_bounds__(LIDF_ROI_THREADS)
+k_roi_align_rays(const float* __restrict__ feat, int B, int H, int W, const int64_t* __restrict__ img_ind,
+                 const int64_t* __restrict__ bid, int64_t R, int half, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t ray = (int64_t)blockIdx.x * 32 + lane;
+  if (ray >= R) return;
+  const int px = (int)img_ind[2 * ray], py = (int)img_ind[2 * ray + 1];
+  const int b = (int)bid[ray];
+  // boxes are built from integers then .float() (pipeline.py:374-381)
+  const float x1 = (float)min(max(px - half, 0), W - 1), x2 = (float)min(max(px + half, 0), W - 1);
+  const float y1 = (float)min(max(py - half, 0), H - 1), y2 = (float)min(max(py + half, 0), H - 1);
+  const float sw = x1 - 0.5f, sh = y1 - 0.5f;
+  const float rw = (x2 - 0.5f) - sw, rh = (y2 - 0.5f) - sh;
+  const float bw = rw / 2.0f, bh = rh / 2.0f;
+  const int gw = (int)ceilf(rw / 2.0f), gh = (int)ceilf(rh / 2.0f);
+  const float count = (float)max(gh * gw, 1);
+  const float* fb = feat + (size_t)b * LIDF_RGB_CH * H * W;
+  for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
+    const float* fc = fb + (size_t)c * H * W;
+    float o[4];
+#pragma unroll
+    for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+      for (int pw = 0; pw < 2; ++pw) {
+        float acc = 0.f;
+        for (int iy = 0; iy < gh; ++iy) {
+          const float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
+          int ylo, yhi; float ly, hy; bool ydead;
+          roi_tap(y, H, ylo, yhi, ly, hy, ydead);
+          for (int ix = 0; ix < gw; ++ix) {
+            const float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
+            int xlo, xhi; float lx, hx; bool xdead;
+            roi_tap(x, W, xlo, xhi, lx, hx, xdead);
+            float val = 0.f;
+            if (!(ydead || xdead)) {
+              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+              // same expression order as torchvision: w1*v1 + w2*v2 + w3*v3 + w4*v4; zero-weight taps are skipped
+              // (v finite => identical result) which makes interior pixels one load per sample.
+              val = w1 * __ldg(fc + (size_t)ylo * W + xlo);
+              if (w2 != 0.f) val += w2 * __ldg(fc + (size_t)ylo * W + xhi);
+              if (w3 != 0.f) val += w3 * __ldg(fc + (size_t)yhi * W + xlo);
+              if (w4 != 0.f) val += w4 * __ldg(fc + (size_t)yhi * W + xhi);
+            }
+            acc += val;
+          }
+        }
+        o[ph * 2 + pw] = acc / count;
+      }
+    }
+    *reinterpret_cast<float4*>(out + (size_t)ray * LIDF_RGB_DIM + c * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Ray termination (reference src/models/pipeline.py:441-454):
+//   soft = scatter_softmax(pred_prob_end, ray)         exp(x - max) / (sum + 1e-12)
+//   max_pair_id = scatter_max(soft | pcl_label, ray)   first maximum (lowest pair index) wins, empty ray -> P
+//   pred_pos = cat(pair_pred_pos, 0)[max_pair_id]
+// One warp per ray over the CSR built above; all reductions are warp shuffles.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_ray_terminate(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
+                                const float* __restrict__ label, const int* __restrict__ ray_start,
+                                const int* __restrict__ perm, int64_t P, int64_t R, float* __restrict__ soft,
+                                int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos) {
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= R) return;
+  const int s = ray_start[ray], e = ray_start[ray + 1];
+  float m = -INFINITY;
+  for (int i = s + lane; i < e; i += 32) m = fmaxf(m, logit[perm ? perm[i] : i]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  // sum in segment order: lane-strided partials, then a fixed shuffle tree (reproducible)
+  float sum = 0.f;
+  for (int i = s + lane; i < e; i += 32) sum += expf(logit[perm ? perm[i] : i] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float denom = sum + 1e-12f;
+  float best = -INFINITY;
+  int best_id = 0x7fffffff;
+  for (int i = s + lane; i < e; i += 32) {
+    const int id = perm ? perm[i] : i;
+    const float sv = expf(logit[id] - m) / denom;
+    soft[id] = sv;
+    const float key = label ? label[id] : sv;
+    if (key > best || (key == best && id < best_id)) { best = key; best_id = id; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
+    if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
+  }
+  if (lane == 0) max_pair_id[ray] = (e > s) ? (int64_t)best_id : P;
+  if (lane < 3) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
+}

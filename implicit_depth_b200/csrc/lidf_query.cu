@@ -1,0 +1,455 @@
+// lidf_query.cu -- C-ABI entry points (include/lidf_query.h) and host-side launch plan.
+//
+// Launch plan of lidf_query_forward (all on the caller's stream, no host sync, no allocation):
+//   1. regroup  : k_count_pairs -> exclusive scan -> k_fill_perm -> k_sort_segments   (pairs -> CSR by ray)
+//   2. k_roi_align_rays                       ROIAlign feature once per ray             (pipeline.py:374-389)
+//   3. weight packing                         k-major fp32 copies / bf16 hi-lo stream images
+//   4. k_rowprep (rays [, voxels])            per-ray / per-voxel part of linear_1
+//   5. decoder kernel                         k_mlp_tc (tcgen05, default) or k_mlp_simt (fp32)
+//   6. k_ray_terminate                        scatter_softmax + scatter_max + pred_pos  (pipeline.py:441-454)
+#include <cuda_runtime.h>
+#include <limits.h>
+#include <math.h>
+#include <stdio.h>
+#include <string.h>
+
+#include "lidf_common.cuh"
+#include "lidf_prep.cuh"
+#include "lidf_simt.cuh"
+#include "lidf_tc.cuh"
+
+static thread_local char g_cuda_err[256] = "";
+static thread_local int64_t g_launches = 0;
+static thread_local cudaEvent_t g_ev_mlp[2] = {nullptr, nullptr};
+static thread_local bool g_ev_valid = false;
+
+static void mlp_event(int which, cudaStream_t st) {
+  if (!g_ev_mlp[0]) { cudaEventCreate(&g_ev_mlp[0]); cudaEventCreate(&g_ev_mlp[1]); }
+  cudaEventRecord(g_ev_mlp[which], st);
+  if (which == 1) g_ev_valid = true;
+}
+
+#define LIDF_LAUNCH_CHECK()                                                        \
+  do {                                                                             \
+    ++g_launches;                                                                  \
+    cudaError_t e__ = cudaGetLastError();                                          \
+    if (e__ != cudaSuccess) {                                                      \
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return LIDF_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+#define LIDF_CUDA(call)                                                            \
+  do {                                                                             \
+    cudaError_t e__ = (call);                                                      \
+    if (e__ != cudaSuccess) {                                                      \
+      snprintf(g_cuda_err, sizeof(g_cuda_err), "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__)); \
+      return LIDF_ERR_CUDA;                                                        \
+    }                                                                              \
+  } while (0)
+
+namespace {
+
+struct Bump {  // workspace carving, 256-byte aligned
+  char* base; size_t off;
+  template <typename T> T* take(size_t n) {
+    off = (size_t)lidf_align_up((int64_t)off, 256);
+    T* p = base ? reinterpret_cast<T*>(base + off) : nullptr;
+    off += n * sizeof(T);
+    return p;
+  }
+};
+
+inline int pad16(int k) { return (k + 15) / 16 * 16; }
+
+struct CsrBufs { int* cnt; int* ray_start; int* block_sums; int* perm; int nb; };
+
+CsrBufs carve_csr(Bump& b, int64_t P, int64_t R) {
+  CsrBufs c;
+  const int64_t n = R + 1;
+  c.nb = (int)((n + LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS - 1) / (LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS));
+  c.cnt = b.take<int>(n + 1);          // +1: error flag lives at cnt[n]
+  c.ray_start = b.take<int>(n);
+  c.block_sums = b.take<int>(c.nb);
+  c.perm = b.take<int>(P > 0 ? P : 1);
+  return c;
+}
+
+int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, cudaStream_t st) {
+  const int64_t n = R + 1;
+  LIDF_CUDA(cudaMemsetAsync(c.cnt, 0, sizeof(int) * (n + 1), st));
+  if (P > 0) {
+    k_count_pairs<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.cnt, c.cnt + n);
+    LIDF_LAUNCH_CHECK();
+  }
+  k_scan_partial<<<c.nb, LIDF_SCAN_BLOCK, 0, st>>>(c.cnt, n, c.ray_start, c.block_sums);
+  LIDF_LAUNCH_CHECK();
+  k_scan_blocksums<<<1, 1024, 0, st>>>(c.block_sums, c.nb);
+  LIDF_LAUNCH_CHECK();
+  k_scan_add<<<c.nb, LIDF_SCAN_BLOCK, 0, st>>>(c.ray_start, n, c.block_sums, nullptr);
+  LIDF_LAUNCH_CHECK();
+  if (P > 0) {
+    LIDF_CUDA(cudaMemsetAsync(c.cnt, 0, sizeof(int) * n, st));
+    k_fill_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, c.ray_start, c.cnt, c.perm);
+    LIDF_LAUNCH_CHECK();
+    k_sort_segments<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(c.ray_start, R, c.perm);
+    LIDF_LAUNCH_CHECK();
+  }
+  return LIDF_OK;
+}
+
+int check_decoder(const LidfDecoder& d, int D) {
+  if (!d.w1 || !d.b1 || !d.w2 || !d.b2 || !d.w3 || !d.b3 || !d.w4 || !d.b4) return LIDF_ERR_NULL;
+  if (d.kind != LIDF_DEC_IMNET && d.kind != LIDF_DEC_IEF) return LIDF_ERR_UNSUPPORTED;
+  if (d.kind == LIDF_DEC_IEF && (!d.w_enc || !d.b_enc || d.n_iter < 1 || d.n_iter > 8)) return LIDF_ERR_ARG;
+  if (d.inp_dim != D) return LIDF_ERR_UNSUPPORTED;
+  return LIDF_OK;
+}
+
+int resolve_impl(int mlp_impl, int* out) {
+  int impl = mlp_impl == LIDF_MLP_AUTO ? LIDF_MLP_TC_BF16X3 : mlp_impl;
+  if (impl != LIDF_MLP_SIMT_FP32 && impl != LIDF_MLP_TC_BF16X3 && impl != LIDF_MLP_TC_BF16X1) return LIDF_ERR_ARG;
+  *out = impl;
+  return LIDF_OK;
+}
+
+// ---- SIMT engine: packed fp32 weights --------------------------------------------------------
+struct SimtPack {
+  // shared row-prep matrices
+  float* Wt_row; int KR; int Ntot;      // per-ray (or per refine-row) part of linear_1, [KR][Ntot]
+  float* bias_row;                      // [Ntot]
+  float* Wt_vox;                        // [128][Ntot] (LIDF only)
+  float* Wt_pe[2]; float* Wt2[2]; float* Wt3[2]; float* u[2];
+  int KP;
+};
+
+SimtPack carve_simt_pack(Bump& b, int n_dec, int KR, int KP, bool with_vox) {
+  SimtPack s;
+  s.KR = KR; s.KP = KP; s.Ntot = 256 * n_dec;
+  s.Wt_row = b.take<float>((size_t)KR * s.Ntot);
+  s.bias_row = b.take<float>(s.Ntot);
+  s.Wt_vox = with_vox ? b.take<float>((size_t)128 * s.Ntot) : nullptr;
+  for (int d = 0; d < 2; ++d) {
+    if (d < n_dec) {
+      s.Wt_pe[d] = b.take<float>((size_t)KP * 256);
+      s.Wt2[d] = b.take<float>(256 * 128);
+      s.Wt3[d] = b.take<float>(128 * 64);
+      s.u[d] = b.take<float>(256);
+    } else { s.Wt_pe[d] = s.Wt2[d] = s.Wt3[d] = s.u[d] = nullptr; }
+  }
+  return s;
+}
+
+int pack_wt(const float* w, int ldw, int col0, int K, int N, float* dst, int ldd, int k_off, int n_off, cudaStream_t st) {
+  if (K <= 0) return LIDF_OK;
+  k_pack_wt<<<(K * N + 255) / 256, 256, 0, st>>>(w, ldw, col0, K, N, dst, ldd, k_off, n_off);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+}  // namespace
+
+// =================================================================================================
+extern "C" int lidf_query_abi_version(void) { return LIDF_QUERY_ABI_VERSION; }
+extern "C" size_t lidf_query_struct_size(int which) {
+  return which == 0 ? sizeof(LidfDecoder) : which == 1 ? sizeof(LidfQueryParams) : which == 2 ? sizeof(LidfRefineParams) : 0;
+}
+
+extern "C" const char* lidf_query_error_string(int code) {
+  switch (code) {
+    case LIDF_OK: return "ok";
+    case LIDF_ERR_NULL: return "null pointer argument";
+    case LIDF_ERR_UNSUPPORTED: return "unsupported configuration (decoder dims / kinds outside the shipped YAML family)";
+    case LIDF_ERR_WORKSPACE: return "workspace too small";
+    case LIDF_ERR_CUDA: return "CUDA error (see lidf_query_last_cuda_error)";
+    case LIDF_ERR_ARG: return "invalid argument";
+    case LIDF_ERR_NO_SM100: return "tcgen05 engine needs an sm_100 device";
+    default: return "unknown error";
+  }
+}
+extern "C" const char* lidf_query_last_cuda_error(void) { return g_cuda_err; }
+extern "C" float lidf_query_last_mlp_ms(void) {
+  if (!g_ev_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_ev_mlp[1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev_mlp[0], g_ev_mlp[1]) != cudaSuccess) return -1.f;
+  return ms;
+}
+extern "C" int64_t lidf_query_launch_count(int reset) {
+  int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+// -------------------------------------------------------------------------------------------------
+extern "C" int lidf_roi_align_rays(const float* feat, int32_t B, int32_t H, int32_t W, const int64_t* img_ind,
+                                   const int64_t* bid, int64_t R, int32_t roi_inp_bbox, float* out, lidf_stream_t stream) {
+  if (!feat || !img_ind || !bid || !out) return LIDF_ERR_NULL;
+  if (R <= 0) return LIDF_OK;
+  k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, stream>>>(feat, B, H, W, img_ind, bid, R,
+                                                                                roi_inp_bbox / 2, out);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+extern "C" size_t lidf_ray_terminate_workspace_bytes(int64_t P, int64_t R) {
+  Bump b{nullptr, 0};
+  carve_csr(b, P, R);
+  return b.off + 256;
+}
+
+extern "C" int lidf_ray_terminate(const float* logit, const int64_t* pair_ray, const float* pair_pred_pos,
+                                  const float* label, int64_t P, int64_t R, float* soft, int64_t* max_pair_id,
+                                  float* pred_pos, void* ws, size_t ws_bytes, lidf_stream_t stream) {
+  if (!max_pair_id || !pred_pos || !ws) return LIDF_ERR_NULL;
+  if (P > 0 && (!logit || !pair_ray || !pair_pred_pos || !soft)) return LIDF_ERR_NULL;
+  if (P >= INT_MAX || R >= INT_MAX / 32) return LIDF_ERR_UNSUPPORTED;
+  if (ws_bytes < lidf_ray_terminate_workspace_bytes(P, R)) return LIDF_ERR_WORKSPACE;
+  if (R <= 0) return LIDF_OK;
+  Bump b{(char*)ws, 0};
+  CsrBufs c = carve_csr(b, P, R);
+  int rc = build_csr(c, pair_ray, P, R, stream);
+  if (rc) return rc;
+  k_ray_terminate<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(logit, pair_pred_pos, label, c.ray_start, c.perm,
+                                                                        P, R, soft, max_pair_id, pred_pos);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+namespace {
+
+struct QueryPlan {
+  int impl, pe_pos, pe_dir, D, KR, KP;
+  CsrBufs csr;
+  float* roi_feat; float* T; float* Av;
+  SimtPack sp;
+  TcBufs tc;
+  size_t bytes;
+};
+
+int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
+  int rc = resolve_impl(p->mlp_impl, &q->impl);
+  if (rc) return rc;
+  if (p->multires < 0 || p->multires > LIDF_MAX_MULTIRES || p->multires_views < 0 || p->multires_views > LIDF_MAX_MULTIRES)
+    return LIDF_ERR_UNSUPPORTED;
+  q->pe_pos = lidf_pe_dim(p->multires, p->pos_encode);
+  q->pe_dir = lidf_pe_dim(p->multires_views, p->pos_encode);
+  q->D = LIDF_VOX_DIM + LIDF_RGB_DIM + 2 * q->pe_pos + q->pe_dir;     // pipeline.py:64-65
+  q->KR = pad16(LIDF_RGB_DIM + q->pe_dir);
+  q->KP = pad16(2 * q->pe_pos);
+  Bump b{base, 0};
+  q->csr = carve_csr(b, p->P, p->R);
+  q->roi_feat = p->roi_feat_per_ray ? p->roi_feat_per_ray : b.take<float>((size_t)p->R * LIDF_RGB_DIM);
+  q->T = b.take<float>((size_t)p->R * 512);
+  if (q->impl == LIDF_MLP_SIMT_FP32) {
+    q->Av = b.take<float>((size_t)p->V * 512);
+    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, true);
+  } else {
+    if (q->KP > TC_KPE_MAX) return LIDF_ERR_UNSUPPORTED;
+    q->Av = nullptr;
+    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, false);   // row-prep matrices are shared with the SIMT engine
+    q->tc = carve_tc(b, p->V, 2);
+  }
+  q->bytes = b.off + 256;
+  return LIDF_OK;
+}
+
+}  // namespace
+
+extern "C" size_t lidf_query_workspace_bytes(const LidfQueryParams* p) {
+  if (!p) return 0;
+  QueryPlan q;
+  if (plan_query(p, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream) {
+  if (!p) return LIDF_ERR_NULL;
+  if (p->P < 0 || p->R < 0 || p->V < 0 || p->B <= 0 || p->H <= 0 || p->W <= 0) return LIDF_ERR_ARG;
+  if (p->P >= INT_MAX || p->R >= INT_MAX / 32 || p->V >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;
+  if (!p->max_pair_id || !p->pred_pos || !p->workspace) return LIDF_ERR_NULL;
+  if (p->R > 0 && (!p->full_rgb_feat || !p->miss_ray_dir || !p->miss_img_ind || !p->miss_bid)) return LIDF_ERR_NULL;
+  if (p->P > 0) {
+    if (!p->occ_voxel_feat || !p->voxel_bound || !p->pair_vox || !p->pair_ray) return LIDF_ERR_NULL;
+    if (!p->pair_dist && !p->dense_dist) return LIDF_ERR_NULL;
+    if (!p->pred_offset || !p->pred_prob_end || !p->pair_pred_pos || !p->pred_prob_end_softmax) return LIDF_ERR_NULL;
+  }
+  if (p->roi_inp_bbox < 0) return LIDF_ERR_ARG;
+  if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;   // pipeline.py:81-85
+  QueryPlan q;
+  int rc = plan_query(p, &q, (char*)p->workspace);
+  if (rc) return rc;
+  if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
+  if ((rc = check_decoder(p->prob_dec, q.D))) return rc;
+  cudaStream_t st = stream;
+  const int64_t P = p->P, R = p->R, V = p->V;
+  if (R == 0) return LIDF_OK;
+
+  // 1. regroup
+  if ((rc = build_csr(q.csr, p->pair_ray, P, R, st))) return rc;
+  // 2. ROIAlign per ray
+  if ((rc = lidf_roi_align_rays(p->full_rgb_feat, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox,
+                                q.roi_feat, stream))) return rc;
+  if (P > 0) {
+    // 3. weights
+    const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
+    SimtPack& sp = q.sp;
+    LIDF_CUDA(cudaMemsetAsync(sp.Wt_row, 0, sizeof(float) * (size_t)sp.KR * sp.Ntot, st));
+    for (int d = 0; d < 2; ++d) {
+      const LidfDecoder& dc = *decs[d];
+      const int ldw = q.D + (dc.kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
+      // per-ray rows: [rgb(128) | PE(dir)]
+      if ((rc = pack_wt(dc.w1, ldw, LIDF_VOX_DIM, LIDF_RGB_DIM, 256, sp.Wt_row, sp.Ntot, 0, 256 * d, st))) return rc;
+      if ((rc = pack_wt(dc.w1, ldw, LIDF_VOX_DIM + LIDF_RGB_DIM + 2 * q.pe_pos, q.pe_dir, 256, sp.Wt_row, sp.Ntot,
+                        LIDF_RGB_DIM, 256 * d, st))) return rc;
+      k_pack_bias1<<<1, 256, 0, st>>>(dc.w1, ldw, q.D, dc.b1, dc.w_enc, dc.b_enc, dc.kind == LIDF_DEC_IEF,
+                                      dc.init_offset, sp.bias_row + 256 * d, sp.u[d]);
+      LIDF_LAUNCH_CHECK();
+      if (q.impl == LIDF_MLP_SIMT_FP32) {
+        if ((rc = pack_wt(dc.w1, ldw, 0, LIDF_VOX_DIM, 256, sp.Wt_vox, sp.Ntot, 0, 256 * d, st))) return rc;
+        LIDF_CUDA(cudaMemsetAsync(sp.Wt_pe[d], 0, sizeof(float) * (size_t)sp.KP * 256, st));
+        if ((rc = pack_wt(dc.w1, ldw, LIDF_VOX_DIM + LIDF_RGB_DIM, 2 * q.pe_pos, 256, sp.Wt_pe[d], 256, 0, 0, st))) return rc;
+        if ((rc = pack_wt(dc.w2, 256, 0, 256, 128, sp.Wt2[d], 128, 0, 0, st))) return rc;
+        if ((rc = pack_wt(dc.w3, 128, 0, 128, 64, sp.Wt3[d], 64, 0, 0, st))) return rc;
+      }
+    }
+    // 4. row prep: per-ray term T[R][512] (both decoders), per-voxel term A_v[V][512] (SIMT engine)
+    {
+      RowPrepArgs a{};
+      a.featA = q.roi_feat; a.featB = nullptr; a.dirs = p->miss_ray_dir; a.rows = R;
+      a.multires_views = p->multires_views; a.pos_encode = p->pos_encode;
+      a.Wt = sp.Wt_row; a.Kpad = sp.KR; a.Ntot = sp.Ntot; a.bias = sp.bias_row; a.out = q.T;
+      const size_t smem = sizeof(float) * ((size_t)LIDF_SIMT_BM * a.Kpad + LIDF_KC * 128);
+      LIDF_CUDA(cudaFuncSetAttribute(k_rowprep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+      k_rowprep<<<dim3((unsigned)((R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem, st>>>(a);
+      LIDF_LAUNCH_CHECK();
+      if (q.impl == LIDF_MLP_SIMT_FP32 && V > 0) {
+        a.featA = p->occ_voxel_feat; a.dirs = nullptr; a.rows = V; a.Wt = sp.Wt_vox; a.Kpad = 128; a.bias = nullptr;
+        a.out = q.Av;
+        const size_t smem2 = sizeof(float) * ((size_t)LIDF_SIMT_BM * 128 + LIDF_KC * 128);
+        k_rowprep<<<dim3((unsigned)((V + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem2, st>>>(a);
+        LIDF_LAUNCH_CHECK();
+      }
+    }
+    // 5. decoders
+    if (q.impl == LIDF_MLP_SIMT_FP32) {
+      SimtMlpArgs a{};
+      a.rows = P; a.refine = 0; a.perm = q.csr.perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray;
+      a.pair_dist = p->pair_dist; a.dense_dist = p->dense_dist; a.R = R; a.ray_dir = p->miss_ray_dir;
+      a.voxel_bound = p->voxel_bound; a.rel = p->intersect_pos_rel; a.pos_encode = p->pos_encode;
+      a.multires = p->multires; a.KP = sp.KP; a.n_dec = 2;
+      float* outs[2] = {p->pred_offset, p->pred_prob_end};
+      for (int d = 0; d < 2; ++d) {
+        const LidfDecoder& dc = *decs[d];
+        SimtDecoder& s = a.dec[d];
+        s.kind = dc.kind; s.n_pass = dc.kind == LIDF_DEC_IEF ? dc.n_iter : 1; s.use_sigmoid = dc.use_sigmoid;
+        s.Wt_pe = sp.Wt_pe[d]; s.Wt2 = sp.Wt2[d]; s.b2 = dc.b2; s.Wt3 = sp.Wt3[d]; s.b3 = dc.b3; s.w4 = dc.w4; s.b4 = dc.b4;
+        s.u = dc.kind == LIDF_DEC_IEF ? sp.u[d] : nullptr; s.o0 = dc.init_offset;
+        s.addA = q.Av; s.ldA = 512; s.offA = 256 * d; s.addB = q.T; s.ldB = 512; s.offB = 256 * d; s.out = outs[d];
+      }
+      a.r0 = p->offset_range0; a.r1 = p->offset_range1; a.scale = (float)sqrt(3.0); a.scale2 = p->part_size;
+      a.pos_out = p->pair_pred_pos;
+      const size_t smem = simt_mlp_smem_bytes(sp.KP);
+      LIDF_CUDA(cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+      mlp_event(0, st);
+      k_mlp_simt<<<(unsigned)((P + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), LIDF_SIMT_THREADS, smem, st>>>(a);
+      mlp_event(1, st);
+      LIDF_LAUNCH_CHECK();
+    } else {
+      if ((rc = tc_query_forward(p, q.tc, q.csr.perm, q.T, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
+                                 sizeof(g_cuda_err), mlp_event))) return rc;
+    }
+  }
+  // 6. ray termination
+  k_ray_terminate<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(p->pred_prob_end, p->pair_pred_pos, p->pcl_label_float,
+                                                                     q.csr.ray_start, q.csr.perm, P, R,
+                                                                     p->pred_prob_end_softmax, p->max_pair_id, p->pred_pos);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+// -------------------------------------------------------------------------------------------------
+// RefineNet decoder tail (pipeline.py:1018-1029).  Per ray; every layer-1 input except PE(pos) is folded into the
+// row-prep GEMM: T'[r] = W1[:,0:128] vox_end[r] + W1[:,128:256] rgb_end[r] + W1[:,dir] PE(dir_r) + b1 (+ IEF const).
+// -------------------------------------------------------------------------------------------------
+namespace {
+struct RefinePlan { int impl, pe_pos, pe_dir, D, KR, KP; float* T; SimtPack sp; size_t bytes; };
+int plan_refine(const LidfRefineParams* p, RefinePlan* q, char* base) {
+  int rc = resolve_impl(p->mlp_impl, &q->impl);
+  if (rc) return rc;
+  if (p->multires < 0 || p->multires > LIDF_MAX_MULTIRES || p->multires_views < 0 || p->multires_views > LIDF_MAX_MULTIRES)
+    return LIDF_ERR_UNSUPPORTED;
+  q->pe_pos = lidf_pe_dim(p->multires, p->pos_encode);
+  q->pe_dir = lidf_pe_dim(p->multires_views, p->pos_encode);
+  q->D = LIDF_VOX_DIM + LIDF_RGB_DIM + q->pe_pos + q->pe_dir;          // pipeline.py:740-742
+  q->KR = pad16(LIDF_VOX_DIM + LIDF_RGB_DIM + q->pe_dir);
+  q->KP = pad16(q->pe_pos);
+  Bump b{base, 0};
+  q->T = b.take<float>((size_t)p->R * 256);
+  q->sp = carve_simt_pack(b, 1, q->KR, q->KP, false);
+  q->bytes = b.off + 256;
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_refine_workspace_bytes(const LidfRefineParams* p) {
+  if (!p) return 0;
+  RefinePlan q;
+  if (plan_refine(p, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stream) {
+  if (!p) return LIDF_ERR_NULL;
+  if (p->R < 0) return LIDF_ERR_ARG;
+  if (p->R >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;
+  if (p->R == 0) return LIDF_OK;
+  if (!p->pred_pos || !p->miss_ray_dir || !p->voxel_feat_end || !p->rgb_feat_end || !p->pred_pos_refine || !p->workspace)
+    return LIDF_ERR_NULL;
+  if (p->intersect_pos_rel && !p->end_voxel_center) return LIDF_ERR_NULL;
+  RefinePlan q;
+  int rc = plan_refine(p, &q, (char*)p->workspace);
+  if (rc) return rc;
+  if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
+  cudaStream_t st = stream;
+  const LidfDecoder& dc = p->offset_dec;
+  const int ldw = q.D + (dc.kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
+  SimtPack& sp = q.sp;
+  LIDF_CUDA(cudaMemsetAsync(sp.Wt_row, 0, sizeof(float) * (size_t)sp.KR * sp.Ntot, st));
+  if ((rc = pack_wt(dc.w1, ldw, 0, 256, 256, sp.Wt_row, 256, 0, 0, st))) return rc;                        // vox | rgb
+  if ((rc = pack_wt(dc.w1, ldw, 256 + q.pe_pos, q.pe_dir, 256, sp.Wt_row, 256, 256, 0, st))) return rc;    // PE(dir)
+  k_pack_bias1<<<1, 256, 0, st>>>(dc.w1, ldw, q.D, dc.b1, dc.w_enc, dc.b_enc, dc.kind == LIDF_DEC_IEF, dc.init_offset,
+                                  sp.bias_row, sp.u[0]);
+  LIDF_LAUNCH_CHECK();
+  LIDF_CUDA(cudaMemsetAsync(sp.Wt_pe[0], 0, sizeof(float) * (size_t)sp.KP * 256, st));
+  if ((rc = pack_wt(dc.w1, ldw, 256, q.pe_pos, 256, sp.Wt_pe[0], 256, 0, 0, st))) return rc;
+  if ((rc = pack_wt(dc.w2, 256, 0, 256, 128, sp.Wt2[0], 128, 0, 0, st))) return rc;
+  if ((rc = pack_wt(dc.w3, 128, 0, 128, 64, sp.Wt3[0], 64, 0, 0, st))) return rc;
+  {
+    RowPrepArgs a{};
+    a.featA = p->voxel_feat_end; a.featB = p->rgb_feat_end; a.dirs = p->miss_ray_dir; a.rows = p->R;
+    a.multires_views = p->multires_views; a.pos_encode = p->pos_encode;
+    a.Wt = sp.Wt_row; a.Kpad = sp.KR; a.Ntot = 256; a.bias = sp.bias_row; a.out = q.T;
+    const size_t smem = sizeof(float) * ((size_t)LIDF_SIMT_BM * a.Kpad + LIDF_KC * 128);
+    LIDF_CUDA(cudaFuncSetAttribute(k_rowprep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    k_rowprep<<<dim3((unsigned)((p->R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), 2), LIDF_SIMT_THREADS, smem, st>>>(a);
+    LIDF_LAUNCH_CHECK();
+  }
+  // The refine tail is ~1% of stage-1 work: it runs on the fp32 engine for every mlp_impl.
+  SimtMlpArgs a{};
+  a.rows = p->R; a.refine = 1; a.ray_dir = p->miss_ray_dir; a.pos_in = p->pred_pos; a.center_in = p->end_voxel_center;
+  a.rel = p->intersect_pos_rel; a.pos_encode = p->pos_encode; a.multires = p->multires; a.KP = sp.KP; a.n_dec = 1;
+  SimtDecoder& s = a.dec[0];
+  s.kind = dc.kind; s.n_pass = dc.kind == LIDF_DEC_IEF ? dc.n_iter : 1; s.use_sigmoid = dc.use_sigmoid;
+  s.Wt_pe = sp.Wt_pe[0]; s.Wt2 = sp.Wt2[0]; s.b2 = dc.b2; s.Wt3 = sp.Wt3[0]; s.b3 = dc.b3; s.w4 = dc.w4; s.b4 = dc.b4;
+  s.u = dc.kind == LIDF_DEC_IEF ? sp.u[0] : nullptr; s.o0 = dc.init_offset;
+  s.addA = nullptr; s.addB = q.T; s.ldB = 256; s.offB = 0; s.out = nullptr;
+  a.r0 = p->offset_range0; a.r1 = p->offset_range1; a.scale = 1.f; a.scale2 = 1.f; a.pos_out = p->pred_pos_refine;
+  const size_t smem = simt_mlp_smem_bytes(sp.KP);
+  LIDF_CUDA(cudaFuncSetAttribute(k_mlp_simt, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_mlp_simt<<<(unsigned)((p->R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), LIDF_SIMT_THREADS, smem, st>>>(a);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}

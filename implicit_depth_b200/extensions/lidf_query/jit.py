@@ -1,0 +1,341 @@
+"""``lidf_query`` extension loader -- same convention as the reference's native extensions.
+
+The reference loads its CUDA ops at import time as ``from extensions.ray_aabb.jit import ray_aabb`` and calls
+``ray_aabb.forward(...)`` (reference src/extensions/ray_aabb/jit.py:1-3, src/models/pipeline.py:18,277).
+This module does the same for the fused query op::
+
+    from extensions.lidf_query.jit import lidf_query
+    outs = lidf_query.forward(full_rgb_feat, occ_voxel_feat, ...)
+
+It binds the C ABI of ``include/lidf_query.h`` with ctypes (no torch types cross the boundary: device pointers,
+sizes and the current CUDA stream handle).  The library is built in-tree by ``implicit_depth_b200/build.py`` (nvcc,
+sm_100a).  There is NO fallback: if the library cannot be loaded, or the tensors are not CUDA tensors, the call
+raises -- exactly like the reference's ``CHECK_CUDA`` (ray_aabb_cuda.cpp:16-18).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+import os
+from typing import Dict, Optional, Sequence
+
+import torch
+
+from implicit_depth_b200 import build as _build
+
+MLP_IMPLS = {"auto": 0, "simt_fp32": 1, "tc_bf16x3": 2, "tc_bf16x1": 3}
+
+
+class _Decoder(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_iter", C.c_int32), ("inp_dim", C.c_int32), ("use_sigmoid", C.c_int32),
+                ("init_offset", C.c_float),
+                ("w1", C.c_void_p), ("b1", C.c_void_p), ("w2", C.c_void_p), ("b2", C.c_void_p),
+                ("w3", C.c_void_p), ("b3", C.c_void_p), ("w4", C.c_void_p), ("b4", C.c_void_p),
+                ("w_enc", C.c_void_p), ("b_enc", C.c_void_p)]
+
+
+class _QueryParams(C.Structure):
+    _fields_ = [("P", C.c_int64), ("R", C.c_int64), ("V", C.c_int64),
+                ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32),
+                ("full_rgb_feat", C.c_void_p), ("occ_voxel_feat", C.c_void_p),
+                ("miss_ray_dir", C.c_void_p), ("miss_img_ind", C.c_void_p), ("miss_bid", C.c_void_p),
+                ("voxel_bound", C.c_void_p), ("pair_vox", C.c_void_p), ("pair_ray", C.c_void_p),
+                ("pair_dist", C.c_void_p), ("dense_dist", C.c_void_p), ("pcl_label_float", C.c_void_p),
+                ("pos_encode", C.c_int32), ("multires", C.c_int32), ("multires_views", C.c_int32),
+                ("intersect_pos_rel", C.c_int32), ("roi_inp_bbox", C.c_int32),
+                ("offset_range0", C.c_float), ("offset_range1", C.c_float), ("part_size", C.c_float),
+                ("offset_dec", _Decoder), ("prob_dec", _Decoder), ("mlp_impl", C.c_int32),
+                ("pred_offset", C.c_void_p), ("pred_prob_end", C.c_void_p), ("pair_pred_pos", C.c_void_p),
+                ("pred_prob_end_softmax", C.c_void_p), ("max_pair_id", C.c_void_p), ("pred_pos", C.c_void_p),
+                ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+class _RefineParams(C.Structure):
+    _fields_ = [("R", C.c_int64), ("pred_pos", C.c_void_p), ("miss_ray_dir", C.c_void_p),
+                ("end_voxel_center", C.c_void_p), ("voxel_feat_end", C.c_void_p), ("rgb_feat_end", C.c_void_p),
+                ("pos_encode", C.c_int32), ("multires", C.c_int32), ("multires_views", C.c_int32),
+                ("intersect_pos_rel", C.c_int32), ("offset_range0", C.c_float), ("offset_range1", C.c_float),
+                ("offset_dec", _Decoder), ("mlp_impl", C.c_int32), ("pred_pos_refine", C.c_void_p),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+
+
+EXPORTED_SYMBOLS = [
+    "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
+    "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
+    "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
+    "lidf_query_last_mlp_ms",
+]
+
+
+def load_library(build_if_needed: bool = True) -> C.CDLL:
+    """dlopen csrc/liblidf_query.so (building it first when nvcc is available and it is missing/stale)."""
+    path = _build.LIB_PATH
+    if build_if_needed and _build.find_nvcc() is not None:
+        path = _build.build()
+    if not os.path.exists(path):
+        raise RuntimeError(f"{path} is missing and nvcc is not available to build it; lidf_query has no fallback path")
+    lib = C.CDLL(path)
+    lib.lidf_query_abi_version.restype = C.c_int
+    lib.lidf_query_error_string.restype = C.c_char_p
+    lib.lidf_query_error_string.argtypes = [C.c_int]
+    lib.lidf_query_last_cuda_error.restype = C.c_char_p
+    lib.lidf_query_workspace_bytes.restype = C.c_size_t
+    lib.lidf_query_workspace_bytes.argtypes = [C.POINTER(_QueryParams)]
+    lib.lidf_query_forward.restype = C.c_int
+    lib.lidf_query_forward.argtypes = [C.POINTER(_QueryParams), C.c_void_p]
+    lib.lidf_refine_workspace_bytes.restype = C.c_size_t
+    lib.lidf_refine_workspace_bytes.argtypes = [C.POINTER(_RefineParams)]
+    lib.lidf_refine_forward.restype = C.c_int
+    lib.lidf_refine_forward.argtypes = [C.POINTER(_RefineParams), C.c_void_p]
+    lib.lidf_roi_align_rays.restype = C.c_int
+    lib.lidf_roi_align_rays.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_int32, C.c_void_p, C.c_void_p]
+    lib.lidf_ray_terminate_workspace_bytes.restype = C.c_size_t
+    lib.lidf_ray_terminate_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.lidf_ray_terminate.restype = C.c_int
+    lib.lidf_ray_terminate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
+                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.lidf_query_last_mlp_ms.restype = C.c_float
+    lib.lidf_query_launch_count.restype = C.c_int64
+    lib.lidf_query_launch_count.argtypes = [C.c_int]
+    if lib.lidf_query_abi_version() != 1:
+        raise RuntimeError("liblidf_query.so ABI version mismatch")
+    lib.lidf_query_struct_size.restype = C.c_size_t
+    lib.lidf_query_struct_size.argtypes = [C.c_int]
+    for which, st in enumerate((_Decoder, _QueryParams, _RefineParams)):
+        if lib.lidf_query_struct_size(which) != C.sizeof(st):
+            raise RuntimeError(f"ctypes layout of {st.__name__} does not match the compiled library")
+    return lib
+
+
+def _chk(t: Optional[torch.Tensor], name: str, dtype, optional: bool = False):
+    """The reference's CHECK_INPUT (ray_aabb_cuda.cpp:16-18) plus a dtype check."""
+    if t is None:
+        if optional:
+            return 0
+        raise RuntimeError(f"{name} must not be None")
+    if not t.is_cuda:
+        raise RuntimeError(f"{name} must be a CUDA tensor")
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name} must be contiguous")
+    if t.dtype != dtype:
+        raise RuntimeError(f"{name} must be {dtype}, got {t.dtype}")
+    return t.data_ptr()
+
+
+def decoder_state(dec) -> Dict[str, torch.Tensor]:
+    """Accept an IMNet/IEF module (ours or the reference's) or a plain state-dict-like mapping."""
+    if isinstance(dec, dict):
+        return dec
+    return {k: v for k, v in dec.state_dict(keep_vars=True).items()}
+
+
+def _decoder_struct(sd: Dict[str, torch.Tensor], n_iter: int, use_sigmoid: bool, keep: list, name: str) -> _Decoder:
+    d = _Decoder()
+    is_ief = "offset_enc.weight" in sd
+    d.kind = 1 if is_ief else 0
+    d.n_iter = int(n_iter) if is_ief else 1
+    d.use_sigmoid = int(bool(use_sigmoid))
+    d.init_offset = 0.001                                  # IEF.init_offset, implicit_net.py:104
+    w1 = sd["linear_1.weight"]
+    if tuple(w1.shape[:1]) != (256,) or tuple(sd["linear_2.weight"].shape) != (128, 256) \
+            or tuple(sd["linear_3.weight"].shape) != (64, 128) or tuple(sd["linear_4.weight"].shape) != (1, 64):
+        raise RuntimeError(f"{name}: lidf_query supports imnet_gf=64, out_dim=1 decoders only (shipped YAMLs)")
+    d.inp_dim = int(w1.shape[1]) - (16 if is_ief else 0)
+    for field, key in (("w1", "linear_1.weight"), ("b1", "linear_1.bias"), ("w2", "linear_2.weight"),
+                       ("b2", "linear_2.bias"), ("w3", "linear_3.weight"), ("b3", "linear_3.bias"),
+                       ("w4", "linear_4.weight"), ("b4", "linear_4.bias")):
+        t = sd[key].detach()
+        keep.append(t)
+        setattr(d, field, _chk(t, f"{name}.{key}", torch.float32))
+    if is_ief:
+        for field, key in (("w_enc", "offset_enc.weight"), ("b_enc", "offset_enc.bias")):
+            t = sd[key].detach()
+            keep.append(t)
+            setattr(d, field, _chk(t, f"{name}.{key}", torch.float32))
+    return d
+
+
+class _LidfQuery:
+    """Object with a ``forward`` like the reference's pybind modules (ray_aabb.forward, pcl_aabb.forward)."""
+
+    def __init__(self):
+        self._lib = None
+
+    @property
+    def lib(self) -> C.CDLL:
+        if self._lib is None:
+            self._lib = load_library()
+        return self._lib
+
+    def _raise(self, rc: int, what: str):
+        if rc != 0:
+            msg = self.lib.lidf_query_error_string(rc).decode()
+            cu = self.lib.lidf_query_last_cuda_error().decode()
+            raise RuntimeError(f"{what} failed: {msg}" + (f" [{cu}]" if rc == -4 else ""))
+
+    def launch_count(self, reset: bool = False) -> int:
+        return int(self.lib.lidf_query_launch_count(1 if reset else 0))
+
+    def last_mlp_ms(self) -> float:
+        """Device time of the decoder kernel in the latest forward (CUDA events on the launching stream)."""
+        return float(self.lib.lidf_query_last_mlp_ms())
+
+    INPUT_KEYS = ("full_rgb_feat", "occ_voxel_feat", "miss_ray_dir", "miss_img_ind", "miss_bid", "voxel_bound",
+                  "occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist")
+    OUTPUT_KEYS = ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos")
+
+    def forward_host(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, out_host=None, **kw):
+        """Same call with HOST buffers (pinned for async copies): H2D of every input, the fused forward, D2H of every
+        output, then a stream synchronise.  Returns (out_host dict, h2d_bytes, d2h_bytes)."""
+        dev = torch.device(device)
+        ins = [host[k].to(dev, non_blocking=True) for k in self.INPUT_KEYS]
+        h2d = sum(host[k].numel() * host[k].element_size() for k in self.INPUT_KEYS)
+        out = self.forward(*ins, offset_dec, prob_dec, **kw)
+        if out_host is None:
+            out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.OUTPUT_KEYS}
+        d2h = 0
+        for k in self.OUTPUT_KEYS:
+            out_host[k].copy_(out[k], non_blocking=True)
+            d2h += out[k].numel() * out[k].element_size()
+        torch.cuda.current_stream(dev).synchronize()
+        return out_host, h2d, d2h
+
+    # ------------------------------------------------------------------ fused get_embedding + get_pred
+    def forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, *,
+                part_size: float, pos_encode: bool = True, multires: int = 8, multires_views: int = 4,
+                intersect_pos_type: str = "abs", roi_inp_bbox: int = 8, roi_out_bbox: int = 2,
+                n_iter: int = 2, use_sigmoid: bool = False, offset_range: Sequence[float] = (0.0, 1.0),
+                pcl_label_float: Optional[torch.Tensor] = None, mlp_impl: str = "auto",
+                want_roi_feat: bool = False) -> Dict[str, torch.Tensor]:
+        """Everything LIDF.get_embedding + LIDF.get_pred compute after the ResNet / PointNet producers
+        (reference src/models/pipeline.py:338-466).  ``dist`` is either the per-pair [P,2] enter/leave distances or
+        the reference's dense [V,R,2] tensor.  Returns the data_dict entries of pipeline.py:460-466 (+ pred_offset)."""
+        if roi_out_bbox != 2 or tuple(full_rgb_feat.shape[1:2]) != (32,) or occ_voxel_feat.shape[-1] != 128:
+            raise RuntimeError("lidf_query supports rgb_out=32, roi_out_bbox=2, pnet_out=128 only (shipped YAMLs)")
+        dev = full_rgb_feat.device
+        P = int(occ_vox_intersect_idx.shape[0]); R = int(miss_ray_dir.shape[0]); V = int(occ_voxel_feat.shape[0])
+        B, _, H, W = (int(s) for s in full_rgb_feat.shape)
+        keep: list = []
+        p = _QueryParams()
+        p.P, p.R, p.V, p.B, p.H, p.W = P, R, V, B, H, W
+        p.full_rgb_feat = _chk(full_rgb_feat, "full_rgb_feat", torch.float32)
+        p.occ_voxel_feat = _chk(occ_voxel_feat, "occ_voxel_feat", torch.float32)
+        p.miss_ray_dir = _chk(miss_ray_dir, "miss_ray_dir", torch.float32)
+        p.miss_img_ind = _chk(miss_img_ind, "miss_img_ind", torch.int64)
+        p.miss_bid = _chk(miss_bid, "miss_bid", torch.int64)
+        p.voxel_bound = _chk(voxel_bound, "voxel_bound", torch.float32)
+        p.pair_vox = _chk(occ_vox_intersect_idx, "occ_vox_intersect_idx", torch.int64)
+        p.pair_ray = _chk(miss_ray_intersect_idx, "miss_ray_intersect_idx", torch.int64)
+        if dist.dim() == 2:
+            if tuple(dist.shape) != (P, 2):
+                raise RuntimeError("per-pair dist must be [P,2]")
+            p.pair_dist = _chk(dist, "dist", torch.float32)
+        else:
+            if tuple(dist.shape) != (V, R, 2):
+                raise RuntimeError("dense dist must be [V,R,2]")
+            p.dense_dist = _chk(dist, "dist", torch.float32)
+        p.pcl_label_float = _chk(pcl_label_float, "pcl_label_float", torch.float32, optional=True)
+        p.pos_encode = int(bool(pos_encode)); p.multires = int(multires); p.multires_views = int(multires_views)
+        p.intersect_pos_rel = int(intersect_pos_type == "rel"); p.roi_inp_bbox = int(roi_inp_bbox)
+        p.offset_range0, p.offset_range1 = float(offset_range[0]), float(offset_range[1])
+        p.part_size = float(part_size)
+        p.offset_dec = _decoder_struct(decoder_state(offset_dec), n_iter, use_sigmoid, keep, "offset_dec")
+        p.prob_dec = _decoder_struct(decoder_state(prob_dec), n_iter, use_sigmoid, keep, "prob_dec")
+        p.mlp_impl = MLP_IMPLS[mlp_impl]
+        f32 = dict(dtype=torch.float32, device=dev)
+        out = dict(pred_offset=torch.empty(P, 1, **f32), pred_prob_end=torch.empty(P, 1, **f32),
+                   pair_pred_pos=torch.empty(P, 3, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
+                   max_pair_id=torch.empty(R, dtype=torch.int64, device=dev), pred_pos=torch.empty(R, 3, **f32))
+        if want_roi_feat:
+            out["roi_feat_per_ray"] = torch.empty(R, 128, **f32)
+            p.roi_feat_per_ray = out["roi_feat_per_ray"].data_ptr()
+        for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
+            setattr(p, k, out[k].data_ptr())
+        nbytes = int(self.lib.lidf_query_workspace_bytes(C.byref(p)))
+        if nbytes == 0:
+            raise RuntimeError("lidf_query: unsupported configuration (lidf_query_workspace_bytes returned 0)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = self.lib.lidf_query_forward(C.byref(p), C.c_void_p(stream))
+        self._raise(rc, "lidf_query_forward")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return out
+
+    # ------------------------------------------------------------------ RefineNet decoder tail
+    def refine_forward(self, pred_pos, miss_ray_dir, end_voxel_center, voxel_feat_end, rgb_feat_end, offset_dec, *,
+                       pos_encode: bool = True, multires: int = 8, multires_views: int = 4,
+                       intersect_pos_type: str = "abs", n_iter: int = 2, use_sigmoid: bool = False,
+                       offset_range: Sequence[float] = (-0.2, 0.2), mlp_impl: str = "auto") -> torch.Tensor:
+        """pipeline.py:1018-1029 for all rays at once."""
+        dev = pred_pos.device
+        R = int(pred_pos.shape[0])
+        keep: list = []
+        p = _RefineParams()
+        p.R = R
+        p.pred_pos = _chk(pred_pos, "pred_pos", torch.float32)
+        p.miss_ray_dir = _chk(miss_ray_dir, "miss_ray_dir", torch.float32)
+        p.end_voxel_center = _chk(end_voxel_center, "end_voxel_center", torch.float32, optional=True)
+        p.voxel_feat_end = _chk(voxel_feat_end, "voxel_feat_end", torch.float32)
+        p.rgb_feat_end = _chk(rgb_feat_end, "rgb_feat_end", torch.float32)
+        p.pos_encode = int(bool(pos_encode)); p.multires = int(multires); p.multires_views = int(multires_views)
+        p.intersect_pos_rel = int(intersect_pos_type == "rel")
+        p.offset_range0, p.offset_range1 = float(offset_range[0]), float(offset_range[1])
+        p.offset_dec = _decoder_struct(decoder_state(offset_dec), n_iter, use_sigmoid, keep, "offset_dec")
+        p.mlp_impl = MLP_IMPLS[mlp_impl]
+        out = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        p.pred_pos_refine = out.data_ptr()
+        nbytes = int(self.lib.lidf_refine_workspace_bytes(C.byref(p)))
+        if nbytes == 0:
+            raise RuntimeError("lidf_refine: unsupported configuration")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
+        with torch.cuda.device(dev):
+            stream = torch.cuda.current_stream(dev).cuda_stream
+            rc = self.lib.lidf_refine_forward(C.byref(p), C.c_void_p(stream))
+        self._raise(rc, "lidf_refine_forward")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return out
+
+    # ------------------------------------------------------------------ stand-alone pieces
+    def roi_align_rays(self, full_rgb_feat, miss_img_ind, miss_bid, roi_inp_bbox: int = 8) -> torch.Tensor:
+        dev = full_rgb_feat.device
+        B, Cc, H, W = (int(s) for s in full_rgb_feat.shape)
+        if Cc != 32:
+            raise RuntimeError("rgb_out must be 32")
+        R = int(miss_bid.shape[0])
+        out = torch.empty(R, 128, dtype=torch.float32, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.lidf_roi_align_rays(_chk(full_rgb_feat, "full_rgb_feat", torch.float32), B, H, W,
+                                              _chk(miss_img_ind, "miss_img_ind", torch.int64),
+                                              _chk(miss_bid, "miss_bid", torch.int64), R, int(roi_inp_bbox),
+                                              out.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_roi_align_rays")
+        return out
+
+    def ray_terminate(self, pred_prob_end, miss_ray_intersect_idx, pair_pred_pos, R: int,
+                      pcl_label_float: Optional[torch.Tensor] = None):
+        dev = pair_pred_pos.device
+        P = int(miss_ray_intersect_idx.shape[0])
+        logit = pred_prob_end.reshape(-1)
+        soft = torch.empty(P, dtype=torch.float32, device=dev)
+        arg = torch.empty(R, dtype=torch.int64, device=dev)
+        pos = torch.empty(R, 3, dtype=torch.float32, device=dev)
+        nbytes = int(self.lib.lidf_ray_terminate_workspace_bytes(P, R))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.lidf_ray_terminate(_chk(logit, "pred_prob_end", torch.float32),
+                                             _chk(miss_ray_intersect_idx, "miss_ray_intersect_idx", torch.int64),
+                                             _chk(pair_pred_pos, "pair_pred_pos", torch.float32),
+                                             _chk(pcl_label_float, "pcl_label_float", torch.float32, optional=True),
+                                             P, R, soft.data_ptr(), arg.data_ptr(), pos.data_ptr(), ws.data_ptr(), nbytes,
+                                             C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_ray_terminate")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return soft, arg, pos
+
+
+lidf_query = _LidfQuery()

@@ -1,0 +1,253 @@
+"""Host-side mirror of the hot-path part of the reference's ``models.pipeline`` (reference src/models/pipeline.py).
+
+Only the per-query-point decoder path is re-implemented: ``LIDF.get_embedding`` (pipeline.py:338-425),
+``LIDF.get_pred`` (:427-466) and the decoder tail of ``RefineNet.get_pred_refine`` (:1018-1029).  Everything
+else in the reference pipeline (data prep, voxelisation, ray generation, ray_aabb, GT, losses, trainers) is out of
+scope and is meant to keep running from the reference tree; INTEGRATION.md shows the two-method override.
+
+``LIDFQueryMixin`` carries the two replacement methods with the reference's exact names, arguments and ``data_dict``
+contract, so it can be mixed into the reference class::
+
+    class LIDF(LIDFQueryMixin, reference_pipeline.LIDF): pass
+
+``LIDF`` / ``RefineNet`` below are stand-alone holders of the same sub-module attributes (``embed_fn``,
+``embeddirs_fn``, ``offset_dec``, ``prob_dec``, ``resnet_model``, ``pnet_model``) for use without the reference tree
+(tests, bench); the two producers are injected, they are not part of this path.
+
+Inference (``torch.no_grad`` / eval) runs the fused sm_100a kernel through the C ABI -- there is no CPU or eager
+fallback for it.  When autograd is recording (training), ``get_pred`` evaluates the same maths with differentiable
+torch ops on the decoder modules, because the native backward does not exist yet ("out of scope").
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+from implicit_depth_b200.models import implicit_net as im_net
+
+
+def _multires_of(fn, default):
+    return getattr(fn, "multires", default)
+
+
+class LIDFQueryMixin:
+    """Replacement ``get_embedding`` / ``get_pred`` (reference pipeline.py:338-466).
+
+    Reads from ``self``: ``opt.model.{pos_encode, multires, multires_views, intersect_pos_type, roi_inp_bbox,
+    roi_out_bbox, n_iter, use_sigmoid, maxpool_label_epo, scatter_type, pnet_pos_type}``, ``opt.grid.offset_range``,
+    ``resnet_model``, ``pnet_model``, ``offset_dec``, ``prob_dec`` -- the same attributes the reference uses.
+    """
+
+    mlp_impl = "auto"   # "auto" | "tc_bf16x3" | "simt_fp32" | "tc_bf16x1" (see include/lidf_query.h)
+
+    def get_embedding(self, data_dict):
+        """Runs the two upstream producers exactly where the reference does (pipeline.py:370, :400-407) and stores
+        their outputs; the per-pair gathers / PE / ROIAlign of the reference happen inside the fused kernel."""
+        data_dict['full_rgb_feat'] = self.resnet_model(data_dict['rgb_img'])
+        valid_v_rgb = data_dict['valid_rgb'][data_dict['valid_v_pid']]
+        if self.opt.model.pnet_pos_type == 'rel':
+            pnet_inp = torch.cat((data_dict['valid_v_rel_coord'], valid_v_rgb), -1)
+        else:
+            raise NotImplementedError('Does not support Pnet pos type: {}'.format(self.opt.model.pnet_pos_type))
+        data_dict['occ_voxel_feat'] = self.pnet_model(inp_feat=pnet_inp, vox2point_idx=data_dict['revidx'])
+
+    def _query_kwargs(self, data_dict):
+        m = self.opt.model
+        return dict(part_size=float(data_dict['part_size']), pos_encode=bool(m.pos_encode), multires=int(m.multires),
+                    multires_views=int(m.multires_views), intersect_pos_type=str(m.intersect_pos_type),
+                    roi_inp_bbox=int(m.roi_inp_bbox), roi_out_bbox=int(m.roi_out_bbox), n_iter=int(m.n_iter),
+                    use_sigmoid=bool(m.use_sigmoid), offset_range=tuple(float(v) for v in self.opt.grid.offset_range))
+
+    def get_pred(self, data_dict, exp_type, epoch):
+        if self.opt.model.scatter_type != 'Maxpool':
+            raise NotImplementedError('Does not support Scatter Type: {}'.format(self.opt.model.scatter_type))
+        use_label = exp_type == 'train' and epoch < self.opt.model.maxpool_label_epo       # pipeline.py:444
+        needs_grad = torch.is_grad_enabled() and (
+            data_dict['full_rgb_feat'].requires_grad or data_dict['occ_voxel_feat'].requires_grad
+            or any(p.requires_grad for p in self.offset_dec.parameters())
+            or any(p.requires_grad for p in self.prob_dec.parameters()))
+        if needs_grad:
+            return self._get_pred_autograd(data_dict, use_label)
+        dist = data_dict['dist'] if 'dist' in data_dict else data_dict['intersect_dist']
+        out = lidf_query.forward(
+            data_dict['full_rgb_feat'].float().contiguous(), data_dict['occ_voxel_feat'].float().contiguous(),
+            data_dict['miss_ray_dir'].contiguous(), data_dict['miss_img_ind'].long().contiguous(),
+            data_dict['miss_bid'].long().contiguous(), data_dict['voxel_bound'].contiguous(),
+            data_dict['occ_vox_intersect_idx'].contiguous(), data_dict['miss_ray_intersect_idx'].contiguous(),
+            dist.contiguous(), self.offset_dec, self.prob_dec,
+            pcl_label_float=data_dict['pcl_label_float'].contiguous() if use_label else None,
+            mlp_impl=self.mlp_impl, want_roi_feat=True, **self._query_kwargs(data_dict))
+        assert out['pred_pos'].shape[0] == data_dict['total_miss_sample_num']
+        data_dict.update({
+            'pair_pred_pos': out['pair_pred_pos'],
+            'max_pair_id': out['max_pair_id'],
+            'pred_prob_end': out['pred_prob_end'],
+            'pred_prob_end_softmax': out['pred_prob_end_softmax'],
+            'pred_pos': out['pred_pos'],
+            'pred_offset': out['pred_offset'],
+            'roi_feat_per_ray': out['roi_feat_per_ray'],
+        })
+
+    # -- training: same maths with differentiable torch ops (no native backward yet) -----------------------------
+    def _get_pred_autograd(self, data_dict, use_label):
+        import torchvision.ops as tv_ops
+        m = self.opt.model
+        vox, ray = data_dict['occ_vox_intersect_idx'], data_dict['miss_ray_intersect_idx']
+        dist = data_dict['dist'][vox, ray] if 'dist' in data_dict else data_dict['intersect_dist']
+        dirs = data_dict['miss_ray_dir'][ray]
+        enter_pos, leave_pos = dirs * dist[:, 0:1], dirs * dist[:, 1:2]
+        if m.intersect_pos_type == 'rel':
+            vb = data_dict['voxel_bound'][vox]
+            c = (vb[:, :3] + vb[:, 3:]) / 2.
+            inp_enter, inp_leave = enter_pos - c, leave_pos - c
+        else:
+            inp_enter, inp_leave = enter_pos, leave_pos
+        feat = data_dict['full_rgb_feat']
+        h, w = feat.shape[2], feat.shape[3]
+        pix, half = data_dict['miss_img_ind'], m.roi_inp_bbox // 2
+        ul = torch.stack(((pix[:, 0] - half).clamp(0, w - 1), (pix[:, 1] - half).clamp(0, h - 1)), -1)
+        br = torch.stack(((pix[:, 0] + half).clamp(0, w - 1), (pix[:, 1] + half).clamp(0, h - 1)), -1)
+        boxes = torch.cat((data_dict['miss_bid'].unsqueeze(-1), ul, br), -1).float()
+        roi = tv_ops.roi_align(feat, boxes, output_size=m.roi_out_bbox, spatial_scale=1.0, aligned=True)
+        roi = roi.reshape(roi.shape[0], -1)                 # once per ray, gathered per pair below
+        inp_embed = torch.cat((data_dict['occ_voxel_feat'][vox], roi[ray], self.embed_fn(inp_enter),
+                               self.embed_fn(inp_leave), self.embeddirs_fn(dirs)), -1)
+        pred_offset = self.offset_dec(inp_embed)
+        pred_prob_end = self.prob_dec(inp_embed)
+        r0, r1 = self.opt.grid.offset_range
+        scaled = (pred_offset * (r1 - r0) + r0) * np.sqrt(3) * data_dict['part_size']
+        pair_pred_pos = enter_pos + scaled * dirs
+        R = data_dict['total_miss_sample_num']
+        with torch.no_grad():                               # pipeline.py:442 detaches before the softmax
+            soft, max_pair_id, _ = lidf_query.ray_terminate(
+                pred_prob_end.detach().contiguous(), ray.contiguous(), pair_pred_pos.detach().contiguous(), R,
+                data_dict['pcl_label_float'].contiguous() if use_label else None) if pred_prob_end.is_cuda \
+                else _ray_terminate_torch(pred_prob_end.detach()[:, 0], ray, R,
+                                          data_dict['pcl_label_float'] if use_label else None)
+        dummy = torch.zeros([1, 3], dtype=pair_pred_pos.dtype, device=pair_pred_pos.device)
+        pred_pos = torch.cat((pair_pred_pos, dummy), 0)[max_pair_id]
+        data_dict.update({'pair_pred_pos': pair_pred_pos, 'max_pair_id': max_pair_id, 'pred_prob_end': pred_prob_end,
+                          'pred_prob_end_softmax': soft, 'pred_pos': pred_pos, 'pred_offset': pred_offset,
+                          'roi_feat_per_ray': roi.detach()})
+
+
+def _ray_terminate_torch(logit, ray, R, label=None):
+    """CPU-side segment softmax / arg-max (first max wins, empty ray -> P) used only by the autograd path on CPU."""
+    P = logit.shape[0]
+    mx = torch.full((R,), -float('inf'), dtype=logit.dtype).scatter_reduce(0, ray, logit, 'amax')
+    e = (logit - mx[ray]).exp()
+    soft = e / (torch.zeros(R, dtype=logit.dtype).index_add_(0, ray, e) + 1e-12)[ray]
+    key = label if label is not None else soft
+    kmx = torch.full((R,), -float('inf'), dtype=key.dtype).scatter_reduce(0, ray, key, 'amax')
+    pos = torch.arange(P)
+    arg = torch.full((R,), P, dtype=torch.long).scatter_reduce(0, ray, torch.where(key == kmx[ray], pos, P), 'amin')
+    return soft, arg, None
+
+
+class LIDF(LIDFQueryMixin, nn.Module):
+    """Stand-alone holder with the reference's attribute names (pipeline.py:39-89); producers are injected."""
+
+    def __init__(self, opt, device, resnet_model=None, pnet_model=None):
+        super().__init__()
+        self.opt = opt
+        self.device = device
+        m = opt.model
+        if m.pos_encode:
+            self.embed_fn, embed_ch = im_net.get_embedder(m.multires)
+            self.embeddirs_fn, embeddirs_ch = im_net.get_embedder(m.multires_views)
+        else:
+            self.embed_fn, embed_ch = im_net.get_embedder(m.multires, i=-1)
+            self.embeddirs_fn, embeddirs_ch = im_net.get_embedder(m.multires_views, i=-1)
+        self.resnet_model = resnet_model
+        self.pnet_model = pnet_model
+        dec_inp_dim = m.pnet_out + m.rgb_out * (m.roi_out_bbox ** 2) + 2 * embed_ch + embeddirs_ch   # pipeline.py:64-65
+        if m.offdec_type == 'IMNET':
+            self.offset_dec = im_net.IMNet(inp_dim=dec_inp_dim, out_dim=1, gf_dim=m.imnet_gf,
+                                           use_sigmoid=m.use_sigmoid).to(device)
+        elif m.offdec_type == 'IEF':
+            self.offset_dec = im_net.IEF(device, inp_dim=dec_inp_dim, out_dim=1, gf_dim=m.imnet_gf, n_iter=m.n_iter,
+                                         use_sigmoid=m.use_sigmoid).to(device)
+        else:
+            raise NotImplementedError('Does not support Offset Decoder Type: {}'.format(m.offdec_type))
+        if m.probdec_type == 'IMNET':
+            self.prob_dec = im_net.IMNet(inp_dim=dec_inp_dim, out_dim=1, gf_dim=m.imnet_gf,
+                                         use_sigmoid=m.use_sigmoid).to(device)
+        else:
+            raise NotImplementedError('Does not support Prob Decoder Type: {}'.format(m.probdec_type))
+
+    def forward(self, data_dict, exp_type='test', epoch=0):
+        """Hot-path segment of the reference forward (pipeline.py:706-708): get_embedding then get_pred."""
+        self.get_embedding(data_dict)
+        self.get_pred(data_dict, exp_type, epoch)
+        return data_dict
+
+
+class RefineDecoderMixin:
+    """Decoder tail of ``RefineNet.get_pred_refine`` (reference pipeline.py:1018-1029) as one fused call."""
+
+    mlp_impl = "auto"
+
+    def refine_decoder_tail(self, data_dict, pred_pos, end_voxel_id, occ_voxel_feat, rgb_feat_per_ray):
+        r = self.opt.refine
+        center = None
+        if r.intersect_pos_type == 'rel':
+            vb = data_dict['voxel_bound'][end_voxel_id]
+            center = ((vb[:, :3] + vb[:, 3:]) / 2.).contiguous()
+        return lidf_query.refine_forward(
+            pred_pos.contiguous(), data_dict['miss_ray_dir'].contiguous(), center,
+            occ_voxel_feat[end_voxel_id].contiguous(), rgb_feat_per_ray.contiguous(), self.offset_dec,
+            pos_encode=bool(r.pos_encode), multires=int(r.multires), multires_views=int(r.multires_views),
+            intersect_pos_type=str(r.intersect_pos_type), n_iter=int(r.n_iter), use_sigmoid=bool(r.use_sigmoid),
+            offset_range=tuple(float(v) for v in r.offset_range), mlp_impl=self.mlp_impl)
+
+
+class RefineNet(RefineDecoderMixin, nn.Module):
+    """Stand-alone holder of RefineNet.offset_dec (pipeline.py:722-758)."""
+
+    def __init__(self, opt, device, pnet_model=None):
+        super().__init__()
+        self.opt = opt
+        self.device = device
+        r, m = opt.refine, opt.model
+        if r.pos_encode:
+            self.embed_fn, embed_ch = im_net.get_embedder(r.multires)
+            self.embeddirs_fn, embeddirs_ch = im_net.get_embedder(r.multires_views)
+        else:
+            self.embed_fn, embed_ch = im_net.get_embedder(r.multires, i=-1)
+            self.embeddirs_fn, embeddirs_ch = im_net.get_embedder(r.multires_views, i=-1)
+        self.pnet_model = pnet_model
+        dec_inp_dim = r.pnet_out + embed_ch + embeddirs_ch + m.rgb_out * (m.roi_out_bbox ** 2)   # pipeline.py:740-742
+        if r.offdec_type == 'IMNET':
+            self.offset_dec = im_net.IMNet(inp_dim=dec_inp_dim, out_dim=1, gf_dim=r.imnet_gf,
+                                           use_sigmoid=r.use_sigmoid).to(device)
+        elif r.offdec_type == 'IEF':
+            self.offset_dec = im_net.IEF(device, inp_dim=dec_inp_dim, out_dim=1, gf_dim=r.imnet_gf, n_iter=r.n_iter,
+                                         use_sigmoid=r.use_sigmoid).to(device)
+        else:
+            raise NotImplementedError('Does not support Offset Decoder Type: {}'.format(r.offdec_type))
+
+
+class _NS:
+    """Tiny attribute namespace standing in for the reference's ``Params`` (src/opt.py) in tests / bench."""
+
+    def __init__(self, **kw):
+        self.__dict__.update(kw)
+
+
+def default_opt(**over):
+    """opt.model / opt.grid / opt.refine with the values of the shipped YAMLs (train_lidf.yaml, train_refine.yaml)."""
+    model = dict(pos_encode=True, multires=8, multires_views=4, intersect_pos_type='abs', rgb_in=3, rgb_out=32,
+                 roi_inp_bbox=8, roi_out_bbox=2, pnet_in=6, pnet_out=128, pnet_gf=32, pnet_pos_type='rel',
+                 offdec_type='IEF', n_iter=2, probdec_type='IMNET', imnet_gf=64, scatter_type='Maxpool',
+                 use_sigmoid=False, maxpool_label_epo=6)
+    refine = dict(pos_encode=True, multires=8, multires_views=4, intersect_pos_type='abs', pnet_out=128,
+                  offdec_type='IEF', n_iter=2, imnet_gf=64, use_sigmoid=False, offset_range=[-0.2, 0.2], forward_times=2)
+    grid = dict(res=8, offset_range=[0., 1.])
+    for k, v in over.items():
+        sect, key = k.split('.')
+        {'model': model, 'refine': refine, 'grid': grid}[sect][key] = v
+    return _NS(model=_NS(**model), refine=_NS(**refine), grid=_NS(**grid), gpu_id=0)

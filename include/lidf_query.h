@@ -1,0 +1,170 @@
+/* lidf_query.h -- C ABI of the B200-native LIDF per-query-point decoder ("lidf_query").
+ *
+ * This is the drop-in boundary for ONE hot path of NVlabs/implicit_depth: everything
+ * LIDF.get_embedding + LIDF.get_pred do after the ResNet / PointNet feature producers have run
+ * (reference src/models/pipeline.py:338-466), plus the RefineNet decoder tail
+ * (src/models/pipeline.py:1018-1029).  The reference has no native implementation of this path --
+ * it is a chain of stock PyTorch / torchvision / torch_scatter ops -- so there is no existing FFI to
+ * mirror symbol-for-symbol.  The entry points below follow the conventions of the reference's own
+ * native extensions (src/extensions/ray_aabb/ray_aabb_cuda.cpp:20-37,
+ * src/extensions/pcl_aabb/pcl_aabb_cuda.cpp:20-37): forward-only, inputs borrowed and read-only,
+ * contiguous row-major device arrays, int/float scalars by value; outputs are written into
+ * caller-owned device buffers (the Python wrapper allocates them with torch, like the reference's
+ * torch::zeros inside ray_aabb_cuda_forward).  Errors come back as negative codes (no exceptions
+ * cross the C ABI); the wrapper raises RuntimeError, matching TORCH_CHECK.
+ *
+ * Plain C: pointers, sizes and a stream handle.  No torch types.  All pointers are DEVICE pointers
+ * unless a name ends in _host.  All float arrays are fp32, index arrays int64 (what torch.nonzero
+ * hands the reference, pipeline.py:283-285).
+ */
+#ifndef LIDF_QUERY_H_
+#define LIDF_QUERY_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LIDF_QUERY_ABI_VERSION 1
+
+/* fixed by the shipped YAMLs (train_lidf.yaml:36-57): rgb_out 32 x roi_out_bbox 2^2, pnet_out 128, imnet_gf 64 */
+#define LIDF_RGB_CH 32
+#define LIDF_ROI_OUT 2
+#define LIDF_RGB_DIM 128
+#define LIDF_VOX_DIM 128
+#define LIDF_H1 256
+#define LIDF_H2 128
+#define LIDF_H3 64
+#define LIDF_IEF_ENC 16
+
+typedef struct CUstream_st* lidf_stream_t; /* == cudaStream_t */
+
+enum { LIDF_OK = 0, LIDF_ERR_NULL = -1, LIDF_ERR_UNSUPPORTED = -2, LIDF_ERR_WORKSPACE = -3,
+       LIDF_ERR_CUDA = -4, LIDF_ERR_ARG = -5, LIDF_ERR_NO_SM100 = -6 };
+
+enum { LIDF_DEC_IMNET = 0, LIDF_DEC_IEF = 1 };
+
+/* which MLP engine runs the decoders */
+enum { LIDF_MLP_AUTO = 0,      /* tcgen05 bf16x3 (split-precision, ~1e-5 rel.) on sm_100          */
+       LIDF_MLP_SIMT_FP32 = 1, /* fp32 FFMA kernel: bit-level close to the reference, slow       */
+       LIDF_MLP_TC_BF16X3 = 2, /* tcgen05, 3 bf16 products per MAC (hi*hi + hi*lo + lo*hi)        */
+       LIDF_MLP_TC_BF16X1 = 3  /* tcgen05, 1 bf16 product per MAC: fast, ~3e-3 rel. -- NOT parity  */ };
+
+/* One decoder = reference IMNet (src/models/implicit_net.py:60-98) or IEF (:100-152).
+ * Weights are the PyTorch nn.Linear tensors as they sit in the state_dict: weight [out,in] row-major. */
+typedef struct LidfDecoder {
+  int32_t kind;            /* LIDF_DEC_IMNET | LIDF_DEC_IEF */
+  int32_t n_iter;          /* IEF iterations (implicit_net.py:133); ignored for IMNet */
+  int32_t inp_dim;         /* D (385 for LIDF, 334 for RefineNet); linear_1.weight is [256, D (+16 if IEF)] */
+  int32_t use_sigmoid;     /* implicit_net.py:93-96 */
+  float init_offset;       /* IEF.init_offset = 0.001 (implicit_net.py:104) */
+  const float* w1; const float* b1;   /* linear_1 */
+  const float* w2; const float* b2;   /* linear_2 [128,256] */
+  const float* w3; const float* b3;   /* linear_3 [64,128] */
+  const float* w4; const float* b4;   /* linear_4 [1,64] */
+  const float* w_enc; const float* b_enc; /* IEF offset_enc [16,1],[16]; NULL for IMNet */
+} LidfDecoder;
+
+/* LIDF.get_embedding + LIDF.get_pred (pipeline.py:338-466) */
+typedef struct LidfQueryParams {
+  int64_t P;               /* ray-voxel intersection pairs (query points) */
+  int64_t R;               /* miss rays  (total_miss_sample_num) */
+  int64_t V;               /* occupied voxels in the batch */
+  int32_t B, H, W;         /* feature-map batch / height / width */
+  /* producers' outputs (not on the path): */
+  const float* full_rgb_feat;   /* [B,32,H,W]  resnet_model(rgb_img), pipeline.py:370 */
+  const float* occ_voxel_feat;  /* [V,128]     pnet_model(...),       pipeline.py:407 */
+  /* rays: */
+  const float* miss_ray_dir;    /* [R,3] unit */
+  const int64_t* miss_img_ind;  /* [R,2] (x,y) */
+  const int64_t* miss_bid;      /* [R] image id */
+  const float* voxel_bound;     /* [V,6] min xyz, max xyz */
+  /* pair list (occ_vox_intersect_idx, miss_ray_intersect_idx), any order; the reference's is voxel-major: */
+  const int64_t* pair_vox;      /* [P] */
+  const int64_t* pair_ray;      /* [P] */
+  /* enter/leave distance per pair: EITHER pair_dist [P,2] OR the reference's dense dist [V,R,2]
+   * (pipeline.py:345 looks it up as dist[vox,ray]) */
+  const float* pair_dist;
+  const float* dense_dist;
+  const float* pcl_label_float; /* [P] or NULL: non-NULL selects the GT-label arg-max branch, pipeline.py:444-446 */
+  /* opt.model.* / opt.grid.* scalars read on the path: */
+  int32_t pos_encode;           /* model.pos_encode  */
+  int32_t multires;             /* model.multires (8)       */
+  int32_t multires_views;       /* model.multires_views (4) */
+  int32_t intersect_pos_rel;    /* model.intersect_pos_type == 'rel' */
+  int32_t roi_inp_bbox;         /* model.roi_inp_bbox (8); roi_out_bbox is fixed at 2 */
+  float offset_range0, offset_range1;   /* grid.offset_range */
+  float part_size;              /* data_dict['part_size'] (pipeline.py:170) */
+  LidfDecoder offset_dec;       /* IMNet or IEF */
+  LidfDecoder prob_dec;         /* IMNet */
+  int32_t mlp_impl;             /* LIDF_MLP_* */
+  /* outputs (data_dict entries, pipeline.py:460-466): */
+  float* pred_offset;           /* [P]   offset_dec output before scaling (pipeline.py:434) */
+  float* pred_prob_end;         /* [P]   prob_dec output (logit after the leaky clamp / sigmoid) */
+  float* pair_pred_pos;         /* [P,3] */
+  float* pred_prob_end_softmax; /* [P]   */
+  int64_t* max_pair_id;         /* [R]   arg-max pair per ray; P for rays without a pair */
+  float* pred_pos;              /* [R,3] */
+  float* roi_feat_per_ray;      /* [R,128] optional (NULL to skip): ROIAlign feature, reused by RefineNet (pipeline.py:964) */
+  void* workspace; size_t workspace_bytes;   /* >= lidf_query_workspace_bytes() */
+} LidfQueryParams;
+
+/* RefineNet.get_pred_refine decoder tail (pipeline.py:1018-1029): per RAY
+ * x = [voxel_feat_end | rgb_feat_end | PE(pos [- centre]) | PE(dir)] -> offset_dec -> pred_pos + (o*(r1-r0)+r0)*dir */
+typedef struct LidfRefineParams {
+  int64_t R;
+  const float* pred_pos;        /* [R,3] */
+  const float* miss_ray_dir;    /* [R,3] */
+  const float* end_voxel_center;/* [R,3] (only read when intersect_pos_rel) */
+  const float* voxel_feat_end;  /* [R,128] occ_voxel_feat[end_voxel_id] */
+  const float* rgb_feat_end;    /* [R,128] ROIAlign feature per ray */
+  int32_t pos_encode, multires, multires_views, intersect_pos_rel;
+  float offset_range0, offset_range1;   /* refine.offset_range */
+  LidfDecoder offset_dec;
+  int32_t mlp_impl;
+  float* pred_pos_refine;       /* [R,3] */
+  void* workspace; size_t workspace_bytes;
+} LidfRefineParams;
+
+int lidf_query_abi_version(void);
+/* sizeof() of the parameter structs as compiled (0: LidfDecoder, 1: LidfQueryParams, 2: LidfRefineParams) so an FFI
+ * binding can verify its own struct layout */
+size_t lidf_query_struct_size(int which);
+const char* lidf_query_error_string(int code);
+/* last CUDA error text recorded by this library on the calling thread ("" if none) */
+const char* lidf_query_last_cuda_error(void);
+
+size_t lidf_query_workspace_bytes(const LidfQueryParams* p);
+int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream);
+
+size_t lidf_refine_workspace_bytes(const LidfRefineParams* p);
+int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stream);
+
+/* stand-alone pieces (same kernels the fused call uses), exposed for tests and for callers that
+ * already hold some of the intermediates: */
+/* torchvision.ops.roi_align(feat, boxes(pix +- bbox/2 clamped), output_size=2, spatial_scale=1, aligned=True)
+ * evaluated once per ray -> [R,128] in (c,ph,pw) order (pipeline.py:374-389) */
+int lidf_roi_align_rays(const float* full_rgb_feat, int32_t B, int32_t H, int32_t W,
+                        const int64_t* miss_img_ind, const int64_t* miss_bid, int64_t R,
+                        int32_t roi_inp_bbox, float* roi_feat_per_ray, lidf_stream_t stream);
+/* torch_scatter.scatter_softmax + scatter_max + pred_pos gather (pipeline.py:441-454) on an arbitrary-order pair list */
+size_t lidf_ray_terminate_workspace_bytes(int64_t P, int64_t R);
+int lidf_ray_terminate(const float* pred_prob_end, const int64_t* pair_ray, const float* pair_pred_pos,
+                       const float* pcl_label_float, int64_t P, int64_t R,
+                       float* pred_prob_end_softmax, int64_t* max_pair_id, float* pred_pos,
+                       void* workspace, size_t workspace_bytes, lidf_stream_t stream);
+
+/* device time (ms) of the dominant decoder kernel (k_mlp_tc / k_mlp_simt) in the most recent lidf_query_forward on
+ * the calling thread, measured with CUDA events recorded around that launch on the caller's stream; synchronises on
+ * the stop event.  < 0 if no decoder kernel has been launched. */
+float lidf_query_last_mlp_ms(void);
+
+/* number of kernels this library launched on the calling thread since the last reset (bench.py's gpu_launches) */
+int64_t lidf_query_launch_count(int reset);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LIDF_QUERY_H_ */

