@@ -167,6 +167,10 @@ extern "C" const char* lidf_query_error_string(int code) {
   }
 }
 extern "C" const char* lidf_query_last_cuda_error(void) { return g_cuda_err; }
+extern "C" int lidf_tc_selftest(const float* A, const float* W, float* D, void* scratch, int32_t variant, lidf_stream_t stream) {
+  if (!A || !W || !D || !scratch) return LIDF_ERR_NULL;
+  return tc_selftest(A, W, D, (uint8_t*)scratch, variant, stream, &g_launches, g_cuda_err, sizeof(g_cuda_err));
+}
 extern "C" float lidf_query_last_mlp_ms(void) {
   if (!g_ev_valid) return -1.f;
   float ms = -1.f;

@@ -1,8 +1,739 @@
-// temporary stub
+// lidf_tc.cuh -- tcgen05 (5th-gen tensor core) engine for the LIDF decoders, sm_100a only.
+//
+// One persistent CTA per SM walks tiles of 128 ray-major pairs (row = TMEM lane = query point) and runs every decoder
+// pass on the tile while all activations stay on chip:
+//
+//   warps 0-7  "row warps"  : build the layer-1 A operand in TMEM (voxel-feature gather + positional encoding),
+//                             then the epilogues TMEM -> regs (bias / per-ray term / leaky) -> bf16 hi|lo -> TMEM
+//   warp  8    MMA issuer   : one elected lane issues tcgen05.mma (A from TMEM, B = weights from smem), accumulators
+//                             in TMEM, completion via tcgen05.commit -> mbarrier
+//   warp  9    weight loader: streams the pre-packed bf16 weight chunks (8 KB, UMMA canonical K-major layout)
+//                             global/L2 -> smem ring with cp.async.bulk (TMA) + mbarrier complete_tx
+//
+// Precision: every fp32 operand x is split x = hi + lo (two bf16); a MAC is the 3 products hi*hi + lo*hi + hi*lo
+// accumulated in fp32 (~2^-16 relative), which is what keeps the result within 1e-3 of the fp32 reference.
+//
+// TMEM plan (512 columns x 128 lanes x 32 bit):
+//   [  0,240) A1 : layer-1 operand, 15 k-steps x (8 cols hi | 8 cols lo); K order = vox(128) | sincos enter(48) |
+//                  sincos leave(48) | xyz enter, xyz leave, 10 x 0
+//   [256,384) X  : layer-1 half accumulator (128 fp32) -> converted IN PLACE to the layer-2 operand half; later the
+//                  layer-3 accumulator (64 fp32)
+//   [384,512) Y  : layer-2 accumulator (128 fp32) -> converted in place to the layer-3 operand
+// Per pass: L1h0 -> epi -> L2k0 ; L1h1 -> epi -> L2k1 -> epi -> L3 -> epi (+ layer 4 dot product in registers).
 #pragma once
+#include <cuda_bf16.h>
+
 #include "lidf_common.cuh"
+
 #define TC_KPE_MAX 112
-struct TcBufs { void* p; };
-template <typename B> inline TcBufs carve_tc(B& b, int64_t V, int n_dec) { return TcBufs{nullptr}; }
-inline int tc_query_forward(const LidfQueryParams*, const TcBufs&, const int*, const float*, const float*, int, int, int,
-                            cudaStream_t, int64_t*, char*, size_t, void (*)(int, cudaStream_t)) { return LIDF_ERR_UNSUPPORTED; }
+#define TC_THREADS 320
+#define TC_ROW_WARPS 8
+#define TC_CHUNK_BYTES 8192
+#define TC_CHUNKS_PER_DEC 50     // 15 (L1 half0) + 8 (L2 k-half0) + 15 (L1 half1) + 8 (L2 k-half1) + 4 (L3)
+#define TC_STAGES 24
+#define TC_K1_STEPS 15
+#define TC_COL_A1 0
+#define TC_COL_X 256
+#define TC_COL_Y 384
+#define TC_MAX_PASSES 9
+#define TC_SPIN_LIMIT (1u << 22)
+
+// ------------------------------------------------------------------------------------------------ PTX wrappers
+namespace tc {
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// bounded spin: a protocol bug traps (-> CUDA error) instead of hanging the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > TC_SPIN_LIMIT) __trap();
+  }
+}
+// TMA bulk copy global -> shared, completion counted on an mbarrier (SASS: UBLKCP)
+__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(dst_smem)),
+               "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(dst_smem)), "r"(ncols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ void commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16 (bf16 in, fp32 accumulate), M = 128.  (SASS: UTCHMMA)
+__device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(d_tmem), "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+
+// instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13), K-major A/B,
+// N>>3 at [17,23), M>>4 at [24,29)
+__host__ __device__ constexpr uint32_t make_idesc(int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+}
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), K-major, SWIZZLE_NONE ("interleave"):
+// core matrix = 8 rows x 16 B stored as 128 contiguous bytes; SBO = byte stride between 8-row groups,
+// LBO = byte stride between the two core matrices along K.  Layout used here: [kgroup(2)][N rows][16 B].
+__device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16) |
+         ((uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
+      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
+      : "memory");
+}
+
+// x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi).  Packs two elements per word, EVEN element in the low half
+// (element order inside a 32-bit TMEM column / smem word is little-endian in K).
+__device__ __forceinline__ void split2(float x_even, float x_odd, uint32_t& hi, uint32_t& lo) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x_odd), "f"(x_even));
+  const float re = x_even - __uint_as_float(hi << 16);
+  const float ro = x_odd - __uint_as_float(hi & 0xFFFF0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(ro), "f"(re));
+}
+// one k-step (16 elements) -> 8 hi words | 8 lo words
+__device__ __forceinline__ void split16(const float* x, uint32_t* out16) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) split2(x[2 * j], x[2 * j + 1], out16[j], out16[8 + j]);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------------------------------------ packing kernels
+// A1 element (K index of the layer-1 operand) -> column of linear_1.weight; -1 = zero padding.
+__host__ __device__ inline int tc_a1_col(int e, int pe_pos) {
+  const int base = LIDF_VOX_DIM + LIDF_RGB_DIM;             // PE(enter) starts at column 256 (pipeline.py:431-433)
+  if (e < 128) return e;                                    // voxel feature
+  if (e < 176) return base + 3 + (e - 128);                 // sin/cos part of PE(enter)
+  if (e < 224) return base + pe_pos + 3 + (e - 176);        // sin/cos part of PE(leave)
+  if (e < 227) return base + (e - 224);                     // raw enter xyz
+  if (e < 230) return base + pe_pos + (e - 227);            // raw leave xyz
+  return -1;
+}
+
+// weight stream of one decoder: 50 chunks x 8 KB.  Chunk with N rows (128, or 64 for layer 3) holds k-steps of
+// [hi: kg0 N x 16 B | kg1 N x 16 B][lo: kg0 | kg1]; an N=128 chunk is one k-step, an N=64 chunk two.
+__global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe_pos, const float* __restrict__ w2,
+                                  const float* __restrict__ w3, uint8_t* __restrict__ stream) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= TC_CHUNKS_PER_DEC * 2048) return;
+  const int c = idx / 2048, r = idx % 2048;
+  float w = 0.f;
+  int n, kk, N, ksub = 0;
+  if (c < 46) {
+    N = 128; n = r / 16; kk = r % 16;
+    if (c < 15 || (c >= 23 && c < 38)) {                    // layer 1, output half 0 / 1
+      const int half = c >= 23, s = half ? c - 23 : c;
+      const int col = tc_a1_col(16 * s + kk, pe_pos);
+      if (col >= 0) w = w1[(size_t)(half * 128 + n) * ldw1 + col];
+    } else {                                                // layer 2, K half 0 / 1
+      const int half = c >= 38, s = half ? c - 38 : c - 15;
+      w = w2[(size_t)n * LIDF_H1 + half * 128 + 16 * s + kk];
+    }
+  } else {                                                  // layer 3: N = 64, two k-steps per chunk
+    N = 64; ksub = r / 1024; const int rr = r % 1024; n = rr / 16; kk = rr % 16;
+    w = w3[(size_t)n * LIDF_H2 + 16 * (2 * (c - 46) + ksub) + kk];
+  }
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const int kg = kk >> 3, e = kk & 7;
+  const size_t kstep_bytes = (size_t)N * 64;                // hi (N*32) + lo (N*32)
+  uint8_t* base = stream + (size_t)c * TC_CHUNK_BYTES + ksub * kstep_bytes;
+  const size_t off = (size_t)kg * N * 16 + (size_t)n * 16 + e * 2;
+  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(base + (size_t)N * 32 + off) = lo;
+}
+
+// voxel table: [V][128 words]; word 16 s + j (j < 8) = bf16 hi of features (16 s + 2 j, +1), j >= 8 the lo parts.
+// This is exactly the TMEM column image of k-steps 0..7 of A1, so a row is 8 x (4 x LDG.128 -> tcgen05.st.x16).
+__global__ void k_pack_voxtab(const float* __restrict__ feat, int64_t V, uint32_t* __restrict__ tab) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= V * 64) return;
+  const int64_t v = idx >> 6;
+  const int p = (int)(idx & 63), s = p >> 3, j = p & 7;
+  const float a = feat[v * 128 + 16 * s + 2 * j], b = feat[v * 128 + 16 * s + 2 * j + 1];
+  uint32_t hi, lo;
+  tc::split2(a, b, hi, lo);
+  tab[v * 128 + 16 * s + j] = hi;
+  tab[v * 128 + 16 * s + 8 + j] = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ self test
+// D[128][128] = A[128][32] * W[128][32]^T through the exact primitives the engine uses (tcgen05.st A operand, TMA'd
+// weight chunks, TS-mode MMA with 3 split products, tcgen05.ld).  variant bit0 swaps LBO/SBO (must then be wrong).
+__global__ void __launch_bounds__(128) k_tc_selftest(const uint8_t* __restrict__ chunks, const float* __restrict__ A,
+                                                     float* __restrict__ D, int variant) {
+  __shared__ __align__(1024) uint8_t s_w[2 * TC_CHUNK_BYTES];
+  __shared__ __align__(8) uint64_t s_full, s_done;
+  __shared__ uint32_t s_tmem;
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  if (tid == 0) { tc::mbar_init(&s_full, 1); tc::mbar_init(&s_done, 1); tc::fence_barrier_init(); }
+  if (warp == 0) tc::tmem_alloc(&s_tmem, 256);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = s_tmem;
+  if (tid == 0) {
+    tc::mbar_arrive_expect_tx(&s_full, 2 * TC_CHUNK_BYTES);
+    tc::bulk_g2s(s_w, chunks, TC_CHUNK_BYTES, &s_full);
+    tc::bulk_g2s(s_w + TC_CHUNK_BYTES, chunks + TC_CHUNK_BYTES, TC_CHUNK_BYTES, &s_full);
+  }
+  {
+    float x[32];
+#pragma unroll
+    for (int k = 0; k < 32; ++k) x[k] = A[tid * 32 + k];
+    uint32_t w[16];
+    const uint32_t row_addr = tmem + ((uint32_t)(warp * 32) << 16);
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      tc::split16(x + 16 * s, w);
+      tc::tmem_st16(row_addr + 16 * s, w);
+    }
+    tc::wait_st();
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (tid == 0) {
+    tc::fence_after_sync();
+    tc::mbar_wait(&s_full, 0);
+    const uint32_t idesc = tc::make_idesc(128);
+    const uint32_t lbo = (variant & 1) ? 128u : 128u * 16u, sbo = (variant & 1) ? 128u * 16u : 128u;
+#pragma unroll
+    for (int s = 0; s < 2; ++s) {
+      const uint32_t whi = tc::smem_u32(s_w + s * TC_CHUNK_BYTES), wlo = whi + 128 * 32;
+      const uint32_t a_hi = tmem + 16 * s, a_lo = a_hi + 8;
+      tc::mma_ts(tmem + 128, a_hi, tc::make_bdesc(whi, lbo, sbo), idesc, s > 0);
+      tc::mma_ts(tmem + 128, a_lo, tc::make_bdesc(whi, lbo, sbo), idesc, 1);
+      tc::mma_ts(tmem + 128, a_hi, tc::make_bdesc(wlo, lbo, sbo), idesc, 1);
+    }
+    tc::commit(&s_done);
+  }
+  tc::mbar_wait(&s_done, 0);
+  tc::fence_after_sync();
+  {
+    const uint32_t row_addr = tmem + ((uint32_t)(warp * 32) << 16) + 128;
+#pragma unroll 1
+    for (int c = 0; c < 4; ++c) {
+      uint32_t r[32];
+      tc::tmem_ld32(row_addr + 32 * c, r);
+      tc::wait_ld();
+#pragma unroll
+      for (int j = 0; j < 32; ++j) D[tid * 128 + 32 * c + j] = __uint_as_float(r[j]);
+    }
+  }
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 0) tc::tmem_dealloc(tmem, 256);
+  (void)lane;
+}
+
+// pack W[128][32] (fp32, row-major) into two N=128 chunks for the self test
+__global__ void k_tc_selftest_pack(const float* __restrict__ W, uint8_t* __restrict__ chunks) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 2 * 2048) return;
+  const int c = idx / 2048, r = idx % 2048, n = r / 16, kk = r % 16;
+  const float w = W[n * 32 + 16 * c + kk];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const size_t off = (size_t)(kk >> 3) * 128 * 16 + (size_t)n * 16 + (kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(chunks + (size_t)c * TC_CHUNK_BYTES + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(chunks + (size_t)c * TC_CHUNK_BYTES + 128 * 32 + off) = lo;
+}
+
+// ------------------------------------------------------------------------------------------------ the engine
+struct TcArgs {
+  int64_t P; int n_tiles;
+  const int* perm; const int64_t* pair_vox; const int64_t* pair_ray;
+  const float* pair_dist; const float* dense_dist; int64_t R;
+  const float* ray_dir; const float* voxel_bound; int rel;
+  const uint32_t* voxtab;          // [V][128]
+  const float* T;                  // [R][512] per-ray layer-1 term, decoder d at column 256 d
+  const uint8_t* wstream;          // [2][50][8192]
+  const float* u;                  // [256] IEF rank-1 vector of decoder 0 (NULL if IMNet)
+  const float* b2[2]; const float* b3[2]; const float* w4[2]; const float* b4[2];
+  int kind[2]; int n_pass[2]; int use_sigmoid[2];
+  float o0, r0, r1, sqrt3, part;
+  float* out[2];                   // pred_offset, pred_prob_end  (written at the original pair index)
+  float* pos_out;                  // pair_pred_pos [P,3]
+  int n_prod;                      // bf16 products per MAC: 3 (hi*hi + lo*hi + hi*lo) or 1
+};
+
+struct TcSmem {
+  uint8_t w[TC_STAGES][TC_CHUNK_BYTES];
+  float u[LIDF_H1];
+  float b2[2][LIDF_H2];
+  float b3[2][LIDF_H3];
+  float w4[2][LIDF_H3];
+  float b4[2];
+  float part[2][2][128];           // [parity][half][row] layer-4 partial sums
+  uint64_t w_full[TC_STAGES], w_empty[TC_STAGES];
+  uint64_t a1_ready, a1_free, x_full, x_done, y_full, y_done;
+  uint32_t tmem_base;
+};
+
+__device__ __forceinline__ void tc_issue_kstep(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_saddr, int N, uint32_t idesc,
+                                               bool first, int n_prod) {
+  // a_tmem: 8 cols hi | 8 cols lo.  w_saddr: [hi N x 32 B][lo N x 32 B], each [kg(2)][N][16 B]
+  const uint64_t bhi = tc::make_bdesc(w_saddr, (uint32_t)N * 16u, 128u);
+  tc::mma_ts(d_tmem, a_tmem, bhi, idesc, first ? 0u : 1u);
+  if (n_prod == 3) {
+    const uint64_t blo = tc::make_bdesc(w_saddr + (uint32_t)N * 32u, (uint32_t)N * 16u, 128u);
+    tc::mma_ts(d_tmem, a_tmem + 8, bhi, idesc, 1u);
+    tc::mma_ts(d_tmem, a_tmem, blo, idesc, 1u);
+  }
+}
+
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant__ TcArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+
+  // ---- one-time setup -------------------------------------------------------------------------------------
+  for (int i = tid; i < LIDF_H1; i += TC_THREADS) S.u[i] = a.u ? a.u[i] : 0.f;
+  for (int i = tid; i < 2 * LIDF_H2; i += TC_THREADS) S.b2[i / LIDF_H2][i % LIDF_H2] = a.b2[i / LIDF_H2][i % LIDF_H2];
+  for (int i = tid; i < 2 * LIDF_H3; i += TC_THREADS) {
+    S.b3[i / LIDF_H3][i % LIDF_H3] = a.b3[i / LIDF_H3][i % LIDF_H3];
+    S.w4[i / LIDF_H3][i % LIDF_H3] = a.w4[i / LIDF_H3][i % LIDF_H3];
+  }
+  if (tid < 2) S.b4[tid] = a.b4[tid][0];
+  if (tid == 0) {
+    for (int i = 0; i < TC_STAGES; ++i) { tc::mbar_init(&S.w_full[i], 1); tc::mbar_init(&S.w_empty[i], 1); }
+    tc::mbar_init(&S.a1_ready, TC_ROW_WARPS);
+    tc::mbar_init(&S.a1_free, 1);
+    tc::mbar_init(&S.x_full, 1);
+    tc::mbar_init(&S.x_done, TC_ROW_WARPS);
+    tc::mbar_init(&S.y_full, 1);
+    tc::mbar_init(&S.y_done, TC_ROW_WARPS);
+    tc::fence_barrier_init();
+  }
+  if (warp == 8) tc::tmem_alloc(&S.tmem_base, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  const int n_pass_total = a.n_pass[0] + a.n_pass[1];
+
+  if (warp == 9) {
+    // ================================ weight loader (TMA) ================================
+    if (lane == 0) {
+      uint32_t stage = 0, fills = 0;
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        for (int p = 0; p < n_pass_total; ++p) {
+          const int d = p < a.n_pass[0] ? 0 : 1;
+          const uint8_t* src = a.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES;
+          for (int c = 0; c < TC_CHUNKS_PER_DEC; ++c) {
+            if (fills >= TC_STAGES) tc::mbar_wait(&S.w_empty[stage], ((fills / TC_STAGES) - 1) & 1);
+            tc::mbar_arrive_expect_tx(&S.w_full[stage], TC_CHUNK_BYTES);
+            tc::bulk_g2s(S.w[stage], src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[stage]);
+            ++fills;
+            stage = (stage + 1 == TC_STAGES) ? 0 : stage + 1;
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 8) {
+    // ================================ MMA issuer ================================
+    if (lane == 0) {
+      const uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
+      uint32_t stage = 0, uses = 0;          // weight ring position
+      uint32_t ph_a1 = 0, ph_xd = 0, ph_yd = 0;
+      bool first_ever = true;
+      auto next_stage = [&]() -> uint32_t {  // wait for the next chunk, return its smem address
+        tc::mbar_wait(&S.w_full[stage], (uses / TC_STAGES) & 1);
+        return tc::smem_u32(S.w[stage]);
+      };
+      auto release_stage = [&]() {
+        tc::commit(&S.w_empty[stage]);
+        ++uses;
+        stage = (stage + 1 == TC_STAGES) ? 0 : stage + 1;
+      };
+      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+        tc::mbar_wait(&S.a1_ready, ph_a1); ph_a1 ^= 1;
+        for (int p = 0; p < n_pass_total; ++p) {
+          // S0: layer 1, output half 0 -> X   (X must have been drained by the previous pass's layer-4 epilogue)
+          if (!first_ever) { tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1; }
+          first_ever = false;
+          tc::fence_after_sync();
+          for (int ks = 0; ks < TC_K1_STEPS; ++ks) {
+            const uint32_t w = next_stage();
+            tc_issue_kstep(tmem + TC_COL_X, tmem + TC_COL_A1 + 16 * ks, w, 128, idesc128, ks == 0, a.n_prod);
+            release_stage();
+          }
+          tc::commit(&S.x_full);
+          // S1: layer 2, K half 0 (operand = X converted in place) -> Y
+          tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
+          tc::fence_after_sync();
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t w = next_stage();
+            tc_issue_kstep(tmem + TC_COL_Y, tmem + TC_COL_X + 16 * ks, w, 128, idesc128, ks == 0, a.n_prod);
+            release_stage();
+          }
+          // S2: layer 1, output half 1 -> X (tensor pipe executes in issue order: S1's reads of X come first)
+          for (int ks = 0; ks < TC_K1_STEPS; ++ks) {
+            const uint32_t w = next_stage();
+            tc_issue_kstep(tmem + TC_COL_X, tmem + TC_COL_A1 + 16 * ks, w, 128, idesc128, ks == 0, a.n_prod);
+            release_stage();
+          }
+          tc::commit(&S.x_full);
+          if (p == n_pass_total - 1) tc::commit(&S.a1_free);       // last reader of A1 for this tile
+          // S3: layer 2, K half 1 -> Y (accumulate)
+          tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
+          tc::fence_after_sync();
+          for (int ks = 0; ks < 8; ++ks) {
+            const uint32_t w = next_stage();
+            tc_issue_kstep(tmem + TC_COL_Y, tmem + TC_COL_X + 16 * ks, w, 128, idesc128, false, a.n_prod);
+            release_stage();
+          }
+          tc::commit(&S.y_full);
+          // S4: layer 3 (N = 64), operand = Y converted in place, accumulator -> X[0,64)
+          tc::mbar_wait(&S.y_done, ph_yd); ph_yd ^= 1;
+          tc::fence_after_sync();
+          for (int c = 0; c < 4; ++c) {
+            const uint32_t w = next_stage();
+#pragma unroll
+            for (int j = 0; j < 2; ++j)
+              tc_issue_kstep(tmem + TC_COL_X, tmem + TC_COL_Y + 16 * (2 * c + j), w + j * 64 * 64, 64, idesc64,
+                             c == 0 && j == 0, a.n_prod);
+            release_stage();
+          }
+          tc::commit(&S.x_full);
+        }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================================ row warps: operand build + epilogues ================================
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    uint32_t ph_xf = 0, ph_yf = 0, ph_a1f = 0, par = 0;
+    bool first_tile = true;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      // ---- row metadata ----
+      const int64_t s = (int64_t)tile * 128 + row;
+      const bool valid = s < a.P;
+      int orig = 0, vox = 0, ray = 0;
+      float dir[3] = {0.f, 0.f, 0.f}, enter[3] = {0.f, 0.f, 0.f}, pin[3] = {0.f, 0.f, 0.f};
+      float pin_other[3] = {0.f, 0.f, 0.f};
+      if (valid) {
+        orig = a.perm ? a.perm[s] : (int)s;
+        vox = (int)a.pair_vox[orig]; ray = (int)a.pair_ray[orig];
+        float t0, t1;
+        if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)orig); t0 = t.x; t1 = t.y; }
+        else { const size_t o = ((size_t)vox * a.R + ray) * 2; t0 = a.dense_dist[o]; t1 = a.dense_dist[o + 1]; }
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+          dir[k] = a.ray_dir[(size_t)ray * 3 + k];
+          const float c = a.rel ? (a.voxel_bound[(size_t)vox * 6 + k] + a.voxel_bound[(size_t)vox * 6 + 3 + k]) / 2.0f : 0.f;
+          enter[k] = dir[k] * t0;
+          const float pe = enter[k] - c, pl = dir[k] * t1 - c;
+          pin[k] = h == 0 ? pe : pl;            // this half encodes enter (h=0) or leave (h=1)
+          pin_other[k] = h == 0 ? pl : pe;
+        }
+      }
+      // ---- build A1 (previous tile's layer-1 MMAs must be done with it) ----
+      if (!first_tile) { tc::mbar_wait(&S.a1_free, ph_a1f); ph_a1f ^= 1; }
+      first_tile = false;
+      tc::fence_after_sync();
+      {
+        const uint4* vrow = reinterpret_cast<const uint4*>(a.voxtab + (size_t)vox * 128);
+#pragma unroll
+        for (int s4 = 0; s4 < 4; ++s4) {                 // voxel k-steps 4h .. 4h+3
+          const int ks = 4 * h + s4;
+          uint32_t w[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (valid) t = __ldg(vrow + ks * 4 + v4);
+            w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
+          }
+          tc::tmem_st16(lane_addr + TC_COL_A1 + 16 * ks, w);
+        }
+        // positional encoding of this half's position: accurate sincos at f = 1 and f = 16, three exact-form
+        // double-angle steps after each (sin 2x = 2 s c, cos 2x = 1 - 2 s^2)
+        float v[48];
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+#pragma unroll
+          for (int g = 0; g < 2; ++g) {
+            float sn, cs;
+            sincosf(pin[c] * (g ? 16.0f : 1.0f), &sn, &cs);
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const int k = 4 * g + kk;
+              v[6 * k + c] = sn; v[6 * k + 3 + c] = cs;
+              const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;
+              sn = s2; cs = c2;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {                    // k-steps 8 + 3h + j
+          uint32_t w[16];
+          tc::split16(v + 16 * j, w);
+          tc::tmem_st16(lane_addr + TC_COL_A1 + 16 * (8 + 3 * h + j), w);
+        }
+        if (h == 0) {                                    // k-step 14: raw xyz of enter, leave, zero padding
+          float x[16];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) x[k] = 0.f;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) { x[k] = pin[k]; x[3 + k] = pin_other[k]; }
+          uint32_t w[16];
+          tc::split16(x, w);
+          tc::tmem_st16(lane_addr + TC_COL_A1 + 16 * 14, w);
+        }
+        tc::wait_st();
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.a1_ready);
+
+      // ---- decoder passes ----
+      float off_val = 0.f;
+      for (int d = 0; d < 2; ++d) {
+        float o = a.kind[d] == LIDF_DEC_IEF ? a.o0 : 0.f;
+        for (int it = 0; it < a.n_pass[d]; ++it) {
+          const float delta = o - a.o0;                   // IEF: T already holds u*o0 + c
+          const bool rank1 = a.kind[d] == LIDF_DEC_IEF && it > 0;
+          // E0 / E1: layer-1 epilogue, output half hf; this warp converts X columns [64 h, 64 h + 64)
+#pragma unroll 1
+          for (int hf = 0; hf < 2; ++hf) {
+            const int n0 = 128 * hf + 64 * h;
+            float4 t[16];
+            {
+              const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)ray * 512 + 256 * d + n0);
+#pragma unroll
+              for (int i = 0; i < 16; ++i) t[i] = valid ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+            tc::mbar_wait(&S.x_full, ph_xf); ph_xf ^= 1;
+            tc::fence_after_sync();
+#pragma unroll
+            for (int cc = 0; cc < 2; ++cc) {
+              uint32_t r[32];
+              tc::tmem_ld32(lane_addr + TC_COL_X + 64 * h + 32 * cc, r);
+              tc::wait_ld();
+              float x[32];
+#pragma unroll
+              for (int j = 0; j < 32; ++j) {
+                const float4 tv = t[8 * cc + (j >> 2)];
+                const float tj = (j & 3) == 0 ? tv.x : (j & 3) == 1 ? tv.y : (j & 3) == 2 ? tv.z : tv.w;
+                float val = __uint_as_float(r[j]) + tj;
+                if (rank1) val = fmaf(S.u[n0 + 32 * cc + j], delta, val);
+                x[j] = lidf_leaky(val);
+              }
+              uint32_t w[16];
+              tc::split16(x, w);
+              tc::tmem_st16(lane_addr + TC_COL_X + 64 * h + 32 * cc, w);
+              tc::split16(x + 16, w);
+              tc::tmem_st16(lane_addr + TC_COL_X + 64 * h + 32 * cc + 16, w);
+            }
+            tc::wait_st();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&S.x_done);
+          }
+          // E2: layer-2 epilogue on Y
+          tc::mbar_wait(&S.y_full, ph_yf); ph_yf ^= 1;
+          tc::fence_after_sync();
+#pragma unroll
+          for (int cc = 0; cc < 2; ++cc) {
+            uint32_t r[32];
+            tc::tmem_ld32(lane_addr + TC_COL_Y + 64 * h + 32 * cc, r);
+            tc::wait_ld();
+            float x[32];
+#pragma unroll
+            for (int j = 0; j < 32; ++j) x[j] = lidf_leaky(__uint_as_float(r[j]) + S.b2[d][64 * h + 32 * cc + j]);
+            uint32_t w[16];
+            tc::split16(x, w);
+            tc::tmem_st16(lane_addr + TC_COL_Y + 64 * h + 32 * cc, w);
+            tc::split16(x + 16, w);
+            tc::tmem_st16(lane_addr + TC_COL_Y + 64 * h + 32 * cc + 16, w);
+          }
+          tc::wait_st();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&S.y_done);
+          // E3: layer-3 epilogue + layer 4 (64-term dot product, 32 terms per half) on X[0,64)
+          tc::mbar_wait(&S.x_full, ph_xf); ph_xf ^= 1;
+          tc::fence_after_sync();
+          float partial = 0.f;
+          {
+            uint32_t r[32];
+            tc::tmem_ld32(lane_addr + TC_COL_X + 32 * h, r);
+            tc::wait_ld();
+            tc::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&S.x_done);      // X is free again for the next pass
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              const int n = 32 * h + j;
+              partial = fmaf(lidf_leaky(__uint_as_float(r[j]) + S.b3[d][n]), S.w4[d][n], partial);
+            }
+          }
+          S.part[par][h][row] = partial;
+          asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 row warps only
+          const float l4 = S.part[par][0][row] + S.part[par][1][row] + S.b4[d];
+          par ^= 1;
+          if (a.kind[d] == LIDF_DEC_IEF) o += l4; else o = l4;
+        }
+        const float res = lidf_final_act(o, a.use_sigmoid[d]);
+        if (d == 0) off_val = res;
+        if (valid && h == 0) a.out[d][orig] = res;
+      }
+      if (valid && h == 0) {
+        float sc = off_val * (a.r1 - a.r0) + a.r0;         // pipeline.py:437-439
+        sc = sc * a.sqrt3;
+        sc = sc * a.part;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)orig * 3 + k] = enter[k] + sc * dir[k];
+      }
+    }
+  }
+  // ---- teardown ----
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ host side
+struct TcBufs { uint32_t* voxtab; uint8_t* wstream; };
+
+template <typename B>
+inline TcBufs carve_tc(B& b, int64_t V, int n_dec) {
+  TcBufs t;
+  t.voxtab = b.template take<uint32_t>((size_t)(V > 0 ? V : 1) * 128);
+  t.wstream = b.template take<uint8_t>((size_t)n_dec * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES);
+  return t;
+}
+
+#define TC_LAUNCH_CHECK()                                                                         \
+  do {                                                                                            \
+    ++(*launches);                                                                                \
+    cudaError_t e__ = cudaGetLastError();                                                         \
+    if (e__ != cudaSuccess) {                                                                     \
+      snprintf(errbuf, errlen, "%s:%d %s", __FILE__, __LINE__, cudaGetErrorString(e__));          \
+      return LIDF_ERR_CUDA;                                                                       \
+    }                                                                                             \
+  } while (0)
+
+inline int tc_device_ok() {
+  int dev = 0, major = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+  if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev) != cudaSuccess) return 0;
+  return major == 10;
+}
+
+// decoders + pair_pred_pos for all P pairs; T = per-ray layer-1 term [R][512], u = IEF rank-1 vector of offset_dec
+inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const int* perm, const float* T, const float* u,
+                            int pe_pos, int D, int impl, cudaStream_t st, int64_t* launches, char* errbuf, size_t errlen,
+                            void (*mlp_event)(int, cudaStream_t)) {
+  if (!p->pos_encode || p->multires != 8 || pe_pos != 51) return LIDF_ERR_UNSUPPORTED;   // A1 layout is built for PE(8)
+  if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
+  const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
+  k_pack_voxtab<<<(unsigned)((p->V * 64 + 255) / 256), 256, 0, st>>>(p->occ_voxel_feat, p->V, tb.voxtab);
+  TC_LAUNCH_CHECK();
+  for (int d = 0; d < 2; ++d) {
+    const int ldw = D + (decs[d]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
+    k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(
+        decs[d]->w1, ldw, pe_pos, decs[d]->w2, decs[d]->w3, tb.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES);
+    TC_LAUNCH_CHECK();
+  }
+  TcArgs a{};
+  a.P = p->P; a.n_tiles = (int)((p->P + 127) / 128);
+  a.perm = perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
+  a.dense_dist = p->dense_dist; a.R = p->R; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
+  a.rel = p->intersect_pos_rel; a.voxtab = tb.voxtab; a.T = T; a.wstream = tb.wstream;
+  a.u = decs[0]->kind == LIDF_DEC_IEF ? u : nullptr;
+  for (int d = 0; d < 2; ++d) {
+    a.b2[d] = decs[d]->b2; a.b3[d] = decs[d]->b3; a.w4[d] = decs[d]->w4; a.b4[d] = decs[d]->b4;
+    a.kind[d] = decs[d]->kind; a.n_pass[d] = decs[d]->kind == LIDF_DEC_IEF ? decs[d]->n_iter : 1;
+    a.use_sigmoid[d] = decs[d]->use_sigmoid;
+  }
+  if (a.n_pass[0] + a.n_pass[1] > TC_MAX_PASSES) return LIDF_ERR_UNSUPPORTED;
+  a.o0 = decs[0]->init_offset; a.r0 = p->offset_range0; a.r1 = p->offset_range1;
+  a.sqrt3 = (float)sqrt(3.0); a.part = p->part_size;
+  a.out[0] = p->pred_offset; a.out[1] = p->pred_prob_end; a.pos_out = p->pair_pred_pos;
+  a.n_prod = impl == LIDF_MLP_TC_BF16X1 ? 1 : 3;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  const size_t smem = sizeof(TcSmem) + 1024;
+  if (cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    snprintf(errbuf, errlen, "cudaFuncSetAttribute(k_mlp_tc, %zu) failed: %s", smem, cudaGetErrorString(cudaGetLastError()));
+    return LIDF_ERR_CUDA;
+  }
+  if (mlp_event) mlp_event(0, st);
+  k_mlp_tc<<<grid, TC_THREADS, smem, st>>>(a);
+  if (mlp_event) mlp_event(1, st);
+  TC_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+// self test entry (exported through lidf_query.cu): D = A W^T, A [128][32], W [128][32], D [128][128], all device fp32
+inline int tc_selftest(const float* A, const float* W, float* D, uint8_t* scratch16k, int variant, cudaStream_t st,
+                       int64_t* launches, char* errbuf, size_t errlen) {
+  if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
+  k_tc_selftest_pack<<<16, 256, 0, st>>>(W, scratch16k);
+  TC_LAUNCH_CHECK();
+  k_tc_selftest<<<1, 128, 0, st>>>(scratch16k, A, D, variant);
+  TC_LAUNCH_CHECK();
+  return LIDF_OK;
+}

@@ -63,7 +63,7 @@ EXPORTED_SYMBOLS = [
     "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
     "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
-    "lidf_query_last_mlp_ms",
+    "lidf_query_last_mlp_ms", "lidf_tc_selftest",
 ]
 
 
@@ -96,6 +96,8 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_ray_terminate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.lidf_query_last_mlp_ms.restype = C.c_float
+    lib.lidf_tc_selftest.restype = C.c_int
+    lib.lidf_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.lidf_query_launch_count.restype = C.c_int64
     lib.lidf_query_launch_count.argtypes = [C.c_int]
     if lib.lidf_query_abi_version() != 1:
@@ -180,6 +182,19 @@ class _LidfQuery:
     def last_mlp_ms(self) -> float:
         """Device time of the decoder kernel in the latest forward (CUDA events on the launching stream)."""
         return float(self.lib.lidf_query_last_mlp_ms())
+
+    def tc_selftest(self, A: torch.Tensor, W: torch.Tensor, variant: int = 0) -> torch.Tensor:
+        """D = A @ W.T through the engine's tcgen05 primitives (A [128,32], W [128,32] fp32 CUDA)."""
+        dev = A.device
+        D = torch.empty(128, 128, dtype=torch.float32, device=dev)
+        scratch = torch.empty(16384, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.lidf_tc_selftest(_chk(A, "A", torch.float32), _chk(W, "W", torch.float32), D.data_ptr(),
+                                           scratch.data_ptr(), int(variant),
+                                           C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_tc_selftest")
+        torch.cuda.synchronize(dev)
+        return D
 
     INPUT_KEYS = ("full_rgb_feat", "occ_voxel_feat", "miss_ray_dir", "miss_img_ind", "miss_bid", "voxel_bound",
                   "occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist")

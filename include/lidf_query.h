@@ -156,6 +156,11 @@ int lidf_ray_terminate(const float* pred_prob_end, const int64_t* pair_ray, cons
                        float* pred_prob_end_softmax, int64_t* max_pair_id, float* pred_pos,
                        void* workspace, size_t workspace_bytes, lidf_stream_t stream);
 
+/* unit test of the tcgen05 primitives the decoder engine is built from (tcgen05.st operand staging, TMA weight chunks,
+ * TS-mode tcgen05.mma with the 3-product bf16 split, tcgen05.ld): D[128,128] = A[128,32] * W[128,32]^T, fp32 device
+ * arrays; scratch >= 16 KB device memory.  variant 0 = the layout the engine uses; 1 = LBO/SBO swapped (must be wrong). */
+int lidf_tc_selftest(const float* A, const float* W, float* D, void* scratch, int32_t variant, lidf_stream_t stream);
+
 /* device time (ms) of the dominant decoder kernel (k_mlp_tc / k_mlp_simt) in the most recent lidf_query_forward on
  * the calling thread, measured with CUDA events recorded around that launch on the caller's stream; synchronises on
  * the stop event.  < 0 if no decoder kernel has been launched. */
