@@ -30,7 +30,7 @@
 #define TC_ROW_WARPS 8
 #define TC_CHUNK_BYTES 8192
 #define TC_CHUNKS_PER_DEC 50     // 15 (L1 half0) + 8 (L2 k-half0) + 15 (L1 half1) + 8 (L2 k-half1) + 4 (L3)
-#define TC_STAGES 24
+#define TC_STAGES 25              // 50 chunks per pass = exactly 2 ring rotations -> stage/parity of a chunk are constants
 #define TC_K1_STEPS 15
 #define TC_COL_A1 0
 #define TC_COL_X 256
@@ -77,6 +77,17 @@ __device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, u
                    smem_u32(dst_smem)),
                "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar))
                : "memory");
+}
+
+// true on exactly one (converged) lane of the warp
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "elect.sync _|p, 0xffffffff;\n\t"
+      "selp.b32 %0, 1, 0, p;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
 }
 
 __device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
@@ -326,18 +337,20 @@ struct TcSmem {
   uint32_t tmem_base;
 };
 
+template <int NPROD>
 __device__ __forceinline__ void tc_issue_kstep(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_saddr, int N, uint32_t idesc,
-                                               bool first, int n_prod) {
+                                               bool first) {
   // a_tmem: 8 cols hi | 8 cols lo.  w_saddr: [hi N x 32 B][lo N x 32 B], each [kg(2)][N][16 B]
   const uint64_t bhi = tc::make_bdesc(w_saddr, (uint32_t)N * 16u, 128u);
   tc::mma_ts(d_tmem, a_tmem, bhi, idesc, first ? 0u : 1u);
-  if (n_prod == 3) {
+  if (NPROD == 3) {
     const uint64_t blo = tc::make_bdesc(w_saddr + (uint32_t)N * 32u, (uint32_t)N * 16u, 128u);
     tc::mma_ts(d_tmem, a_tmem + 8, bhi, idesc, 1u);
     tc::mma_ts(d_tmem, a_tmem, blo, idesc, 1u);
   }
 }
 
+template <int NPROD>
 __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TcSmem& S = *reinterpret_cast<TcSmem*>(smem_raw);
@@ -370,93 +383,98 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
 
   if (warp == 9) {
     // ================================ weight loader (TMA) ================================
-    if (lane == 0) {
-      uint32_t stage = 0, fills = 0;
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        for (int p = 0; p < n_pass_total; ++p) {
-          const int d = p < a.n_pass[0] ? 0 : 1;
-          const uint8_t* src = a.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES;
-          for (int c = 0; c < TC_CHUNKS_PER_DEC; ++c) {
-            if (fills >= TC_STAGES) tc::mbar_wait(&S.w_empty[stage], ((fills / TC_STAGES) - 1) & 1);
-            tc::mbar_arrive_expect_tx(&S.w_full[stage], TC_CHUNK_BYTES);
-            tc::bulk_g2s(S.w[stage], src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[stage]);
-            ++fills;
-            stage = (stage + 1 == TC_STAGES) ? 0 : stage + 1;
+    // chunk c of global pass g lives in stage c % 25 and is the (2 g + c / 25)-th fill of that stage
+    const bool leader = tc::elect_one();
+    bool primed = false;                   // false until the ring has been filled once
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      for (int p = 0; p < n_pass_total; ++p) {
+        const int d = p < a.n_pass[0] ? 0 : 1;
+        const uint8_t* src = a.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES;
+#pragma unroll
+        for (int c = 0; c < TC_CHUNKS_PER_DEC; ++c) {
+          const int stg = c % TC_STAGES;
+          if (primed || c >= TC_STAGES) tc::mbar_wait(&S.w_empty[stg], c >= TC_STAGES ? 0u : 1u);
+          if (leader) {
+            tc::mbar_arrive_expect_tx(&S.w_full[stg], TC_CHUNK_BYTES);
+            tc::bulk_g2s(S.w[stg], src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[stg]);
           }
+          __syncwarp();
         }
+        primed = true;
       }
     }
-    __syncwarp();
   } else if (warp == 8) {
     // ================================ MMA issuer ================================
-    if (lane == 0) {
-      const uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
-      uint32_t stage = 0, uses = 0;          // weight ring position
-      uint32_t ph_a1 = 0, ph_xd = 0, ph_yd = 0;
-      bool first_ever = true;
-      auto next_stage = [&]() -> uint32_t {  // wait for the next chunk, return its smem address
-        tc::mbar_wait(&S.w_full[stage], (uses / TC_STAGES) & 1);
-        return tc::smem_u32(S.w[stage]);
-      };
-      auto release_stage = [&]() {
-        tc::commit(&S.w_empty[stage]);
-        ++uses;
-        stage = (stage + 1 == TC_STAGES) ? 0 : stage + 1;
-      };
-      for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-        tc::mbar_wait(&S.a1_ready, ph_a1); ph_a1 ^= 1;
-        for (int p = 0; p < n_pass_total; ++p) {
-          // S0: layer 1, output half 0 -> X   (X must have been drained by the previous pass's layer-4 epilogue)
-          if (!first_ever) { tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1; }
-          first_ever = false;
-          tc::fence_after_sync();
-          for (int ks = 0; ks < TC_K1_STEPS; ++ks) {
-            const uint32_t w = next_stage();
-            tc_issue_kstep(tmem + TC_COL_X, tmem + TC_COL_A1 + 16 * ks, w, 128, idesc128, ks == 0, a.n_prod);
-            release_stage();
-          }
-          tc::commit(&S.x_full);
-          // S1: layer 2, K half 0 (operand = X converted in place) -> Y
-          tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
-          tc::fence_after_sync();
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t w = next_stage();
-            tc_issue_kstep(tmem + TC_COL_Y, tmem + TC_COL_X + 16 * ks, w, 128, idesc128, ks == 0, a.n_prod);
-            release_stage();
-          }
-          // S2: layer 1, output half 1 -> X (tensor pipe executes in issue order: S1's reads of X come first)
-          for (int ks = 0; ks < TC_K1_STEPS; ++ks) {
-            const uint32_t w = next_stage();
-            tc_issue_kstep(tmem + TC_COL_X, tmem + TC_COL_A1 + 16 * ks, w, 128, idesc128, ks == 0, a.n_prod);
-            release_stage();
-          }
+    // The whole warp stays converged (uniform control flow, uniform operands); one elected lane issues.
+    const bool leader = tc::elect_one();
+    constexpr uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
+    const uint32_t wbase = tc::smem_u32(S.w[0]);
+    uint32_t ph_a1 = 0, ph_xd = 0, ph_yd = 0;
+    bool first_ever = true;
+    // one N=128 chunk = one k-step: 3 (or 1) MMAs, then release the stage
+#define TC_CHUNK128(c, dcol, acol, first)                                                                   \
+    do {                                                                                                    \
+      tc::mbar_wait(&S.w_full[(c) % TC_STAGES], ((c) / TC_STAGES) & 1);                                     \
+      if (leader) {                                                                                         \
+        tc_issue_kstep<NPROD>(tmem + (dcol), tmem + (acol), wbase + ((c) % TC_STAGES) * TC_CHUNK_BYTES, 128, \
+                              idesc128, (first));                                                           \
+        tc::commit(&S.w_empty[(c) % TC_STAGES]);                                                            \
+      }                                                                                                     \
+      __syncwarp();                                                                                         \
+    } while (0)
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      tc::mbar_wait(&S.a1_ready, ph_a1); ph_a1 ^= 1;
+      for (int p = 0; p < n_pass_total; ++p) {
+        // S0: layer 1, output half 0 -> X   (X must have been drained by the previous pass's layer-4 epilogue)
+        if (!first_ever) { tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1; }
+        first_ever = false;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < TC_K1_STEPS; ++ks) TC_CHUNK128(ks, TC_COL_X, TC_COL_A1 + 16 * ks, ks == 0);
+        if (leader) tc::commit(&S.x_full);
+        __syncwarp();
+        // S1: layer 2, K half 0 (operand = X converted in place) -> Y
+        tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) TC_CHUNK128(15 + ks, TC_COL_Y, TC_COL_X + 16 * ks, ks == 0);
+        // S2: layer 1, output half 1 -> X (tensor pipe executes in issue order: S1's reads of X come first)
+#pragma unroll
+        for (int ks = 0; ks < TC_K1_STEPS; ++ks) TC_CHUNK128(23 + ks, TC_COL_X, TC_COL_A1 + 16 * ks, ks == 0);
+        if (leader) {
           tc::commit(&S.x_full);
           if (p == n_pass_total - 1) tc::commit(&S.a1_free);       // last reader of A1 for this tile
-          // S3: layer 2, K half 1 -> Y (accumulate)
-          tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
-          tc::fence_after_sync();
-          for (int ks = 0; ks < 8; ++ks) {
-            const uint32_t w = next_stage();
-            tc_issue_kstep(tmem + TC_COL_Y, tmem + TC_COL_X + 16 * ks, w, 128, idesc128, false, a.n_prod);
-            release_stage();
-          }
-          tc::commit(&S.y_full);
-          // S4: layer 3 (N = 64), operand = Y converted in place, accumulator -> X[0,64)
-          tc::mbar_wait(&S.y_done, ph_yd); ph_yd ^= 1;
-          tc::fence_after_sync();
-          for (int c = 0; c < 4; ++c) {
-            const uint32_t w = next_stage();
+        }
+        __syncwarp();
+        // S3: layer 2, K half 1 -> Y (accumulate)
+        tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int ks = 0; ks < 8; ++ks) TC_CHUNK128(38 + ks, TC_COL_Y, TC_COL_X + 16 * ks, false);
+        if (leader) tc::commit(&S.y_full);
+        __syncwarp();
+        // S4: layer 3 (N = 64, two k-steps per chunk), operand = Y converted in place, accumulator -> X[0,64)
+        tc::mbar_wait(&S.y_done, ph_yd); ph_yd ^= 1;
+        tc::fence_after_sync();
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+          constexpr int c0 = 46;
+          tc::mbar_wait(&S.w_full[(c0 + cc) % TC_STAGES], ((c0 + cc) / TC_STAGES) & 1);
+          if (leader) {
+            const uint32_t w = wbase + ((c0 + cc) % TC_STAGES) * TC_CHUNK_BYTES;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              tc_issue_kstep(tmem + TC_COL_X, tmem + TC_COL_Y + 16 * (2 * c + j), w + j * 64 * 64, 64, idesc64,
-                             c == 0 && j == 0, a.n_prod);
-            release_stage();
+              tc_issue_kstep<NPROD>(tmem + TC_COL_X, tmem + TC_COL_Y + 16 * (2 * cc + j), w + j * 64 * 64, 64, idesc64,
+                                    cc == 0 && j == 0);
+            tc::commit(&S.w_empty[(c0 + cc) % TC_STAGES]);
           }
-          tc::commit(&S.x_full);
+          __syncwarp();
         }
+        if (leader) tc::commit(&S.x_full);
+        __syncwarp();
       }
     }
-    __syncwarp();
+#undef TC_CHUNK128
   } else {
     // ================================ row warps: operand build + epilogues ================================
     const int q = warp & 3, h = warp >> 2;
@@ -716,12 +734,13 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
   const int grid = a.n_tiles < sms ? a.n_tiles : sms;
   const size_t smem = sizeof(TcSmem) + 1024;
-  if (cudaFuncSetAttribute(k_mlp_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+  auto kern = a.n_prod == 3 ? k_mlp_tc<3> : k_mlp_tc<1>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
     snprintf(errbuf, errlen, "cudaFuncSetAttribute(k_mlp_tc, %zu) failed: %s", smem, cudaGetErrorString(cudaGetLastError()));
     return LIDF_ERR_CUDA;
   }
   if (mlp_event) mlp_event(0, st);
-  k_mlp_tc<<<grid, TC_THREADS, smem, st>>>(a);
+  kern<<<grid, TC_THREADS, smem, st>>>(a);
   if (mlp_event) mlp_event(1, st);
   TC_LAUNCH_CHECK();
   return LIDF_OK;
