@@ -13,13 +13,20 @@
 // Precision: every fp32 operand x is split x = hi + lo (two bf16); a MAC is the 3 products hi*hi + lo*hi + hi*lo
 // accumulated in fp32 (~2^-16 relative), which is what keeps the result within 1e-3 of the fp32 reference.
 //
+// Layer-1 operand A1 (K = 240): vox(128) | sincos enter(48) | sincos leave(48) | xyz enter, xyz leave, 10 x 0.
+// Its voxel part lives in TMEM (TS-mode MMA), its PE part in shared memory in the UMMA canonical layout (SS-mode MMA);
+// that split is what leaves TMEM room for TWO layer-1 half buffers, so epilogues overlap the next MMA batch.
 // TMEM plan (512 columns x 128 lanes x 32 bit):
-//   [  0,240) A1 : layer-1 operand, 15 k-steps x (8 cols hi | 8 cols lo); K order = vox(128) | sincos enter(48) |
-//                  sincos leave(48) | xyz enter, xyz leave, 10 x 0
-//   [256,384) X  : layer-1 half accumulator (128 fp32) -> converted IN PLACE to the layer-2 operand half; later the
-//                  layer-3 accumulator (64 fp32)
+//   [  0,128) AV : voxel k-steps, 8 x (8 cols hi | 8 cols lo)
+//   [128,256) X0 : layer-1 output half 0, fp32 accumulator -> converted IN PLACE to the layer-2 operand (K half 0)
+//   [256,384) X1 : layer-1 output half 1, same; afterwards the layer-3 accumulator (64 cols)
 //   [384,512) Y  : layer-2 accumulator (128 fp32) -> converted in place to the layer-3 operand
-// Per pass: L1h0 -> epi -> L2k0 ; L1h1 -> epi -> L2k1 -> epi -> L3 -> epi (+ layer 4 dot product in registers).
+// MMA issue order per pass p (tensor pipe executes in order; Ex = epilogue of the row warps):
+//   S2(p): L1 half 1 -> X1   | E0(p) converts X0 meanwhile
+//   S1(p): L2 K-half 0 -> Y  | E1(p) converts X1 meanwhile
+//   S3(p): L2 K-half 1 -> Y
+//   S0(p+1): L1 half 0 of the NEXT pass -> X0   | E2(p) converts Y meanwhile
+//   S4(p): L3 -> X1[0,64)    | E3(p): layer-3 epilogue + layer-4 dot product
 #pragma once
 #include <cuda_bf16.h>
 
@@ -29,12 +36,15 @@
 #define TC_THREADS 320
 #define TC_ROW_WARPS 8
 #define TC_CHUNK_BYTES 8192
-#define TC_CHUNKS_PER_DEC 50     // 15 (L1 half0) + 8 (L2 k-half0) + 15 (L1 half1) + 8 (L2 k-half1) + 4 (L3)
-#define TC_STAGES 25              // 50 chunks per pass = exactly 2 ring rotations -> stage/parity of a chunk are constants
+#define TC_CHUNKS_PER_DEC 50     // 15 (L1 half 0) + 15 (L1 half 1) + 8 (L2 K-half 0) + 8 (L2 K-half 1) + 4 (L3)
+#define TC_STAGES 16
 #define TC_K1_STEPS 15
-#define TC_COL_A1 0
-#define TC_COL_X 256
-#define TC_COL_Y 384
+#define TC_COL_AV 0               // voxel part of the layer-1 operand: 8 k-steps x (8 cols hi | 8 cols lo)
+#define TC_COL_X0 128             // layer-1 output half 0: accumulator -> (in place) layer-2 operand
+#define TC_COL_X1 256             // layer-1 output half 1; later the layer-3 accumulator (64 cols)
+#define TC_COL_Y 384              // layer-2 accumulator -> (in place) layer-3 operand
+#define TC_PE_KSTEPS 7
+#define TC_PE_PART_BYTES (TC_PE_KSTEPS * 4096)   // one part (hi or lo) of the PE operand tile: [kgroup(14)][128 rows][16 B]
 #define TC_MAX_PASSES 9
 #define TC_SPIN_LIMIT (1u << 22)
 
@@ -117,6 +127,22 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
       : "memory");
 }
 
+// D[tmem] (+)= A[smem] * B[smem]^T
+__device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, {%5, %5, %5, %5}, p;\n\t}"
+      :
+      : "r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+// make generic-proxy smem writes visible to the async proxy (tensor core operand fetch)
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void st_shared_v4(uint32_t saddr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(saddr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // instruction descriptor (cute::UMMA::InstrDescriptor): c=F32 [4,6), a=BF16 [7,10), b=BF16 [10,13), K-major A/B,
 // N>>3 at [17,23), M>>4 at [24,29)
 __host__ __device__ constexpr uint32_t make_idesc(int N) {
@@ -188,12 +214,12 @@ __global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe
   int n, kk, N, ksub = 0;
   if (c < 46) {
     N = 128; n = r / 16; kk = r % 16;
-    if (c < 15 || (c >= 23 && c < 38)) {                    // layer 1, output half 0 / 1
-      const int half = c >= 23, s = half ? c - 23 : c;
+    if (c < 30) {                                           // layer 1, output half 0 / 1
+      const int half = c >= 15, s = half ? c - 15 : c;
       const int col = tc_a1_col(16 * s + kk, pe_pos);
       if (col >= 0) w = w1[(size_t)(half * 128 + n) * ldw1 + col];
     } else {                                                // layer 2, K half 0 / 1
-      const int half = c >= 38, s = half ? c - 38 : c - 15;
+      const int half = c >= 38, s = half ? c - 38 : c - 30;
       w = w2[(size_t)n * LIDF_H1 + half * 128 + 16 * s + kk];
     }
   } else {                                                  // layer 3: N = 64, two k-steps per chunk
@@ -326,27 +352,40 @@ struct TcArgs {
 
 struct TcSmem {
   uint8_t w[TC_STAGES][TC_CHUNK_BYTES];
+  uint8_t pe[2][TC_PE_PART_BYTES];   // PE part of the layer-1 operand: [hi|lo][kgroup(14)][128 rows][16 B]
   float u[LIDF_H1];
   float b2[2][LIDF_H2];
   float b3[2][LIDF_H3];
   float w4[2][LIDF_H3];
   float b4[2];
-  float part[2][2][128];           // [parity][half][row] layer-4 partial sums
+  float part[2][2][128];             // [parity][half][row] layer-4 partial sums
   uint64_t w_full[TC_STAGES], w_empty[TC_STAGES];
-  uint64_t a1_ready, a1_free, x_full, x_done, y_full, y_done;
+  uint64_t a1_ready, a1_free, x_full[2], x_done[2], y_full, y_done;
   uint32_t tmem_base;
 };
 
+// one k-step (K = 16) with the A operand in TMEM: a_tmem = 8 cols hi | 8 cols lo; w_saddr = [hi N x 32 B][lo N x 32 B]
 template <int NPROD>
-__device__ __forceinline__ void tc_issue_kstep(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_saddr, int N, uint32_t idesc,
-                                               bool first) {
-  // a_tmem: 8 cols hi | 8 cols lo.  w_saddr: [hi N x 32 B][lo N x 32 B], each [kg(2)][N][16 B]
+__device__ __forceinline__ void tc_kstep_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_saddr, int N, uint32_t idesc,
+                                            bool first) {
   const uint64_t bhi = tc::make_bdesc(w_saddr, (uint32_t)N * 16u, 128u);
   tc::mma_ts(d_tmem, a_tmem, bhi, idesc, first ? 0u : 1u);
   if (NPROD == 3) {
     const uint64_t blo = tc::make_bdesc(w_saddr + (uint32_t)N * 32u, (uint32_t)N * 16u, 128u);
     tc::mma_ts(d_tmem, a_tmem + 8, bhi, idesc, 1u);
     tc::mma_ts(d_tmem, a_tmem, blo, idesc, 1u);
+  }
+}
+// one k-step with the A operand in shared memory (canonical [kgroup(2)][128][16 B], hi and lo tiles), N = 128
+template <int NPROD>
+__device__ __forceinline__ void tc_kstep_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_saddr, uint32_t idesc,
+                                            bool first) {
+  const uint64_t ahi = tc::make_bdesc(a_hi, 2048u, 128u), bhi = tc::make_bdesc(w_saddr, 2048u, 128u);
+  tc::mma_ss(d_tmem, ahi, bhi, idesc, first ? 0u : 1u);
+  if (NPROD == 3) {
+    const uint64_t alo = tc::make_bdesc(a_lo, 2048u, 128u), blo = tc::make_bdesc(w_saddr + 4096u, 2048u, 128u);
+    tc::mma_ss(d_tmem, alo, bhi, idesc, 1u);
+    tc::mma_ss(d_tmem, ahi, blo, idesc, 1u);
   }
 }
 
@@ -368,8 +407,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     for (int i = 0; i < TC_STAGES; ++i) { tc::mbar_init(&S.w_full[i], 1); tc::mbar_init(&S.w_empty[i], 1); }
     tc::mbar_init(&S.a1_ready, TC_ROW_WARPS);
     tc::mbar_init(&S.a1_free, 1);
-    tc::mbar_init(&S.x_full, 1);
-    tc::mbar_init(&S.x_done, TC_ROW_WARPS);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.x_full[i], 1); tc::mbar_init(&S.x_done[i], TC_ROW_WARPS); }
     tc::mbar_init(&S.y_full, 1);
     tc::mbar_init(&S.y_done, TC_ROW_WARPS);
     tc::fence_barrier_init();
@@ -380,27 +418,36 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
   tc::fence_after_sync();
   const uint32_t tmem = S.tmem_base;
   const int n_pass_total = a.n_pass[0] + a.n_pass[1];
+  // weight-stream segments of one decoder (chunk ranges), in stream order
+  constexpr int SEG_L1H0 = 0, SEG_L1H1 = 15, SEG_L2K0 = 30, SEG_L2K1 = 38, SEG_L3 = 46;
 
   if (warp == 9) {
     // ================================ weight loader (TMA) ================================
-    // chunk c of global pass g lives in stage c % 25 and is the (2 g + c / 25)-th fill of that stage
+    // emits chunks in the order the MMA issuer consumes them:
+    //   L1h0(pass 0), then per pass p: L1h1(p), L2k0(p), L2k1(p), L1h0(p+1) [if any], L3(p)
     const bool leader = tc::elect_one();
-    bool primed = false;                   // false until the ring has been filled once
+    uint32_t f = 0;                        // fill counter: stage = f % 16, fill number of that stage = f / 16
+    auto emit = [&](int d, int c0, int n) {
+      const uint8_t* src = a.wstream + ((size_t)d * TC_CHUNKS_PER_DEC + c0) * TC_CHUNK_BYTES;
+      for (int c = 0; c < n; ++c, ++f) {
+        const uint32_t stg = f % TC_STAGES;
+        if (f >= TC_STAGES) tc::mbar_wait(&S.w_empty[stg], ((f / TC_STAGES) - 1) & 1);
+        if (leader) {
+          tc::mbar_arrive_expect_tx(&S.w_full[stg], TC_CHUNK_BYTES);
+          tc::bulk_g2s(S.w[stg], src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[stg]);
+        }
+        __syncwarp();
+      }
+    };
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
+      emit(0 < a.n_pass[0] ? 0 : 1, SEG_L1H0, 15);
       for (int p = 0; p < n_pass_total; ++p) {
         const int d = p < a.n_pass[0] ? 0 : 1;
-        const uint8_t* src = a.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES;
-#pragma unroll
-        for (int c = 0; c < TC_CHUNKS_PER_DEC; ++c) {
-          const int stg = c % TC_STAGES;
-          if (primed || c >= TC_STAGES) tc::mbar_wait(&S.w_empty[stg], c >= TC_STAGES ? 0u : 1u);
-          if (leader) {
-            tc::mbar_arrive_expect_tx(&S.w_full[stg], TC_CHUNK_BYTES);
-            tc::bulk_g2s(S.w[stg], src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[stg]);
-          }
-          __syncwarp();
-        }
-        primed = true;
+        emit(d, SEG_L1H1, 15);
+        emit(d, SEG_L2K0, 8);
+        emit(d, SEG_L2K1, 8);
+        if (p + 1 < n_pass_total) emit(p + 1 < a.n_pass[0] ? 0 : 1, SEG_L1H0, 15);
+        emit(d, SEG_L3, 4);
       }
     }
   } else if (warp == 8) {
@@ -409,79 +456,107 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     const bool leader = tc::elect_one();
     constexpr uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
     const uint32_t wbase = tc::smem_u32(S.w[0]);
-    uint32_t ph_a1 = 0, ph_xd = 0, ph_yd = 0;
-    bool first_ever = true;
-    // one N=128 chunk = one k-step: 3 (or 1) MMAs, then release the stage
-#define TC_CHUNK128(c, dcol, acol, first)                                                                   \
-    do {                                                                                                    \
-      tc::mbar_wait(&S.w_full[(c) % TC_STAGES], ((c) / TC_STAGES) & 1);                                     \
-      if (leader) {                                                                                         \
-        tc_issue_kstep<NPROD>(tmem + (dcol), tmem + (acol), wbase + ((c) % TC_STAGES) * TC_CHUNK_BYTES, 128, \
-                              idesc128, (first));                                                           \
-        tc::commit(&S.w_empty[(c) % TC_STAGES]);                                                            \
-      }                                                                                                     \
-      __syncwarp();                                                                                         \
-    } while (0)
+    const uint32_t pe_hi = tc::smem_u32(S.pe[0]), pe_lo = tc::smem_u32(S.pe[1]);
+    uint32_t f = 0;                                   // chunks consumed
+    uint32_t ph_a1 = 0, ph_xd0 = 0, ph_xd1 = 0, ph_yd = 0;
+    bool x1_used = false;                             // has X1 ever held a layer-3 accumulator?
+    auto wait_chunk = [&]() -> uint32_t {
+      tc::mbar_wait(&S.w_full[f % TC_STAGES], (f / TC_STAGES) & 1);
+      return wbase + (f % TC_STAGES) * TC_CHUNK_BYTES;
+    };
+    auto release_chunk = [&]() {
+      if (leader) tc::commit(&S.w_empty[f % TC_STAGES]);
+      __syncwarp();
+      ++f;
+    };
+    auto issue_l1 = [&](uint32_t dcol) {              // 8 voxel k-steps (A in TMEM) + 7 PE k-steps (A in smem)
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t w = wait_chunk();
+        if (leader) tc_kstep_ts<NPROD>(tmem + dcol, tmem + TC_COL_AV + 16 * ks, w, 128, idesc128, ks == 0);
+        release_chunk();
+      }
+#pragma unroll
+      for (int ks = 0; ks < TC_PE_KSTEPS; ++ks) {
+        const uint32_t w = wait_chunk();
+        if (leader) tc_kstep_ss<NPROD>(tmem + dcol, pe_hi + ks * 4096, pe_lo + ks * 4096, w, idesc128, false);
+        release_chunk();
+      }
+    };
+    auto issue_l2 = [&](uint32_t acol, bool first_half) {
+#pragma unroll
+      for (int ks = 0; ks < 8; ++ks) {
+        const uint32_t w = wait_chunk();
+        if (leader) tc_kstep_ts<NPROD>(tmem + TC_COL_Y, tmem + acol + 16 * ks, w, 128, idesc128, first_half && ks == 0);
+        release_chunk();
+      }
+    };
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       tc::mbar_wait(&S.a1_ready, ph_a1); ph_a1 ^= 1;
+      tc::fence_after_sync();
+      issue_l1(TC_COL_X0);                            // S0(pass 0)
+      if (leader) tc::commit(&S.x_full[0]);
+      __syncwarp();
       for (int p = 0; p < n_pass_total; ++p) {
-        // S0: layer 1, output half 0 -> X   (X must have been drained by the previous pass's layer-4 epilogue)
-        if (!first_ever) { tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1; }
-        first_ever = false;
+        // S2(p): layer 1, output half 1 -> X1 (the previous layer-3 accumulator must have been read: E3)
+        if (x1_used) { tc::mbar_wait(&S.x_done[1], ph_xd1); ph_xd1 ^= 1; }
         tc::fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < TC_K1_STEPS; ++ks) TC_CHUNK128(ks, TC_COL_X, TC_COL_A1 + 16 * ks, ks == 0);
-        if (leader) tc::commit(&S.x_full);
-        __syncwarp();
-        // S1: layer 2, K half 0 (operand = X converted in place) -> Y
-        tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
-        tc::fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) TC_CHUNK128(15 + ks, TC_COL_Y, TC_COL_X + 16 * ks, ks == 0);
-        // S2: layer 1, output half 1 -> X (tensor pipe executes in issue order: S1's reads of X come first)
-#pragma unroll
-        for (int ks = 0; ks < TC_K1_STEPS; ++ks) TC_CHUNK128(23 + ks, TC_COL_X, TC_COL_A1 + 16 * ks, ks == 0);
+        issue_l1(TC_COL_X1);
         if (leader) {
-          tc::commit(&S.x_full);
-          if (p == n_pass_total - 1) tc::commit(&S.a1_free);       // last reader of A1 for this tile
+          tc::commit(&S.x_full[1]);
+          if (p == n_pass_total - 1) tc::commit(&S.a1_free);   // last reader of the layer-1 operand of this tile
         }
         __syncwarp();
-        // S3: layer 2, K half 1 -> Y (accumulate)
-        tc::mbar_wait(&S.x_done, ph_xd); ph_xd ^= 1;
+        // S1(p): layer 2, K half 0 (X0 converted in place by E0) -> Y
+        tc::mbar_wait(&S.x_done[0], ph_xd0); ph_xd0 ^= 1;
         tc::fence_after_sync();
-#pragma unroll
-        for (int ks = 0; ks < 8; ++ks) TC_CHUNK128(38 + ks, TC_COL_Y, TC_COL_X + 16 * ks, false);
+        issue_l2(TC_COL_X0, true);
+        // S3(p): layer 2, K half 1 (X1 converted by E1) -> Y
+        tc::mbar_wait(&S.x_done[1], ph_xd1); ph_xd1 ^= 1;
+        tc::fence_after_sync();
+        issue_l2(TC_COL_X1, false);
         if (leader) tc::commit(&S.y_full);
         __syncwarp();
-        // S4: layer 3 (N = 64, two k-steps per chunk), operand = Y converted in place, accumulator -> X[0,64)
+        // S0(p+1): layer 1, output half 0 of the next pass -> X0 (free: S1(p) precedes it in the in-order pipe)
+        if (p + 1 < n_pass_total) {
+          issue_l1(TC_COL_X0);
+          if (leader) tc::commit(&S.x_full[0]);
+          __syncwarp();
+        }
+        // S4(p): layer 3 (N = 64, two k-steps per chunk), operand = Y converted by E2, accumulator -> X1[0,64)
         tc::mbar_wait(&S.y_done, ph_yd); ph_yd ^= 1;
         tc::fence_after_sync();
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-          constexpr int c0 = 46;
-          tc::mbar_wait(&S.w_full[(c0 + cc) % TC_STAGES], ((c0 + cc) / TC_STAGES) & 1);
+          const uint32_t w = wait_chunk();
           if (leader) {
-            const uint32_t w = wbase + ((c0 + cc) % TC_STAGES) * TC_CHUNK_BYTES;
 #pragma unroll
             for (int j = 0; j < 2; ++j)
-              tc_issue_kstep<NPROD>(tmem + TC_COL_X, tmem + TC_COL_Y + 16 * (2 * cc + j), w + j * 64 * 64, 64, idesc64,
-                                    cc == 0 && j == 0);
-            tc::commit(&S.w_empty[(c0 + cc) % TC_STAGES]);
+              tc_kstep_ts<NPROD>(tmem + TC_COL_X1, tmem + TC_COL_Y + 16 * (2 * cc + j), w + j * 64 * 64, 64, idesc64,
+                                 cc == 0 && j == 0);
           }
-          __syncwarp();
+          release_chunk();
         }
-        if (leader) tc::commit(&S.x_full);
+        if (leader) tc::commit(&S.x_full[1]);
         __syncwarp();
+        x1_used = true;
       }
     }
-#undef TC_CHUNK128
   } else {
     // ================================ row warps: operand build + epilogues ================================
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    uint32_t ph_xf = 0, ph_yf = 0, ph_a1f = 0, par = 0;
+    const uint32_t pe_row[2] = {tc::smem_u32(S.pe[0]) + row * 16, tc::smem_u32(S.pe[1]) + row * 16};
+    uint32_t ph_xf0 = 0, ph_xf1 = 0, ph_yf = 0, ph_a1f = 0, par = 0;
     bool first_tile = true;
+    // store one k-step (16 values) of the PE operand tile: hi/lo x kgroup 0/1, 16 B each
+    auto st_pe = [&](int ks, const uint32_t* w) {
+      tc::st_shared_v4(pe_row[0] + (2 * ks) * 2048, w[0], w[1], w[2], w[3]);
+      tc::st_shared_v4(pe_row[0] + (2 * ks + 1) * 2048, w[4], w[5], w[6], w[7]);
+      tc::st_shared_v4(pe_row[1] + (2 * ks) * 2048, w[8], w[9], w[10], w[11]);
+      tc::st_shared_v4(pe_row[1] + (2 * ks + 1) * 2048, w[12], w[13], w[14], w[15]);
+    };
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
       // ---- row metadata ----
       const int64_t s = (int64_t)tile * 128 + row;
@@ -505,14 +580,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           pin_other[k] = h == 0 ? pl : pe;
         }
       }
-      // ---- build A1 (previous tile's layer-1 MMAs must be done with it) ----
+      // ---- build the layer-1 operand (previous tile's layer-1 MMAs must be done with it) ----
       if (!first_tile) { tc::mbar_wait(&S.a1_free, ph_a1f); ph_a1f ^= 1; }
       first_tile = false;
       tc::fence_after_sync();
       {
         const uint4* vrow = reinterpret_cast<const uint4*>(a.voxtab + (size_t)vox * 128);
 #pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {                 // voxel k-steps 4h .. 4h+3
+        for (int s4 = 0; s4 < 4; ++s4) {                 // voxel k-steps 4h .. 4h+3 -> TMEM
           const int ks = 4 * h + s4;
           uint32_t w[16];
 #pragma unroll
@@ -521,7 +596,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
             if (valid) t = __ldg(vrow + ks * 4 + v4);
             w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
           }
-          tc::tmem_st16(lane_addr + TC_COL_A1 + 16 * ks, w);
+          tc::tmem_st16(lane_addr + TC_COL_AV + 16 * ks, w);
         }
         // positional encoding of this half's position: accurate sincos at f = 1 and f = 16, three exact-form
         // double-angle steps after each (sin 2x = 2 s c, cos 2x = 1 - 2 s^2)
@@ -542,12 +617,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           }
         }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {                    // k-steps 8 + 3h + j
+        for (int j = 0; j < 3; ++j) {                    // PE k-steps 3h + j -> smem operand tile
           uint32_t w[16];
           tc::split16(v + 16 * j, w);
-          tc::tmem_st16(lane_addr + TC_COL_A1 + 16 * (8 + 3 * h + j), w);
+          st_pe(3 * h + j, w);
         }
-        if (h == 0) {                                    // k-step 14: raw xyz of enter, leave, zero padding
+        if (h == 0) {                                    // PE k-step 6: raw xyz of enter, leave, zero padding
           float x[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) x[k] = 0.f;
@@ -555,9 +630,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           for (int k = 0; k < 3; ++k) { x[k] = pin[k]; x[3 + k] = pin_other[k]; }
           uint32_t w[16];
           tc::split16(x, w);
-          tc::tmem_st16(lane_addr + TC_COL_A1 + 16 * 14, w);
+          st_pe(6, w);
         }
         tc::wait_st();
+        tc::fence_proxy_async();
       }
       tc::fence_before_sync();
       __syncwarp();
@@ -570,22 +646,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         for (int it = 0; it < a.n_pass[d]; ++it) {
           const float delta = o - a.o0;                   // IEF: T already holds u*o0 + c
           const bool rank1 = a.kind[d] == LIDF_DEC_IEF && it > 0;
-          // E0 / E1: layer-1 epilogue, output half hf; this warp converts X columns [64 h, 64 h + 64)
-#pragma unroll 1
+          // E0 / E1: layer-1 epilogue of output half hf (buffer X0 / X1); this warp converts columns [64 h, 64 h + 64)
+#pragma unroll
           for (int hf = 0; hf < 2; ++hf) {
             const int n0 = 128 * hf + 64 * h;
+            const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 64 * h;
             float4 t[16];
             {
               const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)ray * 512 + 256 * d + n0);
 #pragma unroll
               for (int i = 0; i < 16; ++i) t[i] = valid ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
             }
-            tc::mbar_wait(&S.x_full, ph_xf); ph_xf ^= 1;
+            if (hf == 0) { tc::mbar_wait(&S.x_full[0], ph_xf0); ph_xf0 ^= 1; }
+            else { tc::mbar_wait(&S.x_full[1], ph_xf1); ph_xf1 ^= 1; }
             tc::fence_after_sync();
 #pragma unroll
             for (int cc = 0; cc < 2; ++cc) {
               uint32_t r[32];
-              tc::tmem_ld32(lane_addr + TC_COL_X + 64 * h + 32 * cc, r);
+              tc::tmem_ld32(lane_addr + xcol + 32 * cc, r);
               tc::wait_ld();
               float x[32];
 #pragma unroll
@@ -598,14 +676,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
               }
               uint32_t w[16];
               tc::split16(x, w);
-              tc::tmem_st16(lane_addr + TC_COL_X + 64 * h + 32 * cc, w);
+              tc::tmem_st16(lane_addr + xcol + 32 * cc, w);
               tc::split16(x + 16, w);
-              tc::tmem_st16(lane_addr + TC_COL_X + 64 * h + 32 * cc + 16, w);
+              tc::tmem_st16(lane_addr + xcol + 32 * cc + 16, w);
             }
             tc::wait_st();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&S.x_done);
+            if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
           }
           // E2: layer-2 epilogue on Y
           tc::mbar_wait(&S.y_full, ph_yf); ph_yf ^= 1;
@@ -628,17 +706,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&S.y_done);
-          // E3: layer-3 epilogue + layer 4 (64-term dot product, 32 terms per half) on X[0,64)
-          tc::mbar_wait(&S.x_full, ph_xf); ph_xf ^= 1;
+          // E3: layer-3 epilogue + layer 4 (64-term dot product, 32 terms per half) on X1[0,64)
+          tc::mbar_wait(&S.x_full[1], ph_xf1); ph_xf1 ^= 1;
           tc::fence_after_sync();
           float partial = 0.f;
           {
             uint32_t r[32];
-            tc::tmem_ld32(lane_addr + TC_COL_X + 32 * h, r);
+            tc::tmem_ld32(lane_addr + TC_COL_X1 + 32 * h, r);
             tc::wait_ld();
             tc::fence_before_sync();
             __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&S.x_done);      // X is free again for the next pass
+            if (lane == 0) tc::mbar_arrive(&S.x_done[1]);   // X1 is free again for the next pass's layer 1
 #pragma unroll
             for (int j = 0; j < 32; ++j) {
               const int n = 32 * h + j;
