@@ -3,48 +3,62 @@
 // One persistent CTA per SM walks tiles of 128 ray-major pairs (row = TMEM lane = query point) and runs every decoder
 // pass on the tile while all activations stay on chip:
 //
-//   warps 0-7  "row warps"  : build the layer-1 A operand in TMEM (voxel-feature gather + positional encoding),
-//                             then the epilogues TMEM -> regs (bias / per-ray term / leaky) -> bf16 hi|lo -> TMEM
-//   warp  8    MMA issuer   : one elected lane issues tcgen05.mma (A from TMEM, B = weights from smem), accumulators
-//                             in TMEM, completion via tcgen05.commit -> mbarrier
-//   warp  9    weight loader: streams the pre-packed bf16 weight chunks (8 KB, UMMA canonical K-major layout)
-//                             global/L2 -> smem ring with cp.async.bulk (TMA) + mbarrier complete_tx
+//   warps 0-15 "row warps"  : 4 warps per TMEM lane quadrant, each owning 32 of every 128 columns.  They build the
+//                             layer-1 A operand (voxel-feature gather + positional encoding) and run the epilogues
+//                             TMEM -> regs (bias / per-ray term / leaky) -> bf16 hi|lo -> TMEM (in place)
+//   warp 16    MMA issuer   : ONE elected thread issues every tcgen05.mma of the CTA from a fully static schedule
+//                             (weight-ring slot, mbarrier parity and all descriptors are compile-time constants);
+//                             completion via tcgen05.commit -> mbarrier
+//   warp 17    weight loader: ONE elected thread streams the pre-packed bf16 weight chunks (UMMA canonical K-major
+//                             layout) global/L2 -> smem ring with cp.async.bulk (TMA) + mbarrier complete_tx
 //
 // Precision: every fp32 operand x is split x = hi + lo (two bf16); a MAC is the 3 products hi*hi + lo*hi + hi*lo
-// accumulated in fp32 (~2^-16 relative), which is what keeps the result within 1e-3 of the fp32 reference.
+// accumulated in fp32 (~2^-16 relative), which is what keeps the result within 1e-3 of the fp32 reference (a single
+// bf16 or fp16 product is 3e-2 / 4e-3 off on the same inputs).
 //
 // Layer-1 operand A1 (K = 240): vox(128) | sincos enter(48) | sincos leave(48) | xyz enter, xyz leave, 10 x 0.
-// Its voxel part lives in TMEM (TS-mode MMA), its PE part in shared memory in the UMMA canonical layout (SS-mode MMA);
-// that split is what leaves TMEM room for TWO layer-1 half buffers, so epilogues overlap the next MMA batch.
+// Voxel k-steps 0-3 live in TMEM (TS-mode MMA); voxel k-steps 4-7 and the 7 PE k-steps live in shared memory in the
+// UMMA canonical layout (SS-mode MMA).
 // TMEM plan (512 columns x 128 lanes x 32 bit):
-//   [  0,128) AV : voxel k-steps, 8 x (8 cols hi | 8 cols lo)
+//   [  0, 64) AV : voxel k-steps 0-3, 4 x (8 cols hi | 8 cols lo)
+//   [ 64,128) Z  : layer-3 accumulator (64 fp32)
 //   [128,256) X0 : layer-1 output half 0, fp32 accumulator -> converted IN PLACE to the layer-2 operand (K half 0)
-//   [256,384) X1 : layer-1 output half 1, same; afterwards the layer-3 accumulator (64 cols)
+//   [256,384) X1 : layer-1 output half 1, same
 //   [384,512) Y  : layer-2 accumulator (128 fp32) -> converted in place to the layer-3 operand
-// MMA issue order per pass p (tensor pipe executes in order; Ex = epilogue of the row warps):
+// MMA issue order per pass p (the tensor pipe executes in order; Ex = epilogue of the row warps):
 //   S2(p): L1 half 1 -> X1   | E0(p) converts X0 meanwhile
 //   S1(p): L2 K-half 0 -> Y  | E1(p) converts X1 meanwhile
 //   S3(p): L2 K-half 1 -> Y
-//   S0(p+1): L1 half 0 of the NEXT pass -> X0   | E2(p) converts Y meanwhile
-//   S4(p): L3 -> X1[0,64)    | E3(p): layer-3 epilogue + layer-4 dot product
+//   S0(p+1): L1 half 0 of the NEXT pass (possibly of the next tile) -> X0   | E2(p) converts Y meanwhile
+//   S4(p): L3 -> Z           | E3(p): layer-3 epilogue + layer-4 dot product
+// The operand of the next tile is built by the row warps between E1 and E2 of a tile's last pass, as soon as the last
+// layer-1 MMA of the tile has retired, so the tensor pipe does not drain at tile boundaries.
+// Weight ring: 7 slots x 16 KB.  A pass consumes 28 fills (8 + 4 + 4 + 8 + 4) = exactly 4 ring rotations, so the slot
+// and parity of every fill are the same in every pass.
 #pragma once
 #include <cuda_bf16.h>
 
 #include "lidf_common.cuh"
 
-#define TC_KPE_MAX 112
-#define TC_THREADS 320
-#define TC_ROW_WARPS 8
+#define TC_ROW_WARPS 16
+#define TC_ROW_THREADS (TC_ROW_WARPS * 32)
+#define TC_THREADS ((TC_ROW_WARPS + 2) * 32)
 #define TC_CHUNK_BYTES 8192
 #define TC_CHUNKS_PER_DEC 50     // 15 (L1 half 0) + 15 (L1 half 1) + 8 (L2 K-half 0) + 8 (L2 K-half 1) + 4 (L3)
-#define TC_STAGES 16
+#define TC_STAGES 7
+#define TC_STAGE_BYTES 16384
+#define TC_FILLS_PER_PASS 28
 #define TC_K1_STEPS 15
-#define TC_COL_AV 0               // voxel part of the layer-1 operand: 8 k-steps x (8 cols hi | 8 cols lo)
+#define TC_COL_AV 0               // voxel k-steps 0-3 of the layer-1 operand: 4 x (8 cols hi | 8 cols lo)
+#define TC_COL_Z 64               // layer-3 accumulator
 #define TC_COL_X0 128             // layer-1 output half 0: accumulator -> (in place) layer-2 operand
-#define TC_COL_X1 256             // layer-1 output half 1; later the layer-3 accumulator (64 cols)
+#define TC_COL_X1 256             // layer-1 output half 1
 #define TC_COL_Y 384              // layer-2 accumulator -> (in place) layer-3 operand
+#define TC_VOX_TS 4               // voxel k-steps whose A operand is in TMEM
 #define TC_PE_KSTEPS 7
-#define TC_PE_PART_BYTES (TC_PE_KSTEPS * 4096)   // one part (hi or lo) of the PE operand tile: [kgroup(14)][128 rows][16 B]
+#define TC_SM_KSTEPS 11           // k-steps of the shared-memory operand tile: 7 PE + 4 voxel
+#define TC_A1S_PART_BYTES (TC_SM_KSTEPS * 4096)   // one part (hi or lo): [kstep][kgroup(2)][128 rows][16 B]
+#define TC_KPE_MAX 112            // widest per-pair PE block (2 x PE(pos)) the layer-1 operand layout holds
 #define TC_MAX_PASSES 9
 #define TC_SPIN_LIMIT (1u << 22)
 
@@ -333,6 +347,39 @@ __global__ void k_tc_selftest_pack(const float* __restrict__ W, uint8_t* __restr
 }
 
 // ------------------------------------------------------------------------------------------------ the engine
+namespace tc {
+__device__ __forceinline__ void mbar_wait_a(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_saddr), "r"(parity)
+        : "memory");
+    if (ok) break;
+    if (++spins > TC_SPIN_LIMIT) __trap();
+  }
+}
+__device__ __forceinline__ void commit_a(uint32_t bar_saddr) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_a(uint32_t bar_saddr) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(TC_ROW_THREADS) : "memory"); }
+}  // namespace tc
+
 struct TcArgs {
   int64_t P; int n_tiles;
   const int* perm; const int64_t* pair_vox; const int64_t* pair_ray;
@@ -351,41 +398,141 @@ struct TcArgs {
 };
 
 struct TcSmem {
-  uint8_t w[TC_STAGES][TC_CHUNK_BYTES];
-  uint8_t pe[2][TC_PE_PART_BYTES];   // PE part of the layer-1 operand: [hi|lo][kgroup(14)][128 rows][16 B]
+  uint8_t w[TC_STAGES][TC_STAGE_BYTES];
+  uint8_t a1[2][TC_A1S_PART_BYTES];  // smem part of the layer-1 operand: [hi|lo][kstep(11)][kgroup(2)][128 rows][16 B]
   float u[LIDF_H1];
   float b2[2][LIDF_H2];
   float b3[2][LIDF_H3];
   float w4[2][LIDF_H3];
   float b4[2];
-  float part[2][2][128];             // [parity][half][row] layer-4 partial sums
+  float part[2][4][128];             // [parity][column group][row] layer-4 partial sums
+  int m_orig[2][128];                // [tile parity][row] original pair index
+  float m_geo[2][6][128];            // [tile parity][enter xyz, dir xyz][row]
   uint64_t w_full[TC_STAGES], w_empty[TC_STAGES];
-  uint64_t a1_ready, a1_free, x_full[2], x_done[2], y_full, y_done;
+  uint64_t a1_ready, a1_free, x_full[2], x_done[2], y_full, y_done, z_full, z_free;
   uint32_t tmem_base;
 };
 
-// one k-step (K = 16) with the A operand in TMEM: a_tmem = 8 cols hi | 8 cols lo; w_saddr = [hi N x 32 B][lo N x 32 B]
+// everything the MMA issuer thread needs; descriptors are (base + compile-time constant)
+struct TcIssue {
+  uint32_t tmem;
+  uint32_t full0, empty0;            // smem addresses of w_full[0], w_empty[0]
+  uint64_t wd128, wd64;              // B descriptors of ring slot 0 for N = 128 / N = 64 chunks
+  uint64_t ad;                       // A descriptor of k-step 0 of the hi part of the smem operand tile
+};
+
+// one k-step (K = 16), A operand in TMEM (8 cols hi | 8 cols lo), N = 128: B = [hi 4 KB][lo 4 KB] at byte offset off
 template <int NPROD>
-__device__ __forceinline__ void tc_kstep_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t w_saddr, int N, uint32_t idesc,
-                                            bool first) {
-  const uint64_t bhi = tc::make_bdesc(w_saddr, (uint32_t)N * 16u, 128u);
-  tc::mma_ts(d_tmem, a_tmem, bhi, idesc, first ? 0u : 1u);
+__device__ __forceinline__ void tc_k_ts128(const TcIssue& c, uint32_t dcol, uint32_t acol, uint32_t off, bool first) {
+  constexpr uint32_t idesc = tc::make_idesc(128);
+  const uint64_t bhi = c.wd128 + (off >> 4);
+  tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi, idesc, first ? 0u : 1u);
   if (NPROD == 3) {
-    const uint64_t blo = tc::make_bdesc(w_saddr + (uint32_t)N * 32u, (uint32_t)N * 16u, 128u);
-    tc::mma_ts(d_tmem, a_tmem + 8, bhi, idesc, 1u);
-    tc::mma_ts(d_tmem, a_tmem, blo, idesc, 1u);
+    tc::mma_ts(c.tmem + dcol, c.tmem + acol + 8, bhi, idesc, 1u);
+    tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi + (4096u >> 4), idesc, 1u);
   }
 }
-// one k-step with the A operand in shared memory (canonical [kgroup(2)][128][16 B], hi and lo tiles), N = 128
+// same with the A operand in shared memory (k-step sk of the operand tile)
 template <int NPROD>
-__device__ __forceinline__ void tc_kstep_ss(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t w_saddr, uint32_t idesc,
-                                            bool first) {
-  const uint64_t ahi = tc::make_bdesc(a_hi, 2048u, 128u), bhi = tc::make_bdesc(w_saddr, 2048u, 128u);
-  tc::mma_ss(d_tmem, ahi, bhi, idesc, first ? 0u : 1u);
+__device__ __forceinline__ void tc_k_ss128(const TcIssue& c, uint32_t dcol, int sk, uint32_t off) {
+  constexpr uint32_t idesc = tc::make_idesc(128);
+  const uint64_t bhi = c.wd128 + (off >> 4);
+  const uint64_t ahi = c.ad + ((uint32_t)(sk * 4096) >> 4);
+  tc::mma_ss(c.tmem + dcol, ahi, bhi, idesc, 1u);
   if (NPROD == 3) {
-    const uint64_t alo = tc::make_bdesc(a_lo, 2048u, 128u), blo = tc::make_bdesc(w_saddr + 4096u, 2048u, 128u);
-    tc::mma_ss(d_tmem, alo, bhi, idesc, 1u);
-    tc::mma_ss(d_tmem, ahi, blo, idesc, 1u);
+    tc::mma_ss(c.tmem + dcol, ahi + ((uint32_t)TC_A1S_PART_BYTES >> 4), bhi, idesc, 1u);
+    tc::mma_ss(c.tmem + dcol, ahi, bhi + (4096u >> 4), idesc, 1u);
+  }
+}
+// layer 3: A in TMEM, N = 64: B = [hi 2 KB][lo 2 KB] at byte offset off
+template <int NPROD>
+__device__ __forceinline__ void tc_k_ts64(const TcIssue& c, uint32_t dcol, uint32_t acol, uint32_t off, bool first) {
+  constexpr uint32_t idesc = tc::make_idesc(64);
+  const uint64_t bhi = c.wd64 + (off >> 4);
+  tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi, idesc, first ? 0u : 1u);
+  if (NPROD == 3) {
+    tc::mma_ts(c.tmem + dcol, c.tmem + acol + 8, bhi, idesc, 1u);
+    tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi + (2048u >> 4), idesc, 1u);
+  }
+}
+
+// Fill GI (index in the static schedule) lives in ring slot GI % 7 and is the (GI / 7)-th use of that slot.
+#define TC_SLOT(gi) ((gi) % TC_STAGES)
+#define TC_PAR(gi) ((uint32_t)(((gi) / TC_STAGES) & 1))
+
+// layer 1, one output half (15 k-steps = 7 fills of 2 + 1 fill of 1), fills GI0 .. GI0+7
+template <int NPROD, int GI0>
+__device__ __forceinline__ void tc_issue_l1(const TcIssue& c, uint32_t dcol) {
+#pragma unroll
+  for (int sg = 0; sg < 8; ++sg) {
+    const int gi = GI0 + sg, slot = TC_SLOT(gi);
+    tc::mbar_wait_a(c.full0 + 8 * slot, TC_PAR(gi));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ks = 2 * sg + j;
+      if (ks < TC_K1_STEPS) {
+        const uint32_t off = (uint32_t)(slot * TC_STAGE_BYTES + j * TC_CHUNK_BYTES);
+        if (ks < TC_VOX_TS) tc_k_ts128<NPROD>(c, dcol, TC_COL_AV + 16 * ks, off, ks == 0);
+        else tc_k_ss128<NPROD>(c, dcol, ks < 8 ? TC_PE_KSTEPS + (ks - TC_VOX_TS) : ks - 8, off);
+      }
+    }
+    tc::commit_a(c.empty0 + 8 * slot);
+  }
+}
+// layer 2, one K half (8 k-steps = 4 fills), operand = converted layer-1 half at acol, accumulator Y
+template <int NPROD, int GI0>
+__device__ __forceinline__ void tc_issue_l2(const TcIssue& c, uint32_t acol, bool first_half) {
+#pragma unroll
+  for (int sg = 0; sg < 4; ++sg) {
+    const int gi = GI0 + sg, slot = TC_SLOT(gi);
+    tc::mbar_wait_a(c.full0 + 8 * slot, TC_PAR(gi));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ks = 2 * sg + j;
+      tc_k_ts128<NPROD>(c, TC_COL_Y, acol + 16 * ks, (uint32_t)(slot * TC_STAGE_BYTES + j * TC_CHUNK_BYTES),
+                        first_half && ks == 0);
+    }
+    tc::commit_a(c.empty0 + 8 * slot);
+  }
+}
+// layer 3 (K = 128, N = 64: 4 fills of 8 KB = 2 k-steps each), operand = converted Y, accumulator Z
+template <int NPROD, int GI0>
+__device__ __forceinline__ void tc_issue_l3(const TcIssue& c) {
+#pragma unroll
+  for (int sg = 0; sg < 4; ++sg) {
+    const int gi = GI0 + sg, slot = TC_SLOT(gi);
+    tc::mbar_wait_a(c.full0 + 8 * slot, TC_PAR(gi));
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int ks = 2 * sg + j;
+      tc_k_ts64<NPROD>(c, TC_COL_Z, TC_COL_Y + 16 * ks, (uint32_t)(slot * TC_STAGE_BYTES + j * 4096), ks == 0);
+    }
+    tc::commit_a(c.empty0 + 8 * slot);
+  }
+}
+// consume fills without issuing MMAs (keeps the static schedule aligned on the very last pass of the CTA)
+template <int GI0, int N>
+__device__ __forceinline__ void tc_drain(const TcIssue& c) {
+#pragma unroll
+  for (int sg = 0; sg < N; ++sg) {
+    const int gi = GI0 + sg, slot = TC_SLOT(gi);
+    tc::mbar_wait_a(c.full0 + 8 * slot, TC_PAR(gi));
+    tc::mbar_arrive_a(c.empty0 + 8 * slot);
+  }
+}
+
+// loader side of the same static schedule: N fills starting at GI0; `pairs` fills are 16 KB, the rest 8 KB
+template <int GI0, int N, int PAIRS>
+__device__ __forceinline__ void tc_load_seg(TcSmem& S, const uint8_t* src, bool ring_primed) {
+#pragma unroll
+  for (int sg = 0; sg < N; ++sg) {
+    const int gi = GI0 + sg, slot = TC_SLOT(gi);
+    const uint32_t bytes = sg < PAIRS ? TC_STAGE_BYTES : TC_CHUNK_BYTES;
+    // previous use of this slot was fill gi - 7: wait for its release (skip while the ring fills for the first time)
+    if (ring_primed || gi >= TC_STAGES) tc::mbar_wait(&S.w_empty[slot], TC_PAR(gi) ^ 1u);
+    tc::mbar_arrive_expect_tx(&S.w_full[slot], bytes);
+    tc::bulk_g2s(S.w[slot], src, bytes, &S.w_full[slot]);
+    src += bytes;
   }
 }
 
@@ -410,206 +557,150 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.x_full[i], 1); tc::mbar_init(&S.x_done[i], TC_ROW_WARPS); }
     tc::mbar_init(&S.y_full, 1);
     tc::mbar_init(&S.y_done, TC_ROW_WARPS);
+    tc::mbar_init(&S.z_full, 1);
+    tc::mbar_init(&S.z_free, TC_ROW_WARPS);
     tc::fence_barrier_init();
   }
-  if (warp == 8) tc::tmem_alloc(&S.tmem_base, 512);
+  if (warp == TC_ROW_WARPS) tc::tmem_alloc(&S.tmem_base, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = S.tmem_base;
-  const int n_pass_total = a.n_pass[0] + a.n_pass[1];
-  // weight-stream segments of one decoder (chunk ranges), in stream order
+  const int npt = a.n_pass[0] + a.n_pass[1];                                   // passes per tile
+  const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int total_passes = n_my_tiles * npt;
+  // weight-stream segments of one decoder (chunk offsets)
   constexpr int SEG_L1H0 = 0, SEG_L1H1 = 15, SEG_L2K0 = 30, SEG_L2K1 = 38, SEG_L3 = 46;
+  // static fill schedule: prologue S0 = fills 0..7; a pass = fills 8..35 (+ 28 per pass: same slots, same parities)
+  constexpr int GI_S2 = 8, GI_S1 = 16, GI_S3 = 20, GI_S0 = 24, GI_S4 = 32;
 
-  if (warp == 9) {
-    // ================================ weight loader (TMA) ================================
-    // emits chunks in the order the MMA issuer consumes them:
-    //   L1h0(pass 0), then per pass p: L1h1(p), L2k0(p), L2k1(p), L1h0(p+1) [if any], L3(p)
-    const bool leader = tc::elect_one();
-    uint32_t f = 0;                        // fill counter: stage = f % 16, fill number of that stage = f / 16
-    auto emit = [&](int d, int c0, int n) {
-      const uint8_t* src = a.wstream + ((size_t)d * TC_CHUNKS_PER_DEC + c0) * TC_CHUNK_BYTES;
-      for (int c = 0; c < n; ++c, ++f) {
-        const uint32_t stg = f % TC_STAGES;
-        if (f >= TC_STAGES) tc::mbar_wait(&S.w_empty[stg], ((f / TC_STAGES) - 1) & 1);
-        if (leader) {
-          tc::mbar_arrive_expect_tx(&S.w_full[stg], TC_CHUNK_BYTES);
-          tc::bulk_g2s(S.w[stg], src + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[stg]);
-        }
-        __syncwarp();
-      }
-    };
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      emit(0 < a.n_pass[0] ? 0 : 1, SEG_L1H0, 15);
-      for (int p = 0; p < n_pass_total; ++p) {
+  if (warp == TC_ROW_WARPS + 1) {
+    // ================================ weight loader (TMA), one thread ================================
+    if (tc::elect_one()) {
+      auto seg = [&](int d, int chunk) { return a.wstream + ((size_t)d * TC_CHUNKS_PER_DEC + chunk) * TC_CHUNK_BYTES; };
+      const int d_first = a.n_pass[0] > 0 ? 0 : 1;
+      tc_load_seg<0, 8, 7>(S, seg(d_first, SEG_L1H0), false);
+      int p = 0;
+      for (int gp = 0; gp < total_passes; ++gp) {
         const int d = p < a.n_pass[0] ? 0 : 1;
-        emit(d, SEG_L1H1, 15);
-        emit(d, SEG_L2K0, 8);
-        emit(d, SEG_L2K1, 8);
-        if (p + 1 < n_pass_total) emit(p + 1 < a.n_pass[0] ? 0 : 1, SEG_L1H0, 15);
-        emit(d, SEG_L3, 4);
+        const int pn = p + 1 == npt ? 0 : p + 1;
+        const int dn = pn < a.n_pass[0] ? 0 : 1;
+        tc_load_seg<GI_S2, 8, 7>(S, seg(d, SEG_L1H1), gp > 0);
+        tc_load_seg<GI_S1, 4, 4>(S, seg(d, SEG_L2K0), true);
+        tc_load_seg<GI_S3, 4, 4>(S, seg(d, SEG_L2K1), true);
+        tc_load_seg<GI_S0, 8, 7>(S, seg(dn, SEG_L1H0), true);                  // drained unused after the last pass
+        tc_load_seg<GI_S4, 4, 0>(S, seg(d, SEG_L3), true);
+        p = pn;
       }
     }
-  } else if (warp == 8) {
-    // ================================ MMA issuer ================================
-    // The whole warp stays converged (uniform control flow, uniform operands); one elected lane issues.
-    const bool leader = tc::elect_one();
-    constexpr uint32_t idesc128 = tc::make_idesc(128), idesc64 = tc::make_idesc(64);
-    const uint32_t wbase = tc::smem_u32(S.w[0]);
-    const uint32_t pe_hi = tc::smem_u32(S.pe[0]), pe_lo = tc::smem_u32(S.pe[1]);
-    uint32_t f = 0;                                   // chunks consumed
-    uint32_t ph_a1 = 0, ph_xd0 = 0, ph_xd1 = 0, ph_yd = 0;
-    bool x1_used = false;                             // has X1 ever held a layer-3 accumulator?
-    auto wait_chunk = [&]() -> uint32_t {
-      tc::mbar_wait(&S.w_full[f % TC_STAGES], (f / TC_STAGES) & 1);
-      return wbase + (f % TC_STAGES) * TC_CHUNK_BYTES;
-    };
-    auto release_chunk = [&]() {
-      if (leader) tc::commit(&S.w_empty[f % TC_STAGES]);
-      __syncwarp();
-      ++f;
-    };
-    auto issue_l1 = [&](uint32_t dcol) {              // 8 voxel k-steps (A in TMEM) + 7 PE k-steps (A in smem)
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t w = wait_chunk();
-        if (leader) tc_kstep_ts<NPROD>(tmem + dcol, tmem + TC_COL_AV + 16 * ks, w, 128, idesc128, ks == 0);
-        release_chunk();
-      }
-#pragma unroll
-      for (int ks = 0; ks < TC_PE_KSTEPS; ++ks) {
-        const uint32_t w = wait_chunk();
-        if (leader) tc_kstep_ss<NPROD>(tmem + dcol, pe_hi + ks * 4096, pe_lo + ks * 4096, w, idesc128, false);
-        release_chunk();
-      }
-    };
-    auto issue_l2 = [&](uint32_t acol, bool first_half) {
-#pragma unroll
-      for (int ks = 0; ks < 8; ++ks) {
-        const uint32_t w = wait_chunk();
-        if (leader) tc_kstep_ts<NPROD>(tmem + TC_COL_Y, tmem + acol + 16 * ks, w, 128, idesc128, first_half && ks == 0);
-        release_chunk();
-      }
-    };
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      tc::mbar_wait(&S.a1_ready, ph_a1); ph_a1 ^= 1;
+  } else if (warp == TC_ROW_WARPS) {
+    // ================================ MMA issuer, one thread ================================
+    if (tc::elect_one()) {
+      TcIssue c;
+      c.tmem = tmem;
+      c.full0 = tc::smem_u32(&S.w_full[0]);
+      c.empty0 = tc::smem_u32(&S.w_empty[0]);
+      c.wd128 = tc::make_bdesc(tc::smem_u32(S.w[0]), 2048u, 128u);
+      c.wd64 = tc::make_bdesc(tc::smem_u32(S.w[0]), 1024u, 128u);
+      c.ad = tc::make_bdesc(tc::smem_u32(S.a1[0]), 2048u, 128u);
+      tc::mbar_wait(&S.a1_ready, 0);
       tc::fence_after_sync();
-      issue_l1(TC_COL_X0);                            // S0(pass 0)
-      if (leader) tc::commit(&S.x_full[0]);
-      __syncwarp();
-      for (int p = 0; p < n_pass_total; ++p) {
-        // S2(p): layer 1, output half 1 -> X1 (the previous layer-3 accumulator must have been read: E3)
-        if (x1_used) { tc::mbar_wait(&S.x_done[1], ph_xd1); ph_xd1 ^= 1; }
-        tc::fence_after_sync();
-        issue_l1(TC_COL_X1);
-        if (leader) {
-          tc::commit(&S.x_full[1]);
-          if (p == n_pass_total - 1) tc::commit(&S.a1_free);   // last reader of the layer-1 operand of this tile
-        }
-        __syncwarp();
+      tc_issue_l1<NPROD, 0>(c, TC_COL_X0);                                     // S0 of the first pass
+      tc::commit(&S.x_full[0]);
+      int p = 0;
+      uint32_t tl = 0;                                                         // tiles whose operand has been consumed
+      for (int gp = 0; gp < total_passes; ++gp) {
+        const uint32_t ph = (uint32_t)gp & 1u;
+        const bool last_of_tile = p + 1 == npt;
+        // S2(p): layer 1, output half 1 -> X1 (its previous reader S3(p-1) precedes it in the in-order pipe)
+        tc_issue_l1<NPROD, GI_S2>(c, TC_COL_X1);
+        tc::commit(&S.x_full[1]);
+        if (last_of_tile) tc::commit(&S.a1_free);                             // last reader of this tile's layer-1 operand
         // S1(p): layer 2, K half 0 (X0 converted in place by E0) -> Y
-        tc::mbar_wait(&S.x_done[0], ph_xd0); ph_xd0 ^= 1;
+        tc::mbar_wait(&S.x_done[0], ph);
         tc::fence_after_sync();
-        issue_l2(TC_COL_X0, true);
+        tc_issue_l2<NPROD, GI_S1>(c, TC_COL_X0, true);
         // S3(p): layer 2, K half 1 (X1 converted by E1) -> Y
-        tc::mbar_wait(&S.x_done[1], ph_xd1); ph_xd1 ^= 1;
+        tc::mbar_wait(&S.x_done[1], ph);
         tc::fence_after_sync();
-        issue_l2(TC_COL_X1, false);
-        if (leader) tc::commit(&S.y_full);
-        __syncwarp();
+        tc_issue_l2<NPROD, GI_S3>(c, TC_COL_X1, false);
+        tc::commit(&S.y_full);
         // S0(p+1): layer 1, output half 0 of the next pass -> X0 (free: S1(p) precedes it in the in-order pipe)
-        if (p + 1 < n_pass_total) {
-          issue_l1(TC_COL_X0);
-          if (leader) tc::commit(&S.x_full[0]);
-          __syncwarp();
-        }
-        // S4(p): layer 3 (N = 64, two k-steps per chunk), operand = Y converted by E2, accumulator -> X1[0,64)
-        tc::mbar_wait(&S.y_done, ph_yd); ph_yd ^= 1;
-        tc::fence_after_sync();
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-          const uint32_t w = wait_chunk();
-          if (leader) {
-#pragma unroll
-            for (int j = 0; j < 2; ++j)
-              tc_kstep_ts<NPROD>(tmem + TC_COL_X1, tmem + TC_COL_Y + 16 * (2 * cc + j), w + j * 64 * 64, 64, idesc64,
-                                 cc == 0 && j == 0);
+        if (gp + 1 < total_passes) {
+          if (last_of_tile) {
+            ++tl;
+            tc::mbar_wait(&S.a1_ready, tl & 1u);                               // operand of the next tile
+            tc::fence_after_sync();
           }
-          release_chunk();
+          tc_issue_l1<NPROD, GI_S0>(c, TC_COL_X0);
+          tc::commit(&S.x_full[0]);
+        } else {
+          tc_drain<GI_S0, 8>(c);
         }
-        if (leader) tc::commit(&S.x_full[1]);
-        __syncwarp();
-        x1_used = true;
+        // S4(p): layer 3, operand = Y converted by E2, accumulator Z (E3 of the previous pass must have read Z)
+        tc::mbar_wait(&S.y_done, ph);
+        if (gp > 0) tc::mbar_wait(&S.z_free, ph ^ 1u);
+        tc::fence_after_sync();
+        tc_issue_l3<NPROD, GI_S4>(c);
+        tc::commit(&S.z_full);
+        p = last_of_tile ? 0 : p + 1;
       }
     }
   } else {
     // ================================ row warps: operand build + epilogues ================================
-    const int q = warp & 3, h = warp >> 2;
+    const int q = warp & 3, g = warp >> 2;            // TMEM lane quadrant, column group
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t pe_row[2] = {tc::smem_u32(S.pe[0]) + row * 16, tc::smem_u32(S.pe[1]) + row * 16};
-    uint32_t ph_xf0 = 0, ph_xf1 = 0, ph_yf = 0, ph_a1f = 0, par = 0;
-    bool first_tile = true;
-    // store one k-step (16 values) of the PE operand tile: hi/lo x kgroup 0/1, 16 B each
-    auto st_pe = [&](int ks, const uint32_t* w) {
-      tc::st_shared_v4(pe_row[0] + (2 * ks) * 2048, w[0], w[1], w[2], w[3]);
-      tc::st_shared_v4(pe_row[0] + (2 * ks + 1) * 2048, w[4], w[5], w[6], w[7]);
-      tc::st_shared_v4(pe_row[1] + (2 * ks) * 2048, w[8], w[9], w[10], w[11]);
-      tc::st_shared_v4(pe_row[1] + (2 * ks + 1) * 2048, w[12], w[13], w[14], w[15]);
+    const uint32_t a1row_hi = tc::smem_u32(S.a1[0]) + row * 16, a1row_lo = tc::smem_u32(S.a1[1]) + row * 16;
+    // store one k-step (8 hi words | 8 lo words) of the smem operand tile: hi/lo x kgroup 0/1, 16 B each
+    auto st_a1 = [&](int sk, const uint32_t* w) {
+      tc::st_shared_v4(a1row_hi + sk * 4096, w[0], w[1], w[2], w[3]);
+      tc::st_shared_v4(a1row_hi + sk * 4096 + 2048, w[4], w[5], w[6], w[7]);
+      tc::st_shared_v4(a1row_lo + sk * 4096, w[8], w[9], w[10], w[11]);
+      tc::st_shared_v4(a1row_lo + sk * 4096 + 2048, w[12], w[13], w[14], w[15]);
     };
-    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x) {
-      // ---- row metadata ----
+    struct RowMeta { int orig, vox, ray; float t0, t1; bool valid; };
+    auto load_meta = [&](int tile) {
+      RowMeta m{0, 0, 0, 0.f, 0.f, false};
       const int64_t s = (int64_t)tile * 128 + row;
-      const bool valid = s < a.P;
-      int orig = 0, vox = 0, ray = 0;
-      float dir[3] = {0.f, 0.f, 0.f}, enter[3] = {0.f, 0.f, 0.f}, pin[3] = {0.f, 0.f, 0.f};
-      float pin_other[3] = {0.f, 0.f, 0.f};
-      if (valid) {
-        orig = a.perm ? a.perm[s] : (int)s;
-        vox = (int)a.pair_vox[orig]; ray = (int)a.pair_ray[orig];
-        float t0, t1;
-        if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)orig); t0 = t.x; t1 = t.y; }
-        else { const size_t o = ((size_t)vox * a.R + ray) * 2; t0 = a.dense_dist[o]; t1 = a.dense_dist[o + 1]; }
+      if (s < a.P) {
+        m.valid = true;
+        m.orig = a.perm ? a.perm[s] : (int)s;
+        m.vox = (int)a.pair_vox[m.orig]; m.ray = (int)a.pair_ray[m.orig];
+        if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)m.orig); m.t0 = t.x; m.t1 = t.y; }
+        else { const size_t o = ((size_t)m.vox * a.R + m.ray) * 2; m.t0 = a.dense_dist[o]; m.t1 = a.dense_dist[o + 1]; }
+      }
+      return m;
+    };
+    // layer-1 operand of one tile.  Column group 0 encodes the enter position, 1 the leave position, 2 loads voxel
+    // k-steps 0-3 (-> TMEM) and the raw xyz k-step, 3 loads voxel k-steps 4-7 (-> smem).
+    auto build_a1 = [&](const RowMeta& m, int buf) {
+      float dir[3] = {0.f, 0.f, 0.f}, enter[3] = {0.f, 0.f, 0.f}, pe[3] = {0.f, 0.f, 0.f}, pl[3] = {0.f, 0.f, 0.f};
+      if (m.valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          dir[k] = a.ray_dir[(size_t)ray * 3 + k];
-          const float c = a.rel ? (a.voxel_bound[(size_t)vox * 6 + k] + a.voxel_bound[(size_t)vox * 6 + 3 + k]) / 2.0f : 0.f;
-          enter[k] = dir[k] * t0;
-          const float pe = enter[k] - c, pl = dir[k] * t1 - c;
-          pin[k] = h == 0 ? pe : pl;            // this half encodes enter (h=0) or leave (h=1)
-          pin_other[k] = h == 0 ? pl : pe;
+          dir[k] = a.ray_dir[(size_t)m.ray * 3 + k];
+          const float c = a.rel ? (a.voxel_bound[(size_t)m.vox * 6 + k] + a.voxel_bound[(size_t)m.vox * 6 + 3 + k]) / 2.0f : 0.f;
+          enter[k] = dir[k] * m.t0;
+          pe[k] = enter[k] - c;
+          pl[k] = dir[k] * m.t1 - c;
         }
       }
-      // ---- build the layer-1 operand (previous tile's layer-1 MMAs must be done with it) ----
-      if (!first_tile) { tc::mbar_wait(&S.a1_free, ph_a1f); ph_a1f ^= 1; }
-      first_tile = false;
-      tc::fence_after_sync();
-      {
-        const uint4* vrow = reinterpret_cast<const uint4*>(a.voxtab + (size_t)vox * 128);
-#pragma unroll
-        for (int s4 = 0; s4 < 4; ++s4) {                 // voxel k-steps 4h .. 4h+3 -> TMEM
-          const int ks = 4 * h + s4;
-          uint32_t w[16];
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 t = make_uint4(0u, 0u, 0u, 0u);
-            if (valid) t = __ldg(vrow + ks * 4 + v4);
-            w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
-          }
-          tc::tmem_st16(lane_addr + TC_COL_AV + 16 * ks, w);
-        }
-        // positional encoding of this half's position: accurate sincos at f = 1 and f = 16, three exact-form
-        // double-angle steps after each (sin 2x = 2 s c, cos 2x = 1 - 2 s^2)
+      const uint4* vrow = reinterpret_cast<const uint4*>(a.voxtab + (size_t)m.vox * 128);
+      if (g < 2) {
+        // positional encoding: accurate sincos at f = 1 and f = 16, three exact-form double-angle steps after each
+        // (sin 2x = 2 s c, cos 2x = 1 - 2 s^2)
         float v[48];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
+          const float pin = g == 0 ? pe[c] : pl[c];
 #pragma unroll
-          for (int g = 0; g < 2; ++g) {
+          for (int fg = 0; fg < 2; ++fg) {
             float sn, cs;
-            sincosf(pin[c] * (g ? 16.0f : 1.0f), &sn, &cs);
+            sincosf(pin * (fg ? 16.0f : 1.0f), &sn, &cs);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
-              const int k = 4 * g + kk;
+              const int k = 4 * fg + kk;
               v[6 * k + c] = sn; v[6 * k + 3 + c] = cs;
               const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;
               sn = s2; cs = c2;
@@ -617,135 +708,206 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           }
         }
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {                    // PE k-steps 3h + j -> smem operand tile
+        for (int j = 0; j < 3; ++j) {
           uint32_t w[16];
           tc::split16(v + 16 * j, w);
-          st_pe(3 * h + j, w);
+          st_a1(3 * g + j, w);
         }
-        if (h == 0) {                                    // PE k-step 6: raw xyz of enter, leave, zero padding
+      } else if (g == 2) {
+#pragma unroll
+        for (int ks = 0; ks < TC_VOX_TS; ++ks) {
+          uint32_t w[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (m.valid) t = __ldg(vrow + ks * 4 + v4);
+            w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
+          }
+          tc::tmem_st16(lane_addr + TC_COL_AV + 16 * ks, w);
+        }
+        {
           float x[16];
 #pragma unroll
           for (int k = 0; k < 16; ++k) x[k] = 0.f;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) { x[k] = pin[k]; x[3 + k] = pin_other[k]; }
+          for (int k = 0; k < 3; ++k) { x[k] = pe[k]; x[3 + k] = pl[k]; }
           uint32_t w[16];
           tc::split16(x, w);
-          st_pe(6, w);
+          st_a1(6, w);
         }
+        S.m_orig[buf][row] = m.orig;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { S.m_geo[buf][k][row] = enter[k]; S.m_geo[buf][3 + k][row] = dir[k]; }
         tc::wait_st();
-        tc::fence_proxy_async();
+      } else {
+#pragma unroll
+        for (int ks = TC_VOX_TS; ks < 8; ++ks) {
+          uint32_t w[16];
+#pragma unroll
+          for (int v4 = 0; v4 < 4; ++v4) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (m.valid) t = __ldg(vrow + ks * 4 + v4);
+            w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
+          }
+          st_a1(TC_PE_KSTEPS + (ks - TC_VOX_TS), w);
+        }
       }
+      tc::fence_proxy_async();
       tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.a1_ready);
+    };
 
-      // ---- decoder passes ----
-      float off_val = 0.f;
-      for (int d = 0; d < 2; ++d) {
-        float o = a.kind[d] == LIDF_DEC_IEF ? a.o0 : 0.f;
-        for (int it = 0; it < a.n_pass[d]; ++it) {
-          const float delta = o - a.o0;                   // IEF: T already holds u*o0 + c
-          const bool rank1 = a.kind[d] == LIDF_DEC_IEF && it > 0;
-          // E0 / E1: layer-1 epilogue of output half hf (buffer X0 / X1); this warp converts columns [64 h, 64 h + 64)
+    RowMeta cur = load_meta((int)blockIdx.x);
+    build_a1(cur, 0);
+    int ray = cur.ray;
+    bool valid = cur.valid;
+    uint32_t gp = 0, tl = 0, par = 0;
+    for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
+      const int next_tile = tile + (int)gridDim.x;
+      const bool has_next = next_tile < a.n_tiles;
+      RowMeta nxt{0, 0, 0, 0.f, 0.f, false};
+      float o = 0.f, res0 = 0.f, res1 = 0.f;
+      for (int p = 0; p < npt; ++p, ++gp) {
+        const int d = p < a.n_pass[0] ? 0 : 1;
+        const int it = d == 0 ? p : p - a.n_pass[0];
+        const uint32_t ph = gp & 1u;
+        const bool is_ief = a.kind[d] == LIDF_DEC_IEF;
+        if (it == 0) o = is_ief ? a.o0 : 0.f;
+        const bool last = p + 1 == npt;
+        if (last && has_next) nxt = load_meta(next_tile);                      // prefetch: consumed after E1
+        const float delta = o - a.o0;                                         // IEF: T already holds u*o0 + c
+        const bool rank1 = is_ief && it > 0;
+        const float* trow = a.T + (size_t)ray * 512 + 256 * d + 32 * g;
+        // ---- E0 / E1: layer-1 epilogue of output half hf (X0 / X1); this thread converts columns [32 g, 32 g + 32)
+        float4 t[8];
 #pragma unroll
-          for (int hf = 0; hf < 2; ++hf) {
-            const int n0 = 128 * hf + 64 * h;
-            const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 64 * h;
-            float4 t[16];
-            {
-              const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)ray * 512 + 256 * d + n0);
+        for (int i = 0; i < 8; ++i) t[i] = valid ? __ldg(reinterpret_cast<const float4*>(trow) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
-              for (int i = 0; i < 16; ++i) t[i] = valid ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            }
-            if (hf == 0) { tc::mbar_wait(&S.x_full[0], ph_xf0); ph_xf0 ^= 1; }
-            else { tc::mbar_wait(&S.x_full[1], ph_xf1); ph_xf1 ^= 1; }
-            tc::fence_after_sync();
-#pragma unroll
-            for (int cc = 0; cc < 2; ++cc) {
-              uint32_t r[32];
-              tc::tmem_ld32(lane_addr + xcol + 32 * cc, r);
-              tc::wait_ld();
-              float x[32];
-#pragma unroll
-              for (int j = 0; j < 32; ++j) {
-                const float4 tv = t[8 * cc + (j >> 2)];
-                const float tj = (j & 3) == 0 ? tv.x : (j & 3) == 1 ? tv.y : (j & 3) == 2 ? tv.z : tv.w;
-                float val = __uint_as_float(r[j]) + tj;
-                if (rank1) val = fmaf(S.u[n0 + 32 * cc + j], delta, val);
-                x[j] = lidf_leaky(val);
-              }
-              uint32_t w[16];
-              tc::split16(x, w);
-              tc::tmem_st16(lane_addr + xcol + 32 * cc, w);
-              tc::split16(x + 16, w);
-              tc::tmem_st16(lane_addr + xcol + 32 * cc + 16, w);
-            }
-            tc::wait_st();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
-          }
-          // E2: layer-2 epilogue on Y
-          tc::mbar_wait(&S.y_full, ph_yf); ph_yf ^= 1;
+        for (int hf = 0; hf < 2; ++hf) {
+          const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
+          tc::mbar_wait(&S.x_full[hf], ph);
           tc::fence_after_sync();
+          uint32_t r[32];
+          tc::tmem_ld32(lane_addr + xcol, r);
+          tc::wait_ld();
+          float x[32];
+          if (rank1) {
+            const float4* up = reinterpret_cast<const float4*>(&S.u[128 * hf + 32 * g]);
 #pragma unroll
-          for (int cc = 0; cc < 2; ++cc) {
-            uint32_t r[32];
-            tc::tmem_ld32(lane_addr + TC_COL_Y + 64 * h + 32 * cc, r);
-            tc::wait_ld();
-            float x[32];
+            for (int i = 0; i < 8; ++i) {
+              const float4 uv = up[i];
+              x[4 * i + 0] = lidf_leaky(fmaf(uv.x, delta, __uint_as_float(r[4 * i + 0]) + t[i].x));
+              x[4 * i + 1] = lidf_leaky(fmaf(uv.y, delta, __uint_as_float(r[4 * i + 1]) + t[i].y));
+              x[4 * i + 2] = lidf_leaky(fmaf(uv.z, delta, __uint_as_float(r[4 * i + 2]) + t[i].z));
+              x[4 * i + 3] = lidf_leaky(fmaf(uv.w, delta, __uint_as_float(r[4 * i + 3]) + t[i].w));
+            }
+          } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) x[j] = lidf_leaky(__uint_as_float(r[j]) + S.b2[d][64 * h + 32 * cc + j]);
-            uint32_t w[16];
-            tc::split16(x, w);
-            tc::tmem_st16(lane_addr + TC_COL_Y + 64 * h + 32 * cc, w);
-            tc::split16(x + 16, w);
-            tc::tmem_st16(lane_addr + TC_COL_Y + 64 * h + 32 * cc + 16, w);
+            for (int i = 0; i < 8; ++i) {
+              x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + t[i].x);
+              x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + t[i].y);
+              x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + t[i].z);
+              x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + t[i].w);
+            }
           }
+          if (hf == 0) {                                                       // per-ray term of half 1: in flight during the stores
+#pragma unroll
+            for (int i = 0; i < 8; ++i) t[i] = valid ? __ldg(reinterpret_cast<const float4*>(trow + 128) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
+          uint32_t w[16];
+          tc::split16(x, w);
+          tc::tmem_st16(lane_addr + xcol, w);
+          tc::split16(x + 16, w);
+          tc::tmem_st16(lane_addr + xcol + 16, w);
+          tc::wait_st();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
+        }
+        // ---- operand of the next tile: its last reader (S2 of this pass) has retired once a1_free completes
+        if (last && has_next) {
+          tc::mbar_wait(&S.a1_free, tl & 1u);
+          tc::fence_after_sync();
+          build_a1(nxt, (int)((tl + 1) & 1u));
+        }
+        // ---- E2: layer-2 epilogue on Y
+        {
+          tc::mbar_wait(&S.y_full, ph);
+          tc::fence_after_sync();
+          uint32_t r[32];
+          tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
+          tc::wait_ld();
+          float x[32];
+          const float4* bp = reinterpret_cast<const float4*>(&S.b2[d][32 * g]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const float4 bv = bp[i];
+            x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + bv.x);
+            x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + bv.y);
+            x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + bv.z);
+            x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + bv.w);
+          }
+          uint32_t w[16];
+          tc::split16(x, w);
+          tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g, w);
+          tc::split16(x + 16, w);
+          tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16, w);
           tc::wait_st();
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&S.y_done);
-          // E3: layer-3 epilogue + layer 4 (64-term dot product, 32 terms per half) on X1[0,64)
-          tc::mbar_wait(&S.x_full[1], ph_xf1); ph_xf1 ^= 1;
-          tc::fence_after_sync();
-          float partial = 0.f;
-          {
-            uint32_t r[32];
-            tc::tmem_ld32(lane_addr + TC_COL_X1 + 32 * h, r);
-            tc::wait_ld();
-            tc::fence_before_sync();
-            __syncwarp();
-            if (lane == 0) tc::mbar_arrive(&S.x_done[1]);   // X1 is free again for the next pass's layer 1
-#pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              const int n = 32 * h + j;
-              partial = fmaf(lidf_leaky(__uint_as_float(r[j]) + S.b3[d][n]), S.w4[d][n], partial);
-            }
-          }
-          S.part[par][h][row] = partial;
-          asm volatile("bar.sync 1, 256;" ::: "memory");     // the 8 row warps only
-          const float l4 = S.part[par][0][row] + S.part[par][1][row] + S.b4[d];
-          par ^= 1;
-          if (a.kind[d] == LIDF_DEC_IEF) o += l4; else o = l4;
         }
-        const float res = lidf_final_act(o, a.use_sigmoid[d]);
-        if (d == 0) off_val = res;
-        if (valid && h == 0) a.out[d][orig] = res;
-      }
-      if (valid && h == 0) {
-        float sc = off_val * (a.r1 - a.r0) + a.r0;         // pipeline.py:437-439
-        sc = sc * a.sqrt3;
-        sc = sc * a.part;
+        // ---- E3: layer-3 epilogue + layer 4 (64-term dot product, 16 terms per column group) on Z
+        {
+          tc::mbar_wait(&S.z_full, ph);
+          tc::fence_after_sync();
+          uint32_t r[16];
+          tc::tmem_ld16(lane_addr + TC_COL_Z + 16 * g, r);
+          tc::wait_ld();
+          tc::fence_before_sync();
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&S.z_free);                           // Z may be overwritten by the next pass
+          float partial = 0.f;
 #pragma unroll
-        for (int k = 0; k < 3; ++k) a.pos_out[(size_t)orig * 3 + k] = enter[k] + sc * dir[k];
+          for (int j = 0; j < 16; ++j) {
+            const int n = 16 * g + j;
+            partial = fmaf(lidf_leaky(__uint_as_float(r[j]) + S.b3[d][n]), S.w4[d][n], partial);
+          }
+          S.part[par][g][row] = partial;
+          tc::bar_rows();                                                      // the 16 row warps only
+          const float l4 = ((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row] + S.b4[d];
+          par ^= 1;
+          o = is_ief ? o + l4 : l4;
+        }
+        if (it + 1 == a.n_pass[d]) {
+          const float res = lidf_final_act(o, a.use_sigmoid[d]);
+          if (d == 0) res0 = res; else res1 = res;
+        }
       }
+      // ---- outputs of the tile (metadata was parked in smem by the operand build)
+      if (valid) {
+        const int buf = (int)(tl & 1u);
+        const int orig = S.m_orig[buf][row];
+        if (g == 0) a.out[0][orig] = res0;
+        else if (g == 1) a.out[1][orig] = res1;
+        else if (g == 2) {
+          float sc = res0 * (a.r1 - a.r0) + a.r0;            // pipeline.py:437-439
+          sc = sc * a.sqrt3;
+          sc = sc * a.part;
+#pragma unroll
+          for (int k = 0; k < 3; ++k) a.pos_out[(size_t)orig * 3 + k] = S.m_geo[buf][k][row] + sc * S.m_geo[buf][3 + k][row];
+        }
+      }
+      ray = nxt.ray;
+      valid = nxt.valid;
     }
   }
   // ---- teardown ----
+  __syncwarp();
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == 8) tc::tmem_dealloc(tmem, 512);
+  if (warp == TC_ROW_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
 // ------------------------------------------------------------------------------------------------ host side
