@@ -42,7 +42,7 @@ WORKLOADS = {          # name: (B per GPU, H, W, N)   -- BASELINE.json configs
 FLOP_IMNET = 279168            # 2*MAC of the reference Linear stack, per query point
 FLOP_IEF2 = 574784
 FLOP_PER_POINT = {"IEF": FLOP_IEF2 + FLOP_IMNET, "IMNET": 2 * FLOP_IMNET}
-EXEC_MAC_TC = 921600           # MAC-equivalents the tcgen05 engine executes per point (3 bf16 products / MAC)
+EXEC_MAC_TC = 626688           # bf16 MACs the tcgen05 engine executes per point: 3 passes x (112*256 + 256*128 + 128*64) x 3 products
 
 
 def load_peaks():

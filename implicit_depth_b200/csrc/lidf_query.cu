@@ -250,8 +250,8 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
     q->sp = carve_simt_pack(b, 2, q->KR, q->KP, true);
   } else {
     if (q->KP > TC_KPE_MAX) return LIDF_ERR_UNSUPPORTED;
-    q->Av = nullptr;
-    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, false);   // row-prep matrices are shared with the SIMT engine
+    q->Av = b.take<float>((size_t)p->V * 512);
+    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, true);    // row-prep matrices are shared with the SIMT engine
     q->tc = carve_tc(b, p->V, 2);
   }
   q->bytes = b.off + 256;
@@ -310,15 +310,15 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
       k_pack_bias1<<<1, 256, 0, st>>>(dc.w1, ldw, q.D, dc.b1, dc.w_enc, dc.b_enc, dc.kind == LIDF_DEC_IEF,
                                       dc.init_offset, sp.bias_row + 256 * d, sp.u[d]);
       LIDF_LAUNCH_CHECK();
+      if ((rc = pack_wt(dc.w1, ldw, 0, LIDF_VOX_DIM, 256, sp.Wt_vox, sp.Ntot, 0, 256 * d, st))) return rc;
       if (q.impl == LIDF_MLP_SIMT_FP32) {
-        if ((rc = pack_wt(dc.w1, ldw, 0, LIDF_VOX_DIM, 256, sp.Wt_vox, sp.Ntot, 0, 256 * d, st))) return rc;
         LIDF_CUDA(cudaMemsetAsync(sp.Wt_pe[d], 0, sizeof(float) * (size_t)sp.KP * 256, st));
         if ((rc = pack_wt(dc.w1, ldw, LIDF_VOX_DIM + LIDF_RGB_DIM, 2 * q.pe_pos, 256, sp.Wt_pe[d], 256, 0, 0, st))) return rc;
         if ((rc = pack_wt(dc.w2, 256, 0, 256, 128, sp.Wt2[d], 128, 0, 0, st))) return rc;
         if ((rc = pack_wt(dc.w3, 128, 0, 128, 64, sp.Wt3[d], 64, 0, 0, st))) return rc;
       }
     }
-    // 4. row prep: per-ray term T[R][512] (both decoders), per-voxel term A_v[V][512] (SIMT engine)
+    // 4. row prep: per-ray term T[R][512] and per-voxel term A_v[V][512] (both decoders)
     {
       RowPrepArgs a{};
       a.featA = q.roi_feat; a.featB = nullptr; a.dirs = p->miss_ray_dir; a.rows = R;
@@ -328,7 +328,7 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
       LIDF_CUDA(cudaFuncSetAttribute(k_rowprep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
       k_rowprep<<<dim3((unsigned)((R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem, st>>>(a);
       LIDF_LAUNCH_CHECK();
-      if (q.impl == LIDF_MLP_SIMT_FP32 && V > 0) {
+      if (V > 0) {
         a.featA = p->occ_voxel_feat; a.dirs = nullptr; a.rows = V; a.Wt = sp.Wt_vox; a.Kpad = 128; a.bias = nullptr;
         a.out = q.Av;
         const size_t smem2 = sizeof(float) * ((size_t)LIDF_SIMT_BM * 128 + LIDF_KC * 128);
@@ -361,7 +361,7 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
       mlp_event(1, st);
       LIDF_LAUNCH_CHECK();
     } else {
-      if ((rc = tc_query_forward(p, q.tc, q.csr.perm, q.T, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
+      if ((rc = tc_query_forward(p, q.tc, q.csr.perm, q.T, q.Av, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
                                  sizeof(g_cuda_err), mlp_event))) return rc;
     }
   }

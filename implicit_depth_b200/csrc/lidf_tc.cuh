@@ -16,12 +16,16 @@
 // accumulated in fp32 (~2^-16 relative), which is what keeps the result within 1e-3 of the fp32 reference (a single
 // bf16 or fp16 product is 3e-2 / 4e-3 off on the same inputs).
 //
-// Layer-1 operand A1 (K = 240): vox(128) | sincos enter(48) | sincos leave(48) | xyz enter, xyz leave, 10 x 0.
-// Voxel k-steps 0-3 live in TMEM (TS-mode MMA); voxel k-steps 4-7 and the 7 PE k-steps live in shared memory in the
-// UMMA canonical layout (SS-mode MMA).
+// Layer 1 is evaluated in its factored form (exact algebra):
+//   W1 x = W1[:,pos] PE(enter, leave)   <- per pair, K = 102 (padded to 112): the only part that goes through the MMA
+//        + A_v[vox]                     <- per voxel, fp32 row-prep GEMM, gathered in the layer-1 epilogue
+//        + T[ray]                       <- per ray (ROI feature, PE(dir), bias, IEF constant), same
+// The gather is coalesced: 8 lanes fetch one row's 128 B of (A_v + T), the warp transposes through a private smem
+// staging tile, and every lane (= TMEM lane = pair) reads back its own 32 values.
+// Layer-1 MMA operand (K = 112): sincos enter(48) | sincos leave(48) | xyz enter, xyz leave, 10 x 0, in shared memory
+// in the UMMA canonical layout (SS-mode MMA).
 // TMEM plan (512 columns x 128 lanes x 32 bit):
-//   [  0, 64) AV : voxel k-steps 0-3, 4 x (8 cols hi | 8 cols lo)
-//   [ 64,128) Z  : layer-3 accumulator (64 fp32)
+//   [  0, 64) Z  : layer-3 accumulator (64 fp32)          [64,128) unused
 //   [128,256) X0 : layer-1 output half 0, fp32 accumulator -> converted IN PLACE to the layer-2 operand (K half 0)
 //   [256,384) X1 : layer-1 output half 1, same
 //   [384,512) Y  : layer-2 accumulator (128 fp32) -> converted in place to the layer-3 operand
@@ -33,7 +37,7 @@
 //   S4(p): L3 -> Z           | E3(p): layer-3 epilogue + layer-4 dot product
 // The operand of the next tile is built by the row warps between E1 and E2 of a tile's last pass, as soon as the last
 // layer-1 MMA of the tile has retired, so the tensor pipe does not drain at tile boundaries.
-// Weight ring: 7 slots x 16 KB.  A pass consumes 28 fills (8 + 4 + 4 + 8 + 4) = exactly 4 ring rotations, so the slot
+// Weight ring: 5 slots x 16 KB.  A pass consumes 20 fills (4 + 4 + 4 + 4 + 4) = exactly 4 ring rotations, so the slot
 // and parity of every fill are the same in every pass.
 #pragma once
 #include <cuda_bf16.h>
@@ -44,20 +48,17 @@
 #define TC_ROW_THREADS (TC_ROW_WARPS * 32)
 #define TC_THREADS ((TC_ROW_WARPS + 2) * 32)
 #define TC_CHUNK_BYTES 8192
-#define TC_CHUNKS_PER_DEC 50     // 15 (L1 half 0) + 15 (L1 half 1) + 8 (L2 K-half 0) + 8 (L2 K-half 1) + 4 (L3)
-#define TC_STAGES 7
+#define TC_CHUNKS_PER_DEC 34     // 7 (L1 half 0) + 7 (L1 half 1) + 8 (L2 K-half 0) + 8 (L2 K-half 1) + 4 (L3)
+#define TC_STAGES 5
 #define TC_STAGE_BYTES 16384
-#define TC_FILLS_PER_PASS 28
-#define TC_K1_STEPS 15
-#define TC_COL_AV 0               // voxel k-steps 0-3 of the layer-1 operand: 4 x (8 cols hi | 8 cols lo)
-#define TC_COL_Z 64               // layer-3 accumulator
+#define TC_FILLS_PER_PASS 20
+#define TC_K1_STEPS 7             // k-steps of the layer-1 MMA (K = 112)
+#define TC_COL_Z 0                // layer-3 accumulator
 #define TC_COL_X0 128             // layer-1 output half 0: accumulator -> (in place) layer-2 operand
 #define TC_COL_X1 256             // layer-1 output half 1
 #define TC_COL_Y 384              // layer-2 accumulator -> (in place) layer-3 operand
-#define TC_VOX_TS 4               // voxel k-steps whose A operand is in TMEM
-#define TC_PE_KSTEPS 7
-#define TC_SM_KSTEPS 11           // k-steps of the shared-memory operand tile: 7 PE + 4 voxel
-#define TC_A1S_PART_BYTES (TC_SM_KSTEPS * 4096)   // one part (hi or lo): [kstep][kgroup(2)][128 rows][16 B]
+#define TC_A1S_PART_BYTES (TC_K1_STEPS * 4096)    // one part (hi or lo): [kstep][kgroup(2)][128 rows][16 B]
+#define TC_STAGE_PITCH 36         // floats per row of the per-warp gather staging tile (32 + 4: conflict-free LDS.128)
 #define TC_KPE_MAX 112            // widest per-pair PE block (2 x PE(pos)) the layer-1 operand layout holds
 #define TC_MAX_PASSES 9
 #define TC_SPIN_LIMIT (1u << 22)
@@ -206,18 +207,17 @@ __device__ __forceinline__ void split16(const float* x, uint32_t* out16) {
 }  // namespace tc
 
 // ------------------------------------------------------------------------------------------------ packing kernels
-// A1 element (K index of the layer-1 operand) -> column of linear_1.weight; -1 = zero padding.
+// element e of the layer-1 MMA operand (K index) -> column of linear_1.weight; -1 = zero padding.
 __host__ __device__ inline int tc_a1_col(int e, int pe_pos) {
   const int base = LIDF_VOX_DIM + LIDF_RGB_DIM;             // PE(enter) starts at column 256 (pipeline.py:431-433)
-  if (e < 128) return e;                                    // voxel feature
-  if (e < 176) return base + 3 + (e - 128);                 // sin/cos part of PE(enter)
-  if (e < 224) return base + pe_pos + 3 + (e - 176);        // sin/cos part of PE(leave)
-  if (e < 227) return base + (e - 224);                     // raw enter xyz
-  if (e < 230) return base + pe_pos + (e - 227);            // raw leave xyz
+  if (e < 48) return base + 3 + e;                          // sin/cos part of PE(enter)
+  if (e < 96) return base + pe_pos + 3 + (e - 48);          // sin/cos part of PE(leave)
+  if (e < 99) return base + (e - 96);                       // raw enter xyz
+  if (e < 102) return base + pe_pos + (e - 99);             // raw leave xyz
   return -1;
 }
 
-// weight stream of one decoder: 50 chunks x 8 KB.  Chunk with N rows (128, or 64 for layer 3) holds k-steps of
+// weight stream of one decoder: 34 chunks x 8 KB.  Chunk with N rows (128, or 64 for layer 3) holds k-steps of
 // [hi: kg0 N x 16 B | kg1 N x 16 B][lo: kg0 | kg1]; an N=128 chunk is one k-step, an N=64 chunk two.
 __global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe_pos, const float* __restrict__ w2,
                                   const float* __restrict__ w3, uint8_t* __restrict__ stream) {
@@ -226,19 +226,19 @@ __global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe
   const int c = idx / 2048, r = idx % 2048;
   float w = 0.f;
   int n, kk, N, ksub = 0;
-  if (c < 46) {
+  if (c < 30) {
     N = 128; n = r / 16; kk = r % 16;
-    if (c < 30) {                                           // layer 1, output half 0 / 1
-      const int half = c >= 15, s = half ? c - 15 : c;
+    if (c < 14) {                                           // layer 1, output half 0 / 1
+      const int half = c >= 7, s = half ? c - 7 : c;
       const int col = tc_a1_col(16 * s + kk, pe_pos);
       if (col >= 0) w = w1[(size_t)(half * 128 + n) * ldw1 + col];
     } else {                                                // layer 2, K half 0 / 1
-      const int half = c >= 38, s = half ? c - 38 : c - 30;
+      const int half = c >= 22, s = half ? c - 22 : c - 14;
       w = w2[(size_t)n * LIDF_H1 + half * 128 + 16 * s + kk];
     }
   } else {                                                  // layer 3: N = 64, two k-steps per chunk
     N = 64; ksub = r / 1024; const int rr = r % 1024; n = rr / 16; kk = rr % 16;
-    w = w3[(size_t)n * LIDF_H2 + 16 * (2 * (c - 46) + ksub) + kk];
+    w = w3[(size_t)n * LIDF_H2 + 16 * (2 * (c - 30) + ksub) + kk];
   }
   const __nv_bfloat16 hi = __float2bfloat16_rn(w);
   const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
@@ -248,20 +248,6 @@ __global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe
   const size_t off = (size_t)kg * N * 16 + (size_t)n * 16 + e * 2;
   *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
   *reinterpret_cast<__nv_bfloat16*>(base + (size_t)N * 32 + off) = lo;
-}
-
-// voxel table: [V][128 words]; word 16 s + j (j < 8) = bf16 hi of features (16 s + 2 j, +1), j >= 8 the lo parts.
-// This is exactly the TMEM column image of k-steps 0..7 of A1, so a row is 8 x (4 x LDG.128 -> tcgen05.st.x16).
-__global__ void k_pack_voxtab(const float* __restrict__ feat, int64_t V, uint32_t* __restrict__ tab) {
-  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= V * 64) return;
-  const int64_t v = idx >> 6;
-  const int p = (int)(idx & 63), s = p >> 3, j = p & 7;
-  const float a = feat[v * 128 + 16 * s + 2 * j], b = feat[v * 128 + 16 * s + 2 * j + 1];
-  uint32_t hi, lo;
-  tc::split2(a, b, hi, lo);
-  tab[v * 128 + 16 * s + j] = hi;
-  tab[v * 128 + 16 * s + 8 + j] = lo;
 }
 
 // ------------------------------------------------------------------------------------------------ self test
@@ -385,9 +371,9 @@ struct TcArgs {
   const int* perm; const int64_t* pair_vox; const int64_t* pair_ray;
   const float* pair_dist; const float* dense_dist; int64_t R;
   const float* ray_dir; const float* voxel_bound; int rel;
-  const uint32_t* voxtab;          // [V][128]
+  const float* Av;                 // [V][512] per-voxel layer-1 term, decoder d at column 256 d
   const float* T;                  // [R][512] per-ray layer-1 term, decoder d at column 256 d
-  const uint8_t* wstream;          // [2][50][8192]
+  const uint8_t* wstream;          // [2][34][8192]
   const float* u;                  // [256] IEF rank-1 vector of decoder 0 (NULL if IMNet)
   const float* b2[2]; const float* b3[2]; const float* w4[2]; const float* b4[2];
   int kind[2]; int n_pass[2]; int use_sigmoid[2];
@@ -399,7 +385,8 @@ struct TcArgs {
 
 struct TcSmem {
   uint8_t w[TC_STAGES][TC_STAGE_BYTES];
-  uint8_t a1[2][TC_A1S_PART_BYTES];  // smem part of the layer-1 operand: [hi|lo][kstep(11)][kgroup(2)][128 rows][16 B]
+  uint8_t a1[2][TC_A1S_PART_BYTES];  // layer-1 MMA operand: [hi|lo][kstep(7)][kgroup(2)][128 rows][16 B]
+  float stage[TC_ROW_WARPS][32 * TC_STAGE_PITCH];   // per-warp transpose tile of the gathered (A_v + T) rows
   float u[LIDF_H1];
   float b2[2][LIDF_H2];
   float b3[2][LIDF_H3];
@@ -432,18 +419,6 @@ __device__ __forceinline__ void tc_k_ts128(const TcIssue& c, uint32_t dcol, uint
     tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi + (4096u >> 4), idesc, 1u);
   }
 }
-// same with the A operand in shared memory (k-step sk of the operand tile)
-template <int NPROD>
-__device__ __forceinline__ void tc_k_ss128(const TcIssue& c, uint32_t dcol, int sk, uint32_t off) {
-  constexpr uint32_t idesc = tc::make_idesc(128);
-  const uint64_t bhi = c.wd128 + (off >> 4);
-  const uint64_t ahi = c.ad + ((uint32_t)(sk * 4096) >> 4);
-  tc::mma_ss(c.tmem + dcol, ahi, bhi, idesc, 1u);
-  if (NPROD == 3) {
-    tc::mma_ss(c.tmem + dcol, ahi + ((uint32_t)TC_A1S_PART_BYTES >> 4), bhi, idesc, 1u);
-    tc::mma_ss(c.tmem + dcol, ahi, bhi + (4096u >> 4), idesc, 1u);
-  }
-}
 // layer 3: A in TMEM, N = 64: B = [hi 2 KB][lo 2 KB] at byte offset off
 template <int NPROD>
 __device__ __forceinline__ void tc_k_ts64(const TcIssue& c, uint32_t dcol, uint32_t acol, uint32_t off, bool first) {
@@ -460,20 +435,25 @@ __device__ __forceinline__ void tc_k_ts64(const TcIssue& c, uint32_t dcol, uint3
 #define TC_SLOT(gi) ((gi) % TC_STAGES)
 #define TC_PAR(gi) ((uint32_t)(((gi) / TC_STAGES) & 1))
 
-// layer 1, one output half (15 k-steps = 7 fills of 2 + 1 fill of 1), fills GI0 .. GI0+7
+// layer 1, one output half (7 k-steps = 3 fills of 2 + 1 fill of 1), A operand in shared memory
 template <int NPROD, int GI0>
 __device__ __forceinline__ void tc_issue_l1(const TcIssue& c, uint32_t dcol) {
+  constexpr uint32_t idesc = tc::make_idesc(128);
 #pragma unroll
-  for (int sg = 0; sg < 8; ++sg) {
+  for (int sg = 0; sg < 4; ++sg) {
     const int gi = GI0 + sg, slot = TC_SLOT(gi);
     tc::mbar_wait_a(c.full0 + 8 * slot, TC_PAR(gi));
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int ks = 2 * sg + j;
       if (ks < TC_K1_STEPS) {
-        const uint32_t off = (uint32_t)(slot * TC_STAGE_BYTES + j * TC_CHUNK_BYTES);
-        if (ks < TC_VOX_TS) tc_k_ts128<NPROD>(c, dcol, TC_COL_AV + 16 * ks, off, ks == 0);
-        else tc_k_ss128<NPROD>(c, dcol, ks < 8 ? TC_PE_KSTEPS + (ks - TC_VOX_TS) : ks - 8, off);
+        const uint64_t bhi = c.wd128 + ((uint32_t)(slot * TC_STAGE_BYTES + j * TC_CHUNK_BYTES) >> 4);
+        const uint64_t ahi = c.ad + ((uint32_t)(ks * 4096) >> 4);
+        tc::mma_ss(c.tmem + dcol, ahi, bhi, idesc, ks == 0 ? 0u : 1u);
+        if (NPROD == 3) {
+          tc::mma_ss(c.tmem + dcol, ahi + ((uint32_t)TC_A1S_PART_BYTES >> 4), bhi, idesc, 1u);
+          tc::mma_ss(c.tmem + dcol, ahi, bhi + (4096u >> 4), idesc, 1u);
+        }
       }
     }
     tc::commit_a(c.empty0 + 8 * slot);
@@ -570,25 +550,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
   const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_passes = n_my_tiles * npt;
   // weight-stream segments of one decoder (chunk offsets)
-  constexpr int SEG_L1H0 = 0, SEG_L1H1 = 15, SEG_L2K0 = 30, SEG_L2K1 = 38, SEG_L3 = 46;
-  // static fill schedule: prologue S0 = fills 0..7; a pass = fills 8..35 (+ 28 per pass: same slots, same parities)
-  constexpr int GI_S2 = 8, GI_S1 = 16, GI_S3 = 20, GI_S0 = 24, GI_S4 = 32;
+  constexpr int SEG_L1H0 = 0, SEG_L1H1 = 7, SEG_L2K0 = 14, SEG_L2K1 = 22, SEG_L3 = 30;
+  // static fill schedule: prologue S0 = fills 0..3; a pass = fills 4..23 (+ 20 per pass: same slots, same parities)
+  constexpr int GI_S2 = 4, GI_S1 = 8, GI_S3 = 12, GI_S0 = 16, GI_S4 = 20;
 
   if (warp == TC_ROW_WARPS + 1) {
     // ================================ weight loader (TMA), one thread ================================
     if (tc::elect_one()) {
       auto seg = [&](int d, int chunk) { return a.wstream + ((size_t)d * TC_CHUNKS_PER_DEC + chunk) * TC_CHUNK_BYTES; };
       const int d_first = a.n_pass[0] > 0 ? 0 : 1;
-      tc_load_seg<0, 8, 7>(S, seg(d_first, SEG_L1H0), false);
+      tc_load_seg<0, 4, 3>(S, seg(d_first, SEG_L1H0), false);
       int p = 0;
       for (int gp = 0; gp < total_passes; ++gp) {
         const int d = p < a.n_pass[0] ? 0 : 1;
         const int pn = p + 1 == npt ? 0 : p + 1;
         const int dn = pn < a.n_pass[0] ? 0 : 1;
-        tc_load_seg<GI_S2, 8, 7>(S, seg(d, SEG_L1H1), gp > 0);
+        tc_load_seg<GI_S2, 4, 3>(S, seg(d, SEG_L1H1), gp > 0);
         tc_load_seg<GI_S1, 4, 4>(S, seg(d, SEG_L2K0), true);
         tc_load_seg<GI_S3, 4, 4>(S, seg(d, SEG_L2K1), true);
-        tc_load_seg<GI_S0, 8, 7>(S, seg(dn, SEG_L1H0), true);                  // drained unused after the last pass
+        tc_load_seg<GI_S0, 4, 3>(S, seg(dn, SEG_L1H0), true);                  // drained unused after the last pass
         tc_load_seg<GI_S4, 4, 0>(S, seg(d, SEG_L3), true);
         p = pn;
       }
@@ -635,7 +615,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           tc_issue_l1<NPROD, GI_S0>(c, TC_COL_X0);
           tc::commit(&S.x_full[0]);
         } else {
-          tc_drain<GI_S0, 8>(c);
+          tc_drain<GI_S0, 4>(c);
         }
         // S4(p): layer 3, operand = Y converted by E2, accumulator Z (E3 of the previous pass must have read Z)
         tc::mbar_wait(&S.y_done, ph);
@@ -672,8 +652,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       }
       return m;
     };
-    // layer-1 operand of one tile.  Column group 0 encodes the enter position, 1 the leave position, 2 loads voxel
-    // k-steps 0-3 (-> TMEM) and the raw xyz k-step, 3 loads voxel k-steps 4-7 (-> smem).
+    // layer-1 MMA operand of one tile.  Column group 0 encodes the enter position (k-steps 0-2), 1 the leave position
+    // (k-steps 3-5), 2 writes the raw xyz k-step (6) and parks the output metadata in smem.
     auto build_a1 = [&](const RowMeta& m, int buf) {
       float dir[3] = {0.f, 0.f, 0.f}, enter[3] = {0.f, 0.f, 0.f}, pe[3] = {0.f, 0.f, 0.f}, pl[3] = {0.f, 0.f, 0.f};
       if (m.valid) {
@@ -686,7 +666,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           pl[k] = dir[k] * m.t1 - c;
         }
       }
-      const uint4* vrow = reinterpret_cast<const uint4*>(a.voxtab + (size_t)m.vox * 128);
       if (g < 2) {
         // positional encoding: accurate sincos at f = 1 and f = 16, three exact-form double-angle steps after each
         // (sin 2x = 2 s c, cos 2x = 1 - 2 s^2)
@@ -714,53 +693,51 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           st_a1(3 * g + j, w);
         }
       } else if (g == 2) {
+        float x[16];
 #pragma unroll
-        for (int ks = 0; ks < TC_VOX_TS; ++ks) {
-          uint32_t w[16];
+        for (int k = 0; k < 16; ++k) x[k] = 0.f;
 #pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 t = make_uint4(0u, 0u, 0u, 0u);
-            if (m.valid) t = __ldg(vrow + ks * 4 + v4);
-            w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
-          }
-          tc::tmem_st16(lane_addr + TC_COL_AV + 16 * ks, w);
-        }
-        {
-          float x[16];
-#pragma unroll
-          for (int k = 0; k < 16; ++k) x[k] = 0.f;
-#pragma unroll
-          for (int k = 0; k < 3; ++k) { x[k] = pe[k]; x[3 + k] = pl[k]; }
-          uint32_t w[16];
-          tc::split16(x, w);
-          st_a1(6, w);
-        }
+        for (int k = 0; k < 3; ++k) { x[k] = pe[k]; x[3 + k] = pl[k]; }
+        uint32_t w[16];
+        tc::split16(x, w);
+        st_a1(6, w);
         S.m_orig[buf][row] = m.orig;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { S.m_geo[buf][k][row] = enter[k]; S.m_geo[buf][3 + k][row] = dir[k]; }
-        tc::wait_st();
-      } else {
-#pragma unroll
-        for (int ks = TC_VOX_TS; ks < 8; ++ks) {
-          uint32_t w[16];
-#pragma unroll
-          for (int v4 = 0; v4 < 4; ++v4) {
-            uint4 t = make_uint4(0u, 0u, 0u, 0u);
-            if (m.valid) t = __ldg(vrow + ks * 4 + v4);
-            w[4 * v4] = t.x; w[4 * v4 + 1] = t.y; w[4 * v4 + 2] = t.z; w[4 * v4 + 3] = t.w;
-          }
-          st_a1(TC_PE_KSTEPS + (ks - TC_VOX_TS), w);
-        }
       }
       tc::fence_proxy_async();
-      tc::fence_before_sync();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.a1_ready);
+    };
+    // (A_v[vox] + T[ray])[256 d + 128 hf + 32 g .. + 32] of this warp's 32 rows -> t[8]: 8 lanes fetch one row's 128 B
+    // (4 rows per load instruction, fully coalesced), the warp transposes through its private staging tile.
+    float* const stage_w = S.stage[warp];
+    auto gather_term = [&](int vox, int ray, int d, int hf, float4 (&t)[8]) {
+      const int col = 256 * d + 128 * hf + 32 * g + 4 * (lane & 7);
+      float4 av[8], tv[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + (lane >> 3);
+        const int rv = __shfl_sync(0xffffffffu, vox, src), rr = __shfl_sync(0xffffffffu, ray, src);
+        av[i] = __ldg(reinterpret_cast<const float4*>(a.Av + (size_t)rv * 512 + col));
+        tv[i] = __ldg(reinterpret_cast<const float4*>(a.T + (size_t)rr * 512 + col));
+      }
+      __syncwarp();                                                            // previous readers of the tile are done
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int src = 4 * i + (lane >> 3);
+        float4 sum;
+        sum.x = av[i].x + tv[i].x; sum.y = av[i].y + tv[i].y; sum.z = av[i].z + tv[i].z; sum.w = av[i].w + tv[i].w;
+        *reinterpret_cast<float4*>(stage_w + src * TC_STAGE_PITCH + 4 * (lane & 7)) = sum;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stage_w + lane * TC_STAGE_PITCH + 4 * i);
     };
 
     RowMeta cur = load_meta((int)blockIdx.x);
     build_a1(cur, 0);
-    int ray = cur.ray;
+    int ray = cur.ray, vox = cur.vox;
     bool valid = cur.valid;
     uint32_t gp = 0, tl = 0, par = 0;
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
@@ -778,11 +755,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         if (last && has_next) nxt = load_meta(next_tile);                      // prefetch: consumed after E1
         const float delta = o - a.o0;                                         // IEF: T already holds u*o0 + c
         const bool rank1 = is_ief && it > 0;
-        const float* trow = a.T + (size_t)ray * 512 + 256 * d + 32 * g;
         // ---- E0 / E1: layer-1 epilogue of output half hf (X0 / X1); this thread converts columns [32 g, 32 g + 32)
         float4 t[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) t[i] = valid ? __ldg(reinterpret_cast<const float4*>(trow) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+        gather_term(vox, ray, d, 0, t);
 #pragma unroll
         for (int hf = 0; hf < 2; ++hf) {
           const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
@@ -811,10 +786,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
               x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + t[i].w);
             }
           }
-          if (hf == 0) {                                                       // per-ray term of half 1: in flight during the stores
-#pragma unroll
-            for (int i = 0; i < 8; ++i) t[i] = valid ? __ldg(reinterpret_cast<const float4*>(trow + 128) + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
           uint32_t w[16];
           tc::split16(x, w);
           tc::tmem_st16(lane_addr + xcol, w);
@@ -824,11 +795,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           tc::fence_before_sync();
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
+          if (hf == 0) gather_term(vox, ray, d, 1, t);                         // terms of half 1
         }
         // ---- operand of the next tile: its last reader (S2 of this pass) has retired once a1_free completes
         if (last && has_next) {
           tc::mbar_wait(&S.a1_free, tl & 1u);
-          tc::fence_after_sync();
           build_a1(nxt, (int)((tl + 1) & 1u));
         }
         // ---- E2: layer-2 epilogue on Y
@@ -899,7 +870,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           for (int k = 0; k < 3; ++k) a.pos_out[(size_t)orig * 3 + k] = S.m_geo[buf][k][row] + sc * S.m_geo[buf][3 + k][row];
         }
       }
-      ray = nxt.ray;
+      ray = nxt.ray; vox = nxt.vox;
       valid = nxt.valid;
     }
   }
@@ -911,12 +882,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
 }
 
 // ------------------------------------------------------------------------------------------------ host side
-struct TcBufs { uint32_t* voxtab; uint8_t* wstream; };
+struct TcBufs { uint8_t* wstream; };
 
 template <typename B>
 inline TcBufs carve_tc(B& b, int64_t V, int n_dec) {
   TcBufs t;
-  t.voxtab = b.template take<uint32_t>((size_t)(V > 0 ? V : 1) * 128);
+  (void)V;
   t.wstream = b.template take<uint8_t>((size_t)n_dec * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES);
   return t;
 }
@@ -939,14 +910,13 @@ inline int tc_device_ok() {
 }
 
 // decoders + pair_pred_pos for all P pairs; T = per-ray layer-1 term [R][512], u = IEF rank-1 vector of offset_dec
-inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const int* perm, const float* T, const float* u,
+inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const int* perm, const float* T, const float* Av,
+                            const float* u,
                             int pe_pos, int D, int impl, cudaStream_t st, int64_t* launches, char* errbuf, size_t errlen,
                             void (*mlp_event)(int, cudaStream_t)) {
   if (!p->pos_encode || p->multires != 8 || pe_pos != 51) return LIDF_ERR_UNSUPPORTED;   // A1 layout is built for PE(8)
   if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
   const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
-  k_pack_voxtab<<<(unsigned)((p->V * 64 + 255) / 256), 256, 0, st>>>(p->occ_voxel_feat, p->V, tb.voxtab);
-  TC_LAUNCH_CHECK();
   for (int d = 0; d < 2; ++d) {
     const int ldw = D + (decs[d]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
     k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(
@@ -957,7 +927,7 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   a.P = p->P; a.n_tiles = (int)((p->P + 127) / 128);
   a.perm = perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
   a.dense_dist = p->dense_dist; a.R = p->R; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
-  a.rel = p->intersect_pos_rel; a.voxtab = tb.voxtab; a.T = T; a.wstream = tb.wstream;
+  a.rel = p->intersect_pos_rel; a.Av = Av; a.T = T; a.wstream = tb.wstream;
   a.u = decs[0]->kind == LIDF_DEC_IEF ? u : nullptr;
   for (int d = 0; d < 2; ++d) {
     a.b2[d] = decs[d]->b2; a.b3[d] = decs[d]->b3; a.w4[d] = decs[d]->w4; a.b4[d] = decs[d]->b4;
