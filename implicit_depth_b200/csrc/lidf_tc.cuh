@@ -363,6 +363,12 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// 16-byte asynchronous copy global -> shared (LDGSTS), no register staging
+__device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_saddr), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(TC_ROW_THREADS) : "memory"); }
 }  // namespace tc
 
@@ -377,6 +383,9 @@ struct TcArgs {
   const float* u;                  // [256] IEF rank-1 vector of decoder 0 (NULL if IMNet)
   const float* b2[2]; const float* b3[2]; const float* w4[2]; const float* b4[2];
   int kind[2]; int n_pass[2]; int use_sigmoid[2];
+  int npt;                         // passes per tile
+  int pass_dec[TC_MAX_PASSES];     // decoder of pass p: the two decoders are interleaved so that consecutive passes are
+  int pass_it[TC_MAX_PASSES];      // independent wherever possible (IEF iteration k+1 needs the result of iteration k)
   float o0, r0, r1, sqrt3, part;
   float* out[2];                   // pred_offset, pred_prob_end  (written at the original pair index)
   float* pos_out;                  // pair_pred_pos [P,3]
@@ -546,7 +555,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = S.tmem_base;
-  const int npt = a.n_pass[0] + a.n_pass[1];                                   // passes per tile
+  const int npt = a.npt;                                                       // passes per tile
   const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_passes = n_my_tiles * npt;
   // weight-stream segments of one decoder (chunk offsets)
@@ -558,13 +567,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     // ================================ weight loader (TMA), one thread ================================
     if (tc::elect_one()) {
       auto seg = [&](int d, int chunk) { return a.wstream + ((size_t)d * TC_CHUNKS_PER_DEC + chunk) * TC_CHUNK_BYTES; };
-      const int d_first = a.n_pass[0] > 0 ? 0 : 1;
-      tc_load_seg<0, 4, 3>(S, seg(d_first, SEG_L1H0), false);
+      tc_load_seg<0, 4, 3>(S, seg(a.pass_dec[0], SEG_L1H0), false);
       int p = 0;
       for (int gp = 0; gp < total_passes; ++gp) {
-        const int d = p < a.n_pass[0] ? 0 : 1;
+        const int d = a.pass_dec[p];
         const int pn = p + 1 == npt ? 0 : p + 1;
-        const int dn = pn < a.n_pass[0] ? 0 : 1;
+        const int dn = a.pass_dec[pn];
         tc_load_seg<GI_S2, 4, 3>(S, seg(d, SEG_L1H1), gp > 0);
         tc_load_seg<GI_S1, 4, 4>(S, seg(d, SEG_L2K0), true);
         tc_load_seg<GI_S3, 4, 4>(S, seg(d, SEG_L2K1), true);
@@ -709,94 +717,112 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.a1_ready);
     };
-    // (A_v[vox] + T[ray])[256 d + 128 hf + 32 g .. + 32] of this warp's 32 rows -> t[8]: 8 lanes fetch one row's 128 B
-    // (4 rows per load instruction, fully coalesced), the warp transposes through its private staging tile.
+    // Gather of A_v[vox][col .. col + 32) for this warp's 32 rows, one epilogue ahead of its use: 8 lanes copy one row's
+    // 128 B (4 rows per instruction, fully coalesced) with cp.async straight into the warp's private staging tile; the
+    // consumer waits, and every lane (= TMEM lane = pair) reads back its own 32 values.
     float* const stage_w = S.stage[warp];
-    auto gather_term = [&](int vox, int ray, int d, int hf, float4 (&t)[8]) {
-      const int col = 256 * d + 128 * hf + 32 * g + 4 * (lane & 7);
-      float4 av[8], tv[8];
+    const uint32_t stage_sa = tc::smem_u32(stage_w);
+    auto gather_issue = [&](int vox_, int col) {
+      const float* src0 = a.Av + col + 4 * (lane & 7);
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const int src = 4 * i + (lane >> 3);
-        const int rv = __shfl_sync(0xffffffffu, vox, src), rr = __shfl_sync(0xffffffffu, ray, src);
-        av[i] = __ldg(reinterpret_cast<const float4*>(a.Av + (size_t)rv * 512 + col));
-        tv[i] = __ldg(reinterpret_cast<const float4*>(a.T + (size_t)rr * 512 + col));
+        const int rv = __shfl_sync(0xffffffffu, vox_, src);
+        tc::cp_async16(stage_sa + (uint32_t)(src * TC_STAGE_PITCH + 4 * (lane & 7)) * 4u, src0 + (size_t)rv * 512);
       }
-      __syncwarp();                                                            // previous readers of the tile are done
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int src = 4 * i + (lane >> 3);
-        float4 sum;
-        sum.x = av[i].x + tv[i].x; sum.y = av[i].y + tv[i].y; sum.z = av[i].z + tv[i].z; sum.w = av[i].w + tv[i].w;
-        *reinterpret_cast<float4*>(stage_w + src * TC_STAGE_PITCH + 4 * (lane & 7)) = sum;
-      }
+      tc::cp_async_commit();
+    };
+    auto gather_read = [&](float4 (&t)[8]) {
+      tc::cp_async_wait_all();
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) t[i] = *reinterpret_cast<const float4*>(stage_w + lane * TC_STAGE_PITCH + 4 * i);
+      __syncwarp();                                                            // tile may be overwritten by the next gather
+    };
+    // Layer-1 epilogue of output half hf (X0 / X1) of a pass of decoder d: this thread converts columns [32 g, 32 g + 32):
+    // x = leaky(acc + A_v[vox] + T[ray] (+ u * delta)) -> bf16 hi | lo, in place.  Also issues the gather of the NEXT
+    // layer-1 epilogue in program order (next_col < 0: none).
+    auto epi_l1 = [&](int hf, int d, bool rank1, float delta, int ray_, bool valid_, uint32_t ph, int next_vox, int next_col) {
+      const int n0 = 128 * hf + 32 * g;
+      float4 tt[8];
+      {
+        const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)ray_ * 512 + 256 * d + n0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) tt[i] = valid_ ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+      float4 t[8];
+      gather_read(t);
+      if (next_col >= 0) gather_issue(next_vox, next_col);
+      const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
+      tc::mbar_wait(&S.x_full[hf], ph);
+      tc::fence_after_sync();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) { t[i].x += tt[i].x; t[i].y += tt[i].y; t[i].z += tt[i].z; t[i].w += tt[i].w; }
+      uint32_t r[32];
+      tc::tmem_ld32(lane_addr + xcol, r);
+      tc::wait_ld();
+      float x[32];
+      if (rank1) {
+        const float4* up = reinterpret_cast<const float4*>(&S.u[n0]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const float4 uv = up[i];
+          x[4 * i + 0] = lidf_leaky(fmaf(uv.x, delta, __uint_as_float(r[4 * i + 0]) + t[i].x));
+          x[4 * i + 1] = lidf_leaky(fmaf(uv.y, delta, __uint_as_float(r[4 * i + 1]) + t[i].y));
+          x[4 * i + 2] = lidf_leaky(fmaf(uv.z, delta, __uint_as_float(r[4 * i + 2]) + t[i].z));
+          x[4 * i + 3] = lidf_leaky(fmaf(uv.w, delta, __uint_as_float(r[4 * i + 3]) + t[i].w));
+        }
+      } else {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + t[i].x);
+          x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + t[i].y);
+          x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + t[i].z);
+          x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + t[i].w);
+        }
+      }
+      uint32_t w[16];
+      tc::split16(x, w);
+      tc::tmem_st16(lane_addr + xcol, w);
+      tc::split16(x + 16, w);
+      tc::tmem_st16(lane_addr + xcol + 16, w);
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
     };
 
+    // Program order of a row warp (E0/E1 = layer-1 epilogues, E2 = layer 2, E3 = layer 3 + 4):
+    //   E0(first) | E1(p) [build next tile's operand] E2(p) E0(p+1) E3(p) | E1(p+1) ...
+    // E0 of the next pass runs BEFORE E3 of the current one (its accumulator is ready earlier, and the tensor pipe needs
+    // it sooner) unless the next pass is the next IEF iteration of the same decoder, which needs E3's result.
     RowMeta cur = load_meta((int)blockIdx.x);
     build_a1(cur, 0);
     int ray = cur.ray, vox = cur.vox;
     bool valid = cur.valid;
     uint32_t gp = 0, tl = 0, par = 0;
+    float o_a = 0.f, o_b = 0.f, res0 = 0.f, res1 = 0.f;       // running IEF offsets / final values of decoder 0, 1
+    gather_issue(vox, 256 * a.pass_dec[0] + 32 * g);
+    epi_l1(0, a.pass_dec[0], false, 0.f, ray, valid, 0u, vox, 256 * a.pass_dec[0] + 128 + 32 * g);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
       const int next_tile = tile + (int)gridDim.x;
       const bool has_next = next_tile < a.n_tiles;
       RowMeta nxt{0, 0, 0, 0.f, 0.f, false};
-      float o = 0.f, res0 = 0.f, res1 = 0.f;
       for (int p = 0; p < npt; ++p, ++gp) {
-        const int d = p < a.n_pass[0] ? 0 : 1;
-        const int it = d == 0 ? p : p - a.n_pass[0];
+        const int d = a.pass_dec[p], it = a.pass_it[p];
         const uint32_t ph = gp & 1u;
         const bool is_ief = a.kind[d] == LIDF_DEC_IEF;
-        if (it == 0) o = is_ief ? a.o0 : 0.f;
         const bool last = p + 1 == npt;
-        if (last && has_next) nxt = load_meta(next_tile);                      // prefetch: consumed after E1
-        const float delta = o - a.o0;                                         // IEF: T already holds u*o0 + c
-        const bool rank1 = is_ief && it > 0;
-        // ---- E0 / E1: layer-1 epilogue of output half hf (X0 / X1); this thread converts columns [32 g, 32 g + 32)
-        float4 t[8];
-        gather_term(vox, ray, d, 0, t);
-#pragma unroll
-        for (int hf = 0; hf < 2; ++hf) {
-          const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
-          tc::mbar_wait(&S.x_full[hf], ph);
-          tc::fence_after_sync();
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + xcol, r);
-          tc::wait_ld();
-          float x[32];
-          if (rank1) {
-            const float4* up = reinterpret_cast<const float4*>(&S.u[128 * hf + 32 * g]);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 uv = up[i];
-              x[4 * i + 0] = lidf_leaky(fmaf(uv.x, delta, __uint_as_float(r[4 * i + 0]) + t[i].x));
-              x[4 * i + 1] = lidf_leaky(fmaf(uv.y, delta, __uint_as_float(r[4 * i + 1]) + t[i].y));
-              x[4 * i + 2] = lidf_leaky(fmaf(uv.z, delta, __uint_as_float(r[4 * i + 2]) + t[i].z));
-              x[4 * i + 3] = lidf_leaky(fmaf(uv.w, delta, __uint_as_float(r[4 * i + 3]) + t[i].w));
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + t[i].x);
-              x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + t[i].y);
-              x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + t[i].z);
-              x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + t[i].w);
-            }
-          }
-          uint32_t w[16];
-          tc::split16(x, w);
-          tc::tmem_st16(lane_addr + xcol, w);
-          tc::split16(x + 16, w);
-          tc::tmem_st16(lane_addr + xcol + 16, w);
-          tc::wait_st();
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
-          if (hf == 0) gather_term(vox, ray, d, 1, t);                         // terms of half 1
-        }
+        const bool has_next_pass = !last || has_next;
+        const int pn = last ? 0 : p + 1;
+        const int dn = a.pass_dec[pn], itn = a.pass_it[pn];
+        const bool dep = !last && dn == d;                                    // next pass continues this decoder's IEF loop
+        if (has_next && p == (npt >= 2 ? npt - 2 : 0)) nxt = load_meta(next_tile);   // prefetch: first used in E1 of the last pass
+        const int vox_n = last ? nxt.vox : vox, ray_n = last ? nxt.ray : ray;
+        const bool valid_n = last ? nxt.valid : valid;
+        // ---- E1(p)
+        epi_l1(1, d, is_ief && it > 0, (d == 0 ? o_a : o_b) - a.o0, ray, valid, ph, vox_n,
+               has_next_pass ? 256 * dn + 32 * g : -1);
         // ---- operand of the next tile: its last reader (S2 of this pass) has retired once a1_free completes
         if (last && has_next) {
           tc::mbar_wait(&S.a1_free, tl & 1u);
@@ -829,6 +855,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           __syncwarp();
           if (lane == 0) tc::mbar_arrive(&S.y_done);
         }
+        // ---- E0(p+1), when it does not need this pass's result
+        if (has_next_pass && !dep)
+          epi_l1(0, dn, a.kind[dn] == LIDF_DEC_IEF && itn > 0, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n,
+                 256 * dn + 128 + 32 * g);
         // ---- E3: layer-3 epilogue + layer 4 (64-term dot product, 16 terms per column group) on Z
         {
           tc::mbar_wait(&S.z_full, ph);
@@ -849,15 +879,20 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           tc::bar_rows();                                                      // the 16 row warps only
           const float l4 = ((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row] + S.b4[d];
           par ^= 1;
-          o = is_ief ? o + l4 : l4;
+          const float prev = it == 0 ? (is_ief ? a.o0 : 0.f) : (d == 0 ? o_a : o_b);
+          const float onew = is_ief ? prev + l4 : l4;
+          if (d == 0) o_a = onew; else o_b = onew;
+          if (it + 1 == a.n_pass[d]) {
+            const float res = lidf_final_act(onew, a.use_sigmoid[d]);
+            if (d == 0) res0 = res; else res1 = res;
+          }
         }
-        if (it + 1 == a.n_pass[d]) {
-          const float res = lidf_final_act(o, a.use_sigmoid[d]);
-          if (d == 0) res0 = res; else res1 = res;
-        }
+        // ---- E0(p+1) of a dependent pass
+        if (has_next_pass && dep)
+          epi_l1(0, dn, true, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n, 256 * dn + 128 + 32 * g);
       }
       // ---- outputs of the tile (metadata was parked in smem by the operand build)
-      if (valid) {
+      if ((int64_t)tile * 128 + row < a.P) {
         const int buf = (int)(tl & 1u);
         const int orig = S.m_orig[buf][row];
         if (g == 0) a.out[0][orig] = res0;
@@ -867,7 +902,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           sc = sc * a.sqrt3;
           sc = sc * a.part;
 #pragma unroll
-          for (int k = 0; k < 3; ++k) a.pos_out[(size_t)orig * 3 + k] = S.m_geo[buf][k][row] + sc * S.m_geo[buf][3 + k][row];
+          for (int k = 0; k < 3; ++k)
+            a.pos_out[(size_t)orig * 3 + k] = __fadd_rn(S.m_geo[buf][k][row], __fmul_rn(sc, S.m_geo[buf][3 + k][row]));
         }
       }
       ray = nxt.ray; vox = nxt.vox;
@@ -935,6 +971,13 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
     a.use_sigmoid[d] = decs[d]->use_sigmoid;
   }
   if (a.n_pass[0] + a.n_pass[1] > TC_MAX_PASSES) return LIDF_ERR_UNSUPPORTED;
+  {  // interleave the two decoders' passes: d0 it0, d1 it0, d0 it1, d1 it1, ... then whatever is left of the longer one
+    int it[2] = {0, 0};
+    a.npt = 0;
+    while (it[0] < a.n_pass[0] || it[1] < a.n_pass[1])
+      for (int d = 0; d < 2; ++d)
+        if (it[d] < a.n_pass[d]) { a.pass_dec[a.npt] = d; a.pass_it[a.npt] = it[d]++; ++a.npt; }
+  }
   a.o0 = decs[0]->init_offset; a.r0 = p->offset_range0; a.r1 = p->offset_range1;
   a.sqrt3 = (float)sqrt(3.0); a.part = p->part_size;
   a.out[0] = p->pred_offset; a.out[1] = p->pred_prob_end; a.pos_out = p->pair_pred_pos;
