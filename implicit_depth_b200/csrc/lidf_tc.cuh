@@ -634,7 +634,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         p = last_of_tile ? 0 : p + 1;
       }
     }
-  } else {
+  } else if (warp < TC_ROW_WARPS) {
     // ================================ row warps: operand build + epilogues ================================
     const int q = warp & 3, g = warp >> 2;            // TMEM lane quadrant, column group
     const int row = q * 32 + lane;
@@ -648,12 +648,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       tc::st_shared_v4(a1row_lo + sk * 4096 + 2048, w[12], w[13], w[14], w[15]);
     };
     struct RowMeta { int orig, vox, ray; float t0, t1; bool valid; };
-    auto load_meta = [&](int tile) {
+    // two-stage load (the second stage depends on the first): issued a pass apart so neither latency is exposed
+    auto load_orig = [&](int tile) {
+      const int64_t s = (int64_t)tile * 128 + row;
+      return s < a.P ? (a.perm ? a.perm[s] : (int)s) : -1;
+    };
+    auto load_meta = [&](int tile, int orig_) {
       RowMeta m{0, 0, 0, 0.f, 0.f, false};
       const int64_t s = (int64_t)tile * 128 + row;
       if (s < a.P) {
         m.valid = true;
-        m.orig = a.perm ? a.perm[s] : (int)s;
+        m.orig = orig_;
         m.vox = (int)a.pair_vox[m.orig]; m.ray = (int)a.pair_ray[m.orig];
         if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)m.orig); m.t0 = t.x; m.t1 = t.y; }
         else { const size_t o = ((size_t)m.vox * a.R + m.ray) * 2; m.t0 = a.dense_dist[o]; m.t1 = a.dense_dist[o + 1]; }
@@ -724,12 +729,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     const uint32_t stage_sa = tc::smem_u32(stage_w);
     auto gather_issue = [&](int vox_, int col) {
       const float* src0 = a.Av + col + 4 * (lane & 7);
+      const float* srcs[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const int src = 4 * i + (lane >> 3);
-        const int rv = __shfl_sync(0xffffffffu, vox_, src);
-        tc::cp_async16(stage_sa + (uint32_t)(src * TC_STAGE_PITCH + 4 * (lane & 7)) * 4u, src0 + (size_t)rv * 512);
-      }
+      for (int i = 0; i < 8; ++i) srcs[i] = src0 + (size_t)__shfl_sync(0xffffffffu, vox_, 4 * i + (lane >> 3)) * 512;
+      const uint32_t dst0 = stage_sa + (uint32_t)((lane >> 3) * TC_STAGE_PITCH + 4 * (lane & 7)) * 4u;
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tc::cp_async16(dst0 + (uint32_t)(4 * i * TC_STAGE_PITCH) * 4u, srcs[i]);
       tc::cp_async_commit();
     };
     auto gather_read = [&](float4 (&t)[8]) {
@@ -792,22 +797,100 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
     };
 
-    // Program order of a row warp (E0/E1 = layer-1 epilogues, E2 = layer 2, E3 = layer 3 + 4):
-    //   E0(first) | E1(p) [build next tile's operand] E2(p) E0(p+1) E3(p) | E1(p+1) ...
-    // E0 of the next pass runs BEFORE E3 of the current one (its accumulator is ready earlier, and the tensor pipe needs
-    // it sooner) unless the next pass is the next IEF iteration of the same decoder, which needs E3's result.
-    RowMeta cur = load_meta((int)blockIdx.x);
+    // Layer-2 epilogue on Y of a pass of decoder d: x = leaky(acc + b2) -> bf16 hi | lo, in place.
+    auto epi_l2 = [&](int d, uint32_t ph) {
+      tc::mbar_wait(&S.y_full, ph);
+      tc::fence_after_sync();
+      uint32_t r[32];
+      tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
+      tc::wait_ld();
+      float x[32];
+      const float4* bp = reinterpret_cast<const float4*>(&S.b2[d][32 * g]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 bv = bp[i];
+        x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + bv.x);
+        x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + bv.y);
+        x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + bv.z);
+        x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + bv.w);
+      }
+      uint32_t w[16];
+      tc::split16(x, w);
+      tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g, w);
+      tc::split16(x + 16, w);
+      tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16, w);
+      tc::wait_st();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.y_done);
+    };
+    // Layer-3 epilogue + layer 4 (64-term dot product, 16 terms per column group) on Z of pass (d, it) of the tile whose
+    // output metadata sits in buffer `buf`; updates the decoder's running value and, after its last pass, writes the
+    // decoder's outputs (column group 0: pred_offset, 1: pred_prob_end, 2: pair_pred_pos).
+    uint32_t par = 0;
+    float o_a = 0.f, o_b = 0.f;                                // running IEF offsets of decoder 0, 1
+    auto epi_l3 = [&](int d, int it, uint32_t ph, int tile_, int buf) {
+      tc::mbar_wait(&S.z_full, ph);
+      tc::fence_after_sync();
+      uint32_t r[16];
+      tc::tmem_ld16(lane_addr + TC_COL_Z + 16 * g, r);
+      tc::wait_ld();
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.z_free);                               // Z may be overwritten by the next pass
+      float partial = 0.f;
+#pragma unroll
+      for (int j = 0; j < 16; ++j) {
+        const int n = 16 * g + j;
+        partial = fmaf(lidf_leaky(__uint_as_float(r[j]) + S.b3[d][n]), S.w4[d][n], partial);
+      }
+      S.part[par][g][row] = partial;
+      tc::bar_rows();                                                          // the 16 row warps only
+      const float l4 = ((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row] + S.b4[d];
+      par ^= 1;
+      const bool is_ief = a.kind[d] == LIDF_DEC_IEF;
+      const float prev = it == 0 ? (is_ief ? a.o0 : 0.f) : (d == 0 ? o_a : o_b);
+      const float onew = is_ief ? prev + l4 : l4;
+      if (d == 0) o_a = onew; else o_b = onew;
+      if (it + 1 == a.n_pass[d] && (int64_t)tile_ * 128 + row < a.P) {
+        const float res = lidf_final_act(onew, a.use_sigmoid[d]);
+        const int orig = S.m_orig[buf][row];
+        if (d == 0) {
+          if (g == 0) a.out[0][orig] = res;
+          else if (g == 2) {
+            float sc = res * (a.r1 - a.r0) + a.r0;           // pipeline.py:437-439
+            sc = sc * a.sqrt3;
+            sc = sc * a.part;
+#pragma unroll
+            for (int k = 0; k < 3; ++k)
+              a.pos_out[(size_t)orig * 3 + k] = __fadd_rn(S.m_geo[buf][k][row], __fmul_rn(sc, S.m_geo[buf][3 + k][row]));
+          }
+        } else if (g == 1) {
+          a.out[1][orig] = res;
+        }
+      }
+    };
+
+    // Program order of a row warp (E0/E1 = layer-1 epilogues, E2 = layer 2, E3 = layer 3 + 4 + outputs):
+    //   E0(first) | E1(p) E3(p-1) [build next tile's operand] E2(p) E0(p+1) | E1(p+1) E3(p) ...
+    // E3 is deferred into the slot where the row warps would otherwise wait for layer 2 of the next pass, and E0 of the
+    // next pass runs before it (its accumulator is ready earlier and the tensor pipe needs it sooner) -- unless the next
+    // pass is the next IEF iteration of the same decoder, which needs E3's result: then E3 runs right after E2.
+    RowMeta cur = load_meta((int)blockIdx.x, load_orig((int)blockIdx.x));
     build_a1(cur, 0);
     int ray = cur.ray, vox = cur.vox;
     bool valid = cur.valid;
-    uint32_t gp = 0, tl = 0, par = 0;
-    float o_a = 0.f, o_b = 0.f, res0 = 0.f, res1 = 0.f;       // running IEF offsets / final values of decoder 0, 1
+    uint32_t gp = 0, tl = 0;
+    bool pend = false;                                         // a deferred E3
+    int pend_d = 0, pend_it = 0, pend_tile = 0, pend_buf = 0;
+    uint32_t pend_ph = 0;
     gather_issue(vox, 256 * a.pass_dec[0] + 32 * g);
     epi_l1(0, a.pass_dec[0], false, 0.f, ray, valid, 0u, vox, 256 * a.pass_dec[0] + 128 + 32 * g);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
       const int next_tile = tile + (int)gridDim.x;
       const bool has_next = next_tile < a.n_tiles;
       RowMeta nxt{0, 0, 0, 0.f, 0.f, false};
+      int orig_n = -1;
       for (int p = 0; p < npt; ++p, ++gp) {
         const int d = a.pass_dec[p], it = a.pass_it[p];
         const uint32_t ph = gp & 1u;
@@ -817,93 +900,32 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         const int pn = last ? 0 : p + 1;
         const int dn = a.pass_dec[pn], itn = a.pass_it[pn];
         const bool dep = !last && dn == d;                                    // next pass continues this decoder's IEF loop
-        if (has_next && p == (npt >= 2 ? npt - 2 : 0)) nxt = load_meta(next_tile);   // prefetch: first used in E1 of the last pass
+        if (has_next && p == 0) orig_n = load_orig(next_tile);               // prefetch, stage 1
+        if (has_next && p == (npt >= 2 ? npt - 2 : 0)) nxt = load_meta(next_tile, orig_n);   // stage 2: first used in E1 of the last pass
         const int vox_n = last ? nxt.vox : vox, ray_n = last ? nxt.ray : ray;
         const bool valid_n = last ? nxt.valid : valid;
         // ---- E1(p)
         epi_l1(1, d, is_ief && it > 0, (d == 0 ? o_a : o_b) - a.o0, ray, valid, ph, vox_n,
                has_next_pass ? 256 * dn + 32 * g : -1);
+        // ---- deferred E3(p-1): fills the wait for layer 2 of this pass
+        if (pend) { epi_l3(pend_d, pend_it, pend_ph, pend_tile, pend_buf); pend = false; }
         // ---- operand of the next tile: its last reader (S2 of this pass) has retired once a1_free completes
         if (last && has_next) {
           tc::mbar_wait(&S.a1_free, tl & 1u);
           build_a1(nxt, (int)((tl + 1) & 1u));
         }
-        // ---- E2: layer-2 epilogue on Y
-        {
-          tc::mbar_wait(&S.y_full, ph);
-          tc::fence_after_sync();
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
-          tc::wait_ld();
-          float x[32];
-          const float4* bp = reinterpret_cast<const float4*>(&S.b2[d][32 * g]);
-#pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float4 bv = bp[i];
-            x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + bv.x);
-            x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + bv.y);
-            x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + bv.z);
-            x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + bv.w);
-          }
-          uint32_t w[16];
-          tc::split16(x, w);
-          tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g, w);
-          tc::split16(x + 16, w);
-          tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16, w);
-          tc::wait_st();
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&S.y_done);
-        }
-        // ---- E0(p+1), when it does not need this pass's result
-        if (has_next_pass && !dep)
+        // ---- E2(p)
+        epi_l2(d, ph);
+        if (has_next_pass && !dep) {
+          // ---- E0(p+1) first, E3(p) deferred
           epi_l1(0, dn, a.kind[dn] == LIDF_DEC_IEF && itn > 0, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n,
                  256 * dn + 128 + 32 * g);
-        // ---- E3: layer-3 epilogue + layer 4 (64-term dot product, 16 terms per column group) on Z
-        {
-          tc::mbar_wait(&S.z_full, ph);
-          tc::fence_after_sync();
-          uint32_t r[16];
-          tc::tmem_ld16(lane_addr + TC_COL_Z + 16 * g, r);
-          tc::wait_ld();
-          tc::fence_before_sync();
-          __syncwarp();
-          if (lane == 0) tc::mbar_arrive(&S.z_free);                           // Z may be overwritten by the next pass
-          float partial = 0.f;
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = 16 * g + j;
-            partial = fmaf(lidf_leaky(__uint_as_float(r[j]) + S.b3[d][n]), S.w4[d][n], partial);
-          }
-          S.part[par][g][row] = partial;
-          tc::bar_rows();                                                      // the 16 row warps only
-          const float l4 = ((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row] + S.b4[d];
-          par ^= 1;
-          const float prev = it == 0 ? (is_ief ? a.o0 : 0.f) : (d == 0 ? o_a : o_b);
-          const float onew = is_ief ? prev + l4 : l4;
-          if (d == 0) o_a = onew; else o_b = onew;
-          if (it + 1 == a.n_pass[d]) {
-            const float res = lidf_final_act(onew, a.use_sigmoid[d]);
-            if (d == 0) res0 = res; else res1 = res;
-          }
-        }
-        // ---- E0(p+1) of a dependent pass
-        if (has_next_pass && dep)
-          epi_l1(0, dn, true, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n, 256 * dn + 128 + 32 * g);
-      }
-      // ---- outputs of the tile (metadata was parked in smem by the operand build)
-      if ((int64_t)tile * 128 + row < a.P) {
-        const int buf = (int)(tl & 1u);
-        const int orig = S.m_orig[buf][row];
-        if (g == 0) a.out[0][orig] = res0;
-        else if (g == 1) a.out[1][orig] = res1;
-        else if (g == 2) {
-          float sc = res0 * (a.r1 - a.r0) + a.r0;            // pipeline.py:437-439
-          sc = sc * a.sqrt3;
-          sc = sc * a.part;
-#pragma unroll
-          for (int k = 0; k < 3; ++k)
-            a.pos_out[(size_t)orig * 3 + k] = __fadd_rn(S.m_geo[buf][k][row], __fmul_rn(sc, S.m_geo[buf][3 + k][row]));
+          pend = true; pend_d = d; pend_it = it; pend_ph = ph; pend_tile = tile; pend_buf = (int)(tl & 1u);
+        } else {
+          // ---- E3(p) now; then E0(p+1) of the dependent pass
+          epi_l3(d, it, ph, tile, (int)(tl & 1u));
+          if (has_next_pass)
+            epi_l1(0, dn, true, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n, 256 * dn + 128 + 32 * g);
         }
       }
       ray = nxt.ray; vox = nxt.vox;
