@@ -363,13 +363,49 @@ __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+// packed fp32 pairs (Blackwell FADD2 / FMUL2 / FFMA2): same IEEE results as the scalar ops, half the instructions
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+  uint64_t r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) { asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v)); }
+__device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b) {
+  uint64_t r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+  uint64_t r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// (v0, v1) -> x = leaky(v) -> bf16 hi pair | lo pair  (hi = bf16_rn(x), lo = bf16_rn(x - hi); element 0 in the low half)
+__device__ __forceinline__ void leaky_split2(uint64_t v, uint32_t& hi, uint32_t& lo) {
+  const uint64_t m = mul2(v, pack2(LIDF_LEAKY, LIDF_LEAKY));
+  float v0, v1, m0, m1;
+  unpack2(v, v0, v1);
+  unpack2(m, m0, m1);
+  const float x0 = fmaxf(v0, m0), x1 = fmaxf(v1, m1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi) : "f"(x1), "f"(x0));
+  const uint64_t h = pack2(__uint_as_float(hi << 16), __uint_as_float(hi & 0xFFFF0000u));
+  float r0, r1;
+  unpack2(fma2(h, pack2(-1.0f, -1.0f), pack2(x0, x1)), r0, r1);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo) : "f"(r1), "f"(r0));
+}
 // 16-byte asynchronous copy global -> shared (LDGSTS), no register staging
 __device__ __forceinline__ void cp_async16(uint32_t dst_saddr, const void* src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(dst_saddr), "l"(src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
-__device__ __forceinline__ void bar_rows() { asm volatile("bar.sync 1, %0;" ::"n"(TC_ROW_THREADS) : "memory"); }
+// named barrier over the 4 row warps of one TMEM lane quadrant (ids 1..4)
+__device__ __forceinline__ void bar_quadrant(int q) { asm volatile("bar.sync %0, 128;" ::"r"(q + 1) : "memory"); }
 }  // namespace tc
 
 struct TcArgs {
@@ -384,8 +420,9 @@ struct TcArgs {
   const float* b2[2]; const float* b3[2]; const float* w4[2]; const float* b4[2];
   int kind[2]; int n_pass[2]; int use_sigmoid[2];
   int npt;                         // passes per tile
-  int pass_dec[TC_MAX_PASSES];     // decoder of pass p: the two decoders are interleaved so that consecutive passes are
-  int pass_it[TC_MAX_PASSES];      // independent wherever possible (IEF iteration k+1 needs the result of iteration k)
+  uint32_t pass_dec_mask;          // bit p = decoder of pass p: the two decoders are interleaved so that consecutive passes
+  uint64_t pass_it_pack;           // are independent wherever possible (IEF iteration k+1 needs iteration k); 4 bits per
+                                   // pass = its iteration index.  Packed so that the kernel indexes them with shifts.
   float o0, r0, r1, sqrt3, part;
   float* out[2];                   // pred_offset, pred_prob_end  (written at the original pair index)
   float* pos_out;                  // pair_pred_pos [P,3]
@@ -556,6 +593,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
   tc::fence_after_sync();
   const uint32_t tmem = S.tmem_base;
   const int npt = a.npt;                                                       // passes per tile
+  const uint32_t dec_mask = a.pass_dec_mask;
+  const uint64_t it_pack = a.pass_it_pack;
+  auto pass_dec = [&](int p) { return (int)((dec_mask >> p) & 1u); };
+  auto pass_it = [&](int p) { return (int)((it_pack >> (4 * p)) & 15u); };
+  const bool ief0 = a.kind[0] == LIDF_DEC_IEF, ief1 = a.kind[1] == LIDF_DEC_IEF;
+  const int npass0 = a.n_pass[0], npass1 = a.n_pass[1], sig0 = a.use_sigmoid[0], sig1 = a.use_sigmoid[1];
   const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   const int total_passes = n_my_tiles * npt;
   // weight-stream segments of one decoder (chunk offsets)
@@ -567,12 +610,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     // ================================ weight loader (TMA), one thread ================================
     if (tc::elect_one()) {
       auto seg = [&](int d, int chunk) { return a.wstream + ((size_t)d * TC_CHUNKS_PER_DEC + chunk) * TC_CHUNK_BYTES; };
-      tc_load_seg<0, 4, 3>(S, seg(a.pass_dec[0], SEG_L1H0), false);
+      tc_load_seg<0, 4, 3>(S, seg(pass_dec(0), SEG_L1H0), false);
       int p = 0;
       for (int gp = 0; gp < total_passes; ++gp) {
-        const int d = a.pass_dec[p];
+        const int d = pass_dec(p);
         const int pn = p + 1 == npt ? 0 : p + 1;
-        const int dn = a.pass_dec[pn];
+        const int dn = pass_dec(pn);
         tc_load_seg<GI_S2, 4, 3>(S, seg(d, SEG_L1H1), gp > 0);
         tc_load_seg<GI_S1, 4, 4>(S, seg(d, SEG_L2K0), true);
         tc_load_seg<GI_S3, 4, 4>(S, seg(d, SEG_L2K1), true);
@@ -761,36 +804,38 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
       tc::mbar_wait(&S.x_full[hf], ph);
       tc::fence_after_sync();
+      uint64_t tp2[16];                                                        // T + A_v, as packed pairs
 #pragma unroll
-      for (int i = 0; i < 8; ++i) { t[i].x += tt[i].x; t[i].y += tt[i].y; t[i].z += tt[i].z; t[i].w += tt[i].w; }
+      for (int i = 0; i < 8; ++i) {
+        tp2[2 * i] = tc::add2(tc::pack2(t[i].x, t[i].y), tc::pack2(tt[i].x, tt[i].y));
+        tp2[2 * i + 1] = tc::add2(tc::pack2(t[i].z, t[i].w), tc::pack2(tt[i].z, tt[i].w));
+      }
       uint32_t r[32];
       tc::tmem_ld32(lane_addr + xcol, r);
       tc::wait_ld();
-      float x[32];
-      if (rank1) {
-        const float4* up = reinterpret_cast<const float4*>(&S.u[n0]);
+      const uint64_t delta2 = tc::pack2(delta, delta);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const float4 uv = up[i];
-          x[4 * i + 0] = lidf_leaky(fmaf(uv.x, delta, __uint_as_float(r[4 * i + 0]) + t[i].x));
-          x[4 * i + 1] = lidf_leaky(fmaf(uv.y, delta, __uint_as_float(r[4 * i + 1]) + t[i].y));
-          x[4 * i + 2] = lidf_leaky(fmaf(uv.z, delta, __uint_as_float(r[4 * i + 2]) + t[i].z));
-          x[4 * i + 3] = lidf_leaky(fmaf(uv.w, delta, __uint_as_float(r[4 * i + 3]) + t[i].w));
-        }
-      } else {
+      for (int s16 = 0; s16 < 2; ++s16) {
+        uint32_t w[16];
+        if (rank1) {
+          const float4* up = reinterpret_cast<const float4*>(&S.u[n0 + 16 * s16]);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + t[i].x);
-          x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + t[i].y);
-          x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + t[i].z);
-          x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + t[i].w);
+          for (int j = 0; j < 8; ++j) {
+            const int e = 16 * s16 + 2 * j;
+            const float4 uv = up[j >> 1];
+            const uint64_t u2 = (j & 1) ? tc::pack2(uv.z, uv.w) : tc::pack2(uv.x, uv.y);
+            const uint64_t v = tc::add2(tc::pack2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), tp2[e >> 1]);
+            tc::leaky_split2(tc::fma2(u2, delta2, v), w[j], w[8 + j]);
+          }
+        } else {
+#pragma unroll
+          for (int j = 0; j < 8; ++j) {
+            const int e = 16 * s16 + 2 * j;
+            tc::leaky_split2(tc::add2(tc::pack2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), tp2[e >> 1]), w[j], w[8 + j]);
+          }
         }
+        tc::tmem_st16(lane_addr + xcol + 16 * s16, w);
       }
-      uint32_t w[16];
-      tc::split16(x, w);
-      tc::tmem_st16(lane_addr + xcol, w);
-      tc::split16(x + 16, w);
-      tc::tmem_st16(lane_addr + xcol + 16, w);
       tc::wait_st();
       tc::fence_before_sync();
       __syncwarp();
@@ -804,21 +849,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       uint32_t r[32];
       tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
       tc::wait_ld();
-      float x[32];
       const float4* bp = reinterpret_cast<const float4*>(&S.b2[d][32 * g]);
 #pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const float4 bv = bp[i];
-        x[4 * i + 0] = lidf_leaky(__uint_as_float(r[4 * i + 0]) + bv.x);
-        x[4 * i + 1] = lidf_leaky(__uint_as_float(r[4 * i + 1]) + bv.y);
-        x[4 * i + 2] = lidf_leaky(__uint_as_float(r[4 * i + 2]) + bv.z);
-        x[4 * i + 3] = lidf_leaky(__uint_as_float(r[4 * i + 3]) + bv.w);
+      for (int s16 = 0; s16 < 2; ++s16) {
+        uint32_t w[16];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          const int e = 16 * s16 + 2 * j;
+          const float4 bv = bp[e >> 2];
+          const uint64_t b2v = (j & 1) ? tc::pack2(bv.z, bv.w) : tc::pack2(bv.x, bv.y);
+          tc::leaky_split2(tc::add2(tc::pack2(__uint_as_float(r[e]), __uint_as_float(r[e + 1])), b2v), w[j], w[8 + j]);
+        }
+        tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16 * s16, w);
       }
-      uint32_t w[16];
-      tc::split16(x, w);
-      tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g, w);
-      tc::split16(x + 16, w);
-      tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16, w);
       tc::wait_st();
       tc::fence_before_sync();
       __syncwarp();
@@ -845,15 +888,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         partial = fmaf(lidf_leaky(__uint_as_float(r[j]) + S.b3[d][n]), S.w4[d][n], partial);
       }
       S.part[par][g][row] = partial;
-      tc::bar_rows();                                                          // the 16 row warps only
+      tc::bar_quadrant(q);                                                     // the 4 warps that share these rows
       const float l4 = ((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row] + S.b4[d];
       par ^= 1;
-      const bool is_ief = a.kind[d] == LIDF_DEC_IEF;
+      const bool is_ief = d == 0 ? ief0 : ief1;
       const float prev = it == 0 ? (is_ief ? a.o0 : 0.f) : (d == 0 ? o_a : o_b);
       const float onew = is_ief ? prev + l4 : l4;
       if (d == 0) o_a = onew; else o_b = onew;
-      if (it + 1 == a.n_pass[d] && (int64_t)tile_ * 128 + row < a.P) {
-        const float res = lidf_final_act(onew, a.use_sigmoid[d]);
+      if (it + 1 == (d == 0 ? npass0 : npass1) && (int64_t)tile_ * 128 + row < a.P) {
+        const float res = lidf_final_act(onew, d == 0 ? sig0 : sig1);
         const int orig = S.m_orig[buf][row];
         if (d == 0) {
           if (g == 0) a.out[0][orig] = res;
@@ -884,21 +927,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     bool pend = false;                                         // a deferred E3
     int pend_d = 0, pend_it = 0, pend_tile = 0, pend_buf = 0;
     uint32_t pend_ph = 0;
-    gather_issue(vox, 256 * a.pass_dec[0] + 32 * g);
-    epi_l1(0, a.pass_dec[0], false, 0.f, ray, valid, 0u, vox, 256 * a.pass_dec[0] + 128 + 32 * g);
+    gather_issue(vox, 256 * pass_dec(0) + 32 * g);
+    epi_l1(0, pass_dec(0), false, 0.f, ray, valid, 0u, vox, 256 * pass_dec(0) + 128 + 32 * g);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
       const int next_tile = tile + (int)gridDim.x;
       const bool has_next = next_tile < a.n_tiles;
       RowMeta nxt{0, 0, 0, 0.f, 0.f, false};
       int orig_n = -1;
       for (int p = 0; p < npt; ++p, ++gp) {
-        const int d = a.pass_dec[p], it = a.pass_it[p];
+        const int d = pass_dec(p), it = pass_it(p);
         const uint32_t ph = gp & 1u;
-        const bool is_ief = a.kind[d] == LIDF_DEC_IEF;
+        const bool is_ief = d == 0 ? ief0 : ief1;
         const bool last = p + 1 == npt;
         const bool has_next_pass = !last || has_next;
         const int pn = last ? 0 : p + 1;
-        const int dn = a.pass_dec[pn], itn = a.pass_it[pn];
+        const int dn = pass_dec(pn), itn = pass_it(pn);
         const bool dep = !last && dn == d;                                    // next pass continues this decoder's IEF loop
         if (has_next && p == 0) orig_n = load_orig(next_tile);               // prefetch, stage 1
         if (has_next && p == (npt >= 2 ? npt - 2 : 0)) nxt = load_meta(next_tile, orig_n);   // stage 2: first used in E1 of the last pass
@@ -918,7 +961,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         epi_l2(d, ph);
         if (has_next_pass && !dep) {
           // ---- E0(p+1) first, E3(p) deferred
-          epi_l1(0, dn, a.kind[dn] == LIDF_DEC_IEF && itn > 0, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n,
+          epi_l1(0, dn, (dn == 0 ? ief0 : ief1) && itn > 0, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n,
                  256 * dn + 128 + 32 * g);
           pend = true; pend_d = d; pend_it = it; pend_ph = ph; pend_tile = tile; pend_buf = (int)(tl & 1u);
         } else {
@@ -995,10 +1038,14 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   if (a.n_pass[0] + a.n_pass[1] > TC_MAX_PASSES) return LIDF_ERR_UNSUPPORTED;
   {  // interleave the two decoders' passes: d0 it0, d1 it0, d0 it1, d1 it1, ... then whatever is left of the longer one
     int it[2] = {0, 0};
-    a.npt = 0;
+    a.npt = 0; a.pass_dec_mask = 0; a.pass_it_pack = 0;
     while (it[0] < a.n_pass[0] || it[1] < a.n_pass[1])
       for (int d = 0; d < 2; ++d)
-        if (it[d] < a.n_pass[d]) { a.pass_dec[a.npt] = d; a.pass_it[a.npt] = it[d]++; ++a.npt; }
+        if (it[d] < a.n_pass[d]) {
+          a.pass_dec_mask |= (uint32_t)d << a.npt;
+          a.pass_it_pack |= (uint64_t)it[d]++ << (4 * a.npt);
+          ++a.npt;
+        }
   }
   a.o0 = decs[0]->init_offset; a.r0 = p->offset_range0; a.r1 = p->offset_range1;
   a.sqrt3 = (float)sqrt(3.0); a.part = p->part_size;
