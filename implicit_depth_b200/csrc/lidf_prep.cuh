@@ -177,9 +177,46 @@ __device__ __forceinline__ void roi_tap(float p, int size, int& lo, int& hi, flo
 }
 
 #define LIDF_ROI_THREADS 256
+// one channel of one ray: the four bins of torchvision's aligned ROIAlign (adaptive sampling grid gh x gw per bin)
+__device__ __forceinline__ void roi_channel_general(const float* __restrict__ fc, int H, int W, float sw, float sh, float bw,
+                                                    float bh, int gw, int gh, float count, float (&o)[4]) {
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+    for (int pw = 0; pw < 2; ++pw) {
+      float acc = 0.f;
+      for (int iy = 0; iy < gh; ++iy) {
+        const float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
+        int ylo, yhi; float ly, hy; bool ydead;
+        roi_tap(y, H, ylo, yhi, ly, hy, ydead);
+        for (int ix = 0; ix < gw; ++ix) {
+          const float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
+          int xlo, xhi; float lx, hx; bool xdead;
+          roi_tap(x, W, xlo, xhi, lx, hx, xdead);
+          float val = 0.f;
+          if (!(ydead || xdead)) {
+            const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+            // same expression order as torchvision: w1*v1 + w2*v2 + w3*v3 + w4*v4; zero-weight taps are skipped
+            // (v finite => identical result) which makes interior pixels one load per sample.
+            val = w1 * __ldg(fc + (size_t)ylo * W + xlo);
+            if (w2 != 0.f) val += w2 * __ldg(fc + (size_t)ylo * W + xhi);
+            if (w3 != 0.f) val += w3 * __ldg(fc + (size_t)yhi * W + xlo);
+            if (w4 != 0.f) val += w4 * __ldg(fc + (size_t)yhi * W + xhi);
+          }
+          acc += val;
+        }
+      }
+      o[ph * 2 + pw] = acc / count;
+    }
+  }
+}
+
+// BOX != nullptr: interior rays (8x8 box not clamped: every sample sits on a pixel centre with weight 1) read their four
+// bins from the 4x4 box-sum map, which was accumulated in the same order -> bit-identical to the general path.
 __global__ void __launch_bounds__(LIDF_ROI_THREADS)
-k_roi_align_rays(const float* __restrict__ feat, int B, int H, int W, const int64_t* __restrict__ img_ind,
-                 const int64_t* __restrict__ bid, int64_t R, int half, float* __restrict__ out) {
+k_roi_align_rays(const float* __restrict__ feat, const float* __restrict__ box, int B, int H, int W,
+                 const int64_t* __restrict__ img_ind, const int64_t* __restrict__ bid, int64_t R, int half,
+                 float* __restrict__ out) {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ray = (int64_t)blockIdx.x * 32 + lane;
   if (ray >= R) return;
@@ -193,41 +230,37 @@ k_roi_align_rays(const float* __restrict__ feat, int B, int H, int W, const int6
   const float bw = rw / 2.0f, bh = rh / 2.0f;
   const int gw = (int)ceilf(rw / 2.0f), gh = (int)ceilf(rh / 2.0f);
   const float count = (float)max(gh * gw, 1);
-  const float* fb = feat + (size_t)b * LIDF_RGB_CH * H * W;
+  const bool interior = box != nullptr && half == 4 && px - 4 >= 0 && px + 4 <= W - 1 && py - 4 >= 0 && py + 4 <= H - 1;
+  const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
   for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
-    const float* fc = fb + (size_t)c * H * W;
     float o[4];
-#pragma unroll
-    for (int ph = 0; ph < 2; ++ph) {
-#pragma unroll
-      for (int pw = 0; pw < 2; ++pw) {
-        float acc = 0.f;
-        for (int iy = 0; iy < gh; ++iy) {
-          const float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
-          int ylo, yhi; float ly, hy; bool ydead;
-          roi_tap(y, H, ylo, yhi, ly, hy, ydead);
-          for (int ix = 0; ix < gw; ++ix) {
-            const float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
-            int xlo, xhi; float lx, hx; bool xdead;
-            roi_tap(x, W, xlo, xhi, lx, hx, xdead);
-            float val = 0.f;
-            if (!(ydead || xdead)) {
-              const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
-              // same expression order as torchvision: w1*v1 + w2*v2 + w3*v3 + w4*v4; zero-weight taps are skipped
-              // (v finite => identical result) which makes interior pixels one load per sample.
-              val = w1 * __ldg(fc + (size_t)ylo * W + xlo);
-              if (w2 != 0.f) val += w2 * __ldg(fc + (size_t)ylo * W + xhi);
-              if (w3 != 0.f) val += w3 * __ldg(fc + (size_t)yhi * W + xlo);
-              if (w4 != 0.f) val += w4 * __ldg(fc + (size_t)yhi * W + xhi);
-            }
-            acc += val;
-          }
-        }
-        o[ph * 2 + pw] = acc / count;
-      }
+    if (interior) {
+      const float* bc = box + plane0 + (size_t)c * H * W + (size_t)(py - 4) * W + (px - 4);
+      o[0] = __ldg(bc) / count;
+      o[1] = __ldg(bc + 4) / count;
+      o[2] = __ldg(bc + (size_t)4 * W) / count;
+      o[3] = __ldg(bc + (size_t)4 * W + 4) / count;
+    } else {
+      roi_channel_general(feat + plane0 + (size_t)c * H * W, H, W, sw, sh, bw, bh, gw, gh, count, o);
     }
     *reinterpret_cast<float4*>(out + (size_t)ray * LIDF_RGB_DIM + c * 4) = make_float4(o[0], o[1], o[2], o[3]);
   }
+}
+
+// 4x4 box sums of every feature plane, accumulated exactly like the interior case of roi_channel_general: acc = 0, then
+// += f[y + iy][x + ix] for iy (outer), ix (inner).  Positions whose box leaves the plane are never read.
+__global__ void k_box4(const float* __restrict__ feat, int64_t n, int H, int W, float* __restrict__ box) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= n) return;
+  const int x = (int)(idx % W), y = (int)((idx / W) % H);
+  if (x > W - 4 || y > H - 4) return;
+  const float* f = feat + idx;
+  float acc = 0.f;
+#pragma unroll
+  for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+    for (int ix = 0; ix < 4; ++ix) acc += __ldg(f + (size_t)iy * W + ix);
+  box[idx] = acc;
 }
 
 // ------------------------------------------------------------------------------------------------

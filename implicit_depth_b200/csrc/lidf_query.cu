@@ -189,11 +189,25 @@ extern "C" int lidf_roi_align_rays(const float* feat, int32_t B, int32_t H, int3
                                    const int64_t* bid, int64_t R, int32_t roi_inp_bbox, float* out, lidf_stream_t stream) {
   if (!feat || !img_ind || !bid || !out) return LIDF_ERR_NULL;
   if (R <= 0) return LIDF_OK;
-  k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, stream>>>(feat, B, H, W, img_ind, bid, R,
+  k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, stream>>>(feat, nullptr, B, H, W, img_ind, bid, R,
                                                                                 roi_inp_bbox / 2, out);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
+
+namespace {
+// ROIAlign per ray through the 4x4 box-sum map (dense ray sets: the map costs a quarter of a ray per pixel)
+int roi_align_rays_box(const float* feat, float* box, int B, int H, int W, const int64_t* img_ind, const int64_t* bid,
+                       int64_t R, int roi_inp_bbox, float* out, cudaStream_t st) {
+  const int64_t n = (int64_t)B * LIDF_RGB_CH * H * W;
+  k_box4<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feat, n, H, W, box);
+  LIDF_LAUNCH_CHECK();
+  k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, st>>>(feat, box, B, H, W, img_ind, bid, R,
+                                                                            roi_inp_bbox / 2, out);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+}  // namespace
 
 extern "C" size_t lidf_ray_terminate_workspace_bytes(int64_t P, int64_t R) {
   Bump b{nullptr, 0};
@@ -225,7 +239,7 @@ namespace {
 struct QueryPlan {
   int impl, pe_pos, pe_dir, D, KR, KP;
   CsrBufs csr;
-  float* roi_feat; float* T; float* Av;
+  float* roi_feat; float* T; float* Av; float* box4;
   SimtPack sp;
   TcBufs tc;
   size_t bytes;
@@ -244,6 +258,9 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
   Bump b{base, 0};
   q->csr = carve_csr(b, p->P, p->R);
   q->roi_feat = p->roi_feat_per_ray ? p->roi_feat_per_ray : b.take<float>((size_t)p->R * LIDF_RGB_DIM);
+  // dense ray sets (at least a third of the pixels) go through the 4x4 box-sum map
+  q->box4 = (p->roi_inp_bbox == 8 && p->H >= 9 && p->W >= 9 && (int64_t)p->R * 3 >= (int64_t)p->B * p->H * p->W)
+                ? b.take<float>((size_t)p->B * LIDF_RGB_CH * p->H * p->W) : nullptr;
   q->T = b.take<float>((size_t)p->R * 512);
   if (q->impl == LIDF_MLP_SIMT_FP32) {
     q->Av = b.take<float>((size_t)p->V * 512);
@@ -293,8 +310,11 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
   // 1. regroup
   if ((rc = build_csr(q.csr, p->pair_ray, P, R, st))) return rc;
   // 2. ROIAlign per ray
-  if ((rc = lidf_roi_align_rays(p->full_rgb_feat, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox,
-                                q.roi_feat, stream))) return rc;
+  if (q.box4) {
+    if ((rc = roi_align_rays_box(p->full_rgb_feat, q.box4, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R,
+                                 p->roi_inp_bbox, q.roi_feat, st))) return rc;
+  } else if ((rc = lidf_roi_align_rays(p->full_rgb_feat, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox,
+                                       q.roi_feat, stream))) return rc;
   if (P > 0) {
     // 3. weights
     const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};

@@ -222,6 +222,19 @@ def test_roi_align_rays_vs_oracle_and_torchvision():
         assert torch.allclose(got, O.roi_align_aligned(feat, boxes).reshape(-1, 128), atol=2e-6, rtol=1e-5)
 
 
+def test_roi_box_sum_path_is_bit_identical_to_general_path():
+    """Dense ray sets take ROIAlign through the 4x4 box-sum map (interior rays) -- same accumulation order, so the
+    per-ray feature must equal the general kernel's bit for bit, border band included."""
+    from implicit_depth_b200.synthetic import make_inputs
+    d = make_inputs(2, 21, 34, 4, V_img=16, seed=11)             # every pixel is a ray -> box path
+    g = torch.Generator().manual_seed(12)
+    off = O.init_decoder("IEF", 385, mode="trained", generator=g)
+    prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
+    out = _run(d, dict(O.DEFAULT_CFG), off, prob, d["part_size"], "simt_fp32", want_roi_feat=True)
+    direct = _lq().roi_align_rays(d["full_rgb_feat"].cuda(), d["miss_img_ind"].cuda(), d["miss_bid"].cuda(), 8)
+    assert torch.equal(out["roi_feat_per_ray"], direct)
+
+
 def test_ray_terminate_vs_scatter_oracle():
     g = torch.Generator().manual_seed(3)
     R, P = 1000, 7000

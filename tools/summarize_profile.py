@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Turn gpurun_out/{launches_<tag>.csv, prof_mlp_tc_<tag>.ncu-rep} into a committed text summary under profiles/.
-Usage: python tools/summarize_profile.py <tag> [note]"""
+Usage: python tools/summarize_profile.py <tag> [note] [workload]"""
 import collections
 import csv
 import io
@@ -9,10 +9,13 @@ import sys
 
 tag = sys.argv[1]
 note = sys.argv[2] if len(sys.argv) > 2 else ""
+wl = sys.argv[3] if len(sys.argv) > 3 else "c2"
+WL_DESC = {"c2": "c2 = 4 images of 320x240 rays x 64 pairs = 19,660,800 points",
+           "c3": "c3 = 8 images of 640x480 rays x 64 pairs = 157,286,400 points (the bench default)"}[wl]
 out = io.StringIO()
 out.write(f"# ncu summary {tag}\n\n{note}\n\n")
-out.write("Command profiled: `python bench.py --workload c2 --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` "
-          "(c2 = 4 images of 320x240 rays x 64 pairs = 19,660,800 points; per-launch times are cold-cache/serialised: compare shares).\n\n")
+out.write(f"Command profiled: `python bench.py --workload {wl} --steps 2 --warmup 3 --no-e2e --no-cpu-baseline` "
+          f"({WL_DESC}; per-launch times are cold-cache/serialised: compare shares).\n\n")
 
 rows = list(csv.reader(open(f"gpurun_out/launches_{tag}.csv")))
 hi = [i for i, r in enumerate(rows) if r and r[0] == "ID"][0]
@@ -69,5 +72,22 @@ for r in sd:
     if op.startswith(("UTC", "UBLKCP", "LDTM", "STTM")):
         mn[op.split(".")[0] if not op.startswith(("LDTM", "STTM")) else op] += 1
 out.write("\n## Blackwell-native SASS mnemonics present (static count)\n\n" + ", ".join(f"{k} x{v}" for k, v in sorted(mn.items())) + "\n")
+# optional: the two row-prep kernels (image-feature gather = ROIAlign per ray; per-ray / per-voxel layer-1 terms)
+import os
+if os.path.exists(f"gpurun_out/prof_prep_{tag}.ncu-rep"):
+    raw = subprocess.run(["ncu", "-i", f"gpurun_out/prof_prep_{tag}.ncu-rep", "--page", "raw", "--csv"],
+                         capture_output=True, text=True).stdout
+    rr = list(csv.reader(io.StringIO(raw)))
+    h = rr[0]
+    cols = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+            "dram__throughput.avg.pct_of_peak_sustained_elapsed", "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed",
+            "lts__throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+            "launch__grid_size", "launch__block_size"]
+    cols = [c for c in cols if c in h]
+    out.write("\n## `ncu --set full` of the row-prep kernels (one launch each)\n\n| " + " | ".join(cols) + " |\n|" + "---|" * len(cols) + "\n")
+    out.write("| " + " | ".join(rr[1][h.index(c)] for c in cols) + " |\n")
+    for r in rr[2:]:
+        if len(r) == len(h):
+            out.write("| " + " | ".join(r[h.index(c)][:40] for c in cols) + " |\n")
 open(f"profiles/{tag}_k_mlp_tc.md", "w").write(out.getvalue())
 print(out.getvalue())
