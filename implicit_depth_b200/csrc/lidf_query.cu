@@ -346,8 +346,16 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
       a.Wt = sp.Wt_row; a.Kpad = sp.KR; a.Ntot = sp.Ntot; a.bias = sp.bias_row; a.out = q.T;
       const size_t smem = sizeof(float) * ((size_t)LIDF_SIMT_BM * a.Kpad + LIDF_KC * 128);
       LIDF_CUDA(cudaFuncSetAttribute(k_rowprep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
-      k_rowprep<<<dim3((unsigned)((R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem, st>>>(a);
-      LIDF_LAUNCH_CHECK();
+      // tensor-core row prep for the shipped layout ([roi 128 | PE(dir) 27] -> K = 160, both decoders -> N = 512)
+      const bool rp_tc = q.impl != LIDF_MLP_SIMT_FP32 && sp.KR == 16 * RP_KSTEPS && sp.Ntot == 512 && p->pos_encode &&
+                         p->multires_views == 4 && tc_device_ok();
+      if (rp_tc) {
+        if ((rc = tc_rowprep_forward(q.roi_feat, p->miss_ray_dir, R, sp.Wt_row, sp.Ntot, sp.bias_row, q.tc.rp_wstream, q.T,
+                                     q.impl, st, &g_launches, g_cuda_err, sizeof(g_cuda_err)))) return rc;
+      } else {
+        k_rowprep<<<dim3((unsigned)((R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem, st>>>(a);
+        LIDF_LAUNCH_CHECK();
+      }
       if (V > 0) {
         a.featA = p->occ_voxel_feat; a.dirs = nullptr; a.rows = V; a.Wt = sp.Wt_vox; a.Kpad = 128; a.bias = nullptr;
         a.out = q.Av;

@@ -982,14 +982,226 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
   if (warp == TC_ROW_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
+// ------------------------------------------------------------------------------------------------ per-ray row prep
+// T[ray][512] = [roi(128) | PE(dir)(27) | 0 x 5] W_row^T + bias for both decoders (the per-ray layer-1 term) on the tensor
+// cores with the same split-bf16 arithmetic: 128 rays per tile, K = 160 (10 k-steps), N = 4 x 128 (one TMEM quarter per
+// N-chunk).  Simple tile-serial structure (operand build -> 4 x MMA chunk -> epilogue overlapping the next chunk): the
+// whole job is ~1 ms.  8 row warps (TMEM quadrant q, column half h), warp 8 = MMA issuer, warp 9 = weight loader.
+#define RP_KSTEPS 10
+#define RP_ROW_WARPS 8
+#define RP_THREADS ((RP_ROW_WARPS + 2) * 32)
+#define RP_A_PART_BYTES (RP_KSTEPS * 4096)
+#define RP_STAGES 5
+
+struct TcRowPrepArgs {
+  const float* feat;               // [rows][128] ROI feature per ray
+  const float* dirs;               // [rows][3]
+  int64_t rows; int n_tiles;
+  const uint8_t* wstream;          // [4 N-chunks][10 k-steps][8 KB]
+  const float* bias;               // [512]
+  float* out;                      // [rows][512]
+};
+struct TcRowPrepSmem {
+  uint8_t w[RP_STAGES][TC_STAGE_BYTES];
+  uint8_t a[2][RP_A_PART_BYTES];     // [hi|lo][kstep(10)][kgroup(2)][128 rows][16 B]
+  float bias[512];
+  uint64_t w_full[RP_STAGES], w_empty[RP_STAGES];
+  uint64_t a_ready, a_free, d_full[4], d_free[4];
+  uint32_t tmem_base;
+};
+
+// weight stream: chunk (c, s) = N rows 128 c .. 128 c + 127, K elements 16 s .. 16 s + 15 of Wt [Kpad][Ntot]
+__global__ void k_pack_rowprep_tc(const float* __restrict__ Wt, int Ntot, uint8_t* __restrict__ stream) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= 4 * RP_KSTEPS * 2048) return;
+  const int ch = idx / 2048, r = idx % 2048, c = ch / RP_KSTEPS, ks = ch % RP_KSTEPS, n = r / 16, kk = r % 16;
+  const float w = Wt[(size_t)(16 * ks + kk) * Ntot + 128 * c + n];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const size_t off = (size_t)(kk >> 3) * 128 * 16 + (size_t)n * 16 + (kk & 7) * 2;
+  uint8_t* base = stream + (size_t)ch * TC_CHUNK_BYTES;
+  *reinterpret_cast<__nv_bfloat16*>(base + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(base + 128 * 32 + off) = lo;
+}
+
+template <int NPROD>
+__global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_constant__ TcRowPrepArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  TcRowPrepSmem& S = *reinterpret_cast<TcRowPrepSmem*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < 512; i += RP_THREADS) S.bias[i] = a.bias ? a.bias[i] : 0.f;
+  if (tid == 0) {
+    for (int i = 0; i < RP_STAGES; ++i) { tc::mbar_init(&S.w_full[i], 1); tc::mbar_init(&S.w_empty[i], 1); }
+    tc::mbar_init(&S.a_ready, RP_ROW_WARPS);
+    tc::mbar_init(&S.a_free, 1);
+    for (int i = 0; i < 4; ++i) { tc::mbar_init(&S.d_full[i], 1); tc::mbar_init(&S.d_free[i], RP_ROW_WARPS); }
+    tc::fence_barrier_init();
+  }
+  if (warp == RP_ROW_WARPS) tc::tmem_alloc(&S.tmem_base, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+
+  if (warp == RP_ROW_WARPS + 1) {
+    // ---- weight loader: 20 fills of 16 KB per tile (4 N-chunks x 5), ring of 5 -> slot = fill % 5, 4 rotations / tile
+    if (tc::elect_one()) {
+      for (int t = 0; t < n_my_tiles; ++t) {
+#pragma unroll
+        for (int f = 0; f < 20; ++f) {
+          const int slot = f % RP_STAGES;
+          const uint32_t par = (uint32_t)((f / RP_STAGES) & 1);
+          if (t > 0 || f >= RP_STAGES) tc::mbar_wait(&S.w_empty[slot], par ^ 1u);
+          tc::mbar_arrive_expect_tx(&S.w_full[slot], TC_STAGE_BYTES);
+          tc::bulk_g2s(S.w[slot], a.wstream + (size_t)f * TC_STAGE_BYTES, TC_STAGE_BYTES, &S.w_full[slot]);
+        }
+      }
+    }
+  } else if (warp == RP_ROW_WARPS) {
+    // ---- MMA issuer
+    if (tc::elect_one()) {
+      constexpr uint32_t idesc = tc::make_idesc(128);
+      const uint64_t wd = tc::make_bdesc(tc::smem_u32(S.w[0]), 2048u, 128u);
+      const uint64_t ad = tc::make_bdesc(tc::smem_u32(S.a[0]), 2048u, 128u);
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const uint32_t ph = (uint32_t)t & 1u;
+        tc::mbar_wait(&S.a_ready, ph);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          if (t > 0) { tc::mbar_wait(&S.d_free[c], ph ^ 1u); tc::fence_after_sync(); }
+#pragma unroll
+          for (int j = 0; j < 5; ++j) {
+            const int f = 5 * c + j, slot = f % RP_STAGES;
+            tc::mbar_wait(&S.w_full[slot], (uint32_t)((f / RP_STAGES) & 1));
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+              const int ks = 2 * j + i;
+              const uint64_t bhi = wd + ((uint32_t)(slot * TC_STAGE_BYTES + i * TC_CHUNK_BYTES) >> 4);
+              const uint64_t ahi = ad + ((uint32_t)(ks * 4096) >> 4);
+              tc::mma_ss(tmem + 128 * c, ahi, bhi, idesc, ks == 0 ? 0u : 1u);
+              if (NPROD == 3) {
+                tc::mma_ss(tmem + 128 * c, ahi + ((uint32_t)RP_A_PART_BYTES >> 4), bhi, idesc, 1u);
+                tc::mma_ss(tmem + 128 * c, ahi, bhi + (4096u >> 4), idesc, 1u);
+              }
+            }
+            tc::commit(&S.w_empty[slot]);
+          }
+          tc::commit(&S.d_full[c]);
+        }
+        tc::commit(&S.a_free);
+      }
+    }
+  } else {
+    // ---- row warps: operand build + epilogue
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t a_hi = tc::smem_u32(S.a[0]), a_lo = tc::smem_u32(S.a[1]);
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int64_t row0 = (int64_t)tile * 128;
+      const uint32_t ph = (uint32_t)t & 1u;
+      if (t > 0) tc::mbar_wait(&S.a_free, ph ^ 1u);
+      // feature part (k-steps 0-7): one instruction = 8 rows x one k-step, 4 lanes x 16 B per row
+      {
+        const int r8 = lane >> 2, j4 = lane & 3;
+#pragma unroll 4
+        for (int it = warp; it < 16 * 8; it += RP_ROW_WARPS) {
+          const int rg = it >> 3, ks = it & 7;
+          const int r = 8 * rg + r8;
+          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (row0 + r < a.rows) v = __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)(row0 + r) * 128 + 16 * ks) + j4);
+          uint32_t h0, l0, h1, l1;
+          tc::split2(v.x, v.y, h0, l0);
+          tc::split2(v.z, v.w, h1, l1);
+          const uint32_t off = (uint32_t)(ks * 4096 + (j4 >> 1) * 2048 + r * 16 + 8 * (j4 & 1));
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + off), "r"(l0), "r"(l1) : "memory");
+        }
+      }
+      // PE(dir) part (k-steps 8, 9): Embedder order [x, sin f0 x, cos f0 x, sin f1 x, ...], f = 1, 2, 4, 8; 27 values
+      if (h == 0) {
+        float x[32];
+#pragma unroll
+        for (int k = 0; k < 32; ++k) x[k] = 0.f;
+        if (row0 + row < a.rows) {
+          const float* dp = a.dirs + (size_t)(row0 + row) * 3;
+#pragma unroll
+          for (int c = 0; c < 3; ++c) {
+            const float dv = dp[c];
+            x[c] = dv;
+            float sn, cs;
+            sincosf(dv, &sn, &cs);
+#pragma unroll
+            for (int k = 0; k < 4; ++k) {
+              x[3 + 6 * k + c] = sn; x[3 + 6 * k + 3 + c] = cs;
+              const float s2 = 2.0f * sn * cs, c2 = 1.0f - 2.0f * sn * sn;
+              sn = s2; cs = c2;
+            }
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          uint32_t w[16];
+          tc::split16(x + 16 * j, w);
+          const uint32_t off = (uint32_t)((8 + j) * 4096 + row * 16);
+          tc::st_shared_v4(a_hi + off, w[0], w[1], w[2], w[3]);
+          tc::st_shared_v4(a_hi + off + 2048, w[4], w[5], w[6], w[7]);
+          tc::st_shared_v4(a_lo + off, w[8], w[9], w[10], w[11]);
+          tc::st_shared_v4(a_lo + off + 2048, w[12], w[13], w[14], w[15]);
+        }
+      }
+      tc::fence_proxy_async();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.a_ready);
+      // epilogue: this thread owns columns [64 h, 64 h + 64) of every N-chunk of its row
+      const bool live = row0 + row < a.rows;
+      float* orow = a.out + (size_t)(row0 + row) * 512 + 64 * h;
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        tc::mbar_wait(&S.d_full[c], ph);
+        tc::fence_after_sync();
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          uint32_t r[32];
+          tc::tmem_ld32(lane_addr + 128 * c + 64 * h + 32 * k, r);
+          tc::wait_ld();
+          if (live) {
+            const float* bp = &S.bias[128 * c + 64 * h + 32 * k];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              float4 o;
+              o.x = __uint_as_float(r[4 * i + 0]) + bp[4 * i + 0];
+              o.y = __uint_as_float(r[4 * i + 1]) + bp[4 * i + 1];
+              o.z = __uint_as_float(r[4 * i + 2]) + bp[4 * i + 2];
+              o.w = __uint_as_float(r[4 * i + 3]) + bp[4 * i + 3];
+              *reinterpret_cast<float4*>(orow + 128 * c + 32 * k + 4 * i) = o;
+            }
+          }
+        }
+        tc::fence_before_sync();
+        __syncwarp();
+        if (lane == 0) tc::mbar_arrive(&S.d_free[c]);
+      }
+    }
+  }
+  __syncwarp();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == RP_ROW_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
 // ------------------------------------------------------------------------------------------------ host side
-struct TcBufs { uint8_t* wstream; };
+struct TcBufs { uint8_t* wstream; uint8_t* rp_wstream; };
 
 template <typename B>
 inline TcBufs carve_tc(B& b, int64_t V, int n_dec) {
   TcBufs t;
   (void)V;
   t.wstream = b.template take<uint8_t>((size_t)n_dec * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES);
+  t.rp_wstream = b.template take<uint8_t>((size_t)4 * RP_KSTEPS * TC_CHUNK_BYTES);
   return t;
 }
 
@@ -1064,6 +1276,30 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   if (mlp_event) mlp_event(0, st);
   kern<<<grid, TC_THREADS, smem, st>>>(a);
   if (mlp_event) mlp_event(1, st);
+  TC_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+// per-ray layer-1 term on the tensor cores; Wt = sp.Wt_row [160][512], wstream scratch = 4 x 10 x 8 KB
+inline int tc_rowprep_forward(const float* roi_feat, const float* dirs, int64_t R, const float* Wt, int Ntot, const float* bias,
+                              uint8_t* wstream, float* T, int impl, cudaStream_t st, int64_t* launches, char* errbuf,
+                              size_t errlen) {
+  k_pack_rowprep_tc<<<(4 * RP_KSTEPS * 2048 + 255) / 256, 256, 0, st>>>(Wt, Ntot, wstream);
+  TC_LAUNCH_CHECK();
+  TcRowPrepArgs a{};
+  a.feat = roi_feat; a.dirs = dirs; a.rows = R; a.n_tiles = (int)((R + 127) / 128);
+  a.wstream = wstream; a.bias = bias; a.out = T;
+  int dev = 0, sms = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int grid = a.n_tiles < sms ? a.n_tiles : sms;
+  const size_t smem = sizeof(TcRowPrepSmem) + 1024;
+  auto kern = impl == LIDF_MLP_TC_BF16X1 ? k_rowprep_tc<1> : k_rowprep_tc<3>;
+  if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) {
+    snprintf(errbuf, errlen, "cudaFuncSetAttribute(k_rowprep_tc, %zu) failed: %s", smem, cudaGetErrorString(cudaGetLastError()));
+    return LIDF_ERR_CUDA;
+  }
+  kern<<<grid, RP_THREADS, smem, st>>>(a);
   TC_LAUNCH_CHECK();
   return LIDF_OK;
 }
