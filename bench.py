@@ -244,7 +244,7 @@ def main():
     # ---- e2e: the same call with pinned HOST buffers, H2D + D2H inside the timed region ----------------------
     e2e = None
     if not args.no_e2e:
-        host = {k: d[k].cpu().pin_memory() for k in lidf_query.INPUT_KEYS}
+        host = {k: d[k].cpu().pin_memory() for k in lidf_query.INPUT_KEYS + ("occ_vox_bid",)}   # occ_vox_bid stays on the host
         out_host, h2d, d2h = lidf_query.forward_host(host, off, prob, dev, **kw)         # warm-up, allocates pinned outputs
         lidf_query.forward_host(host, off, prob, dev, out_host=out_host, **kw)
         barrier()

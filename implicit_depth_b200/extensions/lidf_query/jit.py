@@ -200,21 +200,114 @@ class _LidfQuery:
                   "occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist")
     OUTPUT_KEYS = ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos")
 
-    def forward_host(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, out_host=None, **kw):
+    def image_splits(self, host: Dict[str, torch.Tensor], B: int):
+        """Per-image offsets into the ray / voxel / pair arrays ([B+1] python lists) for the pipelined host path.
+        The reference keeps rays and voxels image-major (``miss_bid`` / ``occ_vox_bid`` sorted: pipeline.py:226-262,
+        point_utils.py:44-60) and its pair list voxel-major (``torch.nonzero`` of mask[V,R], pipeline.py:283-285), so
+        every image owns one contiguous slice of each array.  Found by binary search (O(B log P) on the host);
+        ``forward_host`` verifies on the device that each slice really is self-contained."""
+        if "occ_vox_bid" not in host:
+            return None
+        edges = torch.arange(B + 1, dtype=torch.int64)
+        rays = torch.searchsorted(host["miss_bid"], edges).tolist()
+        voxels = torch.searchsorted(host["occ_vox_bid"].to(torch.int64), edges).tolist()
+        pairs = torch.searchsorted(host["occ_vox_intersect_idx"], torch.tensor(voxels, dtype=torch.int64)).tolist()
+        return dict(rays=rays, voxels=voxels, pairs=pairs)
+
+    def forward_host(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, out_host=None,
+                     pipeline: bool = True, min_chunk_pairs: int = 1 << 22, **kw):
         """Same call with HOST buffers (pinned for async copies): H2D of every input, the fused forward, D2H of every
-        output, then a stream synchronise.  Returns (out_host dict, h2d_bytes, d2h_bytes)."""
+        output, then a synchronise.  Returns (out_host dict, h2d_bytes, d2h_bytes).
+
+        The path shards by image, so with ``pipeline`` the batch is cut into groups of whole
+        images and run as a three-stage pipeline on three CUDA streams -- H2D of group i+1 and D2H of group i-1 overlap
+        the decoder kernels of group i.  Needs ``host['occ_vox_bid']`` (the reference's data_dict key) next to
+        INPUT_KEYS to find the per-image slices; without it, or when the arrays are not image-contiguous, the whole
+        batch goes through one copy-in / compute / copy-out sequence."""
         dev = torch.device(device)
-        ins = [host[k].to(dev, non_blocking=True) for k in self.INPUT_KEYS]
+        B = int(host["full_rgb_feat"].shape[0])
+        P = int(host["occ_vox_intersect_idx"].shape[0]); R = int(host["miss_ray_dir"].shape[0])
         h2d = sum(host[k].numel() * host[k].element_size() for k in self.INPUT_KEYS)
-        out = self.forward(*ins, offset_dec, prob_dec, **kw)
+        if host["intersect_dist"].dim() != 2 or kw.get("pcl_label_float") is not None:
+            pipeline = False                                # dense dist[V,R,2] / label branch: monolithic call
+        splits = self.image_splits(host, B) if (pipeline and B > 1) else None
+        groups = []
+        if splits is not None:
+            b0 = 0
+            for b in range(1, B + 1):
+                if splits["pairs"][b] - splits["pairs"][b0] >= min_chunk_pairs or b == B:
+                    groups.append((b0, b)); b0 = b
         if out_host is None:
-            out_host = {k: torch.empty(out[k].shape, dtype=out[k].dtype, pin_memory=True) for k in self.OUTPUT_KEYS}
-        d2h = 0
+            f32 = dict(dtype=torch.float32, pin_memory=True)
+            out_host = dict(pred_offset=torch.empty(P, 1, **f32), pred_prob_end=torch.empty(P, 1, **f32),
+                            pair_pred_pos=torch.empty(P, 3, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
+                            max_pair_id=torch.empty(R, dtype=torch.int64, pin_memory=True),
+                            pred_pos=torch.empty(R, 3, **f32))
+        d2h = sum(out_host[k].numel() * out_host[k].element_size() for k in self.OUTPUT_KEYS)
+        if len(groups) > 1 and self._forward_host_pipelined(host, offset_dec, prob_dec, dev, out_host, splits, groups, kw):
+            return out_host, h2d, d2h
+        ins = [host[k].to(dev, non_blocking=True) for k in self.INPUT_KEYS]
+        out = self.forward(*ins, offset_dec, prob_dec, **kw)
         for k in self.OUTPUT_KEYS:
             out_host[k].copy_(out[k], non_blocking=True)
-            d2h += out[k].numel() * out[k].element_size()
         torch.cuda.current_stream(dev).synchronize()
         return out_host, h2d, d2h
+
+    def _forward_host_pipelined(self, host, offset_dec, prob_dec, dev, out_host, splits, groups, kw) -> bool:
+        """Three-stage pipeline over image groups.  Returns False (nothing usable written) when a group turns out not
+        to be self-contained, i.e. some pair of its slice references a ray or voxel outside the group."""
+        P = int(host["occ_vox_intersect_idx"].shape[0])
+        if getattr(self, "_host_streams", None) is None or self._host_streams[0].device != dev:
+            self._host_streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
+        s_in, s_cmp, s_out = self._host_streams
+        cur = torch.cuda.current_stream(dev)
+        for s in (s_in, s_cmp, s_out):
+            s.wait_stream(cur)
+        bad = torch.zeros(1, dtype=torch.int64, device=dev)
+        live = []                                           # keeps every staged tensor alive until the final sync
+        for (b0, b1) in groups:
+            r0, r1 = splits["rays"][b0], splits["rays"][b1]
+            v0, v1 = splits["voxels"][b0], splits["voxels"][b1]
+            p0, p1 = splits["pairs"][b0], splits["pairs"][b1]
+            with torch.cuda.stream(s_in):
+                up = lambda t: t.to(dev, non_blocking=True)
+                ins = dict(full_rgb_feat=up(host["full_rgb_feat"][b0:b1]), occ_voxel_feat=up(host["occ_voxel_feat"][v0:v1]),
+                           miss_ray_dir=up(host["miss_ray_dir"][r0:r1]), miss_img_ind=up(host["miss_img_ind"][r0:r1]),
+                           miss_bid=up(host["miss_bid"][r0:r1]), voxel_bound=up(host["voxel_bound"][v0:v1]),
+                           occ_vox_intersect_idx=up(host["occ_vox_intersect_idx"][p0:p1]),
+                           miss_ray_intersect_idx=up(host["miss_ray_intersect_idx"][p0:p1]),
+                           intersect_dist=up(host["intersect_dist"][p0:p1]))
+                ev_in = torch.cuda.Event(); ev_in.record(s_in)
+            with torch.cuda.stream(s_cmp):
+                s_cmp.wait_event(ev_in)
+                # re-base the group's indices to its own slices and check that the slice is self-contained
+                pv, pr, mb = ins["occ_vox_intersect_idx"], ins["miss_ray_intersect_idx"], ins["miss_bid"]
+                pv.sub_(v0); pr.sub_(r0); mb.sub_(b0)
+                if p1 > p0:
+                    lo_v, hi_v = torch.aminmax(pv); lo_r, hi_r = torch.aminmax(pr)
+                    bad += ((lo_v < 0) | (hi_v >= v1 - v0) | (lo_r < 0) | (hi_r >= r1 - r0)).to(torch.int64)
+                    pv.clamp_(0, max(v1 - v0 - 1, 0)); pr.clamp_(0, max(r1 - r0 - 1, 0))   # never fault; `bad` discards
+                if r1 > r0:
+                    lo_b, hi_b = torch.aminmax(mb)
+                    bad += ((lo_b < 0) | (hi_b >= b1 - b0)).to(torch.int64)
+                    mb.clamp_(0, b1 - b0 - 1)
+                out = self.forward(*[ins[k] for k in self.INPUT_KEYS], offset_dec, prob_dec, **kw)
+                mp = out["max_pair_id"]                     # local pair ids -> ids in the whole list; empty ray -> P
+                out["max_pair_id"] = torch.where(mp == p1 - p0, P, mp + p0)
+                ev_cmp = torch.cuda.Event(); ev_cmp.record(s_cmp)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(ev_cmp)
+                for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax"):
+                    out_host[k][p0:p1].copy_(out[k], non_blocking=True)
+                out_host["max_pair_id"][r0:r1].copy_(out["max_pair_id"], non_blocking=True)
+                out_host["pred_pos"][r0:r1].copy_(out["pred_pos"], non_blocking=True)
+            live.append((ins, out))
+        cur.wait_stream(s_cmp); cur.wait_stream(s_out)
+        for s in (s_in, s_cmp, s_out):
+            s.synchronize()
+        ok = int(bad.item()) == 0
+        del live
+        return ok
 
     # ------------------------------------------------------------------ fused get_embedding + get_pred
     def forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,

@@ -99,3 +99,21 @@ def test_synthetic_generator_contract():
     vb = d["voxel_bound"]
     assert torch.allclose(vb[:, 3:] - vb[:, :3], torch.full((64, 3), 0.25))
     assert [shard_images(8, r, 3) for r in range(3)] == [(0, 3), (3, 3), (6, 2)]
+
+
+def test_image_splits_of_the_reference_layout():
+    """Per-image slices of the ray / voxel / pair arrays used by the pipelined host path (rays and voxels image-major,
+    pair list voxel-major -- reference pipeline.py:226-262, :283-285)."""
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    from implicit_depth_b200.synthetic import make_inputs
+    d = make_inputs(3, 10, 12, 4, V_img=16, seed=3, ragged=True)
+    s = lidf_query.image_splits(d, 3)
+    assert s["rays"] == [0, 120, 240, 360] and s["voxels"] == [0, 16, 32, 48]
+    vox, ray = d["occ_vox_intersect_idx"], d["miss_ray_intersect_idx"]
+    for b in range(3):
+        p0, p1 = s["pairs"][b], s["pairs"][b + 1]
+        assert bool(((vox[p0:p1] >= s["voxels"][b]) & (vox[p0:p1] < s["voxels"][b + 1])).all())
+        assert bool(((ray[p0:p1] >= s["rays"][b]) & (ray[p0:p1] < s["rays"][b + 1])).all())
+    assert s["pairs"][-1] == vox.shape[0]
+    d.pop("occ_vox_bid")
+    assert lidf_query.image_splits(d, 3) is None
