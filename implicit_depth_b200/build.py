@@ -15,7 +15,8 @@ CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO, "include")
 LIB_PATH = os.path.join(CSRC, "liblidf_query.so")
 SOURCES = ["lidf_query.cu"]
-HEADERS = ["lidf_common.cuh", "lidf_prep.cuh", "lidf_simt.cuh", "lidf_tc.cuh", os.path.join(INCLUDE, "lidf_query.h")]
+HEADERS = ["lidf_common.cuh", "lidf_prep.cuh", "lidf_simt.cuh", "lidf_tc.cuh", "lidf_aabb.cuh",
+           os.path.join(INCLUDE, "lidf_query.h"), os.path.join(INCLUDE, "lidf_aabb.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
 NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]   # accurate sincosf/expf are required

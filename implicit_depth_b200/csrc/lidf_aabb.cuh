@@ -1,0 +1,255 @@
+// lidf_aabb.cuh -- ray / point vs voxel-box tests (include/lidf_aabb.h), sm_100a.
+//
+// Bit-identical to the reference kernels (src/extensions/ray_aabb/ray_aabb_cuda_kernel.cu:10-89,
+// src/extensions/pcl_aabb/pcl_aabb_cuda_kernel.cu:10-45).  What differs is the work and the traffic:
+//   * the reference evaluates three double-precision reciprocals 1/(d+1e-12) per (voxel, ray); here once per ray
+//     (k_aabb_ray_prep), the slab test itself is 6 single-precision products + compares;
+//   * the reference launches V x ceil(R/1024) blocks that mostly exit on `ray_bid != voxel_bid`; here a persistent grid
+//     (a multiple of the SM count) walks (voxel, 1024-ray tile) work items and skips a tile whose image-id range
+//     cannot contain the voxel's image after two loads;
+//   * the pair list is produced directly (count -> scan -> fill, in torch.nonzero order) instead of writing and
+//     re-reading the dense 12*V*R-byte mask/dist slab; the dense outputs exist only as a drop-in.
+// All kernels are HBM/L2-bound byte movers: coalesced 4/8-byte accesses per thread, streaming stores for write-once
+// outputs, no tensor-core work.
+#pragma once
+#include "lidf_aabb.h"
+#include "lidf_common.cuh"
+#include "lidf_prep.cuh"
+
+#define AABB_THREADS 256
+#define AABB_RPT 4                              // rays (points) per thread
+#define AABB_TILE (AABB_THREADS * AABB_RPT)      // 1024 rays per work item -- the reference's block size
+#define AABB_WARPS (AABB_THREADS / 32)
+
+struct AabbBox { float lo[3], hi[3]; };
+
+__device__ __forceinline__ AabbBox aabb_load_box(const float* __restrict__ voxel_bound, int64_t v) {
+  AabbBox b;
+  const float* p = voxel_bound + v * 6;
+  b.lo[0] = __ldg(p + 0); b.lo[1] = __ldg(p + 1); b.lo[2] = __ldg(p + 2);
+  b.hi[0] = __ldg(p + 3); b.hi[1] = __ldg(p + 4); b.hi[2] = __ldg(p + 5);
+  return b;
+}
+
+// ray_aabb_cuda_kernel.cu:28-83 with the reciprocal direction already formed.  __fmul_rn keeps the six products
+// plain IEEE multiplies (the reference has no multiply-add here either).
+__device__ __forceinline__ bool aabb_slab(float ix, float iy, float iz, const AabbBox& b, float& t_enter, float& t_leave) {
+  const float txmin = __fmul_rn(ix >= 0 ? b.lo[0] : b.hi[0], ix), txmax = __fmul_rn(ix >= 0 ? b.hi[0] : b.lo[0], ix);
+  const float tymin = __fmul_rn(iy >= 0 ? b.lo[1] : b.hi[1], iy), tymax = __fmul_rn(iy >= 0 ? b.hi[1] : b.lo[1], iy);
+  float tmin_max = txmin, tmax_min = txmax;
+  if ((tmin_max > tymax) || (tmax_min < tymin)) return false;
+  tmin_max = fmaxf(tmin_max, tymin);
+  tmax_min = fminf(tmax_min, tymax);
+  const float tzmin = __fmul_rn(iz >= 0 ? b.lo[2] : b.hi[2], iz), tzmax = __fmul_rn(iz >= 0 ? b.hi[2] : b.lo[2], iz);
+  if ((tmin_max > tzmax) || (tmax_min < tzmin)) return false;
+  t_enter = fmaxf(tmin_max, tzmin);
+  t_leave = fminf(tmax_min, tzmax);
+  return true;
+}
+
+// pcl_aabb_cuda_kernel.cu:28-42 (closed box; the comparisons are written exactly as the reference's so NaN behaves alike)
+__device__ __forceinline__ bool aabb_inside(float x, float y, float z, const AabbBox& b) {
+  if ((x < b.lo[0]) || (x > b.hi[0])) return false;
+  if ((y < b.lo[1]) || (y > b.hi[1])) return false;
+  if ((z < b.lo[2]) || (z > b.hi[2])) return false;
+  return true;
+}
+
+// ---- pre-pass: reciprocal directions + image-id range of every 1024-ray tile ------------------------------------
+__global__ void __launch_bounds__(AABB_THREADS) k_aabb_ray_prep(const float* __restrict__ ray_dir, const int32_t* __restrict__ ray_bid,
+                                                                int64_t R, float* __restrict__ inv, int2* __restrict__ tile_bid) {
+  __shared__ int s_min, s_max;
+  if (threadIdx.x == 0) { s_min = INT_MAX; s_max = INT_MIN; }
+  __syncthreads();
+  int lo = INT_MAX, hi = INT_MIN;
+  const int64_t base = (int64_t)blockIdx.x * AABB_TILE;
+#pragma unroll
+  for (int j = 0; j < AABB_RPT; ++j) {
+    const int64_t r = base + j * AABB_THREADS + threadIdx.x;
+    if (r < R) {
+      const int b = ray_bid[r];
+      lo = min(lo, b); hi = max(hi, b);
+#pragma unroll
+      for (int a = 0; a < 3; ++a)       // float(1 / (double(d) + 1e-12)): ray_aabb_cuda_kernel.cu:32,48,67
+        inv[r * 3 + a] = __double2float_rn(1.0 / ((double)ray_dir[r * 3 + a] + 1e-12));
+    }
+  }
+  lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+  if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
+  __syncthreads();
+  if (threadIdx.x == 0) tile_bid[blockIdx.x] = make_int2(s_min, s_max);
+}
+
+// ---- compact pair list: count -------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(AABB_THREADS) k_aabb_count(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
+                                                             const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
+                                                             const int2* __restrict__ tile_bid, int64_t R, int64_t RB, int64_t M,
+                                                             int* __restrict__ cnt) {
+  for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
+    const int64_t v = w / RB, rb = w - v * RB;
+    const int vbid = __ldg(voxel_bid + v);
+    const int2 tb = __ldg(tile_bid + rb);
+    if (vbid < tb.x || vbid > tb.y) { if (threadIdx.x == 0) cnt[w] = 0; continue; }      // block-uniform
+    const AabbBox box = aabb_load_box(voxel_bound, v);
+    int total = 0;
+#pragma unroll
+    for (int j = 0; j < AABB_RPT; ++j) {
+      const int64_t r = rb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
+      bool hit = false;
+      if (r < R && ray_bid[r] == vbid) {
+        float t0, t1;
+        hit = aabb_slab(inv[r * 3 + 0], inv[r * 3 + 1], inv[r * 3 + 2], box, t0, t1);
+      }
+      total += __syncthreads_count(hit);
+    }
+    if (threadIdx.x == 0) cnt[w] = total;
+  }
+}
+
+// ---- compact pair list: fill (torch.nonzero order: voxel, then ray) --------------------------------------------------
+__global__ void __launch_bounds__(AABB_THREADS) k_aabb_fill(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
+                                                            const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
+                                                            int64_t R, int64_t RB, int64_t M, const int* __restrict__ start,
+                                                            int64_t* __restrict__ pair_vox, int64_t* __restrict__ pair_ray,
+                                                            float2* __restrict__ pair_dist) {
+  __shared__ int s_off[AABB_RPT * AABB_WARPS];                       // 32 (j, warp) groups, in ray order
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
+    const int base = __ldg(start + w);
+    if (__ldg(start + w + 1) == base) continue;                     // nothing to write for this (voxel, tile)
+    const int64_t v = w / RB, rb = w - v * RB;
+    const int vbid = __ldg(voxel_bid + v);
+    const AabbBox box = aabb_load_box(voxel_bound, v);
+    unsigned ball[AABB_RPT];
+    float t0[AABB_RPT], t1[AABB_RPT];
+#pragma unroll
+    for (int j = 0; j < AABB_RPT; ++j) {
+      const int64_t r = rb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
+      bool hit = false;
+      if (r < R && ray_bid[r] == vbid) hit = aabb_slab(inv[r * 3 + 0], inv[r * 3 + 1], inv[r * 3 + 2], box, t0[j], t1[j]);
+      ball[j] = __ballot_sync(0xffffffffu, hit);
+      if (lane == 0) s_off[j * AABB_WARPS + warp] = __popc(ball[j]);
+    }
+    __syncthreads();
+    if (warp == 0) {                                                 // exclusive prefix over the 32 groups
+      const int c = s_off[lane];
+      int inc = c;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) { const int t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+      s_off[lane] = inc - c;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int j = 0; j < AABB_RPT; ++j) {
+      if ((ball[j] >> lane) & 1u) {
+        const int64_t r = rb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
+        const int64_t pos = (int64_t)base + s_off[j * AABB_WARPS + warp] + __popc(ball[j] & ((1u << lane) - 1u));
+        pair_vox[pos] = v;
+        pair_ray[pos] = r;
+        pair_dist[pos] = make_float2(t0[j], t1[j]);
+      }
+    }
+    __syncthreads();                                                 // s_off is reused by the next work item
+  }
+}
+
+// ---- dense drop-in: mask[V,R] int32, dist[V,R,2] -- every element written once with streaming stores -----------------
+__global__ void __launch_bounds__(AABB_THREADS) k_aabb_dense(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
+                                                             const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
+                                                             const int2* __restrict__ tile_bid, int64_t R, int64_t RB, int64_t M,
+                                                             int* __restrict__ mask, float2* __restrict__ dist) {
+  for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
+    const int64_t v = w / RB, rb = w - v * RB;
+    const int vbid = __ldg(voxel_bid + v);
+    const int2 tb = __ldg(tile_bid + rb);
+    const bool live = !(vbid < tb.x || vbid > tb.y);
+    AabbBox box;
+    if (live) box = aabb_load_box(voxel_bound, v);
+#pragma unroll
+    for (int j = 0; j < AABB_RPT; ++j) {
+      const int64_t r = rb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
+      if (r >= R) continue;
+      float t0 = 0.f, t1 = 0.f;
+      bool hit = false;
+      if (live && ray_bid[r] == vbid) hit = aabb_slab(inv[r * 3 + 0], inv[r * 3 + 1], inv[r * 3 + 2], box, t0, t1);
+      if (!hit) { t0 = 0.f; t1 = 0.f; }
+      __stcs(mask + v * R + r, hit ? 1 : 0);
+      __stcs(dist + v * R + r, make_float2(t0, t1));
+    }
+  }
+}
+
+// ---- point-in-box: dense drop-in mask[V,N] ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(AABB_THREADS) k_pcl_dense(const float* __restrict__ pcl_pos, const float* __restrict__ voxel_bound,
+                                                            const int32_t* __restrict__ pcl_bid, const int32_t* __restrict__ voxel_bid,
+                                                            int64_t N, int64_t NB, int64_t M, int* __restrict__ mask) {
+  for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
+    const int64_t v = w / NB, nb = w - v * NB;
+    const int vbid = __ldg(voxel_bid + v);
+    const AabbBox box = aabb_load_box(voxel_bound, v);
+#pragma unroll
+    for (int j = 0; j < AABB_RPT; ++j) {
+      const int64_t n = nb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
+      if (n >= N) continue;
+      bool in = false;
+      if (pcl_bid[n] == vbid) in = aabb_inside(pcl_pos[n * 3 + 0], pcl_pos[n * 3 + 1], pcl_pos[n * 3 + 2], box);
+      __stcs(mask + v * N + n, in ? 1 : 0);
+    }
+  }
+}
+
+// label[i] = pcl_mask[pair_vox[i], pair_ray[i]] without the mask (pipeline.py:305-309)
+__global__ void k_pcl_pair_label(const float* __restrict__ pcl_pos, const float* __restrict__ voxel_bound,
+                                 const int32_t* __restrict__ pcl_bid, const int32_t* __restrict__ voxel_bid, int64_t N, int64_t V,
+                                 const int64_t* __restrict__ pair_vox, const int64_t* __restrict__ pair_ray, int64_t P,
+                                 float* __restrict__ label, int* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int64_t v = pair_vox[i], n = pair_ray[i];
+  if (v < 0 || v >= V || n < 0 || n >= N) { atomicOr(err, 1); label[i] = 0.f; return; }
+  bool in = false;
+  if (__ldg(pcl_bid + n) == __ldg(voxel_bid + v))
+    in = aabb_inside(__ldg(pcl_pos + n * 3 + 0), __ldg(pcl_pos + n * 3 + 1), __ldg(pcl_pos + n * 3 + 2), aabb_load_box(voxel_bound, v));
+  label[i] = in ? 1.f : 0.f;
+}
+
+// end_voxel_id[n] = max(end_voxel_id[n], largest v containing point n)  (pipeline.py:939-944).
+// One thread per point; voxel boxes go through shared memory in tiles of 256, highest ids first, so a thread stops at
+// its first hit and a block stops as soon as every thread is settled.
+#define AABB_VTILE 256
+__global__ void __launch_bounds__(AABB_THREADS) k_pcl_end_voxel(const float* __restrict__ pcl_pos, const float* __restrict__ voxel_bound,
+                                                                const int32_t* __restrict__ pcl_bid, const int32_t* __restrict__ voxel_bid,
+                                                                int64_t N, int64_t V, int64_t* __restrict__ end_voxel_id) {
+  __shared__ float s_box[AABB_VTILE * 6];
+  __shared__ int s_bid[AABB_VTILE];
+  const int64_t n = (int64_t)blockIdx.x * AABB_THREADS + threadIdx.x;
+  const bool act = n < N;
+  float x = 0.f, y = 0.f, z = 0.f;
+  int bid = 0;
+  int64_t cur = V;                                                   // inactive threads are settled from the start
+  if (act) { x = pcl_pos[n * 3 + 0]; y = pcl_pos[n * 3 + 1]; z = pcl_pos[n * 3 + 2]; bid = pcl_bid[n]; cur = end_voxel_id[n]; }
+  const int64_t cur0 = cur;
+  bool done = !act;
+  for (int64_t hi = V; hi > 0; hi -= AABB_VTILE) {
+    const int64_t lo = hi > AABB_VTILE ? hi - AABB_VTILE : 0;
+    const int cntv = (int)(hi - lo);
+    done = done || (cur >= hi - 1);                                  // nothing above `cur` left in this or lower tiles
+    if (__syncthreads_and(done)) break;
+    for (int i = threadIdx.x; i < cntv * 6; i += AABB_THREADS) s_box[i] = voxel_bound[lo * 6 + i];
+    for (int i = threadIdx.x; i < cntv; i += AABB_THREADS) s_bid[i] = voxel_bid[lo + i];
+    __syncthreads();
+    if (!done) {
+      for (int i = cntv - 1; i >= 0; --i) {
+        const int64_t v = lo + i;
+        if (v <= cur) { done = true; break; }
+        if (s_bid[i] != bid) continue;
+        const float* b = s_box + i * 6;
+        if ((x < b[0]) || (x > b[3])) continue;
+        if ((y < b[1]) || (y > b[4])) continue;
+        if ((z < b[2]) || (z > b[5])) continue;
+        cur = v; done = true; break;
+      }
+    }
+  }
+  if (act && cur != cur0) end_voxel_id[n] = cur;
+}

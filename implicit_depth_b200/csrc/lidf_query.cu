@@ -485,3 +485,157 @@ extern "C" int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stre
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
+
+// -------------------------------------------------------------------------------------------------
+// Ray / point vs voxel-box tests (include/lidf_aabb.h): the producers of the pair list the query path consumes.
+// -------------------------------------------------------------------------------------------------
+#include "lidf_aabb.cuh"
+
+namespace {
+struct AabbPlan { int64_t RB, M; int nb; float* inv; int2* tile_bid; int* cnt; int* start; int* block_sums; size_t bytes; };
+
+int plan_aabb(int64_t R, int64_t V, AabbPlan* q, char* base) {
+  if (R < 0 || V < 0) return LIDF_ERR_ARG;
+  q->RB = (R + AABB_TILE - 1) / AABB_TILE;
+  q->M = q->RB * V;
+  if (q->M >= INT_MAX - 2 || R >= ((int64_t)1 << 40)) return LIDF_ERR_UNSUPPORTED;
+  const int64_t n = q->M + 1;
+  q->nb = (int)((n + LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS - 1) / (LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS));
+  Bump b{base, 0};
+  q->inv = b.take<float>((size_t)(R > 0 ? R : 1) * 3);
+  q->tile_bid = b.take<int2>((size_t)(q->RB > 0 ? q->RB : 1));
+  q->cnt = b.take<int>((size_t)n);
+  q->start = b.take<int>((size_t)n);
+  q->block_sums = b.take<int>((size_t)q->nb);
+  q->bytes = b.off + 256;
+  return LIDF_OK;
+}
+
+int persistent_blocks(int64_t items, int per_sm) {
+  static thread_local int sms = 0;
+  if (!sms) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+      sms = 148;
+  }
+  const int64_t g = (int64_t)sms * per_sm;                   // a multiple of the SM count (148 on B200)
+  return (int)(items < g ? (items > 0 ? items : 1) : g);
+}
+
+int aabb_ray_prep(const AabbPlan& q, const float* ray_dir, const int32_t* ray_bid, int64_t R, cudaStream_t st) {
+  k_aabb_ray_prep<<<(unsigned)q.RB, AABB_THREADS, 0, st>>>(ray_dir, ray_bid, R, q.inv, q.tile_bid);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_ray_aabb_workspace_bytes(int64_t R, int64_t V) {
+  AabbPlan q;
+  if (plan_aabb(R, V, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_ray_aabb_forward(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                     const int32_t* voxel_bid, int64_t R, int64_t V, int32_t* mask, float* dist,
+                                     void* workspace, size_t workspace_bytes, lidf_stream_t stream) {
+  AabbPlan q;
+  int rc = plan_aabb(R, V, &q, (char*)workspace);
+  if (rc) return rc;
+  if (R == 0 || V == 0) return LIDF_OK;
+  if (!ray_dir || !voxel_bound || !ray_bid || !voxel_bid || !mask || !dist || !workspace) return LIDF_ERR_NULL;
+  if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  if ((rc = aabb_ray_prep(q, ray_dir, ray_bid, R, st))) return rc;
+  k_aabb_dense<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R, q.RB,
+                                                                    q.M, mask, reinterpret_cast<float2*>(dist));
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+extern "C" int lidf_ray_aabb_pairs_count(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                         const int32_t* voxel_bid, int64_t R, int64_t V, void* workspace,
+                                         size_t workspace_bytes, int64_t* n_pairs_host, lidf_stream_t stream) {
+  if (!n_pairs_host) return LIDF_ERR_NULL;
+  *n_pairs_host = 0;
+  AabbPlan q;
+  int rc = plan_aabb(R, V, &q, (char*)workspace);
+  if (rc) return rc;
+  if (R == 0 || V == 0) return LIDF_OK;
+  if (!ray_dir || !voxel_bound || !ray_bid || !voxel_bid || !workspace) return LIDF_ERR_NULL;
+  if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  if ((rc = aabb_ray_prep(q, ray_dir, ray_bid, R, st))) return rc;
+  const int64_t n = q.M + 1;
+  LIDF_CUDA(cudaMemsetAsync(q.cnt + q.M, 0, sizeof(int), st));
+  k_aabb_count<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R, q.RB,
+                                                                    q.M, q.cnt);
+  LIDF_LAUNCH_CHECK();
+  k_scan_partial<<<q.nb, LIDF_SCAN_BLOCK, 0, st>>>(q.cnt, n, q.start, q.block_sums);
+  LIDF_LAUNCH_CHECK();
+  k_scan_blocksums<<<1, 1024, 0, st>>>(q.block_sums, q.nb);
+  LIDF_LAUNCH_CHECK();
+  k_scan_add<<<q.nb, LIDF_SCAN_BLOCK, 0, st>>>(q.start, n, q.block_sums, nullptr);
+  LIDF_LAUNCH_CHECK();
+  int total = 0;
+  LIDF_CUDA(cudaMemcpyAsync(&total, q.start + q.M, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LIDF_CUDA(cudaStreamSynchronize(st));
+  if (total < 0) return LIDF_ERR_UNSUPPORTED;              // >= 2^31 pairs
+  *n_pairs_host = total;
+  return LIDF_OK;
+}
+
+extern "C" int lidf_ray_aabb_pairs_fill(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                        const int32_t* voxel_bid, int64_t R, int64_t V, void* workspace,
+                                        size_t workspace_bytes, int64_t P, int64_t* pair_vox, int64_t* pair_ray,
+                                        float* pair_dist, lidf_stream_t stream) {
+  (void)ray_dir;
+  AabbPlan q;
+  int rc = plan_aabb(R, V, &q, (char*)workspace);
+  if (rc) return rc;
+  if (P < 0) return LIDF_ERR_ARG;
+  if (R == 0 || V == 0 || P == 0) return LIDF_OK;
+  if (!voxel_bound || !ray_bid || !voxel_bid || !workspace || !pair_vox || !pair_ray || !pair_dist) return LIDF_ERR_NULL;
+  if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  k_aabb_fill<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, R, q.RB, q.M, q.start,
+                                                                   pair_vox, pair_ray, reinterpret_cast<float2*>(pair_dist));
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+extern "C" int lidf_pcl_aabb_forward(const float* pcl_pos, const float* voxel_bound, const int32_t* pcl_bid,
+                                     const int32_t* voxel_bid, int64_t N, int64_t V, int32_t* mask, lidf_stream_t stream) {
+  if (N < 0 || V < 0) return LIDF_ERR_ARG;
+  if (N == 0 || V == 0) return LIDF_OK;
+  if (!pcl_pos || !voxel_bound || !pcl_bid || !voxel_bid || !mask) return LIDF_ERR_NULL;
+  const int64_t NB = (N + AABB_TILE - 1) / AABB_TILE, M = NB * V;
+  k_pcl_dense<<<persistent_blocks(M, 8), AABB_THREADS, 0, (cudaStream_t)stream>>>(pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, NB, M, mask);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+extern "C" int lidf_pcl_aabb_pair_label(const float* pcl_pos, const float* voxel_bound, const int32_t* pcl_bid,
+                                        const int32_t* voxel_bid, int64_t N, int64_t V, const int64_t* pair_vox,
+                                        const int64_t* pair_ray, int64_t P, float* label, lidf_stream_t stream) {
+  if (N < 0 || V < 0 || P < 0) return LIDF_ERR_ARG;
+  if (P == 0) return LIDF_OK;
+  if (!pcl_pos || !voxel_bound || !pcl_bid || !voxel_bid || !pair_vox || !pair_ray || !label) return LIDF_ERR_NULL;
+  static thread_local int* d_err = nullptr;               // sticky device flag for out-of-range pair indices
+  if (!d_err) { LIDF_CUDA(cudaMalloc(&d_err, sizeof(int))); LIDF_CUDA(cudaMemset(d_err, 0, sizeof(int))); }
+  k_pcl_pair_label<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, V,
+                                                                                  pair_vox, pair_ray, P, label, d_err);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+extern "C" int lidf_pcl_aabb_end_voxel(const float* pcl_pos, const float* voxel_bound, const int32_t* pcl_bid,
+                                       const int32_t* voxel_bid, int64_t N, int64_t V, int64_t* end_voxel_id,
+                                       lidf_stream_t stream) {
+  if (N < 0 || V < 0) return LIDF_ERR_ARG;
+  if (N == 0 || V == 0) return LIDF_OK;
+  if (!pcl_pos || !voxel_bound || !pcl_bid || !voxel_bid || !end_voxel_id) return LIDF_ERR_NULL;
+  k_pcl_end_voxel<<<(unsigned)((N + AABB_THREADS - 1) / AABB_THREADS), AABB_THREADS, 0, (cudaStream_t)stream>>>(
+      pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, V, end_voxel_id);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}

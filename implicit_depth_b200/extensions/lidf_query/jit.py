@@ -65,6 +65,11 @@ EXPORTED_SYMBOLS = [
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
     "lidf_query_last_mlp_ms", "lidf_tc_selftest",
 ]
+# include/lidf_aabb.h (bound by extensions/ray_aabb/jit.py and extensions/pcl_aabb/jit.py)
+EXPORTED_SYMBOLS_AABB = [
+    "lidf_ray_aabb_workspace_bytes", "lidf_ray_aabb_forward", "lidf_ray_aabb_pairs_count", "lidf_ray_aabb_pairs_fill",
+    "lidf_pcl_aabb_forward", "lidf_pcl_aabb_pair_label", "lidf_pcl_aabb_end_voxel",
+]
 
 
 def load_library(build_if_needed: bool = True) -> C.CDLL:
@@ -100,6 +105,21 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
     lib.lidf_query_launch_count.restype = C.c_int64
     lib.lidf_query_launch_count.argtypes = [C.c_int]
+    vp, i64, sz = C.c_void_p, C.c_int64, C.c_size_t
+    lib.lidf_ray_aabb_workspace_bytes.restype = sz
+    lib.lidf_ray_aabb_workspace_bytes.argtypes = [i64, i64]
+    lib.lidf_ray_aabb_forward.restype = C.c_int
+    lib.lidf_ray_aabb_forward.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, vp, sz, vp]
+    lib.lidf_ray_aabb_pairs_count.restype = C.c_int
+    lib.lidf_ray_aabb_pairs_count.argtypes = [vp, vp, vp, vp, i64, i64, vp, sz, C.POINTER(C.c_int64), vp]
+    lib.lidf_ray_aabb_pairs_fill.restype = C.c_int
+    lib.lidf_ray_aabb_pairs_fill.argtypes = [vp, vp, vp, vp, i64, i64, vp, sz, i64, vp, vp, vp, vp]
+    lib.lidf_pcl_aabb_forward.restype = C.c_int
+    lib.lidf_pcl_aabb_forward.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
+    lib.lidf_pcl_aabb_pair_label.restype = C.c_int
+    lib.lidf_pcl_aabb_pair_label.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp]
+    lib.lidf_pcl_aabb_end_voxel.restype = C.c_int
+    lib.lidf_pcl_aabb_end_voxel.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
     if lib.lidf_query_abi_version() != 1:
         raise RuntimeError("liblidf_query.so ABI version mismatch")
     lib.lidf_query_struct_size.restype = C.c_size_t

@@ -1,0 +1,143 @@
+"""GPU parity for the ray_aabb / pcl_aabb rows (include/lidf_aabb.h), through the C ABI: bit-exact against
+(1) golden vectors from the reference's own kernels, (2) the numpy oracle on seeded inputs incl. empty / ragged /
+multi-tile shapes, (3) at BASELINE config-2 size, the compact pair list against torch.nonzero of our dense output."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from conftest import GOLDEN_DIR
+from oracle import aabb_oracle as A
+
+pytestmark = pytest.mark.gpu
+AABB_CASES = ["aabb_grid_2x12x16", "aabb_grid_1x9x11", "aabb_edge"]
+
+
+def _ext():
+    from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
+    from implicit_depth_b200.extensions.ray_aabb.jit import ray_aabb
+    return ray_aabb, pcl_aabb
+
+
+def _c(a, dtype=None):
+    t = torch.from_numpy(np.ascontiguousarray(a))
+    return (t.to(dtype) if dtype is not None else t).cuda()
+
+
+def bits(a):
+    return np.ascontiguousarray(a, dtype=np.float32).view(np.uint32)
+
+
+def _check_ray(ray_dir, vb, rb, xb, want_mask, want_dist, want_pairs):
+    ray_aabb, _ = _ext()
+    args = (_c(ray_dir, torch.float32), _c(vb, torch.float32), _c(rb, torch.int32), _c(xb, torch.int32))
+    mask, dist = ray_aabb.forward(*args)
+    assert mask.dtype == torch.int32 and dist.dtype == torch.float32
+    assert np.array_equal(mask.cpu().numpy(), want_mask)
+    assert np.array_equal(bits(dist.cpu().numpy()), bits(want_dist))
+    vox, ray, pd = ray_aabb.pairs(*args)
+    assert vox.dtype == torch.int64 and ray.dtype == torch.int64
+    assert np.array_equal(vox.cpu().numpy(), want_pairs[0]) and np.array_equal(ray.cpu().numpy(), want_pairs[1])
+    assert np.array_equal(bits(pd.cpu().numpy()), bits(want_pairs[2]))
+
+
+@pytest.mark.parametrize("name", AABB_CASES)
+def test_ray_aabb_golden_reference_kernel_outputs(name):
+    z = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    _check_ray(z["ray_dir"], z["voxel_bound"], z["ray_bid"], z["voxel_bid"], z["ref_mask"], z["ref_dist"],
+               (z["ref_pair_vox"], z["ref_pair_ray"], z["ref_pair_dist"]))
+
+
+@pytest.mark.parametrize("name", AABB_CASES)
+def test_pcl_aabb_golden_reference_kernel_outputs(name):
+    _, pcl_aabb = _ext()
+    z = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    vb, xb = _c(z["voxel_bound"]), _c(z["voxel_bid"], torch.int32)
+    m = pcl_aabb.forward(_c(z["pts"]), vb, _c(z["pts_bid"], torch.int32), xb)
+    assert np.array_equal(m.cpu().numpy(), z["ref_pcl_mask"])
+    rp, rb = _c(z["ray_pts"]), _c(z["ray_bid"], torch.int32)
+    assert np.array_equal(pcl_aabb.forward(rp, vb, rb, xb).cpu().numpy(), z["ref_pcl_mask_rays"])
+    lab = pcl_aabb.pair_label(rp, vb, rb, xb, _c(z["ref_pair_vox"]), _c(z["ref_pair_ray"]))
+    assert np.array_equal(lab.cpu().numpy(), z["ref_pair_label"])
+    end = pcl_aabb.end_voxel(rp, vb, rb, xb, _c(z["end_voxel_start"]))
+    assert np.array_equal(end.cpu().numpy(), z["ref_end_voxel"])
+
+
+@pytest.mark.parametrize("R,V,nimg", [(1, 1, 1), (1023, 7, 2), (1024, 3, 1), (1025, 33, 3), (5000, 300, 4), (3, 700, 2)])
+def test_ray_and_pcl_aabb_vs_oracle_seeded(R, V, nimg):
+    _, pcl_aabb = _ext()
+    rng = np.random.default_rng(R * 1000 + V)
+    d = rng.normal(size=(R, 3)); d /= np.linalg.norm(d, axis=1, keepdims=True)
+    d[rng.random((R, 3)) < 0.03] = 0.0
+    d = d.astype(np.float32)
+    lo = rng.uniform(-1, 1, size=(V, 3)); vb = np.concatenate((lo, lo + rng.uniform(0, 1.2, size=(V, 3))), 1).astype(np.float32)
+    rb = np.sort(rng.integers(0, nimg, size=R)).astype(np.int32)
+    xb = rng.integers(0, nimg, size=V).astype(np.int32)              # voxel image ids unsorted on purpose
+    mask, dist = A.ray_aabb_dense(d, vb, rb, xb)
+    _check_ray(d, vb, rb, xb, mask, dist, A.ray_aabb_pairs(d, vb, rb, xb))
+    pts = rng.uniform(-1.2, 2.2, size=(R, 3)).astype(np.float32)
+    args = (_c(pts), _c(vb), _c(rb), _c(xb))
+    assert np.array_equal(pcl_aabb.forward(*args).cpu().numpy(), A.pcl_aabb_dense(pts, vb, rb, xb))
+    start = rng.integers(0, V, size=R).astype(np.int64)
+    assert np.array_equal(pcl_aabb.end_voxel(*args, _c(start)).cpu().numpy(), A.pcl_end_voxel(pts, vb, rb, xb, start))
+    vox, ray, _ = A.ray_aabb_pairs(d, vb, rb, xb)
+    if vox.size:
+        assert np.array_equal(pcl_aabb.pair_label(*args, _c(vox), _c(ray)).cpu().numpy(), A.pcl_pair_label(pts, vb, rb, xb, vox, ray))
+
+
+def test_aabb_empty_inputs_and_no_hits():
+    ray_aabb, pcl_aabb = _ext()
+    f = lambda *s: torch.zeros(*s, dtype=torch.float32, device="cuda")
+    i = lambda *s: torch.zeros(*s, dtype=torch.int32, device="cuda")
+    for R, V in [(0, 4), (5, 0), (0, 0)]:
+        mask, dist = ray_aabb.forward(f(R, 3), f(V, 6), i(R), i(V))
+        assert tuple(mask.shape) == (V, R) and tuple(dist.shape) == (V, R, 2)
+        vox, ray, pd = ray_aabb.pairs(f(R, 3), f(V, 6), i(R), i(V))
+        assert vox.numel() == 0 and ray.numel() == 0 and tuple(pd.shape) == (0, 2)
+        assert tuple(pcl_aabb.forward(f(R, 3), f(V, 6), i(R), i(V)).shape) == (V, R)
+    # rays and voxels of different images never pair up
+    d = torch.tensor([[0., 0., 1.]] * 2000, device="cuda")
+    vb = torch.tensor([[-1., -1., 0.5, 1., 1., 1.]] * 3, device="cuda")
+    vox, ray, pd = ray_aabb.pairs(d, vb, i(2000), i(3) + 1)
+    assert vox.numel() == 0
+    mask, dist = ray_aabb.forward(d, vb, i(2000), i(3) + 1)
+    assert int(mask.sum()) == 0 and float(dist.abs().sum()) == 0.0
+    vox, ray, pd = ray_aabb.pairs(d, vb, i(2000), i(3))
+    assert vox.numel() == 6000 and torch.equal(pd, torch.tensor([[0.5, 1.0]], device="cuda").expand(6000, 2))
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ray_aabb.forward(d.cpu(), vb, i(2000), i(3))
+    with pytest.raises(RuntimeError, match="must be torch.int32"):
+        ray_aabb.forward(d, vb, i(2000).long(), i(3))
+
+
+def test_ray_aabb_pairs_equal_nonzero_of_dense_at_config2_size():
+    """4 images of 320x240 all-pixel rays against 256 occupied cells of the 9^3 grid each (the bench geometry):
+    the compact list must be exactly torch.nonzero(mask) / dist[vox, ray] of the dense drop-in, and a random slice of the
+    dense output must match the oracle."""
+    from implicit_depth_b200.synthetic import make_inputs
+    ray_aabb, pcl_aabb = _ext()
+    d = make_inputs(4, 240, 320, 1, V_img=256, seed=77, device="cuda")
+    rd, vb = d["miss_ray_dir"], d["voxel_bound"]
+    rb, xb = d["miss_bid"].int(), d["occ_vox_bid"].int()
+    mask, dist = ray_aabb.forward(rd, vb, rb, xb)
+    vox, ray, pd = ray_aabb.pairs(rd, vb, rb, xb)
+    idx = torch.nonzero(mask.long(), as_tuple=False)                      # pipeline.py:281-285
+    assert idx.shape[0] == vox.shape[0] and idx.shape[0] > 300000
+    assert torch.equal(idx[:, 0], vox) and torch.equal(idx[:, 1], ray)
+    assert torch.equal(dist[vox, ray].view(torch.int32), pd.view(torch.int32))   # pipeline.py:345, bit patterns
+    assert torch.equal(rb[ray], xb[vox]) and bool((pd[:, 1] >= pd[:, 0]).all())
+    sel_v = torch.arange(0, vb.shape[0], 37, device="cuda"); sel_r = torch.arange(0, rd.shape[0], 41, device="cuda")
+    om, od = A.ray_aabb_dense(rd[sel_r].cpu().numpy(), vb[sel_v].cpu().numpy(), rb[sel_r].cpu().numpy(), xb[sel_v].cpu().numpy())
+    assert np.array_equal(mask[sel_v][:, sel_r].cpu().numpy(), om)
+    assert np.array_equal(bits(dist[sel_v][:, sel_r].cpu().numpy()), bits(od))
+    # points in the middle of each pair's [enter, leave] interval lie inside that pair's voxel -> label 1 everywhere
+    mid = rd[ray] * (0.5 * (pd[:, 0:1] + pd[:, 1:2]))
+    lab = pcl_aabb.pair_label(mid.contiguous(), vb, rb[ray].contiguous(), xb, vox, torch.arange(vox.shape[0], device="cuda"))
+    assert float(lab.mean()) > 0.999
+    # end voxel of those points, starting from 0, is >= the pair's own voxel and contains the point
+    end = pcl_aabb.end_voxel(mid.contiguous(), vb, rb[ray].contiguous(), xb, torch.zeros_like(vox))
+    ok = lab > 0
+    assert bool((end[ok] >= vox[ok]).all())
+    lab2 = pcl_aabb.pair_label(mid.contiguous(), vb, rb[ray].contiguous(), xb, end, torch.arange(vox.shape[0], device="cuda"))
+    assert bool((lab2[ok] == 1).all())

@@ -16,10 +16,14 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     path = build.build()
     assert os.path.exists(path)
     lib = jit.load_library()
-    header = open(os.path.join(REPO, "include", "lidf_query.h")).read()
-    header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
-    declared = set(re.findall(r"\b(lidf_[a-z_0-9]+)\s*\(", header))
-    assert declared == set(jit.EXPORTED_SYMBOLS), declared ^ set(jit.EXPORTED_SYMBOLS)
+    declared = set()
+    for name, want in (("lidf_query.h", jit.EXPORTED_SYMBOLS), ("lidf_aabb.h", jit.EXPORTED_SYMBOLS_AABB)):
+        header = open(os.path.join(REPO, "include", name)).read()
+        header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
+        got = set(re.findall(r"\b(lidf_[a-z_0-9]+)\s*\(", header))
+        assert got == set(want), (name, got ^ set(want))
+        declared |= got
+    assert sorted(os.listdir(os.path.join(REPO, "include"))) == ["lidf_aabb.h", "lidf_query.h"]
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert lib.lidf_query_abi_version() == 1
@@ -29,6 +33,20 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.lidf_refine_forward(None, None) == -1
     assert lib.lidf_query_workspace_bytes(None) == 0
     assert lib.lidf_ray_terminate_workspace_bytes(1000, 10) > 4000
+    assert lib.lidf_ray_aabb_workspace_bytes(5000, 40) > 5000 * 12 and lib.lidf_ray_aabb_workspace_bytes(-1, 4) == 0
+    assert lib.lidf_ray_aabb_forward(None, None, None, None, 5, 5, None, None, None, 0, None) == -1
+    assert lib.lidf_pcl_aabb_forward(None, None, None, None, 5, 5, None, None) == -1
+    assert lib.lidf_pcl_aabb_end_voxel(None, None, None, None, 0, 5, None, None) == 0       # empty problem: no-op
+
+
+def test_no_cpu_fallback_for_aabb_ops():
+    from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
+    from implicit_depth_b200.extensions.ray_aabb.jit import ray_aabb
+    f, i = torch.zeros(4, 3), torch.zeros(4, dtype=torch.int32)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        ray_aabb.forward(f, torch.zeros(2, 6), i, i[:2])
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        pcl_aabb.forward(f, torch.zeros(2, 6), i, i[:2])
 
 
 def test_no_cpu_fallback_for_fused_op():
