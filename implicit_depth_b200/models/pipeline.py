@@ -62,6 +62,30 @@ class LIDFQueryMixin:
                     roi_inp_bbox=int(m.roi_inp_bbox), roi_out_bbox=int(m.roi_out_bbox), n_iter=int(m.n_iter),
                     use_sigmoid=bool(m.use_sigmoid), offset_range=tuple(float(v) for v in self.opt.grid.offset_range))
 
+    def compute_ray_aabb(self, data_dict):
+        """Replacement for ``LIDF.compute_ray_aabb`` (reference pipeline.py:271-296): the same slab test, but the pair list
+        and the per-pair enter/leave distances come straight from the kernel (``ray_aabb.pairs``) instead of
+        ``torch.nonzero`` over a dense [V,R] mask plus a ``dist[vox, ray]`` lookup.  Writes ``occ_vox_intersect_idx``,
+        ``miss_ray_intersect_idx`` (reference order) and ``intersect_dist`` [P,2]; the dense ``mask`` / ``dist`` entries of
+        the reference are not produced -- their only reader is ``get_embedding`` (pipeline.py:345), replaced above."""
+        from implicit_depth_b200.extensions.ray_aabb.jit import ray_aabb
+        vox, ray, dist = ray_aabb.pairs(data_dict['miss_ray_dir'].contiguous(), data_dict['voxel_bound'].contiguous(),
+                                        data_dict['miss_bid'].int().contiguous(), data_dict['occ_vox_bid'].int().contiguous())
+        if vox.shape[0] == 0:
+            print('No miss ray and occ vox intersection pair', data_dict.get('item_path'))
+            return False
+        data_dict.update({'occ_vox_intersect_idx': vox, 'miss_ray_intersect_idx': ray, 'intersect_dist': dist})
+        return True
+
+    def compute_pair_label(self, data_dict, gt_pos):
+        """``pcl_label`` / ``pcl_label_float`` of ``LIDF.compute_gt`` (reference pipeline.py:303-309) without the dense
+        [V,R] point-in-voxel mask."""
+        from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
+        lab = pcl_aabb.pair_label(gt_pos.float().contiguous(), data_dict['voxel_bound'].contiguous(),
+                                  data_dict['miss_bid'].int().contiguous(), data_dict['occ_vox_bid'].int().contiguous(),
+                                  data_dict['occ_vox_intersect_idx'].contiguous(), data_dict['miss_ray_intersect_idx'].contiguous())
+        data_dict.update({'gt_pos': gt_pos, 'pcl_label': lab.long(), 'pcl_label_float': lab})
+
     def get_pred(self, data_dict, exp_type, epoch):
         if self.opt.model.scatter_type != 'Maxpool':
             raise NotImplementedError('Does not support Scatter Type: {}'.format(self.opt.model.scatter_type))
@@ -190,6 +214,18 @@ class RefineDecoderMixin:
     """Decoder tail of ``RefineNet.get_pred_refine`` (reference pipeline.py:1018-1029) as one fused call."""
 
     mlp_impl = "auto"
+
+    def refine_end_voxel(self, data_dict, pred_pos):
+        """``end_voxel_id`` of ``RefineNet.get_pred_refine`` (reference pipeline.py:939-944): the voxel of each ray's
+        arg-max pair, raised to the largest occupied voxel that contains the predicted point -- one kernel instead of
+        the dense pcl_aabb mask + nonzero + torch_scatter.scatter(reduce='max')."""
+        from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
+        vox = data_dict['occ_vox_intersect_idx']
+        dummy = torch.cat((vox, torch.zeros(1, dtype=vox.dtype, device=vox.device)), 0)      # concat_dummy, :924,:942
+        end_voxel_id = dummy[data_dict['max_pair_id']].contiguous()
+        return pcl_aabb.end_voxel(pred_pos.float().contiguous(), data_dict['voxel_bound'].contiguous(),
+                                  data_dict['miss_bid'].int().contiguous(), data_dict['occ_vox_bid'].int().contiguous(),
+                                  end_voxel_id)
 
     def refine_decoder_tail(self, data_dict, pred_pos, end_voxel_id, occ_voxel_feat, rgb_feat_per_ray):
         r = self.opt.refine

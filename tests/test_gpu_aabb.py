@@ -141,3 +141,50 @@ def test_ray_aabb_pairs_equal_nonzero_of_dense_at_config2_size():
     assert bool((end[ok] >= vox[ok]).all())
     lab2 = pcl_aabb.pair_label(mid.contiguous(), vb, rb[ray].contiguous(), xb, end, torch.arange(vox.shape[0], device="cuda"))
     assert bool((lab2[ok] == 1).all())
+
+
+def test_pipeline_mixin_real_geometry_chain_vs_oracle():
+    """compute_ray_aabb -> compute_pair_label -> get_pred -> refine_end_voxel on real ray/voxel geometry (all-pixel rays
+    against occupied cells of the 9^3 grid: ragged pair counts incl. rays without any pair), against the oracle chain
+    aabb_oracle -> lidf_oracle."""
+    from conftest import rel_err
+    from implicit_depth_b200.models.pipeline import LIDF, RefineNet, default_opt
+    from implicit_depth_b200.synthetic import make_inputs
+    from oracle import lidf_oracle as O
+    d = make_inputs(2, 30, 40, 1, V_img=60, seed=91)                # pair arrays of the generator are discarded below
+    vox, ray, pd = A.ray_aabb_pairs(d["miss_ray_dir"].numpy(), d["voxel_bound"].numpy(), d["miss_bid"].numpy(), d["occ_vox_bid"].numpy())
+    R = d["miss_ray_dir"].shape[0]
+    assert 0 < np.unique(ray).size < R                              # some rays have no pair
+    do = dict(d, occ_vox_intersect_idx=torch.from_numpy(vox), miss_ray_intersect_idx=torch.from_numpy(ray),
+              intersect_dist=torch.from_numpy(pd))
+    g = torch.Generator().manual_seed(92)
+    off = O.init_decoder("IEF", 385, mode="trained", generator=g)
+    prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
+    want = O.lidf_query(do, dict(O.DEFAULT_CFG), off, prob, d["part_size"], dedup_rays=True)
+
+    lidf = LIDF(default_opt(), torch.device("cuda")).cuda().eval()
+    lidf.offset_dec.load_state_dict(off); lidf.prob_dec.load_state_dict(prob)
+    dd = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()
+          if k not in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist")}
+    with torch.no_grad():
+        assert lidf.compute_ray_aabb(dd) is True
+        assert np.array_equal(dd["occ_vox_intersect_idx"].cpu().numpy(), vox)
+        assert np.array_equal(dd["miss_ray_intersect_idx"].cpu().numpy(), ray)
+        assert np.array_equal(bits(dd["intersect_dist"].cpu().numpy()), bits(pd))
+        lidf.get_pred(dd, "test", 0)
+    for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax"):
+        assert rel_err(dd[k].cpu(), want[k]) < 1e-3, k
+    same = dd["max_pair_id"].cpu() == want["max_pair_id"]
+    assert float(same.float().mean()) > 0.99
+    empty = want["max_pair_id"] == vox.shape[0]
+    assert bool(empty.any()) and torch.equal(dd["max_pair_id"].cpu()[empty], want["max_pair_id"][empty])
+    # GT labels for points placed at the predicted positions, and the refine stage's end voxel
+    gt_pos = dd["pred_pos"].clone()
+    lidf.compute_pair_label(dd, gt_pos)
+    lab = A.pcl_pair_label(gt_pos.cpu().numpy(), d["voxel_bound"].numpy(), d["miss_bid"].numpy(), d["occ_vox_bid"].numpy(), vox, ray)
+    assert np.array_equal(dd["pcl_label_float"].cpu().numpy(), lab) and dd["pcl_label"].dtype == torch.int64
+    refine = RefineNet(default_opt(), torch.device("cuda"))
+    end = refine.refine_end_voxel(dd, dd["pred_pos"])
+    start = np.concatenate((vox, [0]))[dd["max_pair_id"].cpu().numpy()]
+    want_end = A.pcl_end_voxel(dd["pred_pos"].cpu().numpy(), d["voxel_bound"].numpy(), d["miss_bid"].numpy(), d["occ_vox_bid"].numpy(), start)
+    assert np.array_equal(end.cpu().numpy(), want_end)
