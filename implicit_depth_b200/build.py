@@ -13,7 +13,9 @@ PKG_DIR = os.path.dirname(os.path.abspath(__file__))
 REPO = os.path.dirname(PKG_DIR)
 CSRC = os.path.join(PKG_DIR, "csrc")
 INCLUDE = os.path.join(REPO, "include")
-LIB_PATH = os.path.join(CSRC, "liblidf_query.so")
+# LIDF_QUERY_LIB points the loader at another build of the same sources (A/B timing experiments); it is never rebuilt
+LIB_OVERRIDE = os.environ.get("LIDF_QUERY_LIB")
+LIB_PATH = LIB_OVERRIDE or os.path.join(CSRC, "liblidf_query.so")
 SOURCES = ["lidf_query.cu"]
 HEADERS = ["lidf_common.cuh", "lidf_prep.cuh", "lidf_simt.cuh", "lidf_tc.cuh", "lidf_aabb.cuh",
            os.path.join(INCLUDE, "lidf_query.h"), os.path.join(INCLUDE, "lidf_aabb.h")]
@@ -39,7 +41,7 @@ def is_stale() -> bool:
 
 def build(force: bool = False, verbose: bool = False) -> str:
     """Compile if missing or older than its sources.  Returns the library path."""
-    if not force and not is_stale():
+    if LIB_OVERRIDE or (not force and not is_stale()):
         return LIB_PATH
     nvcc = find_nvcc()
     if nvcc is None:

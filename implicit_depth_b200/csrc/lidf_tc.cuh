@@ -62,6 +62,12 @@
 #define TC_KPE_MAX 112            // widest per-pair PE block (2 x PE(pos)) the layer-1 operand layout holds
 #define TC_MAX_PASSES 9
 #define TC_SPIN_LIMIT (1u << 22)
+// Timing experiments only (results are garbage when non-zero; tools/dbg_modes.sh, profiles/r1l_modes.md): bit 0 = do not
+// issue the MMAs, bit 1 = epilogues skip the TMEM loads, bit 2 = epilogues skip math + TMEM stores, bit 3 = operand build
+// skips sincos.  Never set in a product build.
+#ifndef TC_DEBUG_MODE
+#define TC_DEBUG_MODE 0
+#endif
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 namespace tc {
@@ -133,6 +139,7 @@ __device__ __forceinline__ void commit(uint64_t* bar) {
 
 // D[tmem] (+)= A[tmem] * B[smem]^T, kind::f16 (bf16 in, fp32 accumulate), M = 128.  (SASS: UTCHMMA)
 __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (TC_DEBUG_MODE & 1) return;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -144,6 +151,7 @@ __device__ __forceinline__ void mma_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_
 
 // D[tmem] (+)= A[smem] * B[smem]^T
 __device__ __forceinline__ void mma_ss(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  if (TC_DEBUG_MODE & 1) return;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
       "setp.ne.b32 p, %4, 0;\n\t"
@@ -172,6 +180,11 @@ __device__ __forceinline__ uint64_t make_bdesc(uint32_t saddr, uint32_t lbo_byte
 }
 
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  if (TC_DEBUG_MODE & 2) {
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = taddr + i;
+    return;
+  }
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
       "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
@@ -183,6 +196,7 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
+  if (TC_DEBUG_MODE & 4) return;
   asm volatile(
       "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};" ::"r"(taddr),
       "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
@@ -356,6 +370,11 @@ __device__ __forceinline__ void mbar_arrive_a(uint32_t bar_saddr) {
   asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar_saddr) : "memory");
 }
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+  if (TC_DEBUG_MODE & 2) {
+#pragma unroll
+    for (int i = 0; i < 16; ++i) r[i] = taddr + i;
+    return;
+  }
   asm volatile(
       "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
       : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
@@ -732,7 +751,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
 #pragma unroll
           for (int fg = 0; fg < 2; ++fg) {
             float sn, cs;
-            sincosf(pin * (fg ? 16.0f : 1.0f), &sn, &cs);
+            if (TC_DEBUG_MODE & 8) { sn = pin; cs = pin * 0.5f; } else sincosf(pin * (fg ? 16.0f : 1.0f), &sn, &cs);
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const int k = 4 * fg + kk;
