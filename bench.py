@@ -37,6 +37,7 @@ WORKLOADS = {          # name: (B per GPU, H, W, N)   -- BASELINE.json configs
     "c2": (4, 240, 320, 64),
     "c3": (8, 480, 640, 64),
     "c4": (4, 480, 640, 64),
+    "c5": (8, 480, 640, 128),
     "tiny": (1, 48, 64, 16),
 }
 FLOP_IMNET = 279168            # 2*MAC of the reference Linear stack, per query point
@@ -175,6 +176,9 @@ def main():
     ap.add_argument("--cpu-sample-pairs", type=int, default=1 << 19)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--stage2", action="store_true",
+                    help="also time BASELINE config 5's second stage on this rank's rays: end-voxel lookup + voxel-feature "
+                         "gather + the RefineNet decoder tail, forward_times = 2 (reported as 'stage2', not part of 'value')")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
                     help="also time the stock torch op chain (oracle port) on the GPU over a bounded sample")
     args = ap.parse_args()
@@ -293,9 +297,52 @@ def main():
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
     if args.torch_gpu_baseline:
         line["torch_gpu_baseline"] = torch_gpu_baseline(d, off, prob, args, dev)
+    if args.stage2:
+        line["stage2"] = stage2(d, step, dev, impl=args.engine)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def stage2(d, step, dev, forward_times=2, impl="auto"):
+    """RefineNet.get_pred_refine per ray (reference pipeline.py:922-1041) on the hot-path pieces this repo owns: end-voxel
+    lookup (pcl_aabb.end_voxel), cached per-ray ROI feature, decoder tail incl. the occ_voxel_feat[end_voxel_id] gather
+    (lidf_refine_forward), repeated forward_times (train_refine.yaml:82).  The PointNet re-run is a producer: excluded."""
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
+    from implicit_depth_b200.models import implicit_net as N
+    g = torch.Generator().manual_seed(7)
+    dec = N.IEF(dev, 334, 1, gf_dim=64, n_iter=2)
+    with torch.no_grad():
+        for p_ in dec.parameters():
+            p_.copy_(torch.randn(p_.shape, generator=g) / (p_.shape[1] ** 0.5) if p_.dim() == 2 else torch.randn(p_.shape, generator=g) * 0.1)
+    dec = dec.to(dev).eval()
+    out = step()
+    roi = lidf_query.roi_align_rays(d["full_rgb_feat"], d["miss_img_ind"], d["miss_bid"], 8)
+    vox = d["occ_vox_intersect_idx"]
+    dummy = torch.cat((vox, torch.zeros(1, dtype=vox.dtype, device=dev)), 0)
+    rb, xb = d["miss_bid"].int(), d["occ_vox_bid"].int()
+    R = int(d["miss_ray_dir"].shape[0])
+
+    def run():
+        pos = out["pred_pos"]
+        for _ in range(forward_times):
+            end = pcl_aabb.end_voxel(pos, d["voxel_bound"], rb, xb, dummy[out["max_pair_id"]].contiguous())
+            pos = lidf_query.refine_forward(pos, d["miss_ray_dir"], None, None, roi, dec, occ_voxel_feat=d["occ_voxel_feat"],
+                                            end_voxel_id=end, voxel_bound=d["voxel_bound"], mlp_impl=impl)
+        return pos
+    for _ in range(2):
+        run()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(3):
+        run()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / 3
+    return dict(ms=ms, rays=R, forward_times=forward_times, rays_per_s=R * forward_times / (ms * 1e-3),
+                nominal_tflops=R * forward_times * 522560 / (ms * 1e-3) / 1e12)
 
 
 def torch_gpu_baseline(d, off, prob, args, dev, rays=1 << 14):

@@ -406,7 +406,7 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
 // row-prep GEMM: T'[r] = W1[:,0:128] vox_end[r] + W1[:,128:256] rgb_end[r] + W1[:,dir] PE(dir_r) + b1 (+ IEF const).
 // -------------------------------------------------------------------------------------------------
 namespace {
-struct RefinePlan { int impl, pe_pos, pe_dir, D, KR, KP; float* T; SimtPack sp; size_t bytes; };
+struct RefinePlan { int impl, pe_pos, pe_dir, D, KR, KP; bool tc; float* T; float* Av; float* scratch; SimtPack sp; TcBufs tcb; size_t bytes; };
 int plan_refine(const LidfRefineParams* p, RefinePlan* q, char* base) {
   int rc = resolve_impl(p->mlp_impl, &q->impl);
   if (rc) return rc;
@@ -418,10 +418,55 @@ int plan_refine(const LidfRefineParams* p, RefinePlan* q, char* base) {
   q->KR = pad16(LIDF_VOX_DIM + LIDF_RGB_DIM + q->pe_dir);
   q->KP = pad16(q->pe_pos);
   Bump b{base, 0};
-  q->T = b.take<float>((size_t)p->R * 256);
-  q->sp = carve_simt_pack(b, 1, q->KR, q->KP, false);
+  // tcgen05 path: needs the un-gathered voxel features (per-voxel layer-1 term + in-kernel gather) and the shipped encodings
+  q->tc = q->impl != LIDF_MLP_SIMT_FP32 && p->occ_voxel_feat && p->end_voxel_id && p->V > 0 && p->pos_encode &&
+          p->multires == 8 && p->multires_views == 4 && (!p->intersect_pos_rel || p->voxel_bound);
+  if (q->tc) {
+    q->KR = pad16(LIDF_RGB_DIM + q->pe_dir);                           // per-ray rows: [rgb(128) | PE(dir)], as in stage 1
+    q->T = b.take<float>((size_t)p->R * 512);
+    q->Av = b.take<float>((size_t)p->V * 512);
+    q->scratch = b.take<float>((size_t)p->R);
+    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, true);
+    q->tcb = carve_tc(b, p->V, 1);
+  } else {
+    q->T = b.take<float>((size_t)p->R * 256);
+    q->Av = nullptr; q->scratch = nullptr;
+    q->sp = carve_simt_pack(b, 1, q->KR, q->KP, false);
+  }
   q->bytes = b.off + 256;
   return LIDF_OK;
+}
+
+// tcgen05 path of the refine tail: same factoring as lidf_query_forward with one decoder in slot 0 (slot 1 zero)
+int refine_forward_tc(const LidfRefineParams* p, RefinePlan& q, cudaStream_t st) {
+  int rc;
+  const LidfDecoder& dc = p->offset_dec;
+  const int ldw = q.D + (dc.kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
+  SimtPack& sp = q.sp;                                                  // Ntot = 512
+  LIDF_CUDA(cudaMemsetAsync(sp.Wt_row, 0, sizeof(float) * (size_t)sp.KR * sp.Ntot, st));
+  LIDF_CUDA(cudaMemsetAsync(sp.bias_row, 0, sizeof(float) * sp.Ntot, st));
+  LIDF_CUDA(cudaMemsetAsync(sp.Wt_vox, 0, sizeof(float) * (size_t)128 * sp.Ntot, st));
+  if ((rc = pack_wt(dc.w1, ldw, LIDF_VOX_DIM, LIDF_RGB_DIM, 256, sp.Wt_row, sp.Ntot, 0, 0, st))) return rc;              // rgb
+  if ((rc = pack_wt(dc.w1, ldw, LIDF_VOX_DIM + LIDF_RGB_DIM + q.pe_pos, q.pe_dir, 256, sp.Wt_row, sp.Ntot, LIDF_RGB_DIM, 0,
+                    st))) return rc;                                                                                     // PE(dir)
+  k_pack_bias1<<<1, 256, 0, st>>>(dc.w1, ldw, q.D, dc.b1, dc.w_enc, dc.b_enc, dc.kind == LIDF_DEC_IEF, dc.init_offset,
+                                  sp.bias_row, sp.u[0]);
+  LIDF_LAUNCH_CHECK();
+  if ((rc = pack_wt(dc.w1, ldw, 0, LIDF_VOX_DIM, 256, sp.Wt_vox, sp.Ntot, 0, 0, st))) return rc;                         // voxel
+  if ((rc = tc_rowprep_forward(p->rgb_feat_end, p->miss_ray_dir, p->R, sp.Wt_row, sp.Ntot, sp.bias_row, q.tcb.rp_wstream, q.T,
+                               q.impl, st, &g_launches, g_cuda_err, sizeof(g_cuda_err)))) return rc;
+  {
+    RowPrepArgs a{};
+    a.featA = p->occ_voxel_feat; a.featB = nullptr; a.dirs = nullptr; a.rows = p->V;
+    a.multires_views = p->multires_views; a.pos_encode = p->pos_encode;
+    a.Wt = sp.Wt_vox; a.Kpad = 128; a.Ntot = sp.Ntot; a.bias = nullptr; a.out = q.Av;
+    const size_t smem = sizeof(float) * ((size_t)LIDF_SIMT_BM * 128 + LIDF_KC * 128);
+    LIDF_CUDA(cudaFuncSetAttribute(k_rowprep, cudaFuncAttributeMaxDynamicSharedMemorySize, 100 * 1024));
+    k_rowprep<<<dim3((unsigned)((p->V + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem, st>>>(a);
+    LIDF_LAUNCH_CHECK();
+  }
+  return tc_refine_forward(p, q.tcb, q.T, q.Av, sp.u[0], q.scratch, q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
+                           sizeof(g_cuda_err));
 }
 }  // namespace
 
@@ -437,15 +482,17 @@ extern "C" int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stre
   if (p->R < 0) return LIDF_ERR_ARG;
   if (p->R >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;
   if (p->R == 0) return LIDF_OK;
-  if (!p->pred_pos || !p->miss_ray_dir || !p->voxel_feat_end || !p->rgb_feat_end || !p->pred_pos_refine || !p->workspace)
-    return LIDF_ERR_NULL;
-  if (p->intersect_pos_rel && !p->end_voxel_center) return LIDF_ERR_NULL;
+  if (!p->pred_pos || !p->miss_ray_dir || !p->rgb_feat_end || !p->pred_pos_refine || !p->workspace) return LIDF_ERR_NULL;
+  if (p->V < 0 || p->V >= INT_MAX / 512) return LIDF_ERR_ARG;
   RefinePlan q;
   int rc = plan_refine(p, &q, (char*)p->workspace);
   if (rc) return rc;
   if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
   if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
   cudaStream_t st = stream;
+  if (q.tc) return refine_forward_tc(p, q, st);
+  if (!p->voxel_feat_end) return LIDF_ERR_NULL;
+  if (p->intersect_pos_rel && !p->end_voxel_center) return LIDF_ERR_NULL;
   const LidfDecoder& dc = p->offset_dec;
   const int ldw = q.D + (dc.kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
   SimtPack& sp = q.sp;

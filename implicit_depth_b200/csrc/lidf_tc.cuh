@@ -222,19 +222,21 @@ __device__ __forceinline__ void split16(const float* x, uint32_t* out16) {
 
 // ------------------------------------------------------------------------------------------------ packing kernels
 // element e of the layer-1 MMA operand (K index) -> column of linear_1.weight; -1 = zero padding.
-__host__ __device__ inline int tc_a1_col(int e, int pe_pos) {
+// single_pos (RefineNet decoder tail, pipeline.py:1018-1023): only one encoded position sits at column 256; the
+// "leave" slots of the operand get zero weights.
+__host__ __device__ inline int tc_a1_col(int e, int pe_pos, int single_pos = 0) {
   const int base = LIDF_VOX_DIM + LIDF_RGB_DIM;             // PE(enter) starts at column 256 (pipeline.py:431-433)
   if (e < 48) return base + 3 + e;                          // sin/cos part of PE(enter)
-  if (e < 96) return base + pe_pos + 3 + (e - 48);          // sin/cos part of PE(leave)
+  if (e < 96) return single_pos ? -1 : base + pe_pos + 3 + (e - 48);   // sin/cos part of PE(leave)
   if (e < 99) return base + (e - 96);                       // raw enter xyz
-  if (e < 102) return base + pe_pos + (e - 99);             // raw leave xyz
+  if (e < 102) return single_pos ? -1 : base + pe_pos + (e - 99);      // raw leave xyz
   return -1;
 }
 
 // weight stream of one decoder: 34 chunks x 8 KB.  Chunk with N rows (128, or 64 for layer 3) holds k-steps of
 // [hi: kg0 N x 16 B | kg1 N x 16 B][lo: kg0 | kg1]; an N=128 chunk is one k-step, an N=64 chunk two.
 __global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe_pos, const float* __restrict__ w2,
-                                  const float* __restrict__ w3, uint8_t* __restrict__ stream) {
+                                  const float* __restrict__ w3, uint8_t* __restrict__ stream, int single_pos) {
   const int idx = blockIdx.x * blockDim.x + threadIdx.x;
   if (idx >= TC_CHUNKS_PER_DEC * 2048) return;
   const int c = idx / 2048, r = idx % 2048;
@@ -244,7 +246,7 @@ __global__ void k_pack_tc_weights(const float* __restrict__ w1, int ldw1, int pe
     N = 128; n = r / 16; kk = r % 16;
     if (c < 14) {                                           // layer 1, output half 0 / 1
       const int half = c >= 7, s = half ? c - 7 : c;
-      const int col = tc_a1_col(16 * s + kk, pe_pos);
+      const int col = tc_a1_col(16 * s + kk, pe_pos, single_pos);
       if (col >= 0) w = w1[(size_t)(half * 128 + n) * ldw1 + col];
     } else {                                                // layer 2, K half 0 / 1
       const int half = c >= 22, s = half ? c - 22 : c - 14;
@@ -432,6 +434,7 @@ struct TcArgs {
   const int* perm; const int64_t* pair_vox; const int64_t* pair_ray;
   const float* pair_dist; const float* dense_dist; int64_t R;
   const float* ray_dir; const float* voxel_bound; int rel;
+  const float* pos_in;             // RefineNet tail: row = ray, position given ([P,3]); pair_ray / dist are not read
   const float* Av;                 // [V][512] per-voxel layer-1 term, decoder d at column 256 d
   const float* T;                  // [R][512] per-ray layer-1 term, decoder d at column 256 d
   const uint8_t* wstream;          // [2][34][8192]
@@ -721,8 +724,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       if (s < a.P) {
         m.valid = true;
         m.orig = orig_;
-        m.vox = (int)a.pair_vox[m.orig]; m.ray = (int)a.pair_ray[m.orig];
-        if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)m.orig); m.t0 = t.x; m.t1 = t.y; }
+        m.vox = (int)a.pair_vox[m.orig]; m.ray = a.pos_in ? m.orig : (int)a.pair_ray[m.orig];
+        if (a.pos_in) { }
+        else if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)m.orig); m.t0 = t.x; m.t1 = t.y; }
         else { const size_t o = ((size_t)m.vox * a.R + m.ray) * 2; m.t0 = a.dense_dist[o]; m.t1 = a.dense_dist[o + 1]; }
       }
       return m;
@@ -736,9 +740,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         for (int k = 0; k < 3; ++k) {
           dir[k] = a.ray_dir[(size_t)m.ray * 3 + k];
           const float c = a.rel ? (a.voxel_bound[(size_t)m.vox * 6 + k] + a.voxel_bound[(size_t)m.vox * 6 + 3 + k]) / 2.0f : 0.f;
-          enter[k] = dir[k] * m.t0;
+          enter[k] = a.pos_in ? a.pos_in[(size_t)m.orig * 3 + k] : dir[k] * m.t0;
           pe[k] = enter[k] - c;
-          pl[k] = dir[k] * m.t1 - c;
+          pl[k] = a.pos_in ? 0.f : dir[k] * m.t1 - c;
         }
       }
       if (g < 2) {
@@ -1241,6 +1245,10 @@ inline int tc_device_ok() {
   return major == 10;
 }
 
+struct TcArgs;
+inline int tc_launch(TcArgs& a, cudaStream_t st, int64_t* launches, char* errbuf, size_t errlen,
+                     void (*mlp_event)(int, cudaStream_t));
+
 // decoders + pair_pred_pos for all P pairs; T = per-ray layer-1 term [R][512], u = IEF rank-1 vector of offset_dec
 inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const int* perm, const float* T, const float* Av,
                             const float* u,
@@ -1252,7 +1260,7 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   for (int d = 0; d < 2; ++d) {
     const int ldw = D + (decs[d]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
     k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(
-        decs[d]->w1, ldw, pe_pos, decs[d]->w2, decs[d]->w3, tb.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES);
+        decs[d]->w1, ldw, pe_pos, decs[d]->w2, decs[d]->w3, tb.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES, 0);
     TC_LAUNCH_CHECK();
   }
   TcArgs a{};
@@ -1266,7 +1274,17 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
     a.kind[d] = decs[d]->kind; a.n_pass[d] = decs[d]->kind == LIDF_DEC_IEF ? decs[d]->n_iter : 1;
     a.use_sigmoid[d] = decs[d]->use_sigmoid;
   }
-  if (a.n_pass[0] + a.n_pass[1] > TC_MAX_PASSES) return LIDF_ERR_UNSUPPORTED;
+  a.o0 = decs[0]->init_offset; a.r0 = p->offset_range0; a.r1 = p->offset_range1;
+  a.sqrt3 = (float)sqrt(3.0); a.part = p->part_size;
+  a.out[0] = p->pred_offset; a.out[1] = p->pred_prob_end; a.pos_out = p->pair_pred_pos;
+  a.n_prod = impl == LIDF_MLP_TC_BF16X1 ? 1 : 3;
+  return tc_launch(a, st, launches, errbuf, errlen, mlp_event);
+}
+
+// pass schedule + launch of k_mlp_tc (a.n_pass[] / a.kind[] set by the caller)
+inline int tc_launch(TcArgs& a, cudaStream_t st, int64_t* launches, char* errbuf, size_t errlen,
+                     void (*mlp_event)(int, cudaStream_t)) {
+  if (a.n_pass[0] + a.n_pass[1] > TC_MAX_PASSES || a.n_pass[0] + a.n_pass[1] < 1) return LIDF_ERR_UNSUPPORTED;
   {  // interleave the two decoders' passes: d0 it0, d1 it0, d0 it1, d1 it1, ... then whatever is left of the longer one
     int it[2] = {0, 0};
     a.npt = 0; a.pass_dec_mask = 0; a.pass_it_pack = 0;
@@ -1278,10 +1296,6 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
           ++a.npt;
         }
   }
-  a.o0 = decs[0]->init_offset; a.r0 = p->offset_range0; a.r1 = p->offset_range1;
-  a.sqrt3 = (float)sqrt(3.0); a.part = p->part_size;
-  a.out[0] = p->pred_offset; a.out[1] = p->pred_prob_end; a.pos_out = p->pair_pred_pos;
-  a.n_prod = impl == LIDF_MLP_TC_BF16X1 ? 1 : 3;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -1297,6 +1311,33 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   if (mlp_event) mlp_event(1, st);
   TC_LAUNCH_CHECK();
   return LIDF_OK;
+}
+
+// RefineNet decoder tail on the same engine: row = ray, "voxel of the pair" = end_voxel_id[ray], one decoder (its IEF passes
+// run back to back), layer-1 MMA operand = PE(pos [- centre]) in the enter slots (leave slots carry zero weights),
+// pred_pos_refine = pos + (o (r1 - r0) + r0) dir  (pipeline.py:1018-1029: no sqrt(3) part_size factor here).
+inline int tc_refine_forward(const LidfRefineParams* p, const TcBufs& tb, const float* T, const float* Av, const float* u,
+                             float* scratch_out, int pe_pos, int D, int impl, cudaStream_t st, int64_t* launches,
+                             char* errbuf, size_t errlen) {
+  if (!p->pos_encode || p->multires != 8 || pe_pos != 51) return LIDF_ERR_UNSUPPORTED;
+  if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
+  const LidfDecoder& dc = p->offset_dec;
+  const int ldw = D + (dc.kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
+  k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(dc.w1, ldw, pe_pos, dc.w2, dc.w3, tb.wstream, 1);
+  TC_LAUNCH_CHECK();
+  TcArgs a{};
+  a.P = p->R; a.n_tiles = (int)((p->R + 127) / 128);
+  a.perm = nullptr; a.pair_vox = p->end_voxel_id; a.pair_ray = nullptr; a.pair_dist = nullptr; a.dense_dist = nullptr;
+  a.R = p->R; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound; a.rel = p->intersect_pos_rel;
+  a.pos_in = p->pred_pos; a.Av = Av; a.T = T; a.wstream = tb.wstream;
+  a.u = dc.kind == LIDF_DEC_IEF ? u : nullptr;
+  for (int d = 0; d < 2; ++d) { a.b2[d] = dc.b2; a.b3[d] = dc.b3; a.w4[d] = dc.w4; a.b4[d] = dc.b4; a.use_sigmoid[d] = dc.use_sigmoid; }
+  a.kind[0] = dc.kind; a.n_pass[0] = dc.kind == LIDF_DEC_IEF ? dc.n_iter : 1;
+  a.kind[1] = LIDF_DEC_IMNET; a.n_pass[1] = 0;
+  a.o0 = dc.init_offset; a.r0 = p->offset_range0; a.r1 = p->offset_range1; a.sqrt3 = 1.f; a.part = 1.f;
+  a.out[0] = scratch_out; a.out[1] = scratch_out; a.pos_out = p->pred_pos_refine;
+  a.n_prod = impl == LIDF_MLP_TC_BF16X1 ? 1 : 3;
+  return tc_launch(a, st, launches, errbuf, errlen, nullptr);
 }
 
 // per-ray layer-1 term on the tensor cores; Wt = sp.Wt_row [160][512], wstream scratch = 4 x 10 x 8 KB

@@ -56,9 +56,11 @@ class _RefineParams(C.Structure):
                 ("pos_encode", C.c_int32), ("multires", C.c_int32), ("multires_views", C.c_int32),
                 ("intersect_pos_rel", C.c_int32), ("offset_range0", C.c_float), ("offset_range1", C.c_float),
                 ("offset_dec", _Decoder), ("mlp_impl", C.c_int32), ("pred_pos_refine", C.c_void_p),
-                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("V", C.c_int64), ("occ_voxel_feat", C.c_void_p), ("end_voxel_id", C.c_void_p), ("voxel_bound", C.c_void_p)]
 
 
+ABI_VERSION = 2
 EXPORTED_SYMBOLS = [
     "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
     "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
@@ -120,7 +122,7 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_pcl_aabb_pair_label.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp]
     lib.lidf_pcl_aabb_end_voxel.restype = C.c_int
     lib.lidf_pcl_aabb_end_voxel.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
-    if lib.lidf_query_abi_version() != 1:
+    if lib.lidf_query_abi_version() != ABI_VERSION:
         raise RuntimeError("liblidf_query.so ABI version mismatch")
     lib.lidf_query_struct_size.restype = C.c_size_t
     lib.lidf_query_struct_size.argtypes = [C.c_int]
@@ -397,8 +399,14 @@ class _LidfQuery:
     def refine_forward(self, pred_pos, miss_ray_dir, end_voxel_center, voxel_feat_end, rgb_feat_end, offset_dec, *,
                        pos_encode: bool = True, multires: int = 8, multires_views: int = 4,
                        intersect_pos_type: str = "abs", n_iter: int = 2, use_sigmoid: bool = False,
-                       offset_range: Sequence[float] = (-0.2, 0.2), mlp_impl: str = "auto") -> torch.Tensor:
-        """pipeline.py:1018-1029 for all rays at once."""
+                       offset_range: Sequence[float] = (-0.2, 0.2), mlp_impl: str = "auto",
+                       occ_voxel_feat: Optional[torch.Tensor] = None, end_voxel_id: Optional[torch.Tensor] = None,
+                       voxel_bound: Optional[torch.Tensor] = None) -> torch.Tensor:
+        """pipeline.py:1018-1029 for all rays at once.
+
+        Either pass the gathered ``voxel_feat_end`` [R,128] (+ ``end_voxel_center`` for 'rel'): fp32 FFMA engine.  Or pass
+        what the reference holds just before that gather -- ``occ_voxel_feat`` [V,128], ``end_voxel_id`` [R] (and
+        ``voxel_bound`` [V,6] for 'rel') -- and the decoder runs on the tcgen05 engine (``mlp_impl`` "auto")."""
         dev = pred_pos.device
         R = int(pred_pos.shape[0])
         keep: list = []
@@ -406,9 +414,22 @@ class _LidfQuery:
         p.R = R
         p.pred_pos = _chk(pred_pos, "pred_pos", torch.float32)
         p.miss_ray_dir = _chk(miss_ray_dir, "miss_ray_dir", torch.float32)
+        ungathered = occ_voxel_feat is not None and end_voxel_id is not None
+        if ungathered and mlp_impl == "simt_fp32" and voxel_feat_end is None:
+            voxel_feat_end = occ_voxel_feat[end_voxel_id].contiguous()           # the reference's gather, pipeline.py:1016
+            if intersect_pos_type == "rel" and end_voxel_center is None:
+                vb = voxel_bound[end_voxel_id]
+                end_voxel_center = ((vb[:, :3] + vb[:, 3:]) / 2.).contiguous()
         p.end_voxel_center = _chk(end_voxel_center, "end_voxel_center", torch.float32, optional=True)
-        p.voxel_feat_end = _chk(voxel_feat_end, "voxel_feat_end", torch.float32)
+        p.voxel_feat_end = _chk(voxel_feat_end, "voxel_feat_end", torch.float32, optional=ungathered)
         p.rgb_feat_end = _chk(rgb_feat_end, "rgb_feat_end", torch.float32)
+        if ungathered:
+            if tuple(end_voxel_id.shape) != (R,) or occ_voxel_feat.dim() != 2 or occ_voxel_feat.shape[1] != 128:
+                raise RuntimeError("occ_voxel_feat must be [V,128] and end_voxel_id [R]")
+            p.V = int(occ_voxel_feat.shape[0])
+            p.occ_voxel_feat = _chk(occ_voxel_feat, "occ_voxel_feat", torch.float32)
+            p.end_voxel_id = _chk(end_voxel_id, "end_voxel_id", torch.int64)
+            p.voxel_bound = _chk(voxel_bound, "voxel_bound", torch.float32, optional=intersect_pos_type != "rel")
         p.pos_encode = int(bool(pos_encode)); p.multires = int(multires); p.multires_views = int(multires_views)
         p.intersect_pos_rel = int(intersect_pos_type == "rel")
         p.offset_range0, p.offset_range1 = float(offset_range[0]), float(offset_range[1])

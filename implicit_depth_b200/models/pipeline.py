@@ -228,14 +228,13 @@ class RefineDecoderMixin:
                                   end_voxel_id)
 
     def refine_decoder_tail(self, data_dict, pred_pos, end_voxel_id, occ_voxel_feat, rgb_feat_per_ray):
+        """pipeline.py:1016-1029: gather of the end-voxel feature + decoder + position update, one fused call (the gather
+        and the voxel centre for 'rel' positions happen inside the kernel)."""
         r = self.opt.refine
-        center = None
-        if r.intersect_pos_type == 'rel':
-            vb = data_dict['voxel_bound'][end_voxel_id]
-            center = ((vb[:, :3] + vb[:, 3:]) / 2.).contiguous()
         return lidf_query.refine_forward(
-            pred_pos.contiguous(), data_dict['miss_ray_dir'].contiguous(), center,
-            occ_voxel_feat[end_voxel_id].contiguous(), rgb_feat_per_ray.contiguous(), self.offset_dec,
+            pred_pos.contiguous(), data_dict['miss_ray_dir'].contiguous(), None, None, rgb_feat_per_ray.contiguous(),
+            self.offset_dec, occ_voxel_feat=occ_voxel_feat.float().contiguous(), end_voxel_id=end_voxel_id.long().contiguous(),
+            voxel_bound=data_dict['voxel_bound'].contiguous(),
             pos_encode=bool(r.pos_encode), multires=int(r.multires), multires_views=int(r.multires_views),
             intersect_pos_type=str(r.intersect_pos_type), n_iter=int(r.n_iter), use_sigmoid=bool(r.use_sigmoid),
             offset_range=tuple(float(v) for v in r.offset_range), mlp_impl=self.mlp_impl)

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LIDF_QUERY_ABI_VERSION 1
+#define LIDF_QUERY_ABI_VERSION 2
 
 /* fixed by the shipped YAMLs (train_lidf.yaml:36-57): rgb_out 32 x roi_out_bbox 2^2, pnet_out 128, imnet_gf 64 */
 #define LIDF_RGB_CH 32
@@ -126,6 +126,14 @@ typedef struct LidfRefineParams {
   int32_t mlp_impl;
   float* pred_pos_refine;       /* [R,3] */
   void* workspace; size_t workspace_bytes;
+  /* Optional (ABI 2): the voxel features UN-gathered, as the reference holds them right before the gather
+   * `occ_voxel_feat[end_voxel_id]` (pipeline.py:1016): occ_voxel_feat [V,128] + end_voxel_id [R] (+ voxel_bound [V,6], read
+   * instead of end_voxel_center when intersect_pos_rel).  With these set, voxel_feat_end may be NULL and the decoder runs on
+   * the tcgen05 engine (per-voxel layer-1 term + gather, as in lidf_query_forward) unless mlp_impl = LIDF_MLP_SIMT_FP32. */
+  int64_t V;
+  const float* occ_voxel_feat;
+  const int64_t* end_voxel_id;
+  const float* voxel_bound;
 } LidfRefineParams;
 
 int lidf_query_abi_version(void);

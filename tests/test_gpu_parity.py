@@ -268,14 +268,56 @@ def test_refine_decoder_tail(rel):
     rgb = _lq().roi_align_rays(d["full_rgb_feat"].cuda(), d["miss_img_ind"].cuda(), d["miss_bid"].cuda(), 8)
     rng = tuple(float(v) for v in extra["refine.offset_range"])
     vfe = extra["refine.occ_voxel_feat"][evid].contiguous()
-    out = _lq().refine_forward(ref["pred_pos"].cuda(), d["miss_ray_dir"].cuda(), center.cuda() if rel else None,
-                               vfe.cuda(), rgb, _cuda(rdec), intersect_pos_type="rel" if rel else "abs",
-                               n_iter=extra["refine.n_iter"], offset_range=rng)
+    kw = dict(intersect_pos_type="rel" if rel else "abs", n_iter=extra["refine.n_iter"], offset_range=rng)
     rcfg = dict(O.REFINE_CFG, offset_range=rng, n_iter=extra["refine.n_iter"], intersect_pos_type="rel" if rel else "abs")
     want = O.refine_decoder_tail(ref["pred_pos"], d["miss_ray_dir"], center, vfe, rgb.cpu(), rcfg, rdec)
+    # (1) gathered features -> fp32 engine
+    out = _lq().refine_forward(ref["pred_pos"].cuda(), d["miss_ray_dir"].cuda(), center.cuda() if rel else None,
+                               vfe.cuda(), rgb, _cuda(rdec), **kw)
     assert rel_err(out.cpu(), want) < TOL_FP32
     if not rel:
         assert rel_err(out.cpu(), ref["pred_pos_refine"]) < TOL_FP32        # the reference's own get_pred_refine output
+    # (2) un-gathered features (occ_voxel_feat + end_voxel_id + voxel_bound): tcgen05 engine, gather + centre in-kernel
+    ung = dict(occ_voxel_feat=extra["refine.occ_voxel_feat"].cuda(), end_voxel_id=evid.cuda(), voxel_bound=d["voxel_bound"].cuda())
+    out_tc = _lq().refine_forward(ref["pred_pos"].cuda(), d["miss_ray_dir"].cuda(), None, None, rgb, _cuda(rdec),
+                                  mlp_impl="tc_bf16x3", **ung, **kw)
+    assert rel_err(out_tc.cpu(), want) < TOL_TC
+    # the offset itself (pos_refine - pos along the ray) must hold the tolerance too, not just the position
+    dirs = d["miss_ray_dir"]
+    o_want = ((want - ref["pred_pos"]) * dirs).sum(-1)
+    o_got = ((out_tc.cpu() - ref["pred_pos"]) * dirs).sum(-1)
+    assert rel_err(o_got, o_want) < 2 * TOL_TC
+    # (3) same inputs, fp32 engine requested: the wrapper performs the reference's gather
+    out_f = _lq().refine_forward(ref["pred_pos"].cuda(), d["miss_ray_dir"].cuda(), None, None, rgb, _cuda(rdec),
+                                 mlp_impl="simt_fp32", **ung, **kw)
+    assert torch.equal(out_f, out)
+
+
+@pytest.mark.parametrize("dec_kind,n_iter", [("IMNET", 1), ("IEF", 1), ("IEF", 3)])
+def test_refine_decoder_tail_tc_seeded(dec_kind, n_iter):
+    """RefineNet tail on the tcgen05 engine for other decoder shapes, odd ray counts (partial tile) and a ray set larger
+    than one wave of tiles, against the oracle."""
+    from implicit_depth_b200.synthetic import make_inputs
+    d = make_inputs(2, 97, 113, 2, V_img=40, seed=61)                 # R = 21,922 rays = 171.3 tiles
+    R, V = d["miss_ray_dir"].shape[0], d["occ_voxel_feat"].shape[0]
+    g = torch.Generator().manual_seed(62)
+    rdec = O.init_decoder(dec_kind, 334, mode="trained", generator=g)
+    pos = d["miss_ray_dir"] * (0.4 + 2.0 * torch.rand(R, 1, generator=g))
+    evid = torch.randint(0, V, (R,), generator=g)
+    rgb = _lq().roi_align_rays(d["full_rgb_feat"].cuda(), d["miss_img_ind"].cuda(), d["miss_bid"].cuda(), 8)
+    for rel in (False, True):
+        vb = d["voxel_bound"][evid]
+        center = ((vb[:, :3] + vb[:, 3:]) / 2).contiguous()
+        rcfg = dict(O.REFINE_CFG, n_iter=n_iter, intersect_pos_type="rel" if rel else "abs", offdec_type=dec_kind)
+        want = O.refine_decoder_tail(pos, d["miss_ray_dir"], center, d["occ_voxel_feat"][evid], rgb.cpu(), rcfg, rdec)
+        got = _lq().refine_forward(pos.cuda(), d["miss_ray_dir"].cuda(), None, None, rgb, _cuda(rdec),
+                                   occ_voxel_feat=d["occ_voxel_feat"].cuda(), end_voxel_id=evid.cuda(),
+                                   voxel_bound=d["voxel_bound"].cuda(), intersect_pos_type="rel" if rel else "abs",
+                                   n_iter=n_iter, mlp_impl="tc_bf16x3")
+        assert rel_err(got.cpu(), want) < TOL_TC, (rel, rel_err(got.cpu(), want))
+        o_want = ((want - pos) * d["miss_ray_dir"]).sum(-1)
+        o_got = ((got.cpu() - pos) * d["miss_ray_dir"]).sum(-1)
+        assert rel_err(o_got, o_want) < 2 * TOL_TC, (rel, rel_err(o_got, o_want))
 
 
 def test_module_surface_forward_and_errors():
