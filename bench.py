@@ -197,8 +197,12 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    from implicit_depth_b200.extensions.lidf_query.jit import bind_to_device_numa_node, lidf_query
     from implicit_depth_b200.synthetic import make_inputs
+
+    # one process per GPU: stay on the GPU's NUMA node so the pinned host buffers of the e2e path sit next to its PCIe port
+    # (N > 1 only: at N = 1 the process keeps every core for the CPU baseline it also has to time)
+    numa_node = bind_to_device_numa_node(local)[0] if world > 1 else None
 
     B, H, W, N = WORKLOADS[args.workload]
     d = make_inputs(B, H, W, N, seed=1234 + rank, device=dev)      # this rank's images; pair list voxel-major
@@ -261,7 +265,7 @@ def main():
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
         e2e = dict(value=P * world / float(te), unit="points/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   ms_per_step=float(te) * 1e3)
+                   ms_per_step=float(te) * 1e3, host_numa_node=numa_node)
         del host, out_host
 
     if rank != 0:
@@ -283,7 +287,7 @@ def main():
                     executed_tflops=(P * 2 * EXEC_MAC_TC / (k_ms * 1e-3) / 1e12) if args.engine != "simt_fp32" else None,
                     peak_source=peaks["source"] + ", bf16_tflops_sustained")
     cpu = None
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:     # the CPU baseline is an N = 1 figure (rank 0, all host cores)
         pts, tcpu, threads, sample, _ = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs)
         cpu = dict(value=pts, unit="points/s", cores=threads, kind="port", sample=sample, seconds=tcpu)
     line = dict(metric="lidf_query_points_per_sec", value=value, unit="points/s", n_gpus=world, steps=args.steps,

@@ -132,6 +132,39 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     return lib
 
 
+def bind_to_device_numa_node(device_index: int):
+    """Pin the calling process to the CPUs of the NUMA node the GPU hangs off (sysfs), so that the pinned host buffers of
+    ``forward_host`` are allocated next to the GPU's PCIe root port.  One process per GPU (the reference's mp.spawn /
+    torchrun model) otherwise lands on arbitrary sockets and the H2D / D2H streams of 8 ranks cross the socket
+    interconnect.  Returns (node, previous_affinity) or (None, previous_affinity) when the topology cannot be read."""
+    prev = os.sched_getaffinity(0)
+    try:
+        props = torch.cuda.get_device_properties(device_index)
+        if all(hasattr(props, a) for a in ("pci_domain_id", "pci_bus_id", "pci_device_id")):
+            bus = f"{props.pci_domain_id:04x}:{props.pci_bus_id:02x}:{props.pci_device_id:02x}.0"
+        else:
+            import subprocess
+            out = subprocess.run(["nvidia-smi", "-i", str(device_index), "--query-gpu=pci.bus_id", "--format=csv,noheader"],
+                                 capture_output=True, text=True).stdout.strip().lower()
+            bus = out[-12:] if len(out) >= 12 else out             # nvidia-smi prints an 8-digit domain
+        with open(f"/sys/bus/pci/devices/{bus}/numa_node") as f:
+            node = int(f.read().strip())
+        if node < 0:
+            return None, prev
+        with open(f"/sys/devices/system/node/node{node}/cpulist") as f:
+            cpus = set()
+            for part in f.read().strip().split(","):
+                a, _, b = part.partition("-")
+                cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= prev
+        if not cpus:
+            return None, prev
+        os.sched_setaffinity(0, cpus)
+        return node, prev
+    except Exception:
+        return None, prev
+
+
 def _chk(t: Optional[torch.Tensor], name: str, dtype, optional: bool = False):
     """The reference's CHECK_INPUT (ray_aabb_cuda.cpp:16-18) plus a dtype check."""
     if t is None:
