@@ -154,6 +154,10 @@ __global__ void __launch_bounds__(AABB_THREADS) k_aabb_fill(const float* __restr
 }
 
 // ---- dense drop-in: mask[V,R] int32, dist[V,R,2] -- every element written once with streaming stores -----------------
+// Thread t of a work item owns the 4 consecutive rays 4t .. 4t+3 of the tile: one 16-byte mask store and two 16-byte
+// dist stores per thread (a warp writes 512 B + 1 KB contiguous), 16-byte loads of the image ids and reciprocal
+// directions.  VEC = false (R not a multiple of 4: rows are not 16-byte aligned) falls back to scalar accesses.
+template <bool VEC>
 __global__ void __launch_bounds__(AABB_THREADS) k_aabb_dense(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
                                                              const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
                                                              const int2* __restrict__ tile_bid, int64_t R, int64_t RB, int64_t M,
@@ -163,37 +167,80 @@ __global__ void __launch_bounds__(AABB_THREADS) k_aabb_dense(const float* __rest
     const int vbid = __ldg(voxel_bid + v);
     const int2 tb = __ldg(tile_bid + rb);
     const bool live = !(vbid < tb.x || vbid > tb.y);
-    AabbBox box;
-    if (live) box = aabb_load_box(voxel_bound, v);
+    const int64_t r0 = rb * AABB_TILE + 4 * (int64_t)threadIdx.x;
+    if (r0 >= R) continue;
+    int hit[4] = {0, 0, 0, 0};
+    float t0[4] = {0.f, 0.f, 0.f, 0.f}, t1[4] = {0.f, 0.f, 0.f, 0.f};
+    if (live) {
+      const AabbBox box = aabb_load_box(voxel_bound, v);
+      if (VEC) {
+        const int4 b4 = *reinterpret_cast<const int4*>(ray_bid + r0);
+        const int bid[4] = {b4.x, b4.y, b4.z, b4.w};
+        if (bid[0] == vbid || bid[1] == vbid || bid[2] == vbid || bid[3] == vbid) {
+          const float4 i0 = *reinterpret_cast<const float4*>(inv + r0 * 3), i1 = *reinterpret_cast<const float4*>(inv + r0 * 3 + 4),
+                       i2 = *reinterpret_cast<const float4*>(inv + r0 * 3 + 8);
+          const float iv[12] = {i0.x, i0.y, i0.z, i0.w, i1.x, i1.y, i1.z, i1.w, i2.x, i2.y, i2.z, i2.w};
 #pragma unroll
-    for (int j = 0; j < AABB_RPT; ++j) {
-      const int64_t r = rb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
-      if (r >= R) continue;
-      float t0 = 0.f, t1 = 0.f;
-      bool hit = false;
-      if (live && ray_bid[r] == vbid) hit = aabb_slab(inv[r * 3 + 0], inv[r * 3 + 1], inv[r * 3 + 2], box, t0, t1);
-      if (!hit) { t0 = 0.f; t1 = 0.f; }
-      __stcs(mask + v * R + r, hit ? 1 : 0);
-      __stcs(dist + v * R + r, make_float2(t0, t1));
+          for (int j = 0; j < 4; ++j)
+            if (bid[j] == vbid && aabb_slab(iv[3 * j], iv[3 * j + 1], iv[3 * j + 2], box, t0[j], t1[j])) hit[j] = 1;
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int64_t r = r0 + j;
+          if (r < R && ray_bid[r] == vbid && aabb_slab(inv[r * 3 + 0], inv[r * 3 + 1], inv[r * 3 + 2], box, t0[j], t1[j])) hit[j] = 1;
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (!hit[j]) { t0[j] = 0.f; t1[j] = 0.f; }
+    }
+    int* mp = mask + v * R + r0;
+    float2* dp = dist + v * R + r0;
+    if (VEC) {
+      __stcs(reinterpret_cast<int4*>(mp), make_int4(hit[0], hit[1], hit[2], hit[3]));
+      __stcs(reinterpret_cast<float4*>(dp), make_float4(t0[0], t1[0], t0[1], t1[1]));
+      __stcs(reinterpret_cast<float4*>(dp) + 1, make_float4(t0[2], t1[2], t0[3], t1[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (r0 + j < R) { __stcs(mp + j, hit[j]); __stcs(dp + j, make_float2(t0[j], t1[j])); }
     }
   }
 }
 
-// ---- point-in-box: dense drop-in mask[V,N] ---------------------------------------------------------------------------
+// ---- point-in-box: dense drop-in mask[V,N], same thread mapping ------------------------------------------------------
+template <bool VEC>
 __global__ void __launch_bounds__(AABB_THREADS) k_pcl_dense(const float* __restrict__ pcl_pos, const float* __restrict__ voxel_bound,
                                                             const int32_t* __restrict__ pcl_bid, const int32_t* __restrict__ voxel_bid,
                                                             int64_t N, int64_t NB, int64_t M, int* __restrict__ mask) {
   for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
     const int64_t v = w / NB, nb = w - v * NB;
+    const int64_t n0 = nb * AABB_TILE + 4 * (int64_t)threadIdx.x;
+    if (n0 >= N) continue;
     const int vbid = __ldg(voxel_bid + v);
     const AabbBox box = aabb_load_box(voxel_bound, v);
+    int in[4] = {0, 0, 0, 0};
+    if (VEC) {
+      const int4 b4 = *reinterpret_cast<const int4*>(pcl_bid + n0);
+      const int bid[4] = {b4.x, b4.y, b4.z, b4.w};
+      if (bid[0] == vbid || bid[1] == vbid || bid[2] == vbid || bid[3] == vbid) {
+        const float4 p0 = *reinterpret_cast<const float4*>(pcl_pos + n0 * 3), p1 = *reinterpret_cast<const float4*>(pcl_pos + n0 * 3 + 4),
+                     p2 = *reinterpret_cast<const float4*>(pcl_pos + n0 * 3 + 8);
+        const float pv[12] = {p0.x, p0.y, p0.z, p0.w, p1.x, p1.y, p1.z, p1.w, p2.x, p2.y, p2.z, p2.w};
 #pragma unroll
-    for (int j = 0; j < AABB_RPT; ++j) {
-      const int64_t n = nb * AABB_TILE + j * AABB_THREADS + threadIdx.x;
-      if (n >= N) continue;
-      bool in = false;
-      if (pcl_bid[n] == vbid) in = aabb_inside(pcl_pos[n * 3 + 0], pcl_pos[n * 3 + 1], pcl_pos[n * 3 + 2], box);
-      __stcs(mask + v * N + n, in ? 1 : 0);
+        for (int j = 0; j < 4; ++j)
+          if (bid[j] == vbid && aabb_inside(pv[3 * j], pv[3 * j + 1], pv[3 * j + 2], box)) in[j] = 1;
+      }
+      __stcs(reinterpret_cast<int4*>(mask + v * N + n0), make_int4(in[0], in[1], in[2], in[3]));
+    } else {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int64_t n = n0 + j;
+        if (n >= N) break;
+        const bool inside = pcl_bid[n] == vbid && aabb_inside(pcl_pos[n * 3 + 0], pcl_pos[n * 3 + 1], pcl_pos[n * 3 + 2], box);
+        __stcs(mask + v * N + n, inside ? 1 : 0);
+      }
     }
   }
 }

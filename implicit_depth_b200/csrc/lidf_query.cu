@@ -593,8 +593,14 @@ extern "C" int lidf_ray_aabb_forward(const float* ray_dir, const float* voxel_bo
   if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
   cudaStream_t st = stream;
   if ((rc = aabb_ray_prep(q, ray_dir, ray_bid, R, st))) return rc;
-  k_aabb_dense<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R, q.RB,
-                                                                    q.M, mask, reinterpret_cast<float2*>(dist));
+  // 16-byte accesses need R % 4 == 0 (every mask/dist row then starts 16-byte aligned) and aligned base pointers
+  const bool vec = R % 4 == 0 && ((uintptr_t)mask % 16 == 0) && ((uintptr_t)dist % 16 == 0) && ((uintptr_t)ray_bid % 16 == 0);
+  if (vec)
+    k_aabb_dense<true><<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R,
+                                                                            q.RB, q.M, mask, reinterpret_cast<float2*>(dist));
+  else
+    k_aabb_dense<false><<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R,
+                                                                             q.RB, q.M, mask, reinterpret_cast<float2*>(dist));
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
@@ -656,7 +662,11 @@ extern "C" int lidf_pcl_aabb_forward(const float* pcl_pos, const float* voxel_bo
   if (N == 0 || V == 0) return LIDF_OK;
   if (!pcl_pos || !voxel_bound || !pcl_bid || !voxel_bid || !mask) return LIDF_ERR_NULL;
   const int64_t NB = (N + AABB_TILE - 1) / AABB_TILE, M = NB * V;
-  k_pcl_dense<<<persistent_blocks(M, 8), AABB_THREADS, 0, (cudaStream_t)stream>>>(pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, NB, M, mask);
+  const bool vec = N % 4 == 0 && ((uintptr_t)mask % 16 == 0) && ((uintptr_t)pcl_pos % 16 == 0) && ((uintptr_t)pcl_bid % 16 == 0);
+  if (vec)
+    k_pcl_dense<true><<<persistent_blocks(M, 8), AABB_THREADS, 0, (cudaStream_t)stream>>>(pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, NB, M, mask);
+  else
+    k_pcl_dense<false><<<persistent_blocks(M, 8), AABB_THREADS, 0, (cudaStream_t)stream>>>(pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, NB, M, mask);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
