@@ -306,3 +306,113 @@ __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __
   if (lane == 0) max_pair_id[ray] = (e > s) ? (int64_t)best_id : P;
   if (lane < 3) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Ray-wise loss statistics on the path's outputs: the torch_scatter calls of LIDF.compute_loss that act on per-pair
+// data keyed by ray (pipeline.py:482-486 scatter_log_softmax cross-entropy, :553-557 scatter_max labels / accuracy) plus
+// the two per-ray position errors (:472 L1, :560-567 masked L2).  One warp per ray over the CSR built by build_csr;
+// per-ray partials are reduced in a fixed order (reproducible), in double precision.
+//   log_softmax[i] = (x_i - max_ray) - log(sum_ray exp(x - max_ray) + 1e-12)          (torch_scatter 2.0.x, eps 1e-12)
+//   pred_label[r]  = first arg-max of pred_prob_end_softmax over the ray's pairs, P for a ray without pairs
+//   gt_label[r]    = first arg-max of pcl_label over the ray's pairs (first pair of the ray when no pair is labelled)
+// ray_part[r] = {sum of -log_softmax over labelled pairs, #labelled pairs, pred_label == gt_label, sum |pred - gt| (3 terms),
+//                ||pred - gt||_2 * mask, mask}  with mask = (sum |gt| != 0)
+// ------------------------------------------------------------------------------------------------
+#define LIDF_LOSS_NSTAT 6
+__global__ void k_ray_loss(const float* __restrict__ logit, const float* __restrict__ soft, const float* __restrict__ label,
+                           const int* __restrict__ ray_start, const int* __restrict__ perm, int64_t P, int64_t R,
+                           const float* __restrict__ pred_pos, const float* __restrict__ gt_pos,
+                           float* __restrict__ log_softmax, int64_t* __restrict__ pred_label, int64_t* __restrict__ gt_label,
+                           float* __restrict__ ray_part) {
+  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int lane = threadIdx.x & 31;
+  if (ray >= R) return;
+  const int s = ray_start[ray], e = ray_start[ray + 1];
+  float m = -INFINITY;
+  for (int i = s + lane; i < e; i += 32) m = fmaxf(m, logit[perm[i]]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+  float sum = 0.f;
+  for (int i = s + lane; i < e; i += 32) sum += expf(logit[perm[i]] - m);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float lognorm = logf(sum + 1e-12f);
+  float ce = 0.f, nlab = 0.f;
+  float pbest = -INFINITY, gbest = -INFINITY;
+  int pid = 0x7fffffff, gid = 0x7fffffff;
+  for (int i = s + lane; i < e; i += 32) {
+    const int id = perm[i];
+    const float l = (logit[id] - m) - lognorm;
+    log_softmax[id] = l;
+    const float lab = label[id];
+    if (lab != 0.f) { ce -= l; nlab += 1.f; }
+    const float sv = soft[id];
+    if (sv > pbest || (sv == pbest && id < pid)) { pbest = sv; pid = id; }
+    if (lab > gbest || (lab == gbest && id < gid)) { gbest = lab; gid = id; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    ce += __shfl_xor_sync(0xffffffffu, ce, o);
+    nlab += __shfl_xor_sync(0xffffffffu, nlab, o);
+    const float ob = __shfl_xor_sync(0xffffffffu, pbest, o); const int oi = __shfl_xor_sync(0xffffffffu, pid, o);
+    if (ob > pbest || (ob == pbest && oi < pid)) { pbest = ob; pid = oi; }
+    const float gb = __shfl_xor_sync(0xffffffffu, gbest, o); const int gi = __shfl_xor_sync(0xffffffffu, gid, o);
+    if (gb > gbest || (gb == gbest && gi < gid)) { gbest = gb; gid = gi; }
+  }
+  if (lane == 0) {
+    const int64_t pl = (e > s) ? (int64_t)pid : P, gl = (e > s) ? (int64_t)gid : P;
+    pred_label[ray] = pl; gt_label[ray] = gl;
+    float* o = ray_part + ray * LIDF_LOSS_NSTAT;
+    o[0] = ce; o[1] = nlab; o[2] = pl == gl ? 1.f : 0.f;
+    float l1 = 0.f, l2 = 0.f, mask = 0.f;
+    if (gt_pos) {
+      float az = 0.f, sq = 0.f;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) {
+        const float g = gt_pos[ray * 3 + k], d = pred_pos[ray * 3 + k] - g;
+        l1 += fabsf(d); sq += d * d; az += fabsf(g);
+      }
+      mask = az != 0.f ? 1.f : 0.f;
+      l2 = sqrtf(sq) * mask;
+    }
+    o[3] = l1; o[4] = l2; o[5] = mask;
+  }
+}
+// fixed-order reduction of ray_part[R][6] -> stats[6] (double): each block sums a contiguous slab of rays (thread-strided
+// partials, shuffle tree), then the last block to finish adds the block partials in block order.
+__global__ void k_ray_loss_reduce(const float* __restrict__ ray_part, int64_t R, double* __restrict__ block_part,
+                                  unsigned* __restrict__ done, double* __restrict__ stats) {
+  __shared__ double sh[8][LIDF_LOSS_NSTAT];
+  __shared__ bool last;
+  const int64_t per = (R + gridDim.x - 1) / gridDim.x, r0 = (int64_t)blockIdx.x * per, r1 = r0 + per < R ? r0 + per : R;
+  double acc[LIDF_LOSS_NSTAT];
+#pragma unroll
+  for (int k = 0; k < LIDF_LOSS_NSTAT; ++k) acc[k] = 0.0;
+  for (int64_t r = r0 + threadIdx.x; r < r1; r += blockDim.x)
+#pragma unroll
+    for (int k = 0; k < LIDF_LOSS_NSTAT; ++k) acc[k] += (double)ray_part[r * LIDF_LOSS_NSTAT + k];
+#pragma unroll
+  for (int k = 0; k < LIDF_LOSS_NSTAT; ++k)
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0)
+#pragma unroll
+    for (int k = 0; k < LIDF_LOSS_NSTAT; ++k) sh[warp][k] = acc[k];
+  __syncthreads();
+  if (threadIdx.x < LIDF_LOSS_NSTAT) {
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += sh[w][threadIdx.x];
+    block_part[(size_t)blockIdx.x * LIDF_LOSS_NSTAT + threadIdx.x] = t;
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) last = atomicAdd(done, 1u) == gridDim.x - 1;
+  __syncthreads();
+  if (last && threadIdx.x < LIDF_LOSS_NSTAT) {
+    double t = 0.0;
+    for (unsigned b = 0; b < gridDim.x; ++b) t += ((volatile double*)block_part)[(size_t)b * LIDF_LOSS_NSTAT + threadIdx.x];
+    stats[threadIdx.x] = t;
+    if (threadIdx.x == 0) *done = 0;
+  }
+}

@@ -233,6 +233,45 @@ extern "C" int lidf_ray_terminate(const float* logit, const int64_t* pair_ray, c
   return LIDF_OK;
 }
 
+#define LIDF_LOSS_BLOCKS 592      // 4 x 148: blocks of the fixed-order reduction
+extern "C" size_t lidf_ray_loss_workspace_bytes(int64_t P, int64_t R) {
+  Bump b{nullptr, 0};
+  carve_csr(b, P, R);
+  b.take<float>((size_t)(R > 0 ? R : 1) * LIDF_LOSS_NSTAT);
+  b.take<double>((size_t)LIDF_LOSS_BLOCKS * LIDF_LOSS_NSTAT);
+  b.take<unsigned>(1);
+  return b.off + 256;
+}
+
+extern "C" int lidf_ray_loss(const float* logit, const float* soft, const int64_t* pair_ray, const float* label, int64_t P,
+                             int64_t R, const float* pred_pos, const float* gt_pos, float* log_softmax, int64_t* pred_label,
+                             int64_t* gt_label, double* stats, void* ws, size_t ws_bytes, lidf_stream_t stream) {
+  if (!pred_label || !gt_label || !stats || !ws) return LIDF_ERR_NULL;
+  if (P > 0 && (!logit || !soft || !pair_ray || !label || !log_softmax)) return LIDF_ERR_NULL;
+  if ((gt_pos != nullptr) != (pred_pos != nullptr)) return LIDF_ERR_ARG;
+  if (P < 0 || R < 0) return LIDF_ERR_ARG;
+  if (P >= INT_MAX || R >= INT_MAX / 32) return LIDF_ERR_UNSUPPORTED;
+  if (ws_bytes < lidf_ray_loss_workspace_bytes(P, R)) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  LIDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * LIDF_LOSS_NSTAT, st));
+  if (R == 0) return LIDF_OK;
+  Bump b{(char*)ws, 0};
+  CsrBufs c = carve_csr(b, P, R);
+  float* ray_part = b.take<float>((size_t)R * LIDF_LOSS_NSTAT);
+  double* block_part = b.take<double>((size_t)LIDF_LOSS_BLOCKS * LIDF_LOSS_NSTAT);
+  unsigned* done = b.take<unsigned>(1);
+  int rc = build_csr(c, pair_ray, P, R, st);
+  if (rc) return rc;
+  LIDF_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned), st));
+  k_ray_loss<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(logit, soft, label, c.ray_start, c.perm, P, R, pred_pos, gt_pos,
+                                                                log_softmax, pred_label, gt_label, ray_part);
+  LIDF_LAUNCH_CHECK();
+  const int nb = (int)(R < LIDF_LOSS_BLOCKS ? R : LIDF_LOSS_BLOCKS);
+  k_ray_loss_reduce<<<nb, 256, 0, st>>>(ray_part, R, block_part, done, stats);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 namespace {
 

@@ -65,7 +65,7 @@ EXPORTED_SYMBOLS = [
     "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
     "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
-    "lidf_query_last_mlp_ms", "lidf_tc_selftest",
+    "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
 ]
 # include/lidf_aabb.h (bound by extensions/ray_aabb/jit.py and extensions/pcl_aabb/jit.py)
 EXPORTED_SYMBOLS_AABB = [
@@ -102,6 +102,11 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_ray_terminate.restype = C.c_int
     lib.lidf_ray_terminate.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64,
                                        C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.lidf_ray_loss_workspace_bytes.restype = C.c_size_t
+    lib.lidf_ray_loss_workspace_bytes.argtypes = [C.c_int64, C.c_int64]
+    lib.lidf_ray_loss.restype = C.c_int
+    lib.lidf_ray_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
+                                  C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.lidf_query_last_mlp_ms.restype = C.c_float
     lib.lidf_tc_selftest.restype = C.c_int
     lib.lidf_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -518,6 +523,38 @@ class _LidfQuery:
         self._raise(rc, "lidf_ray_terminate")
         ws.record_stream(torch.cuda.current_stream(dev))
         return soft, arg, pos
+
+    def ray_loss(self, pred_prob_end, pred_prob_end_softmax, miss_ray_intersect_idx, pcl_label_float, R: int,
+                 pred_pos: Optional[torch.Tensor] = None, gt_pos: Optional[torch.Tensor] = None):
+        """The ray-keyed torch_scatter part of LIDF.compute_loss (pipeline.py:482-486, :553-557) and the per-ray position
+        errors (:472, :560-567) in two kernels.  Returns a dict: log_softmax [P], pred_label / gt_label [R], and 0-dim
+        tensors prob_loss, acc (+ pos_loss, err when gt_pos is given) computed from the device-side sums (no host sync)."""
+        dev = pred_prob_end_softmax.device
+        P = int(miss_ray_intersect_idx.shape[0])
+        logit = pred_prob_end.reshape(-1)
+        lsm = torch.empty(P, dtype=torch.float32, device=dev)
+        pl = torch.empty(R, dtype=torch.int64, device=dev)
+        gl = torch.empty(R, dtype=torch.int64, device=dev)
+        stats = torch.empty(6, dtype=torch.float64, device=dev)
+        nbytes = int(self.lib.lidf_ray_loss_workspace_bytes(P, R))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.lidf_ray_loss(_chk(logit, "pred_prob_end", torch.float32),
+                                        _chk(pred_prob_end_softmax, "pred_prob_end_softmax", torch.float32),
+                                        _chk(miss_ray_intersect_idx, "miss_ray_intersect_idx", torch.int64),
+                                        _chk(pcl_label_float, "pcl_label_float", torch.float32), P, R,
+                                        _chk(pred_pos, "pred_pos", torch.float32, optional=True),
+                                        _chk(gt_pos, "gt_pos", torch.float32, optional=True),
+                                        lsm.data_ptr(), pl.data_ptr(), gl.data_ptr(), stats.data_ptr(), ws.data_ptr(), nbytes,
+                                        C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_ray_loss")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        out = dict(log_softmax=lsm, pred_label=pl, gt_label=gl, stats=stats,
+                   prob_loss=(stats[0] / stats[1]).float(), acc=(stats[2] / max(R, 1)).float())
+        if gt_pos is not None:
+            out["pos_loss"] = (stats[3] / max(3 * R, 1)).float()
+            out["err"] = torch.where(stats[5] > 0, stats[4] / stats[5].clamp_min(1), torch.zeros_like(stats[4])).float()
+        return out
 
 
 lidf_query = _LidfQuery()

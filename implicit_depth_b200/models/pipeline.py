@@ -86,6 +86,16 @@ class LIDFQueryMixin:
                                   data_dict['occ_vox_intersect_idx'].contiguous(), data_dict['miss_ray_intersect_idx'].contiguous())
         data_dict.update({'gt_pos': gt_pos, 'pcl_label': lab.long(), 'pcl_label_float': lab})
 
+    def compute_ray_loss(self, data_dict):
+        """The ray-keyed statistics of ``LIDF.compute_loss`` (reference pipeline.py:472, :482-486, :553-567; shipped setting
+        ``hard_neg: False``) from the path's outputs, forward only (evaluation / logging): returns ``pos_loss``, ``prob_loss``,
+        ``acc``, ``err`` as 0-dim tensors without a host sync, plus ``log_softmax`` / ``pred_label`` / ``gt_label``.  The
+        image-space terms (surface normals, smoothness, depth metrics) stay with the reference code."""
+        return lidf_query.ray_loss(data_dict['pred_prob_end'].contiguous(), data_dict['pred_prob_end_softmax'].contiguous(),
+                                   data_dict['miss_ray_intersect_idx'].contiguous(),
+                                   data_dict['pcl_label_float'].contiguous(), int(data_dict['total_miss_sample_num']),
+                                   data_dict['pred_pos'].contiguous(), data_dict['gt_pos'].float().contiguous())
+
     def get_pred(self, data_dict, exp_type, epoch):
         if self.opt.model.scatter_type != 'Maxpool':
             raise NotImplementedError('Does not support Scatter Type: {}'.format(self.opt.model.scatter_type))

@@ -164,6 +164,20 @@ int lidf_ray_terminate(const float* pred_prob_end, const int64_t* pair_ray, cons
                        float* pred_prob_end_softmax, int64_t* max_pair_id, float* pred_pos,
                        void* workspace, size_t workspace_bytes, lidf_stream_t stream);
 
+/* The torch_scatter calls of LIDF.compute_loss that act on the path's outputs, keyed by ray (pipeline.py:482-486
+ * scatter_log_softmax cross-entropy; :553-557 scatter_max labels and accuracy) plus the per-ray position errors (:472 L1,
+ * :560-567 L2 over rays whose gt_pos is not all-zero).  pcl_label_float [P] holds 0/1 (pipeline.py:308-309).
+ * Outputs: log_softmax [P], pred_label [R], gt_label [R] (int64, P for a ray without pairs), stats [6] (device, double):
+ *   {sum of -log_softmax over labelled pairs, #labelled pairs, #rays with pred_label == gt_label,
+ *    sum |pred_pos - gt_pos| over R*3, sum of masked L2 errors, #masked rays};
+ * prob_loss = stats[0]/stats[1], acc = stats[2]/R, pos_loss = stats[3]/(3R), err = stats[4]/stats[5].
+ * gt_pos / pred_pos may be NULL (stats[3..5] = 0). */
+size_t lidf_ray_loss_workspace_bytes(int64_t P, int64_t R);
+int lidf_ray_loss(const float* pred_prob_end, const float* pred_prob_end_softmax, const int64_t* pair_ray,
+                  const float* pcl_label_float, int64_t P, int64_t R, const float* pred_pos, const float* gt_pos,
+                  float* log_softmax, int64_t* pred_label, int64_t* gt_label, double* stats,
+                  void* workspace, size_t workspace_bytes, lidf_stream_t stream);
+
 /* unit test of the tcgen05 primitives the decoder engine is built from (tcgen05.st operand staging, TMA weight chunks,
  * TS-mode tcgen05.mma with the 3-product bf16 split, tcgen05.ld): D[128,128] = A[128,32] * W[128,32]^T, fp32 device
  * arrays; scratch >= 16 KB device memory.  variant 0 = the layout the engine uses; 1 = LBO/SBO swapped (must be wrong). */

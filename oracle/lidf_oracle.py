@@ -222,6 +222,41 @@ def scatter_softmax(src: torch.Tensor, index: torch.Tensor, eps: float = 1e-12) 
     return rec / (ssum + eps)[index]
 
 
+def scatter_log_softmax(src: torch.Tensor, index: torch.Tensor, eps: float = 1e-12) -> torch.Tensor:
+    """torch_scatter.composite.scatter_log_softmax: (src - segmax) - log(segsum(exp(src - segmax)) + eps)."""
+    if src.shape[0] == 0:
+        return src.clone()
+    mx, _ = scatter_max(src, index)
+    rec = src - mx[index]
+    ssum = torch.zeros_like(mx).index_add_(0, index, rec.exp())
+    return rec - (ssum + eps).log()[index]
+
+
+def ray_loss_stats(pred_prob_end: torch.Tensor, pred_prob_end_softmax: torch.Tensor, ray: torch.Tensor,
+                   pcl_label: torch.Tensor, R: int, pred_pos: Optional[torch.Tensor] = None,
+                   gt_pos: Optional[torch.Tensor] = None) -> Dict[str, torch.Tensor]:
+    """The ray-keyed part of LIDF.compute_loss (hard_neg False, the shipped setting):
+      pipeline.py:472      pos_loss = L1Loss()(pred_pos, gt_pos)
+      pipeline.py:482-486  prob_loss = mean(-scatter_log_softmax(pred_prob_end[:,0], ray)[nonzero(pcl_label)])
+      pipeline.py:553-557  acc = mean(scatter_max(softmax, ray)[1] == scatter_max(pcl_label, ray)[1])
+      pipeline.py:560-567  err = sum(||pred_pos - gt_pos||_2 * zero_mask) / sum(zero_mask), zero_mask = (sum|gt_pos| != 0)"""
+    logit = pred_prob_end.reshape(-1)
+    lsm = scatter_log_softmax(logit, ray)
+    idx = torch.nonzero(pcl_label, as_tuple=False).reshape(-1)
+    out = dict(log_softmax=lsm, prob_loss=torch.mean(-1 * lsm[idx]))
+    _, out["pred_label"] = scatter_max(pred_prob_end_softmax, ray, dim_size=R)
+    _, out["gt_label"] = scatter_max(pcl_label.to(pred_prob_end_softmax.dtype), ray, dim_size=R)
+    out["acc"] = torch.sum(torch.eq(out["pred_label"], out["gt_label"]).float()) / max(R, 1)
+    if gt_pos is not None:
+        out["pos_loss"] = F.l1_loss(pred_pos, gt_pos)
+        zero_mask = torch.sum(gt_pos.abs(), dim=-1)
+        zero_mask[zero_mask != 0] = 1.
+        n = torch.sum(zero_mask)
+        out["err"] = torch.zeros(()) if float(n) == 0 else \
+            torch.sum(torch.sqrt(torch.sum((pred_pos - gt_pos) ** 2, -1)) * zero_mask) / n
+    return out
+
+
 # --------------------------------------------------------------------------- #
 # pipeline.py : LIDF.get_embedding + LIDF.get_pred
 # --------------------------------------------------------------------------- #

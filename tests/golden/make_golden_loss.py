@@ -1,0 +1,59 @@
+"""Golden vectors for the ray-wise loss statistics (lidf_ray_loss), produced by the REFERENCE's own compute_loss.
+
+    python tests/golden/make_golden_loss.py        # needs /root/reference; writes tests/golden/loss_*.npz
+
+Runs ``LIDF.compute_loss(data_dict, 'train', epoch)`` (reference src/models/pipeline.py:468-650, unmodified; torch_scatter
+and matplotlib stubbed exactly as in make_golden.py) on the outputs stored in an existing fixture plus seeded
+``gt_pos`` / ``pcl_label`` / ``xyz_flat``, and stores the four scalars this repo reproduces natively -- pos_loss, prob_loss,
+acc, err -- together with the scatter_log_softmax / scatter_max intermediates (computed with the same stub calls).
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+sys.path.insert(0, os.path.dirname(os.path.dirname(HERE)))
+
+import make_golden as MG  # noqa: E402
+
+
+def run(src_name, out_name, seed, zero_frac=0.1, label_frac=0.2):
+    z = np.load(os.path.join(HERE, src_name + ".npz"))
+    opt, lidf, _ = MG.build_reference({})
+    import torch_scatter as ts                                   # the stub installed by build_reference
+    g = torch.Generator().manual_seed(seed)
+    B, H, W = int(z["meta_B"]), int(z["meta_H"]), int(z["meta_W"])
+    ray = torch.from_numpy(z["miss_ray_intersect_idx"]).long()
+    P, R = ray.shape[0], z["miss_ray_dir"].shape[0]
+    pred_pos = torch.from_numpy(z["ref.pred_pos"])
+    gt_pos = pred_pos + 0.05 * torch.randn(R, 3, generator=g)
+    gt_pos[torch.rand(R, generator=g) < zero_frac] = 0.0          # zero-depth points are excluded from `err`
+    label = (torch.rand(P, generator=g) < label_frac).long()
+    img_ind = torch.from_numpy(z["miss_img_ind"]).long()
+    dd = dict(bs=B, h=H, w=W, pred_pos=pred_pos, gt_pos=gt_pos,
+              pred_prob_end=torch.from_numpy(z["ref.pred_prob_end"]),
+              pred_prob_end_softmax=torch.from_numpy(z["ref.pred_prob_end_softmax"]),
+              miss_ray_intersect_idx=ray, pcl_label=label, total_miss_sample_num=R,
+              miss_bid=torch.from_numpy(z["miss_bid"]).long(), miss_flat_img_id=img_ind[:, 1] * W + img_ind[:, 0],
+              xyz_flat=torch.randn(B, H * W, 3, generator=g))
+    with torch.no_grad():
+        loss = lidf.compute_loss(dd, "train", 0)                 # reference code, unmodified
+        lsm = ts.scatter_log_softmax(dd["pred_prob_end"][:, 0], ray)
+        _, pred_label = ts.scatter_max(dd["pred_prob_end_softmax"], ray, dim_size=R)
+        _, gt_label = ts.scatter_max(label, ray, dim_size=R)
+    out = os.path.join(HERE, out_name + ".npz")
+    np.savez_compressed(out, pred_prob_end=z["ref.pred_prob_end"], pred_prob_end_softmax=z["ref.pred_prob_end_softmax"],
+                        miss_ray_intersect_idx=z["miss_ray_intersect_idx"], pcl_label=label.numpy().astype(np.int32),
+                        pred_pos=pred_pos.numpy(), gt_pos=gt_pos.numpy(), R=R,
+                        ref_log_softmax=lsm.numpy(), ref_pred_label=pred_label.numpy(), ref_gt_label=gt_label.numpy(),
+                        **{"ref_" + k: np.float64(float(loss[k])) for k in ("pos_loss", "prob_loss", "acc", "err")})
+    print(out_name, {k: float(loss[k]) for k in ("pos_loss", "prob_loss", "acc", "err")}, "P", P, "R", R,
+          "empty rays", int((pred_label == P).sum()))
+
+
+if __name__ == "__main__":
+    run("ief_ragged_2x24x32", "loss_ief_ragged_2x24x32", 11)
+    run("c1_imnet_64x64x16", "loss_c1_imnet_64x64x16", 12, zero_frac=0.0, label_frac=0.05)

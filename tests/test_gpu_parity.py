@@ -456,3 +456,44 @@ def test_forward_host_falls_back_when_slices_are_not_self_contained():
     got, _, _ = lq.forward_host(host, off, prob, "cuda", part_size=d["part_size"])
     for k in lq.OUTPUT_KEYS:
         assert torch.equal(got[k], want[k].cpu()), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# ray-wise loss statistics (the torch_scatter part of LIDF.compute_loss)
+@pytest.mark.parametrize("name", ["loss_ief_ragged_2x24x32", "loss_c1_imnet_64x64x16"])
+def test_ray_loss_vs_reference_compute_loss(name):
+    from test_oracle import load_loss
+    t, sc, R = load_loss(name)
+    out = _lq().ray_loss(t["pred_prob_end"].cuda(), t["pred_prob_end_softmax"].cuda(), t["miss_ray_intersect_idx"].cuda(),
+                         t["pcl_label"].float().cuda(), R, t["pred_pos"].cuda(), t["gt_pos"].cuda())
+    assert torch.equal(out["pred_label"].cpu(), t["ref_pred_label"]) and torch.equal(out["gt_label"].cpu(), t["ref_gt_label"])
+    assert rel_err(out["log_softmax"].cpu(), t["ref_log_softmax"]) < 2e-6
+    for k in ("pos_loss", "prob_loss", "acc", "err"):
+        assert abs(float(out[k]) - sc["ref_" + k]) <= 5e-6 * max(1.0, abs(sc["ref_" + k])), (k, float(out[k]), sc["ref_" + k])
+    # integer statistics are exact
+    st = out["stats"].cpu()
+    assert float(st[1]) == float((t["pcl_label"] != 0).sum()) and float(st[2]) == float((t["ref_pred_label"] == t["ref_gt_label"]).sum())
+
+
+def test_ray_loss_edge_cases_vs_oracle():
+    lq = _lq()
+    g = torch.Generator().manual_seed(5)
+    # no pairs at all; rays without pairs; no labelled pair; no gt_pos
+    for P, R in [(0, 7), (1, 1), (300, 50), (5000, 4000)]:
+        ray = torch.randint(0, R, (P,), generator=g)
+        logit = torch.randn(P, 1, generator=g) * 3
+        soft = O.scatter_softmax(logit[:, 0], ray) if P else torch.zeros(0)
+        lab = (torch.rand(P, generator=g) < 0.3).long()
+        if P == 300:
+            lab.zero_()
+        want = O.ray_loss_stats(logit, soft, ray, lab, R)
+        got = lq.ray_loss(logit.cuda(), soft.cuda(), ray.cuda(), lab.float().cuda(), R)
+        assert torch.equal(got["pred_label"].cpu(), want["pred_label"]) and torch.equal(got["gt_label"].cpu(), want["gt_label"])
+        assert "pos_loss" not in got
+        if P:
+            assert rel_err(got["log_softmax"].cpu(), want["log_softmax"]) < 2e-6
+        assert abs(float(got["acc"]) - float(want["acc"])) < 1e-6
+        if int(lab.sum()) > 0:
+            assert abs(float(got["prob_loss"]) - float(want["prob_loss"])) < 5e-6 * max(1.0, abs(float(want["prob_loss"])))
+        else:
+            assert torch.isnan(got["prob_loss"]) and (P == 0 or torch.isnan(want["prob_loss"]))   # mean of an empty set

@@ -96,3 +96,29 @@ def test_refine_tail_matches_reference():
     out = O.refine_decoder_tail(ref["pred_pos"], d["miss_ray_dir"], center, extra["refine.occ_voxel_feat"][evid],
                                 rgb.reshape(rgb.shape[0], -1), rcfg, rdec)
     assert rel_err(out, ref["pred_pos_refine"]) < TOL
+
+
+LOSS_CASES = ["loss_ief_ragged_2x24x32", "loss_c1_imnet_64x64x16"]
+
+
+def load_loss(name):
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim > 0}
+    t["miss_ray_intersect_idx"] = t["miss_ray_intersect_idx"].long(); t["pcl_label"] = t["pcl_label"].long()
+    sc = {k: float(z[k]) for k in ("ref_pos_loss", "ref_prob_loss", "ref_acc", "ref_err")}
+    return t, sc, int(z["R"])
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_ray_loss_oracle_matches_reference_compute_loss(name):
+    """pos_loss / prob_loss / acc / err from the reference's own compute_loss (tests/golden/make_golden_loss.py)."""
+    t, sc, R = load_loss(name)
+    out = O.ray_loss_stats(t["pred_prob_end"], t["pred_prob_end_softmax"], t["miss_ray_intersect_idx"], t["pcl_label"], R,
+                           t["pred_pos"], t["gt_pos"])
+    assert torch.equal(out["pred_label"], t["ref_pred_label"]) and torch.equal(out["gt_label"], t["ref_gt_label"])
+    assert rel_err(out["log_softmax"], t["ref_log_softmax"]) < 1e-6
+    for k in ("pos_loss", "prob_loss", "acc", "err"):
+        assert abs(float(out[k]) - sc["ref_" + k]) <= 2e-6 * max(1.0, abs(sc["ref_" + k])), k
