@@ -250,23 +250,44 @@ def main():
     value = P * world / (ms_per_step * 1e-3)
 
     # ---- e2e: the same call with pinned HOST buffers, H2D + D2H inside the timed region ----------------------
+    # Steps are issued back to back through forward_host_async (two sets of pinned output buffers): every step copies its
+    # inputs host -> device and all six outputs device -> host; the copies of neighbouring steps overlap the decoder kernel.
+    # `sync_ms_per_step` is one isolated, fully synchronous forward_host call (pipeline fill + drain exposed).
     e2e = None
     if not args.no_e2e:
         host = {k: d[k].cpu().pin_memory() for k in lidf_query.INPUT_KEYS + ("occ_vox_bid",)}   # occ_vox_bid stays on the host
-        out_host, h2d, d2h = lidf_query.forward_host(host, off, prob, dev, **kw)         # warm-up, allocates pinned outputs
-        lidf_query.forward_host(host, off, prob, dev, out_host=out_host, **kw)
+        out_a, h2d, d2h = lidf_query.forward_host(host, off, prob, dev, **kw)                # warm-up, allocates pinned outputs
+        out_b = {k: torch.empty_like(v).pin_memory() for k, v in out_a.items()}
+        bufs = (out_a, out_b)
+        lidf_query.forward_host(host, off, prob, dev, out_host=out_b, **kw)
         barrier()
-        n_e2e = max(1, min(args.steps, 3))
         t0 = time.perf_counter()
-        for _ in range(n_e2e):
-            lidf_query.forward_host(host, off, prob, dev, out_host=out_host, **kw)
-        torch.cuda.synchronize()
-        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], device=dev)
+        lidf_query.forward_host(host, off, prob, dev, out_host=out_a, **kw)
+        sync_ms = (time.perf_counter() - t0) * 1e3
+        barrier()
+        n_e2e = max(2, min(args.steps, 5))
+
+        def stream_steps(n):
+            pending = None
+            for i in range(n):
+                call = lidf_query.forward_host_async(host, off, prob, dev, out_host=bufs[i & 1], **kw)
+                if pending is not None:
+                    pending.wait()                                                    # step i-1's outputs are on the host
+                pending = call
+            pending.wait()
+            torch.cuda.synchronize()
+        stream_steps(3)                                  # warm-up: two steps in flight double the device working set
+        barrier()
+        t0 = time.perf_counter()
+        stream_steps(n_e2e)
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e, sync_ms], device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = dict(value=P * world / float(te), unit="points/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
-                   ms_per_step=float(te) * 1e3, host_numa_node=numa_node)
-        del host, out_host
+        e2e = dict(value=P * world / float(te[0]), unit="points/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=d2h,
+                   ms_per_step=float(te[0]) * 1e3, steps=n_e2e, mode="steps issued back to back (forward_host_async), "
+                   "every step's inputs H2D and all outputs D2H inside the timed region",
+                   sync_ms_per_step=float(te[1]), host_numa_node=numa_node)
+        del host, out_a, out_b, bufs
 
     if rank != 0:
         if world > 1:

@@ -218,6 +218,38 @@ def _decoder_struct(sd: Dict[str, torch.Tensor], n_iter: int, use_sigmoid: bool,
     return d
 
 
+class _HostCall:
+    """One in-flight ``forward_host_async`` batch."""
+
+    def __init__(self, lq, host, offset_dec, prob_dec, dev, out_host, kw, h2d, d2h):
+        self.lq, self.host, self.offset_dec, self.prob_dec, self.dev = lq, host, offset_dec, prob_dec, dev
+        self.out_host, self.kw, self.h2d, self.d2h = out_host, kw, h2d, d2h
+        self.pending = None
+        self.finished = False
+
+    def run_monolithic(self):
+        lq, dev = self.lq, self.dev
+        ins = [self.host[k].to(dev, non_blocking=True) for k in lq.INPUT_KEYS]
+        out = lq.forward(*ins, self.offset_dec, self.prob_dec, **self.kw)
+        for k in lq.OUTPUT_KEYS:
+            self.out_host[k].copy_(out[k], non_blocking=True)
+        done = torch.cuda.Event(); done.record(torch.cuda.current_stream(dev))
+        self.pending = (done, None, (ins, out), None)
+
+    def wait(self):
+        """Block until the outputs are in ``out_host``.  If a pipelined batch turns out not to be image-contiguous
+        (device-side range check), it is redone as one monolithic call."""
+        if not self.finished:
+            done, bad_host, _live, _bad = self.pending
+            done.synchronize()
+            if bad_host is not None and int(bad_host[0]) != 0:
+                self.run_monolithic()
+                self.pending[0].synchronize()
+            self.pending = None
+            self.finished = True
+        return self.out_host, self.h2d, self.d2h
+
+
 class _LidfQuery:
     """Object with a ``forward`` like the reference's pybind modules (ray_aabb.forward, pcl_aabb.forward)."""
 
@@ -284,6 +316,15 @@ class _LidfQuery:
         the decoder kernels of group i.  Needs ``host['occ_vox_bid']`` (the reference's data_dict key) next to
         INPUT_KEYS to find the per-image slices; without it, or when the arrays are not image-contiguous, the whole
         batch goes through one copy-in / compute / copy-out sequence."""
+        return self.forward_host_async(host, offset_dec, prob_dec, device, out_host=out_host, pipeline=pipeline,
+                                       min_chunk_pairs=min_chunk_pairs, **kw).wait()
+
+    def forward_host_async(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, out_host=None,
+                           pipeline: bool = True, min_chunk_pairs: int = 1 << 22, **kw) -> "_HostCall":
+        """``forward_host`` without the final synchronise: enqueues the whole batch and returns a handle whose ``wait()``
+        gives (out_host, h2d_bytes, d2h_bytes).  Back-to-back batches (serving) keep the GPU busy across batch boundaries:
+        the H2D of batch k+1 runs under the tail of batch k, its D2H drains under the head of batch k+2.  Give every
+        in-flight batch its own ``out_host`` buffers."""
         dev = torch.device(device)
         B = int(host["full_rgb_feat"].shape[0])
         P = int(host["occ_vox_intersect_idx"].shape[0]); R = int(host["miss_ray_dir"].shape[0])
@@ -304,18 +345,16 @@ class _LidfQuery:
                             max_pair_id=torch.empty(R, dtype=torch.int64, pin_memory=True),
                             pred_pos=torch.empty(R, 3, **f32))
         d2h = sum(out_host[k].numel() * out_host[k].element_size() for k in self.OUTPUT_KEYS)
-        if len(groups) > 1 and self._forward_host_pipelined(host, offset_dec, prob_dec, dev, out_host, splits, groups, kw):
-            return out_host, h2d, d2h
-        ins = [host[k].to(dev, non_blocking=True) for k in self.INPUT_KEYS]
-        out = self.forward(*ins, offset_dec, prob_dec, **kw)
-        for k in self.OUTPUT_KEYS:
-            out_host[k].copy_(out[k], non_blocking=True)
-        torch.cuda.current_stream(dev).synchronize()
-        return out_host, h2d, d2h
+        call = _HostCall(self, host, offset_dec, prob_dec, dev, out_host, kw, h2d, d2h)
+        if len(groups) > 1:
+            self._enqueue_host_pipeline(call, splits, groups)
+        else:
+            call.run_monolithic()
+        return call
 
-    def _forward_host_pipelined(self, host, offset_dec, prob_dec, dev, out_host, splits, groups, kw) -> bool:
-        """Three-stage pipeline over image groups.  Returns False (nothing usable written) when a group turns out not
-        to be self-contained, i.e. some pair of its slice references a ray or voxel outside the group."""
+    def _enqueue_host_pipeline(self, call: "_HostCall", splits, groups) -> None:
+        """Three-stage pipeline over image groups; nothing here waits on the host."""
+        host, dev, out_host, kw = call.host, call.dev, call.out_host, call.kw
         P = int(host["occ_vox_intersect_idx"].shape[0])
         if getattr(self, "_host_streams", None) is None or self._host_streams[0].device != dev:
             self._host_streams = tuple(torch.cuda.Stream(dev) for _ in range(3))
@@ -324,7 +363,7 @@ class _LidfQuery:
         for s in (s_in, s_cmp, s_out):
             s.wait_stream(cur)
         bad = torch.zeros(1, dtype=torch.int64, device=dev)
-        live = []                                           # keeps every staged tensor alive until the final sync
+        live = []                                           # keeps every staged tensor alive until wait()
         for (b0, b1) in groups:
             r0, r1 = splits["rays"][b0], splits["rays"][b1]
             v0, v1 = splits["voxels"][b0], splits["voxels"][b1]
@@ -351,7 +390,7 @@ class _LidfQuery:
                     lo_b, hi_b = torch.aminmax(mb)
                     bad += ((lo_b < 0) | (hi_b >= b1 - b0)).to(torch.int64)
                     mb.clamp_(0, b1 - b0 - 1)
-                out = self.forward(*[ins[k] for k in self.INPUT_KEYS], offset_dec, prob_dec, **kw)
+                out = self.forward(*[ins[k] for k in self.INPUT_KEYS], call.offset_dec, call.prob_dec, **kw)
                 mp = out["max_pair_id"]                     # local pair ids -> ids in the whole list; empty ray -> P
                 out["max_pair_id"] = torch.where(mp == p1 - p0, P, mp + p0)
                 ev_cmp = torch.cuda.Event(); ev_cmp.record(s_cmp)
@@ -362,12 +401,11 @@ class _LidfQuery:
                 out_host["max_pair_id"][r0:r1].copy_(out["max_pair_id"], non_blocking=True)
                 out_host["pred_pos"][r0:r1].copy_(out["pred_pos"], non_blocking=True)
             live.append((ins, out))
-        cur.wait_stream(s_cmp); cur.wait_stream(s_out)
-        for s in (s_in, s_cmp, s_out):
-            s.synchronize()
-        ok = int(bad.item()) == 0
-        del live
-        return ok
+        with torch.cuda.stream(s_out):
+            bad_host = torch.empty(1, dtype=torch.int64, pin_memory=True)
+            bad_host.copy_(bad, non_blocking=True)
+            done = torch.cuda.Event(); done.record(s_out)
+        call.pending = (done, bad_host, live, bad)
 
     # ------------------------------------------------------------------ fused get_embedding + get_pred
     def forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,

@@ -497,3 +497,27 @@ def test_ray_loss_edge_cases_vs_oracle():
             assert abs(float(got["prob_loss"]) - float(want["prob_loss"])) < 5e-6 * max(1.0, abs(float(want["prob_loss"])))
         else:
             assert torch.isnan(got["prob_loss"]) and (P == 0 or torch.isnan(want["prob_loss"]))   # mean of an empty set
+
+
+def test_forward_host_async_back_to_back_batches():
+    """Two different batches in flight at once (serving pattern): each lands in its own pinned buffers, bit-identical to
+    the device-resident call; a third call reuses the first buffers after its wait()."""
+    from implicit_depth_b200.synthetic import make_inputs
+    lq = _lq()
+    g = torch.Generator().manual_seed(52)
+    off = _cuda(O.init_decoder("IEF", 385, mode="trained", generator=g))
+    prob = _cuda(O.init_decoder("IMNET", 385, mode="trained", generator=g))
+    batches, wants = [], []
+    for seed in (71, 72, 73):
+        d = make_inputs(3, 18, 22, 5, V_img=20, seed=seed, ragged=seed == 72)
+        dc = _cuda(d)
+        wants.append({k: v.cpu() for k, v in lq.forward(*[dc[k] for k in lq.INPUT_KEYS], off, prob, part_size=d["part_size"]).items()})
+        batches.append(({k: d[k].pin_memory() for k in lq.INPUT_KEYS + ("occ_vox_bid",)}, d["part_size"]))
+    calls = [lq.forward_host_async(h, off, prob, "cuda", part_size=ps, min_chunk_pairs=1) for h, ps in batches[:2]]
+    outs = [c.wait()[0] for c in calls]
+    c3 = lq.forward_host_async(batches[2][0], off, prob, "cuda", part_size=batches[2][1], min_chunk_pairs=1)
+    outs.append(c3.wait()[0])
+    assert c3.wait()[0] is outs[2]                                 # wait() is idempotent
+    for got, want in zip(outs, wants):
+        for k in lq.OUTPUT_KEYS:
+            assert torch.equal(got[k], want[k]), k
