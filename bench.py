@@ -54,8 +54,9 @@ def load_peaks():
     if os.path.exists(path):
         with open(path) as f:
             pk = json.load(f)
-        return dict(bf16_tflops=pk["bf16_tflops"], bf16_tflops_sustained=pk["bf16_tflops_sustained"],
-                    hbm_gbs=pk["hbm_gbs"], source="measured (MEASURED_PEAKS.json)")
+        burst = float(pk.get("bf16_tflops", 1590.0))
+        return dict(bf16_tflops=burst, bf16_tflops_sustained=float(pk.get("bf16_tflops_sustained", burst)),
+                    hbm_gbs=float(pk.get("hbm_gbs", 6650.0)), source="measured (MEASURED_PEAKS.json)")
     return dict(bf16_tflops=1590.0, bf16_tflops_sustained=1400.0, hbm_gbs=6650.0, source="fallback (B200_PROFILING.md)")
 
 
