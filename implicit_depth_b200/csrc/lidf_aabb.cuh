@@ -300,3 +300,71 @@ __global__ void __launch_bounds__(AABB_THREADS) k_pcl_end_voxel(const float* __r
   }
   if (act && cur != cur0) end_voxel_id[n] = cur;
 }
+
+// ------------------------------------------------------------------------------------------------
+// Voxelisation of the valid points: batch_get_occupied_idx (src/utils/point_utils.py:12-76, overlap = False) +
+// get_occ_vox_bound (src/models/pipeline.py:162-201).  The reference concatenates (image id, cell) rows and calls
+// torch.unique(dim=0) -- a sort of up to 10^4 x B rows.  The grid has only nx*ny*nz (9^3) cells per image, so the sorted
+// unique list is an occupancy bitmap + a prefix sum: mark -> scan -> fill, no sort.  Row order of torch.unique is
+// lexicographic in (image, cx, cy, cz) = ascending flat cell index.  fp32 operations are the reference's, one by one
+// (__f*_rn keeps nvcc from contracting the multiply-adds torch performs as two roundings).
+// ------------------------------------------------------------------------------------------------
+struct VoxGrid { float xmin[3]; float crop, half_crop; int n[3]; int B; };
+
+__device__ __forceinline__ bool vox_locate(const float* __restrict__ xyz, int64_t i, int bid, const VoxGrid& g, float (&v)[3],
+                                           int (&c)[3]) {
+  bool ok = bid >= 0 && bid < g.B;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    v[k] = __fsub_rn(xyz[i * 3 + k], g.xmin[k]);                       // point_utils.py:23
+    const float q = floorf(__fdiv_rn(v[k], g.crop));                   // :43
+    ok = ok && q >= 0.f && q < (float)g.n[k];                          // :59-61 (also rejects NaN)
+    c[k] = ok ? (int)q : 0;
+  }
+  return ok;
+}
+
+__global__ void k_vox_mark(const float* __restrict__ xyz, const int64_t* __restrict__ bid, int64_t Np, VoxGrid g,
+                           int* __restrict__ cell_flag, int* __restrict__ inside) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np) return;
+  float v[3]; int c[3];
+  const int b = (int)bid[i];
+  const bool ok = vox_locate(xyz, i, b, g, v, c);
+  inside[i] = ok ? 1 : 0;
+  if (ok) cell_flag[((int64_t)b * g.n[0] + c[0]) * g.n[1] * g.n[2] + c[1] * g.n[2] + c[2]] = 1;   // benign same-value race
+}
+
+__global__ void k_vox_fill_voxels(const int* __restrict__ cell_flag, const int* __restrict__ cell_rank, int64_t ncell_total,
+                                  VoxGrid g, int64_t* __restrict__ occ, float* __restrict__ bound) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (w >= ncell_total || !cell_flag[w]) return;
+  const int64_t j = cell_rank[w];
+  const int per = g.n[0] * g.n[1] * g.n[2];
+  const int b = (int)(w / per), r = (int)(w - (int64_t)b * per);
+  const int c[3] = {r / (g.n[1] * g.n[2]), (r / g.n[2]) % g.n[1], r % g.n[2]};
+  occ[j * 4 + 0] = b;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    occ[j * 4 + 1 + k] = c[k];
+    const float lo = __fadd_rn(g.xmin[k], __fmul_rn((float)c[k], g.crop));      // pipeline.py:186
+    bound[j * 6 + k] = lo;
+    bound[j * 6 + 3 + k] = __fadd_rn(lo, g.crop);                                 // :187
+  }
+}
+
+__global__ void k_vox_fill_points(const float* __restrict__ xyz, const int64_t* __restrict__ bid, int64_t Np, VoxGrid g,
+                                  const int* __restrict__ inside, const int* __restrict__ pt_rank, const int* __restrict__ cell_rank,
+                                  int64_t* __restrict__ revidx, int64_t* __restrict__ pid, float* __restrict__ rel) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= Np || !inside[i]) return;
+  float v[3]; int c[3];
+  const int b = (int)bid[i];
+  vox_locate(xyz, i, b, g, v, c);
+  const int64_t j = pt_rank[i];
+  pid[j] = i;                                                                    // point_utils.py:66
+  revidx[j] = cell_rank[((int64_t)b * g.n[0] + c[0]) * g.n[1] * g.n[2] + c[1] * g.n[2] + c[2]];   // :73 inverse index
+#pragma unroll
+  for (int k = 0; k < 3; ++k)                                                    // :50-51 centre, relative coordinate
+    rel[j * 3 + k] = __fsub_rn(v[k], __fadd_rn(__fmul_rn((float)c[k], g.crop), g.half_crop));
+}

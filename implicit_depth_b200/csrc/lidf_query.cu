@@ -735,3 +735,92 @@ extern "C" int lidf_pcl_aabb_end_voxel(const float* pcl_pos, const float* voxel_
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
+
+// ---- voxelisation ------------------------------------------------------------------------------------------------------
+namespace {
+struct VoxPlan { int64_t ncell; int nb_c, nb_p; int* cell_flag; int* cell_rank; int* inside; int* pt_rank; int* bs_c; int* bs_p; size_t bytes; };
+int plan_vox(int64_t Np, int B, int nx, int ny, int nz, VoxPlan* q, char* base) {
+  if (Np < 0 || B <= 0 || nx <= 0 || ny <= 0 || nz <= 0) return LIDF_ERR_ARG;
+  q->ncell = (int64_t)B * nx * ny * nz;
+  if (q->ncell >= INT_MAX - 2 || Np >= INT_MAX - 2) return LIDF_ERR_UNSUPPORTED;
+  const int64_t per = LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS;
+  q->nb_c = (int)((q->ncell + 1 + per - 1) / per);
+  q->nb_p = (int)((Np + 1 + per - 1) / per);
+  Bump b{base, 0};
+  q->cell_flag = b.take<int>((size_t)q->ncell + 1);
+  q->cell_rank = b.take<int>((size_t)q->ncell + 1);
+  q->inside = b.take<int>((size_t)Np + 1);
+  q->pt_rank = b.take<int>((size_t)Np + 1);
+  q->bs_c = b.take<int>((size_t)q->nb_c);
+  q->bs_p = b.take<int>((size_t)q->nb_p);
+  q->bytes = b.off + 256;
+  return LIDF_OK;
+}
+VoxGrid make_grid(int B, float x0, float x1, float x2, float part, float half_part, int nx, int ny, int nz) {
+  VoxGrid g;
+  g.xmin[0] = x0; g.xmin[1] = x1; g.xmin[2] = x2; g.crop = part; g.half_crop = half_part;
+  g.n[0] = nx; g.n[1] = ny; g.n[2] = nz; g.B = B;
+  return g;
+}
+int scan_ints(const int* in, int64_t n, int* out, int* block_sums, int nb, cudaStream_t st) {
+  k_scan_partial<<<nb, LIDF_SCAN_BLOCK, 0, st>>>(in, n, out, block_sums);
+  LIDF_LAUNCH_CHECK();
+  k_scan_blocksums<<<1, 1024, 0, st>>>(block_sums, nb);
+  LIDF_LAUNCH_CHECK();
+  k_scan_add<<<nb, LIDF_SCAN_BLOCK, 0, st>>>(out, n, block_sums, nullptr);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_voxelize_workspace_bytes(int64_t Np, int32_t B, int32_t nx, int32_t ny, int32_t nz) {
+  VoxPlan q;
+  if (plan_vox(Np, B, nx, ny, nz, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_voxelize_count(const float* xyz, const int64_t* bid, int64_t Np, int32_t B, float x0, float x1, float x2,
+                                   float part, float half_part, int32_t nx, int32_t ny, int32_t nz, void* ws, size_t ws_bytes,
+                                   int64_t* n_vox_host, int64_t* n_inside_host, lidf_stream_t stream) {
+  if (!n_vox_host || !n_inside_host) return LIDF_ERR_NULL;
+  *n_vox_host = 0; *n_inside_host = 0;
+  VoxPlan q;
+  int rc = plan_vox(Np, B, nx, ny, nz, &q, (char*)ws);
+  if (rc) return rc;
+  if (!(part > 0.f)) return LIDF_ERR_ARG;
+  if (Np == 0) return LIDF_OK;
+  if (!xyz || !bid || !ws) return LIDF_ERR_NULL;
+  if (ws_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  const VoxGrid g = make_grid(B, x0, x1, x2, part, half_part, nx, ny, nz);
+  LIDF_CUDA(cudaMemsetAsync(q.cell_flag, 0, sizeof(int) * (size_t)(q.ncell + 1), st));
+  LIDF_CUDA(cudaMemsetAsync(q.inside + Np, 0, sizeof(int), st));
+  k_vox_mark<<<(unsigned)((Np + 255) / 256), 256, 0, st>>>(xyz, bid, Np, g, q.cell_flag, q.inside);
+  LIDF_LAUNCH_CHECK();
+  if ((rc = scan_ints(q.cell_flag, q.ncell + 1, q.cell_rank, q.bs_c, q.nb_c, st))) return rc;
+  if ((rc = scan_ints(q.inside, Np + 1, q.pt_rank, q.bs_p, q.nb_p, st))) return rc;
+  int tot[2] = {0, 0};
+  LIDF_CUDA(cudaMemcpyAsync(&tot[0], q.cell_rank + q.ncell, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LIDF_CUDA(cudaMemcpyAsync(&tot[1], q.pt_rank + Np, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LIDF_CUDA(cudaStreamSynchronize(st));
+  *n_vox_host = tot[0]; *n_inside_host = tot[1];
+  return LIDF_OK;
+}
+
+extern "C" int lidf_voxelize_fill(const float* xyz, const int64_t* bid, int64_t Np, int32_t B, float x0, float x1, float x2,
+                                  float part, float half_part, int32_t nx, int32_t ny, int32_t nz, void* ws, size_t ws_bytes,
+                                  int64_t* occ, float* bound, int64_t* revidx, int64_t* pid, float* rel, lidf_stream_t stream) {
+  VoxPlan q;
+  int rc = plan_vox(Np, B, nx, ny, nz, &q, (char*)ws);
+  if (rc) return rc;
+  if (Np == 0) return LIDF_OK;
+  if (!xyz || !bid || !ws || !occ || !bound || !revidx || !pid || !rel) return LIDF_ERR_NULL;
+  if (ws_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  const VoxGrid g = make_grid(B, x0, x1, x2, part, half_part, nx, ny, nz);
+  k_vox_fill_voxels<<<(unsigned)((q.ncell + 255) / 256), 256, 0, st>>>(q.cell_flag, q.cell_rank, q.ncell, g, occ, bound);
+  LIDF_LAUNCH_CHECK();
+  k_vox_fill_points<<<(unsigned)((Np + 255) / 256), 256, 0, st>>>(xyz, bid, Np, g, q.inside, q.pt_rank, q.cell_rank, revidx, pid, rel);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}

@@ -71,6 +71,7 @@ EXPORTED_SYMBOLS = [
 EXPORTED_SYMBOLS_AABB = [
     "lidf_ray_aabb_workspace_bytes", "lidf_ray_aabb_forward", "lidf_ray_aabb_pairs_count", "lidf_ray_aabb_pairs_fill",
     "lidf_pcl_aabb_forward", "lidf_pcl_aabb_pair_label", "lidf_pcl_aabb_end_voxel",
+    "lidf_voxelize_workspace_bytes", "lidf_voxelize_count", "lidf_voxelize_fill",
 ]
 
 
@@ -127,6 +128,14 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_pcl_aabb_pair_label.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp, i64, vp, vp]
     lib.lidf_pcl_aabb_end_voxel.restype = C.c_int
     lib.lidf_pcl_aabb_end_voxel.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
+    i32, f32 = C.c_int32, C.c_float
+    vox_common = [vp, vp, i64, i32, f32, f32, f32, f32, f32, i32, i32, i32, vp, sz]
+    lib.lidf_voxelize_workspace_bytes.restype = sz
+    lib.lidf_voxelize_workspace_bytes.argtypes = [i64, i32, i32, i32, i32]
+    lib.lidf_voxelize_count.restype = C.c_int
+    lib.lidf_voxelize_count.argtypes = vox_common + [C.POINTER(C.c_int64), C.POINTER(C.c_int64), vp]
+    lib.lidf_voxelize_fill.restype = C.c_int
+    lib.lidf_voxelize_fill.argtypes = vox_common + [vp, vp, vp, vp, vp, vp]
     if lib.lidf_query_abi_version() != ABI_VERSION:
         raise RuntimeError("liblidf_query.so ABI version mismatch")
     lib.lidf_query_struct_size.restype = C.c_size_t

@@ -30,6 +30,10 @@ from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
 from implicit_depth_b200.models import implicit_net as im_net
 
 
+XMIN = (-1.0, -1.0, 0.0)     # reference src/constants.py:15
+XMAX = (1.0, 1.0, 2.0)       # reference src/constants.py:16
+
+
 def _multires_of(fn, default):
     return getattr(fn, "multires", default)
 
@@ -61,6 +65,30 @@ class LIDFQueryMixin:
                     multires_views=int(m.multires_views), intersect_pos_type=str(m.intersect_pos_type),
                     roi_inp_bbox=int(m.roi_inp_bbox), roi_out_bbox=int(m.roi_out_bbox), n_iter=int(m.n_iter),
                     use_sigmoid=bool(m.use_sigmoid), offset_range=tuple(float(v) for v in self.opt.grid.offset_range))
+
+    def get_occ_vox_bound(self, data_dict):
+        """Replacement for ``LIDF.get_occ_vox_bound`` (reference pipeline.py:162-201): same grid set-up, same ``data_dict``
+        entries, the (image, cell) ``torch.unique`` replaced by the occupancy-bitmap kernels (``lidf_voxelize_*``)."""
+        from implicit_depth_b200.utils import point_utils
+        dev = data_dict['valid_xyz'].device
+        xmin = torch.Tensor(XMIN).float().to(dev)
+        xmax = torch.Tensor(XMAX).float().to(dev)
+        min_bb = torch.min(xmax - xmin).item()
+        part_size = min_bb / self.opt.grid.res
+        xmin = xmin - 0.5 * part_size                                  # half voxel margin on each side, :172-173
+        xmax = xmax + 0.5 * part_size
+        dims = point_utils._grid_dims(xmin, xmax, part_size)
+        n_images = int(data_dict['bs']) if 'bs' in data_dict else int(data_dict['valid_bid'].max().item()) + 1
+        occ, voxel_bound, revidx, valid_v_pid, valid_v_rel_coord = point_utils.voxelize(
+            data_dict['valid_xyz'].float().contiguous(), data_dict['valid_bid'].long().contiguous(), xmin, part_size, dims,
+            n_images)
+        if occ.shape[0] == 0:
+            print('No occupied voxel', data_dict.get('item_path'))
+            return False
+        data_dict.update({'xmin': xmin, 'part_size': part_size, 'revidx': revidx, 'valid_v_pid': valid_v_pid,
+                          'valid_v_rel_coord': valid_v_rel_coord, 'occ_vox_bid': occ[:, 0],
+                          'occ_vox_global_coord': occ[:, 1:], 'voxel_bound': voxel_bound})
+        return True
 
     def compute_ray_aabb(self, data_dict):
         """Replacement for ``LIDF.compute_ray_aabb`` (reference pipeline.py:271-296): the same slab test, but the pair list

@@ -60,6 +60,24 @@ int lidf_pcl_aabb_pair_label(const float* pcl_pos, const float* voxel_bound, con
 int lidf_pcl_aabb_end_voxel(const float* pcl_pos, const float* voxel_bound, const int32_t* pcl_bid,
                             const int32_t* voxel_bid, int64_t N, int64_t V, int64_t* end_voxel_id, lidf_stream_t stream);
 
+/* Voxelisation of the valid points: point_utils.batch_get_occupied_idx (src/utils/point_utils.py:12-76, overlap = False)
+ * as called by LIDF.get_occ_vox_bound (src/models/pipeline.py:162-201).  Grid: origin xmin[3], cubic cells of edge
+ * part_size, n[3] cells per axis, B images; half_part = (float)(0.5 * part_size) as the reference forms it in double.
+ * Step 1 marks occupied cells and in-grid points, scans both, and returns the two counts (one sync, where the reference
+ * syncs on torch.unique); step 2 writes
+ *   occ_vox_bid_global_coord [V,4] int64 (image, cx, cy, cz), sorted as torch.unique(dim=0) sorts them
+ *   voxel_bound [V,6] = [xmin + c*part, that + part]            (pipeline.py:186-188)
+ *   revidx [Nv] int64, valid_v_pid [Nv] int64, valid_v_rel_coord [Nv,3]   (point_utils.py:66-74) */
+size_t lidf_voxelize_workspace_bytes(int64_t Np, int32_t B, int32_t nx, int32_t ny, int32_t nz);
+int lidf_voxelize_count(const float* valid_xyz /*[Np,3]*/, const int64_t* valid_bid /*[Np]*/, int64_t Np, int32_t B,
+                        float xmin0, float xmin1, float xmin2, float part_size, float half_part, int32_t nx, int32_t ny,
+                        int32_t nz, void* workspace, size_t workspace_bytes, int64_t* n_voxels_host,
+                        int64_t* n_inside_host, lidf_stream_t stream);
+int lidf_voxelize_fill(const float* valid_xyz, const int64_t* valid_bid, int64_t Np, int32_t B, float xmin0, float xmin1,
+                       float xmin2, float part_size, float half_part, int32_t nx, int32_t ny, int32_t nz, void* workspace,
+                       size_t workspace_bytes, int64_t* occ_vox_bid_global_coord, float* voxel_bound, int64_t* revidx,
+                       int64_t* valid_v_pid, float* valid_v_rel_coord, lidf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -88,3 +88,51 @@ def pcl_end_voxel(pcl_pos, voxel_bound, pcl_bid, voxel_bid, end_voxel_id):
     vox, pt = np.nonzero(mask)
     np.maximum.at(out, pt, vox)
     return out
+
+
+# --------------------------------------------------------------------------------------------------------------------
+# Voxelisation of the valid points (the producer of voxel_bound / occ_vox_bid / revidx):
+#   batch_get_occupied_idx   /root/reference/src/utils/point_utils.py:12-76  (overlap = False, the only mode LIDF uses)
+#   get_occ_vox_bound        /root/reference/src/models/pipeline.py:162-201
+# Pinned by tests/golden/voxel_*.npz (made by tests/golden/make_golden_voxel.py from the reference's own code).
+# Arithmetic as torch performs it on float32 tensors with python-float scalars (scalar rounded to fp32, IEEE ops).
+# --------------------------------------------------------------------------------------------------------------------
+XMIN = (-1.0, -1.0, 0.0)     # src/constants.py:15
+XMAX = (1.0, 1.0, 2.0)       # src/constants.py:16
+
+
+def grid_setup(res: int):
+    """pipeline.py:167-173 -> (xmin [3] f32 incl. the half-voxel margin, part_size python float, grid dims rr [3])."""
+    xmin = np.array(XMIN, np.float32); xmax = np.array(XMAX, np.float32)
+    part = float(np.min(xmax - xmin)) / res
+    xmin = (xmin - np.float32(0.5 * part)).astype(np.float32)
+    xmax = (xmax + np.float32(0.5 * part)).astype(np.float32)
+    rr = np.ceil((xmax - xmin) / np.float32(part)).astype(np.int64)            # point_utils.py:25-27
+    return xmin, part, rr
+
+
+def batch_get_occupied_idx(valid_xyz, valid_bid, xmin, part_size: float, rr):
+    """point_utils.py:12-76 -> (occ_bid_global_coord [V,4] i64 sorted unique, revidx [Nv], valid_v_pid [Nv],
+    valid_v_rel_coord [Nv,3] f32)."""
+    crop = np.float32(part_size)
+    v = (_f32(valid_xyz) - _f32(xmin)[None]).astype(np.float32)                 # :23
+    coord = np.floor(v / crop).astype(np.int64)                                 # :43 (shift is zero without overlap)
+    center = (coord.astype(np.float32) * crop + np.float32(0.5 * part_size)).astype(np.float32)   # :50
+    rel = (v - center).astype(np.float32)                                       # :51
+    ok = np.ones(v.shape[0], bool)
+    for i in range(3):                                                          # :59-61
+        ok &= (coord[:, i] >= 0) & (coord[:, i] < rr[i])
+    pid = np.nonzero(ok)[0].astype(np.int64)
+    rows = np.concatenate((np.asarray(valid_bid).astype(np.int64)[ok, None], coord[ok]), 1)      # :70
+    occ, revidx = np.unique(rows, axis=0, return_inverse=True)                  # :73 (sorted, lexicographic)
+    return occ.astype(np.int64), revidx.reshape(-1).astype(np.int64), pid, rel[ok]
+
+
+def get_occ_vox_bound(valid_xyz, valid_bid, res: int):
+    """pipeline.py:162-201 -> dict with the data_dict entries it writes."""
+    xmin, part, rr = grid_setup(res)
+    occ, revidx, pid, rel = batch_get_occupied_idx(valid_xyz, valid_bid, xmin, part, rr)
+    bound_min = (xmin[None] + occ[:, 1:].astype(np.float32) * np.float32(part)).astype(np.float32)   # :186
+    bound_max = (bound_min + np.float32(part)).astype(np.float32)                                    # :187
+    return dict(xmin=xmin, part_size=part, revidx=revidx, valid_v_pid=pid, valid_v_rel_coord=rel, occ_vox_bid=occ[:, 0],
+                occ_vox_global_coord=occ[:, 1:], voxel_bound=np.concatenate((bound_min, bound_max), 1), grid=rr)

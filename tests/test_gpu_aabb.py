@@ -188,3 +188,55 @@ def test_pipeline_mixin_real_geometry_chain_vs_oracle():
     start = np.concatenate((vox, [0]))[dd["max_pair_id"].cpu().numpy()]
     want_end = A.pcl_end_voxel(dd["pred_pos"].cpu().numpy(), d["voxel_bound"].numpy(), d["miss_bid"].numpy(), d["occ_vox_bid"].numpy(), start)
     assert np.array_equal(end.cpu().numpy(), want_end)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+VOXEL_CASES = ["voxel_res8_3img", "voxel_res8_unsorted", "voxel_res5"]
+
+
+@pytest.mark.parametrize("name", VOXEL_CASES)
+def test_voxelisation_golden_reference_outputs(name):
+    """LIDFQueryMixin.get_occ_vox_bound against the reference's own get_occ_vox_bound, bit for bit."""
+    from implicit_depth_b200.models.pipeline import LIDF, default_opt
+    z = dict(np.load(os.path.join(GOLDEN_DIR, name + ".npz")))
+    lidf = LIDF(default_opt(**{"grid.res": int(z["res"])}), torch.device("cuda"))
+    dd = dict(valid_xyz=_c(z["valid_xyz"]), valid_bid=_c(z["valid_bid"], torch.int64), bs=int(z["B"]), item_path=["golden"])
+    assert lidf.get_occ_vox_bound(dd) is True
+    assert dd["part_size"] == float(z["part_size"]) and np.array_equal(bits(dd["xmin"].cpu().numpy()), bits(z["xmin"]))
+    assert np.array_equal(dd["occ_vox_bid"].cpu().numpy(), z["ref_occ_vox_bid"])
+    assert np.array_equal(dd["occ_vox_global_coord"].cpu().numpy(), z["ref_occ_vox_global_coord"])
+    assert np.array_equal(bits(dd["voxel_bound"].cpu().numpy()), bits(z["ref_voxel_bound"]))
+    assert np.array_equal(dd["revidx"].cpu().numpy(), z["ref_revidx"])
+    assert np.array_equal(dd["valid_v_pid"].cpu().numpy(), z["ref_valid_v_pid"])
+    assert np.array_equal(bits(dd["valid_v_rel_coord"].cpu().numpy()), bits(z["ref_valid_v_rel_coord"]))
+    assert dd["occ_vox_bid"].dtype == torch.int64 and dd["revidx"].dtype == torch.int64
+
+
+def test_voxelisation_vs_oracle_seeded_and_edge_cases():
+    from implicit_depth_b200.utils import point_utils as PU
+    rng = np.random.default_rng(8)
+    for n, B, res in [(1, 1, 8), (257, 2, 8), (100000, 8, 8), (5000, 3, 3), (4096, 1, 13)]:
+        xyz = rng.uniform(-1.5, 2.5, size=(n, 3)).astype(np.float32)
+        xyz[rng.random((n, 3)) < 0.1] = np.float32(0.125)                       # on cell faces
+        bid = np.sort(rng.integers(0, B, size=n))
+        want = A.get_occ_vox_bound(xyz, bid, res)
+        xmin, part, rr = A.grid_setup(res)
+        occ, bound, revidx, pid, rel = PU.voxelize(_c(xyz), _c(bid, torch.int64), torch.from_numpy(xmin), part, rr.tolist(), B)
+        assert np.array_equal(occ[:, 0].cpu().numpy(), want["occ_vox_bid"])
+        assert np.array_equal(occ[:, 1:].cpu().numpy(), want["occ_vox_global_coord"])
+        assert np.array_equal(bits(bound.cpu().numpy()), bits(want["voxel_bound"]))
+        assert np.array_equal(revidx.cpu().numpy(), want["revidx"]) and np.array_equal(pid.cpu().numpy(), want["valid_v_pid"])
+        assert np.array_equal(bits(rel.cpu().numpy()), bits(want["valid_v_rel_coord"]))
+    # reference signature: batch_id [N,1], python-tuple bounds; no point inside the grid -> empty outputs
+    far = torch.full((10, 3), 50.0, device="cuda")
+    occ, revidx, pid, rel, idx_grid = PU.batch_get_occupied_idx(far, torch.zeros(10, 1, dtype=torch.int64, device="cuda"),
+                                                                xmin=(-1.125, -1.125, -0.125), xmax=(1.125, 1.125, 2.125),
+                                                                crop_size=0.25)
+    assert occ.shape == (0, 4) and revidx.numel() == 0 and pid.numel() == 0 and tuple(idx_grid.shape) == (9, 9, 9, 3)
+    occ, revidx, pid, rel, _ = PU.batch_get_occupied_idx(torch.zeros(0, 3, device="cuda"), torch.zeros(0, 1, dtype=torch.int64, device="cuda"),
+                                                         xmin=(-1.125, -1.125, -0.125), xmax=(1.125, 1.125, 2.125), crop_size=0.25)
+    assert occ.shape == (0, 4)
+    with pytest.raises(NotImplementedError):
+        PU.batch_get_occupied_idx(far, torch.zeros(10, 1, dtype=torch.int64, device="cuda"), overlap=True)
+    with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        PU.batch_get_occupied_idx(far.cpu(), torch.zeros(10, 1, dtype=torch.int64))

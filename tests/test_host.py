@@ -37,6 +37,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.lidf_ray_aabb_forward(None, None, None, None, 5, 5, None, None, None, 0, None) == -1
     assert lib.lidf_pcl_aabb_forward(None, None, None, None, 5, 5, None, None) == -1
     assert lib.lidf_pcl_aabb_end_voxel(None, None, None, None, 0, 5, None, None) == 0       # empty problem: no-op
+    assert lib.lidf_voxelize_workspace_bytes(10000, 8, 9, 9, 9) > 8 * 729 * 8 and lib.lidf_voxelize_workspace_bytes(5, 0, 9, 9, 9) == 0
 
 
 def test_no_cpu_fallback_for_aabb_ops():

@@ -75,3 +75,19 @@ def test_oracle_vs_reference_kernel_on_fresh_random_inputs():
         assert np.array_equal(m, rm) and np.array_equal(bits(dist), bits(rd))
         pts = rng.uniform(-1.2, 2.2, size=(R, 3))
         assert np.array_equal(A.pcl_aabb_dense(pts, vb, rb, xb), ref.pcl_aabb(pts, vb, rb, xb))
+
+
+VOXEL_CASES = ["voxel_res8_3img", "voxel_res8_unsorted", "voxel_res5"]
+
+
+@pytest.mark.parametrize("name", VOXEL_CASES)
+def test_voxelisation_oracle_is_bit_exact_against_reference_code(name):
+    z = load(name)
+    out = A.get_occ_vox_bound(z["valid_xyz"], z["valid_bid"], int(z["res"]))
+    assert out["part_size"] == float(z["part_size"]) and np.array_equal(bits(out["xmin"]), bits(z["xmin"]))
+    assert np.array_equal(out["occ_vox_bid"], z["ref_occ_vox_bid"])
+    assert np.array_equal(out["occ_vox_global_coord"], z["ref_occ_vox_global_coord"])
+    assert np.array_equal(bits(out["voxel_bound"]), bits(z["ref_voxel_bound"]))
+    assert np.array_equal(out["revidx"], z["ref_revidx"]) and np.array_equal(out["valid_v_pid"], z["ref_valid_v_pid"])
+    assert np.array_equal(bits(out["valid_v_rel_coord"]), bits(z["ref_valid_v_rel_coord"]))
+    assert 0 < out["valid_v_pid"].size < z["valid_xyz"].shape[0]          # some points fall outside the grid
