@@ -240,3 +240,83 @@ def test_voxelisation_vs_oracle_seeded_and_edge_cases():
         PU.batch_get_occupied_idx(far, torch.zeros(10, 1, dtype=torch.int64, device="cuda"), overlap=True)
     with pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         PU.batch_get_occupied_idx(far.cpu(), torch.zeros(10, 1, dtype=torch.int64))
+
+
+def test_front_to_back_chain_from_points():
+    """The whole native front half feeding the query path, on a synthetic scene: valid points -> get_occ_vox_bound
+    (bitmap voxelisation) -> compute_ray_aabb (pair list) -> get_pred (fused decoders + ray termination) ->
+    compute_pair_label / compute_ray_loss / refine_end_voxel / refine_decoder_tail -- every stage against its oracle."""
+    from conftest import rel_err
+    from implicit_depth_b200.models.pipeline import LIDF, RefineNet, default_opt
+    from implicit_depth_b200.synthetic import make_rays
+    from oracle import lidf_oracle as O
+    B, H, W = 2, 36, 48
+    g = torch.Generator().manual_seed(101)
+    # scene: a tilted plane around z = 1.1 + noise, sampled at 900 valid points per image
+    n_pts = 900
+    xy = torch.rand(B * n_pts, 2, generator=g) * 1.6 - 0.8
+    zz = 1.1 + 0.3 * xy[:, :1] + 0.05 * torch.randn(B * n_pts, 1, generator=g)
+    valid_xyz = torch.cat((xy, zz), 1).contiguous()
+    valid_bid = torch.arange(B).repeat_interleave(n_pts)
+    miss_bid, miss_img_ind, miss_ray_dir = make_rays(B, H, W, "cpu")
+    full_rgb_feat = torch.randn(B, 32, H, W, generator=g)
+
+    lidf = LIDF(default_opt(), torch.device("cuda")).cuda().eval()
+    off = O.init_decoder("IEF", 385, mode="trained", generator=g); prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
+    lidf.offset_dec.load_state_dict(off); lidf.prob_dec.load_state_dict(prob)
+    dd = dict(bs=B, h=H, w=W, valid_xyz=valid_xyz.cuda(), valid_bid=valid_bid.cuda(), miss_bid=miss_bid.cuda(),
+              miss_img_ind=miss_img_ind.cuda(), miss_ray_dir=miss_ray_dir.cuda(), full_rgb_feat=full_rgb_feat.cuda(),
+              total_miss_sample_num=miss_bid.shape[0], item_path=["scene"])
+    with torch.no_grad():
+        # 1. voxelisation
+        assert lidf.get_occ_vox_bound(dd)
+        wv = A.get_occ_vox_bound(valid_xyz.numpy(), valid_bid.numpy(), 8)
+        assert np.array_equal(bits(dd["voxel_bound"].cpu().numpy()), bits(wv["voxel_bound"]))
+        assert np.array_equal(dd["revidx"].cpu().numpy(), wv["revidx"])
+        V = dd["voxel_bound"].shape[0]
+        assert V > 20
+        # 2. pairs
+        assert lidf.compute_ray_aabb(dd)
+        vox, ray, pd = A.ray_aabb_pairs(miss_ray_dir.numpy(), wv["voxel_bound"], miss_bid.numpy(), wv["occ_vox_bid"])
+        assert np.array_equal(dd["occ_vox_intersect_idx"].cpu().numpy(), vox) and np.array_equal(dd["miss_ray_intersect_idx"].cpu().numpy(), ray)
+        assert np.array_equal(bits(dd["intersect_dist"].cpu().numpy()), bits(pd))
+        P = vox.shape[0]
+        assert P > 1000
+        # 3. decoders + termination (the voxel features are a producer's output: random stand-in)
+        occ_voxel_feat = torch.relu(torch.randn(V, 128, generator=g))
+        dd["occ_voxel_feat"] = occ_voxel_feat.cuda()
+        lidf.get_pred(dd, "test", 0)
+        do = dict(full_rgb_feat=full_rgb_feat, occ_voxel_feat=occ_voxel_feat, voxel_bound=torch.from_numpy(wv["voxel_bound"]),
+                  miss_ray_dir=miss_ray_dir, miss_img_ind=miss_img_ind, miss_bid=miss_bid,
+                  occ_vox_intersect_idx=torch.from_numpy(vox), miss_ray_intersect_idx=torch.from_numpy(ray),
+                  intersect_dist=torch.from_numpy(pd))
+        want = O.lidf_query(do, dict(O.DEFAULT_CFG), off, prob, wv["part_size"], dedup_rays=True)
+        for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax"):
+            assert rel_err(dd[k].cpu(), want[k]) < 1e-3, k
+        same = dd["max_pair_id"].cpu() == want["max_pair_id"]
+        assert float(same.float().mean()) > 0.99
+        # 4. labels + ray-wise loss statistics, with the GPU's own outputs as inputs to the oracle
+        gt_pos = (dd["pred_pos"] + 0.02 * torch.randn(dd["pred_pos"].shape, generator=g).cuda()).contiguous()
+        lidf.compute_pair_label(dd, gt_pos)
+        lab = A.pcl_pair_label(gt_pos.cpu().numpy(), wv["voxel_bound"], miss_bid.numpy(), wv["occ_vox_bid"], vox, ray)
+        assert np.array_equal(dd["pcl_label_float"].cpu().numpy(), lab)
+        st = lidf.compute_ray_loss(dd)
+        ws = O.ray_loss_stats(dd["pred_prob_end"].cpu(), dd["pred_prob_end_softmax"].cpu(), torch.from_numpy(ray),
+                              torch.from_numpy(lab).long(), miss_bid.shape[0], dd["pred_pos"].cpu(), gt_pos.cpu())
+        assert torch.equal(st["pred_label"].cpu(), ws["pred_label"]) and torch.equal(st["gt_label"].cpu(), ws["gt_label"])
+        for k in ("pos_loss", "prob_loss", "acc", "err"):
+            assert abs(float(st[k]) - float(ws[k])) < 1e-5 * max(1.0, abs(float(ws[k]))), k
+        # 5. stage 2
+        refine = RefineNet(default_opt(), torch.device("cuda")).cuda().eval()
+        rdec = O.init_decoder("IEF", 334, mode="trained", generator=g)
+        refine.offset_dec.load_state_dict(rdec)
+        end = refine.refine_end_voxel(dd, dd["pred_pos"])
+        start = np.concatenate((vox, [0]))[dd["max_pair_id"].cpu().numpy()]
+        want_end = A.pcl_end_voxel(dd["pred_pos"].cpu().numpy(), wv["voxel_bound"], miss_bid.numpy(), wv["occ_vox_bid"], start)
+        assert np.array_equal(end.cpu().numpy(), want_end)
+        feat2 = torch.relu(torch.randn(V, 128, generator=g))
+        out2 = refine.refine_decoder_tail(dd, dd["pred_pos"], end, feat2.cuda(), dd["roi_feat_per_ray"])
+        vb = torch.from_numpy(wv["voxel_bound"])[torch.from_numpy(want_end)]
+        want2 = O.refine_decoder_tail(dd["pred_pos"].cpu(), miss_ray_dir, (vb[:, :3] + vb[:, 3:]) / 2, feat2[torch.from_numpy(want_end)],
+                                      dd["roi_feat_per_ray"].cpu(), dict(O.REFINE_CFG), rdec)
+        assert rel_err(out2.cpu(), want2) < 1e-3
