@@ -19,10 +19,8 @@ LIB_PATH = LIB_OVERRIDE or os.path.join(CSRC, "liblidf_query.so")
 SOURCES = ["lidf_query.cu"]
 HEADERS = ["lidf_common.cuh", "lidf_prep.cuh", "lidf_simt.cuh", "lidf_tc.cuh", "lidf_aabb.cuh",
            os.path.join(INCLUDE, "lidf_query.h"), os.path.join(INCLUDE, "lidf_aabb.h")]
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-shared", "-Xcompiler", "-fPIC", "--use_fast_math=false"]
-NVCC_FLAGS = [f for f in NVCC_FLAGS if f != "--use_fast_math=false"]   # accurate sincosf/expf are required
-
+# no --use_fast_math: the path needs the accurate sincosf / expf / IEEE division
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-shared", "-Xcompiler", "-fPIC"]
 
 def find_nvcc():
     for cand in (shutil.which("nvcc"), "/usr/local/cuda/bin/nvcc"):
