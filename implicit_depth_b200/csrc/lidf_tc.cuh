@@ -68,6 +68,10 @@
 #ifndef TC_DEBUG_MODE
 #define TC_DEBUG_MODE 0
 #endif
+// suspend-time hint (ns) of mbarrier.try_wait: the warp is parked by the hardware instead of spinning through the loop
+#ifndef TC_WAIT_HINT_NS
+#define TC_WAIT_HINT_NS 1000
+#endif
 
 // ------------------------------------------------------------------------------------------------ PTX wrappers
 namespace tc {
@@ -88,10 +92,10 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
   uint32_t ok;
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
       "selp.b32 %0, 1, 0, p;\n\t}"
       : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
+      : "r"(smem_u32(bar)), "r"(parity), "r"((uint32_t)TC_WAIT_HINT_NS)
       : "memory");
   return ok != 0;
 }
@@ -356,10 +360,10 @@ __device__ __forceinline__ void mbar_wait_a(uint32_t bar_saddr, uint32_t parity)
     uint32_t ok;
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
         "selp.b32 %0, 1, 0, p;\n\t}"
         : "=r"(ok)
-        : "r"(bar_saddr), "r"(parity)
+        : "r"(bar_saddr), "r"(parity), "r"((uint32_t)TC_WAIT_HINT_NS)
         : "memory");
     if (ok) break;
     if (++spins > TC_SPIN_LIMIT) __trap();
