@@ -330,32 +330,52 @@ def main():
         dist.destroy_process_group()
 
 
-def stage2(d, step, dev, forward_times=2, impl="auto"):
-    """RefineNet.get_pred_refine per ray (reference pipeline.py:922-1041) on the hot-path pieces this repo owns: end-voxel
-    lookup (pcl_aabb.end_voxel), cached per-ray ROI feature, decoder tail incl. the occ_voxel_feat[end_voxel_id] gather
-    (lidf_refine_forward), repeated forward_times (train_refine.yaml:82).  The PointNet re-run is a producer: excluded."""
+def stage2(d, step, dev, forward_times=2, impl="auto", valid_per_image=10000):
+    """RefineNet.get_pred_refine per ray (reference pipeline.py:922-1041) on this repo's kernels: end-voxel lookup
+    (pcl_aabb.end_voxel), PointNet2Stage re-run over the valid points + one predicted point per ray (lidf_pointnet_forward),
+    cached per-ray ROI feature, decoder tail incl. the occ_voxel_feat[end_voxel_id] gather (lidf_refine_forward), repeated
+    forward_times (train_refine.yaml:82).  The torch glue between them (voxel centres, torch.cat of the PointNet inputs,
+    pipeline.py:975-1010) is inside the timed region."""
     from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
     from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
     from implicit_depth_b200.models import implicit_net as N
+    from implicit_depth_b200.models.pointnet import PointNet2Stage, pointnet_forward
     g = torch.Generator().manual_seed(7)
     dec = N.IEF(dev, 334, 1, gf_dim=64, n_iter=2)
     with torch.no_grad():
         for p_ in dec.parameters():
             p_.copy_(torch.randn(p_.shape, generator=g) / (p_.shape[1] ** 0.5) if p_.dim() == 2 else torch.randn(p_.shape, generator=g) * 0.1)
     dec = dec.to(dev).eval()
+    pnet = PointNet2Stage(6, 128, 32).to(dev).eval()
     out = step()
     roi = lidf_query.roi_align_rays(d["full_rgb_feat"], d["miss_img_ind"], d["miss_bid"], 8)
     vox = d["occ_vox_intersect_idx"]
     dummy = torch.cat((vox, torch.zeros(1, dtype=vox.dtype, device=dev)), 0)
     rb, xb = d["miss_bid"].int(), d["occ_vox_bid"].int()
-    R = int(d["miss_ray_dir"].shape[0])
+    R, V = int(d["miss_ray_dir"].shape[0]), int(d["occ_voxel_feat"].shape[0])
+    B = int(d["full_rgb_feat"].shape[0])
+    nv = valid_per_image * B                                         # grid.valid_sample_num points per image (test_lidf.yaml:55)
+    pnet_inp = torch.cat((0.25 * (torch.rand(nv, 3, generator=g) - 0.5), torch.rand(nv, 3, generator=g)), 1).to(dev)
+    revidx = torch.randint(0, V, (nv,), generator=g).sort().values.to(dev)
+    miss_rgb = torch.rand(R, 3, generator=g).to(dev)
+    vb = d["voxel_bound"]
+    t_pn = []
 
-    def run():
+    def run(record=False):
         pos = out["pred_pos"]
-        for _ in range(forward_times):
-            end = pcl_aabb.end_voxel(pos, d["voxel_bound"], rb, xb, dummy[out["max_pair_id"]].contiguous())
-            pos = lidf_query.refine_forward(pos, d["miss_ray_dir"], None, None, roi, dec, occ_voxel_feat=d["occ_voxel_feat"],
-                                            end_voxel_id=end, voxel_bound=d["voxel_bound"], mlp_impl=impl)
+        with torch.no_grad():
+            for _ in range(forward_times):
+                end = pcl_aabb.end_voxel(pos, vb, rb, xb, dummy[out["max_pair_id"]].contiguous())
+                evb = vb[end]
+                pred_inp = torch.cat((pos - (evb[:, :3] + evb[:, 3:]) / 2., miss_rgb), 1)          # pipeline.py:975-984
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                feat = pointnet_forward(pnet, torch.cat((pnet_inp, pred_inp), 0), torch.cat((revidx, end), 0), V)   # :1008-1014
+                e1.record()
+                if record:
+                    t_pn.append((e0, e1))
+                pos = lidf_query.refine_forward(pos, d["miss_ray_dir"], None, None, roi, dec, occ_voxel_feat=feat,
+                                                end_voxel_id=end, voxel_bound=vb, mlp_impl=impl)
         return pos
     for _ in range(2):
         run()
@@ -363,12 +383,13 @@ def stage2(d, step, dev, forward_times=2, impl="auto"):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(3):
-        run()
+        run(record=True)
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / 3
-    return dict(ms=ms, rays=R, forward_times=forward_times, rays_per_s=R * forward_times / (ms * 1e-3),
-                nominal_tflops=R * forward_times * 522560 / (ms * 1e-3) / 1e12)
+    pn_ms = sum(a.elapsed_time(b) for a, b in t_pn) / 3
+    return dict(ms=ms, pointnet_ms=pn_ms, rays=R, pointnet_points=nv + R, forward_times=forward_times,
+                rays_per_s=R * forward_times / (ms * 1e-3))
 
 
 def torch_gpu_baseline(d, off, prob, args, dev, rays=1 << 14):

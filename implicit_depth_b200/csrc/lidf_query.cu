@@ -824,3 +824,65 @@ extern "C" int lidf_voxelize_fill(const float* xyz, const int64_t* bid, int64_t 
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
+
+// ---- PointNet2Stage forward (include/lidf_pointnet.h) ------------------------------------------------------------------
+#include "lidf_pointnet.cuh"
+
+namespace {
+struct PnPlan { float* vmax1; float* vf1; float* vmax2; int* err; size_t bytes; };
+int plan_pn(int64_t N, int64_t V, PnPlan* q, char* base) {
+  if (N < 0 || V < 0) return LIDF_ERR_ARG;
+  if (V >= INT_MAX / 256 || N >= ((int64_t)1 << 40)) return LIDF_ERR_UNSUPPORTED;
+  Bump b{base, 0};
+  const size_t v = (size_t)(V > 0 ? V : 1);
+  q->vmax1 = b.take<float>(v * PN_C1);
+  q->vmax2 = b.take<float>(v * PN_C2);      // contiguous with vmax1: one memset clears both
+  q->vf1 = b.take<float>(v * PN_C1);
+  q->err = b.take<int>(1);
+  q->bytes = b.off + 256;
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_pointnet_workspace_bytes(int64_t N, int64_t V) {
+  PnPlan q;
+  if (plan_pn(N, V, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_pointnet_forward(const LidfPointNet* wp, const float* inp, const int64_t* idx, int64_t N, int64_t V,
+                                     float* out, void* ws, size_t ws_bytes, lidf_stream_t stream) {
+  if (!wp) return LIDF_ERR_NULL;
+  PnPlan q;
+  int rc = plan_pn(N, V, &q, (char*)ws);
+  if (rc) return rc;
+  if (V == 0) return LIDF_OK;
+  if (!out || !ws || (N > 0 && (!inp || !idx))) return LIDF_ERR_NULL;
+  if (ws_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  PnWeights w{wp->point_lin1_w, wp->point_lin1_b, wp->point_lin2_w, wp->point_lin2_b, wp->vox_lin1_w, wp->vox_lin1_b,
+              wp->point_lin3_w, wp->point_lin3_b, wp->point_lin4_w, wp->point_lin4_b, wp->vox_lin2_w, wp->vox_lin2_b};
+  const float* const* all = &w.w_p1;
+  for (int i = 0; i < 12; ++i)
+    if (!all[i]) return LIDF_ERR_NULL;
+  cudaStream_t st = stream;
+  LIDF_CUDA(cudaMemsetAsync(q.vmax1, 0, (size_t)((char*)q.vf1 - (char*)q.vmax1), st));     // vmax1 and vmax2
+  LIDF_CUDA(cudaMemsetAsync(q.err, 0, sizeof(int), st));
+  const size_t sm1 = pn_stage1_smem(), sm2 = pn_stage2_smem();
+  LIDF_CUDA(cudaFuncSetAttribute(k_pn_stage1, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm1));
+  LIDF_CUDA(cudaFuncSetAttribute(k_pn_stage2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2));
+  if (N > 0) {
+    const int64_t t1 = (N + PN1_THREADS - 1) / PN1_THREADS;
+    k_pn_stage1<<<persistent_blocks(t1, 2), PN1_THREADS, sm1, st>>>(inp, idx, N, V, w, q.vmax1, q.err);
+    LIDF_LAUNCH_CHECK();
+  }
+  k_pn_vox<PN_C1><<<(unsigned)((V + 7) / 8), PN_C1, 0, st>>>(q.vmax1, w.w_v1, w.b_v1, V, q.vf1);
+  LIDF_LAUNCH_CHECK();
+  if (N > 0) {
+    const int64_t t2 = (N + PN2_TP - 1) / PN2_TP;
+    k_pn_stage2<<<persistent_blocks(t2, 1), PN2_THREADS, sm2, st>>>(inp, idx, N, V, w, q.vf1, q.vmax2);
+    LIDF_LAUNCH_CHECK();
+  }
+  k_pn_vox<PN_C2><<<(unsigned)((V + 7) / 8), PN_C2, 0, st>>>(q.vmax2, w.w_v2, w.b_v2, V, out);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}

@@ -67,6 +67,8 @@ EXPORTED_SYMBOLS = [
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
     "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
 ]
+# include/lidf_pointnet.h (bound by models/pointnet.py)
+EXPORTED_SYMBOLS_POINTNET = ["lidf_pointnet_workspace_bytes", "lidf_pointnet_forward"]
 # include/lidf_aabb.h (bound by extensions/ray_aabb/jit.py and extensions/pcl_aabb/jit.py)
 EXPORTED_SYMBOLS_AABB = [
     "lidf_ray_aabb_workspace_bytes", "lidf_ray_aabb_forward", "lidf_ray_aabb_pairs_count", "lidf_ray_aabb_pairs_fill",

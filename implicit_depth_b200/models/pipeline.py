@@ -28,6 +28,7 @@ import torch.nn as nn
 
 from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
 from implicit_depth_b200.models import implicit_net as im_net
+from implicit_depth_b200.models import pointnet as pnet
 
 
 XMIN = (-1.0, -1.0, 0.0)     # reference src/constants.py:15
@@ -224,7 +225,9 @@ class LIDF(LIDFQueryMixin, nn.Module):
         else:
             self.embed_fn, embed_ch = im_net.get_embedder(m.multires, i=-1)
             self.embeddirs_fn, embeddirs_ch = im_net.get_embedder(m.multires_views, i=-1)
-        self.resnet_model = resnet_model
+        self.resnet_model = resnet_model          # cuDNN backbone: out of scope, injected (reference pipeline.py:50-54)
+        if pnet_model is None and m.pnet_model_type == 'twostage':                                   # pipeline.py:56-58
+            pnet_model = pnet.PointNet2Stage(input_channels=m.pnet_in, output_channels=m.pnet_out, gf_dim=m.pnet_gf).to(device)
         self.pnet_model = pnet_model
         dec_inp_dim = m.pnet_out + m.rgb_out * (m.roi_out_bbox ** 2) + 2 * embed_ch + embeddirs_ch   # pipeline.py:64-65
         if m.offdec_type == 'IMNET':
@@ -278,6 +281,54 @@ class RefineDecoderMixin:
             offset_range=tuple(float(v) for v in r.offset_range), mlp_impl=self.mlp_impl)
 
 
+    def get_pred_refine(self, data_dict, pred_pos, exp_type, cur_iter):
+        """Replacement for ``RefineNet.get_pred_refine`` (reference pipeline.py:922-1030), inference path: the same steps in
+        the same order with this repo's kernels -- end-voxel lookup (``pcl_aabb.end_voxel``), the per-ray ROI feature cached
+        by stage 1 (``data_dict['roi_feat_per_ray']``) instead of a second ``roi_align`` (:952-970), the PointNet re-run over
+        the valid points plus the predicted points (``self.pnet_model``; ``models.pointnet.PointNet2Stage`` runs it natively),
+        and the fused decoder tail.  The training-time perturbation (:926-937) is reproduced as written."""
+        bs, h, w = data_dict['bs'], data_dict['h'], data_dict['w']
+        r = self.opt.refine
+        if exp_type == 'train' and r.perturb and cur_iter == 0 and np.random.random() < r.perturb_prob:
+            prob = np.random.random()
+            if prob < 0.5:
+                noise = np.random.random() * (0 + 0.05) - 0.05
+            elif prob < 0.8:
+                noise = np.random.random() * (0.05 - 0)
+            elif prob < 0.9:
+                noise = np.random.random() * (-0.05 + 0.1) - 0.1
+            else:
+                noise = np.random.random() * (0.1 - 0.05) + 0.05
+            pred_pos = pred_pos + noise * data_dict['miss_ray_dir']
+        end_voxel_id = self.refine_end_voxel(data_dict, pred_pos)                                   # :939-944
+        rgb_img_flat = data_dict['rgb_img'].permute(0, 2, 3, 1).contiguous().reshape(bs, -1, 3)     # :972-973
+        miss_rgb = rgb_img_flat[data_dict['miss_bid'], data_dict['miss_flat_img_id']]
+        end_voxel_bound = data_dict['voxel_bound'][end_voxel_id]                                    # :975-977
+        end_voxel_center = (end_voxel_bound[:, :3] + end_voxel_bound[:, 3:]) / 2.
+        if r.pnet_pos_type == 'rel':                                                                # :979-984
+            pred_inp = torch.cat((pred_pos - end_voxel_center, miss_rgb), 1)
+        else:
+            pred_inp = torch.cat((pred_pos, miss_rgb), 1)
+        if exp_type != 'train' and self.opt.mask_type == 'all' and r.use_all_pix == False:          # noqa: E712  (:985-995)
+            zero_pixel_idx = torch.nonzero(1 - data_dict['valid_mask'], as_tuple=False)
+            sel = (zero_pixel_idx[:, 0], zero_pixel_idx[:, 1], zero_pixel_idx[:, 2])
+            new_pred_inp = pred_inp.reshape(bs, h, w, pred_inp.shape[-1])[sel]
+            new_end_voxel_id = end_voxel_id.reshape(bs, h, w)[sel]
+        else:
+            new_pred_inp, new_end_voxel_id = pred_inp, end_voxel_id
+        valid_v_rgb = data_dict['valid_rgb'][data_dict['valid_v_pid']]                              # :999-1007
+        if r.pnet_pos_type == 'rel':
+            pnet_inp = torch.cat((data_dict['valid_v_rel_coord'], valid_v_rgb), -1)
+        elif r.pnet_pos_type == 'abs':
+            pnet_inp = torch.cat((data_dict['valid_xyz'][data_dict['valid_v_pid']], valid_v_rgb), -1)
+        else:
+            raise NotImplementedError('Does not support Pnet pos type: {}'.format(r.pnet_pos_type))
+        final_pnet_inp = torch.cat((pnet_inp, new_pred_inp), 0)                                     # :1008-1010
+        final_revidx = torch.cat((data_dict['revidx'], new_end_voxel_id), 0)
+        occ_voxel_feat = self.pnet_model(inp_feat=final_pnet_inp, vox2point_idx=final_revidx)       # :1011-1014
+        return self.refine_decoder_tail(data_dict, pred_pos, end_voxel_id, occ_voxel_feat, data_dict['roi_feat_per_ray'])
+
+
 class RefineNet(RefineDecoderMixin, nn.Module):
     """Stand-alone holder of RefineNet.offset_dec (pipeline.py:722-758)."""
 
@@ -292,6 +343,8 @@ class RefineNet(RefineDecoderMixin, nn.Module):
         else:
             self.embed_fn, embed_ch = im_net.get_embedder(r.multires, i=-1)
             self.embeddirs_fn, embeddirs_ch = im_net.get_embedder(r.multires_views, i=-1)
+        if pnet_model is None and r.pnet_model_type == 'twostage':                                   # pipeline.py:733-735
+            pnet_model = pnet.PointNet2Stage(input_channels=r.pnet_in, output_channels=r.pnet_out, gf_dim=r.pnet_gf).to(device)
         self.pnet_model = pnet_model
         dec_inp_dim = r.pnet_out + embed_ch + embeddirs_ch + m.rgb_out * (m.roi_out_bbox ** 2)   # pipeline.py:740-742
         if r.offdec_type == 'IMNET':
@@ -315,12 +368,14 @@ def default_opt(**over):
     """opt.model / opt.grid / opt.refine with the values of the shipped YAMLs (train_lidf.yaml, train_refine.yaml)."""
     model = dict(pos_encode=True, multires=8, multires_views=4, intersect_pos_type='abs', rgb_in=3, rgb_out=32,
                  roi_inp_bbox=8, roi_out_bbox=2, pnet_in=6, pnet_out=128, pnet_gf=32, pnet_pos_type='rel',
-                 offdec_type='IEF', n_iter=2, probdec_type='IMNET', imnet_gf=64, scatter_type='Maxpool',
+                 offdec_type='IEF', n_iter=2, probdec_type='IMNET', imnet_gf=64, scatter_type='Maxpool', pnet_model_type='twostage',
                  use_sigmoid=False, maxpool_label_epo=6)
     refine = dict(pos_encode=True, multires=8, multires_views=4, intersect_pos_type='abs', pnet_out=128,
-                  offdec_type='IEF', n_iter=2, imnet_gf=64, use_sigmoid=False, offset_range=[-0.2, 0.2], forward_times=2)
+                  offdec_type='IEF', n_iter=2, imnet_gf=64, use_sigmoid=False, offset_range=[-0.2, 0.2], forward_times=2,
+                  pnet_in=6, pnet_gf=32, pnet_pos_type='rel', pnet_model_type='twostage', perturb=False, perturb_prob=0.,
+                  use_all_pix=True)
     grid = dict(res=8, offset_range=[0., 1.])
     for k, v in over.items():
         sect, key = k.split('.')
         {'model': model, 'refine': refine, 'grid': grid}[sect][key] = v
-    return _NS(model=_NS(**model), refine=_NS(**refine), grid=_NS(**grid), gpu_id=0)
+    return _NS(model=_NS(**model), refine=_NS(**refine), grid=_NS(**grid), gpu_id=0, mask_type='all')

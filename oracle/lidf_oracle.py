@@ -415,6 +415,29 @@ def refine_decoder_tail(pred_pos: torch.Tensor, miss_ray_dir: torch.Tensor, end_
 
 
 # --------------------------------------------------------------------------- #
+# pointnet.py : PointNet2Stage (the producer of occ_voxel_feat)
+# --------------------------------------------------------------------------- #
+def _scatter_rows_max(src: torch.Tensor, index: torch.Tensor, n: int) -> torch.Tensor:
+    """torch_scatter.scatter(src, index, dim=0, reduce='max'): per-row segment max; rows nobody writes stay 0."""
+    out = torch.full((n, src.shape[1]), -float("inf"), dtype=src.dtype)
+    out = out.scatter_reduce(0, index.reshape(-1, 1).expand_as(src), src, reduce="amax", include_self=True)
+    return torch.where(torch.isinf(out), torch.zeros_like(out), out)
+
+
+def pointnet2stage_forward(p: Dict[str, torch.Tensor], inp_feat: torch.Tensor, vox2point_idx: torch.Tensor,
+                           n_vox: Optional[int] = None) -> torch.Tensor:
+    """/root/reference/src/models/pointnet.py:22-38, state_dict keys point_lin{1..4}, vox_lin{1,2}."""
+    n = int(vox2point_idx.max()) + 1 if n_vox is None else n_vox
+    lin = lambda name, x: F.linear(x, p[name + ".weight"], p[name + ".bias"])
+    f1 = F.relu(lin("point_lin1", inp_feat))                                   # :24
+    f2 = F.relu(lin("point_lin2", f1))                                         # :25
+    v1 = F.relu(lin("vox_lin1", _scatter_rows_max(f2, vox2point_idx, n)))      # :27-28
+    f3 = torch.cat((v1[vox2point_idx], f2), -1)                                # :30-31
+    f5 = F.relu(lin("point_lin4", F.relu(lin("point_lin3", f3))))              # :32-33
+    return F.relu(lin("vox_lin2", _scatter_rows_max(f5, vox2point_idx, n)))    # :35-36
+
+
+# --------------------------------------------------------------------------- #
 # helpers shared by tests / bench
 # --------------------------------------------------------------------------- #
 

@@ -75,6 +75,13 @@ def _shim_scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
             if s[i] > o[idx[i]]:
                 o[idx[i]] = s[i]
         return out
+    if reduce == "max" and out is None and dim == 0:                # pointnet.py:27,35: per-voxel max of [N,C] rows
+        n = int(index.max()) + 1 if dim_size is None else dim_size  # torch_scatter: rows without any source stay 0
+        s = src.detach().numpy(); idx = index.numpy()
+        o = np.full((n,) + s.shape[1:], -np.inf, dtype=s.dtype)
+        np.maximum.at(o, idx, s)
+        o[np.isneginf(o)] = 0
+        return torch.from_numpy(o)
     if reduce == "sum":
         n = int(index.max()) + 1 if dim_size is None else dim_size
         return torch.zeros((n,) + src.shape[1:], dtype=src.dtype).index_add_(0, index, src)

@@ -521,3 +521,97 @@ def test_forward_host_async_back_to_back_batches():
     for got, want in zip(outs, wants):
         for k in lq.OUTPUT_KEYS:
             assert torch.equal(got[k], want[k]), k
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# PointNet2Stage forward (the producer of occ_voxel_feat)
+@pytest.mark.parametrize("name", ["pointnet_2000x60", "pointnet_257x3"])
+def test_pointnet_golden_reference_module_outputs(name):
+    from test_oracle import load_pointnet
+    from implicit_depth_b200.models.pointnet import PointNet2Stage
+    w, inp, idx, V, ref = load_pointnet(name)
+    net = PointNet2Stage(input_channels=6, output_channels=128, gf_dim=32).cuda().eval()
+    net.load_state_dict(w)                                   # reference checkpoint keys
+    with torch.no_grad():
+        out = net(inp.cuda(), idx.cuda())
+    assert out.shape == ref.shape
+    assert rel_err(out.cpu(), ref) < TOL_FP32
+
+
+@pytest.mark.parametrize("N,V,sorted_idx", [(1, 1, True), (63, 5, False), (64, 64, True), (65, 2, False), (5000, 300, True),
+                                            (100000, 2048, True), (3000, 40, False), (0, 3, True)])
+def test_pointnet_vs_oracle_seeded(N, V, sorted_idx):
+    from implicit_depth_b200.models.pointnet import pointnet_forward
+    g = torch.Generator().manual_seed(N + V)
+    w = {}
+    for name, (o, i) in {"point_lin1": (32, 6), "point_lin2": (64, 32), "vox_lin1": (64, 64), "point_lin3": (128, 128),
+                         "point_lin4": (128, 128), "vox_lin2": (128, 128)}.items():
+        w[name + ".weight"] = torch.randn(o, i, generator=g) / i ** 0.5
+        w[name + ".bias"] = 0.1 * torch.randn(o, generator=g)
+    inp = torch.cat((0.3 * torch.randn(N, 3, generator=g), torch.rand(N, 3, generator=g)), 1)
+    idx = torch.randint(0, V, (N,), generator=g)
+    if sorted_idx:
+        idx = idx.sort().values                              # long runs of equal voxel ids (the run-reduced path)
+    want = O.pointnet2stage_forward(w, inp, idx, V)
+    got = pointnet_forward(_cuda(w), inp.cuda(), idx.cuda(), V)
+    assert got.shape == (V, 128)
+    assert rel_err(got.cpu(), want) < TOL_FP32, rel_err(got.cpu(), want)
+    if N:                                                    # voxels that own no point: relu(b) through the voxel layers only
+        empty = torch.ones(V, dtype=torch.bool); empty[idx] = False
+        if empty.any():
+            assert torch.allclose(got.cpu()[empty], want[empty], atol=1e-6)
+
+
+def test_get_pred_refine_mirror_vs_reference_output():
+    """RefineDecoderMixin.get_pred_refine (end voxel -> PointNet inputs -> decoder tail) against the output of the
+    reference's own get_pred_refine stored in the fixture (its PointNet was a fixed stand-in there; same here), and the same
+    call with the native PointNet2Stage against the oracle chain."""
+    from implicit_depth_b200.models.pipeline import RefineNet, default_opt
+    from implicit_depth_b200.models.pointnet import PointNet2Stage
+    d, cfg, off, prob, part, ref, extra = load_golden("ief_ragged_2x24x32")
+    rdec = {k[len("refine_dec."):]: v for k, v in extra.items() if k.startswith("refine_dec.")}
+    B, H, W = d["full_rgb_feat"].shape[0], d["full_rgb_feat"].shape[2], d["full_rgb_feat"].shape[3]
+    vfeat2 = extra["refine.occ_voxel_feat"]
+
+    class _Fixed(torch.nn.Module):
+        def __init__(self, value):
+            super().__init__(); self.value = value; self.last = None
+
+        def forward(self, *a, **kw):
+            self.last = kw
+            return self.value
+
+    refine = RefineNet(default_opt(), torch.device("cuda"), pnet_model=_Fixed(vfeat2.cuda())).cuda().eval()
+    refine.offset_dec.load_state_dict(rdec)
+    dd = _cuda(d)
+    dd.update(bs=B, h=H, w=W, max_pair_id=ref["max_pair_id"].cuda(), rgb_img=torch.zeros(B, 3, H, W, device="cuda"),
+              miss_flat_img_id=(d["miss_img_ind"][:, 1] * W + d["miss_img_ind"][:, 0]).cuda(),
+              valid_rgb=torch.zeros(4, 3, device="cuda"), valid_v_pid=torch.zeros(4, dtype=torch.long, device="cuda"),
+              valid_v_rel_coord=torch.zeros(4, 3, device="cuda"), revidx=torch.zeros(4, dtype=torch.long, device="cuda"),
+              roi_feat_per_ray=_lq().roi_align_rays(d["full_rgb_feat"].cuda(), d["miss_img_ind"].cuda(), d["miss_bid"].cuda(), 8))
+    with torch.no_grad():
+        out = refine.get_pred_refine(dd, ref["pred_pos"].cuda(), "test", 0)
+    R = d["miss_ray_dir"].shape[0]
+    assert torch.equal(refine.pnet_model.last["vox2point_idx"][-R:].cpu(), extra["refine.end_voxel_id"].long())   # pipeline.py:1010
+    assert rel_err(out.cpu(), ref["pred_pos_refine"]) < TOL_TC
+    # with the native PointNet: oracle chain on the same PointNet inputs
+    g = torch.Generator().manual_seed(77)
+    pn = PointNet2Stage(6, 128, 32)
+    refine.pnet_model = pn.cuda().eval()
+    V = d["occ_voxel_feat"].shape[0]
+    nv = 500
+    dd.update(valid_rgb=torch.rand(nv, 3, generator=g).cuda(), valid_v_pid=torch.arange(nv).cuda(),
+              valid_v_rel_coord=(0.2 * (torch.rand(nv, 3, generator=g) - 0.5)).cuda(),
+              revidx=torch.cat((torch.arange(V), torch.randint(0, V, (nv - V,), generator=g))).cuda())
+    with torch.no_grad():
+        out2 = refine.get_pred_refine(dd, ref["pred_pos"].cuda(), "test", 0)
+    evid = extra["refine.end_voxel_id"].long()
+    vb = d["voxel_bound"][evid]
+    center = (vb[:, :3] + vb[:, 3:]) / 2
+    pn_inp = torch.cat((torch.cat((dd["valid_v_rel_coord"].cpu(), dd["valid_rgb"].cpu()), 1),
+                        torch.cat((ref["pred_pos"] - center, torch.zeros(R, 3)), 1)), 0)
+    feat = O.pointnet2stage_forward({k: v.cpu() for k, v in pn.state_dict().items()}, pn_inp, torch.cat((dd["revidx"].cpu(), evid)), V)
+    want2 = O.refine_decoder_tail(ref["pred_pos"], d["miss_ray_dir"], center, feat[evid], dd["roi_feat_per_ray"].cpu(),
+                                  dict(O.REFINE_CFG, offset_range=tuple(float(v) for v in extra["refine.offset_range"]),
+                                       n_iter=extra["refine.n_iter"]), rdec)
+    assert rel_err(out2.cpu(), want2) < TOL_TC

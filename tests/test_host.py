@@ -17,13 +17,14 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert os.path.exists(path)
     lib = jit.load_library()
     declared = set()
-    for name, want in (("lidf_query.h", jit.EXPORTED_SYMBOLS), ("lidf_aabb.h", jit.EXPORTED_SYMBOLS_AABB)):
+    for name, want in (("lidf_query.h", jit.EXPORTED_SYMBOLS), ("lidf_aabb.h", jit.EXPORTED_SYMBOLS_AABB),
+                       ("lidf_pointnet.h", jit.EXPORTED_SYMBOLS_POINTNET)):
         header = open(os.path.join(REPO, "include", name)).read()
         header = re.sub(r"/\*.*?\*/", "", header, flags=re.S)
         got = set(re.findall(r"\b(lidf_[a-z_0-9]+)\s*\(", header))
         assert got == set(want), (name, got ^ set(want))
         declared |= got
-    assert sorted(os.listdir(os.path.join(REPO, "include"))) == ["lidf_aabb.h", "lidf_query.h"]
+    assert sorted(os.listdir(os.path.join(REPO, "include"))) == ["lidf_aabb.h", "lidf_pointnet.h", "lidf_query.h"]
     for sym in declared:
         assert hasattr(lib, sym), sym
     assert lib.lidf_query_abi_version() == 2
@@ -37,6 +38,9 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.lidf_ray_aabb_forward(None, None, None, None, 5, 5, None, None, None, 0, None) == -1
     assert lib.lidf_pcl_aabb_forward(None, None, None, None, 5, 5, None, None) == -1
     assert lib.lidf_pcl_aabb_end_voxel(None, None, None, None, 0, 5, None, None) == 0       # empty problem: no-op
+    lib.lidf_pointnet_workspace_bytes.restype = ctypes.c_size_t
+    lib.lidf_pointnet_workspace_bytes.argtypes = [ctypes.c_int64, ctypes.c_int64]
+    assert lib.lidf_pointnet_workspace_bytes(1000, 10) >= 10 * 256 * 4 and lib.lidf_pointnet_forward(None, None, None, 0, 0, None, None, 0, None) == -1
     assert lib.lidf_voxelize_workspace_bytes(10000, 8, 9, 9, 9) > 8 * 729 * 8 and lib.lidf_voxelize_workspace_bytes(5, 0, 9, 9, 9) == 0
 
 
@@ -136,3 +140,20 @@ def test_image_splits_of_the_reference_layout():
     assert s["pairs"][-1] == vox.shape[0]
     d.pop("occ_vox_bid")
     assert lidf_query.image_splits(d, 3) is None
+
+
+def test_pointnet_mirror_state_dict_and_autograd_path():
+    """models.pointnet.PointNet2Stage mirror: reference checkpoint keys, reference values on the torch (training) path,
+    and no CPU fallback for the native (inference) path."""
+    from test_oracle import load_pointnet
+    from implicit_depth_b200.models.pointnet import PointNet2Stage
+    w, inp, idx, V, ref = load_pointnet("pointnet_2000x60")
+    net = PointNet2Stage(input_channels=6, output_channels=128, gf_dim=32)
+    assert set(net.state_dict().keys()) == set(w.keys())
+    net.load_state_dict(w)
+    out = net(inp, idx)                                      # parameters require grad -> torch path
+    assert rel_err(out.detach(), ref) < 2e-6
+    out.sum().backward()
+    assert net.point_lin1.weight.grad is not None and net.vox_lin2.weight.grad is not None
+    with torch.no_grad(), pytest.raises(RuntimeError, match="must be a CUDA tensor"):
+        net(inp, idx)

@@ -122,3 +122,23 @@ def test_ray_loss_oracle_matches_reference_compute_loss(name):
     assert rel_err(out["log_softmax"], t["ref_log_softmax"]) < 1e-6
     for k in ("pos_loss", "prob_loss", "acc", "err"):
         assert abs(float(out[k]) - sc["ref_" + k]) <= 2e-6 * max(1.0, abs(sc["ref_" + k])), k
+
+
+POINTNET_CASES = ["pointnet_2000x60", "pointnet_257x3"]
+
+
+def load_pointnet(name):
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    w = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    return w, torch.from_numpy(z["inp_feat"]), torch.from_numpy(z["vox2point_idx"]).long(), int(z["V"]), torch.from_numpy(z["ref_out"])
+
+
+@pytest.mark.parametrize("name", POINTNET_CASES)
+def test_pointnet_oracle_matches_reference_module(name):
+    w, inp, idx, V, ref = load_pointnet(name)
+    out = O.pointnet2stage_forward(w, inp, idx, V)
+    assert out.shape == ref.shape == (V, 128)
+    assert rel_err(out, ref) < 2e-6
