@@ -249,11 +249,11 @@ __global__ void __launch_bounds__(AABB_THREADS) k_pcl_dense(const float* __restr
 __global__ void k_pcl_pair_label(const float* __restrict__ pcl_pos, const float* __restrict__ voxel_bound,
                                  const int32_t* __restrict__ pcl_bid, const int32_t* __restrict__ voxel_bid, int64_t N, int64_t V,
                                  const int64_t* __restrict__ pair_vox, const int64_t* __restrict__ pair_ray, int64_t P,
-                                 float* __restrict__ label, int* __restrict__ err) {
+                                 float* __restrict__ label) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const int64_t v = pair_vox[i], n = pair_ray[i];
-  if (v < 0 || v >= V || n < 0 || n >= N) { atomicOr(err, 1); label[i] = 0.f; return; }
+  if (v < 0 || v >= V || n < 0 || n >= N) { label[i] = 0.f; return; }      // index outside the mask: never a hit
   bool in = false;
   if (__ldg(pcl_bid + n) == __ldg(voxel_bid + v))
     in = aabb_inside(__ldg(pcl_pos + n * 3 + 0), __ldg(pcl_pos + n * 3 + 1), __ldg(pcl_pos + n * 3 + 2), aabb_load_box(voxel_bound, v));

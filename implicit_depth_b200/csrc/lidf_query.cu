@@ -716,10 +716,8 @@ extern "C" int lidf_pcl_aabb_pair_label(const float* pcl_pos, const float* voxel
   if (N < 0 || V < 0 || P < 0) return LIDF_ERR_ARG;
   if (P == 0) return LIDF_OK;
   if (!pcl_pos || !voxel_bound || !pcl_bid || !voxel_bid || !pair_vox || !pair_ray || !label) return LIDF_ERR_NULL;
-  static thread_local int* d_err = nullptr;               // sticky device flag for out-of-range pair indices
-  if (!d_err) { LIDF_CUDA(cudaMalloc(&d_err, sizeof(int))); LIDF_CUDA(cudaMemset(d_err, 0, sizeof(int))); }
   k_pcl_pair_label<<<(unsigned)((P + 255) / 256), 256, 0, (cudaStream_t)stream>>>(pcl_pos, voxel_bound, pcl_bid, voxel_bid, N, V,
-                                                                                  pair_vox, pair_ray, P, label, d_err);
+                                                                                  pair_vox, pair_ray, P, label);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
