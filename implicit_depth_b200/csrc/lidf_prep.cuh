@@ -416,3 +416,77 @@ __global__ void k_ray_loss_reduce(const float* __restrict__ ray_part, int64_t R,
     if (threadIdx.x == 0) *done = 0;
   }
 }
+
+// ------------------------------------------------------------------------------------------------
+// Image-space loss terms of LIDF.compute_loss (pipeline.py:494-541): surface-normal loss, angle error and smoothness loss
+// at the miss pixels of the point image with pred_pos / gt_pos scattered in (point_utils.gradient / get_surface_normal,
+// src/utils/point_utils.py:208-235).  The reference builds two full [B,3,H,W] normal images and three gradient images
+// and then gathers R pixels from each; here one thread per miss pixel evaluates its two normals from the 3 neighbouring
+// points directly.  ray_part[r] = {(1 - cos)/2, acos(clamp(cos)), |dx|^2, |dy|^2, 0, 0} -> k_ray_loss_reduce.
+// ------------------------------------------------------------------------------------------------
+__global__ void k_img_scatter(const float* __restrict__ pred_pos, const float* __restrict__ gt_pos, const int64_t* __restrict__ bid,
+                              const int64_t* __restrict__ flat, int64_t R, int64_t HW, float* __restrict__ pred_pcl,
+                              float* __restrict__ gt_pcl) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t o = (bid[r] * HW + flat[r]) * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) { pred_pcl[o + k] = pred_pos[r * 3 + k]; gt_pcl[o + k] = gt_pos[r * 3 + k]; }
+}
+
+// forward differences (zero in the last column / row), cross product, n / (|n| + 1e-8)
+__device__ __forceinline__ void img_normal_at(const float* __restrict__ pcl, int64_t b, int y, int x, int H, int W, float (&n)[3],
+                                              float (&dx)[3], float (&dy)[3]) {
+  const float* p = pcl + ((b * H + y) * (int64_t)W + x) * 3;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) {
+    dx[k] = x == W - 1 ? 0.f : __fsub_rn(p[3 + k], p[k]);
+    dy[k] = y == H - 1 ? 0.f : __fsub_rn(p[(int64_t)W * 3 + k], p[k]);
+  }
+  // torch.cross evaluates a_i b_j - a_j b_i as fma(a_i, b_j, -round(a_j b_i)) (compiler contraction, CPU and CUDA builds
+  // alike).  It matters: where dx == dy (both neighbours are rays without a pair, pred_pos = 0) the result is the rounding
+  // error of one product instead of 0, and the normalisation below blows it up to a near-unit vector.
+  n[0] = fmaf(dx[1], dy[2], -__fmul_rn(dx[2], dy[1]));
+  n[1] = fmaf(dx[2], dy[0], -__fmul_rn(dx[0], dy[2]));
+  n[2] = fmaf(dx[0], dy[1], -__fmul_rn(dx[1], dy[0]));
+  const float len = sqrtf(__fadd_rn(__fadd_rn(__fmul_rn(n[0], n[0]), __fmul_rn(n[1], n[1])), __fmul_rn(n[2], n[2])));
+  const float d = __fadd_rn(len, 1e-8f);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) n[k] = __fdiv_rn(n[k], d);
+}
+
+__global__ void k_img_loss(const float* __restrict__ pred_pcl, const float* __restrict__ gt_pcl, const int64_t* __restrict__ bid,
+                           const int64_t* __restrict__ flat, int64_t R, int H, int W, float* __restrict__ ray_part) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t b = bid[r], f = flat[r];
+  const int y = (int)(f / W), x = (int)(f - (int64_t)y * W);
+  float pn[3], gn[3], dx[3], dy[3], t0[3], t1[3];
+  img_normal_at(gt_pcl, b, y, x, H, W, gn, t0, t1);
+  img_normal_at(pred_pcl, b, y, x, H, W, pn, dx, dy);
+  // F.cosine_similarity (torch 2.x): sum((a / max(|a|, eps)) * (b / max(|b|, eps))), eps = 1e-8
+  const float na = fmaxf(sqrtf(pn[0] * pn[0] + pn[1] * pn[1] + pn[2] * pn[2]), 1e-8f);
+  const float nb = fmaxf(sqrtf(gn[0] * gn[0] + gn[1] * gn[1] + gn[2] * gn[2]), 1e-8f);
+  float cosv = 0.f;
+#pragma unroll
+  for (int k = 0; k < 3; ++k) cosv += (pn[k] / na) * (gn[k] / nb);
+  float* o = ray_part + r * LIDF_LOSS_NSTAT;
+  o[0] = (1.f - cosv) / 2.f;
+  o[1] = acosf(fminf(fmaxf(cosv, -1.f), 1.f));
+  o[2] = dx[0] * dx[0] + dx[1] * dx[1] + dx[2] * dx[2];
+  o[3] = dy[0] * dy[0] + dy[1] * dy[1] + dy[2] * dy[2];
+  o[4] = 0.f; o[5] = 0.f;
+}
+
+// optional: the full normal image [B,3,H,W] (data_dict['pred_surf_norm_img'] / ['gt_surf_norm_img'], pipeline.py:609-611)
+__global__ void k_img_normals(const float* __restrict__ pcl, int B, int H, int W, float* __restrict__ out) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t HW = (int64_t)H * W;
+  if (i >= B * HW) return;
+  const int64_t b = i / HW, f = i - b * HW;
+  const int y = (int)(f / W), x = (int)(f - (int64_t)y * W);
+  float n[3], dx[3], dy[3];
+  img_normal_at(pcl, b, y, x, H, W, n, dx, dy);
+#pragma unroll
+  for (int k = 0; k < 3; ++k) out[(b * 3 + k) * HW + f] = n[k];
+}

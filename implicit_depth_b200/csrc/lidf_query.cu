@@ -272,6 +272,49 @@ extern "C" int lidf_ray_loss(const float* logit, const float* soft, const int64_
   return LIDF_OK;
 }
 
+extern "C" size_t lidf_image_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int64_t R) {
+  if (B <= 0 || H <= 0 || W <= 0 || R < 0) return 0;
+  Bump b{nullptr, 0};
+  b.take<float>((size_t)B * H * W * 3); b.take<float>((size_t)B * H * W * 3);
+  b.take<float>((size_t)(R > 0 ? R : 1) * LIDF_LOSS_NSTAT);
+  b.take<double>((size_t)LIDF_LOSS_BLOCKS * LIDF_LOSS_NSTAT);
+  b.take<unsigned>(1);
+  return b.off + 256;
+}
+
+extern "C" int lidf_image_loss(const float* xyz_flat, const int64_t* bid, const int64_t* flat, const float* pred_pos,
+                               const float* gt_pos, int32_t B, int32_t H, int32_t W, int64_t R, float* pred_img, float* gt_img,
+                               double* stats, void* ws, size_t ws_bytes, lidf_stream_t stream) {
+  if (!xyz_flat || !stats || !ws) return LIDF_ERR_NULL;
+  if (B <= 0 || H <= 0 || W <= 0 || R < 0) return LIDF_ERR_ARG;
+  if (R > 0 && (!bid || !flat || !pred_pos || !gt_pos)) return LIDF_ERR_NULL;
+  if (ws_bytes < lidf_image_loss_workspace_bytes(B, H, W, R)) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  const size_t npix = (size_t)B * H * W;
+  Bump b{(char*)ws, 0};
+  float* pred_pcl = b.take<float>(npix * 3);
+  float* gt_pcl = b.take<float>(npix * 3);
+  float* ray_part = b.take<float>((size_t)(R > 0 ? R : 1) * LIDF_LOSS_NSTAT);
+  double* block_part = b.take<double>((size_t)LIDF_LOSS_BLOCKS * LIDF_LOSS_NSTAT);
+  unsigned* done = b.take<unsigned>(1);
+  LIDF_CUDA(cudaMemsetAsync(stats, 0, sizeof(double) * LIDF_LOSS_NSTAT, st));
+  LIDF_CUDA(cudaMemcpyAsync(pred_pcl, xyz_flat, sizeof(float) * npix * 3, cudaMemcpyDeviceToDevice, st));   // .clone(), :496-500
+  LIDF_CUDA(cudaMemcpyAsync(gt_pcl, xyz_flat, sizeof(float) * npix * 3, cudaMemcpyDeviceToDevice, st));
+  if (R > 0) {
+    k_img_scatter<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(pred_pos, gt_pos, bid, flat, R, (int64_t)H * W, pred_pcl, gt_pcl);
+    LIDF_LAUNCH_CHECK();
+    k_img_loss<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(pred_pcl, gt_pcl, bid, flat, R, H, W, ray_part);
+    LIDF_LAUNCH_CHECK();
+    LIDF_CUDA(cudaMemsetAsync(done, 0, sizeof(unsigned), st));
+    const int nb = (int)(R < LIDF_LOSS_BLOCKS ? R : LIDF_LOSS_BLOCKS);
+    k_ray_loss_reduce<<<nb, 256, 0, st>>>(ray_part, R, block_part, done, stats);
+    LIDF_LAUNCH_CHECK();
+  }
+  if (pred_img) { k_img_normals<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(pred_pcl, B, H, W, pred_img); LIDF_LAUNCH_CHECK(); }
+  if (gt_img) { k_img_normals<<<(unsigned)((npix + 255) / 256), 256, 0, st>>>(gt_pcl, B, H, W, gt_img); LIDF_LAUNCH_CHECK(); }
+  return LIDF_OK;
+}
+
 // -------------------------------------------------------------------------------------------------
 namespace {
 

@@ -66,6 +66,7 @@ EXPORTED_SYMBOLS = [
     "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
     "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
+    "lidf_image_loss_workspace_bytes", "lidf_image_loss",
 ]
 # include/lidf_pointnet.h (bound by models/pointnet.py)
 EXPORTED_SYMBOLS_POINTNET = ["lidf_pointnet_workspace_bytes", "lidf_pointnet_forward"]
@@ -110,6 +111,10 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_ray_loss.restype = C.c_int
     lib.lidf_ray_loss.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_void_p,
                                   C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.lidf_image_loss_workspace_bytes.restype = C.c_size_t
+    lib.lidf_image_loss_workspace_bytes.argtypes = [C.c_int32, C.c_int32, C.c_int32, C.c_int64]
+    lib.lidf_image_loss.restype = C.c_int
+    lib.lidf_image_loss.argtypes = [C.c_void_p] * 5 + [C.c_int32, C.c_int32, C.c_int32, C.c_int64] + [C.c_void_p] * 4 + [C.c_size_t, C.c_void_p]
     lib.lidf_query_last_mlp_ms.restype = C.c_float
     lib.lidf_tc_selftest.restype = C.c_int
     lib.lidf_tc_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int32, C.c_void_p]
@@ -603,6 +608,33 @@ class _LidfQuery:
         if gt_pos is not None:
             out["pos_loss"] = (stats[3] / max(3 * R, 1)).float()
             out["err"] = torch.where(stats[5] > 0, stats[4] / stats[5].clamp_min(1), torch.zeros_like(stats[4])).float()
+        return out
+
+    def image_loss(self, xyz_flat, miss_bid, miss_flat_img_id, pred_pos, gt_pos, h: int, w: int, want_normal_imgs: bool = False):
+        """The image-space terms of LIDF.compute_loss (pipeline.py:494-541): returns 0-dim tensors surf_norm_loss, angle_err
+        (degrees), smooth_loss (no host sync) and, on request, the two [B,3,H,W] surface-normal images."""
+        dev = xyz_flat.device
+        B, R = int(xyz_flat.shape[0]), int(miss_bid.shape[0])
+        if tuple(xyz_flat.shape) != (B, h * w, 3):
+            raise RuntimeError("xyz_flat must be [B, h*w, 3]")
+        stats = torch.empty(6, dtype=torch.float64, device=dev)
+        imgs = [torch.empty(B, 3, h, w, dtype=torch.float32, device=dev) for _ in range(2)] if want_normal_imgs else [None, None]
+        nbytes = int(self.lib.lidf_image_loss_workspace_bytes(B, h, w, R))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.lidf_image_loss(_chk(xyz_flat, "xyz_flat", torch.float32), _chk(miss_bid, "miss_bid", torch.int64),
+                                          _chk(miss_flat_img_id, "miss_flat_img_id", torch.int64),
+                                          _chk(pred_pos, "pred_pos", torch.float32), _chk(gt_pos, "gt_pos", torch.float32),
+                                          B, int(h), int(w), R, imgs[0].data_ptr() if want_normal_imgs else None,
+                                          imgs[1].data_ptr() if want_normal_imgs else None, stats.data_ptr(), ws.data_ptr(), nbytes,
+                                          C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_image_loss")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        n = max(R, 1)
+        out = dict(stats=stats, surf_norm_loss=(stats[0] / n).float(), angle_err=(stats[1] / n * (180.0 / math.pi)).float(),
+                   smooth_loss=((stats[2] + stats[3]) / n).float())
+        if want_normal_imgs:
+            out["pred_surf_norm_img"], out["gt_surf_norm_img"] = imgs
         return out
 
 

@@ -125,6 +125,44 @@ class LIDFQueryMixin:
                                    data_dict['pcl_label_float'].contiguous(), int(data_dict['total_miss_sample_num']),
                                    data_dict['pred_pos'].contiguous(), data_dict['gt_pos'].float().contiguous())
 
+    def compute_loss_eval(self, data_dict, exp_type, epoch):
+        """Forward-only mirror of ``LIDF.compute_loss`` (reference pipeline.py:468-650) for evaluation / logging, shipped
+        setting ``hard_neg: False``: the ray-keyed terms come from ``lidf_ray_loss``, the image-space terms from
+        ``lidf_image_loss``; ``loss_net`` is assembled with the same weights and epoch gates (:538-543).  Returns the
+        reference's ``loss_dict`` keys as 0-dim tensors (no host sync).  For ``exp_type != 'train'`` the depth metrics
+        (:570-606) are added for ``bs != 1``; the ``bs == 1`` variant resamples through cv2 on the host and is left to the
+        reference code.  Training needs gradients and keeps using the reference's ``compute_loss``."""
+        L = self.opt.loss
+        if getattr(L, 'hard_neg', False):
+            raise NotImplementedError('compute_loss_eval covers hard_neg: False (the shipped lidf YAMLs)')
+        bs, h, w = data_dict['bs'], data_dict['h'], data_dict['w']
+        ray = self.compute_ray_loss(data_dict)
+        xyz = data_dict['xyz_flat'] if exp_type == 'train' else data_dict['xyz_corrupt_flat']      # :494-500
+        img = lidf_query.image_loss(xyz.float().contiguous(), data_dict['miss_bid'].long().contiguous(),
+                                    data_dict['miss_flat_img_id'].long().contiguous(), data_dict['pred_pos'].contiguous(),
+                                    data_dict['gt_pos'].float().contiguous(), h, w, want_normal_imgs=True)
+        loss_net = L.pos_w * ray['pos_loss'] + L.prob_w * ray['prob_loss']
+        if L.surf_norm_w > 0 and epoch >= L.surf_norm_epo:
+            loss_net = loss_net + L.surf_norm_w * img['surf_norm_loss']
+        if L.smooth_w > 0 and epoch >= L.smooth_epo:
+            loss_net = loss_net + L.smooth_w * img['smooth_loss']
+        data_dict.update({'gt_surf_norm_img': img['gt_surf_norm_img'], 'pred_surf_norm_img': img['pred_surf_norm_img']})
+        loss_dict = {'pos_loss': ray['pos_loss'], 'prob_loss': ray['prob_loss'], 'surf_norm_loss': img['surf_norm_loss'],
+                     'smooth_loss': img['smooth_loss'], 'loss_net': loss_net, 'acc': ray['acc'], 'err': ray['err'],
+                     'angle_err': img['angle_err']}
+        if exp_type != 'train' and bs != 1:
+            keep = torch.sum(data_dict['gt_pos'].abs(), dim=-1) != 0                                # zero_mask, :560-568
+            pred, gt = data_dict['pred_pos'][:, 2][keep], data_dict['gt_pos'][:, 2][keep]
+            safe_log = lambda x: torch.log(torch.clamp(x, 1e-6, 1e6))
+            thresh = torch.max(gt / pred, pred / gt)
+            loss_dict.update({'a1': (thresh < 1.05).float().mean(), 'a2': (thresh < 1.10).float().mean(),
+                              'a3': (thresh < 1.25).float().mean(), 'rmse': ((gt - pred) ** 2).mean().sqrt(),
+                              'rmse_log': ((safe_log(gt) - safe_log(pred)) ** 2).mean().sqrt(),
+                              'log10': (safe_log(gt) - safe_log(pred)).abs().mean(),       # sic: the reference's safe_log10 is log
+                              'abs_rel': ((gt - pred).abs() / gt).mean(), 'mae': (gt - pred).abs().mean(),
+                              'sq_rel': ((gt - pred) ** 2 / gt).mean()})
+        return loss_dict
+
     def get_pred(self, data_dict, exp_type, epoch):
         if self.opt.model.scatter_type != 'Maxpool':
             raise NotImplementedError('Does not support Scatter Type: {}'.format(self.opt.model.scatter_type))
@@ -375,7 +413,9 @@ def default_opt(**over):
                   pnet_in=6, pnet_gf=32, pnet_pos_type='rel', pnet_model_type='twostage', perturb=False, perturb_prob=0.,
                   use_all_pix=True)
     grid = dict(res=8, offset_range=[0., 1.])
+    loss = dict(pos_loss_type='single', prob_loss_type='ray', hard_neg=False, hard_neg_ratio=None, pos_w=100.0, prob_w=0.5,
+                surf_norm_w=10.0, surf_norm_epo=0, smooth_w=0.0, smooth_epo=0)
     for k, v in over.items():
         sect, key = k.split('.')
-        {'model': model, 'refine': refine, 'grid': grid}[sect][key] = v
-    return _NS(model=_NS(**model), refine=_NS(**refine), grid=_NS(**grid), gpu_id=0, mask_type='all')
+        {'model': model, 'refine': refine, 'grid': grid, 'loss': loss}[sect][key] = v
+    return _NS(model=_NS(**model), refine=_NS(**refine), grid=_NS(**grid), loss=_NS(**loss), gpu_id=0, mask_type='all')

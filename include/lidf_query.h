@@ -178,6 +178,17 @@ int lidf_ray_loss(const float* pred_prob_end, const float* pred_prob_end_softmax
                   float* log_softmax, int64_t* pred_label, int64_t* gt_label, double* stats,
                   void* workspace, size_t workspace_bytes, lidf_stream_t stream);
 
+/* The image-space terms of LIDF.compute_loss (pipeline.py:494-541; point_utils.gradient / get_surface_normal,
+ * src/utils/point_utils.py:208-235): xyz_flat [B,H*W,3] (xyz_flat for 'train', xyz_corrupt_flat otherwise) with pred_pos /
+ * gt_pos [R,3] scattered in at (miss_bid, miss_flat_img_id), forward-difference surface normals, and at the R miss pixels
+ *   stats [6] (device, double) = {sum (1 - cos)/2, sum acos(clamp(cos)) [rad], sum |dx|^2, sum |dy|^2, 0, 0}
+ * so that surf_norm_loss = stats[0]/R, angle_err = stats[1]/R * 180/pi, smooth_loss = (stats[2] + stats[3])/R.
+ * Optional outputs (NULL to skip): the two full normal images [B,3,H,W] the reference stores in data_dict (:609-611). */
+size_t lidf_image_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int64_t R);
+int lidf_image_loss(const float* xyz_flat, const int64_t* miss_bid, const int64_t* miss_flat_img_id, const float* pred_pos,
+                    const float* gt_pos, int32_t B, int32_t H, int32_t W, int64_t R, float* pred_surf_norm_img,
+                    float* gt_surf_norm_img, double* stats, void* workspace, size_t workspace_bytes, lidf_stream_t stream);
+
 /* unit test of the tcgen05 primitives the decoder engine is built from (tcgen05.st operand staging, TMA weight chunks,
  * TS-mode tcgen05.mma with the 3-product bf16 split, tcgen05.ld): D[128,128] = A[128,32] * W[128,32]^T, fp32 device
  * arrays; scratch >= 16 KB device memory.  variant 0 = the layout the engine uses; 1 = LBO/SBO swapped (must be wrong). */

@@ -257,6 +257,47 @@ def ray_loss_stats(pred_prob_end: torch.Tensor, pred_prob_end_softmax: torch.Ten
     return out
 
 
+def image_gradient(x: torch.Tensor):
+    """point_utils.gradient (/root/reference/src/utils/point_utils.py:208-227): forward differences, zero in the last
+    column (dx) / last row (dy).  x: [b,c,h,w]."""
+    right = F.pad(x, [0, 1, 0, 0])[:, :, :, 1:]
+    bottom = F.pad(x, [0, 0, 0, 1])[:, :, 1:, :]
+    dx, dy = right - x, bottom - x
+    dx[:, :, :, -1] = 0
+    dy[:, :, -1, :] = 0
+    return dx, dy
+
+
+def surface_normal(x: torch.Tensor):
+    """point_utils.get_surface_normal (point_utils.py:229-235)."""
+    dx, dy = image_gradient(x)
+    n = torch.cross(dx, dy, dim=1)
+    n = n / (torch.norm(n, dim=1, keepdim=True) + 1e-8)
+    return n, dx, dy
+
+
+def image_loss_stats(xyz_flat: torch.Tensor, miss_bid: torch.Tensor, miss_flat_img_id: torch.Tensor, pred_pos: torch.Tensor,
+                     gt_pos: torch.Tensor, bs: int, h: int, w: int) -> Dict[str, torch.Tensor]:
+    """The image-space part of LIDF.compute_loss (hard_neg False): pipeline.py:494-541 -- surface-normal loss, angle error
+    and smoothness loss at the miss pixels of the point image with pred_pos / gt_pos scattered in.  ``xyz_flat`` [bs,h*w,3]
+    is xyz_flat (train) or xyz_corrupt_flat (otherwise), :495-500."""
+    gt_pcl = xyz_flat.clone(); pred_pcl = xyz_flat.clone()
+    gt_pcl[miss_bid, miss_flat_img_id] = gt_pos                                           # :501
+    gt_n, _, _ = surface_normal(gt_pcl.reshape(bs, h, w, 3).permute(0, 3, 1, 2).contiguous())
+    gt_sn = gt_n.permute(0, 2, 3, 1).contiguous().reshape(bs, h * w, 3)[miss_bid, miss_flat_img_id]
+    pred_pcl[miss_bid, miss_flat_img_id] = pred_pos                                       # :507
+    pred_n, dx, dy = surface_normal(pred_pcl.reshape(bs, h, w, 3).permute(0, 3, 1, 2).contiguous())
+    pred_sn = pred_n.permute(0, 2, 3, 1).contiguous().reshape(bs, h * w, 3)[miss_bid, miss_flat_img_id]
+    cosine_val = F.cosine_similarity(pred_sn, gt_sn, dim=-1)                              # :514
+    surf_norm_loss = torch.mean((1 - cosine_val) / 2.)                                    # :515-517
+    angle_err = torch.mean(torch.acos(torch.clamp(cosine_val, min=-1, max=1))) / math.pi * 180.   # :523-524
+    dxd = torch.sum(dx * dx, 1).reshape(bs, h * w)[miss_bid, miss_flat_img_id]            # :527-529
+    dyd = torch.sum(dy * dy, 1).reshape(bs, h * w)[miss_bid, miss_flat_img_id]            # :531-533
+    smooth_loss = torch.mean(dxd) + torch.mean(dyd)                                       # :536
+    return dict(surf_norm_loss=surf_norm_loss, angle_err=angle_err, smooth_loss=smooth_loss, pred_surf_norm_img=pred_n,
+                gt_surf_norm_img=gt_n, cosine_val=cosine_val)
+
+
 # --------------------------------------------------------------------------- #
 # pipeline.py : LIDF.get_embedding + LIDF.get_pred
 # --------------------------------------------------------------------------- #

@@ -47,10 +47,14 @@ def run(src_name, out_name, seed, zero_frac=0.1, label_frac=0.2):
     out = os.path.join(HERE, out_name + ".npz")
     np.savez_compressed(out, pred_prob_end=z["ref.pred_prob_end"], pred_prob_end_softmax=z["ref.pred_prob_end_softmax"],
                         miss_ray_intersect_idx=z["miss_ray_intersect_idx"], pcl_label=label.numpy().astype(np.int32),
-                        pred_pos=pred_pos.numpy(), gt_pos=gt_pos.numpy(), R=R,
+                        pred_pos=pred_pos.numpy(), gt_pos=gt_pos.numpy(), R=R, B=B, H=H, W=W,
+                        xyz_flat=dd["xyz_flat"].numpy(), miss_bid=z["miss_bid"], miss_flat_img_id=dd["miss_flat_img_id"].numpy().astype(np.int32),
+                        ref_pred_surf_norm_img=dd["pred_surf_norm_img"].numpy(), ref_gt_surf_norm_img=dd["gt_surf_norm_img"].numpy(),
+                        ref_surf_norm_loss=np.float64(float(loss["surf_norm_loss"])), ref_smooth_loss=np.float64(float(loss["smooth_loss"])),
+                        ref_angle_err=np.float64(float(loss["angle_err"])), ref_loss_net=np.float64(float(loss["loss_net"])),
                         ref_log_softmax=lsm.numpy(), ref_pred_label=pred_label.numpy(), ref_gt_label=gt_label.numpy(),
                         **{"ref_" + k: np.float64(float(loss[k])) for k in ("pos_loss", "prob_loss", "acc", "err")})
-    print(out_name, {k: float(loss[k]) for k in ("pos_loss", "prob_loss", "acc", "err")}, "P", P, "R", R,
+    print(out_name, {k: float(loss[k]) for k in ("pos_loss", "prob_loss", "acc", "err", "surf_norm_loss", "smooth_loss", "angle_err")}, "P", P, "R", R,
           "empty rays", int((pred_label == P).sum()))
 
 

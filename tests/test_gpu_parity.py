@@ -615,3 +615,66 @@ def test_get_pred_refine_mirror_vs_reference_output():
                                   dict(O.REFINE_CFG, offset_range=tuple(float(v) for v in extra["refine.offset_range"]),
                                        n_iter=extra["refine.n_iter"]), rdec)
     assert rel_err(out2.cpu(), want2) < TOL_TC
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# image-space loss terms (surface normals, smoothness) of LIDF.compute_loss
+@pytest.mark.parametrize("name", ["loss_ief_ragged_2x24x32", "loss_c1_imnet_64x64x16"])
+def test_image_loss_vs_reference_compute_loss(name):
+    from test_oracle import load_loss
+    t, sc, R = load_loss(name)
+    H, W = int(sc["H"]), int(sc["W"])
+    out = _lq().image_loss(t["xyz_flat"].cuda(), t["miss_bid"].cuda(), t["miss_flat_img_id"].cuda(), t["pred_pos"].cuda(),
+                           t["gt_pos"].cuda(), H, W, want_normal_imgs=True)
+    for k in ("surf_norm_loss", "smooth_loss", "angle_err"):
+        assert abs(float(out[k]) - sc["ref_" + k]) <= 1e-5 * max(1.0, abs(sc["ref_" + k])), (k, float(out[k]), sc["ref_" + k])
+    assert (out["pred_surf_norm_img"].cpu() - t["ref_pred_surf_norm_img"]).abs().max() < 2e-6      # unit vectors
+    assert (out["gt_surf_norm_img"].cpu() - t["ref_gt_surf_norm_img"]).abs().max() < 2e-6
+
+
+def test_image_loss_partial_miss_set_vs_oracle():
+    """Only some pixels are miss rays (the rest keep the sensor's xyz), unsorted ray order, 1-pixel-wide images."""
+    g = torch.Generator().manual_seed(9)
+    for B, H, W, frac in [(2, 17, 23, 0.3), (1, 1, 40, 0.5), (1, 40, 1, 0.5), (3, 9, 9, 1.0), (1, 5, 5, 0.0)]:
+        xyz = torch.randn(B, H * W, 3, generator=g)
+        mask = torch.rand(B, H * W, generator=g) < frac
+        idx = torch.nonzero(mask, as_tuple=False)
+        idx = idx[torch.randperm(idx.shape[0], generator=g)]
+        bid, flat = idx[:, 0].contiguous(), idx[:, 1].contiguous()
+        R = bid.shape[0]
+        pred = torch.randn(R, 3, generator=g); gt = pred + 0.1 * torch.randn(R, 3, generator=g)
+        got = _lq().image_loss(xyz.cuda(), bid.cuda(), flat.cuda(), pred.cuda(), gt.cuda(), H, W, want_normal_imgs=True)
+        if R == 0:
+            assert float(got["stats"].abs().sum()) == 0.0
+            continue
+        want = O.image_loss_stats(xyz, bid, flat, pred, gt, B, H, W)
+        for k in ("surf_norm_loss", "smooth_loss", "angle_err"):
+            assert abs(float(got[k]) - float(want[k])) <= 1e-5 * max(1.0, abs(float(want[k]))), (k, B, H, W)
+        assert (got["pred_surf_norm_img"].cpu() - want["pred_surf_norm_img"]).abs().max() < 2e-6
+
+
+@pytest.mark.parametrize("name", ["loss_ief_ragged_2x24x32", "loss_c1_imnet_64x64x16"])
+def test_compute_loss_eval_mirror_vs_reference_loss_dict(name):
+    """LIDFQueryMixin.compute_loss_eval: every scalar of the reference's loss_dict (train branch), incl. loss_net."""
+    from test_oracle import load_loss
+    from implicit_depth_b200.models.pipeline import LIDF, default_opt
+    t, sc, R = load_loss(name)
+    B, H, W = int(sc["B"]), int(sc["H"]), int(sc["W"])
+    lidf = LIDF(default_opt(), torch.device("cuda"))
+    dd = dict(bs=B, h=H, w=W, total_miss_sample_num=R, pred_prob_end=t["pred_prob_end"].cuda(),
+              pred_prob_end_softmax=t["pred_prob_end_softmax"].cuda(), miss_ray_intersect_idx=t["miss_ray_intersect_idx"].cuda(),
+              pcl_label_float=t["pcl_label"].float().cuda(), pred_pos=t["pred_pos"].cuda(), gt_pos=t["gt_pos"].cuda(),
+              xyz_flat=t["xyz_flat"].cuda(), xyz_corrupt_flat=t["xyz_flat"].cuda(), miss_bid=t["miss_bid"].cuda(),
+              miss_flat_img_id=t["miss_flat_img_id"].cuda())
+    loss = lidf.compute_loss_eval(dd, "train", 0)
+    assert set(loss) == {"pos_loss", "prob_loss", "surf_norm_loss", "smooth_loss", "loss_net", "acc", "err", "angle_err"}
+    for k, v in loss.items():
+        assert abs(float(v) - sc["ref_" + k]) <= 1e-5 * max(1.0, abs(sc["ref_" + k])), (k, float(v), sc["ref_" + k])
+    assert dd["pred_surf_norm_img"].shape == (B, 3, H, W)
+    ev = lidf.compute_loss_eval(dd, "test", 0)                  # bs != 1 for the first fixture: depth metrics appear
+    if B != 1:
+        assert {"a1", "a2", "a3", "rmse", "rmse_log", "log10", "abs_rel", "mae", "sq_rel"} <= set(ev)
+        keep = t["gt_pos"].abs().sum(-1) != 0
+        assert abs(float(ev["mae"]) - float((t["gt_pos"][:, 2][keep] - t["pred_pos"][:, 2][keep]).abs().mean())) < 1e-6
+    else:
+        assert "a1" not in ev

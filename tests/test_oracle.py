@@ -108,7 +108,9 @@ def load_loss(name):
     z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
     t = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim > 0}
     t["miss_ray_intersect_idx"] = t["miss_ray_intersect_idx"].long(); t["pcl_label"] = t["pcl_label"].long()
-    sc = {k: float(z[k]) for k in ("ref_pos_loss", "ref_prob_loss", "ref_acc", "ref_err")}
+    sc = {k: float(z[k]) for k in ("ref_pos_loss", "ref_prob_loss", "ref_acc", "ref_err", "ref_surf_norm_loss", "ref_smooth_loss",
+                                   "ref_angle_err", "ref_loss_net", "B", "H", "W")}
+    t["miss_bid"] = t["miss_bid"].long(); t["miss_flat_img_id"] = t["miss_flat_img_id"].long()
     return t, sc, int(z["R"])
 
 
@@ -142,3 +144,14 @@ def test_pointnet_oracle_matches_reference_module(name):
     out = O.pointnet2stage_forward(w, inp, idx, V)
     assert out.shape == ref.shape == (V, 128)
     assert rel_err(out, ref) < 2e-6
+
+
+@pytest.mark.parametrize("name", LOSS_CASES)
+def test_image_loss_oracle_matches_reference_compute_loss(name):
+    """surf_norm_loss / smooth_loss / angle_err and both normal images from the reference's own compute_loss."""
+    t, sc, R = load_loss(name)
+    out = O.image_loss_stats(t["xyz_flat"], t["miss_bid"], t["miss_flat_img_id"], t["pred_pos"], t["gt_pos"],
+                             int(sc["B"]), int(sc["H"]), int(sc["W"]))
+    assert torch.equal(out["pred_surf_norm_img"], t["ref_pred_surf_norm_img"]) and torch.equal(out["gt_surf_norm_img"], t["ref_gt_surf_norm_img"])
+    for k in ("surf_norm_loss", "smooth_loss", "angle_err"):
+        assert abs(float(out[k]) - sc["ref_" + k]) <= 2e-6 * max(1.0, abs(sc["ref_" + k])), k
