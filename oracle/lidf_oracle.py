@@ -18,11 +18,19 @@ against the reference source (paths relative to /root/reference):
   get_embedding         src/models/pipeline.py:338-425 (minus resnet_model :370, pnet_model :407)
   get_pred              src/models/pipeline.py:427-466
   refine_decoder_tail   src/models/pipeline.py:1018-1029
+  scatter_log_softmax, ray_loss_stats
+                        src/models/pipeline.py:472,482-486,553-567 (compute_loss, ray-keyed terms)
+  image_gradient, surface_normal, image_loss_stats
+                        src/utils/point_utils.py:208-235, src/models/pipeline.py:494-541 (compute_loss, image-space terms)
+  pointnet2stage_forward
+                        src/models/pointnet.py:22-38
+  (the geometry ops -- ray_aabb, pcl_aabb, voxelisation -- are restated in oracle/aabb_oracle.py)
 
 Parity pinning: the reference ships no tests / golden vectors for this path
 (SURVEY.md section 4), so this oracle is pinned against outputs of the reference's own
 unmodified ``LIDF.get_embedding`` + ``LIDF.get_pred`` executed in the build
-container (tests/golden/make_golden.py -> tests/golden/*.npz) and against
+container (tests/golden/make_golden.py -> tests/golden/*.npz), of its ``compute_loss``
+(make_golden_loss.py) and of its ``PointNet2Stage`` (make_golden_pointnet.py), and against
 torchvision's ``roi_align`` (tests/test_oracle.py).
 
 All functions are dtype-generic: pass float64 tensors to get an error budget
