@@ -236,10 +236,11 @@ k_roi_align_rays(const float* __restrict__ feat, const float* __restrict__ box, 
     float o[4];
     if (interior) {
       const float* bc = box + plane0 + (size_t)c * H * W + (size_t)(py - 4) * W + (px - 4);
-      o[0] = __ldg(bc) / count;
-      o[1] = __ldg(bc + 4) / count;
-      o[2] = __ldg(bc + (size_t)4 * W) / count;
-      o[3] = __ldg(bc + (size_t)4 * W + 4) / count;
+      // interior: gh = gw = 4, count = 16 -- dividing by a power of two is the same IEEE result as multiplying by 1/16
+      o[0] = __ldg(bc) * 0.0625f;
+      o[1] = __ldg(bc + 4) * 0.0625f;
+      o[2] = __ldg(bc + (size_t)4 * W) * 0.0625f;
+      o[3] = __ldg(bc + (size_t)4 * W + 4) * 0.0625f;
     } else {
       roi_channel_general(feat + plane0 + (size_t)c * H * W, H, W, sw, sh, bw, bh, gw, gh, count, o);
     }
