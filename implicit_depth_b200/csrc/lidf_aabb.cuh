@@ -55,13 +55,18 @@ __device__ __forceinline__ bool aabb_inside(float x, float y, float z, const Aab
   return true;
 }
 
-// ---- pre-pass: reciprocal directions + image-id range of every 1024-ray tile ------------------------------------
+// ---- pre-pass: reciprocal directions + image-id range + direction bounds of every 1024-ray tile ---------------------
+// tile_tan[rb] = (min dx/dz, max dx/dz, min dy/dz, max dy/dz) over the tile's rays, or (-inf, +inf, -inf, +inf) when some
+// ray of the tile does not look down +z: a conservative "frustum" of the tile used to cull (voxel, tile) work items.
 __global__ void __launch_bounds__(AABB_THREADS) k_aabb_ray_prep(const float* __restrict__ ray_dir, const int32_t* __restrict__ ray_bid,
-                                                                int64_t R, float* __restrict__ inv, int2* __restrict__ tile_bid) {
-  __shared__ int s_min, s_max;
-  if (threadIdx.x == 0) { s_min = INT_MAX; s_max = INT_MIN; }
+                                                                int64_t R, float* __restrict__ inv, int2* __restrict__ tile_bid,
+                                                                float4* __restrict__ tile_tan) {
+  __shared__ int s_min, s_max, s_bad;
+  __shared__ float s_t[AABB_WARPS][4];
+  if (threadIdx.x == 0) { s_min = INT_MAX; s_max = INT_MIN; s_bad = 0; }
   __syncthreads();
-  int lo = INT_MAX, hi = INT_MIN;
+  int lo = INT_MAX, hi = INT_MIN, bad = 0;
+  float t[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
   const int64_t base = (int64_t)blockIdx.x * AABB_TILE;
 #pragma unroll
   for (int j = 0; j < AABB_RPT; ++j) {
@@ -69,27 +74,95 @@ __global__ void __launch_bounds__(AABB_THREADS) k_aabb_ray_prep(const float* __r
     if (r < R) {
       const int b = ray_bid[r];
       lo = min(lo, b); hi = max(hi, b);
+      float d[3];
 #pragma unroll
-      for (int a = 0; a < 3; ++a)       // float(1 / (double(d) + 1e-12)): ray_aabb_cuda_kernel.cu:32,48,67
-        inv[r * 3 + a] = __double2float_rn(1.0 / ((double)ray_dir[r * 3 + a] + 1e-12));
+      for (int a = 0; a < 3; ++a) {     // float(1 / (double(d) + 1e-12)): ray_aabb_cuda_kernel.cu:32,48,67
+        d[a] = ray_dir[r * 3 + a];
+        inv[r * 3 + a] = __double2float_rn(1.0 / ((double)d[a] + 1e-12));
+      }
+      if (d[2] > 1e-6f && isfinite(d[0]) && isfinite(d[1])) {
+        const float tx = d[0] / d[2], ty = d[1] / d[2];
+        t[0] = fminf(t[0], tx); t[1] = fmaxf(t[1], tx); t[2] = fminf(t[2], ty); t[3] = fmaxf(t[3], ty);
+      } else {
+        bad = 1;
+      }
     }
   }
   lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
-  if ((threadIdx.x & 31) == 0) { atomicMin(&s_min, lo); atomicMax(&s_max, hi); }
+  bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    t[0] = fminf(t[0], __shfl_xor_sync(0xffffffffu, t[0], o)); t[1] = fmaxf(t[1], __shfl_xor_sync(0xffffffffu, t[1], o));
+    t[2] = fminf(t[2], __shfl_xor_sync(0xffffffffu, t[2], o)); t[3] = fmaxf(t[3], __shfl_xor_sync(0xffffffffu, t[3], o));
+  }
+  if ((threadIdx.x & 31) == 0) {
+    atomicMin(&s_min, lo); atomicMax(&s_max, hi);
+    if (bad) atomicOr(&s_bad, 1);
+#pragma unroll
+    for (int k = 0; k < 4; ++k) s_t[threadIdx.x >> 5][k] = t[k];
+  }
   __syncthreads();
-  if (threadIdx.x == 0) tile_bid[blockIdx.x] = make_int2(s_min, s_max);
+  if (threadIdx.x == 0) {
+    tile_bid[blockIdx.x] = make_int2(s_min, s_max);
+    float4 o = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+    for (int w = 0; w < AABB_WARPS; ++w) {
+      o.x = fminf(o.x, s_t[w][0]); o.y = fmaxf(o.y, s_t[w][1]); o.z = fminf(o.z, s_t[w][2]); o.w = fmaxf(o.w, s_t[w][3]);
+    }
+    if (s_bad) o = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
+    tile_tan[blockIdx.x] = o;
+  }
 }
 
-// ---- compact pair list: count -------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(AABB_THREADS) k_aabb_count(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
-                                                             const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
-                                                             const int2* __restrict__ tile_bid, int64_t R, int64_t RB, int64_t M,
-                                                             int* __restrict__ cnt) {
-  for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
+// Can any ray of the tile meet the box?  A line through the origin with direction d (dz > 0) meets a box with z in
+// [zlo, zhi], zlo > 0, only at points with x/z in [min(xlo/zlo, xlo/zhi), max(xhi/zlo, xhi/zhi)] (same for y), and x/z is
+// dx/dz on the whole line.  The interval is widened by 1e-4 (relative + absolute), four orders of magnitude above the fp32
+// rounding of either side, so the cull never drops a pair the slab test would report.  Boxes that touch z <= 0 and tiles
+// with rays not looking down +z are never culled.
+__device__ __forceinline__ bool aabb_tile_may_hit(const float4 tt, const AabbBox& b) {
+  if (!(b.lo[2] > 1e-6f) || !(b.hi[2] >= b.lo[2]) || !(b.hi[0] >= b.lo[0]) || !(b.hi[1] >= b.lo[1])) return true;
+  const float ilo = 1.0f / b.lo[2], ihi = 1.0f / b.hi[2];
+  const float xl = fminf(b.lo[0] * ilo, b.lo[0] * ihi), xh = fmaxf(b.hi[0] * ilo, b.hi[0] * ihi);
+  const float yl = fminf(b.lo[1] * ilo, b.lo[1] * ihi), yh = fmaxf(b.hi[1] * ilo, b.hi[1] * ihi);
+  const float mx = 1e-4f * (1.0f + fmaxf(fabsf(xl), fabsf(xh))), my = 1e-4f * (1.0f + fmaxf(fabsf(yl), fabsf(yh)));
+  return !(tt.y < xl - mx || tt.x > xh + mx || tt.w < yl - my || tt.z > yh + my);
+}
+
+// ---- compact pair list: live work items --------------------------------------------------------------------------
+// One thread per (voxel, ray-tile) item: keep it if the tile's image-id range contains the voxel's image and the tile's
+// direction bounds can meet the box.  Survivors are appended to `items` (warp-aggregated atomic; the order is irrelevant:
+// an item's output position comes from the scan of cnt[], indexed by the item id).  count / fill then walk only the
+// survivors -- at the bench geometry 4.9 M items shrink to a few 10^5, and the per-item latency chain (two dependent
+// loads + a 64-bit division) disappears from the persistent loops.
+__global__ void k_aabb_items(const float* __restrict__ voxel_bound, const int32_t* __restrict__ voxel_bid,
+                             const int2* __restrict__ tile_bid, const float4* __restrict__ tile_tan, int64_t RB, int64_t M,
+                             int* __restrict__ items, int* __restrict__ n_items) {
+  const int64_t w = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool live = false;
+  if (w < M) {
     const int64_t v = w / RB, rb = w - v * RB;
     const int vbid = __ldg(voxel_bid + v);
     const int2 tb = __ldg(tile_bid + rb);
-    if (vbid < tb.x || vbid > tb.y) { if (threadIdx.x == 0) cnt[w] = 0; continue; }      // block-uniform
+    if (!(vbid < tb.x || vbid > tb.y)) live = aabb_tile_may_hit(__ldg(tile_tan + rb), aabb_load_box(voxel_bound, v));
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (m == 0) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(n_items, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (live) items[base + __popc(m & ((1u << lane) - 1u))] = (int)w;
+}
+
+// ---- compact pair list: count (cnt[] zeroed by the caller; only live items are visited) ---------------------------------
+__global__ void __launch_bounds__(AABB_THREADS) k_aabb_count(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
+                                                             const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
+                                                             const int* __restrict__ items, const int* __restrict__ n_items,
+                                                             int64_t R, int64_t RB, int* __restrict__ cnt) {
+  const int n = *n_items;
+  for (int it = blockIdx.x; it < n; it += gridDim.x) {
+    const int64_t w = items[it];
+    const int64_t v = w / RB, rb = w - v * RB;
+    const int vbid = __ldg(voxel_bid + v);
     const AabbBox box = aabb_load_box(voxel_bound, v);
     int total = 0;
 #pragma unroll
@@ -109,12 +182,15 @@ __global__ void __launch_bounds__(AABB_THREADS) k_aabb_count(const float* __rest
 // ---- compact pair list: fill (torch.nonzero order: voxel, then ray) --------------------------------------------------
 __global__ void __launch_bounds__(AABB_THREADS) k_aabb_fill(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
                                                             const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
-                                                            int64_t R, int64_t RB, int64_t M, const int* __restrict__ start,
+                                                            const int* __restrict__ items, const int* __restrict__ n_items,
+                                                            int64_t R, int64_t RB, const int* __restrict__ start,
                                                             int64_t* __restrict__ pair_vox, int64_t* __restrict__ pair_ray,
                                                             float2* __restrict__ pair_dist) {
   __shared__ int s_off[AABB_RPT * AABB_WARPS];                       // 32 (j, warp) groups, in ray order
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
+  const int n = *n_items;
+  for (int it = blockIdx.x; it < n; it += gridDim.x) {
+    const int64_t w = items[it];
     const int base = __ldg(start + w);
     if (__ldg(start + w + 1) == base) continue;                     // nothing to write for this (voxel, tile)
     const int64_t v = w / RB, rb = w - v * RB;
@@ -160,13 +236,14 @@ __global__ void __launch_bounds__(AABB_THREADS) k_aabb_fill(const float* __restr
 template <bool VEC>
 __global__ void __launch_bounds__(AABB_THREADS) k_aabb_dense(const float* __restrict__ inv, const float* __restrict__ voxel_bound,
                                                              const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
-                                                             const int2* __restrict__ tile_bid, int64_t R, int64_t RB, int64_t M,
-                                                             int* __restrict__ mask, float2* __restrict__ dist) {
+                                                             const int2* __restrict__ tile_bid, const float4* __restrict__ tile_tan,
+                                                             int64_t R, int64_t RB, int64_t M, int* __restrict__ mask,
+                                                             float2* __restrict__ dist) {
   for (int64_t w = blockIdx.x; w < M; w += gridDim.x) {
     const int64_t v = w / RB, rb = w - v * RB;
     const int vbid = __ldg(voxel_bid + v);
     const int2 tb = __ldg(tile_bid + rb);
-    const bool live = !(vbid < tb.x || vbid > tb.y);
+    const bool live = !(vbid < tb.x || vbid > tb.y) && aabb_tile_may_hit(__ldg(tile_tan + rb), aabb_load_box(voxel_bound, v));
     const int64_t r0 = rb * AABB_TILE + 4 * (int64_t)threadIdx.x;
     if (r0 >= R) continue;
     int hit[4] = {0, 0, 0, 0};

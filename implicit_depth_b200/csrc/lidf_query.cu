@@ -621,7 +621,7 @@ extern "C" int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stre
 #include "lidf_aabb.cuh"
 
 namespace {
-struct AabbPlan { int64_t RB, M; int nb; float* inv; int2* tile_bid; int* cnt; int* start; int* block_sums; size_t bytes; };
+struct AabbPlan { int64_t RB, M; int nb; float* inv; int2* tile_bid; float4* tile_tan; int* cnt; int* start; int* block_sums; int* items; int* n_items; size_t bytes; };
 
 int plan_aabb(int64_t R, int64_t V, AabbPlan* q, char* base) {
   if (R < 0 || V < 0) return LIDF_ERR_ARG;
@@ -633,9 +633,12 @@ int plan_aabb(int64_t R, int64_t V, AabbPlan* q, char* base) {
   Bump b{base, 0};
   q->inv = b.take<float>((size_t)(R > 0 ? R : 1) * 3);
   q->tile_bid = b.take<int2>((size_t)(q->RB > 0 ? q->RB : 1));
+  q->tile_tan = b.take<float4>((size_t)(q->RB > 0 ? q->RB : 1));
   q->cnt = b.take<int>((size_t)n);
   q->start = b.take<int>((size_t)n);
   q->block_sums = b.take<int>((size_t)q->nb);
+  q->items = b.take<int>((size_t)(q->M > 0 ? q->M : 1));
+  q->n_items = b.take<int>(1);
   q->bytes = b.off + 256;
   return LIDF_OK;
 }
@@ -652,7 +655,7 @@ int persistent_blocks(int64_t items, int per_sm) {
 }
 
 int aabb_ray_prep(const AabbPlan& q, const float* ray_dir, const int32_t* ray_bid, int64_t R, cudaStream_t st) {
-  k_aabb_ray_prep<<<(unsigned)q.RB, AABB_THREADS, 0, st>>>(ray_dir, ray_bid, R, q.inv, q.tile_bid);
+  k_aabb_ray_prep<<<(unsigned)q.RB, AABB_THREADS, 0, st>>>(ray_dir, ray_bid, R, q.inv, q.tile_bid, q.tile_tan);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
@@ -678,11 +681,13 @@ extern "C" int lidf_ray_aabb_forward(const float* ray_dir, const float* voxel_bo
   // 16-byte accesses need R % 4 == 0 (every mask/dist row then starts 16-byte aligned) and aligned base pointers
   const bool vec = R % 4 == 0 && ((uintptr_t)mask % 16 == 0) && ((uintptr_t)dist % 16 == 0) && ((uintptr_t)ray_bid % 16 == 0);
   if (vec)
-    k_aabb_dense<true><<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R,
-                                                                            q.RB, q.M, mask, reinterpret_cast<float2*>(dist));
+    k_aabb_dense<true><<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid,
+                                                                            q.tile_tan, R, q.RB, q.M, mask,
+                                                                            reinterpret_cast<float2*>(dist));
   else
-    k_aabb_dense<false><<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R,
-                                                                             q.RB, q.M, mask, reinterpret_cast<float2*>(dist));
+    k_aabb_dense<false><<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid,
+                                                                             q.tile_tan, R, q.RB, q.M, mask,
+                                                                             reinterpret_cast<float2*>(dist));
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
@@ -701,9 +706,13 @@ extern "C" int lidf_ray_aabb_pairs_count(const float* ray_dir, const float* voxe
   cudaStream_t st = stream;
   if ((rc = aabb_ray_prep(q, ray_dir, ray_bid, R, st))) return rc;
   const int64_t n = q.M + 1;
-  LIDF_CUDA(cudaMemsetAsync(q.cnt + q.M, 0, sizeof(int), st));
-  k_aabb_count<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.tile_bid, R, q.RB,
-                                                                    q.M, q.cnt);
+  LIDF_CUDA(cudaMemsetAsync(q.cnt, 0, sizeof(int) * (size_t)n, st));
+  LIDF_CUDA(cudaMemsetAsync(q.n_items, 0, sizeof(int), st));
+  k_aabb_items<<<(unsigned)((q.M + 255) / 256), 256, 0, st>>>(voxel_bound, voxel_bid, q.tile_bid, q.tile_tan, q.RB, q.M, q.items,
+                                                               q.n_items);
+  LIDF_LAUNCH_CHECK();
+  k_aabb_count<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.items, q.n_items, R,
+                                                                    q.RB, q.cnt);
   LIDF_LAUNCH_CHECK();
   k_scan_partial<<<q.nb, LIDF_SCAN_BLOCK, 0, st>>>(q.cnt, n, q.start, q.block_sums);
   LIDF_LAUNCH_CHECK();
@@ -732,8 +741,9 @@ extern "C" int lidf_ray_aabb_pairs_fill(const float* ray_dir, const float* voxel
   if (!voxel_bound || !ray_bid || !voxel_bid || !workspace || !pair_vox || !pair_ray || !pair_dist) return LIDF_ERR_NULL;
   if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
   cudaStream_t st = stream;
-  k_aabb_fill<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, R, q.RB, q.M, q.start,
-                                                                   pair_vox, pair_ray, reinterpret_cast<float2*>(pair_dist));
+  k_aabb_fill<<<persistent_blocks(q.M, 8), AABB_THREADS, 0, st>>>(q.inv, voxel_bound, ray_bid, voxel_bid, q.items, q.n_items, R,
+                                                                   q.RB, q.start, pair_vox, pair_ray,
+                                                                   reinterpret_cast<float2*>(pair_dist));
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }

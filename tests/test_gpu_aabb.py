@@ -320,3 +320,32 @@ def test_front_to_back_chain_from_points():
         want2 = O.refine_decoder_tail(dd["pred_pos"].cpu(), miss_ray_dir, (vb[:, :3] + vb[:, 3:]) / 2, feat2[torch.from_numpy(want_end)],
                                       dd["roi_feat_per_ray"].cpu(), dict(O.REFINE_CFG), rdec)
         assert rel_err(out2.cpu(), want2) < 1e-3
+
+
+@pytest.mark.parametrize("H,W,B", [(64, 64, 1), (48, 100, 3), (130, 33, 2)])
+def test_ray_aabb_tile_culling_is_conservative(H, W, B):
+    """Image-ordered all-pixel rays make the (voxel, 1024-ray tile) frustum cull bite (a tile spans a few image rows, most
+    voxels project elsewhere): the pair list and the dense slab must still equal the oracle exactly, including voxels that
+    touch z <= 0 (never culled), grazing boxes, and boxes stretched across the whole frustum."""
+    from implicit_depth_b200.synthetic import make_rays
+    rng = np.random.default_rng(H * W + B)
+    miss_bid, _, ray_dir = make_rays(B, H, W, "cpu")
+    V_img = 90
+    lo = np.stack((rng.uniform(-1.2, 1.0, V_img * B), rng.uniform(-1.2, 1.0, V_img * B), rng.uniform(-0.2, 2.0, V_img * B)), 1)
+    size = rng.uniform(0.02, 0.5, size=(V_img * B, 3))
+    size[::17] = 3.0                                                  # a few huge boxes
+    vb = np.concatenate((lo, lo + size), 1).astype(np.float32)
+    # boxes whose faces pass exactly through pixel rays: snap a corner onto a ray at depth 1
+    d = ray_dir.numpy()
+    pick = rng.integers(0, d.shape[0], size=20)
+    vb[:20, 0:3] = d[pick] / d[pick][:, 2:3]
+    vb[:20, 3:6] = vb[:20, 0:3] + np.float32(0.1)
+    xb = np.repeat(np.arange(B), V_img).astype(np.int32)
+    rb = miss_bid.numpy().astype(np.int32)
+    mask, dist = A.ray_aabb_dense(d, vb, rb, xb)
+    assert mask.sum() > 1000
+    _check_ray(d, vb, rb, xb, mask, dist, A.ray_aabb_pairs(d, vb, rb, xb))
+    # rays not looking down +z in the middle of the list: their tile must not be culled
+    d2 = d.copy(); d2[1500 % d.shape[0]] = np.array([0.3, -0.2, -0.9], np.float32); d2[7] = np.array([1.0, 0.0, 0.0], np.float32)
+    mask2, dist2 = A.ray_aabb_dense(d2, vb, rb, xb)
+    _check_ray(d2, vb, rb, xb, mask2, dist2, A.ray_aabb_pairs(d2, vb, rb, xb))
