@@ -339,19 +339,30 @@ __global__ void k_pcl_pair_label(const float* __restrict__ pcl_pos, const float*
 
 // end_voxel_id[n] = max(end_voxel_id[n], largest v containing point n)  (pipeline.py:939-944).
 // One thread per point; voxel boxes go through shared memory in tiles of 256, highest ids first, so a thread stops at
-// its first hit and a block stops as soon as every thread is settled.
+// its first hit and a block stops as soon as every thread is settled.  A voxel tile none of whose image ids falls into
+// the block's image-id range is skipped before its boxes are even loaded (points and voxels are image-major in practice,
+// so 7 of 8 tiles go that way at batch 8).
 #define AABB_VTILE 256
 __global__ void __launch_bounds__(AABB_THREADS) k_pcl_end_voxel(const float* __restrict__ pcl_pos, const float* __restrict__ voxel_bound,
                                                                 const int32_t* __restrict__ pcl_bid, const int32_t* __restrict__ voxel_bid,
                                                                 int64_t N, int64_t V, int64_t* __restrict__ end_voxel_id) {
   __shared__ float s_box[AABB_VTILE * 6];
   __shared__ int s_bid[AABB_VTILE];
+  __shared__ int s_bmin, s_bmax;
   const int64_t n = (int64_t)blockIdx.x * AABB_THREADS + threadIdx.x;
   const bool act = n < N;
   float x = 0.f, y = 0.f, z = 0.f;
   int bid = 0;
   int64_t cur = V;                                                   // inactive threads are settled from the start
   if (act) { x = pcl_pos[n * 3 + 0]; y = pcl_pos[n * 3 + 1]; z = pcl_pos[n * 3 + 2]; bid = pcl_bid[n]; cur = end_voxel_id[n]; }
+  if (threadIdx.x == 0) { s_bmin = INT_MAX; s_bmax = INT_MIN; }
+  __syncthreads();
+  {
+    const int lo = __reduce_min_sync(0xffffffffu, act ? bid : INT_MAX), hi = __reduce_max_sync(0xffffffffu, act ? bid : INT_MIN);
+    if ((threadIdx.x & 31) == 0) { atomicMin(&s_bmin, lo); atomicMax(&s_bmax, hi); }
+  }
+  __syncthreads();
+  const int bmin = s_bmin, bmax = s_bmax;
   const int64_t cur0 = cur;
   bool done = !act;
   for (int64_t hi = V; hi > 0; hi -= AABB_VTILE) {
@@ -359,8 +370,14 @@ __global__ void __launch_bounds__(AABB_THREADS) k_pcl_end_voxel(const float* __r
     const int cntv = (int)(hi - lo);
     done = done || (cur >= hi - 1);                                  // nothing above `cur` left in this or lower tiles
     if (__syncthreads_and(done)) break;
+    bool mine = false;
+    for (int i = threadIdx.x; i < cntv; i += AABB_THREADS) {
+      const int vb = voxel_bid[lo + i];
+      s_bid[i] = vb;
+      mine = mine || (vb >= bmin && vb <= bmax);
+    }
+    if (!__syncthreads_or(mine)) continue;                           // no voxel of this tile belongs to an image of this block
     for (int i = threadIdx.x; i < cntv * 6; i += AABB_THREADS) s_box[i] = voxel_bound[lo * 6 + i];
-    for (int i = threadIdx.x; i < cntv; i += AABB_THREADS) s_bid[i] = voxel_bid[lo + i];
     __syncthreads();
     if (!done) {
       for (int i = cntv - 1; i >= 0; --i) {
