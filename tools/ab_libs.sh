@@ -1,5 +1,6 @@
 #!/bin/bash
-# A/B timing of alternative builds of the library (build/dbg/lib_<tag>.so, selected with LIDF_QUERY_LIB): decoder-kernel
+# A/B timing of alternative builds of the library (build/dbg/lib_<tag>.so from tools/build_variants.sh, selected with
+# LIDF_QUERY_LIB): decoder-kernel
 # time, step time and SM clock of the bench workload for every tag given.  Usage: bash tools/ab_libs.sh c3 base h1000 ...
 WL=$1; shift
 for tag in "$@"; do

@@ -1,5 +1,6 @@
 #!/bin/bash
-# Timing experiment: decoder-kernel time with parts of k_mlp_tc compiled out (build/dbg/lib_m<mode>.so, TC_DEBUG_MODE bits:
+# Timing experiment: decoder-kernel time with parts of k_mlp_tc compiled out (build/dbg/lib_m<mode>.so, made beforehand by
+# `bash tools/build_variants.sh modes`; TC_DEBUG_MODE bits:
 # 1 no MMA issue, 2 no TMEM loads in the epilogues, 4 no epilogue math/stores, 8 no sincos in the operand build).
 WL=${1:-c2}
 for m in 0 1 2 4 6 7 8 14; do
