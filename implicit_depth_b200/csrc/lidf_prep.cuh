@@ -211,40 +211,105 @@ __device__ __forceinline__ void roi_channel_general(const float* __restrict__ fc
   }
 }
 
-// BOX != nullptr: interior rays (8x8 box not clamped: every sample sits on a pixel centre with weight 1) read their four
-// bins from the 4x4 box-sum map, which was accumulated in the same order -> bit-identical to the general path.
+// per-ray box set-up shared by the two ROI kernels (boxes are built from integers then .float(), pipeline.py:374-381)
+struct RoiBox { float sw, sh, bw, bh, count; int gw, gh; };
+__device__ __forceinline__ RoiBox roi_box(int px, int py, int half, int H, int W) {
+  const float x1 = (float)min(max(px - half, 0), W - 1), x2 = (float)min(max(px + half, 0), W - 1);
+  const float y1 = (float)min(max(py - half, 0), H - 1), y2 = (float)min(max(py + half, 0), H - 1);
+  RoiBox r;
+  r.sw = x1 - 0.5f; r.sh = y1 - 0.5f;
+  const float rw = (x2 - 0.5f) - r.sw, rh = (y2 - 0.5f) - r.sh;
+  r.bw = rw / 2.0f; r.bh = rh / 2.0f;
+  r.gw = (int)ceilf(rw / 2.0f); r.gh = (int)ceilf(rh / 2.0f);
+  r.count = (float)max(r.gh * r.gw, 1);
+  return r;
+}
+
+// Block = 32 rays (lane) x 8 channel groups (warp).  Results go through a shared tile [32 rays][128 (+4)] so that the global
+// stores are whole 512-byte rows (one warp instruction = one ray's row).
+// BOX != nullptr (dense ray sets): interior rays (8x8 box not clamped: every sample sits on a pixel centre with weight 1)
+// read their four bins from the 4x4 box-sum map, which was accumulated in the same order -> bit-identical to the general
+// path.  Rays in the 4-pixel border band need the general path (up to 16 bilinear samples per bin); they are only a few
+// per cent of the rays but sit in 10-20 % of the warps, so instead of dragging those warps through the slow path with a
+// handful of active lanes they are appended to `border_list` and done by k_roi_align_border with full warps.
+// BOX == nullptr: every ray takes the general path here.
 __global__ void __launch_bounds__(LIDF_ROI_THREADS)
 k_roi_align_rays(const float* __restrict__ feat, const float* __restrict__ box, int B, int H, int W,
                  const int64_t* __restrict__ img_ind, const int64_t* __restrict__ bid, int64_t R, int half,
-                 float* __restrict__ out) {
+                 float* __restrict__ out, int* __restrict__ border_list, int* __restrict__ border_count) {
+  __shared__ float s_tile[32][LIDF_RGB_DIM + 4];
+  __shared__ unsigned s_deferred;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-  const int64_t ray = (int64_t)blockIdx.x * 32 + lane;
-  if (ray >= R) return;
+  const int64_t ray_raw = (int64_t)blockIdx.x * 32 + lane;
+  const int64_t ray = ray_raw < R ? ray_raw : R - 1;                 // tail lanes recompute the last ray (never stored)
   const int px = (int)img_ind[2 * ray], py = (int)img_ind[2 * ray + 1];
   const int b = (int)bid[ray];
-  // boxes are built from integers then .float() (pipeline.py:374-381)
-  const float x1 = (float)min(max(px - half, 0), W - 1), x2 = (float)min(max(px + half, 0), W - 1);
-  const float y1 = (float)min(max(py - half, 0), H - 1), y2 = (float)min(max(py + half, 0), H - 1);
-  const float sw = x1 - 0.5f, sh = y1 - 0.5f;
-  const float rw = (x2 - 0.5f) - sw, rh = (y2 - 0.5f) - sh;
-  const float bw = rw / 2.0f, bh = rh / 2.0f;
-  const int gw = (int)ceilf(rw / 2.0f), gh = (int)ceilf(rh / 2.0f);
-  const float count = (float)max(gh * gw, 1);
   const bool interior = box != nullptr && half == 4 && px - 4 >= 0 && px + 4 <= W - 1 && py - 4 >= 0 && py + 4 <= H - 1;
-  const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
-  for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
-    float o[4];
-    if (interior) {
-      const float* bc = box + plane0 + (size_t)c * H * W + (size_t)(py - 4) * W + (px - 4);
-      // interior: gh = gw = 4, count = 16 -- dividing by a power of two is the same IEEE result as multiplying by 1/16
-      o[0] = __ldg(bc) * 0.0625f;
-      o[1] = __ldg(bc + 4) * 0.0625f;
-      o[2] = __ldg(bc + (size_t)4 * W) * 0.0625f;
-      o[3] = __ldg(bc + (size_t)4 * W + 4) * 0.0625f;
-    } else {
-      roi_channel_general(feat + plane0 + (size_t)c * H * W, H, W, sw, sh, bw, bh, gw, gh, count, o);
+  const bool defer = box != nullptr && border_list != nullptr && !interior;
+  const unsigned dmask = __ballot_sync(0xffffffffu, defer && ray_raw < R);
+  if (warp == 0) {
+    if (lane == 0) s_deferred = dmask;
+    if (dmask) {                                                     // warp-aggregated append (order is irrelevant)
+      const int leader = __ffs(dmask) - 1;
+      int base = 0;
+      if (lane == leader) base = atomicAdd(border_count, __popc(dmask));
+      base = __shfl_sync(0xffffffffu, base, leader);
+      if ((dmask >> lane) & 1u) border_list[base + __popc(dmask & ((1u << lane) - 1u))] = (int)ray_raw;
     }
-    *reinterpret_cast<float4*>(out + (size_t)ray * LIDF_RGB_DIM + c * 4) = make_float4(o[0], o[1], o[2], o[3]);
+  }
+  const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
+  if (!defer) {
+    const RoiBox rb = roi_box(px, py, half, H, W);
+    for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
+      float o[4];
+      if (interior) {
+        const float* bc = box + plane0 + (size_t)c * H * W + (size_t)(py - 4) * W + (px - 4);
+        // interior: gh = gw = 4, count = 16 -- dividing by a power of two is the same IEEE result as multiplying by 1/16
+        o[0] = __ldg(bc) * 0.0625f;
+        o[1] = __ldg(bc + 4) * 0.0625f;
+        o[2] = __ldg(bc + (size_t)4 * W) * 0.0625f;
+        o[3] = __ldg(bc + (size_t)4 * W + 4) * 0.0625f;
+      } else {
+        roi_channel_general(feat + plane0 + (size_t)c * H * W, H, W, rb.sw, rb.sh, rb.bw, rb.bh, rb.gw, rb.gh, rb.count, o);
+      }
+      *reinterpret_cast<float4*>(&s_tile[lane][c * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+  }
+  __syncthreads();
+  const int64_t ray0 = (int64_t)blockIdx.x * 32;
+  const unsigned deferred = s_deferred;
+  for (int r = warp; r < 32; r += LIDF_ROI_THREADS / 32)
+    if (ray0 + r < R && !((deferred >> r) & 1u))
+      *reinterpret_cast<float4*>(out + (size_t)(ray0 + r) * LIDF_RGB_DIM + 4 * lane) = *reinterpret_cast<const float4*>(&s_tile[r][4 * lane]);
+}
+
+// the deferred border rays, 32 per block iteration, general path only (same arithmetic as above -> same bits)
+__global__ void __launch_bounds__(LIDF_ROI_THREADS)
+k_roi_align_border(const float* __restrict__ feat, int B, int H, int W, const int64_t* __restrict__ img_ind,
+                   const int64_t* __restrict__ bid, int half, float* __restrict__ out, const int* __restrict__ border_list,
+                   const int* __restrict__ border_count) {
+  __shared__ float s_tile[32][LIDF_RGB_DIM + 4];
+  __shared__ int s_ray[32];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int n = *border_count;
+  for (int chunk = blockIdx.x; chunk * 32 < n; chunk += gridDim.x) {
+    const int idx = chunk * 32 + lane;
+    const int64_t ray = border_list[idx < n ? idx : n - 1];
+    if (warp == 0) s_ray[lane] = idx < n ? (int)ray : -1;
+    const int px = (int)img_ind[2 * ray], py = (int)img_ind[2 * ray + 1];
+    const int b = (int)bid[ray];
+    const RoiBox rb = roi_box(px, py, half, H, W);
+    const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
+    for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
+      float o[4];
+      roi_channel_general(feat + plane0 + (size_t)c * H * W, H, W, rb.sw, rb.sh, rb.bw, rb.bh, rb.gw, rb.gh, rb.count, o);
+      *reinterpret_cast<float4*>(&s_tile[lane][c * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+    }
+    __syncthreads();
+    for (int r = warp; r < 32; r += LIDF_ROI_THREADS / 32)
+      if (s_ray[r] >= 0)
+        *reinterpret_cast<float4*>(out + (size_t)s_ray[r] * LIDF_RGB_DIM + 4 * lane) = *reinterpret_cast<const float4*>(&s_tile[r][4 * lane]);
+    __syncthreads();
   }
 }
 

@@ -49,6 +49,8 @@ static void mlp_event(int which, cudaStream_t st) {
 
 namespace {
 
+int persistent_blocks(int64_t items, int per_sm);   // grid of a persistent kernel: min(items, SM count x per_sm)
+
 struct Bump {  // workspace carving, 256-byte aligned
   char* base; size_t off;
   template <typename T> T* take(size_t n) {
@@ -190,20 +192,25 @@ extern "C" int lidf_roi_align_rays(const float* feat, int32_t B, int32_t H, int3
   if (!feat || !img_ind || !bid || !out) return LIDF_ERR_NULL;
   if (R <= 0) return LIDF_OK;
   k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, stream>>>(feat, nullptr, B, H, W, img_ind, bid, R,
-                                                                                roi_inp_bbox / 2, out);
+                                                                                roi_inp_bbox / 2, out, nullptr, nullptr);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
 
 namespace {
 // ROIAlign per ray through the 4x4 box-sum map (dense ray sets: the map costs a quarter of a ray per pixel)
-int roi_align_rays_box(const float* feat, float* box, int B, int H, int W, const int64_t* img_ind, const int64_t* bid,
-                       int64_t R, int roi_inp_bbox, float* out, cudaStream_t st) {
+int roi_align_rays_box(const float* feat, float* box, int* border_list, int* border_count, int B, int H, int W,
+                       const int64_t* img_ind, const int64_t* bid, int64_t R, int roi_inp_bbox, float* out, cudaStream_t st) {
   const int64_t n = (int64_t)B * LIDF_RGB_CH * H * W;
   k_box4<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feat, n, H, W, box);
   LIDF_LAUNCH_CHECK();
+  LIDF_CUDA(cudaMemsetAsync(border_count, 0, sizeof(int), st));
   k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, st>>>(feat, box, B, H, W, img_ind, bid, R,
-                                                                            roi_inp_bbox / 2, out);
+                                                                            roi_inp_bbox / 2, out, border_list, border_count);
+  LIDF_LAUNCH_CHECK();
+  k_roi_align_border<<<persistent_blocks((R + 31) / 32, 8), LIDF_ROI_THREADS, 0, st>>>(feat, B, H, W, img_ind, bid,
+                                                                                        roi_inp_bbox / 2, out, border_list,
+                                                                                        border_count);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
@@ -321,7 +328,7 @@ namespace {
 struct QueryPlan {
   int impl, pe_pos, pe_dir, D, KR, KP;
   CsrBufs csr;
-  float* roi_feat; float* T; float* Av; float* box4;
+  float* roi_feat; float* T; float* Av; float* box4; int* border_list; int* border_count;
   SimtPack sp;
   TcBufs tc;
   size_t bytes;
@@ -341,8 +348,10 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
   q->csr = carve_csr(b, p->P, p->R);
   q->roi_feat = p->roi_feat_per_ray ? p->roi_feat_per_ray : b.take<float>((size_t)p->R * LIDF_RGB_DIM);
   // dense ray sets (at least a third of the pixels) go through the 4x4 box-sum map
-  q->box4 = (p->roi_inp_bbox == 8 && p->H >= 9 && p->W >= 9 && (int64_t)p->R * 3 >= (int64_t)p->B * p->H * p->W)
-                ? b.take<float>((size_t)p->B * LIDF_RGB_CH * p->H * p->W) : nullptr;
+  const bool use_box = p->roi_inp_bbox == 8 && p->H >= 9 && p->W >= 9 && (int64_t)p->R * 3 >= (int64_t)p->B * p->H * p->W;
+  q->box4 = use_box ? b.take<float>((size_t)p->B * LIDF_RGB_CH * p->H * p->W) : nullptr;   // (nullptr in the sizing pass too)
+  q->border_list = use_box ? b.take<int>((size_t)(p->R > 0 ? p->R : 1)) : nullptr;
+  q->border_count = use_box ? b.take<int>(1) : nullptr;
   q->T = b.take<float>((size_t)p->R * 512);
   if (q->impl == LIDF_MLP_SIMT_FP32) {
     q->Av = b.take<float>((size_t)p->V * 512);
@@ -393,8 +402,8 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
   if ((rc = build_csr(q.csr, p->pair_ray, P, R, st))) return rc;
   // 2. ROIAlign per ray
   if (q.box4) {
-    if ((rc = roi_align_rays_box(p->full_rgb_feat, q.box4, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R,
-                                 p->roi_inp_bbox, q.roi_feat, st))) return rc;
+    if ((rc = roi_align_rays_box(p->full_rgb_feat, q.box4, q.border_list, q.border_count, p->B, p->H, p->W, p->miss_img_ind,
+                                 p->miss_bid, R, p->roi_inp_bbox, q.roi_feat, st))) return rc;
   } else if ((rc = lidf_roi_align_rays(p->full_rgb_feat, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox,
                                        q.roi_feat, stream))) return rc;
   if (P > 0) {
