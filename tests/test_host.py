@@ -157,3 +157,21 @@ def test_pointnet_mirror_state_dict_and_autograd_path():
     assert net.point_lin1.weight.grad is not None and net.vox_lin2.weight.grad is not None
     with torch.no_grad(), pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         net(inp, idx)
+
+
+def test_bench_reference_arm_runs_without_a_gpu_and_prints_the_contract_line():
+    """`bench.py --impl reference` is pure CPU (oracle port): one JSON line with the driver's keys; other ranks stay silent."""
+    import json
+    import subprocess
+    import sys
+    cmd = [sys.executable, os.path.join(REPO, "bench.py"), "--impl", "reference", "--workload", "tiny", "--steps", "1",
+           "--warmup", "0", "--cpu-sample-pairs", "4096"]
+    out = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="0"))
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["metric"] == "lidf_query_points_per_sec" and line["unit"] == "points/s"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["gpu_launches"] == 0
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1 and "sample" in line["cpu_baseline"]
+    assert line["e2e"] == dict(value=line["value"], unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
+    quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
+    assert quiet.returncode == 0 and quiet.stdout.strip() == ""
