@@ -175,3 +175,35 @@ def test_bench_reference_arm_runs_without_a_gpu_and_prints_the_contract_line():
     assert line["e2e"] == dict(value=line["value"], unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0)
     quiet = subprocess.run(cmd, capture_output=True, text=True, timeout=300, env=dict(os.environ, RANK="1", WORLD_SIZE="2"))
     assert quiet.returncode == 0 and quiet.stdout.strip() == ""
+
+
+@pytest.mark.parametrize("name,gname", [("ief_ragged_2x24x32", "grad_ief_ragged_2x24x32"),
+                                        ("ief_rel_sigmoid_1x16x20", "grad_ief_rel_sigmoid_1x16x20")])
+def test_training_path_gradients_match_reference_autograd(name, gname):
+    """The mirror's training path (torch autograd on the same maths, `_get_pred_autograd`) against gradients produced by the
+    reference's own get_embedding + get_pred under autograd (tests/golden/make_golden_grad.py): decoder parameters,
+    full_rgb_feat (through roi_align) and occ_voxel_feat."""
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    from implicit_depth_b200.models.pipeline import LIDF, default_opt
+    d, cfg, off, prob, part, ref, _ = load_golden(name)
+    z = np.load(os.path.join(GOLDEN_DIR, gname + ".npz"))
+    opt = default_opt(**{"model.n_iter": cfg["n_iter"], "model.use_sigmoid": cfg["use_sigmoid"],
+                         "model.intersect_pos_type": cfg["intersect_pos_type"]})
+    lidf = LIDF(opt, torch.device("cpu"))
+    lidf.offset_dec.load_state_dict(off); lidf.prob_dec.load_state_dict(prob)
+    dd = dict(d); dd.update(total_miss_sample_num=d["miss_ray_dir"].shape[0], part_size=part)
+    dd["full_rgb_feat"] = d["full_rgb_feat"].clone().requires_grad_(True)
+    dd["occ_voxel_feat"] = d["occ_voxel_feat"].clone().requires_grad_(True)
+    lidf.train()
+    lidf.get_pred(dd, "train", 100)
+    assert torch.equal(dd["max_pair_id"], torch.from_numpy(z["max_pair_id"]).long())
+    loss = (torch.from_numpy(z["c_pos"]) * dd["pred_pos"]).sum() + (torch.from_numpy(z["c_prob"]) * dd["pred_prob_end"]).sum()
+    assert abs(float(loss.detach()) - float(z["loss"])) < 1e-4 * max(1.0, abs(float(z["loss"])))
+    loss.backward()
+    assert rel_err(dd["full_rgb_feat"].grad, torch.from_numpy(z["grad.full_rgb_feat"])) < 1e-4
+    assert rel_err(dd["occ_voxel_feat"].grad, torch.from_numpy(z["grad.occ_voxel_feat"])) < 1e-4
+    for mod_name, mod in (("offset_dec", lidf.offset_dec), ("prob_dec", lidf.prob_dec)):
+        for k, p in mod.named_parameters():
+            want = torch.from_numpy(z[f"grad.{mod_name}.{k}"])
+            assert p.grad is not None and rel_err(p.grad, want) < 1e-4, (mod_name, k, rel_err(p.grad, want))

@@ -155,3 +155,28 @@ def test_image_loss_oracle_matches_reference_compute_loss(name):
     assert torch.equal(out["pred_surf_norm_img"], t["ref_pred_surf_norm_img"]) and torch.equal(out["gt_surf_norm_img"], t["ref_gt_surf_norm_img"])
     for k in ("surf_norm_loss", "smooth_loss", "angle_err"):
         assert abs(float(out[k]) - sc["ref_" + k]) <= 2e-6 * max(1.0, abs(sc["ref_" + k])), k
+
+
+@pytest.mark.parametrize("name,gname", [("ief_ragged_2x24x32", "grad_ief_ragged_2x24x32"),
+                                        ("ief_rel_sigmoid_1x16x20", "grad_ief_rel_sigmoid_1x16x20")])
+def test_oracle_is_differentiable_and_matches_reference_gradients(name, gname):
+    """Autograd through the oracle restatement reproduces the reference's own gradients (tests/golden/make_golden_grad.py):
+    the yardstick for the native backward planned in DESIGN.md section 9."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    d, cfg, off, prob, part, ref, _ = load_golden(name)
+    z = np.load(os.path.join(GOLDEN_DIR, gname + ".npz"))
+    d = dict(d)
+    d["full_rgb_feat"] = d["full_rgb_feat"].clone().requires_grad_(True)
+    d["occ_voxel_feat"] = d["occ_voxel_feat"].clone().requires_grad_(True)
+    off = {k: v.clone().requires_grad_(True) for k, v in off.items()}
+    prob = {k: v.clone().requires_grad_(True) for k, v in prob.items()}
+    out = O.lidf_query(d, cfg, off, prob, part, dedup_rays=True)
+    loss = (torch.from_numpy(z["c_pos"]) * out["pred_pos"]).sum() + (torch.from_numpy(z["c_prob"]) * out["pred_prob_end"]).sum()
+    loss.backward()
+    assert rel_err(d["full_rgb_feat"].grad, torch.from_numpy(z["grad.full_rgb_feat"])) < 1e-4
+    assert rel_err(d["occ_voxel_feat"].grad, torch.from_numpy(z["grad.occ_voxel_feat"])) < 1e-4
+    for mod_name, params in (("offset_dec", off), ("prob_dec", prob)):
+        for k, p in params.items():
+            assert rel_err(p.grad, torch.from_numpy(z[f"grad.{mod_name}.{k}"])) < 1e-4, (mod_name, k)
