@@ -310,6 +310,19 @@ class RefineDecoderMixin:
         """pipeline.py:1016-1029: gather of the end-voxel feature + decoder + position update, one fused call (the gather
         and the voxel centre for 'rel' positions happen inside the kernel)."""
         r = self.opt.refine
+        needs_grad = torch.is_grad_enabled() and (occ_voxel_feat.requires_grad or pred_pos.requires_grad
+                                                  or any(p.requires_grad for p in self.offset_dec.parameters()))
+        if needs_grad:
+            # training (train_refine.yaml optimises pnet_model + offset_dec): the same maths on differentiable torch ops,
+            # reference pipeline.py:1016-1029, because the native backward does not exist yet
+            end_voxel_bound = data_dict['voxel_bound'][end_voxel_id]
+            end_voxel_center = (end_voxel_bound[:, :3] + end_voxel_bound[:, 3:]) / 2.
+            inp_pos = pred_pos - end_voxel_center if r.intersect_pos_type == 'rel' else pred_pos
+            inp_embed = torch.cat((occ_voxel_feat[end_voxel_id], rgb_feat_per_ray, self.embed_fn(inp_pos),
+                                   self.embeddirs_fn(data_dict['miss_ray_dir'])), -1)
+            pred_refine_offset = self.offset_dec(inp_embed)
+            r0, r1 = r.offset_range
+            return pred_pos + (pred_refine_offset * (r1 - r0) + r0) * data_dict['miss_ray_dir']
         return lidf_query.refine_forward(
             pred_pos.contiguous(), data_dict['miss_ray_dir'].contiguous(), None, None, rgb_feat_per_ray.contiguous(),
             self.offset_dec, occ_voxel_feat=occ_voxel_feat.float().contiguous(), end_voxel_id=end_voxel_id.long().contiguous(),

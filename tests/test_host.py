@@ -207,3 +207,33 @@ def test_training_path_gradients_match_reference_autograd(name, gname):
         for k, p in mod.named_parameters():
             want = torch.from_numpy(z[f"grad.{mod_name}.{k}"])
             assert p.grad is not None and rel_err(p.grad, want) < 1e-4, (mod_name, k, rel_err(p.grad, want))
+
+
+def test_refine_training_path_cpu_matches_reference_output_and_has_gradients():
+    """RefineDecoderMixin.refine_decoder_tail while autograd records (train_refine.yaml trains pnet_model + offset_dec):
+    torch ops, same values as the reference's get_pred_refine, gradients reach the decoder and the voxel features."""
+    from implicit_depth_b200.models.pipeline import RefineNet, default_opt
+    d, cfg, off, prob, part, ref, extra = load_golden("ief_ragged_2x24x32")
+    rdec = {k[len("refine_dec."):]: v for k, v in extra.items() if k.startswith("refine_dec.")}
+    refine = RefineNet(default_opt(), torch.device("cpu"))
+    refine.offset_dec.load_state_dict(rdec)
+    refine.train()
+    vfeat = extra["refine.occ_voxel_feat"].clone().requires_grad_(True)
+    roi = O.get_embedding(d, cfg, dedup_rays=True)["intersect_rgb_feat"]
+    R = d["miss_ray_dir"].shape[0]
+    roi_per_ray = torch.zeros(R, 128); roi_per_ray[d["miss_ray_intersect_idx"]] = roi
+    roi_per_ray = torch.where(torch.isnan(ref["roi_feat_per_ray"]), roi_per_ray, ref["roi_feat_per_ray"])   # rays without pairs
+    # rays without a pair have no ROI row in the fixture; compute them with the oracle's roi_align
+    boxes_missing = torch.isnan(ref["roi_feat_per_ray"]).any(1)
+    if boxes_missing.any():
+        pix = d["miss_img_ind"].float(); H, W = d["full_rgb_feat"].shape[2:]
+        ul = torch.stack(((pix[:, 0] - 4).clamp(0, W - 1), (pix[:, 1] - 4).clamp(0, H - 1)), -1)
+        br = torch.stack(((pix[:, 0] + 4).clamp(0, W - 1), (pix[:, 1] + 4).clamp(0, H - 1)), -1)
+        boxes = torch.cat((d["miss_bid"].float().unsqueeze(-1), ul, br), -1)
+        full = O.roi_align_aligned(d["full_rgb_feat"], boxes, 2, 1.0).reshape(R, -1)
+        roi_per_ray = torch.where(boxes_missing.unsqueeze(1), full, roi_per_ray)
+    out = refine.refine_decoder_tail(dict(d), ref["pred_pos"], extra["refine.end_voxel_id"].long(), vfeat, roi_per_ray)
+    assert rel_err(out.detach(), ref["pred_pos_refine"]) < 2e-5
+    out.abs().sum().backward()
+    assert vfeat.grad is not None and float(vfeat.grad.abs().sum()) > 0
+    assert refine.offset_dec.linear_1.weight.grad is not None
