@@ -75,6 +75,12 @@ def _shim_scatter(src, index, dim=-1, out=None, dim_size=None, reduce="sum"):
             if s[i] > o[idx[i]]:
                 o[idx[i]] = s[i]
         return out
+    if reduce == "max" and out is None and dim == 0 and src.requires_grad:
+        # differentiable variant (gradient goes to the arg-max row of every (voxel, channel), as in torch_scatter)
+        n = int(index.max()) + 1 if dim_size is None else dim_size
+        o = torch.full((n,) + tuple(src.shape[1:]), -float("inf"), dtype=src.dtype)
+        o = o.scatter_reduce(0, index.reshape(-1, 1).expand_as(src), src, reduce="amax", include_self=True)
+        return torch.where(torch.isinf(o), torch.zeros_like(o), o)
     if reduce == "max" and out is None and dim == 0:                # pointnet.py:27,35: per-voxel max of [N,C] rows
         n = int(index.max()) + 1 if dim_size is None else dim_size  # torch_scatter: rows without any source stay 0
         s = src.detach().numpy(); idx = index.numpy()

@@ -33,6 +33,16 @@ def run(name, seed, N, V, empty_voxels=()):
     with torch.no_grad():
         out = net(inp_feat=inp, vox2point_idx=idx)
     save = {"inp_feat": inp.numpy(), "vox2point_idx": idx.numpy().astype(np.int32), "V": V, "ref_out": out.numpy()}
+    # gradients of sum(c * out) through the reference module (its scatter-max stub routes the gradient to the arg-max rows
+    # exactly like torch_scatter does: ties are not expected with continuous random inputs)
+    c = torch.randn(out.shape, generator=g)
+    inp_g = inp.clone().requires_grad_(True)
+    net.train()
+    out_g = net(inp_feat=inp_g, vox2point_idx=idx)
+    (c * out_g).sum().backward()
+    save["c_out"] = c.numpy(); save["grad.inp_feat"] = inp_g.grad.numpy()
+    for k, p_ in net.named_parameters():
+        save["grad." + k] = p_.grad.numpy()
     for k, v in net.state_dict().items():
         save["w." + k] = v.numpy()
     path = os.path.join(HERE, name + ".npz")

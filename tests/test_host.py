@@ -151,10 +151,16 @@ def test_pointnet_mirror_state_dict_and_autograd_path():
     net = PointNet2Stage(input_channels=6, output_channels=128, gf_dim=32)
     assert set(net.state_dict().keys()) == set(w.keys())
     net.load_state_dict(w)
-    out = net(inp, idx)                                      # parameters require grad -> torch path
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, "pointnet_2000x60.npz"))
+    inp_g = inp.clone().requires_grad_(True)
+    out = net(inp_g, idx)                                    # parameters require grad -> torch path
     assert rel_err(out.detach(), ref) < 2e-6
-    out.sum().backward()
-    assert net.point_lin1.weight.grad is not None and net.vox_lin2.weight.grad is not None
+    (torch.from_numpy(z["c_out"]) * out).sum().backward()    # gradients of the reference module, make_golden_pointnet.py
+    assert rel_err(inp_g.grad, torch.from_numpy(z["grad.inp_feat"])) < 1e-5
+    for k, p_ in net.named_parameters():
+        assert rel_err(p_.grad, torch.from_numpy(z["grad." + k])) < 1e-5, k
     with torch.no_grad(), pytest.raises(RuntimeError, match="must be a CUDA tensor"):
         net(inp, idx)
 
