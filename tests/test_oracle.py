@@ -180,3 +180,26 @@ def test_oracle_is_differentiable_and_matches_reference_gradients(name, gname):
     for mod_name, params in (("offset_dec", off), ("prob_dec", prob)):
         for k, p in params.items():
             assert rel_err(p.grad, torch.from_numpy(z[f"grad.{mod_name}.{k}"])) < 1e-4, (mod_name, k)
+
+
+def test_factored_layer1_backward_algebra():
+    """with linear_1 applied to cat(voxel[vox], roi[ray], PE(pos), PE(dir)[ray]), the gradients of
+    the per-voxel / per-ray blocks are segment sums of delta1 followed by small GEMMs.  Checked against autograd in fp64."""
+    g = torch.Generator().manual_seed(11)
+    P, R, V = 500, 60, 17
+    vox = torch.randint(0, V, (P,), generator=g); ray = torch.randint(0, R, (P,), generator=g)
+    vf = torch.randn(V, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    roi = torch.randn(R, 128, generator=g, dtype=torch.float64, requires_grad=True)
+    pdir = torch.randn(R, 27, generator=g, dtype=torch.float64)
+    ppos = torch.randn(P, 102, generator=g, dtype=torch.float64)
+    W1 = torch.randn(256, 385, generator=g, dtype=torch.float64, requires_grad=True)
+    x = torch.cat((vf[vox], roi[ray], ppos, pdir[ray]), -1)                       # pipeline.py:431-433 column order
+    z1 = x @ W1.t()
+    delta1 = torch.randn(P, 256, generator=g, dtype=torch.float64)                # dL/dz1 arriving from layer 2
+    (z1 * delta1).sum().backward()
+    Gv = torch.zeros(V, 256, dtype=torch.float64).index_add_(0, vox, delta1)      # per-voxel segment sum
+    Gr = torch.zeros(R, 256, dtype=torch.float64).index_add_(0, ray, delta1)      # per-ray segment sum (CSR segments)
+    dW1 = torch.cat((Gv.t() @ vf.detach(), Gr.t() @ roi.detach(), delta1.t() @ ppos, Gr.t() @ pdir), 1)
+    assert torch.allclose(dW1, W1.grad, rtol=1e-10, atol=1e-10)
+    assert torch.allclose(Gv @ W1.detach()[:, :128], vf.grad, rtol=1e-10, atol=1e-10)
+    assert torch.allclose(Gr @ W1.detach()[:, 128:256], roi.grad, rtol=1e-10, atol=1e-10)
