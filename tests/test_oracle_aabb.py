@@ -91,3 +91,28 @@ def test_voxelisation_oracle_is_bit_exact_against_reference_code(name):
     assert np.array_equal(out["revidx"], z["ref_revidx"]) and np.array_equal(out["valid_v_pid"], z["ref_valid_v_pid"])
     assert np.array_equal(bits(out["valid_v_rel_coord"]), bits(z["ref_valid_v_rel_coord"]))
     assert 0 < out["valid_v_pid"].size < z["valid_xyz"].shape[0]          # some points fall outside the grid
+
+
+@pytest.mark.skipif(not os.path.exists(build_ref.LIB), reason="oracle/_ref not built (needs /root/reference)")
+def test_oracle_vs_reference_kernel_on_non_finite_and_extreme_inputs():
+    """inf / nan / denormal / huge components in directions, boxes and points: the restatement must follow the reference
+    kernel's comparisons and fmaxf / fminf exactly (NaN compares false, fmax ignores a NaN operand)."""
+    ref = build_ref.load()
+    rng = np.random.default_rng(7)
+    special = np.array([0.0, -0.0, np.inf, -np.inf, np.nan, 1e-45, -1e-45, 1e-38, 3e38, -3e38, 1e-12, -1e-12, 1.0, -1.0], np.float32)
+    for trial in range(6):
+        R, V = 300, 40
+        d = rng.normal(size=(R, 3)).astype(np.float32)
+        vb = np.concatenate((rng.uniform(-1, 1, (V, 3)), rng.uniform(1, 2, (V, 3))), 1).astype(np.float32)
+        pts = rng.uniform(-1.5, 2.5, size=(R, 3)).astype(np.float32)
+        for arr, frac in ((d, 0.15), (vb, 0.08), (pts, 0.15)):
+            m = rng.random(arr.shape) < frac
+            arr[m] = rng.choice(special, size=int(m.sum()))
+        rb = rng.integers(0, 2, size=R); xb = rng.integers(0, 2, size=V)
+        with np.errstate(all="ignore"):
+            m, dist = A.ray_aabb_dense(d, vb, rb, xb)
+        rm, rd = ref.ray_aabb(d, vb, rb, xb)
+        assert np.array_equal(m, rm), trial
+        hit = rm.astype(bool)
+        assert np.array_equal(bits(dist)[hit], bits(rd)[hit]) or np.array_equal(np.nan_to_num(dist[hit], nan=7.0), np.nan_to_num(rd[hit], nan=7.0))
+        assert np.array_equal(A.pcl_aabb_dense(pts, vb, rb, xb), ref.pcl_aabb(pts, vb, rb, xb)), trial
