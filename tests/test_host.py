@@ -243,3 +243,10 @@ def test_refine_training_path_cpu_matches_reference_output_and_has_gradients():
     out.abs().sum().backward()
     assert vfeat.grad is not None and float(vfeat.grad.abs().sum()) > 0
     assert refine.offset_dec.linear_1.weight.grad is not None
+
+
+def test_integration_doc_names_every_exported_symbol():
+    from implicit_depth_b200.extensions.lidf_query import jit
+    doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
+    for sym in jit.EXPORTED_SYMBOLS + jit.EXPORTED_SYMBOLS_AABB + jit.EXPORTED_SYMBOLS_POINTNET:
+        assert sym in doc, f"INTEGRATION.md does not mention {sym}"
