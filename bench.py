@@ -9,9 +9,11 @@ Workload at every N: BASELINE config 3 per GPU -- 8 images of 640x480 rays x 64 
 shipped decoders (IEF n_iter 2 + IMNet), i.e. weak scaling by image (no data-path collective).
 
 Printed JSON (one line, rank 0): value = whole-job points/s with inputs resident in HBM (CUDA-event timed, max over
-ranks); e2e = same metric through ``lidf_query.forward_host`` with pinned HOST buffers (H2D + D2H inside the timed
-region); roofline = nominal decoder FLOPs / decoder-kernel time vs the measured bf16 peak; cpu_baseline = the oracle
-port of the reference (stock torch CPU ops + torchvision roi_align) on the host cores, on a bounded sample.
+ranks); e2e = same metric through ``lidf_query.forward_host_async`` with pinned HOST buffers, steps issued back to back
+(every step's inputs H2D and all six outputs D2H inside the timed region; ``sync_ms_per_step`` = one isolated synchronous
+``forward_host`` call); roofline = nominal decoder FLOPs / decoder-kernel time vs the measured bf16 peak; cpu_baseline (N = 1
+only) = the oracle port of the reference (stock torch CPU ops + torchvision roi_align) on the host cores, on a bounded
+sample.  ``--workload c1|c2|c4|c5`` select the other BASELINE configs, ``--stage2`` adds config 5's RefineNet stage.
 
 ``--impl reference`` times that same CPU port as the reference arm (the reference is a Python/PyTorch program with no
 compiled artefact; /root/reference is not available on the GPU box).
