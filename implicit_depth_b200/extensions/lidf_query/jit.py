@@ -439,6 +439,15 @@ class _LidfQuery:
         dev = full_rgb_feat.device
         P = int(occ_vox_intersect_idx.shape[0]); R = int(miss_ray_dir.shape[0]); V = int(occ_voxel_feat.shape[0])
         B, _, H, W = (int(s) for s in full_rgb_feat.shape)
+        # shapes the kernels index with (the reference's CHECK_INPUT does not look at shapes; an out-of-bounds read would)
+        for name, t, shape in (("occ_voxel_feat", occ_voxel_feat, (V, 128)), ("miss_ray_dir", miss_ray_dir, (R, 3)),
+                               ("miss_img_ind", miss_img_ind, (R, 2)), ("miss_bid", miss_bid, (R,)),
+                               ("voxel_bound", voxel_bound, (V, 6)), ("occ_vox_intersect_idx", occ_vox_intersect_idx, (P,)),
+                               ("miss_ray_intersect_idx", miss_ray_intersect_idx, (P,))):
+            if tuple(t.shape) != shape:
+                raise RuntimeError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+        if pcl_label_float is not None and tuple(pcl_label_float.shape) != (P,):
+            raise RuntimeError(f"pcl_label_float must have shape {(P,)}, got {tuple(pcl_label_float.shape)}")
         keep: list = []
         p = _QueryParams()
         p.P, p.R, p.V, p.B, p.H, p.W = P, R, V, B, H, W

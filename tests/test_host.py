@@ -250,3 +250,18 @@ def test_integration_doc_names_every_exported_symbol():
     doc = open(os.path.join(REPO, "INTEGRATION.md")).read()
     for sym in jit.EXPORTED_SYMBOLS + jit.EXPORTED_SYMBOLS_AABB + jit.EXPORTED_SYMBOLS_POINTNET:
         assert sym in doc, f"INTEGRATION.md does not mention {sym}"
+
+
+def test_forward_rejects_inconsistent_shapes_before_touching_the_gpu():
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    d, cfg, off, prob, part, ref, _ = load_golden("ief_rel_sigmoid_1x16x20")
+    args = [d[k] for k in lidf_query.INPUT_KEYS]
+    bad = list(args); bad[3] = d["miss_img_ind"][:-1]                       # one ray short
+    with pytest.raises(RuntimeError, match="miss_img_ind must have shape"):
+        lidf_query.forward(*bad, off, prob, part_size=part)
+    bad = list(args); bad[5] = d["voxel_bound"][:, :5].contiguous()
+    with pytest.raises(RuntimeError, match="voxel_bound must have shape"):
+        lidf_query.forward(*bad, off, prob, part_size=part)
+    bad = list(args); bad[7] = d["miss_ray_intersect_idx"][:-2]
+    with pytest.raises(RuntimeError, match="miss_ray_intersect_idx must have shape"):
+        lidf_query.forward(*bad, off, prob, part_size=part)
