@@ -17,7 +17,7 @@ INCLUDE = os.path.join(REPO, "include")
 LIB_OVERRIDE = os.environ.get("LIDF_QUERY_LIB")
 LIB_PATH = LIB_OVERRIDE or os.path.join(CSRC, "liblidf_query.so")
 SOURCES = ["lidf_query.cu"]
-HEADERS = ["lidf_common.cuh", "lidf_prep.cuh", "lidf_simt.cuh", "lidf_tc.cuh", "lidf_aabb.cuh",
+HEADERS = ["lidf_common.cuh", "lidf_prep.cuh", "lidf_simt.cuh", "lidf_tc.cuh", "lidf_bwd.cuh", "lidf_aabb.cuh",
            "lidf_pointnet.cuh", os.path.join(INCLUDE, "lidf_query.h"), os.path.join(INCLUDE, "lidf_aabb.h"),
            os.path.join(INCLUDE, "lidf_pointnet.h")]
 # no --use_fast_math: the path needs the accurate sincosf / expf / IEEE division

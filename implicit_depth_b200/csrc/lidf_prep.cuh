@@ -8,14 +8,27 @@
 // ray adjacent, so we build a CSR by ray: ray_start[R+1] and perm[P] (sorted slot -> original pair).
 // Outputs are always written back at the ORIGINAL pair index, so results are order-independent.
 // ------------------------------------------------------------------------------------------------
+// Out-of-range keys are clamped into range (so every pair lands in some segment and nothing downstream indexes out of
+// bounds) and reported through *err; every kernel that reads pair_ray / pair_vox / miss_bid again clamps the same way.
+__device__ __forceinline__ int64_t lidf_clamp_idx(int64_t v, int64_t n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
 __global__ void k_count_pairs(const int64_t* __restrict__ pair_ray, int64_t P, int64_t R, int* __restrict__ cnt,
                               int* __restrict__ err) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   int64_t r = pair_ray[i];
-  if (r < 0 || r >= R) { atomicOr(err, 1); return; }
+  if (r < 0 || r >= R) { atomicOr(err, 1); r = lidf_clamp_idx(r, R); }
   atomicAdd(cnt + r, 1);
 }
+// range check of the other index arrays the kernels dereference (pair_vox over P, miss_bid over R)
+__global__ void k_validate_indices(const int64_t* __restrict__ pair_vox, int64_t P, int64_t V, const int64_t* __restrict__ bid,
+                                   int64_t R, int64_t B, int* __restrict__ err) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  bool bad = false;
+  if (pair_vox && i < P) { const int64_t v = pair_vox[i]; bad |= v < 0 || v >= V; }
+  if (bid && i < R) { const int64_t b = bid[i]; bad |= b < 0 || b >= B; }
+  if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(err, 2);
+}
+__global__ void k_publish_flag(const int* __restrict__ err, int32_t* __restrict__ out) { *out = *err; }
 
 // exclusive scan of int32 counts, 3 kernels (block partials, scan of partials, add back)
 #define LIDF_SCAN_BLOCK 1024
@@ -84,11 +97,11 @@ __global__ void k_scan_add(int* __restrict__ out, int64_t n, const int* __restri
 }
 
 // perm fill: slot = ray_start[ray] + (running cursor); cursor array must be zero on entry
-__global__ void k_fill_perm(const int64_t* __restrict__ pair_ray, int64_t P, const int* __restrict__ ray_start,
+__global__ void k_fill_perm(const int64_t* __restrict__ pair_ray, int64_t P, int64_t R, const int* __restrict__ ray_start,
                             int* __restrict__ cursor, int* __restrict__ perm) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
-  int r = (int)pair_ray[i];
+  int r = (int)lidf_clamp_idx(pair_ray[i], R);
   int slot = ray_start[r] + atomicAdd(cursor + r, 1);
   perm[slot] = (int)i;
 }
@@ -243,7 +256,7 @@ k_roi_align_rays(const float* __restrict__ feat, const float* __restrict__ box, 
   const int64_t ray_raw = (int64_t)blockIdx.x * 32 + lane;
   const int64_t ray = ray_raw < R ? ray_raw : R - 1;                 // tail lanes recompute the last ray (never stored)
   const int px = (int)img_ind[2 * ray], py = (int)img_ind[2 * ray + 1];
-  const int b = (int)bid[ray];
+  const int b = (int)lidf_clamp_idx(bid[ray], B);
   const bool interior = box != nullptr && half == 4 && px - 4 >= 0 && px + 4 <= W - 1 && py - 4 >= 0 && py + 4 <= H - 1;
   const bool defer = box != nullptr && border_list != nullptr && !interior;
   const unsigned dmask = __ballot_sync(0xffffffffu, defer && ray_raw < R);
@@ -297,7 +310,7 @@ k_roi_align_border(const float* __restrict__ feat, int B, int H, int W, const in
     const int64_t ray = border_list[idx < n ? idx : n - 1];
     if (warp == 0) s_ray[lane] = idx < n ? (int)ray : -1;
     const int px = (int)img_ind[2 * ray], py = (int)img_ind[2 * ray + 1];
-    const int b = (int)bid[ray];
+    const int b = (int)lidf_clamp_idx(bid[ray], B);
     const RoiBox rb = roi_box(px, py, half, H, W);
     const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
     for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {

@@ -17,6 +17,7 @@
 #include "lidf_prep.cuh"
 #include "lidf_simt.cuh"
 #include "lidf_tc.cuh"
+#include "lidf_bwd.cuh"
 
 static thread_local char g_cuda_err[256] = "";
 static thread_local int64_t g_launches = 0;
@@ -76,7 +77,7 @@ CsrBufs carve_csr(Bump& b, int64_t P, int64_t R) {
   return c;
 }
 
-int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, cudaStream_t st) {
+int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, cudaStream_t st, bool sort_segments = true) {
   const int64_t n = R + 1;
   LIDF_CUDA(cudaMemsetAsync(c.cnt, 0, sizeof(int) * (n + 1), st));
   if (P > 0) {
@@ -91,10 +92,12 @@ int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, c
   LIDF_LAUNCH_CHECK();
   if (P > 0) {
     LIDF_CUDA(cudaMemsetAsync(c.cnt, 0, sizeof(int) * n, st));
-    k_fill_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, c.ray_start, c.cnt, c.perm);
+    k_fill_perm<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.ray_start, c.cnt, c.perm);
     LIDF_LAUNCH_CHECK();
-    k_sort_segments<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(c.ray_start, R, c.perm);
-    LIDF_LAUNCH_CHECK();
+    if (sort_segments) {
+      k_sort_segments<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(c.ray_start, R, c.perm);
+      LIDF_LAUNCH_CHECK();
+    }
   }
   return LIDF_OK;
 }
@@ -153,7 +156,8 @@ int pack_wt(const float* w, int ldw, int col0, int K, int N, float* dst, int ldd
 // =================================================================================================
 extern "C" int lidf_query_abi_version(void) { return LIDF_QUERY_ABI_VERSION; }
 extern "C" size_t lidf_query_struct_size(int which) {
-  return which == 0 ? sizeof(LidfDecoder) : which == 1 ? sizeof(LidfQueryParams) : which == 2 ? sizeof(LidfRefineParams) : 0;
+  return which == 0 ? sizeof(LidfDecoder) : which == 1 ? sizeof(LidfQueryParams) : which == 2 ? sizeof(LidfRefineParams)
+         : which == 3 ? sizeof(LidfQueryBackwardParams) : 0;
 }
 
 extern "C" const char* lidf_query_error_string(int code) {
@@ -368,44 +372,26 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
 
 }  // namespace
 
-extern "C" size_t lidf_query_workspace_bytes(const LidfQueryParams* p) {
-  if (!p) return 0;
-  QueryPlan q;
-  if (plan_query(p, &q, nullptr) != LIDF_OK) return 0;
-  return q.bytes;
-}
 
-extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream) {
-  if (!p) return LIDF_ERR_NULL;
-  if (p->P < 0 || p->R < 0 || p->V < 0 || p->B <= 0 || p->H <= 0 || p->W <= 0) return LIDF_ERR_ARG;
-  if (p->P >= INT_MAX || p->R >= INT_MAX / 32 || p->V >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;
-  if (!p->max_pair_id || !p->pred_pos || !p->workspace) return LIDF_ERR_NULL;
-  if (p->R > 0 && (!p->full_rgb_feat || !p->miss_ray_dir || !p->miss_img_ind || !p->miss_bid)) return LIDF_ERR_NULL;
-  if (p->P > 0) {
-    if (!p->occ_voxel_feat || !p->voxel_bound || !p->pair_vox || !p->pair_ray) return LIDF_ERR_NULL;
-    if (!p->pair_dist && !p->dense_dist) return LIDF_ERR_NULL;
-    if (!p->pred_offset || !p->pred_prob_end || !p->pair_pred_pos || !p->pred_prob_end_softmax) return LIDF_ERR_NULL;
-  }
-  if (p->roi_inp_bbox < 0) return LIDF_ERR_ARG;
-  if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;   // pipeline.py:81-85
-  QueryPlan q;
-  int rc = plan_query(p, &q, (char*)p->workspace);
-  if (rc) return rc;
-  if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
-  if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
-  if ((rc = check_decoder(p->prob_dec, q.D))) return rc;
-  cudaStream_t st = stream;
+namespace {
+// steps 1-4 of the launch plan (shared by the forward and the backward, which recomputes them instead of keeping the
+// forward's workspace alive): pair regroup + index range check, ROIAlign per ray, weight packing, row prep (T, A_v)
+int run_prep(const LidfQueryParams* p, QueryPlan& q, cudaStream_t st) {
+  int rc;
   const int64_t P = p->P, R = p->R, V = p->V;
-  if (R == 0) return LIDF_OK;
-
-  // 1. regroup
+  // 1. regroup (flags out-of-range pair_ray in csr.cnt[R + 1]); range check of pair_vox / miss_bid into the same flag
   if ((rc = build_csr(q.csr, p->pair_ray, P, R, st))) return rc;
+  {
+    const int64_t n = P > R ? P : R;
+    k_validate_indices<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->pair_vox, P, V, p->miss_bid, R, p->B, q.csr.cnt + (R + 1));
+    LIDF_LAUNCH_CHECK();
+  }
   // 2. ROIAlign per ray
   if (q.box4) {
     if ((rc = roi_align_rays_box(p->full_rgb_feat, q.box4, q.border_list, q.border_count, p->B, p->H, p->W, p->miss_img_ind,
                                  p->miss_bid, R, p->roi_inp_bbox, q.roi_feat, st))) return rc;
   } else if ((rc = lidf_roi_align_rays(p->full_rgb_feat, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox,
-                                       q.roi_feat, stream))) return rc;
+                                       q.roi_feat, st))) return rc;
   if (P > 0) {
     // 3. weights
     const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
@@ -455,13 +441,54 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
         LIDF_LAUNCH_CHECK();
       }
     }
+  }
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_query_workspace_bytes(const LidfQueryParams* p) {
+  if (!p) return 0;
+  QueryPlan q;
+  if (plan_query(p, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream) {
+  if (!p) return LIDF_ERR_NULL;
+  if (p->P < 0 || p->R < 0 || p->V < 0 || p->B <= 0 || p->H <= 0 || p->W <= 0) return LIDF_ERR_ARG;
+  if (p->P >= INT_MAX || p->R >= INT_MAX / 32 || p->V >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;
+  if (!p->max_pair_id || !p->pred_pos || !p->workspace) return LIDF_ERR_NULL;
+  if (p->R > 0 && (!p->full_rgb_feat || !p->miss_ray_dir || !p->miss_img_ind || !p->miss_bid)) return LIDF_ERR_NULL;
+  if (p->P > 0) {
+    if (!p->occ_voxel_feat || !p->voxel_bound || !p->pair_vox || !p->pair_ray) return LIDF_ERR_NULL;
+    if (!p->pair_dist && !p->dense_dist) return LIDF_ERR_NULL;
+    if (!p->pred_offset || !p->pred_prob_end || !p->pair_pred_pos || !p->pred_prob_end_softmax) return LIDF_ERR_NULL;
+  }
+  if (p->roi_inp_bbox < 0) return LIDF_ERR_ARG;
+  if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;   // pipeline.py:81-85
+  QueryPlan q;
+  int rc = plan_query(p, &q, (char*)p->workspace);
+  if (rc) return rc;
+  if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
+  if ((rc = check_decoder(p->prob_dec, q.D))) return rc;
+  cudaStream_t st = stream;
+  const int64_t P = p->P, R = p->R, V = p->V;
+  if (R == 0) return LIDF_OK;
+
+  if ((rc = run_prep(p, q, st))) return rc;
+  if (p->index_error) { k_publish_flag<<<1, 1, 0, st>>>(q.csr.cnt + (R + 1), p->index_error); LIDF_LAUNCH_CHECK(); }
+  if (P > 0) {
+    const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
+    SimtPack& sp = q.sp;
     // 5. decoders
     if (q.impl == LIDF_MLP_SIMT_FP32) {
       SimtMlpArgs a{};
       a.rows = P; a.refine = 0; a.perm = q.csr.perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray;
-      a.pair_dist = p->pair_dist; a.dense_dist = p->dense_dist; a.R = R; a.ray_dir = p->miss_ray_dir;
+      a.pair_dist = p->pair_dist; a.dense_dist = p->dense_dist; a.R = R; a.V = V; a.ray_dir = p->miss_ray_dir;
       a.voxel_bound = p->voxel_bound; a.rel = p->intersect_pos_rel; a.pos_encode = p->pos_encode;
       a.multires = p->multires; a.KP = sp.KP; a.n_dec = 2;
+      a.o_iter = decs[0]->kind == LIDF_DEC_IEF ? p->ief_iter_out : nullptr;
       float* outs[2] = {p->pred_offset, p->pred_prob_end};
       for (int d = 0; d < 2; ++d) {
         const LidfDecoder& dc = *decs[d];
@@ -489,6 +516,308 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
                                                                      q.csr.ray_start, q.csr.perm, P, R,
                                                                      p->pred_prob_end_softmax, p->max_pair_id, p->pred_pos);
   LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
+
+// -------------------------------------------------------------------------------------------------
+// Backward of lidf_query_forward (lidf_bwd.cuh).  Launch plan, all on the caller's stream:
+//   run_prep (CSR, ROIAlign, T, A_v recomputed) -> weight streams (forward + transposed chunks) -> k_bwd_seed
+//   per decoder, per chunk of ray-major pairs, IEF passes in reverse order:
+//       k_mlp_bwd_tc -> k_wgrad_tc (dW3, dW2) ; after the passes: k_wgrad_tc (dW1[:,pos]), G_r / G_v segment sums
+//   per decoder: wgrad finish, column sums, dW1[:,rgb|dir|vox] = G^T [roi | PE(dir) | occ_voxel_feat] (k_wgrad_tc)
+//   d roi = G_r W1[:,rgb] -> k_roi_align_backward ; d occ_voxel_feat = G_v W1[:,vox]
+// -------------------------------------------------------------------------------------------------
+static thread_local cudaEvent_t g_ev_bwd[2] = {nullptr, nullptr};
+static thread_local bool g_ev_bwd_valid = false;
+
+namespace {
+struct BwdPlan {
+  QueryPlan q;
+  uint8_t* wbwd;                 // [2][20][8 KB]
+  float* g[2];                   // [P] dL/d o of the running IEF iteration, per decoder
+  int64_t chunk_rows;
+  float *h1, *h2, *d1, *d2, *d3, *pe;
+  int64_t* vkeys; CsrBufs vcsr;
+  float *Gr, *Gv, *pedir, *droi, *Wg;
+  float* partial; size_t partial_floats; int n_cta;
+  float* colpart; float* du; float* dc;
+  size_t bytes;
+};
+
+int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
+  LidfQueryParams fp = bp->fwd;
+  fp.mlp_impl = LIDF_MLP_TC_BF16X3; fp.roi_feat_per_ray = nullptr;
+  int rc = plan_query(&fp, &b->q, base);
+  if (rc) return rc;
+  const int64_t P = fp.P, R = fp.R, V = fp.V;
+  Bump bm{base, b->q.bytes};
+  b->wbwd = bm.take<uint8_t>((size_t)2 * BW_CHUNKS_BWD * TC_CHUNK_BYTES);
+  for (int d = 0; d < 2; ++d) b->g[d] = bm.take<float>((size_t)(P > 0 ? P : 1));
+  int64_t cr = bp->chunk_rows > 0 ? bp->chunk_rows : ((int64_t)1 << 21);
+  cr = (cr + 127) / 128 * 128;
+  const int64_t p_pad = (P + 127) / 128 * 128;
+  if (cr > p_pad) cr = p_pad;
+  if (cr < 128) cr = 128;
+  b->chunk_rows = cr;
+  b->h1 = bm.take<float>((size_t)cr * LIDF_H1); b->h2 = bm.take<float>((size_t)cr * LIDF_H2);
+  b->d1 = bm.take<float>((size_t)cr * LIDF_H1); b->d2 = bm.take<float>((size_t)cr * LIDF_H2);
+  b->d3 = bm.take<float>((size_t)cr * LIDF_H3); b->pe = bm.take<float>((size_t)cr * BW_PE_LD);
+  b->vkeys = bm.take<int64_t>((size_t)cr);
+  b->vcsr = carve_csr(bm, cr, V > 0 ? V : 1);
+  b->Gr = bm.take<float>((size_t)(R > 0 ? R : 1) * 512); b->Gv = bm.take<float>((size_t)(V > 0 ? V : 1) * 512);
+  b->pedir = bm.take<float>((size_t)(R > 0 ? R : 1) * 32);
+  b->droi = bm.take<float>((size_t)(R > 0 ? R : 1) * 128);
+  b->Wg = bm.take<float>((size_t)512 * 128);
+  b->n_cta = 148;
+  b->partial_floats = (size_t)256 * 128 + 256 * 32 + 256 * 128;                // row level: rgb | dir | vox  (>= dW3^T | dW2 | dW1[:,pos])
+  b->partial = bm.take<float>(b->partial_floats * b->n_cta);
+  b->colpart = bm.take<float>((size_t)b->n_cta * TC_ROW_WARPS * 32 * BW_COLPART);
+  b->du = bm.take<float>(256); b->dc = bm.take<float>(256);
+  b->bytes = bm.off + 256;
+  return LIDF_OK;
+}
+
+int sm_count() {
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0) sms = 148;
+  return sms;
+}
+
+size_t wgrad_smem_bytes(int M, int N) { return 1024 + 2 * ((size_t)(M / 128) * 4 * 8192 + (size_t)4 * N * 64); }
+
+// C partial slices += A^T B over `rows` rows
+int launch_wgrad(const float* A, int lda, int M, const float* B, int ldb, int N, int n_valid, int64_t rows, float* partial,
+                 int n_cta, cudaStream_t st) {
+  if (rows <= 0) return LIDF_OK;
+  if ((M != 128 && M != 256) || N % 16 || N < 16 || N > 256 || (M / 128) * N > 512) return LIDF_ERR_ARG;
+  WgArgs a{};
+  a.A = A; a.lda = lda; a.M = M; a.B = B; a.ldb = ldb; a.N = N; a.n_valid = n_valid; a.rows = rows; a.partial = partial;
+  const int64_t groups = (rows + WG_ROWS - 1) / WG_ROWS;
+  const int grid = (int)(groups < n_cta ? groups : n_cta);
+  const size_t smem = wgrad_smem_bytes(M, N);
+  LIDF_CUDA(cudaFuncSetAttribute(k_wgrad_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_wgrad_tc<3><<<grid, WG_THREADS, smem, st>>>(a);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+int finish_wgrad(const float* partial, int n_cta, int M, int N, int mode, float* dst, int ldd, int n_keep, int pe_pos,
+                 int ones_col, float* extra, cudaStream_t st) {
+  WgFinishArgs f{partial, n_cta, M, N, mode, dst, ldd, n_keep, pe_pos, ones_col, extra};
+  k_wgrad_finish<<<(M * N + 255) / 256, 256, 0, st>>>(f);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_query_backward_workspace_bytes(const LidfQueryBackwardParams* bp) {
+  if (!bp) return 0;
+  BwdPlan b;
+  if (plan_backward(bp, &b, nullptr) != LIDF_OK) return 0;
+  return b.bytes;
+}
+
+extern "C" float lidf_query_last_bwd_ms(void) {
+  if (!g_ev_bwd_valid) return -1.f;
+  float ms = -1.f;
+  if (cudaEventSynchronize(g_ev_bwd[1]) != cudaSuccess) return -1.f;
+  if (cudaEventElapsedTime(&ms, g_ev_bwd[0], g_ev_bwd[1]) != cudaSuccess) return -1.f;
+  return ms;
+}
+
+extern "C" size_t lidf_wgrad_selftest_scratch_bytes(int32_t M, int32_t N) { return (size_t)148 * M * N * sizeof(float) + 256; }
+extern "C" int lidf_wgrad_selftest(const float* A, const float* B, float* C, int64_t rows, int32_t M, int32_t N, void* scratch,
+                                   lidf_stream_t stream) {
+  if (!A || !B || !C || !scratch) return LIDF_ERR_NULL;
+  if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
+  cudaStream_t st = stream;
+  float* partial = (float*)scratch;
+  LIDF_CUDA(cudaMemsetAsync(partial, 0, (size_t)148 * M * N * sizeof(float), st));
+  int rc = launch_wgrad(A, M, M, B, N, N, N, rows, partial, 148, st);
+  if (rc) return rc;
+  return finish_wgrad(partial, 148, M, N, 1, C, N, N, 0, -1, nullptr, st);
+}
+
+extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_stream_t stream) {
+  if (!bp) return LIDF_ERR_NULL;
+  LidfQueryParams fp = bp->fwd;
+  fp.mlp_impl = LIDF_MLP_TC_BF16X3; fp.roi_feat_per_ray = nullptr; fp.index_error = nullptr; fp.ief_iter_out = nullptr;
+  const LidfQueryParams* p = &fp;
+  if (p->P < 0 || p->R < 0 || p->V < 0 || p->B <= 0 || p->H <= 0 || p->W <= 0) return LIDF_ERR_ARG;
+  if (p->P >= INT_MAX || p->R >= INT_MAX / 32 || p->V >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;
+  if (!bp->workspace) return LIDF_ERR_NULL;
+  if (p->R > 0 && (!p->full_rgb_feat || !p->miss_ray_dir || !p->miss_img_ind || !p->miss_bid || !p->max_pair_id)) return LIDF_ERR_NULL;
+  if (p->P > 0) {
+    if (!p->occ_voxel_feat || !p->voxel_bound || !p->pair_vox || !p->pair_ray) return LIDF_ERR_NULL;
+    if (!p->pair_dist && !p->dense_dist) return LIDF_ERR_NULL;
+    if (!p->pred_offset || !p->pred_prob_end) return LIDF_ERR_NULL;
+  }
+  if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;
+  if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
+  BwdPlan b;
+  int rc = plan_backward(bp, &b, (char*)bp->workspace);
+  if (rc) return rc;
+  if (bp->workspace_bytes < b.bytes) return LIDF_ERR_WORKSPACE;
+  QueryPlan& q = b.q;
+  if (!p->pos_encode || p->multires != 8 || q.pe_pos != 51 || p->multires_views != 4) return LIDF_ERR_UNSUPPORTED;
+  if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
+  if ((rc = check_decoder(p->prob_dec, q.D))) return rc;
+  const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
+  const LidfDecoderGrad* grads[2] = {&bp->g_offset_dec, &bp->g_prob_dec};
+  for (int d = 0; d < 2; ++d) {
+    const LidfDecoderGrad& gd = *grads[d];
+    if (!gd.w1 || !gd.b1 || !gd.w2 || !gd.b2 || !gd.w3 || !gd.b3 || !gd.w4 || !gd.b4) return LIDF_ERR_NULL;
+    if (decs[d]->kind == LIDF_DEC_IEF && (!gd.w_enc || !gd.b_enc)) return LIDF_ERR_NULL;
+  }
+  const int n_pass0 = decs[0]->kind == LIDF_DEC_IEF ? decs[0]->n_iter : 1;
+  if (n_pass0 > 1 && p->P > 0 && !bp->ief_iter) return LIDF_ERR_NULL;
+  cudaStream_t st = stream;
+  const int64_t P = p->P, R = p->R, V = p->V;
+  const int ldw[2] = {q.D + (decs[0]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0), q.D + (decs[1]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0)};
+
+  // every output is overwritten
+  for (int d = 0; d < 2; ++d) {
+    const LidfDecoderGrad& gd = *grads[d];
+    LIDF_CUDA(cudaMemsetAsync(gd.w1, 0, sizeof(float) * 256 * (size_t)ldw[d], st));
+    LIDF_CUDA(cudaMemsetAsync(gd.b1, 0, sizeof(float) * 256, st));
+    LIDF_CUDA(cudaMemsetAsync(gd.w2, 0, sizeof(float) * 128 * 256, st));
+    LIDF_CUDA(cudaMemsetAsync(gd.b2, 0, sizeof(float) * 128, st));
+    LIDF_CUDA(cudaMemsetAsync(gd.w3, 0, sizeof(float) * 64 * 128, st));
+    LIDF_CUDA(cudaMemsetAsync(gd.b3, 0, sizeof(float) * 64, st));
+    LIDF_CUDA(cudaMemsetAsync(gd.w4, 0, sizeof(float) * 64, st));
+    LIDF_CUDA(cudaMemsetAsync(gd.b4, 0, sizeof(float), st));
+    if (decs[d]->kind == LIDF_DEC_IEF) {
+      LIDF_CUDA(cudaMemsetAsync(gd.w_enc, 0, sizeof(float) * LIDF_IEF_ENC, st));
+      LIDF_CUDA(cudaMemsetAsync(gd.b_enc, 0, sizeof(float) * LIDF_IEF_ENC, st));
+    }
+  }
+  if (bp->g_full_rgb_feat) LIDF_CUDA(cudaMemsetAsync(bp->g_full_rgb_feat, 0, sizeof(float) * (size_t)p->B * LIDF_RGB_CH * p->H * p->W, st));
+  if (bp->g_occ_voxel_feat && V > 0) LIDF_CUDA(cudaMemsetAsync(bp->g_occ_voxel_feat, 0, sizeof(float) * (size_t)V * 128, st));
+  if (R == 0 || P == 0) return LIDF_OK;
+
+  if ((rc = run_prep(p, q, st))) return rc;
+  for (int d = 0; d < 2; ++d) {
+    k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(
+        decs[d]->w1, ldw[d], q.pe_pos, decs[d]->w2, decs[d]->w3, q.tc.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES, 0);
+    LIDF_LAUNCH_CHECK();
+    k_pack_tc_weights_bwd<<<(BW_CHUNKS_BWD * 2048 + 255) / 256, 256, 0, st>>>(decs[d]->w2, decs[d]->w3,
+                                                                             b.wbwd + (size_t)d * BW_CHUNKS_BWD * TC_CHUNK_BYTES);
+    LIDF_LAUNCH_CHECK();
+  }
+  LIDF_CUDA(cudaMemsetAsync(b.Gr, 0, sizeof(float) * (size_t)R * 512, st));
+  LIDF_CUDA(cudaMemsetAsync(b.Gv, 0, sizeof(float) * (size_t)V * 512, st));
+  {
+    BwSeedArgs a{};
+    a.P = P; a.R = R; a.pair_ray = p->pair_ray; a.max_pair_id = p->max_pair_id; a.ray_dir = p->miss_ray_dir;
+    a.pred_offset = p->pred_offset; a.pred_prob_end = p->pred_prob_end;
+    a.g_pred_pos = bp->g_pred_pos; a.g_pred_prob_end = bp->g_pred_prob_end; a.g_pred_offset = bp->g_pred_offset;
+    a.g_pair_pred_pos = bp->g_pair_pred_pos;
+    a.scale = (float)((double)(p->offset_range1 - p->offset_range0) * sqrt(3.0) * (double)p->part_size);
+    a.sig0 = decs[0]->use_sigmoid; a.sig1 = decs[1]->use_sigmoid; a.g0 = b.g[0]; a.g1 = b.g[1];
+    k_bwd_seed<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a);
+    LIDF_LAUNCH_CHECK();
+  }
+  k_bwd_pedir<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(p->miss_ray_dir, R, p->multires_views, p->pos_encode, b.pedir);
+  LIDF_LAUNCH_CHECK();
+
+  const int sms = sm_count();
+  const int n_cta = sms < b.n_cta ? sms : b.n_cta;
+  const size_t bw_smem = sizeof(BwSmem) + 1024;
+  LIDF_CUDA(cudaFuncSetAttribute(k_mlp_bwd_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw_smem));
+  if (!g_ev_bwd[0]) { cudaEventCreate(&g_ev_bwd[0]); cudaEventCreate(&g_ev_bwd[1]); }
+  cudaEventRecord(g_ev_bwd[0], st);
+  float* part_w3 = b.partial;                                   // [n_cta][128*64]
+  float* part_w2 = part_w3 + (size_t)b.n_cta * 128 * 64;        // [n_cta][128*256]
+  float* part_w1 = part_w2 + (size_t)b.n_cta * 128 * 256;       // [n_cta][256*112]
+  for (int d = 0; d < 2; ++d) {
+    const LidfDecoder& dc = *decs[d];
+    const LidfDecoderGrad& gd = *grads[d];
+    const bool ief = dc.kind == LIDF_DEC_IEF;
+    const int n_pass = ief ? dc.n_iter : 1;
+    LIDF_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float) * b.partial_floats * b.n_cta, st));
+    LIDF_CUDA(cudaMemsetAsync(b.colpart, 0, sizeof(float) * (size_t)b.n_cta * TC_ROW_WARPS * 32 * BW_COLPART, st));
+    for (int64_t s0 = 0; s0 < P; s0 += b.chunk_rows) {
+      const int n_rows = (int)((P - s0) < b.chunk_rows ? (P - s0) : b.chunk_rows);
+      const int n_tiles = (n_rows + 127) / 128;
+      for (int it = n_pass - 1; it >= 0; --it) {
+        BwArgs a{};
+        a.P = P; a.s0 = s0; a.n_rows = n_rows; a.n_tiles = n_tiles;
+        a.perm = q.csr.perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
+        a.dense_dist = p->dense_dist; a.R = R; a.V = V; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
+        a.rel = p->intersect_pos_rel; a.Av = q.Av; a.T = q.T; a.dcol = 256 * d;
+        a.wfwd = q.tc.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES;
+        a.wbwd = b.wbwd + (size_t)d * BW_CHUNKS_BWD * TC_CHUNK_BYTES;
+        a.u = ief ? q.sp.u[d] : nullptr; a.b2 = dc.b2; a.b3 = dc.b3; a.w4 = dc.w4;
+        a.is_ief = ief ? 1 : 0; a.it = it; a.o0 = ief ? dc.init_offset : 0.f;
+        a.o_in = (ief && it > 0) ? bp->ief_iter + (size_t)(it - 1) * P : nullptr;
+        a.g = b.g[d];
+        a.h1 = b.h1; a.h2 = b.h2; a.d1 = b.d1; a.d2 = b.d2; a.d3 = b.d3;
+        a.pe = it == n_pass - 1 ? b.pe : nullptr;
+        a.d1_accumulate = it == n_pass - 1 ? 0 : 1;
+        a.colpart = b.colpart;
+        const int grid = n_tiles < n_cta ? n_tiles : n_cta;
+        k_mlp_bwd_tc<3><<<grid, TC_THREADS, bw_smem, st>>>(a);
+        LIDF_LAUNCH_CHECK();
+        if ((rc = launch_wgrad(b.h2, LIDF_H2, 128, b.d3, LIDF_H3, 64, 64, n_rows, part_w3, n_cta, st))) return rc;     // dW3^T
+        if ((rc = launch_wgrad(b.d2, LIDF_H2, 128, b.h1, LIDF_H1, 256, 256, n_rows, part_w2, n_cta, st))) return rc;   // dW2
+      }
+      if ((rc = launch_wgrad(b.d1, LIDF_H1, 256, b.pe, BW_PE_LD, BW_PE_LD, BW_PE_LD, n_rows, part_w1, n_cta, st))) return rc;   // dW1[:,pos]
+      k_segsum_rays<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(b.d1, s0, n_rows, q.csr.ray_start, R, b.Gr, 256 * d);
+      LIDF_LAUNCH_CHECK();
+      k_chunk_vox_keys<<<(n_rows + 255) / 256, 256, 0, st>>>(q.csr.perm, p->pair_vox, s0, n_rows, V, b.vkeys);
+      LIDF_LAUNCH_CHECK();
+      if ((rc = build_csr(b.vcsr, b.vkeys, n_rows, V, st, false))) return rc;
+      k_segsum_vox<<<(n_rows + 63) / 64, 64, 0, st>>>(b.d1, b.vcsr.perm, b.vcsr.ray_start, V, n_rows, b.Gv, 256 * d);
+      LIDF_LAUNCH_CHECK();
+    }
+    if ((rc = finish_wgrad(part_w3, n_cta, 128, 64, 0, gd.w3, 0, 0, 0, -1, nullptr, st))) return rc;
+    if ((rc = finish_wgrad(part_w2, n_cta, 128, 256, 1, gd.w2, 256, 256, 0, -1, nullptr, st))) return rc;
+    if ((rc = finish_wgrad(part_w1, n_cta, 256, BW_PE_LD, 2, gd.w1, ldw[d], 0, q.pe_pos, -1, nullptr, st))) return rc;
+    k_bwd_colpart_finish<<<1, 512, 0, st>>>(b.colpart, n_cta, gd.b2, gd.b3, gd.w4, gd.b4, ief ? b.du : nullptr);
+    LIDF_LAUNCH_CHECK();
+    // row-level weight gradients of layer 1 from the segment sums: dW1[:,rgb] = G_r^T roi, dW1[:,dir] = G_r^T PE(dir)
+    // (+ its ones column = sum_r G_r = db1 / d c), dW1[:,vox] = G_v^T occ_voxel_feat
+    LIDF_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float) * b.partial_floats * b.n_cta, st));
+    float* part_rgb = b.partial;                                // [n_cta][256*128]
+    float* part_dir = part_rgb + (size_t)b.n_cta * 256 * 128;   // [n_cta][256*32]
+    float* part_vox = part_dir + (size_t)b.n_cta * 256 * 32;    // [n_cta][256*128]
+    if ((rc = launch_wgrad(b.Gr + 256 * d, 512, 256, q.roi_feat, 128, 128, 128, R, part_rgb, n_cta, st))) return rc;
+    if ((rc = launch_wgrad(b.Gr + 256 * d, 512, 256, b.pedir, 32, 32, 32, R, part_dir, n_cta, st))) return rc;
+    if ((rc = launch_wgrad(b.Gv + 256 * d, 512, 256, p->occ_voxel_feat, 128, 128, 128, V, part_vox, n_cta, st))) return rc;
+    if ((rc = finish_wgrad(part_rgb, n_cta, 256, 128, 1, gd.w1 + LIDF_VOX_DIM, ldw[d], 128, 0, -1, nullptr, st))) return rc;
+    if ((rc = finish_wgrad(part_dir, n_cta, 256, 32, 3, gd.w1 + LIDF_VOX_DIM + LIDF_RGB_DIM + 2 * q.pe_pos, ldw[d], q.pe_dir, 0, 27,
+                           b.dc, st))) return rc;
+    if ((rc = finish_wgrad(part_vox, n_cta, 256, 128, 1, gd.w1, ldw[d], 128, 0, -1, nullptr, st))) return rc;
+    k_bwd_finish_decoder<<<1, 256, 0, st>>>(dc.w1, ldw[d], q.D, dc.w_enc, dc.b_enc, ief ? 1 : 0, b.du, b.dc, gd.w1, gd.b1,
+                                            gd.w_enc, gd.b_enc);
+    LIDF_LAUNCH_CHECK();
+  }
+  cudaEventRecord(g_ev_bwd[1], st);
+  g_ev_bwd_valid = true;
+  // feature gradients: d roi = G_r [W1_off[:,rgb]; W1_prob[:,rgb]] -> ROIAlign^T ; d occ_voxel_feat = G_v [W1[:,vox]; ...]
+  const size_t gemm_smem = sizeof(float) * ((size_t)LIDF_SIMT_BM * 512 + LIDF_KC * 128);
+  LIDF_CUDA(cudaFuncSetAttribute(k_bwd_rows_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
+  if (bp->g_full_rgb_feat) {
+    for (int d = 0; d < 2; ++d) {
+      k_bwd_pack_rows<<<(256 * 128 + 255) / 256, 256, 0, st>>>(decs[d]->w1, ldw[d], LIDF_VOX_DIM, 256, b.Wg, 256 * d);
+      LIDF_LAUNCH_CHECK();
+    }
+    k_bwd_rows_gemm<<<(unsigned)((R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), LIDF_SIMT_THREADS, gemm_smem, st>>>(b.Gr, R, b.Wg, b.droi);
+    LIDF_LAUNCH_CHECK();
+    k_roi_align_backward<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, st>>>(b.droi, p->B, p->H, p->W, p->miss_img_ind,
+                                                                                  p->miss_bid, R, p->roi_inp_bbox / 2,
+                                                                                  bp->g_full_rgb_feat);
+    LIDF_LAUNCH_CHECK();
+  }
+  if (bp->g_occ_voxel_feat && V > 0) {
+    for (int d = 0; d < 2; ++d) {
+      k_bwd_pack_rows<<<(256 * 128 + 255) / 256, 256, 0, st>>>(decs[d]->w1, ldw[d], 0, 256, b.Wg, 256 * d);
+      LIDF_LAUNCH_CHECK();
+    }
+    k_bwd_rows_gemm<<<(unsigned)((V + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), LIDF_SIMT_THREADS, gemm_smem, st>>>(b.Gv, V, b.Wg,
+                                                                                                             bp->g_occ_voxel_feat);
+    LIDF_LAUNCH_CHECK();
+  }
   return LIDF_OK;
 }
 

@@ -9,6 +9,7 @@
 // so the static part of layer 1 is evaluated once and every IEF iteration adds the rank-1 term u*(o - o0).
 #pragma once
 #include "lidf_common.cuh"
+#include "lidf_prep.cuh"
 
 #define LIDF_SIMT_THREADS 256
 #define LIDF_SIMT_BM 64
@@ -172,7 +173,7 @@ struct SimtMlpArgs {
   // pair mode
   const int* perm;              // sorted slot -> original pair (NULL = identity)
   const int64_t* pair_vox; const int64_t* pair_ray;
-  const float* pair_dist; const float* dense_dist; int64_t R;
+  const float* pair_dist; const float* dense_dist; int64_t R; int64_t V;
   const float* ray_dir; const float* voxel_bound;
   // refine mode
   const float* pos_in; const float* center_in;
@@ -182,6 +183,7 @@ struct SimtMlpArgs {
   float r0, r1, scale;          // pos = enter + ((off*(r1-r0)+r0)*scale_a)*scale_b * dir
   float scale2;
   float* pos_out;               // pair_pred_pos [P,3] / pred_pos_refine [R,3]
+  float* o_iter;                // [n_pass-1][rows] or NULL: dec[0]'s running IEF offset after every iteration but the last
 };
 
 __global__ void __launch_bounds__(LIDF_SIMT_THREADS) k_mlp_simt(const SimtMlpArgs a) {
@@ -210,7 +212,7 @@ __global__ void __launch_bounds__(LIDF_SIMT_THREADS) k_mlp_simt(const SimtMlpArg
     if (s < a.rows) {
       if (!a.refine) {
         orig = a.perm ? a.perm[s] : (int)s;
-        vox = (int)a.pair_vox[orig]; ray = (int)a.pair_ray[orig];
+        vox = (int)lidf_clamp_idx(a.pair_vox[orig], a.V); ray = (int)lidf_clamp_idx(a.pair_ray[orig], a.R);
         float t0, t1;
         if (a.pair_dist) { t0 = a.pair_dist[2 * (size_t)orig]; t1 = a.pair_dist[2 * (size_t)orig + 1]; }
         else { const size_t o = ((size_t)vox * a.R + ray) * 2; t0 = a.dense_dist[o]; t1 = a.dense_dist[o + 1]; }
@@ -323,6 +325,8 @@ __global__ void __launch_bounds__(LIDF_SIMT_THREADS) k_mlp_simt(const SimtMlpArg
           p += D.b4[0];
           if (D.kind == LIDF_DEC_IEF) s_o[r] += p;      // pred_offset += l4 (implicit_net.py:146)
           else s_o[r] = p;
+          if (a.o_iter && di == 0 && D.kind == LIDF_DEC_IEF && it + 1 < D.n_pass && s_orig[r] >= 0)
+            a.o_iter[(size_t)it * a.rows + s_orig[r]] = s_o[r];
         }
       }
       __syncthreads();

@@ -43,6 +43,7 @@
 #include <cuda_bf16.h>
 
 #include "lidf_common.cuh"
+#include "lidf_prep.cuh"
 
 #define TC_ROW_WARPS 16
 #define TC_ROW_THREADS (TC_ROW_WARPS * 32)
@@ -436,7 +437,7 @@ __device__ __forceinline__ void bar_quadrant(int q) { asm volatile("bar.sync %0,
 struct TcArgs {
   int64_t P; int n_tiles;
   const int* perm; const int64_t* pair_vox; const int64_t* pair_ray;
-  const float* pair_dist; const float* dense_dist; int64_t R;
+  const float* pair_dist; const float* dense_dist; int64_t R; int64_t V;
   const float* ray_dir; const float* voxel_bound; int rel;
   const float* pos_in;             // RefineNet tail: row = ray, position given ([P,3]); pair_ray / dist are not read
   const float* Av;                 // [V][512] per-voxel layer-1 term, decoder d at column 256 d
@@ -453,6 +454,7 @@ struct TcArgs {
   float* out[2];                   // pred_offset, pred_prob_end  (written at the original pair index)
   float* pos_out;                  // pair_pred_pos [P,3]
   int n_prod;                      // bf16 products per MAC: 3 (hi*hi + lo*hi + hi*lo) or 1
+  float* o_iter;                   // [n_pass[0]-1][P] or NULL: decoder 0's running IEF offset after every iteration but the last
 };
 
 struct TcSmem {
@@ -728,7 +730,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       if (s < a.P) {
         m.valid = true;
         m.orig = orig_;
-        m.vox = (int)a.pair_vox[m.orig]; m.ray = a.pos_in ? m.orig : (int)a.pair_ray[m.orig];
+        // out-of-range indices are clamped (and reported by k_count_pairs / k_validate_indices), never dereferenced
+        m.vox = (int)lidf_clamp_idx(a.pair_vox[m.orig], a.V);
+        m.ray = a.pos_in ? m.orig : (int)lidf_clamp_idx(a.pair_ray[m.orig], a.R);
         if (a.pos_in) { }
         else if (a.pair_dist) { const float2 t = *reinterpret_cast<const float2*>(a.pair_dist + 2 * (size_t)m.orig); m.t0 = t.x; m.t1 = t.y; }
         else { const size_t o = ((size_t)m.vox * a.R + m.ray) * 2; m.t0 = a.dense_dist[o]; m.t1 = a.dense_dist[o + 1]; }
@@ -922,6 +926,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       const float prev = it == 0 ? (is_ief ? a.o0 : 0.f) : (d == 0 ? o_a : o_b);
       const float onew = is_ief ? prev + l4 : l4;
       if (d == 0) o_a = onew; else o_b = onew;
+      if (a.o_iter && d == 0 && g == 0 && it + 1 < npass0 && (int64_t)tile_ * 128 + row < a.P)
+        a.o_iter[(size_t)it * a.P + S.m_orig[buf][row]] = onew;
       if (it + 1 == (d == 0 ? npass0 : npass1) && (int64_t)tile_ * 128 + row < a.P) {
         const float res = lidf_final_act(onew, d == 0 ? sig0 : sig1);
         const int orig = S.m_orig[buf][row];
@@ -1270,8 +1276,9 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   TcArgs a{};
   a.P = p->P; a.n_tiles = (int)((p->P + 127) / 128);
   a.perm = perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
-  a.dense_dist = p->dense_dist; a.R = p->R; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
+  a.dense_dist = p->dense_dist; a.R = p->R; a.V = p->V; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
   a.rel = p->intersect_pos_rel; a.Av = Av; a.T = T; a.wstream = tb.wstream;
+  a.o_iter = decs[0]->kind == LIDF_DEC_IEF ? p->ief_iter_out : nullptr;
   a.u = decs[0]->kind == LIDF_DEC_IEF ? u : nullptr;
   for (int d = 0; d < 2; ++d) {
     a.b2[d] = decs[d]->b2; a.b3[d] = decs[d]->b3; a.w4[d] = decs[d]->w4; a.b4[d] = decs[d]->b4;
@@ -1332,7 +1339,7 @@ inline int tc_refine_forward(const LidfRefineParams* p, const TcBufs& tb, const 
   TcArgs a{};
   a.P = p->R; a.n_tiles = (int)((p->R + 127) / 128);
   a.perm = nullptr; a.pair_vox = p->end_voxel_id; a.pair_ray = nullptr; a.pair_dist = nullptr; a.dense_dist = nullptr;
-  a.R = p->R; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound; a.rel = p->intersect_pos_rel;
+  a.R = p->R; a.V = p->V; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound; a.rel = p->intersect_pos_rel;
   a.pos_in = p->pred_pos; a.Av = Av; a.T = T; a.wstream = tb.wstream;
   a.u = dc.kind == LIDF_DEC_IEF ? u : nullptr;
   for (int d = 0; d < 2; ++d) { a.b2[d] = dc.b2; a.b3[d] = dc.b3; a.w4[d] = dc.w4; a.b4[d] = dc.b4; a.use_sigmoid[d] = dc.use_sigmoid; }

@@ -47,7 +47,20 @@ class _QueryParams(C.Structure):
                 ("offset_dec", _Decoder), ("prob_dec", _Decoder), ("mlp_impl", C.c_int32),
                 ("pred_offset", C.c_void_p), ("pred_prob_end", C.c_void_p), ("pair_pred_pos", C.c_void_p),
                 ("pred_prob_end_softmax", C.c_void_p), ("max_pair_id", C.c_void_p), ("pred_pos", C.c_void_p),
-                ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
+                ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
+                ("ief_iter_out", C.c_void_p), ("index_error", C.c_void_p)]
+
+
+class _DecoderGrad(C.Structure):
+    _fields_ = [(k, C.c_void_p) for k in ("w1", "b1", "w2", "b2", "w3", "b3", "w4", "b4", "w_enc", "b_enc")]
+
+
+class _BackwardParams(C.Structure):
+    _fields_ = [("fwd", _QueryParams), ("ief_iter", C.c_void_p),
+                ("g_pred_pos", C.c_void_p), ("g_pred_prob_end", C.c_void_p), ("g_pred_offset", C.c_void_p),
+                ("g_pair_pred_pos", C.c_void_p), ("g_full_rgb_feat", C.c_void_p), ("g_occ_voxel_feat", C.c_void_p),
+                ("g_offset_dec", _DecoderGrad), ("g_prob_dec", _DecoderGrad), ("chunk_rows", C.c_int64),
+                ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t)]
 
 
 class _RefineParams(C.Structure):
@@ -60,13 +73,15 @@ class _RefineParams(C.Structure):
                 ("V", C.c_int64), ("occ_voxel_feat", C.c_void_p), ("end_voxel_id", C.c_void_p), ("voxel_bound", C.c_void_p)]
 
 
-ABI_VERSION = 2
+ABI_VERSION = 3
 EXPORTED_SYMBOLS = [
     "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
     "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
     "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
     "lidf_image_loss_workspace_bytes", "lidf_image_loss",
+    "lidf_query_backward_workspace_bytes", "lidf_query_backward", "lidf_query_last_bwd_ms",
+    "lidf_wgrad_selftest_scratch_bytes", "lidf_wgrad_selftest",
 ]
 # include/lidf_pointnet.h (bound by models/pointnet.py)
 EXPORTED_SYMBOLS_POINTNET = ["lidf_pointnet_workspace_bytes", "lidf_pointnet_forward"]
@@ -94,6 +109,15 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_query_workspace_bytes.argtypes = [C.POINTER(_QueryParams)]
     lib.lidf_query_forward.restype = C.c_int
     lib.lidf_query_forward.argtypes = [C.POINTER(_QueryParams), C.c_void_p]
+    lib.lidf_query_backward_workspace_bytes.restype = C.c_size_t
+    lib.lidf_query_backward_workspace_bytes.argtypes = [C.POINTER(_BackwardParams)]
+    lib.lidf_query_backward.restype = C.c_int
+    lib.lidf_query_backward.argtypes = [C.POINTER(_BackwardParams), C.c_void_p]
+    lib.lidf_query_last_bwd_ms.restype = C.c_float
+    lib.lidf_wgrad_selftest_scratch_bytes.restype = C.c_size_t
+    lib.lidf_wgrad_selftest_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
+    lib.lidf_wgrad_selftest.restype = C.c_int
+    lib.lidf_wgrad_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.lidf_refine_workspace_bytes.restype = C.c_size_t
     lib.lidf_refine_workspace_bytes.argtypes = [C.POINTER(_RefineParams)]
     lib.lidf_refine_forward.restype = C.c_int
@@ -147,7 +171,7 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
         raise RuntimeError("liblidf_query.so ABI version mismatch")
     lib.lidf_query_struct_size.restype = C.c_size_t
     lib.lidf_query_struct_size.argtypes = [C.c_int]
-    for which, st in enumerate((_Decoder, _QueryParams, _RefineParams)):
+    for which, st in enumerate((_Decoder, _QueryParams, _RefineParams, _BackwardParams)):
         if lib.lidf_query_struct_size(which) != C.sizeof(st):
             raise RuntimeError(f"ctypes layout of {st.__name__} does not match the compiled library")
     return lib
@@ -424,19 +448,14 @@ class _LidfQuery:
         call.pending = (done, bad_host, live, bad)
 
     # ------------------------------------------------------------------ fused get_embedding + get_pred
-    def forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
-                occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, *,
-                part_size: float, pos_encode: bool = True, multires: int = 8, multires_views: int = 4,
-                intersect_pos_type: str = "abs", roi_inp_bbox: int = 8, roi_out_bbox: int = 2,
-                n_iter: int = 2, use_sigmoid: bool = False, offset_range: Sequence[float] = (0.0, 1.0),
-                pcl_label_float: Optional[torch.Tensor] = None, mlp_impl: str = "auto",
-                want_roi_feat: bool = False) -> Dict[str, torch.Tensor]:
-        """Everything LIDF.get_embedding + LIDF.get_pred compute after the ResNet / PointNet producers
-        (reference src/models/pipeline.py:338-466).  ``dist`` is either the per-pair [P,2] enter/leave distances or
-        the reference's dense [V,R,2] tensor.  Returns the data_dict entries of pipeline.py:460-466 (+ pred_offset)."""
+    def _query_params(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                      occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, keep, *,
+                      part_size, pos_encode=True, multires=8, multires_views=4, intersect_pos_type="abs", roi_inp_bbox=8,
+                      roi_out_bbox=2, n_iter=2, use_sigmoid=False, offset_range=(0.0, 1.0), pcl_label_float=None,
+                      mlp_impl="auto") -> _QueryParams:
+        """Input half of the parameter block (shared by forward and backward): shape / dtype / device checks included."""
         if roi_out_bbox != 2 or tuple(full_rgb_feat.shape[1:2]) != (32,) or occ_voxel_feat.shape[-1] != 128:
             raise RuntimeError("lidf_query supports rgb_out=32, roi_out_bbox=2, pnet_out=128 only (shipped YAMLs)")
-        dev = full_rgb_feat.device
         P = int(occ_vox_intersect_idx.shape[0]); R = int(miss_ray_dir.shape[0]); V = int(occ_voxel_feat.shape[0])
         B, _, H, W = (int(s) for s in full_rgb_feat.shape)
         # shapes the kernels index with (the reference's CHECK_INPUT does not look at shapes; an out-of-bounds read would)
@@ -448,7 +467,6 @@ class _LidfQuery:
                 raise RuntimeError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
         if pcl_label_float is not None and tuple(pcl_label_float.shape) != (P,):
             raise RuntimeError(f"pcl_label_float must have shape {(P,)}, got {tuple(pcl_label_float.shape)}")
-        keep: list = []
         p = _QueryParams()
         p.P, p.R, p.V, p.B, p.H, p.W = P, R, V, B, H, W
         p.full_rgb_feat = _chk(full_rgb_feat, "full_rgb_feat", torch.float32)
@@ -475,6 +493,47 @@ class _LidfQuery:
         p.offset_dec = _decoder_struct(decoder_state(offset_dec), n_iter, use_sigmoid, keep, "offset_dec")
         p.prob_dec = _decoder_struct(decoder_state(prob_dec), n_iter, use_sigmoid, keep, "prob_dec")
         p.mlp_impl = MLP_IMPLS[mlp_impl]
+        return p
+
+    def check_index_errors(self, wait: bool = True) -> None:
+        """Raise if an earlier ``forward`` saw an out-of-range pair_ray / pair_vox / miss_bid value.  The kernels clamp
+        such indices (no out-of-bounds access) and set a device flag that is copied to pinned host memory right behind
+        the call; it is looked at here -- without a sync when ``wait`` is false (every later ``forward`` does that), after
+        waiting for the copy when true.  The reference trips a device-side assert in the same situation."""
+        pend, self._pending_flags = getattr(self, "_pending_flags", []), []
+        for flag_host, ev in pend:
+            if wait:
+                ev.synchronize()
+            if not ev.query():
+                self._pending_flags.append((flag_host, ev))
+            elif int(flag_host[0]) != 0:
+                self._pending_flags = []
+                raise RuntimeError("lidf_query_forward: index out of range in miss_ray_intersect_idx / occ_vox_intersect_idx "
+                                   f"/ miss_bid (flag {int(flag_host[0])}); the affected outputs are meaningless")
+
+    def forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, *,
+                part_size: float, pos_encode: bool = True, multires: int = 8, multires_views: int = 4,
+                intersect_pos_type: str = "abs", roi_inp_bbox: int = 8, roi_out_bbox: int = 2,
+                n_iter: int = 2, use_sigmoid: bool = False, offset_range: Sequence[float] = (0.0, 1.0),
+                pcl_label_float: Optional[torch.Tensor] = None, mlp_impl: str = "auto",
+                want_roi_feat: bool = False, save_for_backward: bool = False,
+                check_indices: bool = False) -> Dict[str, torch.Tensor]:
+        """Everything LIDF.get_embedding + LIDF.get_pred compute after the ResNet / PointNet producers
+        (reference src/models/pipeline.py:338-466).  ``dist`` is either the per-pair [P,2] enter/leave distances or
+        the reference's dense [V,R,2] tensor.  Returns the data_dict entries of pipeline.py:460-466 (+ pred_offset).
+        ``save_for_backward`` adds ``ief_iter`` (the IEF offsets between iterations, which ``backward`` needs);
+        ``check_indices`` waits for the call and raises on an out-of-range index (otherwise the next call reports it)."""
+        self.check_index_errors(wait=False)
+        dev = full_rgb_feat.device
+        keep: list = []
+        p = self._query_params(full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                               occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, keep,
+                               part_size=part_size, pos_encode=pos_encode, multires=multires, multires_views=multires_views,
+                               intersect_pos_type=intersect_pos_type, roi_inp_bbox=roi_inp_bbox, roi_out_bbox=roi_out_bbox,
+                               n_iter=n_iter, use_sigmoid=use_sigmoid, offset_range=offset_range,
+                               pcl_label_float=pcl_label_float, mlp_impl=mlp_impl)
+        P, R = int(p.P), int(p.R)
         f32 = dict(dtype=torch.float32, device=dev)
         out = dict(pred_offset=torch.empty(P, 1, **f32), pred_prob_end=torch.empty(P, 1, **f32),
                    pair_pred_pos=torch.empty(P, 3, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
@@ -482,6 +541,12 @@ class _LidfQuery:
         if want_roi_feat:
             out["roi_feat_per_ray"] = torch.empty(R, 128, **f32)
             p.roi_feat_per_ray = out["roi_feat_per_ray"].data_ptr()
+        if save_for_backward:
+            n_it = int(p.offset_dec.n_iter) if p.offset_dec.kind == 1 else 1
+            out["ief_iter"] = torch.empty(max(n_it - 1, 0), P, **f32)
+            p.ief_iter_out = out["ief_iter"].data_ptr() if n_it > 1 and P > 0 else None
+        flag = torch.zeros(1, dtype=torch.int32, device=dev)
+        p.index_error = flag.data_ptr()
         for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
             setattr(p, k, out[k].data_ptr())
         nbytes = int(self.lib.lidf_query_workspace_bytes(C.byref(p)))
@@ -490,10 +555,96 @@ class _LidfQuery:
         ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
         p.workspace, p.workspace_bytes = ws.data_ptr(), nbytes
         with torch.cuda.device(dev):
-            stream = torch.cuda.current_stream(dev).cuda_stream
-            rc = self.lib.lidf_query_forward(C.byref(p), C.c_void_p(stream))
-        self._raise(rc, "lidf_query_forward")
-        ws.record_stream(torch.cuda.current_stream(dev))
+            cur = torch.cuda.current_stream(dev)
+            rc = self.lib.lidf_query_forward(C.byref(p), C.c_void_p(cur.cuda_stream))
+            self._raise(rc, "lidf_query_forward")
+            flag_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            flag_host.copy_(flag, non_blocking=True)
+            ev = torch.cuda.Event(); ev.record(cur)
+        ws.record_stream(cur); flag.record_stream(cur)
+        if not hasattr(self, "_pending_flags"):
+            self._pending_flags = []
+        self._pending_flags.append((flag_host, ev))
+        if check_indices:
+            self.check_index_errors(wait=True)
+        return out
+
+    def backward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                 occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, fwd_out, *,
+                 g_pred_pos=None, g_pred_prob_end=None, g_pred_offset=None, g_pair_pred_pos=None,
+                 need_feat_grad: bool = True, need_vox_grad: bool = True, chunk_rows: int = 0, **kw):
+        """Backward of ``forward`` (include/lidf_query.h: lidf_query_backward): what torch autograd does for the reference's
+        get_embedding + get_pred under ``loss_net.backward()`` (reference src/trainers/train_lidf.py:394).  ``fwd_out`` is
+        the dict ``forward(..., save_for_backward=True)`` returned; ``kw`` are the same scalar settings.  Returns
+        ``dict(full_rgb_feat=..., occ_voxel_feat=..., offset_dec={state_dict key: grad}, prob_dec={...})``."""
+        dev = full_rgb_feat.device
+        keep: list = []
+        kw.pop("want_roi_feat", None); kw.pop("save_for_backward", None); kw.pop("check_indices", None)
+        bp = _BackwardParams()
+        bp.fwd = self._query_params(full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                                    occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, keep, **kw)
+        P, R, V = int(bp.fwd.P), int(bp.fwd.R), int(bp.fwd.V)
+        f32 = dict(dtype=torch.float32, device=dev)
+        bp.fwd.pred_offset = _chk(fwd_out["pred_offset"], "pred_offset", torch.float32)
+        bp.fwd.pred_prob_end = _chk(fwd_out["pred_prob_end"], "pred_prob_end", torch.float32)
+        bp.fwd.max_pair_id = _chk(fwd_out["max_pair_id"], "max_pair_id", torch.int64)
+        n_it = int(bp.fwd.offset_dec.n_iter) if bp.fwd.offset_dec.kind == 1 else 1
+        if n_it > 1 and P > 0:
+            it = fwd_out.get("ief_iter")
+            if it is None or tuple(it.shape) != (n_it - 1, P):
+                raise RuntimeError("backward needs fwd_out['ief_iter'] [n_iter-1, P]: call forward(save_for_backward=True)")
+            bp.ief_iter = _chk(it, "ief_iter", torch.float32)
+        for name, t, shape in (("g_pred_pos", g_pred_pos, (R, 3)), ("g_pred_prob_end", g_pred_prob_end, (P, 1)),
+                               ("g_pred_offset", g_pred_offset, (P, 1)), ("g_pair_pred_pos", g_pair_pred_pos, (P, 3))):
+            if t is not None:
+                if tuple(t.shape) != shape and tuple(t.shape) != shape[:1]:
+                    raise RuntimeError(f"{name} must have shape {shape}, got {tuple(t.shape)}")
+                t = t.contiguous(); keep.append(t)
+                setattr(bp, name, _chk(t, name, torch.float32))
+        res = dict(full_rgb_feat=torch.empty_like(full_rgb_feat) if need_feat_grad else None,
+                   occ_voxel_feat=torch.empty_like(occ_voxel_feat) if need_vox_grad else None)
+        bp.g_full_rgb_feat = res["full_rgb_feat"].data_ptr() if need_feat_grad else None
+        bp.g_occ_voxel_feat = res["occ_voxel_feat"].data_ptr() if need_vox_grad else None
+        names = (("w1", "linear_1.weight"), ("b1", "linear_1.bias"), ("w2", "linear_2.weight"), ("b2", "linear_2.bias"),
+                 ("w3", "linear_3.weight"), ("b3", "linear_3.bias"), ("w4", "linear_4.weight"), ("b4", "linear_4.bias"),
+                 ("w_enc", "offset_enc.weight"), ("b_enc", "offset_enc.bias"))
+        for field, dec in (("g_offset_dec", offset_dec), ("g_prob_dec", prob_dec)):
+            sd = decoder_state(dec)
+            gd, gs = _DecoderGrad(), {}
+            for f, key in names:
+                if key in sd:
+                    gs[key] = torch.empty(sd[key].shape, **f32)
+                    setattr(gd, f, gs[key].data_ptr())
+            setattr(bp, field, gd)
+            res[field[2:]] = gs
+        bp.chunk_rows = int(chunk_rows)
+        nbytes = int(self.lib.lidf_query_backward_workspace_bytes(C.byref(bp)))
+        if nbytes == 0:
+            raise RuntimeError("lidf_query_backward: unsupported configuration")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        bp.workspace, bp.workspace_bytes = ws.data_ptr(), nbytes
+        with torch.cuda.device(dev):
+            cur = torch.cuda.current_stream(dev)
+            rc = self.lib.lidf_query_backward(C.byref(bp), C.c_void_p(cur.cuda_stream))
+        self._raise(rc, "lidf_query_backward")
+        ws.record_stream(cur)
+        return res
+
+    def last_bwd_ms(self) -> float:
+        """Device time of the backward's tcgen05 section in the latest ``backward`` (CUDA events on the launching stream)."""
+        return float(self.lib.lidf_query_last_bwd_ms())
+
+    def wgrad_selftest(self, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
+        """C = A.T @ B through k_wgrad_tc (A [rows,M], M in {128,256}; B [rows,N], N % 16 == 0, N <= 256)."""
+        dev = A.device
+        rows, M = (int(v) for v in A.shape); N = int(B.shape[1])
+        out = torch.empty(M, N, dtype=torch.float32, device=dev)
+        scratch = torch.empty(int(self.lib.lidf_wgrad_selftest_scratch_bytes(M, N)), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            rc = self.lib.lidf_wgrad_selftest(_chk(A, "A", torch.float32), _chk(B, "B", torch.float32), out.data_ptr(), rows, M, N,
+                                              scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_wgrad_selftest")
+        torch.cuda.synchronize(dev)
         return out
 
     # ------------------------------------------------------------------ RefineNet decoder tail

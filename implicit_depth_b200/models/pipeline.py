@@ -14,9 +14,10 @@ contract, so it can be mixed into the reference class::
 ``embeddirs_fn``, ``offset_dec``, ``prob_dec``, ``resnet_model``, ``pnet_model``) for use without the reference tree
 (tests, bench); the two producers are injected, they are not part of this path.
 
-Inference (``torch.no_grad`` / eval) runs the fused sm_100a kernel through the C ABI -- there is no CPU or eager
-fallback for it.  When autograd is recording (training), ``get_pred`` evaluates the same maths with differentiable
-torch ops on the decoder modules, because the native backward does not exist yet ("out of scope").
+Both inference and training run the fused sm_100a kernels through the C ABI -- there is no CPU or eager fallback.
+When autograd is recording, ``get_pred`` is ONE autograd node (``_LidfQueryFn``): forward = ``lidf_query_forward``,
+backward = ``lidf_query_backward`` (tcgen05 dgrad / wgrad kernels, csrc/lidf_bwd.cuh); the decoder parameters receive
+ordinary ``.grad`` tensors, so the reference's DistributedDataParallel wrapper (train_lidf.py:120) works unchanged.
 """
 from __future__ import annotations
 
@@ -167,21 +168,24 @@ class LIDFQueryMixin:
         if self.opt.model.scatter_type != 'Maxpool':
             raise NotImplementedError('Does not support Scatter Type: {}'.format(self.opt.model.scatter_type))
         use_label = exp_type == 'train' and epoch < self.opt.model.maxpool_label_epo       # pipeline.py:444
+        dist = data_dict['dist'] if 'dist' in data_dict else data_dict['intersect_dist']
+        args = (data_dict['full_rgb_feat'].float().contiguous(), data_dict['occ_voxel_feat'].float().contiguous(),
+                data_dict['miss_ray_dir'].contiguous(), data_dict['miss_img_ind'].long().contiguous(),
+                data_dict['miss_bid'].long().contiguous(), data_dict['voxel_bound'].contiguous(),
+                data_dict['occ_vox_intersect_idx'].contiguous(), data_dict['miss_ray_intersect_idx'].contiguous(),
+                dist.contiguous())
+        kw = dict(pcl_label_float=data_dict['pcl_label_float'].contiguous() if use_label else None,
+                  mlp_impl=self.mlp_impl, **self._query_kwargs(data_dict))
         needs_grad = torch.is_grad_enabled() and (
-            data_dict['full_rgb_feat'].requires_grad or data_dict['occ_voxel_feat'].requires_grad
+            args[0].requires_grad or args[1].requires_grad
             or any(p.requires_grad for p in self.offset_dec.parameters())
             or any(p.requires_grad for p in self.prob_dec.parameters()))
         if needs_grad:
-            return self._get_pred_autograd(data_dict, use_label)
-        dist = data_dict['dist'] if 'dist' in data_dict else data_dict['intersect_dist']
-        out = lidf_query.forward(
-            data_dict['full_rgb_feat'].float().contiguous(), data_dict['occ_voxel_feat'].float().contiguous(),
-            data_dict['miss_ray_dir'].contiguous(), data_dict['miss_img_ind'].long().contiguous(),
-            data_dict['miss_bid'].long().contiguous(), data_dict['voxel_bound'].contiguous(),
-            data_dict['occ_vox_intersect_idx'].contiguous(), data_dict['miss_ray_intersect_idx'].contiguous(),
-            dist.contiguous(), self.offset_dec, self.prob_dec,
-            pcl_label_float=data_dict['pcl_label_float'].contiguous() if use_label else None,
-            mlp_impl=self.mlp_impl, want_roi_feat=True, **self._query_kwargs(data_dict))
+            # training: the same fused forward, recorded as ONE autograd node whose backward is lidf_query_backward
+            # (tcgen05 dgrad / wgrad kernels); DDP sees ordinary .grad tensors on the decoder parameters
+            out = lidf_query_autograd(args, self.offset_dec, self.prob_dec, kw)
+        else:
+            out = lidf_query.forward(*args, self.offset_dec, self.prob_dec, want_roi_feat=True, **kw)
         assert out['pred_pos'].shape[0] == data_dict['total_miss_sample_num']
         data_dict.update({
             'pair_pred_pos': out['pair_pred_pos'],
@@ -193,60 +197,55 @@ class LIDFQueryMixin:
             'roi_feat_per_ray': out['roi_feat_per_ray'],
         })
 
-    # -- training: same maths with differentiable torch ops (no native backward yet) -----------------------------
-    def _get_pred_autograd(self, data_dict, use_label):
-        import torchvision.ops as tv_ops
-        m = self.opt.model
-        vox, ray = data_dict['occ_vox_intersect_idx'], data_dict['miss_ray_intersect_idx']
-        dist = data_dict['dist'][vox, ray] if 'dist' in data_dict else data_dict['intersect_dist']
-        dirs = data_dict['miss_ray_dir'][ray]
-        enter_pos, leave_pos = dirs * dist[:, 0:1], dirs * dist[:, 1:2]
-        if m.intersect_pos_type == 'rel':
-            vb = data_dict['voxel_bound'][vox]
-            c = (vb[:, :3] + vb[:, 3:]) / 2.
-            inp_enter, inp_leave = enter_pos - c, leave_pos - c
-        else:
-            inp_enter, inp_leave = enter_pos, leave_pos
-        feat = data_dict['full_rgb_feat']
-        h, w = feat.shape[2], feat.shape[3]
-        pix, half = data_dict['miss_img_ind'], m.roi_inp_bbox // 2
-        ul = torch.stack(((pix[:, 0] - half).clamp(0, w - 1), (pix[:, 1] - half).clamp(0, h - 1)), -1)
-        br = torch.stack(((pix[:, 0] + half).clamp(0, w - 1), (pix[:, 1] + half).clamp(0, h - 1)), -1)
-        boxes = torch.cat((data_dict['miss_bid'].unsqueeze(-1), ul, br), -1).float()
-        roi = tv_ops.roi_align(feat, boxes, output_size=m.roi_out_bbox, spatial_scale=1.0, aligned=True)
-        roi = roi.reshape(roi.shape[0], -1)                 # once per ray, gathered per pair below
-        inp_embed = torch.cat((data_dict['occ_voxel_feat'][vox], roi[ray], self.embed_fn(inp_enter),
-                               self.embed_fn(inp_leave), self.embeddirs_fn(dirs)), -1)
-        pred_offset = self.offset_dec(inp_embed)
-        pred_prob_end = self.prob_dec(inp_embed)
-        r0, r1 = self.opt.grid.offset_range
-        scaled = (pred_offset * (r1 - r0) + r0) * np.sqrt(3) * data_dict['part_size']
-        pair_pred_pos = enter_pos + scaled * dirs
-        R = data_dict['total_miss_sample_num']
-        with torch.no_grad():                               # pipeline.py:442 detaches before the softmax
-            soft, max_pair_id, _ = lidf_query.ray_terminate(
-                pred_prob_end.detach().contiguous(), ray.contiguous(), pair_pred_pos.detach().contiguous(), R,
-                data_dict['pcl_label_float'].contiguous() if use_label else None) if pred_prob_end.is_cuda \
-                else _ray_terminate_torch(pred_prob_end.detach()[:, 0], ray, R,
-                                          data_dict['pcl_label_float'] if use_label else None)
-        dummy = torch.zeros([1, 3], dtype=pair_pred_pos.dtype, device=pair_pred_pos.device)
-        pred_pos = torch.cat((pair_pred_pos, dummy), 0)[max_pair_id]
-        data_dict.update({'pair_pred_pos': pair_pred_pos, 'max_pair_id': max_pair_id, 'pred_prob_end': pred_prob_end,
-                          'pred_prob_end_softmax': soft, 'pred_pos': pred_pos, 'pred_offset': pred_offset,
-                          'roi_feat_per_ray': roi.detach()})
+
+class _LidfQueryFn(torch.autograd.Function):
+    """``lidf_query.forward`` as one autograd node (reference: the op chain of pipeline.py:338-466 recorded op by op).
+    Differentiable outputs: pred_offset, pred_prob_end, pair_pred_pos, pred_pos.  pred_prob_end_softmax and max_pair_id
+    come from a detached soft-max in the reference (:442) and carry no gradient; neither does the cached ROI feature."""
+
+    @staticmethod
+    def forward(ctx, meta, full_rgb_feat, occ_voxel_feat, *params):
+        n_off = len(meta['off_keys'])
+        off = dict(zip(meta['off_keys'], params[:n_off]))
+        prob = dict(zip(meta['prob_keys'], params[n_off:]))
+        out = lidf_query.forward(full_rgb_feat, occ_voxel_feat, *meta['index_args'], off, prob, want_roi_feat=True,
+                                 save_for_backward=True, **meta['kw'])
+        ctx.meta = meta
+        ctx.fwd_out = {k: out[k] for k in ('pred_offset', 'pred_prob_end', 'max_pair_id', 'ief_iter')}
+        ctx.save_for_backward(full_rgb_feat, occ_voxel_feat, *params)
+        ctx.mark_non_differentiable(out['pred_prob_end_softmax'], out['max_pair_id'], out['roi_feat_per_ray'])
+        return (out['pred_offset'], out['pred_prob_end'], out['pair_pred_pos'], out['pred_prob_end_softmax'],
+                out['max_pair_id'], out['pred_pos'], out['roi_feat_per_ray'])
+
+    @staticmethod
+    def backward(ctx, g_off, g_prob, g_pair, _g_soft, _g_arg, g_pos, _g_roi):
+        meta = ctx.meta
+        full_rgb_feat, occ_voxel_feat, *params = ctx.saved_tensors
+        n_off = len(meta['off_keys'])
+        off = dict(zip(meta['off_keys'], params[:n_off]))
+        prob = dict(zip(meta['prob_keys'], params[n_off:]))
+        kw = {k: v for k, v in meta['kw'].items() if k != 'pcl_label_float'}
+        res = lidf_query.backward(full_rgb_feat, occ_voxel_feat, *meta['index_args'], off, prob, ctx.fwd_out,
+                                  g_pred_pos=g_pos, g_pred_prob_end=g_prob, g_pred_offset=g_off, g_pair_pred_pos=g_pair,
+                                  need_feat_grad=ctx.needs_input_grad[1], need_vox_grad=ctx.needs_input_grad[2], **kw)
+        grads = [res['offset_dec'][k] for k in meta['off_keys']] + [res['prob_dec'][k] for k in meta['prob_keys']]
+        grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
+        return (None, res['full_rgb_feat'], res['occ_voxel_feat'], *grads)
 
 
-def _ray_terminate_torch(logit, ray, R, label=None):
-    """CPU-side segment softmax / arg-max (first max wins, empty ray -> P) used only by the autograd path on CPU."""
-    P = logit.shape[0]
-    mx = torch.full((R,), -float('inf'), dtype=logit.dtype).scatter_reduce(0, ray, logit, 'amax')
-    e = (logit - mx[ray]).exp()
-    soft = e / (torch.zeros(R, dtype=logit.dtype).index_add_(0, ray, e) + 1e-12)[ray]
-    key = label if label is not None else soft
-    kmx = torch.full((R,), -float('inf'), dtype=key.dtype).scatter_reduce(0, ray, key, 'amax')
-    pos = torch.arange(P)
-    arg = torch.full((R,), P, dtype=torch.long).scatter_reduce(0, ray, torch.where(key == kmx[ray], pos, P), 'amin')
-    return soft, arg, None
+def lidf_query_autograd(args, offset_dec, prob_dec, kw):
+    """Training entry: ``args`` = the nine tensor inputs of ``lidf_query.forward`` (features first), decoders as modules.
+    There is no CPU / eager fallback: the tensors must live on a CUDA device."""
+    full_rgb_feat, occ_voxel_feat = args[0], args[1]
+    if not full_rgb_feat.is_cuda:
+        raise RuntimeError('lidf_query: the training path runs on the sm_100a kernels only (no CPU fallback)')
+    off_sd = dict(offset_dec.named_parameters())
+    prob_sd = dict(prob_dec.named_parameters())
+    meta = dict(off_keys=list(off_sd), prob_keys=list(prob_sd), index_args=tuple(a.detach() for a in args[2:]), kw=kw)
+    names = ('pred_offset', 'pred_prob_end', 'pair_pred_pos', 'pred_prob_end_softmax', 'max_pair_id', 'pred_pos',
+             'roi_feat_per_ray')
+    outs = _LidfQueryFn.apply(meta, full_rgb_feat, occ_voxel_feat, *off_sd.values(), *prob_sd.values())
+    return dict(zip(names, outs))
 
 
 class LIDF(LIDFQueryMixin, nn.Module):

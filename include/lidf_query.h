@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LIDF_QUERY_ABI_VERSION 2
+#define LIDF_QUERY_ABI_VERSION 3
 
 /* fixed by the shipped YAMLs (train_lidf.yaml:36-57): rgb_out 32 x roi_out_bbox 2^2, pnet_out 128, imnet_gf 64 */
 #define LIDF_RGB_CH 32
@@ -109,7 +109,40 @@ typedef struct LidfQueryParams {
   float* pred_pos;              /* [R,3] */
   float* roi_feat_per_ray;      /* [R,128] optional (NULL to skip): ROIAlign feature, reused by RefineNet (pipeline.py:964) */
   void* workspace; size_t workspace_bytes;   /* >= lidf_query_workspace_bytes() */
+  /* ABI 3, both optional (NULL to skip): */
+  float* ief_iter_out;          /* [n_iter-1][P] IEF offset after iteration k < n_iter-1 (implicit_net.py:146), at the
+                                 * original pair index: what lidf_query_backward needs to re-run an iteration */
+  int32_t* index_error;         /* [1] device flag, set non-zero when a pair_ray / pair_vox / miss_bid value is out of
+                                 * range.  Such entries are clamped into range (nothing is read or written out of
+                                 * bounds) and the results for them are meaningless -- the reference trips a device-side
+                                 * assert in the same situation. */
 } LidfQueryParams;
+
+/* Gradients of one decoder's parameters: fp32 device buffers with the shapes of the LidfDecoder tensors; every buffer is
+ * OVERWRITTEN (not accumulated).  w_enc / b_enc are ignored for IMNet. */
+typedef struct LidfDecoderGrad {
+  float* w1; float* b1; float* w2; float* b2; float* w3; float* b3; float* w4; float* b4; float* w_enc; float* b_enc;
+} LidfDecoderGrad;
+
+/* Backward of lidf_query_forward: what torch autograd does for LIDF.get_embedding + LIDF.get_pred in training
+ * (pipeline.py:338-466 under loss_net.backward(), src/trainers/train_lidf.py:394).  `fwd` is the forward call's parameter
+ * block: its inputs are re-read and its outputs pred_offset, pred_prob_end, max_pair_id (and ief_iter_out, handed in as
+ * `ief_iter`) are READ; fwd.workspace / roi_feat_per_ray / index_error are ignored.  Upstream gradients may be NULL
+ * (= zero).  The soft-max that picks max_pair_id is detached in the reference (:442), so pred_prob_end_softmax and
+ * max_pair_id carry no gradient.  Runs on the tcgen05 engine (split-bf16, fp32 accumulate) whatever fwd.mlp_impl says. */
+typedef struct LidfQueryBackwardParams {
+  LidfQueryParams fwd;
+  const float* ief_iter;          /* [n_iter-1][P]; required when offset_dec is an IEF with n_iter > 1 */
+  const float* g_pred_pos;        /* [R,3] */
+  const float* g_pred_prob_end;   /* [P]   */
+  const float* g_pred_offset;     /* [P]   */
+  const float* g_pair_pred_pos;   /* [P,3] */
+  float* g_full_rgb_feat;         /* [B,32,H,W] or NULL */
+  float* g_occ_voxel_feat;        /* [V,128]    or NULL */
+  LidfDecoderGrad g_offset_dec, g_prob_dec;
+  int64_t chunk_rows;             /* pairs whose activations are resident at once (0 = auto, ~2 M); multiple of 128 */
+  void* workspace; size_t workspace_bytes;   /* >= lidf_query_backward_workspace_bytes() */
+} LidfQueryBackwardParams;
 
 /* RefineNet.get_pred_refine decoder tail (pipeline.py:1018-1029): per RAY
  * x = [voxel_feat_end | rgb_feat_end | PE(pos [- centre]) | PE(dir)] -> offset_dec -> pred_pos + (o*(r1-r0)+r0)*dir */
@@ -137,7 +170,8 @@ typedef struct LidfRefineParams {
 } LidfRefineParams;
 
 int lidf_query_abi_version(void);
-/* sizeof() of the parameter structs as compiled (0: LidfDecoder, 1: LidfQueryParams, 2: LidfRefineParams) so an FFI
+/* sizeof() of the parameter structs as compiled (0: LidfDecoder, 1: LidfQueryParams, 2: LidfRefineParams,
+ * 3: LidfQueryBackwardParams) so an FFI
  * binding can verify its own struct layout */
 size_t lidf_query_struct_size(int which);
 const char* lidf_query_error_string(int code);
@@ -146,6 +180,18 @@ const char* lidf_query_last_cuda_error(void);
 
 size_t lidf_query_workspace_bytes(const LidfQueryParams* p);
 int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream);
+
+size_t lidf_query_backward_workspace_bytes(const LidfQueryBackwardParams* p);
+int lidf_query_backward(const LidfQueryBackwardParams* p, lidf_stream_t stream);
+/* device time (ms) of the backward's tcgen05 kernels (k_mlp_bwd_tc + k_wgrad_tc launches summed) in the most recent
+ * lidf_query_backward on the calling thread; synchronises; < 0 if none */
+float lidf_query_last_bwd_ms(void);
+
+/* unit test of the wgrad kernel: C[M,N] = A^T B, A [rows,M] (M = 128 or 256), B [rows,N] (N % 16 == 0, <= 256), fp32
+ * device arrays, C [M,N] row-major; scratch >= lidf_wgrad_selftest_scratch_bytes(M, N) */
+size_t lidf_wgrad_selftest_scratch_bytes(int32_t M, int32_t N);
+int lidf_wgrad_selftest(const float* A, const float* B, float* C, int64_t rows, int32_t M, int32_t N, void* scratch,
+                        lidf_stream_t stream);
 
 size_t lidf_refine_workspace_bytes(const LidfRefineParams* p);
 int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stream);

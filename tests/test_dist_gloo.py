@@ -1,5 +1,8 @@
 """World-size-2 gloo test (CPU): the path shards by image with no data-path collective;
-the only exchange is DDP's gradient all-reduce over the decoder parameters, exercised here on the torch autograd path."""
+the only exchange is DDP's gradient all-reduce over the decoder parameters.  The product's training path runs on the
+sm_100a kernels only, so on this CPU box the op inside the DDP-wrapped module is stood in for by the oracle (test
+infrastructure): what is exercised is the host logic -- image sharding, the module surface DDP wraps, gradients landing on
+the decoder parameters and being averaged across ranks."""
 import os
 
 import torch
@@ -30,7 +33,15 @@ def _worker(rank, world, port, q):
     first, n = shard_images(B, rank, world)
     d = make_inputs(n, 8, 8, 3, V_img=16, seed=100 + first)          # this rank's images only: no exchange
     d["full_rgb_feat"].requires_grad_(True)
-    lidf = LIDF(default_opt(), torch.device("cpu"), resnet_model=_Fixed(d["full_rgb_feat"]), pnet_model=_Fixed(d["occ_voxel_feat"]))
+    from oracle import lidf_oracle as O
+
+    class _OracleLIDF(LIDF):                                         # CPU stand-in for the fused kernels (oracle = checker)
+        def get_pred(self, data_dict, exp_type, epoch):
+            cfg = dict(O.DEFAULT_CFG)
+            off = dict(self.offset_dec.named_parameters()); prob = dict(self.prob_dec.named_parameters())
+            data_dict.update(O.lidf_query(data_dict, cfg, off, prob, data_dict["part_size"], dedup_rays=True))
+
+    lidf = _OracleLIDF(default_opt(), torch.device("cpu"), resnet_model=_Fixed(d["full_rgb_feat"]), pnet_model=_Fixed(d["occ_voxel_feat"]))
     ddp = torch.nn.parallel.DistributedDataParallel(lidf, find_unused_parameters=True)
     dd = dict(d); dd["total_miss_sample_num"] = d["miss_ray_dir"].shape[0]
     dd.update(rgb_img=torch.zeros(n, 3, 8, 8), valid_rgb=torch.zeros(4, 3), valid_v_pid=torch.zeros(4, dtype=torch.long),
