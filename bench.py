@@ -182,8 +182,12 @@ def main():
     ap.add_argument("--stage2", action="store_true",
                     help="also time BASELINE config 5's second stage on this rank's rays: end-voxel lookup + voxel-feature "
                          "gather + the RefineNet decoder tail, forward_times = 2 (reported as 'stage2', not part of 'value')")
-    ap.add_argument("--torch-gpu-baseline", action="store_true",
-                    help="also time the stock torch op chain (oracle port) on the GPU over a bounded sample")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true",
+                    help="skip timing the stock torch op chain on the same GPU (north_star's '>= 10x the reference PyTorch "
+                         "decoder' target; N = 1 only, bounded sample of >= 2^20 points)")
+    ap.add_argument("--train", action="store_true",
+                    help="BASELINE config 4's training step on this rank's images: fused forward + lidf_query_backward + "
+                         "NCCL all-reduce of the decoder gradients (DDP's exchange), synthetic upstream gradients")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference_arm(args)
@@ -213,6 +217,8 @@ def main():
     P = int(d["occ_vox_intersect_idx"].shape[0]); R = int(d["miss_ray_dir"].shape[0])
     kw = dict(part_size=d["part_size"], mlp_impl=args.engine)
     ins = [d[k] for k in lidf_query.INPUT_KEYS]
+    if args.train:
+        return run_train(args, d, ins, off, prob, kw, dev, rank, world, local)
 
     def barrier():
         if world > 1:
@@ -323,10 +329,119 @@ def main():
                             engine=args.engine, l2="inputs (>3 GB/step) exceed the 126 MB L2; no explicit flush",
                             pair_order="reference voxel-major (regroup inside the timed region)"),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
-    if args.torch_gpu_baseline:
-        line["torch_gpu_baseline"] = torch_gpu_baseline(d, off, prob, args, dev)
+    if not args.no_torch_gpu_baseline and world == 1:
+        tg = torch_gpu_baseline(d, off, prob, args, dev)
+        line["torch_gpu_baseline"] = tg
+        line["vs_torch_gpu"] = dict(value=value / tg["value"], e2e=(e2e["value"] / tg["value"]) if e2e else None,
+                                    note="this arm (device-resident / e2e) over the stock torch op chain on the same B200; "
+                                         "north_star target >= 10")
     if args.stage2:
         line["stage2"] = stage2(d, step, dev, impl=args.engine)
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_train(args, d, ins, off, prob, kw, dev, rank, world, local):
+    """BASELINE config 4: one training step of the hot path per rank = fused forward (activations are not kept) +
+    lidf_query_backward (recompute + tcgen05 dgrad / wgrad) + all-reduce of the decoder gradients over NCCL (the one
+    exchange DDP performs, reference src/trainers/train_lidf.py:120,394).  Upstream gradients dL/d pred_pos and
+    dL/d pred_prob_end are synthetic and resident (the reference's compute_loss is outside the path)."""
+    import torch.distributed as dist
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    P = int(d["occ_vox_intersect_idx"].shape[0]); R = int(d["miss_ray_dir"].shape[0])
+    B, H, W, N = WORKLOADS[args.workload]
+    g = torch.Generator(device=dev).manual_seed(77 + rank)
+    g_pos = torch.randn(R, 3, generator=g, device=dev) / R
+    g_prob = torch.randn(P, 1, generator=g, device=dev) / P
+    names = [k for k, _ in off.named_parameters()], [k for k, _ in prob.named_parameters()]
+    n_dec_params = sum(p.numel() for p in off.parameters()) + sum(p.numel() for p in prob.parameters())
+    full_model = torch.zeros(21641314, device=dev) if world > 1 else None      # the reference's whole DDP payload (SURVEY section 5)
+    ev = lambda: torch.cuda.Event(enable_timing=True)
+    t_ar, t_fwd, t_bwd, t_bwd_tc, t_mlp = [], [], [], [], []
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(record=False):
+        e = [ev() for _ in range(4)]
+        e[0].record()
+        out = lidf_query.forward(*ins, off, prob, save_for_backward=True, **kw)
+        e[1].record()
+        res = lidf_query.backward(*ins, off, prob, out, g_pred_pos=g_pos, g_pred_prob_end=g_prob, **kw)
+        e[2].record()
+        flat = torch.cat([res["offset_dec"][k].reshape(-1) for k in names[0]] + [res["prob_dec"][k].reshape(-1) for k in names[1]])
+        if world > 1:
+            dist.all_reduce(flat)
+            flat /= world
+        e[3].record()
+        if record:
+            t_mlp.append(lidf_query.last_mlp_ms()); t_bwd_tc.append(lidf_query.last_bwd_ms())
+            torch.cuda.synchronize()
+            t_fwd.append(e[0].elapsed_time(e[1])); t_bwd.append(e[1].elapsed_time(e[2])); t_ar.append(e[2].elapsed_time(e[3]))
+        return flat
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        sampler.start()
+    lidf_query.launch_count(reset=True)
+    e0, e1 = ev(), ev()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    launches = lidf_query.launch_count()
+    total_ms = e0.elapsed_time(e1)
+    for _ in range(min(3, args.steps)):
+        step(record=True)
+    ar_full = None
+    if world > 1:
+        for _ in range(2):
+            dist.all_reduce(full_model)
+        a, b = ev(), ev()
+        barrier(); a.record()
+        for _ in range(5):
+            dist.all_reduce(full_model)
+        b.record(); torch.cuda.synchronize()
+        ar_full = a.elapsed_time(b) / 5
+    clocks = sampler.stop() if rank == 0 else None
+    t = torch.tensor([total_ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = float(t) / args.steps
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peaks = load_peaks()
+    med = statistics.median
+    flop_pt = 3 * FLOP_PER_POINT[args.offdec]                 # forward + backward (dgrad + wgrad) as written by the reference
+    k_ms = med(t_mlp) + med(t_bwd_tc)
+    achieved = P * flop_pt / (k_ms * 1e-3) / 1e12
+    peak = peaks["bf16_tflops_sustained"]
+    line = dict(metric="lidf_train_step_points_per_sec", value=P * world / (ms_per_step * 1e-3), unit="points/s", n_gpus=world,
+                steps=args.steps, warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
+                vs_baseline=None, dtype="bf16x3 (split bf16 operands, fp32 accumulate)", data="synthetic",
+                config=dict(workload=f"{args.workload} train: {B} images/GPU of {H}x{W} rays x {N} pairs/ray = {P} points/GPU, "
+                                     f"decoders {args.offdec}(n_iter 2)+IMNET; step = fused forward + native backward + "
+                                     f"all-reduce of the {n_dec_params} decoder gradients",
+                            l2="inputs exceed the 126 MB L2; no explicit flush"),
+                clocks=clocks, gpu_launches=launches,
+                train=dict(forward_ms=med(t_fwd), backward_ms=med(t_bwd), allreduce_decoder_grads_ms=med(t_ar),
+                           allreduce_bytes=4 * n_dec_params, allreduce_full_model_86MB_ms=ar_full,
+                           forward_mlp_kernel_ms=med(t_mlp), backward_tc_section_ms=med(t_bwd_tc)),
+                roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
+                              kernel="k_mlp_tc + k_mlp_bwd_tc + k_wgrad_tc", kernel_ms=k_ms, kernel_share_of_step=k_ms / ms_per_step,
+                              flop_per_point_nominal=flop_pt, peak_source=peaks["source"] + ", bf16_tflops_sustained",
+                              note="nominal forward + backward FLOPs of the reference's Linear stack (3 x forward) over the "
+                                   "decoder kernel of the forward plus the backward's tcgen05 section"),
+                e2e=None, cpu_baseline=None)
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -394,7 +509,7 @@ def stage2(d, step, dev, forward_times=2, impl="auto", valid_per_image=10000):
                 rays_per_s=R * forward_times / (ms * 1e-3))
 
 
-def torch_gpu_baseline(d, off, prob, args, dev, rays=1 << 14):
+def torch_gpu_baseline(d, off, prob, args, dev, rays=1 << 15):
     """Extra, not part of the contract: the reference's stock op chain (oracle port, torch CUDA ops, fp32, TF32 off)
     on the same GPU over the first ``rays`` rays -- the 'reference PyTorch decoder' BASELINE.json's 10x target names."""
     from oracle import lidf_oracle as O
