@@ -29,6 +29,28 @@
 #define BW_PE_LD 112                   // row pitch of the stored layer-1 MMA operand (K order of tc_a1_col)
 #define BW_COLPART 8                   // floats per (cta, warp, lane) slot of the column-sum partials
 
+// mbarrier waits of the backward kernels: the tile-serial kernels hand over between the row warps and the MMA issuer a dozen
+// times per tile, so the wake-up latency matters more than the power a parked warp saves -> short suspend hint.
+#ifndef BW_WAIT_HINT_NS
+#define BW_WAIT_HINT_NS 20
+#endif
+__device__ __forceinline__ void bw_wait_a(uint32_t bar_saddr, uint32_t parity) {
+  uint32_t spins = 0;
+  for (;;) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.b32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar_saddr), "r"(parity), "r"((uint32_t)BW_WAIT_HINT_NS)
+        : "memory");
+    if (ok) break;
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void bw_wait(uint64_t* bar, uint32_t parity) { bw_wait_a(tc::smem_u32(bar), parity); }
+
 // ------------------------------------------------------------------------------------------------ seed
 // dL/d o_last per pair and decoder, at the ORIGINAL pair index.
 //   pair_pred_pos = enter + ((off (r1-r0) + r0) sqrt3 part) dir      (pipeline.py:437-439)
@@ -187,7 +209,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       for (int t = 0; t < n_my_tiles; ++t) {
         for (int c = 0; c < NCH; ++c, ++fill) {
           const uint32_t slot = fill % BW_SLOTS;
-          if (fill >= BW_SLOTS) tc::mbar_wait(&S.w_empty[slot], ((fill / BW_SLOTS) & 1u) ^ 1u);
+          if (fill >= BW_SLOTS) bw_wait(&S.w_empty[slot], ((fill / BW_SLOTS) & 1u) ^ 1u);
           tc::mbar_arrive_expect_tx(&S.w_full[slot], TC_CHUNK_BYTES);
           const uint8_t* src = c < BW_CHUNKS_FWD ? a.wfwd + (size_t)c * TC_CHUNK_BYTES
                                                  : a.wbwd + (size_t)(c - BW_CHUNKS_FWD) * TC_CHUNK_BYTES;
@@ -206,14 +228,14 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       uint32_t fill = 0;
       auto acquire = [&]() {
         const uint32_t slot = fill % BW_SLOTS;
-        tc::mbar_wait_a(full0 + 8 * slot, (fill / BW_SLOTS) & 1u);
+        bw_wait_a(full0 + 8 * slot, (fill / BW_SLOTS) & 1u);
         ++fill;
         return slot;
       };
       for (int t = 0; t < n_my_tiles; ++t) {
         const uint32_t ph = (uint32_t)t & 1u;
-        tc::mbar_wait(&S.a1_ready, ph);
-        if (t > 0) tc::mbar_wait(&S.x2_done, ph ^ 1u);           // Ed1 of the previous tile has read X0 / X1
+        bw_wait(&S.a1_ready, ph);
+        if (t > 0) bw_wait(&S.x2_done, ph ^ 1u);           // Ed1 of the previous tile has read X0 / X1
         tc::fence_after_sync();
         for (int hf = 0; hf < 2; ++hf) {                          // layer 1 (SS): PE operand x W1[:,pos] -> X0 / X1
           const uint32_t dcol = hf ? TC_COL_X1 : TC_COL_X0;
@@ -232,7 +254,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
         }
         tc::commit(&S.a1_free);
         for (int kh = 0; kh < 2; ++kh) {                          // layer 2 (TS): h1 (in X) x W2 -> Y
-          tc::mbar_wait(&S.x_done[kh], ph);
+          bw_wait(&S.x_done[kh], ph);
           tc::fence_after_sync();
           for (int s = 0; s < 8; ++s) {
             const uint32_t slot = acquire();
@@ -241,7 +263,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           }
         }
         tc::commit(&S.y_full);
-        tc::mbar_wait(&S.y_done, ph);                             // layer 3 (TS): h2 (in Y) x W3 -> Z
+        bw_wait(&S.y_done, ph);                             // layer 3 (TS): h2 (in Y) x W3 -> Z
         tc::fence_after_sync();
         for (int c = 0; c < 4; ++c) {
           const uint32_t slot = acquire();
@@ -250,7 +272,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           tc::commit_a(empty0 + 8 * slot);
         }
         tc::commit(&S.z_full);
-        tc::mbar_wait(&S.z_done, ph);                             // dgrad 2 (TS): delta3 (in Z, K = 64) x W3^T -> Y
+        bw_wait(&S.z_done, ph);                             // dgrad 2 (TS): delta3 (in Z, K = 64) x W3^T -> Y
         tc::fence_after_sync();
         for (int s = 0; s < 4; ++s) {
           const uint32_t slot = acquire();
@@ -258,7 +280,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           tc::commit_a(empty0 + 8 * slot);
         }
         tc::commit(&S.y2_full);
-        tc::mbar_wait(&S.y2_done, ph);                            // dgrad 1 (TS): delta2 (in Y) x W2^T -> X0, X1
+        bw_wait(&S.y2_done, ph);                            // dgrad 1 (TS): delta2 (in Y) x W2^T -> X0, X1
         tc::fence_after_sync();
         for (int hf = 0; hf < 2; ++hf) {
           for (int s = 0; s < 8; ++s) {
@@ -395,7 +417,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           }
         }
         const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
-        tc::mbar_wait(&S.x_full[hf], ph);
+        bw_wait(&S.x_full[hf], ph);
         tc::fence_after_sync();
         uint32_t r[32];
         tc::tmem_ld32(lane_addr + xcol, r);
@@ -433,12 +455,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       // ---- operand of the next tile (its last reader, L1 of this tile, has retired once a1_free completes)
       if (has_next) {
-        tc::mbar_wait(&S.a1_free, ph);
+        bw_wait(&S.a1_free, ph);
         build_a1(nxt, tile_local + (int)gridDim.x);
       }
       // ---- E2: h2 = leaky(acc + b2)
       {
-        tc::mbar_wait(&S.y_full, ph);
+        bw_wait(&S.y_full, ph);
         tc::fence_after_sync();
         uint32_t r[32];
         tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
@@ -468,7 +490,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       // ---- E3: z3 -> delta3 = g w4 leaky'(z3) (this thread: columns [16 g, 16 g + 16)), in place as the D2 operand
       {
-        tc::mbar_wait(&S.z_full, ph);
+        bw_wait(&S.z_full, ph);
         tc::fence_after_sync();
         uint32_t r[16];
         tc::tmem_ld16(lane_addr + TC_COL_Z + 16 * g, r);
@@ -500,7 +522,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       // ---- Ed2: delta2 = (delta3 W3) leaky'(z2)
       {
-        tc::mbar_wait(&S.y2_full, ph);
+        bw_wait(&S.y2_full, ph);
         tc::fence_after_sync();
         uint32_t r[32];
         tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
@@ -529,7 +551,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
         const int n0 = 128 * hf + 32 * g;
-        tc::mbar_wait(&S.x2_full[hf], ph);
+        bw_wait(&S.x2_full[hf], ph);
         tc::fence_after_sync();
         uint32_t r[32];
         tc::tmem_ld32(lane_addr + (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g, r);
@@ -646,7 +668,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
       const uint32_t idesc = tc::make_idesc(N);
       for (int it = 0; it < n_it; ++it) {
         const int buf = it & 1;
-        tc::mbar_wait(&S.full[buf], (uint32_t)(it >> 1) & 1u);
+        bw_wait(&S.full[buf], (uint32_t)(it >> 1) & 1u);
         tc::fence_after_sync();
         const uint32_t sa = data0 + buf * stage_bytes, sb = sa + a_bytes;
 #pragma unroll 1
@@ -673,7 +695,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
     const int a_blocks = a.M / 32, b_blocks = (N + 31) / 32, n_units = (a_blocks + b_blocks) * 8;
     for (int it = 0; it < n_it; ++it) {
       const int buf = it & 1;
-      if (it >= 2) tc::mbar_wait(&S.empty[buf], (uint32_t)((it >> 1) - 1) & 1u);
+      if (it >= 2) bw_wait(&S.empty[buf], (uint32_t)((it >> 1) - 1) & 1u);
       const uint32_t sa = data0 + buf * stage_bytes, sb = sa + a_bytes;
       const int64_t row0 = (g0 + it) * WG_ROWS;
       for (int un = warp; un < n_units; un += WG_LOAD_WARPS) {
@@ -709,7 +731,7 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
     }
     // ---- epilogue: TMEM -> this CTA's partial slice (accumulated across launches)
     if (n_it > 0) {
-      tc::mbar_wait(&S.done, 0);
+      bw_wait(&S.done, 0);
       tc::fence_after_sync();
       const int q = warp & 3, cg = warp >> 2;
       const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);

@@ -261,17 +261,17 @@ def _decoder_struct(sd: Dict[str, torch.Tensor], n_iter: int, use_sigmoid: bool,
 class _HostCall:
     """One in-flight ``forward_host_async`` batch."""
 
-    def __init__(self, lq, host, offset_dec, prob_dec, dev, out_host, kw, h2d, d2h):
+    def __init__(self, lq, host, offset_dec, prob_dec, dev, out_host, kw, h2d, d2h, outputs):
         self.lq, self.host, self.offset_dec, self.prob_dec, self.dev = lq, host, offset_dec, prob_dec, dev
-        self.out_host, self.kw, self.h2d, self.d2h = out_host, kw, h2d, d2h
+        self.out_host, self.kw, self.h2d, self.d2h, self.outputs = out_host, kw, h2d, d2h, outputs
         self.pending = None
         self.finished = False
 
     def run_monolithic(self):
         lq, dev = self.lq, self.dev
-        ins = [self.host[k].to(dev, non_blocking=True) for k in lq.INPUT_KEYS]
+        ins = [lq._widen(k, self.host[k].to(dev, non_blocking=True)) for k in lq.INPUT_KEYS]
         out = lq.forward(*ins, self.offset_dec, self.prob_dec, **self.kw)
-        for k in lq.OUTPUT_KEYS:
+        for k in self.outputs:
             self.out_host[k].copy_(out[k], non_blocking=True)
         done = torch.cuda.Event(); done.record(torch.cuda.current_stream(dev))
         self.pending = (done, None, (ins, out), None)
@@ -332,6 +332,14 @@ class _LidfQuery:
                   "occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist")
     OUTPUT_KEYS = ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos")
 
+    INDEX_KEYS = ("miss_img_ind", "miss_bid", "occ_vox_intersect_idx", "miss_ray_intersect_idx")
+
+    @staticmethod
+    def _widen(key, t):
+        """Host index arrays may be int32 (half the H2D bytes of the reference's int64 ``torch.nonzero`` output); the
+        kernels read int64, so they are widened on the device right after the copy."""
+        return t.long() if (key in _LidfQuery.INDEX_KEYS and t.dtype == torch.int32) else t
+
     def image_splits(self, host: Dict[str, torch.Tensor], B: int):
         """Per-image offsets into the ray / voxel / pair arrays ([B+1] python lists) for the pipelined host path.
         The reference keeps rays and voxels image-major (``miss_bid`` / ``occ_vox_bid`` sorted: pipeline.py:226-262,
@@ -341,13 +349,14 @@ class _LidfQuery:
         if "occ_vox_bid" not in host:
             return None
         edges = torch.arange(B + 1, dtype=torch.int64)
-        rays = torch.searchsorted(host["miss_bid"], edges).tolist()
+        rays = torch.searchsorted(host["miss_bid"], edges.to(host["miss_bid"].dtype)).tolist()
         voxels = torch.searchsorted(host["occ_vox_bid"].to(torch.int64), edges).tolist()
-        pairs = torch.searchsorted(host["occ_vox_intersect_idx"], torch.tensor(voxels, dtype=torch.int64)).tolist()
+        pairs = torch.searchsorted(host["occ_vox_intersect_idx"],
+                                   torch.tensor(voxels, dtype=host["occ_vox_intersect_idx"].dtype)).tolist()
         return dict(rays=rays, voxels=voxels, pairs=pairs)
 
     def forward_host(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, out_host=None,
-                     pipeline: bool = True, min_chunk_pairs: int = 1 << 22, **kw):
+                     pipeline: bool = True, min_chunk_pairs: int = 1 << 22, outputs=None, **kw):
         """Same call with HOST buffers (pinned for async copies): H2D of every input, the fused forward, D2H of every
         output, then a synchronise.  Returns (out_host dict, h2d_bytes, d2h_bytes).
 
@@ -357,14 +366,19 @@ class _LidfQuery:
         INPUT_KEYS to find the per-image slices; without it, or when the arrays are not image-contiguous, the whole
         batch goes through one copy-in / compute / copy-out sequence."""
         return self.forward_host_async(host, offset_dec, prob_dec, device, out_host=out_host, pipeline=pipeline,
-                                       min_chunk_pairs=min_chunk_pairs, **kw).wait()
+                                       min_chunk_pairs=min_chunk_pairs, outputs=outputs, **kw).wait()
 
     def forward_host_async(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, out_host=None,
-                           pipeline: bool = True, min_chunk_pairs: int = 1 << 22, **kw) -> "_HostCall":
+                           pipeline: bool = True, min_chunk_pairs: int = 1 << 22, outputs=None, **kw) -> "_HostCall":
         """``forward_host`` without the final synchronise: enqueues the whole batch and returns a handle whose ``wait()``
         gives (out_host, h2d_bytes, d2h_bytes).  Back-to-back batches (serving) keep the GPU busy across batch boundaries:
         the H2D of batch k+1 runs under the tail of batch k, its D2H drains under the head of batch k+2.  Give every
-        in-flight batch its own ``out_host`` buffers."""
+        in-flight batch its own ``out_host`` buffers.
+
+        ``outputs``: which of OUTPUT_KEYS are copied back (default: all six).  Inference reads ``pred_pos`` (+
+        ``max_pair_id`` for RefineNet, reference pipeline.py:942); the four per-pair tensors are 24 B per query point of
+        D2H that only the training losses look at.  The index arrays in ``host`` may be int32 (see ``_widen``)."""
+        outputs = tuple(outputs) if outputs is not None else self.OUTPUT_KEYS
         dev = torch.device(device)
         B = int(host["full_rgb_feat"].shape[0])
         P = int(host["occ_vox_intersect_idx"].shape[0]); R = int(host["miss_ray_dir"].shape[0])
@@ -380,12 +394,12 @@ class _LidfQuery:
                     groups.append((b0, b)); b0 = b
         if out_host is None:
             f32 = dict(dtype=torch.float32, pin_memory=True)
-            out_host = dict(pred_offset=torch.empty(P, 1, **f32), pred_prob_end=torch.empty(P, 1, **f32),
-                            pair_pred_pos=torch.empty(P, 3, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
-                            max_pair_id=torch.empty(R, dtype=torch.int64, pin_memory=True),
-                            pred_pos=torch.empty(R, 3, **f32))
-        d2h = sum(out_host[k].numel() * out_host[k].element_size() for k in self.OUTPUT_KEYS)
-        call = _HostCall(self, host, offset_dec, prob_dec, dev, out_host, kw, h2d, d2h)
+            shapes = dict(pred_offset=((P, 1), f32), pred_prob_end=((P, 1), f32), pair_pred_pos=((P, 3), f32),
+                          pred_prob_end_softmax=((P,), f32), max_pair_id=((R,), dict(dtype=torch.int64, pin_memory=True)),
+                          pred_pos=((R, 3), f32))
+            out_host = {k: torch.empty(*shapes[k][0], **shapes[k][1]) for k in outputs}
+        d2h = sum(out_host[k].numel() * out_host[k].element_size() for k in outputs)
+        call = _HostCall(self, host, offset_dec, prob_dec, dev, out_host, kw, h2d, d2h, outputs)
         if len(groups) > 1:
             self._enqueue_host_pipeline(call, splits, groups)
         else:
@@ -419,6 +433,8 @@ class _LidfQuery:
                 ev_in = torch.cuda.Event(); ev_in.record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)
+                for k in self.INDEX_KEYS:
+                    ins[k] = self._widen(k, ins[k])
                 # re-base the group's indices to its own slices and check that the slice is self-contained
                 pv, pr, mb = ins["occ_vox_intersect_idx"], ins["miss_ray_intersect_idx"], ins["miss_bid"]
                 pv.sub_(v0); pr.sub_(r0); mb.sub_(b0)
@@ -436,10 +452,9 @@ class _LidfQuery:
                 ev_cmp = torch.cuda.Event(); ev_cmp.record(s_cmp)
             with torch.cuda.stream(s_out):
                 s_out.wait_event(ev_cmp)
-                for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax"):
-                    out_host[k][p0:p1].copy_(out[k], non_blocking=True)
-                out_host["max_pair_id"][r0:r1].copy_(out["max_pair_id"], non_blocking=True)
-                out_host["pred_pos"][r0:r1].copy_(out["pred_pos"], non_blocking=True)
+                for k in call.outputs:
+                    sl = slice(r0, r1) if k in ("max_pair_id", "pred_pos") else slice(p0, p1)
+                    out_host[k][sl].copy_(out[k], non_blocking=True)
             live.append((ins, out))
         with torch.cuda.stream(s_out):
             bad_host = torch.empty(1, dtype=torch.int64, pin_memory=True)

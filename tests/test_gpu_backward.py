@@ -234,11 +234,11 @@ def test_backward_chunking_and_repeat_are_consistent():
     _, c = _native_grads(d, cfg, off, prob, part, coef, chunk_rows=0)
     for mod in ("offset_dec", "prob_dec"):
         for k in a[mod]:
-            assert rel_err(b[mod][k].cpu(), a[mod][k].cpu()) < 2e-5, (mod, k)
+            assert rel_err(b[mod][k].cpu(), a[mod][k].cpu()) < 1e-4, (mod, k)
             if k != "linear_1.weight":                           # its voxel columns go through float atomics (G_v)
                 assert torch.equal(a[mod][k], c[mod][k]), (mod, k)
-    assert rel_err(b["full_rgb_feat"].cpu(), a["full_rgb_feat"].cpu()) < 2e-5
-    assert rel_err(b["occ_voxel_feat"].cpu(), a["occ_voxel_feat"].cpu()) < 2e-5
+    assert rel_err(b["full_rgb_feat"].cpu(), a["full_rgb_feat"].cpu()) < 1e-4
+    assert rel_err(b["occ_voxel_feat"].cpu(), a["occ_voxel_feat"].cpu()) < 1e-4
 
 
 def test_label_branch_gradient_follows_the_label_argmax():

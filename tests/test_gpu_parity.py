@@ -434,6 +434,13 @@ def test_forward_host_pipeline_matches_device_call(ragged):
     got2, _, _ = lq.forward_host(host, off, prob, "cuda", out_host=got, part_size=d["part_size"], min_chunk_pairs=1)
     for k in lq.OUTPUT_KEYS:
         assert torch.equal(got2[k], want[k].cpu()), k
+    # int32 index arrays on the host (half the H2D bytes, widened on the device) and only the outputs inference reads
+    host32 = {k: (v.to(torch.int32).pin_memory() if k in lq.INDEX_KEYS else v) for k, v in host.items()}
+    for chunk in (1, 1 << 30):                                  # pipelined and monolithic branch
+        got3, h2d3, d2h3 = lq.forward_host(host32, off, prob, "cuda", part_size=d["part_size"], min_chunk_pairs=chunk,
+                                           outputs=("pred_pos", "max_pair_id"))
+        assert sorted(got3) == ["max_pair_id", "pred_pos"] and h2d3 < h2d and d2h3 == got3["pred_pos"].numel() * 4 + got3["max_pair_id"].numel() * 8
+        assert torch.equal(got3["pred_pos"], want["pred_pos"].cpu()) and torch.equal(got3["max_pair_id"], want["max_pair_id"].cpu())
 
 
 def test_forward_host_falls_back_when_slices_are_not_self_contained():
