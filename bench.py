@@ -51,6 +51,15 @@ ALGO_BYTES_PER_POINT = 80      # decoder kernel: perm 4 + pair_vox 8 + pair_ray 
 EXEC_MAC_TC = 626688           # bf16 MACs the tcgen05 engine executes per point: 3 passes x (112*256 + 256*128 + 128*64) x 3 products
 
 
+_T0 = time.perf_counter()
+
+
+def progress(msg):
+    """phase markers on stderr (LIDF_BENCH_VERBOSE=1): the JSON line on stdout stays the only stdout output"""
+    if os.environ.get("LIDF_BENCH_VERBOSE"):
+        print(f"[bench {time.perf_counter() - _T0:7.1f}s] {msg}", file=sys.stderr, flush=True)
+
+
 def load_peaks():
     path = os.path.join(REPO, "MEASURED_PEAKS.json")
     if os.path.exists(path):
@@ -229,9 +238,12 @@ def main():
     def step():
         return lidf_query.forward(*ins, off, prob, **kw)
 
+    progress(f"inputs ready: P={P} R={R}")
     for _ in range(max(3, args.warmup)):
         out = step()
     del out
+    torch.cuda.synchronize()
+    progress("warm-up done")
     sampler = ClockSampler(local)
     barrier()
     if rank == 0:
@@ -263,9 +275,11 @@ def main():
     # Steps are issued back to back through forward_host_async (two sets of pinned output buffers): every step copies its
     # inputs host -> device and all six outputs device -> host; the copies of neighbouring steps overlap the decoder kernel.
     # `sync_ms_per_step` is one isolated, fully synchronous forward_host call (pipeline fill + drain exposed).
+    progress(f"device-resident timing done: {ms_per_step:.1f} ms/step")
     e2e = None
     if not args.no_e2e:
         def measure_e2e(host, outputs, n_e2e):
+            progress(f"e2e: outputs={outputs} steps={n_e2e}")
             out_a, h2d, d2h = lidf_query.forward_host(host, off, prob, dev, outputs=outputs, **kw)   # warm-up, allocates pinned outputs
             out_b = {k: torch.empty_like(v).pin_memory() for k, v in out_a.items()}
             bufs = (out_a, out_b)
@@ -329,6 +343,7 @@ def main():
                     kernel_share_of_step=k_ms / ms_per_step, flop_per_point_nominal=flop_pt,
                     executed_tflops=(P * 2 * EXEC_MAC_TC / (k_ms * 1e-3) / 1e12) if args.engine != "simt_fp32" else None,
                     peak_source=peaks["source"] + ", bf16_tflops_sustained")
+    progress("e2e done")
     cpu = None
     if not args.no_cpu_baseline and world == 1:     # the CPU baseline is an N = 1 figure (rank 0, all host cores)
         pts, tcpu, threads, sample, _ = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs)
@@ -342,8 +357,10 @@ def main():
                             engine=args.engine, l2="inputs (>3 GB/step) exceed the 126 MB L2; no explicit flush",
                             pair_order="reference voxel-major (regroup inside the timed region)"),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+    progress("cpu baseline done")
     if not args.no_torch_gpu_baseline and world == 1:
         tg = torch_gpu_baseline(d, off, prob, args, dev)
+        progress("torch gpu baseline done")
         line["torch_gpu_baseline"] = tg
         line["vs_torch_gpu"] = dict(value=value / tg["value"], e2e=(e2e["value"] / tg["value"]) if e2e else None,
                                     note="this arm (device-resident / e2e) over the stock torch op chain on the same B200; "
@@ -543,8 +560,10 @@ def torch_gpu_baseline(d, off, prob, args, dev, rays=1 << 15):
     kind, run = None, None
     if ref_loader.find_ref_src() is not None:
         try:
-            ref, opt = ref_loader.load({"model.offdec_type": args.offdec})
-            lidf = ref.LIDF(opt, dev).to(dev).eval()
+            import contextlib
+            with contextlib.redirect_stdout(sys.stderr):                             # the reference prints from its constructors
+                ref, opt = ref_loader.load({"model.offdec_type": args.offdec})
+                lidf = ref.LIDF(opt, dev).to(dev).eval()
             lidf.offset_dec.load_state_dict(off.state_dict()); lidf.prob_dec.load_state_dict(prob.state_dict())
 
             class _Fixed(torch.nn.Module):

@@ -157,6 +157,11 @@ __global__ void k_sort_segments(const int* __restrict__ ray_start, int64_t R, in
   if (n <= 32) { sort_segment_regs<1>(perm, s, n, lane); return; }
   if (n <= 64) { sort_segment_regs<2>(perm, s, n, lane); return; }
   if (n <= 128) { sort_segment_regs<4>(perm, s, n, lane); return; }
+  // Segments beyond a few thousand pairs do not occur in this workload (a ray meets at most a few hundred voxels); they
+  // appear only when out-of-range indices were clamped onto one ray (reported through the index_error flag).  The
+  // transposition sort is quadratic, so such a segment is left in fill order: results stay valid, only the order of its
+  // floating-point reductions is then not reproducible.
+  if (n > 4096) return;
   for (int pass = 0; pass < n; ++pass) {   // long segment (rare): odd-even transposition, n passes
     const int off = pass & 1;
     for (int i = off + 2 * lane; i + 1 < n; i += 64) {

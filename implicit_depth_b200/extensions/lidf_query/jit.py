@@ -433,8 +433,10 @@ class _LidfQuery:
                 ev_in = torch.cuda.Event(); ev_in.record(s_in)
             with torch.cuda.stream(s_cmp):
                 s_cmp.wait_event(ev_in)
+                raw = {k: ins[k] for k in self.INDEX_KEYS}      # the uploaded (possibly int32) tensors live on s_in's pool:
+                live.append(raw)                                # keep them until wait(), or the next group's upload reuses them
                 for k in self.INDEX_KEYS:
-                    ins[k] = self._widen(k, ins[k])
+                    ins[k] = self._widen(k, raw[k])
                 # re-base the group's indices to its own slices and check that the slice is self-contained
                 pv, pr, mb = ins["occ_vox_intersect_idx"], ins["miss_ray_intersect_idx"], ins["miss_bid"]
                 pv.sub_(v0); pr.sub_(r0); mb.sub_(b0)
