@@ -120,24 +120,19 @@ struct BwArgs {
   float* g;                                         // [P] in: dL/d o_it, out (IEF, it > 0): dL/d o_{it-1}
   float* h1; float* h2; float* d1; float* d2; float* d3; float* pe;   // chunk-local rows; pe NULL = do not write
   int d1_accumulate;
-  float* colpart;                                   // [grid][4 quadrants][4 column blocks][32][BW_COLPART], accumulated
+  float* colpart;                                   // [grid][16][32][BW_COLPART], accumulated
 };
 
-#define BW_ROW_WARPS 8
-#define BW_THREADS ((BW_ROW_WARPS + 2) * 32)
-#define BW_RING 4                      // weight ring: 4 x 8 KB chunks (two CTAs share an SM)
-#define BW_COL_X 0                     // 128 columns: layer-1 output half / h1 operand half / delta1pre half, one half at a time
-#define BW_COL_Z 0                     //  64 columns inside X: layer-3 accumulator -> delta3 operand (X is dead in between)
-#define BW_COL_Y 128                   // 128 columns: layer-2 accumulator -> h2 operand -> delta2pre -> delta2 operand
-#define BW_TMEM_COLS 256
-
+#define BW_SLOTS 8                     // weight ring: 8 x 8 KB chunks
+#define BW_STAGE_PITCH 36              // floats per row of a staging tile (32 + 4: conflict-free 128-bit accesses)
 struct BwSmem {
-  uint8_t w[BW_RING][TC_CHUNK_BYTES];
+  uint8_t w[BW_SLOTS][TC_CHUNK_BYTES];
   uint8_t a1[2][TC_A1S_PART_BYTES];
   float u[LIDF_H1]; float b2[LIDF_H2]; float b3[LIDF_H3]; float w4[LIDF_H3];
-  float part[2][2][128];
-  uint64_t w_full[BW_RING], w_empty[BW_RING];
-  uint64_t a1_ready, a1_free, x_full[2], x_done[2], y_full, y_done, z_full, z_done, y2_full, y2_done, x2_full[2], x2_done[2];
+  float part[2][4][128];
+  float stage[TC_ROW_WARPS][32 * BW_STAGE_PITCH];   // per-warp transpose tile: rows <-> lanes, so that global accesses are whole rows
+  uint64_t w_full[BW_SLOTS], w_empty[BW_SLOTS];
+  uint64_t a1_ready, a1_free, x_full[2], x_done[2], y_full, y_done, z_full, z_done, y2_full, y2_done, x2_full[2], x2_done;
   uint32_t tmem_base;
 };
 
@@ -177,47 +172,34 @@ __device__ __forceinline__ void bw_ts64(uint32_t tmem, uint64_t wd64, uint32_t d
   }
 }
 
-// chunk of the weight streams consumed by the i-th ring fill of a tile (MMA order below): fwd chunk index, or 34 + bwd index
-__device__ __forceinline__ int bw_chunk_of_fill(int i) {
-  if (i < 7) return i;                    // L1 half 0      fwd  0..6
-  if (i < 15) return 14 + (i - 7);        // L2 K-half 0    fwd 14..21
-  if (i < 22) return 7 + (i - 15);        // L1 half 1      fwd  7..13
-  if (i < 30) return 22 + (i - 22);       // L2 K-half 1    fwd 22..29
-  if (i < 34) return 30 + (i - 30);       // L3             fwd 30..33
-  return i;                               // D2, D1 half 0, D1 half 1 = bwd 0..19 at 34..53
-}
-
-// One decoder pass over a chunk: forward recompute + dgrad, tile-serial per CTA.  The kernel is bound by latency (a dozen
-// MMA <-> epilogue hand-overs per tile) and by the fp32 rows it writes, so TWO CTAs share an SM (256 TMEM columns, 92 KB of
-// shared memory, 8 row warps each): while one waits, the other computes.
-//   TMEM: X [0,128) one half of layer 1 at a time (its converted output is consumed by layer 2's K-half right away);
-//         Z [0,64) aliases X (layer-3 accumulator / delta3 operand, live only while X is dead); Y [128,256).
-//   MMA order per tile : L1h0 -> X | L2k0: X -> Y | L1h1 -> X | L2k1: X -> Y | L3: Y -> Z | D2: Z W3 -> Y | D1h0: Y W2 -> X |
-//                        D1h1: Y W2 -> X           (the tensor pipe executes in issue order, so a later MMA may overwrite
-//                                                    an operand of an earlier one without a barrier)
-//   row warps per tile : E1(0) E1(1) [next tile's operand] E2 E3 Ed2 Ed1(0) Ed1(1)
-//   warp (q, g): TMEM lane quadrant q, columns [64 g, 64 g + 64) of every 128-column block, in two 32-column sub-blocks.
+// One decoder pass, forward recompute + dgrad, tile-serial (the kernel is bound by the fp32 rows it writes, not by the
+// tensor pipe).  Same roles and TMEM plan as k_mlp_tc: Z [0,64), X0 [128,256), X1 [256,384), Y [384,512).
+// Global traffic goes through a per-warp shared-memory transpose tile: a thread owns a ROW (TMEM lane) but a coalesced
+// access wants 8 lanes per 128-byte row segment -- the first version stored 16 bytes per lane into 32 different lines per
+// instruction and sat at 70 % L1TEX throughput / 26 % of the HBM rate (profiles/r2a); two CTAs per SM did not help.
+//   MMA order per tile : L1 -> X0, X1 | L2 -> Y | L3 -> Z | D2: delta3 (in Z) W3 -> Y | D1: delta2 (in Y) W2 -> X0, X1
+//   row warps per tile : E1 x2 (h1, mask1) | [next tile's operand] | E2 (h2, mask2) | E3 (delta3) | Ed2 (delta2) | Ed1 x2
 template <int NPROD>
-__global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_constant__ BwArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_constant__ BwArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   BwSmem& S = *reinterpret_cast<BwSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < LIDF_H1; i += BW_THREADS) S.u[i] = a.u ? a.u[i] : 0.f;
-  for (int i = tid; i < LIDF_H2; i += BW_THREADS) S.b2[i] = a.b2[i];
-  for (int i = tid; i < LIDF_H3; i += BW_THREADS) { S.b3[i] = a.b3[i]; S.w4[i] = a.w4[i]; }
+  for (int i = tid; i < LIDF_H1; i += TC_THREADS) S.u[i] = a.u ? a.u[i] : 0.f;
+  for (int i = tid; i < LIDF_H2; i += TC_THREADS) S.b2[i] = a.b2[i];
+  for (int i = tid; i < LIDF_H3; i += TC_THREADS) { S.b3[i] = a.b3[i]; S.w4[i] = a.w4[i]; }
   if (tid == 0) {
-    for (int i = 0; i < BW_RING; ++i) { tc::mbar_init(&S.w_full[i], 1); tc::mbar_init(&S.w_empty[i], 1); }
-    tc::mbar_init(&S.a1_ready, BW_ROW_WARPS); tc::mbar_init(&S.a1_free, 1);
+    for (int i = 0; i < BW_SLOTS; ++i) { tc::mbar_init(&S.w_full[i], 1); tc::mbar_init(&S.w_empty[i], 1); }
+    tc::mbar_init(&S.a1_ready, TC_ROW_WARPS); tc::mbar_init(&S.a1_free, 1);
     for (int i = 0; i < 2; ++i) {
-      tc::mbar_init(&S.x_full[i], 1); tc::mbar_init(&S.x_done[i], BW_ROW_WARPS);
-      tc::mbar_init(&S.x2_full[i], 1); tc::mbar_init(&S.x2_done[i], BW_ROW_WARPS);
+      tc::mbar_init(&S.x_full[i], 1); tc::mbar_init(&S.x_done[i], TC_ROW_WARPS); tc::mbar_init(&S.x2_full[i], 1);
     }
-    tc::mbar_init(&S.y_full, 1); tc::mbar_init(&S.y_done, BW_ROW_WARPS);
-    tc::mbar_init(&S.z_full, 1); tc::mbar_init(&S.z_done, BW_ROW_WARPS);
-    tc::mbar_init(&S.y2_full, 1); tc::mbar_init(&S.y2_done, BW_ROW_WARPS);
+    tc::mbar_init(&S.y_full, 1); tc::mbar_init(&S.y_done, TC_ROW_WARPS);
+    tc::mbar_init(&S.z_full, 1); tc::mbar_init(&S.z_done, TC_ROW_WARPS);
+    tc::mbar_init(&S.y2_full, 1); tc::mbar_init(&S.y2_done, TC_ROW_WARPS);
+    tc::mbar_init(&S.x2_done, TC_ROW_WARPS);
     tc::fence_barrier_init();
   }
-  if (warp == BW_ROW_WARPS) tc::tmem_alloc(&S.tmem_base, BW_TMEM_COLS);
+  if (warp == TC_ROW_WARPS) tc::tmem_alloc(&S.tmem_base, 512);
   tc::fence_before_sync();
   __syncthreads();
   tc::fence_after_sync();
@@ -225,23 +207,22 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
   const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
   constexpr int NCH = BW_CHUNKS_FWD + BW_CHUNKS_BWD;
 
-  if (warp == BW_ROW_WARPS + 1) {
+  if (warp == TC_ROW_WARPS + 1) {
     // ================================ weight loader ================================
     if (tc::elect_one()) {
       uint32_t fill = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
-        for (int i = 0; i < NCH; ++i, ++fill) {
-          const uint32_t slot = fill % BW_RING;
-          if (fill >= BW_RING) bw_wait(&S.w_empty[slot], ((fill / BW_RING) & 1u) ^ 1u);
+        for (int c = 0; c < NCH; ++c, ++fill) {
+          const uint32_t slot = fill % BW_SLOTS;
+          if (fill >= BW_SLOTS) bw_wait(&S.w_empty[slot], ((fill / BW_SLOTS) & 1u) ^ 1u);
           tc::mbar_arrive_expect_tx(&S.w_full[slot], TC_CHUNK_BYTES);
-          const int c = bw_chunk_of_fill(i);
           const uint8_t* src = c < BW_CHUNKS_FWD ? a.wfwd + (size_t)c * TC_CHUNK_BYTES
                                                  : a.wbwd + (size_t)(c - BW_CHUNKS_FWD) * TC_CHUNK_BYTES;
           tc::bulk_g2s(S.w[slot], src, TC_CHUNK_BYTES, &S.w_full[slot]);
         }
       }
     }
-  } else if (warp == BW_ROW_WARPS) {
+  } else if (warp == TC_ROW_WARPS) {
     // ================================ MMA issuer ================================
     if (tc::elect_one()) {
       const uint32_t full0 = tc::smem_u32(&S.w_full[0]), empty0 = tc::smem_u32(&S.w_empty[0]);
@@ -251,72 +232,72 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
       constexpr uint32_t id128 = tc::make_idesc(128);
       uint32_t fill = 0;
       auto acquire = [&]() {
-        const uint32_t slot = fill % BW_RING;
-        bw_wait_a(full0 + 8 * slot, (fill / BW_RING) & 1u);
+        const uint32_t slot = fill % BW_SLOTS;
+        bw_wait_a(full0 + 8 * slot, (fill / BW_SLOTS) & 1u);
         ++fill;
         return slot;
-      };
-      auto issue_l1 = [&]() {                                     // PE operand (smem) x W1[:,pos] half -> X
-        for (int s = 0; s < TC_K1_STEPS; ++s) {
-          const uint32_t slot = acquire();
-          const uint64_t bhi = wd128 + ((slot * TC_CHUNK_BYTES) >> 4);
-          const uint64_t ahi = ad + ((uint32_t)(s * 4096) >> 4);
-          tc::mma_ss(tmem + BW_COL_X, ahi, bhi, id128, s == 0 ? 0u : 1u);
-          if (NPROD == 3) {
-            tc::mma_ss(tmem + BW_COL_X, ahi + ((uint32_t)TC_A1S_PART_BYTES >> 4), bhi, id128, 1u);
-            tc::mma_ss(tmem + BW_COL_X, ahi, bhi + (4096u >> 4), id128, 1u);
-          }
-          tc::commit_a(empty0 + 8 * slot);
-        }
-      };
-      auto issue_ts128 = [&](uint32_t dcol, uint32_t acol, int ksteps, bool first) {
-        for (int s = 0; s < ksteps; ++s) {
-          const uint32_t slot = acquire();
-          bw_ts128<NPROD>(tmem, wd128, dcol, acol + 16 * s, slot * TC_CHUNK_BYTES, first && s == 0);
-          tc::commit_a(empty0 + 8 * slot);
-        }
       };
       for (int t = 0; t < n_my_tiles; ++t) {
         const uint32_t ph = (uint32_t)t & 1u;
         bw_wait(&S.a1_ready, ph);
-        if (t > 0) bw_wait(&S.x2_done[1], ph ^ 1u);               // Ed1(1) of the previous tile has read X
+        if (t > 0) bw_wait(&S.x2_done, ph ^ 1u);           // Ed1 of the previous tile has read X0 / X1
         tc::fence_after_sync();
-        issue_l1();                                               // L1 half 0 -> X
-        tc::commit(&S.x_full[0]);
-        bw_wait(&S.x_done[0], ph);
-        tc::fence_after_sync();
-        issue_ts128(BW_COL_Y, BW_COL_X, 8, true);                 // L2 K-half 0: h1[:, 0:128] (in X) x W2 -> Y
-        issue_l1();                                               // L1 half 1 -> X (after L2k0 in the pipe)
-        tc::commit(&S.x_full[1]);
+        for (int hf = 0; hf < 2; ++hf) {                          // layer 1 (SS): PE operand x W1[:,pos] -> X0 / X1
+          const uint32_t dcol = hf ? TC_COL_X1 : TC_COL_X0;
+          for (int s = 0; s < TC_K1_STEPS; ++s) {
+            const uint32_t slot = acquire();
+            const uint64_t bhi = wd128 + ((slot * TC_CHUNK_BYTES) >> 4);
+            const uint64_t ahi = ad + ((uint32_t)(s * 4096) >> 4);
+            tc::mma_ss(tmem + dcol, ahi, bhi, id128, s == 0 ? 0u : 1u);
+            if (NPROD == 3) {
+              tc::mma_ss(tmem + dcol, ahi + ((uint32_t)TC_A1S_PART_BYTES >> 4), bhi, id128, 1u);
+              tc::mma_ss(tmem + dcol, ahi, bhi + (4096u >> 4), id128, 1u);
+            }
+            tc::commit_a(empty0 + 8 * slot);
+          }
+          tc::commit(&S.x_full[hf]);
+        }
         tc::commit(&S.a1_free);
-        bw_wait(&S.x_done[1], ph);
-        tc::fence_after_sync();
-        issue_ts128(BW_COL_Y, BW_COL_X, 8, false);                // L2 K-half 1
+        for (int kh = 0; kh < 2; ++kh) {                          // layer 2 (TS): h1 (in X) x W2 -> Y
+          bw_wait(&S.x_done[kh], ph);
+          tc::fence_after_sync();
+          for (int s = 0; s < 8; ++s) {
+            const uint32_t slot = acquire();
+            bw_ts128<NPROD>(tmem, wd128, TC_COL_Y, (kh ? TC_COL_X1 : TC_COL_X0) + 16 * s, slot * TC_CHUNK_BYTES, kh == 0 && s == 0);
+            tc::commit_a(empty0 + 8 * slot);
+          }
+        }
         tc::commit(&S.y_full);
-        bw_wait(&S.y_done, ph);                                   // L3: h2 (in Y) x W3 -> Z
+        bw_wait(&S.y_done, ph);                             // layer 3 (TS): h2 (in Y) x W3 -> Z
         tc::fence_after_sync();
         for (int c = 0; c < 4; ++c) {
           const uint32_t slot = acquire();
           for (int j = 0; j < 2; ++j)
-            bw_ts64<NPROD>(tmem, wd64, BW_COL_Z, BW_COL_Y + 16 * (2 * c + j), slot * TC_CHUNK_BYTES + j * 4096, c == 0 && j == 0);
+            bw_ts64<NPROD>(tmem, wd64, TC_COL_Z, TC_COL_Y + 16 * (2 * c + j), slot * TC_CHUNK_BYTES + j * 4096, c == 0 && j == 0);
           tc::commit_a(empty0 + 8 * slot);
         }
         tc::commit(&S.z_full);
-        bw_wait(&S.z_done, ph);                                   // D2: delta3 (in Z, K = 64) x W3^T -> Y
+        bw_wait(&S.z_done, ph);                             // dgrad 2 (TS): delta3 (in Z, K = 64) x W3^T -> Y
         tc::fence_after_sync();
-        issue_ts128(BW_COL_Y, BW_COL_Z, 4, true);
+        for (int s = 0; s < 4; ++s) {
+          const uint32_t slot = acquire();
+          bw_ts128<NPROD>(tmem, wd128, TC_COL_Y, TC_COL_Z + 16 * s, slot * TC_CHUNK_BYTES, s == 0);
+          tc::commit_a(empty0 + 8 * slot);
+        }
         tc::commit(&S.y2_full);
-        bw_wait(&S.y2_done, ph);                                  // D1 half 0: delta2 (in Y) x W2^T -> X
+        bw_wait(&S.y2_done, ph);                            // dgrad 1 (TS): delta2 (in Y) x W2^T -> X0, X1
         tc::fence_after_sync();
-        issue_ts128(BW_COL_X, BW_COL_Y, 8, true);
-        tc::commit(&S.x2_full[0]);
-        bw_wait(&S.x2_done[0], ph);                               // Ed1(0) has read X
-        tc::fence_after_sync();
-        issue_ts128(BW_COL_X, BW_COL_Y, 8, true);                 // D1 half 1
-        tc::commit(&S.x2_full[1]);
+        for (int hf = 0; hf < 2; ++hf) {
+          for (int s = 0; s < 8; ++s) {
+            const uint32_t slot = acquire();
+            bw_ts128<NPROD>(tmem, wd128, hf ? TC_COL_X1 : TC_COL_X0, TC_COL_Y + 16 * s, slot * TC_CHUNK_BYTES, s == 0);
+            tc::commit_a(empty0 + 8 * slot);
+          }
+          tc::commit(&S.x2_full[hf]);
+        }
       }
     }
-  } else if (warp < BW_ROW_WARPS) {
+  } else if (warp < TC_ROW_WARPS) {
     // ================================ row warps ================================
     const int q = warp & 3, g = warp >> 2;
     const int row = q * 32 + lane;
@@ -327,6 +308,72 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
       tc::st_shared_v4(a1row_hi + sk * 4096 + 2048, w[4], w[5], w[6], w[7]);
       tc::st_shared_v4(a1row_lo + sk * 4096, w[8], w[9], w[10], w[11]);
       tc::st_shared_v4(a1row_lo + sk * 4096 + 2048, w[12], w[13], w[14], w[15]);
+    };
+
+    // ---- coalesced global <-> register-row transposes through this warp's staging tile
+    float* const stg = S.stage[warp];
+    const int tr = lane >> 3, tc4 = 4 * (lane & 7);              // instruction j touches rows 4 j + tr, floats [tc4, tc4 + 4)
+    // rows (lanes) x 32 floats -> global rows gbase + r * pitch (+ col)
+    auto store32 = [&](const float* x, float* gbase, int pitch) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        *reinterpret_cast<float4*>(stg + lane * BW_STAGE_PITCH + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + tr;
+        *reinterpret_cast<float4*>(gbase + (size_t)r * pitch + tc4) = *reinterpret_cast<const float4*>(stg + r * BW_STAGE_PITCH + tc4);
+      }
+      __syncwarp();
+    };
+    auto store16 = [&](const float* x, float* gbase, int pitch) {   // 16 floats per row: 4 lanes per row, 8 rows per instruction
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+        *reinterpret_cast<float4*>(stg + lane * BW_STAGE_PITCH + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
+      __syncwarp();
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int r = 8 * j + (lane >> 2), c = 4 * (lane & 3);
+        *reinterpret_cast<float4*>(gbase + (size_t)r * pitch + c) = *reinterpret_cast<const float4*>(stg + r * BW_STAGE_PITCH + c);
+      }
+      __syncwarp();
+    };
+    auto load32 = [&](float* x, const float* gbase, int pitch) {    // global rows -> this lane's row
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + tr;
+        *reinterpret_cast<float4*>(stg + r * BW_STAGE_PITCH + tc4) = *reinterpret_cast<const float4*>(gbase + (size_t)r * pitch + tc4);
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(stg + lane * BW_STAGE_PITCH + 4 * i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+      __syncwarp();
+    };
+    // x[lane's row][0..32) = A_v[vox][col ..) + T[ray][col ..) gathered with whole-row accesses (row indices via shuffles)
+    auto gather_sum32 = [&](float* x, int vox_, int ray_, bool valid_, int col) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const int r = 4 * j + tr;
+        const int vr = __shfl_sync(0xffffffffu, vox_, r), rr = __shfl_sync(0xffffffffu, ray_, r);
+        const bool ok = __shfl_sync(0xffffffffu, valid_ ? 1 : 0, r) != 0;
+        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (ok) {
+          const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.T + (size_t)rr * 512 + col + tc4));
+          const float4 a4 = __ldg(reinterpret_cast<const float4*>(a.Av + (size_t)vr * 512 + col + tc4));
+          s4 = make_float4(a4.x + t4.x, a4.y + t4.y, a4.z + t4.z, a4.w + t4.w);
+        }
+        *reinterpret_cast<float4*>(stg + r * BW_STAGE_PITCH + tc4) = s4;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const float4 v = *reinterpret_cast<const float4*>(stg + lane * BW_STAGE_PITCH + 4 * i);
+        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+      }
+      __syncwarp();
     };
     struct RowMeta { int orig, vox, ray; float t0, t1; bool valid; };
     auto load_meta = [&](int tile_local) {
@@ -342,21 +389,20 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
       }
       return m;
     };
-    // layer-1 MMA operand (same values as k_mlp_tc::build_a1) + optional fp32 copy of it for the dW1[:,pos] wgrad.
-    // g = 0: PE(enter) sin/cos (k-steps 0-2) + the raw xyz k-step (6); g = 1: PE(leave) sin/cos (k-steps 3-5).
+    // layer-1 MMA operand (identical to k_mlp_tc::build_a1) + optional fp32 copy of it for the dW1[:,pos] wgrad
     auto build_a1 = [&](const RowMeta& m, int tile_local) {
-      float pe[3] = {0.f, 0.f, 0.f}, pl[3] = {0.f, 0.f, 0.f};
+      float dir[3] = {0.f, 0.f, 0.f}, pe[3] = {0.f, 0.f, 0.f}, pl[3] = {0.f, 0.f, 0.f};
       if (m.valid) {
 #pragma unroll
         for (int k = 0; k < 3; ++k) {
-          const float dk = a.ray_dir[(size_t)m.ray * 3 + k];
+          dir[k] = a.ray_dir[(size_t)m.ray * 3 + k];
           const float c = a.rel ? (a.voxel_bound[(size_t)m.vox * 6 + k] + a.voxel_bound[(size_t)m.vox * 6 + 3 + k]) / 2.0f : 0.f;
-          pe[k] = dk * m.t0 - c;
-          pl[k] = dk * m.t1 - c;
+          pe[k] = dir[k] * m.t0 - c;
+          pl[k] = dir[k] * m.t1 - c;
         }
       }
-      float* perow = a.pe ? a.pe + (size_t)(tile_local * 128 + row) * BW_PE_LD : nullptr;
-      {
+      float* pewarp = a.pe ? a.pe + (size_t)(tile_local * 128 + q * 32) * BW_PE_LD : nullptr;   // row 0 of this warp's 32 rows
+      if (g < 2) {
         float v[48];
 #pragma unroll
         for (int c = 0; c < 3; ++c) {
@@ -384,13 +430,8 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
           tc::split16(v + 16 * j, w);
           st_a1(3 * g + j, w);
         }
-        if (perow) {
-#pragma unroll
-          for (int j = 0; j < 12; ++j)
-            *reinterpret_cast<float4*>(perow + 48 * g + 4 * j) = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-        }
-      }
-      if (g == 0) {
+        if (pewarp) { store32(v, pewarp + 48 * g, BW_PE_LD); store16(v + 32, pewarp + 48 * g + 32, BW_PE_LD); }
+      } else if (g == 2) {
         float x[16];
 #pragma unroll
         for (int k = 0; k < 16; ++k) x[k] = 0.f;
@@ -399,18 +440,14 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
         uint32_t w[16];
         tc::split16(x, w);
         st_a1(6, w);
-        if (perow) {
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            *reinterpret_cast<float4*>(perow + 96 + 4 * j) = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
-        }
+        if (pewarp) store16(x, pewarp + 96, BW_PE_LD);
       }
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.a1_ready);
     };
 
-    float acc_k0[2] = {0.f, 0.f}, acc_b2[2] = {0.f, 0.f}, acc_du[2][2] = {{0.f, 0.f}, {0.f, 0.f}}, acc_b4 = 0.f;
+    float acc_k0 = 0.f, acc_b2 = 0.f, acc_du0 = 0.f, acc_du1 = 0.f, acc_b4 = 0.f;
     uint32_t par = 0;
     RowMeta cur = load_meta((int)blockIdx.x);
     build_a1(cur, (int)blockIdx.x);
@@ -418,7 +455,7 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
       const int tile_local = (int)blockIdx.x + t * (int)gridDim.x;
       const uint32_t ph = (uint32_t)t & 1u;
       const bool has_next = t + 1 < n_my_tiles;
-      const size_t rowpos = (size_t)tile_local * 128 + row;
+      const size_t wrow0 = (size_t)tile_local * 128 + q * 32;    // first of this warp's 32 chunk rows
       const bool valid = cur.valid;
       const float gin = valid ? a.g[cur.orig] : 0.f;
       const float oin = (valid && a.o_in) ? a.o_in[cur.orig] : a.o0;
@@ -426,59 +463,42 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
       const bool rank1 = a.is_ief && a.it > 0;
       RowMeta nxt{0, 0, 0, 0.f, 0.f, false};
       if (has_next) nxt = load_meta(tile_local + (int)gridDim.x);
-      uint32_t m1_00 = 0u, m1_01 = 0u, m1_10 = 0u, m1_11 = 0u, m2_0 = 0u, m2_1 = 0u;     // sign masks [half][sub-block]
+      uint32_t mask1a = 0u, mask1b = 0u, mask2 = 0u;
       // ---- E1 x 2: h1 = leaky(acc + A_v + T (+ u delta)) -> HBM row, sign mask, bf16 hi|lo in place
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
+        const int n0 = 128 * hf + 32 * g;
+        float xo[32];
+        gather_sum32(xo, cur.vox, cur.ray, valid, a.dcol + n0);   // A_v + T, before waiting for the accumulator
+        const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
         bw_wait(&S.x_full[hf], ph);
         tc::fence_after_sync();
-#pragma unroll 1
-        for (int sb = 0; sb < 2; ++sb) {
-          const int c0 = 64 * g + 32 * sb, n0 = 128 * hf + c0;
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + BW_COL_X + c0, r);
-          float xo[32];
-          uint32_t mk = 0u;
-          const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)cur.ray * 512 + a.dcol + n0);
-          const float4* ap = reinterpret_cast<const float4*>(a.Av + (size_t)cur.vox * 512 + a.dcol + n0);
-          float4 tt[8], av[8];
+        uint32_t r[32];
+        tc::tmem_ld32(lane_addr + xcol, r);
+        tc::wait_ld();
+        uint32_t mk = 0u;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            tt[i] = valid ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-            av[i] = valid ? __ldg(ap + i) : make_float4(0.f, 0.f, 0.f, 0.f);
-          }
-          tc::wait_ld();
+        for (int e = 0; e < 32; ++e) {
+          float v = __uint_as_float(r[e]) + xo[e];
+          if (rank1) v = fmaf(S.u[n0 + e], delta, v);
+          const float x = fmaxf(v, LIDF_LEAKY * v);
+          xo[e] = x;
+          mk |= (x > 0.f ? 1u : 0u) << e;
+        }
+        if (hf == 0) mask1a = mk; else mask1b = mk;
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            const float add[4] = {av[i].x + tt[i].x, av[i].y + tt[i].y, av[i].z + tt[i].z, av[i].w + tt[i].w};
-#pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              const int e = 4 * i + k;
-              float v = __uint_as_float(r[e]) + add[k];
-              if (rank1) v = fmaf(S.u[n0 + e], delta, v);
-              const float x = fmaxf(v, LIDF_LEAKY * v);
-              xo[e] = x;
-              mk |= (x > 0.f ? 1u : 0u) << e;
-            }
-          }
-          if (hf == 0) { if (sb == 0) m1_00 = mk; else m1_01 = mk; } else { if (sb == 0) m1_10 = mk; else m1_11 = mk; }
-#pragma unroll
-          for (int s16 = 0; s16 < 2; ++s16) {
-            uint32_t w[16];
-            tc::split16(xo + 16 * s16, w);
-            tc::tmem_st16(lane_addr + BW_COL_X + c0 + 16 * s16, w);
-          }
-          float* hrow = a.h1 + rowpos * LIDF_H1 + n0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(hrow + 4 * i) = make_float4(xo[4 * i], xo[4 * i + 1], xo[4 * i + 2], xo[4 * i + 3]);
+        for (int s16 = 0; s16 < 2; ++s16) {
+          uint32_t w[16];
+          tc::split16(xo + 16 * s16, w);
+          tc::tmem_st16(lane_addr + xcol + 16 * s16, w);
         }
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
+        store32(xo, a.h1 + wrow0 * LIDF_H1 + n0, LIDF_H1);        // after the hand-over: the layer-2 MMAs run meanwhile
       }
-      // ---- operand of the next tile (its last reader, L1 half 1 of this tile, has retired once a1_free completes)
+      // ---- operand of the next tile (its last reader, L1 of this tile, has retired once a1_free completes)
       if (has_next) {
         bw_wait(&S.a1_free, ph);
         build_a1(nxt, tile_local + (int)gridDim.x);
@@ -487,194 +507,152 @@ __global__ void __launch_bounds__(BW_THREADS, 2) k_mlp_bwd_tc(const __grid_const
       {
         bw_wait(&S.y_full, ph);
         tc::fence_after_sync();
-#pragma unroll 1
-        for (int sb = 0; sb < 2; ++sb) {
-          const int c0 = 64 * g + 32 * sb;
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + BW_COL_Y + c0, r);
-          tc::wait_ld();
-          float xo[32];
-          uint32_t mk = 0u;
+        uint32_t r[32];
+        tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
+        tc::wait_ld();
+        float xo[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) {
-            const float v = __uint_as_float(r[e]) + S.b2[c0 + e];
-            const float x = fmaxf(v, LIDF_LEAKY * v);
-            xo[e] = x;
-            mk |= (x > 0.f ? 1u : 0u) << e;
-          }
-          if (sb == 0) m2_0 = mk; else m2_1 = mk;
+        for (int e = 0; e < 32; ++e) {
+          const float v = __uint_as_float(r[e]) + S.b2[32 * g + e];
+          const float x = fmaxf(v, LIDF_LEAKY * v);
+          xo[e] = x;
+          mask2 |= (x > 0.f ? 1u : 0u) << e;
+        }
 #pragma unroll
-          for (int s16 = 0; s16 < 2; ++s16) {
-            uint32_t w[16];
-            tc::split16(xo + 16 * s16, w);
-            tc::tmem_st16(lane_addr + BW_COL_Y + c0 + 16 * s16, w);
-          }
-          float* hrow = a.h2 + rowpos * LIDF_H2 + c0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(hrow + 4 * i) = make_float4(xo[4 * i], xo[4 * i + 1], xo[4 * i + 2], xo[4 * i + 3]);
+        for (int s16 = 0; s16 < 2; ++s16) {
+          uint32_t w[16];
+          tc::split16(xo + 16 * s16, w);
+          tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16 * s16, w);
         }
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.y_done);
+        store32(xo, a.h2 + wrow0 * LIDF_H2 + 32 * g, LIDF_H2);
       }
-      // ---- E3: z3 -> delta3 = g w4 leaky'(z3) (columns [32 g, 32 g + 32) as two 16-column blocks), in place as the D2 operand
+      // ---- E3: z3 -> delta3 = g w4 leaky'(z3) (this thread: columns [16 g, 16 g + 16)), in place as the D2 operand
       {
         bw_wait(&S.z_full, ph);
         tc::fence_after_sync();
-#pragma unroll 1
-        for (int sb = 0; sb < 2; ++sb) {
-          const int c0 = 32 * g + 16 * sb;
-          uint32_t r[16];
-          tc::tmem_ld16(lane_addr + BW_COL_Z + c0, r);
-          tc::wait_ld();
-          float d3[16], red[32];
+        uint32_t r[16];
+        tc::tmem_ld16(lane_addr + TC_COL_Z + 16 * g, r);
+        tc::wait_ld();
+        float d3[16], red[32];
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = c0 + j;
-            const float z = __uint_as_float(r[j]) + S.b3[n];
-            const bool pos = z > 0.f;
-            const float h3 = pos ? z : LIDF_LEAKY * z;
-            d3[j] = gin * S.w4[n] * (pos ? 1.0f : LIDF_LEAKY);
-            red[j] = d3[j];
-            red[16 + j] = gin * h3;
-          }
-          uint32_t w[16];
-          tc::split16(d3, w);
-          tc::tmem_st16(lane_addr + BW_COL_Z + c0, w);
-          float* drow = a.d3 + rowpos * LIDF_H3 + c0;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            *reinterpret_cast<float4*>(drow + 4 * i) = make_float4(d3[4 * i], d3[4 * i + 1], d3[4 * i + 2], d3[4 * i + 3]);
-          const float cs = bw_colreduce32(red, lane);             // lanes 0-15: db3[c0 + l], 16-31: dw4[c0 + l - 16]
-          if (sb == 0) acc_k0[0] += cs; else acc_k0[1] += cs;
+        for (int j = 0; j < 16; ++j) {
+          const int n = 16 * g + j;
+          const float z = __uint_as_float(r[j]) + S.b3[n];
+          const bool pos = z > 0.f;
+          const float h3 = pos ? z : LIDF_LEAKY * z;
+          d3[j] = gin * S.w4[n] * (pos ? 1.0f : LIDF_LEAKY);
+          red[j] = d3[j];
+          red[16 + j] = gin * h3;
         }
+        uint32_t w[16];
+        tc::split16(d3, w);
+        tc::tmem_st16(lane_addr + TC_COL_Z + 16 * g, w);
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.z_done);
+        store16(d3, a.d3 + wrow0 * LIDF_H3 + 16 * g, LIDF_H3);
+        acc_k0 += bw_colreduce32(red, lane);                      // lanes 0-15: db3[16 g + l], 16-31: dw4[16 g + l - 16]
         if (g == 0) acc_b4 += gin;
       }
       // ---- Ed2: delta2 = (delta3 W3) leaky'(z2)
       {
         bw_wait(&S.y2_full, ph);
         tc::fence_after_sync();
-#pragma unroll 1
-        for (int sb = 0; sb < 2; ++sb) {
-          const int c0 = 64 * g + 32 * sb;
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + BW_COL_Y + c0, r);
-          tc::wait_ld();
-          const uint32_t mk = sb == 0 ? m2_0 : m2_1;
-          float d2[32];
+        uint32_t r[32];
+        tc::tmem_ld32(lane_addr + TC_COL_Y + 32 * g, r);
+        tc::wait_ld();
+        float d2[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) d2[e] = __uint_as_float(r[e]) * (((mk >> e) & 1u) ? 1.0f : LIDF_LEAKY);
+        for (int e = 0; e < 32; ++e) d2[e] = __uint_as_float(r[e]) * (((mask2 >> e) & 1u) ? 1.0f : LIDF_LEAKY);
 #pragma unroll
-          for (int s16 = 0; s16 < 2; ++s16) {
-            uint32_t w[16];
-            tc::split16(d2 + 16 * s16, w);
-            tc::tmem_st16(lane_addr + BW_COL_Y + c0 + 16 * s16, w);
-          }
-          float* drow = a.d2 + rowpos * LIDF_H2 + c0;
-#pragma unroll
-          for (int i = 0; i < 8; ++i)
-            *reinterpret_cast<float4*>(drow + 4 * i) = make_float4(d2[4 * i], d2[4 * i + 1], d2[4 * i + 2], d2[4 * i + 3]);
-          const float cs = bw_colreduce32(d2, lane);              // db2[c0 + l]
-          if (sb == 0) acc_b2[0] += cs; else acc_b2[1] += cs;
+        for (int s16 = 0; s16 < 2; ++s16) {
+          uint32_t w[16];
+          tc::split16(d2 + 16 * s16, w);
+          tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16 * s16, w);
         }
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.y2_done);
+        store32(d2, a.d2 + wrow0 * LIDF_H2 + 32 * g, LIDF_H2);
+        acc_b2 += bw_colreduce32(d2, lane);                       // db2[32 g + l]
       }
       // ---- Ed1 x 2: delta1 = (delta2 W2) leaky'(z1) -> HBM (summed over the IEF passes), du, IEF feedback
       float fb = 0.f;
 #pragma unroll 1
       for (int hf = 0; hf < 2; ++hf) {
+        const int n0 = 128 * hf + 32 * g;
         bw_wait(&S.x2_full[hf], ph);
         tc::fence_after_sync();
-#pragma unroll 1
-        for (int sb = 0; sb < 2; ++sb) {
-          const int c0 = 64 * g + 32 * sb, n0 = 128 * hf + c0;
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + BW_COL_X + c0, r);
-          tc::wait_ld();
-          const uint32_t mk = hf == 0 ? (sb == 0 ? m1_00 : m1_01) : (sb == 0 ? m1_10 : m1_11);
-          float d1[32];
+        uint32_t r[32];
+        tc::tmem_ld32(lane_addr + (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g, r);
+        tc::wait_ld();
+        const uint32_t mk = hf == 0 ? mask1a : mask1b;
+        float d1[32];
 #pragma unroll
-          for (int e = 0; e < 32; ++e) d1[e] = __uint_as_float(r[e]) * (((mk >> e) & 1u) ? 1.0f : LIDF_LEAKY);
-          float* drow = a.d1 + rowpos * LIDF_H1 + n0;
-          if (a.d1_accumulate) {
+        for (int e = 0; e < 32; ++e) d1[e] = __uint_as_float(r[e]) * (((mk >> e) & 1u) ? 1.0f : LIDF_LEAKY);
+        float* dwarp = a.d1 + wrow0 * LIDF_H1 + n0;
+        if (a.d1_accumulate) {
+          float old[32];
+          load32(old, dwarp, LIDF_H1);
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              const float4 o = *reinterpret_cast<const float4*>(drow + 4 * i);
-              *reinterpret_cast<float4*>(drow + 4 * i) = make_float4(o.x + d1[4 * i], o.y + d1[4 * i + 1], o.z + d1[4 * i + 2], o.w + d1[4 * i + 3]);
-            }
-          } else {
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              *reinterpret_cast<float4*>(drow + 4 * i) = make_float4(d1[4 * i], d1[4 * i + 1], d1[4 * i + 2], d1[4 * i + 3]);
-          }
-          if (a.is_ief) {
-#pragma unroll
-            for (int e = 0; e < 32; ++e) { fb = fmaf(S.u[n0 + e], d1[e], fb); d1[e] *= oin; }
-            const float du = bw_colreduce32(d1, lane);            // du[n0 + l] += sum_rows delta1 o_in
-            if (hf == 0) { if (sb == 0) acc_du[0][0] += du; else acc_du[0][1] += du; }
-            else { if (sb == 0) acc_du[1][0] += du; else acc_du[1][1] += du; }
-          }
+          for (int e = 0; e < 32; ++e) old[e] += d1[e];
+          store32(old, dwarp, LIDF_H1);
+        } else {
+          store32(d1, dwarp, LIDF_H1);
         }
-        tc::fence_before_sync();
-        __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&S.x2_done[hf]);
+        if (a.is_ief) {
+#pragma unroll
+          for (int e = 0; e < 32; ++e) { fb = fmaf(S.u[n0 + e], d1[e], fb); d1[e] *= oin; }
+          const float du = bw_colreduce32(d1, lane);              // du[n0 + l] += sum_rows delta1 o_in
+          if (hf == 0) acc_du0 += du; else acc_du1 += du;
+        }
       }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.x2_done);
       if (rank1) {                                                // dL/d o_{it-1} = dL/d o_it + u . delta1
         S.part[par][g][row] = fb;
-        switch (q) {                                              // the two warps that share these rows (ids 1-4)
-          case 0: asm volatile("bar.sync 1, 64;" ::: "memory"); break;
-          case 1: asm volatile("bar.sync 2, 64;" ::: "memory"); break;
-          case 2: asm volatile("bar.sync 3, 64;" ::: "memory"); break;
-          default: asm volatile("bar.sync 4, 64;" ::: "memory"); break;
-        }
-        if (g == 0 && valid) a.g[cur.orig] = gin + (S.part[par][0][row] + S.part[par][1][row]);
+        tc::bar_quadrant(q);
+        if (g == 0 && valid)
+          a.g[cur.orig] = gin + (((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row]);
         par ^= 1;
       }
       cur = nxt;
     }
-    // column-sum partials: slot (cta, q, column block cb = 2 g + sub-block, lane)
-#pragma unroll
-    for (int sb = 0; sb < 2; ++sb) {
-      float* cp = a.colpart + ((((size_t)blockIdx.x * 4 + q) * 4 + (2 * g + sb)) * 32 + lane) * BW_COLPART;
-      cp[0] += acc_k0[sb]; cp[1] += acc_b2[sb]; cp[2] += acc_du[0][sb]; cp[3] += acc_du[1][sb];
-      if (sb == 0) cp[4] += acc_b4;
-    }
+    float* cp = a.colpart + (((size_t)blockIdx.x * TC_ROW_WARPS + warp) * 32 + lane) * BW_COLPART;
+    cp[0] += acc_k0; cp[1] += acc_b2; cp[2] += acc_du0; cp[3] += acc_du1; cp[4] += acc_b4;
   }
   __syncwarp();
   tc::fence_before_sync();
   __syncthreads();
-  if (warp == BW_ROW_WARPS) tc::tmem_dealloc(tmem, BW_TMEM_COLS);
+  if (warp == TC_ROW_WARPS) tc::tmem_dealloc(tmem, 512);
 }
 
 // column-sum partials -> db2, db3, dw4, db4, du (fixed summation order: cta, then quadrant)
 __global__ void k_bwd_colpart_finish(const float* __restrict__ colpart, int n_cta, float* __restrict__ db2, float* __restrict__ db3,
                                      float* __restrict__ dw4, float* __restrict__ db4, float* __restrict__ du) {
-  const int t = threadIdx.x;                 // 512 threads: (column block cb = (t % 128) / 32, lane, kind = t / 128)
-  auto sum = [&](int cb, int l, int k) {
+  const int t = threadIdx.x;                 // 512 threads: (g = t / 128, kind/col by t % 128)
+  auto sum = [&](int g, int l, int k) {
     float s = 0.f;
     for (int c = 0; c < n_cta; ++c)
-      for (int q = 0; q < 4; ++q) s += colpart[((((size_t)c * 4 + q) * 4 + cb) * 32 + l) * BW_COLPART + k];
+      for (int q = 0; q < 4; ++q) s += colpart[(((size_t)c * TC_ROW_WARPS + (q + 4 * g)) * 32 + l) * BW_COLPART + k];
     return s;
   };
-  const int cb = (t % 128) / 32, l = t % 32;
-  if (t < 128) { if (l < 16) db3[16 * cb + l] = sum(cb, l, 0); else dw4[16 * cb + l - 16] = sum(cb, l, 0); }
-  else if (t < 256) db2[32 * cb + l] = sum(cb, l, 1);
-  else if (t < 384) { if (du) du[32 * cb + l] = sum(cb, l, 2); }
-  else if (t < 512) { if (du) du[128 + 32 * cb + l] = sum(cb, l, 3); }
+  if (t < 128) { const int g = t / 32, l = t % 32; if (l < 16) db3[16 * g + l] = sum(g, l, 0); else dw4[16 * g + l - 16] = sum(g, l, 0); }
+  else if (t < 256) { const int g = (t - 128) / 32, l = t % 32; db2[32 * g + l] = sum(g, l, 1); }
+  else if (t < 384) { const int g = (t - 256) / 32, l = t % 32; if (du) du[32 * g + l] = sum(g, l, 2); }
+  else if (t < 512) { const int g = (t - 384) / 32, l = t % 32; if (du) du[128 + 32 * g + l] = sum(g, l, 3); }
   if (t == 0) {
     float s = 0.f;
     for (int c = 0; c < n_cta; ++c)
       for (int q = 0; q < 4; ++q)
-        for (int ll = 0; ll < 32; ++ll) s += colpart[((((size_t)c * 4 + q) * 4 + 0) * 32 + ll) * BW_COLPART + 4];
+        for (int l = 0; l < 32; ++l) s += colpart[(((size_t)c * TC_ROW_WARPS + q) * 32 + l) * BW_COLPART + 4];
     db4[0] = s;
   }
 }

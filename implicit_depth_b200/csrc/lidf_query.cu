@@ -572,7 +572,7 @@ int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
   b->n_cta = 148;
   b->partial_floats = (size_t)256 * 128 + 256 * 32 + 256 * 128;                // row level: rgb | dir | vox  (>= dW3^T | dW2 | dW1[:,pos])
   b->partial = bm.take<float>(b->partial_floats * b->n_cta);
-  b->colpart = bm.take<float>((size_t)2 * b->n_cta * 16 * 32 * BW_COLPART);      // k_mlp_bwd_tc runs 2 CTAs per SM
+  b->colpart = bm.take<float>((size_t)b->n_cta * TC_ROW_WARPS * 32 * BW_COLPART);
   b->du = bm.take<float>(256); b->dc = bm.take<float>(256);
   b->bytes = bm.off + 256;
   return LIDF_OK;
@@ -735,7 +735,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     const bool ief = dc.kind == LIDF_DEC_IEF;
     const int n_pass = ief ? dc.n_iter : 1;
     LIDF_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float) * b.partial_floats * b.n_cta, st));
-    LIDF_CUDA(cudaMemsetAsync(b.colpart, 0, sizeof(float) * (size_t)2 * b.n_cta * 16 * 32 * BW_COLPART, st));
+    LIDF_CUDA(cudaMemsetAsync(b.colpart, 0, sizeof(float) * (size_t)b.n_cta * TC_ROW_WARPS * 32 * BW_COLPART, st));
     for (int64_t s0 = 0; s0 < P; s0 += b.chunk_rows) {
       const int n_rows = (int)((P - s0) < b.chunk_rows ? (P - s0) : b.chunk_rows);
       const int n_tiles = (n_rows + 127) / 128;
@@ -755,8 +755,8 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
         a.pe = it == n_pass - 1 ? b.pe : nullptr;
         a.d1_accumulate = it == n_pass - 1 ? 0 : 1;
         a.colpart = b.colpart;
-        const int grid = n_tiles < 2 * n_cta ? n_tiles : 2 * n_cta;
-        k_mlp_bwd_tc<3><<<grid, BW_THREADS, bw_smem, st>>>(a);
+        const int grid = n_tiles < n_cta ? n_tiles : n_cta;
+        k_mlp_bwd_tc<3><<<grid, TC_THREADS, bw_smem, st>>>(a);
         LIDF_LAUNCH_CHECK();
         if ((rc = launch_wgrad(b.h2, LIDF_H2, 128, b.d3, LIDF_H3, 64, 64, n_rows, part_w3, n_cta, st))) return rc;     // dW3^T
         if ((rc = launch_wgrad(b.d2, LIDF_H2, 128, b.h1, LIDF_H1, 256, 256, n_rows, part_w2, n_cta, st))) return rc;   // dW2
@@ -773,7 +773,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     if ((rc = finish_wgrad(part_w3, n_cta, 128, 64, 0, gd.w3, 0, 0, 0, -1, nullptr, st))) return rc;
     if ((rc = finish_wgrad(part_w2, n_cta, 128, 256, 1, gd.w2, 256, 256, 0, -1, nullptr, st))) return rc;
     if ((rc = finish_wgrad(part_w1, n_cta, 256, BW_PE_LD, 2, gd.w1, ldw[d], 0, q.pe_pos, -1, nullptr, st))) return rc;
-    k_bwd_colpart_finish<<<1, 512, 0, st>>>(b.colpart, 2 * n_cta, gd.b2, gd.b3, gd.w4, gd.b4, ief ? b.du : nullptr);
+    k_bwd_colpart_finish<<<1, 512, 0, st>>>(b.colpart, n_cta, gd.b2, gd.b3, gd.w4, gd.b4, ief ? b.du : nullptr);
     LIDF_LAUNCH_CHECK();
     // row-level weight gradients of layer 1 from the segment sums: dW1[:,rgb] = G_r^T roi, dW1[:,dir] = G_r^T PE(dir)
     // (+ its ones column = sum_r G_r = db1 / d c), dW1[:,vox] = G_v^T occ_voxel_feat
