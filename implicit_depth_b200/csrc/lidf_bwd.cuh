@@ -732,19 +732,25 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
       if (it >= 2) bw_wait(&S.empty[buf], (uint32_t)((it >> 1) - 1) & 1u);
       const uint32_t sa = data0 + buf * stage_bytes, sb = sa + a_bytes;
       const int64_t row0 = (g0 + it) * WG_ROWS;
-      for (int un = warp; un < n_units; un += WG_LOAD_WARPS) {
+      // three units per warp in flight (24 independent 128-byte loads) before any conversion: the kernel is bound by
+      // memory-level parallelism, not by instruction issue
+      auto unit_load = [&](int un, float (&x)[8]) {
         const int blk = un >> 3, rg = un & 7;
         const bool isA = blk < a_blocks;
         const int f = (isA ? blk : blk - a_blocks) * 32 + lane;
         const float* src = isA ? a.A : a.B;
         const int ld = isA ? a.lda : a.ldb;
         const bool fok = isA ? true : (f < a.n_valid);
-        float x[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
           const int64_t rr = row0 + 8 * rg + i;
           x[i] = (fok && rr < a.rows) ? __ldg(src + (size_t)rr * ld + f) : 0.f;
         }
+      };
+      auto unit_store = [&](int un, const float (&x)[8]) {
+        const int blk = un >> 3, rg = un & 7;
+        const bool isA = blk < a_blocks;
+        const int f = (isA ? blk : blk - a_blocks) * 32 + lane;
         uint32_t h[4], l[4];
 #pragma unroll
         for (int j = 0; j < 4; ++j) tc::split2(x[2 * j], x[2 * j + 1], h[j], l[j]);
@@ -758,6 +764,16 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
           tc::st_shared_v4(base, h[0], h[1], h[2], h[3]);
           tc::st_shared_v4(base + (uint32_t)N * 32u, l[0], l[1], l[2], l[3]);
         }
+      };
+      for (int un = warp; un < n_units; un += 3 * WG_LOAD_WARPS) {
+        float x0[8], x1[8], x2[8];
+        const bool h1 = un + WG_LOAD_WARPS < n_units, h2 = un + 2 * WG_LOAD_WARPS < n_units;
+        unit_load(un, x0);
+        if (h1) unit_load(un + WG_LOAD_WARPS, x1);
+        if (h2) unit_load(un + 2 * WG_LOAD_WARPS, x2);
+        unit_store(un, x0);
+        if (h1) unit_store(un + WG_LOAD_WARPS, x1);
+        if (h2) unit_store(un + 2 * WG_LOAD_WARPS, x2);
       }
       tc::fence_proxy_async();
       __syncwarp();
