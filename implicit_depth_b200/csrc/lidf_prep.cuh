@@ -28,6 +28,18 @@ __global__ void k_validate_indices(const int64_t* __restrict__ pair_vox, int64_t
   if (bid && i < R) { const int64_t b = bid[i]; bad |= b < 0 || b >= B; }
   if (__any_sync(0xffffffffu, bad) && (threadIdx.x & 31) == 0) atomicOr(err, 2);
 }
+// rays that own at least one pair, appended in arbitrary order (every consumer treats rows independently)
+__global__ void k_live_rays(const int* __restrict__ ray_start, int64_t R, int* __restrict__ list, int* __restrict__ count) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const bool live = r < R && ray_start[r + 1] > ray_start[r];
+  const unsigned m = __ballot_sync(0xffffffffu, live);
+  if (!m) return;
+  const int lane = threadIdx.x & 31, leader = __ffs(m) - 1;
+  int base = 0;
+  if (lane == leader) base = atomicAdd(count, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, leader);
+  if (live) list[base + __popc(m & ((1u << lane) - 1u))] = (int)r;
+}
 __global__ void k_publish_flag(const int* __restrict__ err, int32_t* __restrict__ out) { *out = *err; }
 
 // exclusive scan of int32 counts, 3 kernels (block partials, scan of partials, add back)
@@ -254,19 +266,24 @@ __device__ __forceinline__ RoiBox roi_box(int px, int py, int half, int H, int W
 __global__ void __launch_bounds__(LIDF_ROI_THREADS)
 k_roi_align_rays(const float* __restrict__ feat, const float* __restrict__ box, int B, int H, int W,
                  const int64_t* __restrict__ img_ind, const int64_t* __restrict__ bid, int64_t R, int half,
-                 float* __restrict__ out, int* __restrict__ border_list, int* __restrict__ border_count) {
+                 float* __restrict__ out, int* __restrict__ border_list, int* __restrict__ border_count,
+                 const int* __restrict__ ray_start = nullptr) {
   __shared__ float s_tile[32][LIDF_RGB_DIM + 4];
   __shared__ unsigned s_deferred;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int64_t ray_raw = (int64_t)blockIdx.x * 32 + lane;
   const int64_t ray = ray_raw < R ? ray_raw : R - 1;                 // tail lanes recompute the last ray (never stored)
+  // sparse regime (ray_start given): a ray without pairs is never looked at by the decoders -> no feature for it
+  const bool dead = ray_start != nullptr && ray_start[ray + 1] == ray_start[ray];
+  if (ray_start != nullptr && __ballot_sync(0xffffffffu, !dead && ray_raw < R) == 0u) return;   // whole warp column idle
   const int px = (int)img_ind[2 * ray], py = (int)img_ind[2 * ray + 1];
   const int b = (int)lidf_clamp_idx(bid[ray], B);
   const bool interior = box != nullptr && half == 4 && px - 4 >= 0 && px + 4 <= W - 1 && py - 4 >= 0 && py + 4 <= H - 1;
-  const bool defer = box != nullptr && border_list != nullptr && !interior;
+  const bool defer = box != nullptr && border_list != nullptr && !interior && !dead;
   const unsigned dmask = __ballot_sync(0xffffffffu, defer && ray_raw < R);
+  const unsigned deadmask = __ballot_sync(0xffffffffu, dead);
   if (warp == 0) {
-    if (lane == 0) s_deferred = dmask;
+    if (lane == 0) s_deferred = dmask | deadmask;                    // neither group is stored by this kernel
     if (dmask) {                                                     // warp-aggregated append (order is irrelevant)
       const int leader = __ffs(dmask) - 1;
       int base = 0;
@@ -276,7 +293,7 @@ k_roi_align_rays(const float* __restrict__ feat, const float* __restrict__ box, 
     }
   }
   const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
-  if (!defer) {
+  if (!defer && !dead) {
     const RoiBox rb = roi_box(px, py, half, H, W);
     for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
       float o[4];
@@ -573,4 +590,66 @@ __global__ void k_img_normals(const float* __restrict__ pcl, int B, int H, int W
   img_normal_at(pcl, b, y, x, H, W, n, dx, dy);
 #pragma unroll
   for (int k = 0; k < 3; ++k) out[(b * 3 + k) * HW + f] = n[k];
+}
+
+// ------------------------------------------------------------------------------------------------
+// Depth metrics of LIDF.compute_loss for exp_type != 'train' (reference src/models/pipeline.py:570-618): a1/a2/a3, rmse,
+// rmse_log, log10 (sic: natural log, :607), abs_rel, mae, sq_rel over a set of (pred, gt) depth pairs.
+//   rays  (bs != 1, :571-575): the rays whose gt_pos is not all-zero, depth = z of pred_pos / gt_pos
+//   image (bs == 1, :576-603): the reference pulls gt depth, the corrupt mask and the predicted depth image to the host and
+//     resamples them to 256x144 with cv2.resize(INTER_NEAREST); the same nearest-neighbour pick is done here on the device:
+//     dst(y, x) <- src(min(floor(y * H / 144), H - 1), min(floor(x * W / 256), W - 1)) (OpenCV resizeNN, double arithmetic);
+//     valid = gt_depth > 0 (after nan / inf -> 0) and corrupt_mask != 0.
+// Per-element terms are written as two [n][6] slabs for the fixed-order reduction k_ray_loss_reduce:
+//   A = {valid, thresh < 1.05, < 1.10, < 1.25, (gt-pred)^2, (log gt - log pred)^2}
+//   B = {|log gt - log pred|, |gt-pred| / gt, |gt-pred|, (gt-pred)^2 / gt, 0, 0}
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void depth_metric_terms(float pred, float gt, bool valid, float* A, float* B) {
+  if (!valid) {
+#pragma unroll
+    for (int k = 0; k < 6; ++k) { A[k] = 0.f; B[k] = 0.f; }
+    return;
+  }
+  const float thresh = fmaxf(gt / pred, pred / gt);
+  const float d = gt - pred;
+  const float lg = logf(fminf(fmaxf(gt, 1e-6f), 1e6f)) - logf(fminf(fmaxf(pred, 1e-6f), 1e6f));
+  A[0] = 1.f; A[1] = thresh < 1.05f ? 1.f : 0.f; A[2] = thresh < 1.10f ? 1.f : 0.f; A[3] = thresh < 1.25f ? 1.f : 0.f;
+  A[4] = d * d; A[5] = lg * lg;
+  B[0] = fabsf(lg); B[1] = fabsf(d) / gt; B[2] = fabsf(d); B[3] = d * d / gt; B[4] = 0.f; B[5] = 0.f;
+}
+__global__ void k_depth_terms_rays(const float* __restrict__ pred_pos, const float* __restrict__ gt_pos, int64_t R,
+                                   float* __restrict__ partA, float* __restrict__ partB) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const float gx = gt_pos[3 * r], gy = gt_pos[3 * r + 1], gz = gt_pos[3 * r + 2];
+  const bool valid = (fabsf(gx) + fabsf(gy) + fabsf(gz)) != 0.f;             // zero_mask, :560-568
+  depth_metric_terms(pred_pos[3 * r + 2], gz, valid, partA + r * 6, partB + r * 6);
+}
+// z channel of xyz_corrupt_flat with pred_pos scattered in at the miss pixels (:590-592)
+__global__ void k_depth_pred_image(const float* __restrict__ xyz_corrupt_flat, int64_t HW, float* __restrict__ predz) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < HW) predz[i] = xyz_corrupt_flat[3 * i + 2];
+}
+__global__ void k_depth_pred_scatter(const float* __restrict__ pred_pos, const int64_t* __restrict__ flat, int64_t R, int64_t HW,
+                                     float* __restrict__ predz) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  const int64_t f = flat[r];
+  if (f >= 0 && f < HW) predz[f] = pred_pos[3 * r + 2];
+}
+#define LIDF_METRIC_W 256
+#define LIDF_METRIC_H 144
+__global__ void k_depth_terms_image(const float* __restrict__ xyz_flat, const float* __restrict__ corrupt_mask,
+                                    const float* __restrict__ predz, int H, int W, float* __restrict__ partA,
+                                    float* __restrict__ partB) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= LIDF_METRIC_W * LIDF_METRIC_H) return;
+  const int y = i / LIDF_METRIC_W, x = i % LIDF_METRIC_W;
+  const int sy = min((int)floor((double)y * ((double)H / (double)LIDF_METRIC_H)), H - 1);
+  const int sx = min((int)floor((double)x * ((double)W / (double)LIDF_METRIC_W)), W - 1);
+  const size_t s = (size_t)sy * W + sx;
+  float gt = xyz_flat[3 * s + 2];
+  if (isnan(gt) || isinf(gt)) gt = 0.f;
+  const bool valid = gt > 0.f && ((unsigned char)corrupt_mask[s]) != 0;       // seg_mask.astype(np.uint8), :584-588
+  depth_metric_terms(predz[s], gt, valid, partA + (size_t)i * 6, partB + (size_t)i * 6);
 }

@@ -327,18 +327,83 @@ extern "C" int lidf_image_loss(const float* xyz_flat, const int64_t* bid, const 
 }
 
 // -------------------------------------------------------------------------------------------------
+// depth metrics (pipeline.py:570-618): per-element terms -> two fixed-order reductions -> stats[12]
+namespace {
+struct MetricPlan { float* partA; float* partB; double* blockA; double* blockB; unsigned* done; float* predz; size_t bytes; };
+MetricPlan plan_metrics(int64_t n, int64_t HW, char* base) {
+  Bump b{base, 0};
+  MetricPlan m;
+  m.partA = b.take<float>((size_t)(n > 0 ? n : 1) * 6); m.partB = b.take<float>((size_t)(n > 0 ? n : 1) * 6);
+  m.blockA = b.take<double>((size_t)LIDF_LOSS_BLOCKS * 6); m.blockB = b.take<double>((size_t)LIDF_LOSS_BLOCKS * 6);
+  m.done = b.take<unsigned>(2);
+  m.predz = b.take<float>((size_t)(HW > 0 ? HW : 1));
+  m.bytes = b.off + 256;
+  return m;
+}
+int reduce_metrics(const MetricPlan& m, int64_t n, double* stats, cudaStream_t st) {
+  LIDF_CUDA(cudaMemsetAsync(m.done, 0, 2 * sizeof(unsigned), st));
+  const int nb = (int)(n < LIDF_LOSS_BLOCKS ? n : LIDF_LOSS_BLOCKS);
+  k_ray_loss_reduce<<<nb, 256, 0, st>>>(m.partA, n, m.blockA, m.done, stats);
+  LIDF_LAUNCH_CHECK();
+  k_ray_loss_reduce<<<nb, 256, 0, st>>>(m.partB, n, m.blockB, m.done + 1, stats + 6);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_depth_metrics_workspace_bytes(int64_t n_rays, int32_t H, int32_t W) {
+  const int64_t n = n_rays > (int64_t)LIDF_METRIC_W * LIDF_METRIC_H ? n_rays : (int64_t)LIDF_METRIC_W * LIDF_METRIC_H;
+  return plan_metrics(n, (int64_t)H * W, nullptr).bytes;
+}
+extern "C" int lidf_depth_metrics_rays(const float* pred_pos, const float* gt_pos, int64_t R, double* stats, void* ws,
+                                       size_t ws_bytes, lidf_stream_t stream) {
+  if (!stats || !ws) return LIDF_ERR_NULL;
+  cudaStream_t st = stream;
+  LIDF_CUDA(cudaMemsetAsync(stats, 0, 12 * sizeof(double), st));
+  if (R <= 0) return LIDF_OK;
+  if (!pred_pos || !gt_pos) return LIDF_ERR_NULL;
+  MetricPlan m = plan_metrics(R, 0, (char*)ws);
+  if (ws_bytes < m.bytes) return LIDF_ERR_WORKSPACE;
+  k_depth_terms_rays<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(pred_pos, gt_pos, R, m.partA, m.partB);
+  LIDF_LAUNCH_CHECK();
+  return reduce_metrics(m, R, stats, st);
+}
+extern "C" int lidf_depth_metrics_image(const float* xyz_flat, const float* xyz_corrupt_flat, const float* corrupt_mask,
+                                        const int64_t* miss_flat_img_id, const float* pred_pos, int64_t R, int32_t H, int32_t W,
+                                        double* stats, void* ws, size_t ws_bytes, lidf_stream_t stream) {
+  if (!xyz_flat || !xyz_corrupt_flat || !corrupt_mask || !stats || !ws) return LIDF_ERR_NULL;
+  if (H <= 0 || W <= 0 || R < 0 || (R > 0 && (!miss_flat_img_id || !pred_pos))) return LIDF_ERR_ARG;
+  cudaStream_t st = stream;
+  const int64_t HW = (int64_t)H * W, n = (int64_t)LIDF_METRIC_W * LIDF_METRIC_H;
+  MetricPlan m = plan_metrics(n, HW, (char*)ws);
+  if (ws_bytes < m.bytes) return LIDF_ERR_WORKSPACE;
+  k_depth_pred_image<<<(unsigned)((HW + 255) / 256), 256, 0, st>>>(xyz_corrupt_flat, HW, m.predz);
+  LIDF_LAUNCH_CHECK();
+  if (R > 0) {
+    k_depth_pred_scatter<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(pred_pos, miss_flat_img_id, R, HW, m.predz);
+    LIDF_LAUNCH_CHECK();
+  }
+  k_depth_terms_image<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(xyz_flat, corrupt_mask, m.predz, H, W, m.partA, m.partB);
+  LIDF_LAUNCH_CHECK();
+  return reduce_metrics(m, n, stats, st);
+}
+
+// -------------------------------------------------------------------------------------------------
 namespace {
 
 struct QueryPlan {
   int impl, pe_pos, pe_dir, D, KR, KP;
   CsrBufs csr;
   float* roi_feat; float* T; float* Av; float* box4; int* border_list; int* border_count;
+  int* live_list; int* live_count;          // sparse regime: rays that own a pair (row prep works on these only)
   SimtPack sp;
   TcBufs tc;
-  size_t bytes;
+  size_t bytes;                             // workspace
+  size_t cache_bytes;                       // packed-weight region (inside the workspace unless p->weight_cache is given)
+  bool packed;                              // the packed weights in the cache are valid: skip the packing launches
 };
 
-int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
+int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base, bool sizing_cache_only = false, bool allow_sparse = true) {
   int rc = resolve_impl(p->mlp_impl, &q->impl);
   if (rc) return rc;
   if (p->multires < 0 || p->multires > LIDF_MAX_MULTIRES || p->multires_views < 0 || p->multires_views > LIDF_MAX_MULTIRES)
@@ -357,16 +422,23 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base) {
   q->border_list = use_box ? b.take<int>((size_t)(p->R > 0 ? p->R : 1)) : nullptr;
   q->border_count = use_box ? b.take<int>(1) : nullptr;
   q->T = b.take<float>((size_t)p->R * 512);
-  if (q->impl == LIDF_MLP_SIMT_FP32) {
-    q->Av = b.take<float>((size_t)p->V * 512);
-    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, true);
-  } else {
-    if (q->KP > TC_KPE_MAX) return LIDF_ERR_UNSUPPORTED;
-    q->Av = b.take<float>((size_t)p->V * 512);
-    q->sp = carve_simt_pack(b, 2, q->KR, q->KP, true);    // row-prep matrices are shared with the SIMT engine
-    q->tc = carve_tc(b, p->V, 2);
-  }
-  q->bytes = b.off + 256;
+  q->Av = b.take<float>((size_t)p->V * 512);
+  // sparse regime (fewer than 8 pairs per ray on average, no per-ray ROI output requested): per-ray work only for rays
+  // that own a pair
+  const bool sparse = allow_sparse && !p->roi_feat_per_ray && p->P < 8 * p->R && !use_box;
+  q->live_list = sparse ? b.take<int>((size_t)(p->R > 0 ? p->R : 1)) : nullptr;
+  q->live_count = sparse ? b.take<int>(1) : nullptr;
+  if (q->impl != LIDF_MLP_SIMT_FP32 && q->KP > TC_KPE_MAX) return LIDF_ERR_UNSUPPORTED;
+  // packed weights: in the caller's cache buffer when given, else at the end of the workspace
+  const bool ext = p->weight_cache != nullptr && base != nullptr;
+  Bump c{ext ? (char*)p->weight_cache : base, ext || sizing_cache_only ? 0 : b.off};
+  if (sizing_cache_only) c.base = nullptr;
+  q->sp = carve_simt_pack(c, 2, q->KR, q->KP, true);      // row-prep matrices are shared by both engines
+  if (q->impl != LIDF_MLP_SIMT_FP32) q->tc = carve_tc(c, p->V, 2);
+  q->cache_bytes = (ext || sizing_cache_only ? c.off : c.off - b.off) + 256;
+  q->packed = ext && p->weight_cache_valid != 0;
+  if (ext && p->weight_cache_bytes < q->cache_bytes) return LIDF_ERR_WORKSPACE;
+  q->bytes = (ext ? b.off : c.off) + 256;
   return LIDF_OK;
 }
 
@@ -387,17 +459,27 @@ int run_prep(const LidfQueryParams* p, QueryPlan& q, cudaStream_t st) {
     LIDF_LAUNCH_CHECK();
   }
   // 2. ROIAlign per ray
+  if (q.live_list) {
+    LIDF_CUDA(cudaMemsetAsync(q.live_count, 0, sizeof(int), st));
+    k_live_rays<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(q.csr.ray_start, R, q.live_list, q.live_count);
+    LIDF_LAUNCH_CHECK();
+  }
   if (q.box4) {
     if ((rc = roi_align_rays_box(p->full_rgb_feat, q.box4, q.border_list, q.border_count, p->B, p->H, p->W, p->miss_img_ind,
                                  p->miss_bid, R, p->roi_inp_bbox, q.roi_feat, st))) return rc;
+  } else if (q.live_list && R > 0) {
+    k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, st>>>(p->full_rgb_feat, nullptr, p->B, p->H, p->W,
+                                                                              p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox / 2,
+                                                                              q.roi_feat, nullptr, nullptr, q.csr.ray_start);
+    LIDF_LAUNCH_CHECK();
   } else if ((rc = lidf_roi_align_rays(p->full_rgb_feat, p->B, p->H, p->W, p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox,
                                        q.roi_feat, st))) return rc;
   if (P > 0) {
-    // 3. weights
+    // 3. weights (skipped when the caller's weight cache already holds them)
     const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
     SimtPack& sp = q.sp;
-    LIDF_CUDA(cudaMemsetAsync(sp.Wt_row, 0, sizeof(float) * (size_t)sp.KR * sp.Ntot, st));
-    for (int d = 0; d < 2; ++d) {
+    if (!q.packed) LIDF_CUDA(cudaMemsetAsync(sp.Wt_row, 0, sizeof(float) * (size_t)sp.KR * sp.Ntot, st));
+    for (int d = 0; d < 2 && !q.packed; ++d) {
       const LidfDecoder& dc = *decs[d];
       const int ldw = q.D + (dc.kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
       // per-ray rows: [rgb(128) | PE(dir)]
@@ -428,7 +510,8 @@ int run_prep(const LidfQueryParams* p, QueryPlan& q, cudaStream_t st) {
                          p->multires_views == 4 && tc_device_ok();
       if (rp_tc) {
         if ((rc = tc_rowprep_forward(q.roi_feat, p->miss_ray_dir, R, sp.Wt_row, sp.Ntot, sp.bias_row, q.tc.rp_wstream, q.T,
-                                     q.impl, st, &g_launches, g_cuda_err, sizeof(g_cuda_err)))) return rc;
+                                     q.impl, st, &g_launches, g_cuda_err, sizeof(g_cuda_err), q.packed, q.live_list,
+                                     q.live_count))) return rc;
       } else {
         k_rowprep<<<dim3((unsigned)((R + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), a.Ntot / 128), LIDF_SIMT_THREADS, smem, st>>>(a);
         LIDF_LAUNCH_CHECK();
@@ -451,6 +534,12 @@ extern "C" size_t lidf_query_workspace_bytes(const LidfQueryParams* p) {
   QueryPlan q;
   if (plan_query(p, &q, nullptr) != LIDF_OK) return 0;
   return q.bytes;
+}
+extern "C" size_t lidf_query_weight_cache_bytes(const LidfQueryParams* p) {
+  if (!p) return 0;
+  QueryPlan q;
+  if (plan_query(p, &q, nullptr, true) != LIDF_OK) return 0;
+  return q.cache_bytes;
 }
 
 extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream) {
@@ -547,8 +636,8 @@ struct BwdPlan {
 
 int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
   LidfQueryParams fp = bp->fwd;
-  fp.mlp_impl = LIDF_MLP_TC_BF16X3; fp.roi_feat_per_ray = nullptr;
-  int rc = plan_query(&fp, &b->q, base);
+  fp.mlp_impl = LIDF_MLP_TC_BF16X3; fp.roi_feat_per_ray = nullptr; fp.weight_cache = nullptr; fp.weight_cache_valid = 0;
+  int rc = plan_query(&fp, &b->q, base, false, false);    // dense per-ray rows: the wgrad GEMMs read every ROI / T row
   if (rc) return rc;
   const int64_t P = fp.P, R = fp.R, V = fp.V;
   Bump bm{base, b->q.bytes};
@@ -642,6 +731,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
   if (!bp) return LIDF_ERR_NULL;
   LidfQueryParams fp = bp->fwd;
   fp.mlp_impl = LIDF_MLP_TC_BF16X3; fp.roi_feat_per_ray = nullptr; fp.index_error = nullptr; fp.ief_iter_out = nullptr;
+  fp.weight_cache = nullptr; fp.weight_cache_valid = 0;
   const LidfQueryParams* p = &fp;
   if (p->P < 0 || p->R < 0 || p->V < 0 || p->B <= 0 || p->H <= 0 || p->W <= 0) return LIDF_ERR_ARG;
   if (p->P >= INT_MAX || p->R >= INT_MAX / 32 || p->V >= INT_MAX / 512) return LIDF_ERR_UNSUPPORTED;

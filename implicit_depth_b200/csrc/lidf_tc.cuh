@@ -1033,6 +1033,8 @@ struct TcRowPrepArgs {
   const uint8_t* wstream;          // [4 N-chunks][10 k-steps][8 KB]
   const float* bias;               // [512]
   float* out;                      // [rows][512]
+  const int* row_list;             // optional: work on rows row_list[0 .. *n_list) only (sparse regime: rays that own a pair)
+  const int* n_list;
 };
 struct TcRowPrepSmem {
   uint8_t w[RP_STAGES][TC_STAGE_BYTES];
@@ -1075,7 +1077,9 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = S.tmem_base;
-  const int n_my_tiles = (a.n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int64_t n_rows = a.row_list ? (int64_t)*a.n_list : a.rows;
+  const int n_tiles = a.row_list ? (int)((n_rows + 127) / 128) : a.n_tiles;
+  const int n_my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == RP_ROW_WARPS + 1) {
     // ---- weight loader: 20 fills of 16 KB per tile (4 N-chunks x 5), ring of 5 -> slot = fill % 5, 4 rotations / tile
@@ -1145,7 +1149,10 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
           const int rg = it >> 3, ks = it & 7;
           const int r = 8 * rg + r8;
           float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + r < a.rows) v = __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)(row0 + r) * 128 + 16 * ks) + j4);
+          if (row0 + r < n_rows) {
+            const int64_t src = a.row_list ? (int64_t)a.row_list[row0 + r] : row0 + r;
+            v = __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)src * 128 + 16 * ks) + j4);
+          }
           uint32_t h0, l0, h1, l1;
           tc::split2(v.x, v.y, h0, l0);
           tc::split2(v.z, v.w, h1, l1);
@@ -1159,8 +1166,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
         float x[32];
 #pragma unroll
         for (int k = 0; k < 32; ++k) x[k] = 0.f;
-        if (row0 + row < a.rows) {
-          const float* dp = a.dirs + (size_t)(row0 + row) * 3;
+        if (row0 + row < n_rows) {
+          const float* dp = a.dirs + (size_t)(a.row_list ? (int64_t)a.row_list[row0 + row] : row0 + row) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float dv = dp[c];
@@ -1190,8 +1197,8 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.a_ready);
       // epilogue: this thread owns columns [64 h, 64 h + 64) of every N-chunk of its row
-      const bool live = row0 + row < a.rows;
-      float* orow = a.out + (size_t)(row0 + row) * 512 + 64 * h;
+      const bool live = row0 + row < n_rows;
+      float* orow = a.out + (size_t)(live && a.row_list ? (int64_t)a.row_list[row0 + row] : row0 + row) * 512 + 64 * h;
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tc::mbar_wait(&S.d_full[c], ph);
@@ -1267,7 +1274,7 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   if (!p->pos_encode || p->multires != 8 || pe_pos != 51) return LIDF_ERR_UNSUPPORTED;   // A1 layout is built for PE(8)
   if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
   const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
-  for (int d = 0; d < 2; ++d) {
+  for (int d = 0; d < 2 && !(p->weight_cache && p->weight_cache_valid); ++d) {
     const int ldw = D + (decs[d]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
     k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(
         decs[d]->w1, ldw, pe_pos, decs[d]->w2, decs[d]->w3, tb.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES, 0);
@@ -1354,12 +1361,14 @@ inline int tc_refine_forward(const LidfRefineParams* p, const TcBufs& tb, const 
 // per-ray layer-1 term on the tensor cores; Wt = sp.Wt_row [160][512], wstream scratch = 4 x 10 x 8 KB
 inline int tc_rowprep_forward(const float* roi_feat, const float* dirs, int64_t R, const float* Wt, int Ntot, const float* bias,
                               uint8_t* wstream, float* T, int impl, cudaStream_t st, int64_t* launches, char* errbuf,
-                              size_t errlen) {
-  k_pack_rowprep_tc<<<(4 * RP_KSTEPS * 2048 + 255) / 256, 256, 0, st>>>(Wt, Ntot, wstream);
-  TC_LAUNCH_CHECK();
+                              size_t errlen, bool packed = false, const int* row_list = nullptr, const int* n_list = nullptr) {
+  if (!packed) {
+    k_pack_rowprep_tc<<<(4 * RP_KSTEPS * 2048 + 255) / 256, 256, 0, st>>>(Wt, Ntot, wstream);
+    TC_LAUNCH_CHECK();
+  }
   TcRowPrepArgs a{};
   a.feat = roi_feat; a.dirs = dirs; a.rows = R; a.n_tiles = (int)((R + 127) / 128);
-  a.wstream = wstream; a.bias = bias; a.out = T;
+  a.wstream = wstream; a.bias = bias; a.out = T; a.row_list = row_list; a.n_list = n_list;
   int dev = 0, sms = 0;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);

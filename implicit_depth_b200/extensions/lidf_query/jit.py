@@ -48,7 +48,8 @@ class _QueryParams(C.Structure):
                 ("pred_offset", C.c_void_p), ("pred_prob_end", C.c_void_p), ("pair_pred_pos", C.c_void_p),
                 ("pred_prob_end_softmax", C.c_void_p), ("max_pair_id", C.c_void_p), ("pred_pos", C.c_void_p),
                 ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
-                ("ief_iter_out", C.c_void_p), ("index_error", C.c_void_p)]
+                ("ief_iter_out", C.c_void_p), ("index_error", C.c_void_p),
+                ("weight_cache", C.c_void_p), ("weight_cache_bytes", C.c_size_t), ("weight_cache_valid", C.c_int32)]
 
 
 class _DecoderGrad(C.Structure):
@@ -76,12 +77,13 @@ class _RefineParams(C.Structure):
 ABI_VERSION = 3
 EXPORTED_SYMBOLS = [
     "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
-    "lidf_query_workspace_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
+    "lidf_query_workspace_bytes", "lidf_query_weight_cache_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
     "lidf_roi_align_rays", "lidf_ray_terminate_workspace_bytes", "lidf_ray_terminate", "lidf_query_launch_count",
     "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
     "lidf_image_loss_workspace_bytes", "lidf_image_loss",
     "lidf_query_backward_workspace_bytes", "lidf_query_backward", "lidf_query_last_bwd_ms",
     "lidf_wgrad_selftest_scratch_bytes", "lidf_wgrad_selftest",
+    "lidf_depth_metrics_workspace_bytes", "lidf_depth_metrics_rays", "lidf_depth_metrics_image",
 ]
 # include/lidf_pointnet.h (bound by models/pointnet.py)
 EXPORTED_SYMBOLS_POINTNET = ["lidf_pointnet_workspace_bytes", "lidf_pointnet_forward"]
@@ -107,6 +109,8 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_query_last_cuda_error.restype = C.c_char_p
     lib.lidf_query_workspace_bytes.restype = C.c_size_t
     lib.lidf_query_workspace_bytes.argtypes = [C.POINTER(_QueryParams)]
+    lib.lidf_query_weight_cache_bytes.restype = C.c_size_t
+    lib.lidf_query_weight_cache_bytes.argtypes = [C.POINTER(_QueryParams)]
     lib.lidf_query_forward.restype = C.c_int
     lib.lidf_query_forward.argtypes = [C.POINTER(_QueryParams), C.c_void_p]
     lib.lidf_query_backward_workspace_bytes.restype = C.c_size_t
@@ -118,6 +122,12 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_wgrad_selftest_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.lidf_wgrad_selftest.restype = C.c_int
     lib.lidf_wgrad_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.lidf_depth_metrics_workspace_bytes.restype = C.c_size_t
+    lib.lidf_depth_metrics_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    lib.lidf_depth_metrics_rays.restype = C.c_int
+    lib.lidf_depth_metrics_rays.argtypes = [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
+    lib.lidf_depth_metrics_image.restype = C.c_int
+    lib.lidf_depth_metrics_image.argtypes = [C.c_void_p] * 5 + [C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p, C.c_size_t, C.c_void_p]
     lib.lidf_refine_workspace_bytes.restype = C.c_size_t
     lib.lidf_refine_workspace_bytes.argtypes = [C.POINTER(_RefineParams)]
     lib.lidf_refine_forward.restype = C.c_int
@@ -512,6 +522,30 @@ class _LidfQuery:
         p.mlp_impl = MLP_IMPLS[mlp_impl]
         return p
 
+    use_weight_cache = True
+
+    def _attach_weight_cache(self, p: _QueryParams, keep: list, dev) -> None:
+        """Packed decoder weights persist across calls in a device buffer owned by this wrapper (one per device, stream
+        and engine).  They are re-packed only when a decoder tensor was replaced or modified in place (``data_ptr`` /
+        ``_version`` of every tensor -- an optimizer step bumps the version) or a setting that enters the packing changed."""
+        if not self.use_weight_cache:
+            return
+        stream = torch.cuda.current_stream(dev).cuda_stream
+        slot = (dev.index if dev.index is not None else torch.cuda.current_device(), stream, int(p.mlp_impl))
+        key = tuple((t.data_ptr(), t._version, tuple(t.shape)) for t in keep) + (
+            int(p.pos_encode), int(p.multires), int(p.multires_views), int(p.offset_dec.kind), int(p.offset_dec.n_iter),
+            float(p.offset_dec.init_offset))
+        nbytes = int(self.lib.lidf_query_weight_cache_bytes(C.byref(p)))
+        if nbytes == 0:
+            return
+        caches = self.__dict__.setdefault("_wcaches", {})
+        buf, old_key = caches.get(slot, (None, None))
+        if buf is None or buf.numel() < nbytes:
+            buf, old_key = torch.empty(nbytes, dtype=torch.uint8, device=dev), None
+        p.weight_cache, p.weight_cache_bytes = buf.data_ptr(), buf.numel()
+        p.weight_cache_valid = int(old_key == key)
+        caches[slot] = (buf, key)
+
     def check_index_errors(self, wait: bool = True) -> None:
         """Raise if an earlier ``forward`` saw an out-of-range pair_ray / pair_vox / miss_bid value.  The kernels clamp
         such indices (no out-of-bounds access) and set a device flag that is copied to pinned host memory right behind
@@ -564,6 +598,7 @@ class _LidfQuery:
             p.ief_iter_out = out["ief_iter"].data_ptr() if n_it > 1 and P > 0 else None
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         p.index_error = flag.data_ptr()
+        self._attach_weight_cache(p, keep, dev)
         for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
             setattr(p, k, out[k].data_ptr())
         nbytes = int(self.lib.lidf_query_workspace_bytes(C.byref(p)))
@@ -815,4 +850,48 @@ class _LidfQuery:
         return out
 
 
+METRIC_KEYS = ("a1", "a2", "a3", "rmse", "rmse_log", "log10", "abs_rel", "mae", "sq_rel")
+
+
+def _metrics_from_stats(stats: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """stats[12] (include/lidf_query.h) -> the reference's nine depth metrics as 0-dim fp32 tensors (no host sync)."""
+    n = stats[0]
+    out = {"a1": stats[1] / n, "a2": stats[2] / n, "a3": stats[3] / n, "rmse": (stats[4] / n).sqrt(),
+           "rmse_log": (stats[5] / n).sqrt(), "log10": stats[6] / n, "abs_rel": stats[7] / n, "mae": stats[8] / n,
+           "sq_rel": stats[9] / n}
+    return {k: v.float() for k, v in out.items()}
+
+
+def _depth_metrics(self, pred_pos, gt_pos=None, *, xyz_flat=None, xyz_corrupt_flat=None, corrupt_mask=None,
+                   miss_flat_img_id=None, h: int = 0, w: int = 0):
+    """Depth metrics of LIDF.compute_loss for exp_type != 'train' (reference pipeline.py:570-618).  With ``gt_pos``: the
+    bs != 1 branch over rays.  With ``xyz_flat`` / ``xyz_corrupt_flat`` [1,H*W,3], ``corrupt_mask`` [1,H,W] and
+    ``miss_flat_img_id``: the bs == 1 branch (cv2 nearest-neighbour resampling to 256x144) entirely on the device."""
+    dev = pred_pos.device
+    R = int(pred_pos.shape[0])
+    stats = torch.empty(12, dtype=torch.float64, device=dev)
+    nbytes = int(self.lib.lidf_depth_metrics_workspace_bytes(R, int(h), int(w)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+    with torch.cuda.device(dev):
+        st = C.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+        if gt_pos is not None:
+            rc = self.lib.lidf_depth_metrics_rays(_chk(pred_pos, "pred_pos", torch.float32), _chk(gt_pos, "gt_pos", torch.float32), R,
+                                                  stats.data_ptr(), ws.data_ptr(), nbytes, st)
+        else:
+            if tuple(xyz_flat.shape) != (1, h * w, 3) or tuple(xyz_corrupt_flat.shape) != (1, h * w, 3) or corrupt_mask.numel() != h * w:
+                raise RuntimeError("depth_metrics (bs == 1): xyz_flat / xyz_corrupt_flat must be [1,h*w,3], corrupt_mask [1,h,w]")
+            rc = self.lib.lidf_depth_metrics_image(_chk(xyz_flat, "xyz_flat", torch.float32),
+                                                   _chk(xyz_corrupt_flat, "xyz_corrupt_flat", torch.float32),
+                                                   _chk(corrupt_mask, "corrupt_mask", torch.float32),
+                                                   _chk(miss_flat_img_id, "miss_flat_img_id", torch.int64),
+                                                   _chk(pred_pos, "pred_pos", torch.float32), R, int(h), int(w),
+                                                   stats.data_ptr(), ws.data_ptr(), nbytes, st)
+    self._raise(rc, "lidf_depth_metrics")
+    ws.record_stream(torch.cuda.current_stream(dev))
+    out = _metrics_from_stats(stats)
+    out["stats"] = stats
+    return out
+
+
+_LidfQuery.depth_metrics = _depth_metrics
 lidf_query = _LidfQuery()

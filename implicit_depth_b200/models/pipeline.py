@@ -131,8 +131,9 @@ class LIDFQueryMixin:
         setting ``hard_neg: False``: the ray-keyed terms come from ``lidf_ray_loss``, the image-space terms from
         ``lidf_image_loss``; ``loss_net`` is assembled with the same weights and epoch gates (:538-543).  Returns the
         reference's ``loss_dict`` keys as 0-dim tensors (no host sync).  For ``exp_type != 'train'`` the depth metrics
-        (:570-606) are added for ``bs != 1``; the ``bs == 1`` variant resamples through cv2 on the host and is left to the
-        reference code.  Training needs gradients and keeps using the reference's ``compute_loss``."""
+        (:570-618) are added by ``lidf_depth_metrics_*`` -- both the ``bs != 1`` branch over rays and the ``bs == 1`` branch,
+        whose cv2 nearest-neighbour resampling to 256x144 is done on the device instead of through the host.  Training
+        needs gradients and keeps using the reference's ``compute_loss``."""
         L = self.opt.loss
         if getattr(L, 'hard_neg', False):
             raise NotImplementedError('compute_loss_eval covers hard_neg: False (the shipped lidf YAMLs)')
@@ -151,17 +152,15 @@ class LIDFQueryMixin:
         loss_dict = {'pos_loss': ray['pos_loss'], 'prob_loss': ray['prob_loss'], 'surf_norm_loss': img['surf_norm_loss'],
                      'smooth_loss': img['smooth_loss'], 'loss_net': loss_net, 'acc': ray['acc'], 'err': ray['err'],
                      'angle_err': img['angle_err']}
-        if exp_type != 'train' and bs != 1:
-            keep = torch.sum(data_dict['gt_pos'].abs(), dim=-1) != 0                                # zero_mask, :560-568
-            pred, gt = data_dict['pred_pos'][:, 2][keep], data_dict['gt_pos'][:, 2][keep]
-            safe_log = lambda x: torch.log(torch.clamp(x, 1e-6, 1e6))
-            thresh = torch.max(gt / pred, pred / gt)
-            loss_dict.update({'a1': (thresh < 1.05).float().mean(), 'a2': (thresh < 1.10).float().mean(),
-                              'a3': (thresh < 1.25).float().mean(), 'rmse': ((gt - pred) ** 2).mean().sqrt(),
-                              'rmse_log': ((safe_log(gt) - safe_log(pred)) ** 2).mean().sqrt(),
-                              'log10': (safe_log(gt) - safe_log(pred)).abs().mean(),       # sic: the reference's safe_log10 is log
-                              'abs_rel': ((gt - pred).abs() / gt).mean(), 'mae': (gt - pred).abs().mean(),
-                              'sq_rel': ((gt - pred) ** 2 / gt).mean()})
+        if exp_type != 'train':                                                                  # depth metrics, :570-618
+            if bs != 1:
+                m = lidf_query.depth_metrics(data_dict['pred_pos'].contiguous(), data_dict['gt_pos'].float().contiguous())
+            else:       # the reference's cv2.resize(256x144, INTER_NEAREST) host round trip, done on the device
+                m = lidf_query.depth_metrics(data_dict['pred_pos'].contiguous(), xyz_flat=data_dict['xyz_flat'].float().contiguous(),
+                                             xyz_corrupt_flat=data_dict['xyz_corrupt_flat'].float().contiguous(),
+                                             corrupt_mask=data_dict['corrupt_mask'].float().contiguous(),
+                                             miss_flat_img_id=data_dict['miss_flat_img_id'].long().contiguous(), h=h, w=w)
+            loss_dict.update({k: m[k] for k in ('a1', 'a2', 'a3', 'rmse', 'rmse_log', 'log10', 'abs_rel', 'mae', 'sq_rel')})
         return loss_dict
 
     def get_pred(self, data_dict, exp_type, epoch):

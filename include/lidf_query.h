@@ -116,6 +116,10 @@ typedef struct LidfQueryParams {
                                  * range.  Such entries are clamped into range (nothing is read or written out of
                                  * bounds) and the results for them are meaningless -- the reference trips a device-side
                                  * assert in the same situation. */
+  void* weight_cache;           /* optional caller-owned device buffer, >= lidf_query_weight_cache_bytes(p): holds the   */
+  size_t weight_cache_bytes;    /* packed decoder weights (k-major fp32 copies, bf16 hi|lo MMA streams, folded biases)   */
+  int32_t weight_cache_valid;   /* between calls.  0: this call packs into it; 1: the ~20 packing launches are skipped   */
+                                /* (the caller vouches that no decoder tensor changed since the call that filled it).    */
 } LidfQueryParams;
 
 /* Gradients of one decoder's parameters: fp32 device buffers with the shapes of the LidfDecoder tensors; every buffer is
@@ -179,6 +183,7 @@ const char* lidf_query_error_string(int code);
 const char* lidf_query_last_cuda_error(void);
 
 size_t lidf_query_workspace_bytes(const LidfQueryParams* p);
+size_t lidf_query_weight_cache_bytes(const LidfQueryParams* p);
 int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream);
 
 size_t lidf_query_backward_workspace_bytes(const LidfQueryBackwardParams* p);
@@ -234,6 +239,22 @@ size_t lidf_image_loss_workspace_bytes(int32_t B, int32_t H, int32_t W, int64_t 
 int lidf_image_loss(const float* xyz_flat, const int64_t* miss_bid, const int64_t* miss_flat_img_id, const float* pred_pos,
                     const float* gt_pos, int32_t B, int32_t H, int32_t W, int64_t R, float* pred_surf_norm_img,
                     float* gt_surf_norm_img, double* stats, void* workspace, size_t workspace_bytes, lidf_stream_t stream);
+
+/* Depth metrics of LIDF.compute_loss for exp_type != 'train' (pipeline.py:570-618).  stats[12] (device, double) =
+ *   {n, #(thresh < 1.05), #(< 1.10), #(< 1.25), sum (gt-pred)^2, sum (log gt - log pred)^2,
+ *    sum |log gt - log pred|, sum |gt-pred|/gt, sum |gt-pred|, sum (gt-pred)^2/gt, 0, 0}
+ * so that a1 = s1/n, a2 = s2/n, a3 = s3/n, rmse = sqrt(s4/n), rmse_log = sqrt(s5/n), log10 = s6/n (natural log, as the
+ * reference computes it), abs_rel = s7/n, mae = s8/n, sq_rel = s9/n.
+ * _rays  (bs != 1, :571-575): rays whose gt_pos is not all-zero; depth = z of pred_pos / gt_pos [R,3].
+ * _image (bs == 1, :576-603): the reference's host round trip -- gt depth (z of xyz_flat [H*W,3], nan/inf -> 0), corrupt_mask
+ *   [H,W] (fp32 0/1) and the predicted depth image (z of xyz_corrupt_flat with pred_pos scattered in at miss_flat_img_id)
+ *   resampled to 256x144 by cv2.resize(INTER_NEAREST) -- as one device-side nearest-neighbour pick; valid = gt > 0 and mask. */
+size_t lidf_depth_metrics_workspace_bytes(int64_t n_rays, int32_t H, int32_t W);
+int lidf_depth_metrics_rays(const float* pred_pos, const float* gt_pos, int64_t R, double* stats, void* workspace,
+                            size_t workspace_bytes, lidf_stream_t stream);
+int lidf_depth_metrics_image(const float* xyz_flat, const float* xyz_corrupt_flat, const float* corrupt_mask,
+                             const int64_t* miss_flat_img_id, const float* pred_pos, int64_t R, int32_t H, int32_t W,
+                             double* stats, void* workspace, size_t workspace_bytes, lidf_stream_t stream);
 
 /* unit test of the tcgen05 primitives the decoder engine is built from (tcgen05.st operand staging, TMA weight chunks,
  * TS-mode tcgen05.mma with the 3-product bf16 split, tcgen05.ld): D[128,128] = A[128,32] * W[128,32]^T, fp32 device

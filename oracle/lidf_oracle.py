@@ -317,6 +317,44 @@ DEFAULT_CFG = dict(
 )
 
 
+def depth_metrics(pred: torch.Tensor, gt: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """The nine depth metrics of LIDF.compute_loss (pipeline.py:605-618) over matched 1-D depth tensors."""
+    safe_log = lambda x: torch.log(torch.clamp(x, 1e-6, 1e6))      # noqa: E731  (safe_log10 is the same natural log, :607)
+    thresh = torch.max(gt / pred, pred / gt)
+    return dict(a1=(thresh < 1.05).float().mean(), a2=(thresh < 1.10).float().mean(), a3=(thresh < 1.25).float().mean(),
+                rmse=((gt - pred) ** 2).mean().sqrt(), rmse_log=((safe_log(gt) - safe_log(pred)) ** 2).mean().sqrt(),
+                log10=(safe_log(gt) - safe_log(pred)).abs().mean(), abs_rel=((gt - pred).abs() / gt).mean(),
+                mae=(gt - pred).abs().mean(), sq_rel=((gt - pred) ** 2 / gt).mean())
+
+
+def resize_nearest(img: torch.Tensor, out_w: int = 256, out_h: int = 144) -> torch.Tensor:
+    """cv2.resize(img, (out_w, out_h), interpolation=cv2.INTER_NEAREST) for a 2-D array (OpenCV resizeNN):
+    dst(y, x) = src(min(floor(y * H / out_h), H - 1), min(floor(x * W / out_w), W - 1)), double arithmetic."""
+    H, W = img.shape
+    ys = torch.clamp(torch.floor(torch.arange(out_h, dtype=torch.float64) * (H / out_h)).long(), max=H - 1)
+    xs = torch.clamp(torch.floor(torch.arange(out_w, dtype=torch.float64) * (W / out_w)).long(), max=W - 1)
+    return img[ys][:, xs]
+
+
+def depth_metrics_rays(pred_pos: torch.Tensor, gt_pos: torch.Tensor) -> Dict[str, torch.Tensor]:
+    """bs != 1 branch (pipeline.py:560-575): rays whose gt_pos is not all-zero, z components."""
+    keep = gt_pos.abs().sum(-1) != 0
+    return depth_metrics(pred_pos[:, 2][keep], gt_pos[:, 2][keep])
+
+
+def depth_metrics_image(xyz_flat: torch.Tensor, xyz_corrupt_flat: torch.Tensor, corrupt_mask: torch.Tensor,
+                        miss_flat_img_id: torch.Tensor, pred_pos: torch.Tensor, h: int, w: int) -> Dict[str, torch.Tensor]:
+    """bs == 1 branch (pipeline.py:576-603) without the host round trip."""
+    gt = resize_nearest(xyz_flat[0, :, 2].reshape(h, w))
+    gt = torch.where(torch.isnan(gt) | torch.isinf(gt), torch.zeros_like(gt), gt)
+    seg = resize_nearest(corrupt_mask.reshape(h, w).to(torch.uint8))
+    pz = xyz_corrupt_flat[0, :, 2].clone()
+    pz[miss_flat_img_id] = pred_pos[:, 2]
+    pred = resize_nearest(pz.reshape(h, w))
+    m = (gt > 0) & (seg != 0)
+    return depth_metrics(pred[m], gt[m])
+
+
 def get_embedding(d: Dict[str, torch.Tensor], cfg: dict, *, roi_fn=None, dedup_rays: bool = False
                   ) -> Dict[str, torch.Tensor]:
     """LIDF.get_embedding (pipeline.py:338-425) with resnet_model / pnet_model outputs given.

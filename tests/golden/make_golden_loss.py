@@ -58,6 +58,47 @@ def run(src_name, out_name, seed, zero_frac=0.1, label_frac=0.2):
           "empty rays", int((pred_label == P).sum()))
 
 
+def run_metrics(src_name, out_name, seed):
+    """Depth metrics of compute_loss(..., 'test', epoch) (pipeline.py:570-618): the bs != 1 branch (rays) and, for one-image
+    fixtures, the bs == 1 branch with its cv2.resize(256x144, INTER_NEAREST) host round trip -- reference code, unmodified."""
+    z = np.load(os.path.join(HERE, src_name + ".npz"))
+    opt, lidf, _ = MG.build_reference({})
+    g = torch.Generator().manual_seed(seed)
+    B, H, W = int(z["meta_B"]), int(z["meta_H"]), int(z["meta_W"])
+    ray = torch.from_numpy(z["miss_ray_intersect_idx"]).long()
+    P, R = ray.shape[0], z["miss_ray_dir"].shape[0]
+    pred_pos = torch.from_numpy(z["ref.pred_pos"])
+    gt_pos = pred_pos * (1 + 0.08 * torch.randn(R, 1, generator=g))
+    gt_pos[torch.rand(R, generator=g) < 0.1] = 0.0
+    label = (torch.rand(P, generator=g) < 0.2).long()
+    img_ind = torch.from_numpy(z["miss_img_ind"]).long()
+    depth = 0.4 + 1.5 * torch.rand(B, H * W, generator=g)
+    depth[torch.rand(B, H * W, generator=g) < 0.03] = 0.0                       # holes
+    depth[0, 5] = float("nan"); depth[0, 9] = float("inf")                      # the reference zeroes these (:581-582)
+    xyz_flat = torch.stack((torch.randn(B, H * W, generator=g), torch.randn(B, H * W, generator=g), depth), -1)
+    corrupt = (torch.rand(B, H, W, generator=g) < 0.5).float()
+    xyz_corrupt_flat = xyz_flat * (1 - corrupt).reshape(B, H * W, 1)
+    xyz_corrupt_flat = torch.where(torch.isfinite(xyz_corrupt_flat), xyz_corrupt_flat, torch.zeros_like(xyz_corrupt_flat))
+    dd = dict(bs=B, h=H, w=W, pred_pos=pred_pos, gt_pos=gt_pos, pred_prob_end=torch.from_numpy(z["ref.pred_prob_end"]),
+              pred_prob_end_softmax=torch.from_numpy(z["ref.pred_prob_end_softmax"]), miss_ray_intersect_idx=ray,
+              pcl_label=label, total_miss_sample_num=R, miss_bid=torch.from_numpy(z["miss_bid"]).long(),
+              miss_flat_img_id=img_ind[:, 1] * W + img_ind[:, 0], xyz_flat=xyz_flat, xyz_corrupt_flat=xyz_corrupt_flat,
+              corrupt_mask=corrupt)
+    with torch.no_grad():
+        loss = lidf.compute_loss(dd, "test", 0)                  # reference code, unmodified (cv2 branch when bs == 1)
+    keys = ("a1", "a2", "a3", "rmse", "rmse_log", "log10", "abs_rel", "mae", "sq_rel")
+    out = os.path.join(HERE, out_name + ".npz")
+    np.savez_compressed(out, pred_pos=pred_pos.numpy(), gt_pos=gt_pos.numpy(), xyz_flat=xyz_flat.numpy(),
+                        xyz_corrupt_flat=xyz_corrupt_flat.numpy(), corrupt_mask=corrupt.numpy(),
+                        miss_flat_img_id=dd["miss_flat_img_id"].numpy().astype(np.int32), B=B, H=H, W=W,
+                        **{"ref_" + k: np.float64(float(loss[k])) for k in keys})
+    print(out_name, "bs", B, {k: round(float(loss[k]), 6) for k in keys})
+
+
 if __name__ == "__main__":
+    run_metrics("c1_imnet_64x64x16", "metrics_bs1_64x64", 21)
+    run_metrics("ief_ragged_2x24x32", "metrics_bs2_24x32", 22)
+    if "--metrics-only" in sys.argv:
+        sys.exit(0)
     run("ief_ragged_2x24x32", "loss_ief_ragged_2x24x32", 11)
     run("c1_imnet_64x64x16", "loss_c1_imnet_64x64x16", 12, zero_frac=0.0, label_frac=0.05)

@@ -138,11 +138,31 @@ def test_dense_dist_and_pair_order_invariance(engine, tol):
     assert (out2["max_pair_id"].cpu() == want).float().mean() > 0.99
 
 
-@pytest.mark.parametrize("engine,tol", ENGINES)
-def test_properties_at_scale(engine, tol):
-    """BASELINE config-2 shape per image (320x240, 64 pairs/ray), one image: properties that need no oracle."""
+def test_128_pairs_per_ray_against_oracle():
+    """BASELINE config 5's stage-1 shape per ray: 128 pairs on every ray (two full 128-row tiles of the tcgen05 engine per
+    ray pair, segments longer than a warp in the ray termination), whole problem against the oracle."""
     from implicit_depth_b200.synthetic import make_inputs
-    B, H, W, N = (1, 240, 320, 64) if engine != "simt_fp32" else (1, 120, 160, 64)
+    d = make_inputs(2, 12, 16, 128, V_img=160, seed=128)
+    g = torch.Generator().manual_seed(129)
+    cfg = dict(O.DEFAULT_CFG)
+    off = O.init_decoder("IEF", 385, mode="trained", generator=g)
+    prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
+    ref = O.lidf_query(d, cfg, off, prob, d["part_size"], dedup_rays=True)
+    assert ref["pred_offset"].shape[0] == 2 * 12 * 16 * 128
+    for engine, tol in ENGINES:
+        out = _run(d, cfg, off, prob, d["part_size"], engine)
+        for k in FLOAT_KEYS:
+            assert rel_err(out[k].cpu(), ref[k]) < tol, (engine, k, rel_err(out[k].cpu(), ref[k]))
+        agree = float((out["max_pair_id"].cpu() == ref["max_pair_id"]).float().mean())
+        assert agree > 0.98, (engine, agree)
+
+
+@pytest.mark.parametrize("engine,tol,B", [(e, t, 1) for e, t in ENGINES] + [("auto", TOL_TC, 4)])
+def test_properties_at_scale(engine, tol, B):
+    """BASELINE config-2 shape (320x240 rays per image, 64 pairs/ray), one image and the config's full batch of 4:
+    properties that need no oracle, plus a random slice of rays against the oracle."""
+    from implicit_depth_b200.synthetic import make_inputs
+    B, H, W, N = (B, 240, 320, 64) if engine != "simt_fp32" else (1, 120, 160, 64)
     d = _cuda(make_inputs(B, H, W, N, seed=2024, device="cuda"))
     g = torch.Generator().manual_seed(1)
     off = _cuda(O.init_decoder("IEF", 385, mode="trained", generator=g))
@@ -685,3 +705,57 @@ def test_compute_loss_eval_mirror_vs_reference_loss_dict(name):
         assert abs(float(ev["mae"]) - float((t["gt_pos"][:, 2][keep] - t["pred_pos"][:, 2][keep]).abs().mean())) < 1e-6
     else:
         assert "a1" not in ev
+
+
+@pytest.mark.parametrize("name", ["metrics_bs1_64x64", "metrics_bs2_24x32"])
+def test_depth_metrics_match_reference_compute_loss(name):
+    """lidf_depth_metrics_rays / _image against the reference's own compute_loss(..., 'test', ...) (fixtures from
+    make_golden_loss.py): bs != 1 over rays; bs == 1 incl. the cv2 nearest-neighbour resampling, done on the device."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    t = {k: torch.from_numpy(z[k]).cuda() for k in z.files if z[k].ndim > 0}
+    B, H, W = int(z["B"]), int(z["H"]), int(z["W"])
+    lq = _lq()
+    if B == 1:
+        got = lq.depth_metrics(t["pred_pos"], xyz_flat=t["xyz_flat"], xyz_corrupt_flat=t["xyz_corrupt_flat"],
+                               corrupt_mask=t["corrupt_mask"], miss_flat_img_id=t["miss_flat_img_id"].long(), h=H, w=W)
+    else:
+        got = lq.depth_metrics(t["pred_pos"], t["gt_pos"])
+    for k in ("a1", "a2", "a3", "rmse", "rmse_log", "log10", "abs_rel", "mae", "sq_rel"):
+        assert abs(float(got[k]) - float(z["ref_" + k])) <= 1e-5 * max(1.0, abs(float(z["ref_" + k]))), (k, float(got[k]), float(z["ref_" + k]))
+
+
+def test_weight_cache_and_sparse_ray_path_are_bit_identical():
+    """(1) The packed-weight cache: a second call with unchanged decoders skips the packing launches and returns the same
+    bits; an in-place weight update (what an optimizer step does) is noticed through the tensor version counter.
+    (2) Sparse regime (< 8 pairs per ray, no ROI output requested): ROIAlign / row prep only for rays that own a pair --
+    same bits as the dense path that computes every ray."""
+    from implicit_depth_b200.synthetic import make_inputs
+    lq = _lq()
+    d = _cuda(make_inputs(2, 24, 32, 5, V_img=24, seed=77, ragged=True))          # ragged: ~1/6 of the rays have no pair
+    g = torch.Generator().manual_seed(78)
+    off = _cuda(O.init_decoder("IEF", 385, mode="trained", generator=g))
+    prob = _cuda(O.init_decoder("IMNET", 385, mode="trained", generator=g))
+    ins = [d[k] for k in lq.INPUT_KEYS]
+    kw = dict(part_size=d["part_size"])
+    lq.launch_count(reset=True)
+    a = lq.forward(*ins, off, prob, want_roi_feat=True, **kw)                    # dense per-ray path (ROI output requested)
+    n_first = lq.launch_count(reset=True)
+    b = lq.forward(*ins, off, prob, want_roi_feat=True, **kw)
+    n_cached = lq.launch_count(reset=True)
+    assert n_cached <= n_first - 15, (n_first, n_cached)                          # the ~20 packing launches are gone
+    c = lq.forward(*ins, off, prob, **kw)                                         # sparse path
+    for k in lq.OUTPUT_KEYS:
+        assert torch.equal(a[k], b[k]) and torch.equal(a[k], c[k]), k
+    off["linear_2.weight"].mul_(1.5)                                              # in-place update -> version bump -> re-pack
+    e = lq.forward(*ins, off, prob, **kw)
+    assert not torch.equal(e["pred_offset"], a["pred_offset"])
+    lq.use_weight_cache = False
+    try:
+        f = lq.forward(*ins, off, prob, **kw)
+    finally:
+        lq.use_weight_cache = True
+    for k in lq.OUTPUT_KEYS:
+        assert torch.equal(e[k], f[k]), k

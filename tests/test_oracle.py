@@ -203,3 +203,31 @@ def test_factored_layer1_backward_algebra():
     assert torch.allclose(dW1, W1.grad, rtol=1e-10, atol=1e-10)
     assert torch.allclose(Gv @ W1.detach()[:, :128], vf.grad, rtol=1e-10, atol=1e-10)
     assert torch.allclose(Gr @ W1.detach()[:, 128:256], roi.grad, rtol=1e-10, atol=1e-10)
+
+
+@pytest.mark.parametrize("name", ["metrics_bs1_64x64", "metrics_bs2_24x32"])
+def test_depth_metrics_oracle_matches_reference_compute_loss(name):
+    """The nine depth metrics of compute_loss(..., 'test', ...) (pipeline.py:570-618), both batch-size branches, against
+    fixtures produced by the reference's unmodified code (make_golden_loss.py: run_metrics) -- incl. the bs == 1 branch's
+    cv2.resize(INTER_NEAREST) round trip, restated as an index pick."""
+    import os
+    import numpy as np
+    from conftest import GOLDEN_DIR
+    z = np.load(os.path.join(GOLDEN_DIR, name + ".npz"))
+    t = {k: torch.from_numpy(z[k]) for k in z.files if z[k].ndim > 0}
+    B, H, W = int(z["B"]), int(z["H"]), int(z["W"])
+    if B == 1:
+        got = O.depth_metrics_image(t["xyz_flat"], t["xyz_corrupt_flat"], t["corrupt_mask"], t["miss_flat_img_id"].long(), t["pred_pos"], H, W)
+    else:
+        got = O.depth_metrics_rays(t["pred_pos"], t["gt_pos"])
+    for k in ("a1", "a2", "a3", "rmse", "rmse_log", "log10", "abs_rel", "mae", "sq_rel"):
+        assert abs(float(got[k]) - float(z["ref_" + k])) <= 2e-6 * max(1.0, abs(float(z["ref_" + k]))), k
+
+
+def test_resize_nearest_restatement_matches_cv2():
+    cv2 = pytest.importorskip("cv2")
+    g = torch.Generator().manual_seed(4)
+    for H, W in ((64, 64), (240, 320), (97, 131), (480, 640)):
+        img = torch.rand(H, W, generator=g)
+        want = cv2.resize(img.numpy(), (256, 144), interpolation=cv2.INTER_NEAREST)
+        assert torch.equal(O.resize_nearest(img), torch.from_numpy(want)), (H, W)
