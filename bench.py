@@ -195,6 +195,9 @@ def main():
     ap.add_argument("--no-torch-gpu-baseline", action="store_true",
                     help="skip timing the stock torch op chain on the same GPU (north_star's '>= 10x the reference PyTorch "
                          "decoder' target; N = 1 only, bounded sample of >= 2^20 points)")
+    ap.add_argument("--cuda-graph", action="store_true",
+                    help="time the device-resident step as a CUDA-graph replay (lidf_query.make_graphed_forward): for the "
+                         "launch-bound small configs (c1)")
     ap.add_argument("--train", action="store_true",
                     help="BASELINE config 4's training step on this rank's images: fused forward + lidf_query_backward + "
                          "NCCL all-reduce of the decoder gradients (DDP's exchange), synthetic upstream gradients")
@@ -235,9 +238,13 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    def step():
-        return lidf_query.forward(*ins, off, prob, **kw)
+    graphed = lidf_query.make_graphed_forward(*ins, off, prob, **kw) if args.cuda_graph else None
 
+    def step():
+        return graphed() if graphed is not None else lidf_query.forward(*ins, off, prob, **kw)
+
+    in_bytes = sum(t.numel() * t.element_size() for t in ins)
+    flush_buf = torch.empty(192 << 20, dtype=torch.uint8, device=dev) if in_bytes <= 126e6 else None
     progress(f"inputs ready: P={P} R={R}")
     for _ in range(max(3, args.warmup)):
         out = step()
@@ -251,19 +258,33 @@ def main():
     lidf_query.launch_count(reset=True)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     mlp_ms = []
-    e0.record()
-    for _ in range(args.steps):
-        out = step()
-        del out
-    e1.record()
-    barrier()
+    if flush_buf is None:
+        e0.record()
+        for _ in range(args.steps):
+            out = step()
+            del out
+        e1.record()
+        barrier()
+        total_ms = e0.elapsed_time(e1)
+    else:                                            # small workload: flush L2 between the timed iterations, time each step alone
+        total_ms = 0.0
+        for _ in range(args.steps):
+            flush_buf.fill_(1)
+            e0.record()
+            out = step()
+            e1.record()
+            del out
+            torch.cuda.synchronize()
+            total_ms += e0.elapsed_time(e1)
+        barrier()
     launches = lidf_query.launch_count()
-    total_ms = e0.elapsed_time(e1)
     # decoder-kernel time: CUDA events recorded by the library around that launch, on the launching stream
     for _ in range(min(3, args.steps)):
         step()
         mlp_ms.append(lidf_query.last_mlp_ms())
     torch.cuda.synchronize()
+    if args.cuda_graph:                              # the library's event pair is not usable inside a captured graph
+        mlp_ms = [total_ms / args.steps]
     clocks = sampler.stop() if rank == 0 else None
     t = torch.tensor([total_ms], device=dev)
     if world > 1:
@@ -354,7 +375,8 @@ def main():
                 data="synthetic",
                 config=dict(workload=f"{args.workload}: {B} images/GPU of {H}x{W} rays x {N} pairs/ray = {P} points/GPU, "
                                      f"decoders {args.offdec}(n_iter 2)+IMNET, trained-like random weights",
-                            engine=args.engine, l2="inputs (>3 GB/step) exceed the 126 MB L2; no explicit flush",
+                            engine=args.engine, cuda_graph=bool(args.cuda_graph), l2=("inputs (>3 GB/step) exceed the 126 MB L2; no explicit flush" if in_bytes > 126e6 else
+                                f"inputs ({in_bytes / 1e6:.1f} MB) fit in the 126 MB L2: a 192 MB buffer is written between steps to flush it"),
                             pair_order="reference voxel-major (regroup inside the timed region)"),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
     progress("cpu baseline done")

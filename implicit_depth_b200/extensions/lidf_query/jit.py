@@ -527,7 +527,10 @@ class _LidfQuery:
     def _attach_weight_cache(self, p: _QueryParams, keep: list, dev) -> None:
         """Packed decoder weights persist across calls in a device buffer owned by this wrapper (one per device, stream
         and engine).  They are re-packed only when a decoder tensor was replaced or modified in place (``data_ptr`` /
-        ``_version`` of every tensor -- an optimizer step bumps the version) or a setting that enters the packing changed."""
+        ``_version`` of every tensor -- optimizer steps, ``load_state_dict`` and ``nn.init`` all bump the version) or a
+        setting that enters the packing changed.  The cache entry keeps the decoder tensors alive, so an address can not be
+        recycled by a different tensor while it is cached.  In-place writes through ``param.data`` bypass the version
+        counter: call ``invalidate_weight_cache()`` after those (or set ``use_weight_cache = False``)."""
         if not self.use_weight_cache:
             return
         stream = torch.cuda.current_stream(dev).cuda_stream
@@ -539,12 +542,15 @@ class _LidfQuery:
         if nbytes == 0:
             return
         caches = self.__dict__.setdefault("_wcaches", {})
-        buf, old_key = caches.get(slot, (None, None))
+        buf, old_key, _alive = caches.get(slot, (None, None, None))
         if buf is None or buf.numel() < nbytes:
             buf, old_key = torch.empty(nbytes, dtype=torch.uint8, device=dev), None
         p.weight_cache, p.weight_cache_bytes = buf.data_ptr(), buf.numel()
         p.weight_cache_valid = int(old_key == key)
-        caches[slot] = (buf, key)
+        caches[slot] = (buf, key, list(keep))            # strong refs: the storages behind `key` stay allocated
+
+    def invalidate_weight_cache(self) -> None:
+        self.__dict__.pop("_wcaches", None)
 
     def check_index_errors(self, wait: bool = True) -> None:
         """Raise if an earlier ``forward`` saw an out-of-range pair_ray / pair_vox / miss_bid value.  The kernels clamp
@@ -575,7 +581,9 @@ class _LidfQuery:
         the reference's dense [V,R,2] tensor.  Returns the data_dict entries of pipeline.py:460-466 (+ pred_offset).
         ``save_for_backward`` adds ``ief_iter`` (the IEF offsets between iterations, which ``backward`` needs);
         ``check_indices`` waits for the call and raises on an out-of-range index (otherwise the next call reports it)."""
-        self.check_index_errors(wait=False)
+        capturing = torch.cuda.is_current_stream_capturing() if full_rgb_feat.is_cuda else False
+        if not capturing:
+            self.check_index_errors(wait=False)
         dev = full_rgb_feat.device
         keep: list = []
         p = self._query_params(full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
@@ -610,6 +618,9 @@ class _LidfQuery:
             cur = torch.cuda.current_stream(dev)
             rc = self.lib.lidf_query_forward(C.byref(p), C.c_void_p(cur.cuda_stream))
             self._raise(rc, "lidf_query_forward")
+            if capturing:                       # inside a CUDA graph: no host-side bookkeeping; the flag stays on the device
+                out["index_error"] = flag
+                return out
             flag_host = torch.empty(1, dtype=torch.int32, pin_memory=True)
             flag_host.copy_(flag, non_blocking=True)
             ev = torch.cuda.Event(); ev.record(cur)
@@ -620,6 +631,39 @@ class _LidfQuery:
         if check_indices:
             self.check_index_errors(wait=True)
         return out
+
+    def make_graphed_forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                             occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, **kw):
+        """Inference with fixed shapes (same image size, same pair count -- e.g. BASELINE config 1, or a serving loop over
+        equally sized batches): the whole ``forward`` -- ~15 launches, 0.3 ms of Python / launch latency for 0.07 ms of
+        kernels at config 1 -- is captured once into a CUDA graph and replayed with one launch.  Returns
+        ``run(*nine_input_tensors) -> out`` (pass nothing to re-run on the static buffers, ``run.inputs``); the outputs are
+        the graph's static tensors, overwritten by the next replay.  The decoder tensors are read (and re-packed) by
+        every replay, so in-place weight updates are picked up; replacing a decoder tensor needs a new graph."""
+        dev = full_rgb_feat.device
+        static = [t.clone() for t in (full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
+                                      occ_vox_intersect_idx, miss_ray_intersect_idx, dist)]
+        kw.pop("check_indices", None)
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):                                          # warm-up outside the capture (function attributes, allocator)
+                self.forward(*static, offset_dec, prob_dec, **kw)
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        self.check_index_errors(wait=True)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            out = self.forward(*static, offset_dec, prob_dec, **kw)
+
+        def run(*new_inputs):
+            for dst, src in zip(static, new_inputs):
+                if src is not dst:
+                    dst.copy_(src, non_blocking=True)
+            graph.replay()
+            return out
+        run.inputs, run.graph = static, graph
+        return run
 
     def backward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
                  occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, fwd_out, *,
