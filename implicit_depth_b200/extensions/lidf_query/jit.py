@@ -638,8 +638,10 @@ class _LidfQuery:
         equally sized batches): the whole ``forward`` -- ~15 launches, 0.3 ms of Python / launch latency for 0.07 ms of
         kernels at config 1 -- is captured once into a CUDA graph and replayed with one launch.  Returns
         ``run(*nine_input_tensors) -> out`` (pass nothing to re-run on the static buffers, ``run.inputs``); the outputs are
-        the graph's static tensors, overwritten by the next replay.  The decoder tensors are read (and re-packed) by
-        every replay, so in-place weight updates are picked up; replacing a decoder tensor needs a new graph."""
+        the graph's static tensors, overwritten by the next replay.  The packed decoder weights are taken from the weight
+        cache (filled by the warm-up on the capture stream), so the graph holds no packing kernels; after an in-place
+        update of a decoder tensor call ``run.repack()`` (one eager call that re-packs into the same buffer), after
+        replacing a tensor build a new graph."""
         dev = full_rgb_feat.device
         static = [t.clone() for t in (full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
                                       occ_vox_intersect_idx, miss_ray_intersect_idx, dist)]
@@ -653,7 +655,7 @@ class _LidfQuery:
         torch.cuda.synchronize(dev)
         self.check_index_errors(wait=True)
         graph = torch.cuda.CUDAGraph()
-        with torch.cuda.graph(graph):
+        with torch.cuda.graph(graph, stream=side):                      # same stream as the warm-up: its weight cache is valid
             out = self.forward(*static, offset_dec, prob_dec, **kw)
 
         def run(*new_inputs):
@@ -662,7 +664,13 @@ class _LidfQuery:
                     dst.copy_(src, non_blocking=True)
             graph.replay()
             return out
-        run.inputs, run.graph = static, graph
+
+        def repack():
+            side.wait_stream(torch.cuda.current_stream(dev))
+            with torch.cuda.stream(side):
+                self.forward(*static, offset_dec, prob_dec, **kw)
+            torch.cuda.current_stream(dev).wait_stream(side)
+        run.inputs, run.graph, run.repack = static, graph, repack
         return run
 
     def backward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,

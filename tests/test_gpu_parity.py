@@ -767,7 +767,7 @@ def test_weight_cache_and_sparse_ray_path_are_bit_identical():
 
 def test_graphed_forward_replays_bit_identically_and_follows_weight_updates():
     """CUDA-graph replay of the whole forward (launch-bound small batches): same bits as the eager call, new inputs are
-    picked up through the static buffers, in-place decoder updates through the re-pack inside the graph."""
+    picked up through the static buffers, in-place decoder updates after run.repack()."""
     from implicit_depth_b200.synthetic import make_inputs
     lq = _lq()
     d = _cuda(make_inputs(1, 64, 64, 16, V_img=64, seed=5))
@@ -788,6 +788,7 @@ def test_graphed_forward_replays_bit_identically_and_follows_weight_updates():
     assert int(got2["index_error"]) == 0
     off["linear_3.bias"].add_(0.25)
     want3 = lq.forward(*ins2, off, prob, **kw)
+    run.repack()
     got3 = run()
     torch.cuda.synchronize()
     assert torch.equal(got3["pred_offset"], want3["pred_offset"]) and not torch.equal(want3["pred_offset"], want2["pred_offset"])
