@@ -45,8 +45,15 @@ WORKLOADS = {          # name: (B per GPU, H, W, N)   -- BASELINE.json configs
 FLOP_IMNET = 279168            # 2*MAC of the reference Linear stack, per query point
 FLOP_IEF2 = 574784
 FLOP_PER_POINT = {"IEF": FLOP_IEF2 + FLOP_IMNET, "IMNET": 2 * FLOP_IMNET}
-# dram__bytes_read.sum + dram__bytes_write.sum of ONE k_mlp_tc launch at c3 (profiles/r1j_k_mlp_tc.md, ncu --set full)
-NCU_DRAM_BYTES_PER_LAUNCH = {"c3": 9.540175e9 + 3.162020e9, "c2": 1.190496e9 + 0.378852e9}
+def ncu_traffic(workload):
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE k_mlp_tc launch, from the latest committed ncu capture
+    (profiles/traffic.json, written when a capture is summarised; names the capture it came from)."""
+    try:
+        with open(os.path.join(REPO, "profiles", "traffic.json")) as f:
+            t = json.load(f).get(workload)
+        return (float(t["bytes"]), t["source"]) if t else (None, None)
+    except Exception:
+        return None, None
 ALGO_BYTES_PER_POINT = 80      # decoder kernel: perm 4 + pair_vox 8 + pair_ray 8 + dist 8 + T row share 32 read; 4 + 4 + 12 written
 EXEC_MAC_TC = 626688           # DESIGN.md: bf16 MACs the tcgen05 engine executes per point: 3 passes x (112*256 + 256*128 + 128*64) x 3 products
 
@@ -356,9 +363,9 @@ def main():
     flop_pt = FLOP_PER_POINT[args.offdec]
     achieved = P * flop_pt / (k_ms * 1e-3) / 1e12
     peak = peaks["bf16_tflops_sustained"]           # the kernel is ~the whole of a long step -> sustained figure
-    traffic = NCU_DRAM_BYTES_PER_LAUNCH.get(args.workload) if (args.engine != "simt_fp32" and args.offdec == "IEF") else None
+    traffic, traffic_src = ncu_traffic(args.workload) if (args.engine != "simt_fp32" and args.offdec == "IEF") else (None, None)
     roofline = dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=traffic,
-                    traffic_source="ncu dram__bytes_read.sum + dram__bytes_write.sum, one launch, profiles/r1j_k_mlp_tc.md (c3) / r1g (c2)",
+                    traffic_source=traffic_src,
                     algorithmic_bytes_per_launch=P * ALGO_BYTES_PER_POINT,
                     kernel="k_mlp_simt" if args.engine == "simt_fp32" else "k_mlp_tc", kernel_ms=k_ms,
                     kernel_share_of_step=k_ms / ms_per_step, flop_per_point_nominal=flop_pt,

@@ -411,7 +411,11 @@ __device__ __forceinline__ bool vox_locate(const float* __restrict__ xyz, int64_
 #pragma unroll
   for (int k = 0; k < 3; ++k) {
     v[k] = __fsub_rn(xyz[i * 3 + k], g.xmin[k]);                       // point_utils.py:23
-    const float q = floorf(__fdiv_rn(v[k], g.crop));                   // :43
+    // :43.  True IEEE division = what the reference computes on the CPU (where the voxel goldens were made).  torch's CUDA
+    // kernel for `tensor / python_scalar` multiplies by the reciprocal instead; for the shipped grid.res = 8 (crop 0.25, a power
+    // of two) both are exact and agree; for a non-power-of-two crop a point within 1 ulp of a cell face may land in the
+    // neighbouring cell under the GPU reference -- parity here is defined against exact division.
+    const float q = floorf(__fdiv_rn(v[k], g.crop));
     ok = ok && q >= 0.f && q < (float)g.n[k];                          // :59-61 (also rejects NaN)
     c[k] = ok ? (int)q : 0;
   }

@@ -1,5 +1,7 @@
 // lidf_prep.cuh -- pair regroup (voxel-major -> ray-major CSR), ROIAlign per ray, ray termination.
 #pragma once
+#include <cuda.h>          // CUtensorMap (types only: cuTensorMapEncodeTiled is fetched through cudaGetDriverEntryPoint)
+
 #include "lidf_common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -362,6 +364,62 @@ __global__ void k_box4(const float* __restrict__ feat, int64_t n, int H, int W, 
 #pragma unroll
     for (int ix = 0; ix < 4; ++ix) acc += __ldg(f + (size_t)iy * W + ix);
   box[idx] = acc;
+}
+
+// The same box sums with the feature tiles staged by TMA: the map is a 3-D tensor (W, H, B * 32 planes); one CTA owns a
+// 64 x 32 output tile of one plane, one elected thread issues ONE cp.async.bulk.tensor (SASS: UTMALDG) for the 68 x 35
+// input tile (out-of-range elements arrive as zeros and belong to outputs that are never written), the completion is
+// counted on an mbarrier, and all 256 threads then read their 16 taps from shared memory in exactly the order of k_box4
+// (iy outer, ix inner, sequential adds) -> bit-identical.  Needs W % 4 == 0 (global strides of a tensor map are multiples
+// of 16 bytes); other widths take k_box4.
+#define BOX_TW 64
+#define BOX_TH 32
+#define BOX_SW 68                    // 64 + 3 halo, padded to a multiple of 4 floats (TMA inner box = 272 bytes)
+#define BOX_SH 35
+__global__ void __launch_bounds__(256) k_box4_tma(const __grid_constant__ CUtensorMap tmap, int H, int W, float* __restrict__ box) {
+  __shared__ __align__(128) float s_tile[BOX_SH][BOX_SW];
+  __shared__ __align__(8) uint64_t s_bar;
+  const int x0 = blockIdx.x * BOX_TW, y0 = blockIdx.y * BOX_TH, plane = blockIdx.z;
+  const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_bar), dst = (uint32_t)__cvta_generic_to_shared(&s_tile[0][0]);
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(bar));
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"((uint32_t)(BOX_SW * BOX_SH * 4)) : "memory");
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3, %4}], [%5];"
+        ::"r"(dst), "l"(reinterpret_cast<uint64_t>(&tmap)), "r"(x0), "r"(y0), "r"(plane), "r"(bar)
+        : "memory");
+  }
+  {
+    uint32_t ok = 0, spins = 0;
+    while (!ok) {
+      asm volatile(
+          "{\n\t.reg .pred p;\n\t"
+          "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+          "selp.b32 %0, 1, 0, p;\n\t}"
+          : "=r"(ok)
+          : "r"(bar), "r"(0u)
+          : "memory");
+      if (!ok && ++spins > (1u << 24)) __trap();
+    }
+  }
+  const int tx = threadIdx.x & 63, ty0 = threadIdx.x >> 6;               // 64 columns x 4 row phases
+  const int x = x0 + tx;
+  float* bp = box + (size_t)plane * H * W;
+#pragma unroll 2
+  for (int ty = ty0; ty < BOX_TH; ty += 4) {
+    const int y = y0 + ty;
+    if (x > W - 4 || y > H - 4) continue;
+    float acc = 0.f;
+#pragma unroll
+    for (int iy = 0; iy < 4; ++iy)
+#pragma unroll
+      for (int ix = 0; ix < 4; ++ix) acc += s_tile[ty + iy][tx + ix];
+    bp[(size_t)y * W + x] = acc;
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

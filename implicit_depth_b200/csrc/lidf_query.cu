@@ -21,12 +21,20 @@
 
 static thread_local char g_cuda_err[256] = "";
 static thread_local int64_t g_launches = 0;
-static thread_local cudaEvent_t g_ev_mlp[2] = {nullptr, nullptr};
+// timing events of the decoder kernel: one pair per device ordinal (an event belongs to the device it was created on)
+#define LIDF_MAX_DEVICES 64
+static thread_local cudaEvent_t g_ev_mlp_dev[LIDF_MAX_DEVICES][2] = {};
+static thread_local cudaEvent_t* g_ev_mlp = g_ev_mlp_dev[0];
 static thread_local bool g_ev_valid = false;
 
 static void mlp_event(int which, cudaStream_t st) {
-  if (!g_ev_mlp[0]) { cudaEventCreate(&g_ev_mlp[0]); cudaEventCreate(&g_ev_mlp[1]); }
-  cudaEventRecord(g_ev_mlp[which], st);
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= LIDF_MAX_DEVICES) { cudaGetLastError(); return; }
+  g_ev_mlp = g_ev_mlp_dev[dev];
+  if (!g_ev_mlp[0] && (cudaEventCreate(&g_ev_mlp[0]) != cudaSuccess || cudaEventCreate(&g_ev_mlp[1]) != cudaSuccess)) {
+    cudaGetLastError(); g_ev_mlp[0] = g_ev_mlp[1] = nullptr; return;
+  }
+  if (cudaEventRecord(g_ev_mlp[which], st) != cudaSuccess) { cudaGetLastError(); g_ev_valid = false; return; }   // e.g. inside a graph capture
   if (which == 1) g_ev_valid = true;
 }
 
@@ -202,11 +210,45 @@ extern "C" int lidf_roi_align_rays(const float* feat, int32_t B, int32_t H, int3
 }
 
 namespace {
+// 3-D tensor map (W, H, B * 32) over full_rgb_feat [B,32,H,W] fp32 for k_box4_tma.  cuTensorMapEncodeTiled is a driver entry
+// point; it is looked up through the runtime so that the library keeps linking against libcudart only.
+bool make_feat_tensor_map(CUtensorMap* tmap, const float* feat, int B, int H, int W) {
+  typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                               const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                               CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  static thread_local EncodeFn encode = nullptr;
+  static thread_local bool looked_up = false;
+  if (!looked_up) {
+    looked_up = true;
+    void* fn = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      encode = reinterpret_cast<EncodeFn>(fn);
+    else
+      cudaGetLastError();
+  }
+  if (!encode || ((uintptr_t)feat & 15) != 0) return false;
+  const cuuint64_t dims[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B * LIDF_RGB_CH};
+  const cuuint64_t strides[2] = {(cuuint64_t)W * 4, (cuuint64_t)W * H * 4};          // bytes, dims 1 and 2
+  const cuuint32_t box[3] = {BOX_SW, BOX_SH, 1};
+  const cuuint32_t estr[3] = {1, 1, 1};
+  return encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(feat), dims, strides, box, estr,
+                CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
 // ROIAlign per ray through the 4x4 box-sum map (dense ray sets: the map costs a quarter of a ray per pixel)
 int roi_align_rays_box(const float* feat, float* box, int* border_list, int* border_count, int B, int H, int W,
                        const int64_t* img_ind, const int64_t* bid, int64_t R, int roi_inp_bbox, float* out, cudaStream_t st) {
   const int64_t n = (int64_t)B * LIDF_RGB_CH * H * W;
-  k_box4<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feat, n, H, W, box);
+  CUtensorMap tmap;
+  if (W % 4 == 0 && (int64_t)B * LIDF_RGB_CH <= 65535 && make_feat_tensor_map(&tmap, feat, B, H, W)) {
+    // feature tiles staged by TMA (cp.async.bulk.tensor, one 68 x 35 tile per CTA)
+    k_box4_tma<<<dim3((W + BOX_TW - 1) / BOX_TW, (H + BOX_TH - 1) / BOX_TH, B * LIDF_RGB_CH), 256, 0, st>>>(tmap, H, W, box);
+  } else {
+    k_box4<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(feat, n, H, W, box);
+  }
   LIDF_LAUNCH_CHECK();
   LIDF_CUDA(cudaMemsetAsync(border_count, 0, sizeof(int), st));
   k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, st>>>(feat, box, B, H, W, img_ind, bid, R,
@@ -1072,12 +1114,9 @@ int plan_aabb(int64_t R, int64_t V, AabbPlan* q, char* base) {
 }
 
 int persistent_blocks(int64_t items, int per_sm) {
-  static thread_local int sms = 0;
-  if (!sms) {
-    int dev = 0;
-    if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
-      sms = 148;
-  }
+  int dev = 0, sms = 0;                                      // per call: the current device may differ between calls
+  if (cudaGetDevice(&dev) != cudaSuccess || cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || sms <= 0)
+    sms = 148;
   const int64_t g = (int64_t)sms * per_sm;                   // a multiple of the SM count (148 on B200)
   return (int)(items < g ? (items > 0 ? items : 1) : g);
 }

@@ -375,7 +375,11 @@ class RefineDecoderMixin:
         final_pnet_inp = torch.cat((pnet_inp, new_pred_inp), 0)                                     # :1008-1010
         final_revidx = torch.cat((data_dict['revidx'], new_end_voxel_id), 0)
         occ_voxel_feat = self.pnet_model(inp_feat=final_pnet_inp, vox2point_idx=final_revidx)       # :1011-1014
-        return self.refine_decoder_tail(data_dict, pred_pos, end_voxel_id, occ_voxel_feat, data_dict['roi_feat_per_ray'])
+        roi = data_dict.get('roi_feat_per_ray')
+        if roi is None:     # stage 1 ran on the stock reference LIDF (no cached per-ray feature): recompute it, pipeline.py:952-970
+            roi = lidf_query.roi_align_rays(data_dict['full_rgb_feat'].float().contiguous(), data_dict['miss_img_ind'].long().contiguous(),
+                                            data_dict['miss_bid'].long().contiguous(), int(self.opt.model.roi_inp_bbox))
+        return self.refine_decoder_tail(data_dict, pred_pos, end_voxel_id, occ_voxel_feat, roi)
 
 
 class RefineNet(RefineDecoderMixin, nn.Module):
