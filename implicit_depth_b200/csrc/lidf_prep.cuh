@@ -14,12 +14,16 @@
 // bounds) and reported through *err; every kernel that reads pair_ray / pair_vox / miss_bid again clamps the same way.
 __device__ __forceinline__ int64_t lidf_clamp_idx(int64_t v, int64_t n) { return v < 0 ? 0 : (v >= n ? n - 1 : v); }
 __global__ void k_count_pairs(const int64_t* __restrict__ pair_ray, int64_t P, int64_t R, int* __restrict__ cnt,
-                              int* __restrict__ err) {
+                              int* __restrict__ err, const int64_t* __restrict__ pair_vox = nullptr, int64_t V = 0) {
   int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   int64_t r = pair_ray[i];
   if (r < 0 || r >= R) { atomicOr(err, 1); r = lidf_clamp_idx(r, R); }
   atomicAdd(cnt + r, 1);
+  if (pair_vox) {                                   // range check of the voxel index in the same pass over the pair list
+    const int64_t v = pair_vox[i];
+    if (v < 0 || v >= V) atomicOr(err, 2);
+  }
 }
 // range check of the other index arrays the kernels dereference (pair_vox over P, miss_bid over R)
 __global__ void k_validate_indices(const int64_t* __restrict__ pair_vox, int64_t P, int64_t V, const int64_t* __restrict__ bid,

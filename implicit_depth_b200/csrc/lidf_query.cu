@@ -85,11 +85,12 @@ CsrBufs carve_csr(Bump& b, int64_t P, int64_t R) {
   return c;
 }
 
-int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, cudaStream_t st, bool sort_segments = true) {
+int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, cudaStream_t st, bool sort_segments = true,
+              const int64_t* check_vox = nullptr, int64_t V = 0) {
   const int64_t n = R + 1;
   LIDF_CUDA(cudaMemsetAsync(c.cnt, 0, sizeof(int) * (n + 1), st));
   if (P > 0) {
-    k_count_pairs<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.cnt, c.cnt + n);
+    k_count_pairs<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.cnt, c.cnt + n, check_vox, V);
     LIDF_LAUNCH_CHECK();
   }
   k_scan_partial<<<c.nb, LIDF_SCAN_BLOCK, 0, st>>>(c.cnt, n, c.ray_start, c.block_sums);
@@ -494,10 +495,9 @@ int run_prep(const LidfQueryParams* p, QueryPlan& q, cudaStream_t st) {
   int rc;
   const int64_t P = p->P, R = p->R, V = p->V;
   // 1. regroup (flags out-of-range pair_ray in csr.cnt[R + 1]); range check of pair_vox / miss_bid into the same flag
-  if ((rc = build_csr(q.csr, p->pair_ray, P, R, st))) return rc;
-  {
-    const int64_t n = P > R ? P : R;
-    k_validate_indices<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(p->pair_vox, P, V, p->miss_bid, R, p->B, q.csr.cnt + (R + 1));
+  if ((rc = build_csr(q.csr, p->pair_ray, P, R, st, true, p->pair_vox, V))) return rc;
+  if (R > 0) {
+    k_validate_indices<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(nullptr, 0, V, p->miss_bid, R, p->B, q.csr.cnt + (R + 1));
     LIDF_LAUNCH_CHECK();
   }
   // 2. ROIAlign per ray

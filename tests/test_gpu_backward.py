@@ -302,3 +302,40 @@ def test_forward_reports_out_of_range_indices_without_faulting():
         torch.cuda.synchronize()
     ins = _to_dev(d, lidf_query.INPUT_KEYS)
     lidf_query.forward(*ins, off, prob, part_size=d["part_size"], check_indices=True)      # clean inputs: no report
+
+
+def test_backward_is_linear_in_the_upstream_gradient_at_config2_image_size():
+    """Size-independent property at a BASELINE-size image (320x240 rays x 64 pairs = 4.9 M points, three chunks): the
+    backward is linear in the upstream gradients, and scaling by a power of two is exact in floating point -- every
+    deterministic output of backward(2 g) is bit-for-bit 2 x backward(g).  (linear_1.weight's voxel columns and
+    occ_voxel_feat go through float atomics: compared to 1e-5.)  Also: d(bias of linear_4) = sum of the seeds."""
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    from implicit_depth_b200.synthetic import make_inputs
+    from oracle import lidf_oracle as O
+    d = make_inputs(1, 240, 320, 64, seed=11, device="cuda")
+    g = torch.Generator().manual_seed(12)
+    off = {k: v.cuda() for k, v in O.init_decoder("IEF", 385, mode="trained", generator=g).items()}
+    prob = {k: v.cuda() for k, v in O.init_decoder("IMNET", 385, mode="trained", generator=g).items()}
+    ins = [d[k] for k in lidf_query.INPUT_KEYS]
+    kw = dict(part_size=d["part_size"])
+    P, R = ins[6].shape[0], ins[2].shape[0]
+    out = lidf_query.forward(*ins, off, prob, save_for_backward=True, **kw)
+    gp = torch.randn(R, 3, generator=g).cuda() / R
+    gq = torch.randn(P, 1, generator=g).cuda() / P
+    a = lidf_query.backward(*ins, off, prob, out, g_pred_pos=gp, g_pred_prob_end=gq, **kw)
+    b = lidf_query.backward(*ins, off, prob, out, g_pred_pos=2 * gp, g_pred_prob_end=2 * gq, **kw)
+    torch.cuda.synchronize()
+    for mod in ("offset_dec", "prob_dec"):
+        for k in a[mod]:
+            assert torch.isfinite(a[mod][k]).all(), (mod, k)
+            if k == "linear_1.weight":
+                assert torch.equal(2 * a[mod][k][:, 128:], b[mod][k][:, 128:]), (mod, k)
+                assert rel_err(b[mod][k][:, :128].cpu(), 2 * a[mod][k][:, :128].cpu()) < 1e-5
+            else:
+                assert torch.equal(2 * a[mod][k], b[mod][k]), (mod, k)
+    assert rel_err(b["occ_voxel_feat"].cpu(), 2 * a["occ_voxel_feat"].cpu()) < 1e-5
+    assert rel_err(b["full_rgb_feat"].cpu(), 2 * a["full_rgb_feat"].cpu()) < 1e-5
+    # d b4 of prob_dec = sum over pairs of g * act'(y): leaky clamp -> 1 inside (0, 1), 0.01 outside
+    y = out["pred_prob_end"]
+    seed = gq * torch.where((y > 0) & (y < 1), torch.ones_like(y), torch.full_like(y, 0.01))
+    assert abs(float(a["prob_dec"]["linear_4.bias"]) - float(seed.double().sum())) < 1e-4 * float(seed.double().abs().sum())
