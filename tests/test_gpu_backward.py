@@ -308,7 +308,7 @@ def test_backward_is_linear_in_the_upstream_gradient_at_config2_image_size():
     """Size-independent property at a BASELINE-size image (320x240 rays x 64 pairs = 4.9 M points, three chunks): the
     backward is linear in the upstream gradients, and scaling by a power of two is exact in floating point -- every
     deterministic output of backward(2 g) is bit-for-bit 2 x backward(g).  (linear_1.weight's voxel columns and
-    occ_voxel_feat go through float atomics: compared to 1e-5.)  Also: d(bias of linear_4) = sum of the seeds."""
+    occ_voxel_feat go through float atomics over millions of terms: compared to 2e-4.)  Also: d(bias of linear_4) = sum of the seeds."""
     from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
     from implicit_depth_b200.synthetic import make_inputs
     from oracle import lidf_oracle as O
@@ -330,11 +330,11 @@ def test_backward_is_linear_in_the_upstream_gradient_at_config2_image_size():
             assert torch.isfinite(a[mod][k]).all(), (mod, k)
             if k == "linear_1.weight":
                 assert torch.equal(2 * a[mod][k][:, 128:], b[mod][k][:, 128:]), (mod, k)
-                assert rel_err(b[mod][k][:, :128].cpu(), 2 * a[mod][k][:, :128].cpu()) < 1e-5
+                assert rel_err(b[mod][k][:, :128].cpu(), 2 * a[mod][k][:, :128].cpu()) < 2e-4
             else:
                 assert torch.equal(2 * a[mod][k], b[mod][k]), (mod, k)
-    assert rel_err(b["occ_voxel_feat"].cpu(), 2 * a["occ_voxel_feat"].cpu()) < 1e-5
-    assert rel_err(b["full_rgb_feat"].cpu(), 2 * a["full_rgb_feat"].cpu()) < 1e-5
+    assert rel_err(b["occ_voxel_feat"].cpu(), 2 * a["occ_voxel_feat"].cpu()) < 2e-4
+    assert rel_err(b["full_rgb_feat"].cpu(), 2 * a["full_rgb_feat"].cpu()) < 2e-4
     # d b4 of prob_dec = sum over pairs of g * act'(y): leaky clamp -> 1 inside (0, 1), 0.01 outside
     y = out["pred_prob_end"]
     seed = gq * torch.where((y > 0) & (y < 1), torch.ones_like(y), torch.full_like(y, 0.01))
