@@ -69,6 +69,13 @@
 #ifndef TC_DEBUG_MODE
 #define TC_DEBUG_MODE 0
 #endif
+// Energy experiments (results are garbage when non-zero; profiles/r2i_energy.md): bit 0 = the weight ring is filled from L2
+// only during the CTA's first pass (later fills just complete the barrier), bit 1 = layer 1 issued as N = 256 MMAs (half the
+// instructions), bit 2 = no layer-1 MMAs for IEF iterations > 0, bit 3 = only the hi*hi product in layer 3, bit 4 = every row reads T[0]
+// (L1-resident: no DRAM latency on the per-ray term), bit 5 = every row gathers A_v[0].
+#ifndef TC_EXP
+#define TC_EXP 0
+#endif
 // suspend-time hint (ns) of mbarrier.try_wait: the warp is parked by the hardware instead of spinning through the loop
 #ifndef TC_WAIT_HINT_NS
 #define TC_WAIT_HINT_NS 1000
@@ -499,7 +506,7 @@ __device__ __forceinline__ void tc_k_ts64(const TcIssue& c, uint32_t dcol, uint3
   constexpr uint32_t idesc = tc::make_idesc(64);
   const uint64_t bhi = c.wd64 + (off >> 4);
   tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi, idesc, first ? 0u : 1u);
-  if (NPROD == 3) {
+  if (NPROD == 3 && !(TC_EXP & 8)) {
     tc::mma_ts(c.tmem + dcol, c.tmem + acol + 8, bhi, idesc, 1u);
     tc::mma_ts(c.tmem + dcol, c.tmem + acol, bhi + (2048u >> 4), idesc, 1u);
   }
@@ -511,8 +518,8 @@ __device__ __forceinline__ void tc_k_ts64(const TcIssue& c, uint32_t dcol, uint3
 
 // layer 1, one output half (7 k-steps = 3 fills of 2 + 1 fill of 1), A operand in shared memory
 template <int NPROD, int GI0>
-__device__ __forceinline__ void tc_issue_l1(const TcIssue& c, uint32_t dcol) {
-  constexpr uint32_t idesc = tc::make_idesc(128);
+__device__ __forceinline__ void tc_issue_l1(const TcIssue& c, uint32_t dcol, bool exp_skip = false, bool exp_n256 = false) {
+  const uint32_t idesc = (TC_EXP & 2) && exp_n256 ? tc::make_idesc(256) : tc::make_idesc(128);
 #pragma unroll
   for (int sg = 0; sg < 4; ++sg) {
     const int gi = GI0 + sg, slot = TC_SLOT(gi);
@@ -520,7 +527,7 @@ __device__ __forceinline__ void tc_issue_l1(const TcIssue& c, uint32_t dcol) {
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
       const int ks = 2 * sg + j;
-      if (ks < TC_K1_STEPS) {
+      if (ks < TC_K1_STEPS && !((TC_EXP & 6) && exp_skip)) {
         const uint64_t bhi = c.wd128 + ((uint32_t)(slot * TC_STAGE_BYTES + j * TC_CHUNK_BYTES) >> 4);
         const uint64_t ahi = c.ad + ((uint32_t)(ks * 4096) >> 4);
         tc::mma_ss(c.tmem + dcol, ahi, bhi, idesc, ks == 0 ? 0u : 1u);
@@ -577,13 +584,14 @@ __device__ __forceinline__ void tc_drain(const TcIssue& c) {
 
 // loader side of the same static schedule: N fills starting at GI0; `pairs` fills are 16 KB, the rest 8 KB
 template <int GI0, int N, int PAIRS>
-__device__ __forceinline__ void tc_load_seg(TcSmem& S, const uint8_t* src, bool ring_primed) {
+__device__ __forceinline__ void tc_load_seg(TcSmem& S, const uint8_t* src, bool ring_primed, bool no_stream = false) {
 #pragma unroll
   for (int sg = 0; sg < N; ++sg) {
     const int gi = GI0 + sg, slot = TC_SLOT(gi);
     const uint32_t bytes = sg < PAIRS ? TC_STAGE_BYTES : TC_CHUNK_BYTES;
     // previous use of this slot was fill gi - 7: wait for its release (skip while the ring fills for the first time)
     if (ring_primed || gi >= TC_STAGES) tc::mbar_wait(&S.w_empty[slot], TC_PAR(gi) ^ 1u);
+    if ((TC_EXP & 1) && ring_primed && no_stream) { tc::mbar_arrive(&S.w_full[slot]); src += bytes; continue; }
     tc::mbar_arrive_expect_tx(&S.w_full[slot], bytes);
     tc::bulk_g2s(S.w[slot], src, bytes, &S.w_full[slot]);
     src += bytes;
@@ -644,11 +652,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         const int d = pass_dec(p);
         const int pn = p + 1 == npt ? 0 : p + 1;
         const int dn = pass_dec(pn);
-        tc_load_seg<GI_S2, 4, 3>(S, seg(d, SEG_L1H1), gp > 0);
-        tc_load_seg<GI_S1, 4, 4>(S, seg(d, SEG_L2K0), true);
-        tc_load_seg<GI_S3, 4, 4>(S, seg(d, SEG_L2K1), true);
-        tc_load_seg<GI_S0, 4, 3>(S, seg(dn, SEG_L1H0), true);                  // drained unused after the last pass
-        tc_load_seg<GI_S4, 4, 0>(S, seg(d, SEG_L3), true);
+        tc_load_seg<GI_S2, 4, 3>(S, seg(d, SEG_L1H1), gp > 0, gp > 0);
+        tc_load_seg<GI_S1, 4, 4>(S, seg(d, SEG_L2K0), true, gp > 0);
+        tc_load_seg<GI_S3, 4, 4>(S, seg(d, SEG_L2K1), true, gp > 0);
+        tc_load_seg<GI_S0, 4, 3>(S, seg(dn, SEG_L1H0), true, gp > 0);          // drained unused after the last pass
+        tc_load_seg<GI_S4, 4, 0>(S, seg(d, SEG_L3), true, gp > 0);
         p = pn;
       }
     }
@@ -664,7 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       c.ad = tc::make_bdesc(tc::smem_u32(S.a1[0]), 2048u, 128u);
       tc::mbar_wait(&S.a1_ready, 0);
       tc::fence_after_sync();
-      tc_issue_l1<NPROD, 0>(c, TC_COL_X0);                                     // S0 of the first pass
+      tc_issue_l1<NPROD, 0>(c, TC_COL_X0, false, true);                        // S0 of the first pass
       tc::commit(&S.x_full[0]);
       int p = 0;
       uint32_t tl = 0;                                                         // tiles whose operand has been consumed
@@ -672,7 +680,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         const uint32_t ph = (uint32_t)gp & 1u;
         const bool last_of_tile = p + 1 == npt;
         // S2(p): layer 1, output half 1 -> X1 (its previous reader S3(p-1) precedes it in the in-order pipe)
-        tc_issue_l1<NPROD, GI_S2>(c, TC_COL_X1);
+        tc_issue_l1<NPROD, GI_S2>(c, TC_COL_X1, (TC_EXP & 2) || ((TC_EXP & 4) && pass_it(p) > 0));
         tc::commit(&S.x_full[1]);
         if (last_of_tile) tc::commit(&S.a1_free);                             // last reader of this tile's layer-1 operand
         // S1(p): layer 2, K half 0 (X0 converted in place by E0) -> Y
@@ -691,7 +699,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
             tc::mbar_wait(&S.a1_ready, tl & 1u);                               // operand of the next tile
             tc::fence_after_sync();
           }
-          tc_issue_l1<NPROD, GI_S0>(c, TC_COL_X0);
+          tc_issue_l1<NPROD, GI_S0>(c, TC_COL_X0, (TC_EXP & 4) && pass_it(last_of_tile ? 0 : p + 1) > 0, true);
           tc::commit(&S.x_full[0]);
         } else {
           tc_drain<GI_S0, 4>(c);
@@ -805,7 +813,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       const float* src0 = a.Av + col + 4 * (lane & 7);
       const float* srcs[8];
 #pragma unroll
-      for (int i = 0; i < 8; ++i) srcs[i] = src0 + (size_t)__shfl_sync(0xffffffffu, vox_, 4 * i + (lane >> 3)) * 512;
+      for (int i = 0; i < 8; ++i) srcs[i] = src0 + (size_t)((TC_EXP & 32) ? 0 : __shfl_sync(0xffffffffu, vox_, 4 * i + (lane >> 3))) * 512;
       const uint32_t dst0 = stage_sa + (uint32_t)((lane >> 3) * TC_STAGE_PITCH + 4 * (lane & 7)) * 4u;
 #pragma unroll
       for (int i = 0; i < 8; ++i) tc::cp_async16(dst0 + (uint32_t)(4 * i * TC_STAGE_PITCH) * 4u, srcs[i]);
@@ -825,7 +833,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       const int n0 = 128 * hf + 32 * g;
       float4 tt[8];
       {
-        const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)ray_ * 512 + 256 * d + n0);
+        const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)((TC_EXP & 16) ? 0 : ray_) * 512 + 256 * d + n0);
 #pragma unroll
         for (int i = 0; i < 8; ++i) tt[i] = valid_ ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
