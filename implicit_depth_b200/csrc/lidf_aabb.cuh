@@ -229,6 +229,127 @@ __global__ void __launch_bounds__(AABB_THREADS) k_aabb_fill(const float* __restr
   }
 }
 
+// ---- compact pair list, RAY-MAJOR (sorted by ray, then voxel) + its CSR ------------------------------------------------
+// The consumer of the pair list (lidf_query_forward) wants all pairs of a ray adjacent; emitting them that way makes its
+// regroup (count / scan / scatter / segment sort over all P pairs) a binary search per ray.  One thread per ray, one block
+// per 256 consecutive rays.  The block forms the image-id range and the direction bounds ("frustum") of its rays, then
+// walks the voxels in tiles of 256: thread i keeps voxel v0 + i if its image id lies in the range and the frustum can meet
+// the box (aabb_tile_may_hit, the same conservative test as the voxel-major generator); survivors are compacted IN ORDER
+// into shared memory, and every ray runs the exact slab test (aabb_slab: bit-identical enter / leave distances) against
+// that short list only.  Pass 1 (FILL = false) counts per ray; after a scan, pass 2 writes each ray's pairs contiguously
+// in ascending voxel order -- no atomics, deterministic.
+#define AABB_RM_THREADS 256
+template <bool FILL>
+__global__ void __launch_bounds__(AABB_RM_THREADS) k_aabb_ray_major(const float* __restrict__ ray_dir, const float* __restrict__ voxel_bound,
+                                                                    const int32_t* __restrict__ ray_bid, const int32_t* __restrict__ voxel_bid,
+                                                                    int64_t R, int64_t V, int* __restrict__ cnt, const int* __restrict__ start,
+                                                                    int64_t* __restrict__ pair_vox, int64_t* __restrict__ pair_ray,
+                                                                    float2* __restrict__ pair_dist) {
+  __shared__ float s_box[AABB_RM_THREADS * 6];
+  __shared__ int s_vid[AABB_RM_THREADS], s_vb[AABB_RM_THREADS];
+  __shared__ int s_woff[AABB_RM_THREADS / 32 + 1];
+  __shared__ float s_t[AABB_RM_THREADS / 32][4];
+  __shared__ int s_bmin, s_bmax, s_bad;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t r = (int64_t)blockIdx.x * AABB_RM_THREADS + threadIdx.x;
+  const bool act = r < R;
+  if (threadIdx.x == 0) { s_bmin = INT_MAX; s_bmax = INT_MIN; s_bad = 0; }
+  __syncthreads();
+  float inv[3] = {0.f, 0.f, 0.f};
+  int bid = 0;
+  {
+    int lo = INT_MAX, hi = INT_MIN, bad = 0;
+    float t[4] = {INFINITY, -INFINITY, INFINITY, -INFINITY};
+    if (act) {
+      bid = ray_bid[r];
+      lo = hi = bid;
+      float d[3];
+#pragma unroll
+      for (int a = 0; a < 3; ++a) {     // float(1 / (double(d) + 1e-12)): ray_aabb_cuda_kernel.cu:32,48,67
+        d[a] = ray_dir[r * 3 + a];
+        inv[a] = __double2float_rn(1.0 / ((double)d[a] + 1e-12));
+      }
+      if (d[2] > 1e-6f && isfinite(d[0]) && isfinite(d[1])) {
+        const float tx = d[0] / d[2], ty = d[1] / d[2];
+        t[0] = t[1] = tx; t[2] = t[3] = ty;
+      } else {
+        bad = 1;
+      }
+    }
+    lo = __reduce_min_sync(0xffffffffu, lo); hi = __reduce_max_sync(0xffffffffu, hi);
+    bad = __any_sync(0xffffffffu, bad);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      t[0] = fminf(t[0], __shfl_xor_sync(0xffffffffu, t[0], o)); t[1] = fmaxf(t[1], __shfl_xor_sync(0xffffffffu, t[1], o));
+      t[2] = fminf(t[2], __shfl_xor_sync(0xffffffffu, t[2], o)); t[3] = fmaxf(t[3], __shfl_xor_sync(0xffffffffu, t[3], o));
+    }
+    if (lane == 0) {
+      atomicMin(&s_bmin, lo); atomicMax(&s_bmax, hi);
+      if (bad) atomicOr(&s_bad, 1);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) s_t[warp][k] = t[k];
+    }
+  }
+  __syncthreads();
+  const int bmin = s_bmin, bmax = s_bmax;
+  float4 fr = make_float4(INFINITY, -INFINITY, INFINITY, -INFINITY);
+#pragma unroll
+  for (int w = 0; w < AABB_RM_THREADS / 32; ++w) {
+    fr.x = fminf(fr.x, s_t[w][0]); fr.y = fmaxf(fr.y, s_t[w][1]); fr.z = fminf(fr.z, s_t[w][2]); fr.w = fmaxf(fr.w, s_t[w][3]);
+  }
+  if (s_bad) fr = make_float4(-INFINITY, INFINITY, -INFINITY, INFINITY);
+  int count = 0;
+  int64_t pos = (FILL && act) ? (int64_t)start[r] : 0;
+  for (int64_t v0 = 0; v0 < V; v0 += AABB_RM_THREADS) {
+    const int64_t v = v0 + threadIdx.x;
+    bool live = false;
+    AabbBox box;
+    int vb = 0;
+    if (v < V) {
+      vb = __ldg(voxel_bid + v);
+      if (vb >= bmin && vb <= bmax) { box = aabb_load_box(voxel_bound, v); live = aabb_tile_may_hit(fr, box); }
+    }
+    const unsigned m = __ballot_sync(0xffffffffu, live);
+    if (lane == 0) s_woff[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {                                           // exclusive prefix over the 8 warps; total in s_woff[8]
+      int run = 0;
+#pragma unroll
+      for (int w = 0; w < AABB_RM_THREADS / 32; ++w) { const int c = s_woff[w]; s_woff[w] = run; run += c; }
+      s_woff[AABB_RM_THREADS / 32] = run;
+    }
+    __syncthreads();
+    if (live) {
+      const int i = s_woff[warp] + __popc(m & ((1u << lane) - 1u));
+      s_vid[i] = (int)threadIdx.x; s_vb[i] = vb;
+#pragma unroll
+      for (int k = 0; k < 3; ++k) { s_box[i * 6 + k] = box.lo[k]; s_box[i * 6 + 3 + k] = box.hi[k]; }
+    }
+    __syncthreads();
+    const int n = s_woff[AABB_RM_THREADS / 32];
+    if (act) {
+      for (int i = 0; i < n; ++i) {
+        if (s_vb[i] != bid) continue;
+        AabbBox b;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { b.lo[k] = s_box[i * 6 + k]; b.hi[k] = s_box[i * 6 + 3 + k]; }
+        float t0, t1;
+        if (!aabb_slab(inv[0], inv[1], inv[2], b, t0, t1)) continue;
+        if (FILL) {
+          pair_vox[pos] = v0 + s_vid[i];
+          pair_ray[pos] = r;
+          pair_dist[pos] = make_float2(t0, t1);
+          ++pos;
+        } else {
+          ++count;
+        }
+      }
+    }
+    __syncthreads();                                                  // the lists are rebuilt by the next voxel tile
+  }
+  if (!FILL && act) cnt[r] = count;
+}
+
 // ---- dense drop-in: mask[V,R] int32, dist[V,R,2] -- every element written once with streaming stores -----------------
 // Thread t of a work item owns the 4 consecutive rays 4t .. 4t+3 of the tile: one 16-byte mask store and two 16-byte
 // dist stores per thread (a warp writes 512 B + 1 KB contiguous), 16-byte loads of the image ids and reciprocal

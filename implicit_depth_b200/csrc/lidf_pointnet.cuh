@@ -235,6 +235,228 @@ __global__ void __launch_bounds__(PN2_THREADS, 1) k_pn_stage2(const float* __res
   }
 }
 
+// ---- stage 2 on the tensor cores (tcgen05) ------------------------------------------------------------------------------
+// The two 128 -> 128 per-point layers are 97 % of PointNet2Stage's MACs (32,768 of 33,984 per point).  Same split-bf16
+// arithmetic and primitives as the decoder engine (lidf_tc.cuh): x = hi + lo, three products per MAC, fp32 accumulators
+// in TMEM.  Persistent CTA per SM, tile = 128 points (row = TMEM lane = point):
+//   16 row warps (TMEM quadrant q, column group g): build the layer-3 operand [voxel feature (64) | point feature (64)]
+//     in shared memory (UMMA canonical K-major layout; the 6 -> 32 -> 64 point MLP stays on the FMA pipe, 16 outputs per
+//     thread), run the two epilogues (bias + ReLU; layer 3's output is re-split and written back to TMEM as the layer-4
+//     operand) and the per-voxel run-reduced max of the tile
+//   warp 16: one thread loads BOTH packed weight matrices once (2 x 64 KB stay resident in shared memory for the CTA's
+//     lifetime -- no weight streaming) and issues the 2 x 24 MMAs of a tile (layer 3 SS-mode, layer 4 TS-mode).
+// TMEM: [0,128) layer-3 accumulator, [128,256) layer-4 operand (hi | lo), [256,384) layer-4 accumulator.
+// The operand tile doubles as the fp32 [channel][point] staging buffer of the scatter-max once layer 3 has consumed it.
+#define PNT_ROW_WARPS 16
+#define PNT_THREADS ((PNT_ROW_WARPS + 1) * 32)
+#define PNT_KSTEPS 8
+
+struct PnTcSmem {
+  uint8_t w[2][PNT_KSTEPS][TC_CHUNK_BYTES];      // point_lin3, point_lin4: per k-step [hi: kg0 | kg1][lo: kg0 | kg1], N = 128
+  uint8_t x[2][PNT_KSTEPS * 4096];                // layer-3 operand [hi | lo][k-step][kgroup][128 rows][16 B]; later O[128][128] fp32
+  float W1[PN_GF * PN_IN], b1[PN_GF], W2[PN_C1 * PN_GF], b2[PN_C1], b3[PN_C2], b4[PN_C2];
+  int idx[128];
+  uint64_t w_full, a_ready, d3_full, a4_ready, d4_full;
+  uint32_t tmem_base;
+};
+
+// W [128 out][128 in] fp32 row-major -> 8 k-step chunks of 8 KB in the UMMA canonical layout, bf16 hi | lo
+__global__ void k_pn_pack_tc(const float* __restrict__ W, uint8_t* __restrict__ chunks) {
+  const int idx = blockIdx.x * blockDim.x + threadIdx.x;
+  if (idx >= PNT_KSTEPS * 2048) return;
+  const int c = idx / 2048, r = idx % 2048, n = r / 16, kk = r % 16;
+  const float w = W[n * PN_C2 + 16 * c + kk];
+  const __nv_bfloat16 hi = __float2bfloat16_rn(w);
+  const __nv_bfloat16 lo = __float2bfloat16_rn(w - __bfloat162float(hi));
+  const size_t off = (size_t)(kk >> 3) * 128 * 16 + (size_t)n * 16 + (kk & 7) * 2;
+  *reinterpret_cast<__nv_bfloat16*>(chunks + (size_t)c * TC_CHUNK_BYTES + off) = hi;
+  *reinterpret_cast<__nv_bfloat16*>(chunks + (size_t)c * TC_CHUNK_BYTES + 128 * 32 + off) = lo;
+}
+
+__global__ void __launch_bounds__(PNT_THREADS, 1) k_pn_stage2_tc(const float* __restrict__ inp, const int64_t* __restrict__ idx,
+                                                                 int64_t N, int64_t V, PnWeights w, const uint8_t* __restrict__ wpack,
+                                                                 const float* __restrict__ vf1, float* __restrict__ vmax2) {
+  extern __shared__ __align__(1024) uint8_t pn_smem_raw[];
+  PnTcSmem& S = *reinterpret_cast<PnTcSmem*>(pn_smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  for (int i = tid; i < PN_GF * PN_IN; i += PNT_THREADS) S.W1[i] = w.w_p1[i];
+  for (int i = tid; i < PN_GF; i += PNT_THREADS) S.b1[i] = w.b_p1[i];
+  for (int i = tid; i < PN_C1 * PN_GF; i += PNT_THREADS) S.W2[i] = w.w_p2[i];
+  for (int i = tid; i < PN_C1; i += PNT_THREADS) S.b2[i] = w.b_p2[i];
+  for (int i = tid; i < PN_C2; i += PNT_THREADS) { S.b3[i] = w.b_p3[i]; S.b4[i] = w.b_p4[i]; }
+  if (tid == 0) {
+    tc::mbar_init(&S.w_full, 1);
+    tc::mbar_init(&S.a_ready, PNT_ROW_WARPS);
+    tc::mbar_init(&S.d3_full, 1);
+    tc::mbar_init(&S.a4_ready, PNT_ROW_WARPS);
+    tc::mbar_init(&S.d4_full, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == PNT_ROW_WARPS) tc::tmem_alloc(&S.tmem_base, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  const int n_tiles = (int)((N + 127) / 128);
+  const int n_my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  constexpr uint32_t COL_D3 = 0, COL_A4 = 128, COL_D4 = 256;
+
+  if (warp == PNT_ROW_WARPS) {
+    // ================================ weight load (once) + MMA issue, one thread ================================
+    if (tc::elect_one()) {
+      tc::mbar_arrive_expect_tx(&S.w_full, 2 * PNT_KSTEPS * TC_CHUNK_BYTES);
+#pragma unroll 1
+      for (int c = 0; c < 2 * PNT_KSTEPS; ++c)
+        tc::bulk_g2s(&S.w[0][0][0] + (size_t)c * TC_CHUNK_BYTES, wpack + (size_t)c * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full);
+      tc::mbar_wait(&S.w_full, 0);
+      constexpr uint32_t idesc = tc::make_idesc(128);
+      const uint64_t w3d = tc::make_bdesc(tc::smem_u32(&S.w[0][0][0]), 2048u, 128u);
+      const uint64_t w4d = tc::make_bdesc(tc::smem_u32(&S.w[1][0][0]), 2048u, 128u);
+      const uint64_t ad = tc::make_bdesc(tc::smem_u32(S.x[0]), 2048u, 128u);
+      for (int t = 0; t < n_my_tiles; ++t) {
+        const uint32_t ph = (uint32_t)t & 1u;
+        tc::mbar_wait(&S.a_ready, ph);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int ks = 0; ks < PNT_KSTEPS; ++ks) {                                // layer 3: operand in shared memory
+          const uint64_t bhi = w3d + ((uint32_t)(ks * TC_CHUNK_BYTES) >> 4), ahi = ad + ((uint32_t)(ks * 4096) >> 4);
+          tc::mma_ss(tmem + COL_D3, ahi, bhi, idesc, ks == 0 ? 0u : 1u);
+          tc::mma_ss(tmem + COL_D3, ahi + ((uint32_t)(PNT_KSTEPS * 4096) >> 4), bhi, idesc, 1u);
+          tc::mma_ss(tmem + COL_D3, ahi, bhi + (4096u >> 4), idesc, 1u);
+        }
+        tc::commit(&S.d3_full);
+        tc::mbar_wait(&S.a4_ready, ph);
+        tc::fence_after_sync();
+#pragma unroll 1
+        for (int ks = 0; ks < PNT_KSTEPS; ++ks) {                                // layer 4: operand in TMEM (8 cols hi | 8 cols lo)
+          const uint64_t bhi = w4d + ((uint32_t)(ks * TC_CHUNK_BYTES) >> 4);
+          const uint32_t acol = tmem + COL_A4 + 16 * ks;
+          tc::mma_ts(tmem + COL_D4, acol, bhi, idesc, ks == 0 ? 0u : 1u);
+          tc::mma_ts(tmem + COL_D4, acol + 8, bhi, idesc, 1u);
+          tc::mma_ts(tmem + COL_D4, acol, bhi + (4096u >> 4), idesc, 1u);
+        }
+        tc::commit(&S.d4_full);
+      }
+    }
+  } else {
+    // ================================ row warps ================================
+    const int q = warp & 3, g = warp >> 2;
+    const int row = q * 32 + lane;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    const uint32_t x_hi = tc::smem_u32(S.x[0]) + row * 16, x_lo = tc::smem_u32(S.x[1]) + row * 16;
+    float* const O = reinterpret_cast<float*>(&S.x[0][0]);
+    auto st_x = [&](int ks, const uint32_t* wd) {
+      tc::st_shared_v4(x_hi + ks * 4096, wd[0], wd[1], wd[2], wd[3]);
+      tc::st_shared_v4(x_hi + ks * 4096 + 2048, wd[4], wd[5], wd[6], wd[7]);
+      tc::st_shared_v4(x_lo + ks * 4096, wd[8], wd[9], wd[10], wd[11]);
+      tc::st_shared_v4(x_lo + ks * 4096 + 2048, wd[12], wd[13], wd[14], wd[15]);
+    };
+    for (int t = 0; t < n_my_tiles; ++t) {
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int64_t base = (int64_t)tile * 128;
+      const int np = (int)min((int64_t)128, N - base);
+      const uint32_t ph = (uint32_t)t & 1u;
+      // ---- layer-3 operand: cat((voxel feature, point feature), -1), pointnet.py:31; this thread owns 16 + 16 of the 128
+      {
+        const int64_t i = base + row;
+        int v = -1;
+        if (row < np) { const int64_t vv = idx[i]; if (vv >= 0 && vv < V) v = (int)vv; }
+        if (g == 0) S.idx[row] = v;
+        uint32_t wd[16];
+        {                                                                    // point feature: 6 -> 32 -> 64, outputs 16 g .. 16 g + 15
+          float f2[16];
+          if (v >= 0) {
+            float x[PN_IN];
+#pragma unroll
+            for (int k = 0; k < PN_IN; ++k) x[k] = inp[i * PN_IN + k];
+            pn_point_mlp<16>(x, S.W1, S.b1, S.W2, S.b2, 16 * g, f2);
+          } else {
+#pragma unroll
+            for (int c = 0; c < 16; ++c) f2[c] = 0.f;
+          }
+          tc::split16(f2, wd);
+          st_x(4 + g, wd);
+        }
+        {                                                                    // voxel feature of the point's voxel, columns 16 g .. 16 g + 15
+          float xv[16];
+#pragma unroll
+          for (int c = 0; c < 16; ++c) xv[c] = 0.f;
+          if (v >= 0) {
+            const float4* vr = reinterpret_cast<const float4*>(vf1 + (size_t)v * PN_C1 + 16 * g);
+#pragma unroll
+            for (int c4 = 0; c4 < 4; ++c4) {
+              const float4 gq = __ldg(vr + c4);
+              xv[4 * c4] = gq.x; xv[4 * c4 + 1] = gq.y; xv[4 * c4 + 2] = gq.z; xv[4 * c4 + 3] = gq.w;
+            }
+          }
+          tc::split16(xv, wd);
+          st_x(g, wd);
+        }
+      }
+      tc::fence_proxy_async();
+      tc::fence_before_sync();                                               // also orders the previous tile's TMEM loads
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.a_ready);
+      // ---- layer-3 epilogue: relu(acc + b3) -> hi | lo -> layer-4 operand in TMEM
+      tc::mbar_wait(&S.d3_full, ph);
+      tc::fence_after_sync();
+      {
+        uint32_t r[32];
+        tc::tmem_ld32(lane_addr + COL_D3 + 32 * g, r);
+        tc::wait_ld();
+#pragma unroll
+        for (int s16 = 0; s16 < 2; ++s16) {
+          float h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) h[j] = fmaxf(__uint_as_float(r[16 * s16 + j]) + S.b3[32 * g + 16 * s16 + j], 0.f);
+          uint32_t wd[16];
+          tc::split16(h, wd);
+          tc::tmem_st16(lane_addr + COL_A4 + 32 * g + 16 * s16, wd);
+        }
+        tc::wait_st();
+      }
+      tc::fence_before_sync();
+      __syncwarp();
+      if (lane == 0) tc::mbar_arrive(&S.a4_ready);
+      // ---- layer-4 epilogue: relu(acc + b4) -> O[channel][point] (XOR-swizzled columns: conflict-free both ways)
+      tc::mbar_wait(&S.d4_full, ph);
+      tc::fence_after_sync();
+      {
+        uint32_t r[32];
+        tc::tmem_ld32(lane_addr + COL_D4 + 32 * g, r);
+        tc::wait_ld();
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+          const int c = 32 * g + j;
+          O[c * 128 + (row ^ j)] = fmaxf(__uint_as_float(r[j]) + S.b4[c], 0.f);
+        }
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PNT_ROW_WARPS * 32) : "memory");
+      // ---- per-voxel max of the tile: thread (channel c, quarter part) scans 32 points, one atomic per run of equal voxel ids
+      {
+        const int c = tid & 127, part = tid >> 7;
+        const int p0 = 32 * part, p1 = min(np, p0 + 32);
+        int cur = -1;
+        float m = 0.f;
+        for (int p = p0; p < p1; ++p) {
+          const int v = S.idx[p];
+          if (v != cur) {
+            if (cur >= 0) atomicMax(reinterpret_cast<int*>(vmax2 + (size_t)cur * PN_C2 + c), __float_as_int(m));
+            cur = v; m = 0.f;
+          }
+          m = fmaxf(m, O[c * 128 + (p ^ (c & 31))]);
+        }
+        if (cur >= 0) atomicMax(reinterpret_cast<int*>(vmax2 + (size_t)cur * PN_C2 + c), __float_as_int(m));
+      }
+      asm volatile("bar.sync 1, %0;" ::"n"(PNT_ROW_WARPS * 32) : "memory");    // O / idx are overwritten by the next tile's build
+    }
+  }
+  __syncwarp();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == PNT_ROW_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
 inline size_t pn_stage1_smem() { return sizeof(float) * (PN_GF * PN_IN + PN_GF + PN_C1 * PN_GF + PN_C1 + PN_C1 * PN1_PITCH) + sizeof(int) * PN1_THREADS; }
 inline size_t pn_stage2_smem() {
   return sizeof(float) * (PN_GF * PN_IN + PN_GF + PN_C1 * PN_GF + PN_C1 + 2 * PN_C2 + 2 * PN_C2 * PN_C2 + 2 * PN_C2 * PN2_PITCH) +

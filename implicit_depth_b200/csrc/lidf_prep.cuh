@@ -25,6 +25,30 @@ __global__ void k_count_pairs(const int64_t* __restrict__ pair_ray, int64_t P, i
     if (v < 0 || v >= V) atomicOr(err, 2);
   }
 }
+// Pair list already ray-major (pair_ray non-decreasing, LidfQueryParams::pairs_ray_major): the CSR is a binary search per
+// ray (ray_start[r] = first i with pair_ray[i] >= r, ray_start[R] = P) and perm is the identity.  k_check_sorted_pairs is the
+// pass over the list that keeps the range checks of k_count_pairs and verifies the order (err bit 2).
+__global__ void k_ray_start_sorted(const int64_t* __restrict__ pair_ray, int64_t P, int64_t R, int* __restrict__ ray_start) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  int64_t lo = 0, hi = P;                             // lower bound of r (clamped keys: < 0 counts as ray 0, >= R as R - 1)
+  while (lo < hi) {
+    const int64_t mid = (lo + hi) >> 1;
+    if (lidf_clamp_idx(__ldg(pair_ray + mid), R) < r) lo = mid + 1; else hi = mid;
+  }
+  ray_start[r] = (int)(r == R ? P : lo);
+}
+__global__ void k_check_sorted_pairs(const int64_t* __restrict__ pair_ray, int64_t P, int64_t R, int* __restrict__ perm,
+                                     int* __restrict__ err, const int64_t* __restrict__ pair_vox, int64_t V) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const int64_t r = pair_ray[i];
+  int bad = (r < 0 || r >= R) ? 1 : 0;
+  if (i > 0 && lidf_clamp_idx(pair_ray[i - 1], R) > lidf_clamp_idx(r, R)) bad |= 4;
+  if (pair_vox) { const int64_t v = pair_vox[i]; if (v < 0 || v >= V) bad |= 2; }
+  perm[i] = (int)i;
+  if (bad) atomicOr(err, bad);
+}
 // range check of the other index arrays the kernels dereference (pair_vox over P, miss_bid over R)
 __global__ void k_validate_indices(const int64_t* __restrict__ pair_vox, int64_t P, int64_t V, const int64_t* __restrict__ bid,
                                    int64_t R, int64_t B, int* __restrict__ err) {

@@ -86,8 +86,18 @@ CsrBufs carve_csr(Bump& b, int64_t P, int64_t R) {
 }
 
 int build_csr(const CsrBufs& c, const int64_t* pair_ray, int64_t P, int64_t R, cudaStream_t st, bool sort_segments = true,
-              const int64_t* check_vox = nullptr, int64_t V = 0) {
+              const int64_t* check_vox = nullptr, int64_t V = 0, bool ray_major = false) {
   const int64_t n = R + 1;
+  if (ray_major) {                                   // caller's list is sorted by ray: no regroup, see k_ray_start_sorted
+    LIDF_CUDA(cudaMemsetAsync(c.cnt + n, 0, sizeof(int), st));
+    k_ray_start_sorted<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.ray_start);
+    LIDF_LAUNCH_CHECK();
+    if (P > 0) {
+      k_check_sorted_pairs<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.perm, c.cnt + n, check_vox, V);
+      LIDF_LAUNCH_CHECK();
+    }
+    return LIDF_OK;
+  }
   LIDF_CUDA(cudaMemsetAsync(c.cnt, 0, sizeof(int) * (n + 1), st));
   if (P > 0) {
     k_count_pairs<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(pair_ray, P, R, c.cnt, c.cnt + n, check_vox, V);
@@ -495,7 +505,7 @@ int run_prep(const LidfQueryParams* p, QueryPlan& q, cudaStream_t st) {
   int rc;
   const int64_t P = p->P, R = p->R, V = p->V;
   // 1. regroup (flags out-of-range pair_ray in csr.cnt[R + 1]); range check of pair_vox / miss_bid into the same flag
-  if ((rc = build_csr(q.csr, p->pair_ray, P, R, st, true, p->pair_vox, V))) return rc;
+  if ((rc = build_csr(q.csr, p->pair_ray, P, R, st, true, p->pair_vox, V, p->pairs_ray_major != 0))) return rc;
   if (R > 0) {
     k_validate_indices<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(nullptr, 0, V, p->miss_bid, R, p->B, q.csr.cnt + (R + 1));
     LIDF_LAUNCH_CHECK();
@@ -1215,6 +1225,86 @@ extern "C" int lidf_ray_aabb_pairs_fill(const float* ray_dir, const float* voxel
   return LIDF_OK;
 }
 
+namespace {
+struct AabbRmPlan { int* cnt; int* start; int* block_sums; int nb; size_t bytes; };
+int plan_aabb_rm(int64_t R, int64_t V, AabbRmPlan* q, char* base) {
+  if (R < 0 || V < 0) return LIDF_ERR_ARG;
+  if (R >= INT_MAX - 2 || V >= INT_MAX - 2) return LIDF_ERR_UNSUPPORTED;
+  const int64_t n = R + 1;
+  q->nb = (int)((n + LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS - 1) / (LIDF_SCAN_BLOCK * LIDF_SCAN_ITEMS));
+  Bump b{base, 0};
+  q->cnt = b.take<int>((size_t)n);
+  q->start = b.take<int>((size_t)n);
+  q->block_sums = b.take<int>((size_t)q->nb);
+  q->bytes = b.off + 256;
+  return LIDF_OK;
+}
+}  // namespace
+
+extern "C" size_t lidf_ray_aabb_ray_major_workspace_bytes(int64_t R, int64_t V) {
+  AabbRmPlan q;
+  if (plan_aabb_rm(R, V, &q, nullptr) != LIDF_OK) return 0;
+  return q.bytes;
+}
+
+extern "C" int lidf_ray_aabb_pairs_ray_major_count(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                                   const int32_t* voxel_bid, int64_t R, int64_t V, void* workspace,
+                                                   size_t workspace_bytes, int64_t* n_pairs_host, lidf_stream_t stream) {
+  if (!n_pairs_host) return LIDF_ERR_NULL;
+  *n_pairs_host = 0;
+  AabbRmPlan q;
+  int rc = plan_aabb_rm(R, V, &q, (char*)workspace);
+  if (rc) return rc;
+  if (R == 0) return LIDF_OK;
+  if (!workspace) return LIDF_ERR_NULL;
+  if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  cudaStream_t st = stream;
+  const int64_t n = R + 1;
+  LIDF_CUDA(cudaMemsetAsync(q.cnt, 0, sizeof(int) * (size_t)n, st));
+  if (V > 0) {
+    if (!ray_dir || !voxel_bound || !ray_bid || !voxel_bid) return LIDF_ERR_NULL;
+    k_aabb_ray_major<false><<<(unsigned)((R + AABB_RM_THREADS - 1) / AABB_RM_THREADS), AABB_RM_THREADS, 0, st>>>(
+        ray_dir, voxel_bound, ray_bid, voxel_bid, R, V, q.cnt, nullptr, nullptr, nullptr, nullptr);
+    LIDF_LAUNCH_CHECK();
+  }
+  k_scan_partial<<<q.nb, LIDF_SCAN_BLOCK, 0, st>>>(q.cnt, n, q.start, q.block_sums);
+  LIDF_LAUNCH_CHECK();
+  k_scan_blocksums<<<1, 1024, 0, st>>>(q.block_sums, q.nb);
+  LIDF_LAUNCH_CHECK();
+  k_scan_add<<<q.nb, LIDF_SCAN_BLOCK, 0, st>>>(q.start, n, q.block_sums, nullptr);
+  LIDF_LAUNCH_CHECK();
+  int total = 0;
+  LIDF_CUDA(cudaMemcpyAsync(&total, q.start + R, sizeof(int), cudaMemcpyDeviceToHost, st));
+  LIDF_CUDA(cudaStreamSynchronize(st));
+  if (total < 0) return LIDF_ERR_UNSUPPORTED;              // >= 2^31 pairs
+  *n_pairs_host = total;
+  return LIDF_OK;
+}
+
+extern "C" int lidf_ray_aabb_pairs_ray_major_fill(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                                  const int32_t* voxel_bid, int64_t R, int64_t V, void* workspace,
+                                                  size_t workspace_bytes, int64_t P, int64_t* pair_vox, int64_t* pair_ray,
+                                                  float* pair_dist, int32_t* ray_start, lidf_stream_t stream) {
+  AabbRmPlan q;
+  int rc = plan_aabb_rm(R, V, &q, (char*)workspace);
+  if (rc) return rc;
+  if (P < 0) return LIDF_ERR_ARG;
+  cudaStream_t st = stream;
+  if (R == 0) {
+    if (ray_start) LIDF_CUDA(cudaMemsetAsync(ray_start, 0, sizeof(int), st));
+    return LIDF_OK;
+  }
+  if (!workspace) return LIDF_ERR_NULL;
+  if (workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
+  if (ray_start) LIDF_CUDA(cudaMemcpyAsync(ray_start, q.start, sizeof(int) * (size_t)(R + 1), cudaMemcpyDeviceToDevice, st));
+  if (V == 0 || P == 0) return LIDF_OK;
+  if (!ray_dir || !voxel_bound || !ray_bid || !voxel_bid || !pair_vox || !pair_ray || !pair_dist) return LIDF_ERR_NULL;
+  k_aabb_ray_major<true><<<(unsigned)((R + AABB_RM_THREADS - 1) / AABB_RM_THREADS), AABB_RM_THREADS, 0, st>>>(
+      ray_dir, voxel_bound, ray_bid, voxel_bid, R, V, nullptr, q.start, pair_vox, pair_ray, reinterpret_cast<float2*>(pair_dist));
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
+
 extern "C" int lidf_pcl_aabb_forward(const float* pcl_pos, const float* voxel_bound, const int32_t* pcl_bid,
                                      const int32_t* voxel_bid, int64_t N, int64_t V, int32_t* mask, lidf_stream_t stream) {
   if (N < 0 || V < 0) return LIDF_ERR_ARG;
@@ -1347,7 +1437,7 @@ extern "C" int lidf_voxelize_fill(const float* xyz, const int64_t* bid, int64_t 
 #include "lidf_pointnet.cuh"
 
 namespace {
-struct PnPlan { float* vmax1; float* vf1; float* vmax2; int* err; size_t bytes; };
+struct PnPlan { float* vmax1; float* vf1; float* vmax2; int* err; uint8_t* wpack; size_t bytes; };
 int plan_pn(int64_t N, int64_t V, PnPlan* q, char* base) {
   if (N < 0 || V < 0) return LIDF_ERR_ARG;
   if (V >= INT_MAX / 256 || N >= ((int64_t)1 << 40)) return LIDF_ERR_UNSUPPORTED;
@@ -1357,6 +1447,7 @@ int plan_pn(int64_t N, int64_t V, PnPlan* q, char* base) {
   q->vmax2 = b.take<float>(v * PN_C2);      // contiguous with vmax1: one memset clears both
   q->vf1 = b.take<float>(v * PN_C1);
   q->err = b.take<int>(1);
+  q->wpack = b.take<uint8_t>((size_t)2 * PNT_KSTEPS * TC_CHUNK_BYTES);     // point_lin3 / point_lin4 as bf16 hi | lo MMA chunks
   q->bytes = b.off + 256;
   return LIDF_OK;
 }
@@ -1370,7 +1461,15 @@ extern "C" size_t lidf_pointnet_workspace_bytes(int64_t N, int64_t V) {
 
 extern "C" int lidf_pointnet_forward(const LidfPointNet* wp, const float* inp, const int64_t* idx, int64_t N, int64_t V,
                                      float* out, void* ws, size_t ws_bytes, lidf_stream_t stream) {
+  return lidf_pointnet_forward_impl(wp, inp, idx, N, V, out, ws, ws_bytes, LIDF_MLP_AUTO, stream);
+}
+
+extern "C" int lidf_pointnet_forward_impl(const LidfPointNet* wp, const float* inp, const int64_t* idx, int64_t N, int64_t V,
+                                          float* out, void* ws, size_t ws_bytes, int32_t mlp_impl, lidf_stream_t stream) {
   if (!wp) return LIDF_ERR_NULL;
+  if (mlp_impl != LIDF_MLP_AUTO && mlp_impl != LIDF_MLP_SIMT_FP32 && mlp_impl != LIDF_MLP_TC_BF16X3) return LIDF_ERR_ARG;
+  const bool use_tc = mlp_impl != LIDF_MLP_SIMT_FP32;
+  if (use_tc && !tc_device_ok()) return LIDF_ERR_NO_SM100;
   PnPlan q;
   int rc = plan_pn(N, V, &q, (char*)ws);
   if (rc) return rc;
@@ -1395,7 +1494,17 @@ extern "C" int lidf_pointnet_forward(const LidfPointNet* wp, const float* inp, c
   }
   k_pn_vox<PN_C1><<<(unsigned)((V + 7) / 8), PN_C1, 0, st>>>(q.vmax1, w.w_v1, w.b_v1, V, q.vf1);
   LIDF_LAUNCH_CHECK();
-  if (N > 0) {
+  if (N > 0 && use_tc) {
+    // the two 128 -> 128 layers on the tensor cores (split bf16, fp32 accumulate), weights resident in shared memory
+    k_pn_pack_tc<<<(PNT_KSTEPS * 2048 + 255) / 256, 256, 0, st>>>(w.w_p3, q.wpack);
+    LIDF_LAUNCH_CHECK();
+    k_pn_pack_tc<<<(PNT_KSTEPS * 2048 + 255) / 256, 256, 0, st>>>(w.w_p4, q.wpack + (size_t)PNT_KSTEPS * TC_CHUNK_BYTES);
+    LIDF_LAUNCH_CHECK();
+    const size_t smt = sizeof(PnTcSmem) + 1024;
+    LIDF_CUDA(cudaFuncSetAttribute(k_pn_stage2_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smt));
+    k_pn_stage2_tc<<<persistent_blocks((N + 127) / 128, 1), PNT_THREADS, smt, st>>>(inp, idx, N, V, w, q.wpack, q.vf1, q.vmax2);
+    LIDF_LAUNCH_CHECK();
+  } else if (N > 0) {
     const int64_t t2 = (N + PN2_TP - 1) / PN2_TP;
     k_pn_stage2<<<persistent_blocks(t2, 1), PN2_THREADS, sm2, st>>>(inp, idx, N, V, w, q.vf1, q.vmax2);
     LIDF_LAUNCH_CHECK();

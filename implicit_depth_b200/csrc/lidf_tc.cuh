@@ -965,9 +965,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     int ray = cur.ray, vox = cur.vox;
     bool valid = cur.valid;
     uint32_t gp = 0, tl = 0;
-    bool pend = false;                                         // a deferred E3
-    int pend_d = 0, pend_it = 0, pend_tile = 0, pend_buf = 0;
-    uint32_t pend_ph = 0;
+    bool pend = false;                                         // E3 of the previous pass is deferred (its arguments are re-derived)
     gather_issue(vox, 256 * pass_dec(0) + 32 * g);
     epi_l1(0, pass_dec(0), false, 0.f, ray, valid, 0u, vox, 256 * pass_dec(0) + 128 + 32 * g);
     for (int tile = blockIdx.x; tile < a.n_tiles; tile += gridDim.x, ++tl) {
@@ -992,7 +990,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         epi_l1(1, d, is_ief && it > 0, (d == 0 ? o_a : o_b) - a.o0, ray, valid, ph, vox_n,
                has_next_pass ? 256 * dn + 32 * g : -1);
         // ---- deferred E3(p-1): fills the wait for layer 2 of this pass
-        if (pend) { epi_l3(pend_d, pend_it, pend_ph, pend_tile, pend_buf); pend = false; }
+        if (pend) {
+          const int pp = p == 0 ? npt - 1 : p - 1;                           // the previous pass: of this tile, or the last one of the previous tile
+          epi_l3(pass_dec(pp), pass_it(pp), ph ^ 1u, p == 0 ? tile - (int)gridDim.x : tile, (int)((p == 0 ? tl + 1u : tl) & 1u));
+          pend = false;
+        }
         // ---- operand of the next tile: its last reader (S2 of this pass) has retired once a1_free completes
         if (last && has_next) {
           tc::mbar_wait(&S.a1_free, tl & 1u);
@@ -1004,7 +1006,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
           // ---- E0(p+1) first, E3(p) deferred
           epi_l1(0, dn, (dn == 0 ? ief0 : ief1) && itn > 0, (dn == 0 ? o_a : o_b) - a.o0, ray_n, valid_n, ph ^ 1u, vox_n,
                  256 * dn + 128 + 32 * g);
-          pend = true; pend_d = d; pend_it = it; pend_ph = ph; pend_tile = tile; pend_buf = (int)(tl & 1u);
+          pend = true;
         } else {
           // ---- E3(p) now; then E0(p+1) of the dependent pass
           epi_l3(d, it, ph, tile, (int)(tl & 1u));

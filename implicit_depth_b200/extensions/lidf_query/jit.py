@@ -49,7 +49,8 @@ class _QueryParams(C.Structure):
                 ("pred_prob_end_softmax", C.c_void_p), ("max_pair_id", C.c_void_p), ("pred_pos", C.c_void_p),
                 ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("ief_iter_out", C.c_void_p), ("index_error", C.c_void_p),
-                ("weight_cache", C.c_void_p), ("weight_cache_bytes", C.c_size_t), ("weight_cache_valid", C.c_int32)]
+                ("weight_cache", C.c_void_p), ("weight_cache_bytes", C.c_size_t), ("weight_cache_valid", C.c_int32),
+                ("pairs_ray_major", C.c_int32)]
 
 
 class _DecoderGrad(C.Structure):
@@ -74,7 +75,7 @@ class _RefineParams(C.Structure):
                 ("V", C.c_int64), ("occ_voxel_feat", C.c_void_p), ("end_voxel_id", C.c_void_p), ("voxel_bound", C.c_void_p)]
 
 
-ABI_VERSION = 3
+ABI_VERSION = 4
 EXPORTED_SYMBOLS = [
     "lidf_query_abi_version", "lidf_query_struct_size", "lidf_query_error_string", "lidf_query_last_cuda_error",
     "lidf_query_workspace_bytes", "lidf_query_weight_cache_bytes", "lidf_query_forward", "lidf_refine_workspace_bytes", "lidf_refine_forward",
@@ -86,10 +87,11 @@ EXPORTED_SYMBOLS = [
     "lidf_depth_metrics_workspace_bytes", "lidf_depth_metrics_rays", "lidf_depth_metrics_image",
 ]
 # include/lidf_pointnet.h (bound by models/pointnet.py)
-EXPORTED_SYMBOLS_POINTNET = ["lidf_pointnet_workspace_bytes", "lidf_pointnet_forward"]
+EXPORTED_SYMBOLS_POINTNET = ["lidf_pointnet_workspace_bytes", "lidf_pointnet_forward", "lidf_pointnet_forward_impl"]
 # include/lidf_aabb.h (bound by extensions/ray_aabb/jit.py and extensions/pcl_aabb/jit.py)
 EXPORTED_SYMBOLS_AABB = [
     "lidf_ray_aabb_workspace_bytes", "lidf_ray_aabb_forward", "lidf_ray_aabb_pairs_count", "lidf_ray_aabb_pairs_fill",
+    "lidf_ray_aabb_ray_major_workspace_bytes", "lidf_ray_aabb_pairs_ray_major_count", "lidf_ray_aabb_pairs_ray_major_fill",
     "lidf_pcl_aabb_forward", "lidf_pcl_aabb_pair_label", "lidf_pcl_aabb_end_voxel",
     "lidf_voxelize_workspace_bytes", "lidf_voxelize_count", "lidf_voxelize_fill",
 ]
@@ -163,6 +165,12 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_ray_aabb_pairs_count.argtypes = [vp, vp, vp, vp, i64, i64, vp, sz, C.POINTER(C.c_int64), vp]
     lib.lidf_ray_aabb_pairs_fill.restype = C.c_int
     lib.lidf_ray_aabb_pairs_fill.argtypes = [vp, vp, vp, vp, i64, i64, vp, sz, i64, vp, vp, vp, vp]
+    lib.lidf_ray_aabb_ray_major_workspace_bytes.restype = sz
+    lib.lidf_ray_aabb_ray_major_workspace_bytes.argtypes = [i64, i64]
+    lib.lidf_ray_aabb_pairs_ray_major_count.restype = C.c_int
+    lib.lidf_ray_aabb_pairs_ray_major_count.argtypes = [vp, vp, vp, vp, i64, i64, vp, sz, C.POINTER(C.c_int64), vp]
+    lib.lidf_ray_aabb_pairs_ray_major_fill.restype = C.c_int
+    lib.lidf_ray_aabb_pairs_ray_major_fill.argtypes = [vp, vp, vp, vp, i64, i64, vp, sz, i64, vp, vp, vp, vp, vp]
     lib.lidf_pcl_aabb_forward.restype = C.c_int
     lib.lidf_pcl_aabb_forward.argtypes = [vp, vp, vp, vp, i64, i64, vp, vp]
     lib.lidf_pcl_aabb_pair_label.restype = C.c_int
@@ -479,7 +487,7 @@ class _LidfQuery:
                       occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, keep, *,
                       part_size, pos_encode=True, multires=8, multires_views=4, intersect_pos_type="abs", roi_inp_bbox=8,
                       roi_out_bbox=2, n_iter=2, use_sigmoid=False, offset_range=(0.0, 1.0), pcl_label_float=None,
-                      mlp_impl="auto") -> _QueryParams:
+                      mlp_impl="auto", pairs_ray_major=False) -> _QueryParams:
         """Input half of the parameter block (shared by forward and backward): shape / dtype / device checks included."""
         if roi_out_bbox != 2 or tuple(full_rgb_feat.shape[1:2]) != (32,) or occ_voxel_feat.shape[-1] != 128:
             raise RuntimeError("lidf_query supports rgb_out=32, roi_out_bbox=2, pnet_out=128 only (shipped YAMLs)")
@@ -520,6 +528,7 @@ class _LidfQuery:
         p.offset_dec = _decoder_struct(decoder_state(offset_dec), n_iter, use_sigmoid, keep, "offset_dec")
         p.prob_dec = _decoder_struct(decoder_state(prob_dec), n_iter, use_sigmoid, keep, "prob_dec")
         p.mlp_impl = MLP_IMPLS[mlp_impl]
+        p.pairs_ray_major = int(bool(pairs_ray_major))
         return p
 
     use_weight_cache = True
@@ -566,7 +575,8 @@ class _LidfQuery:
             elif int(flag_host[0]) != 0:
                 self._pending_flags = []
                 raise RuntimeError("lidf_query_forward: index out of range in miss_ray_intersect_idx / occ_vox_intersect_idx "
-                                   f"/ miss_bid (flag {int(flag_host[0])}); the affected outputs are meaningless")
+                                   f"/ miss_bid, or a pair list passed as pairs_ray_major that is not sorted by ray (flag "
+                                   f"{int(flag_host[0])}: 1 ray, 2 voxel / image, 4 order); the affected outputs are meaningless")
 
     def forward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
                 occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, *,
@@ -575,12 +585,15 @@ class _LidfQuery:
                 n_iter: int = 2, use_sigmoid: bool = False, offset_range: Sequence[float] = (0.0, 1.0),
                 pcl_label_float: Optional[torch.Tensor] = None, mlp_impl: str = "auto",
                 want_roi_feat: bool = False, save_for_backward: bool = False,
-                check_indices: bool = False) -> Dict[str, torch.Tensor]:
+                check_indices: bool = False, pairs_ray_major: bool = False) -> Dict[str, torch.Tensor]:
         """Everything LIDF.get_embedding + LIDF.get_pred compute after the ResNet / PointNet producers
         (reference src/models/pipeline.py:338-466).  ``dist`` is either the per-pair [P,2] enter/leave distances or
         the reference's dense [V,R,2] tensor.  Returns the data_dict entries of pipeline.py:460-466 (+ pred_offset).
         ``save_for_backward`` adds ``ief_iter`` (the IEF offsets between iterations, which ``backward`` needs);
-        ``check_indices`` waits for the call and raises on an out-of-range index (otherwise the next call reports it)."""
+        ``check_indices`` waits for the call and raises on an out-of-range index (otherwise the next call reports it).
+        ``pairs_ray_major``: the caller vouches that ``miss_ray_intersect_idx`` is non-decreasing (what
+        ``ray_aabb.pairs(..., order="ray")`` emits); the in-call regroup by ray is then a binary search per ray.  A list
+        that is not sorted raises like an out-of-range index (flag bit 2)."""
         capturing = torch.cuda.is_current_stream_capturing() if full_rgb_feat.is_cuda else False
         if not capturing:
             self.check_index_errors(wait=False)
@@ -591,7 +604,7 @@ class _LidfQuery:
                                part_size=part_size, pos_encode=pos_encode, multires=multires, multires_views=multires_views,
                                intersect_pos_type=intersect_pos_type, roi_inp_bbox=roi_inp_bbox, roi_out_bbox=roi_out_bbox,
                                n_iter=n_iter, use_sigmoid=use_sigmoid, offset_range=offset_range,
-                               pcl_label_float=pcl_label_float, mlp_impl=mlp_impl)
+                               pcl_label_float=pcl_label_float, mlp_impl=mlp_impl, pairs_ray_major=pairs_ray_major)
         P, R = int(p.P), int(p.R)
         f32 = dict(dtype=torch.float32, device=dev)
         out = dict(pred_offset=torch.empty(P, 1, **f32), pred_prob_end=torch.empty(P, 1, **f32),

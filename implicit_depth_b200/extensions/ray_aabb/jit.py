@@ -50,9 +50,15 @@ class _RayAabb:
         ws.record_stream(torch.cuda.current_stream(dev))
         return [mask, dist]
 
-    def pairs(self, ray_dir, voxel_bound, ray_bid, voxel_bid) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
-        """-> (occ_vox_intersect_idx [P] int64, miss_ray_intersect_idx [P] int64, intersect_dist [P,2] float32) in
-        torch.nonzero order (voxel, then ray).  Synchronises once to learn P, like torch.nonzero."""
+    def pairs(self, ray_dir, voxel_bound, ray_bid, voxel_bid, order: str = "nonzero", return_ray_start: bool = False):
+        """-> (occ_vox_intersect_idx [P] int64, miss_ray_intersect_idx [P] int64, intersect_dist [P,2] float32).
+        ``order="nonzero"``: torch.nonzero order (voxel, then ray), the reference's.  ``order="ray"``: the same pairs sorted
+        by ray, then voxel -- what ``lidf_query.forward(..., pairs_ray_major=True)`` consumes without regrouping;
+        ``return_ray_start`` appends the CSR offsets [R+1] int32.  Synchronises once to learn P, like torch.nonzero."""
+        if order == "ray":
+            return self._pairs_ray_major(ray_dir, voxel_bound, ray_bid, voxel_bid, return_ray_start)
+        if order != "nonzero" or return_ray_start:
+            raise ValueError("order must be 'nonzero' or 'ray' (ray_start comes with order='ray')")
         lib = lidf_query.lib
         R, V, ptrs = self._args(ray_dir, voxel_bound, ray_bid, voxel_bid)
         dev = ray_dir.device
@@ -74,6 +80,30 @@ class _RayAabb:
             lidf_query._raise(rc, "lidf_ray_aabb_pairs_fill")
         ws.record_stream(torch.cuda.current_stream(dev))
         return vox, ray, dist
+
+    def _pairs_ray_major(self, ray_dir, voxel_bound, ray_bid, voxel_bid, return_ray_start):
+        lib = lidf_query.lib
+        R, V, ptrs = self._args(ray_dir, voxel_bound, ray_bid, voxel_bid)
+        dev = ray_dir.device
+        nbytes = int(lib.lidf_ray_aabb_ray_major_workspace_bytes(R, V))
+        if nbytes == 0:
+            raise RuntimeError("ray_aabb: problem too large (R and V must stay below 2^31)")
+        ws = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+        n = C.c_int64(0)
+        with torch.cuda.device(dev):
+            st = self._stream(dev)
+            rc = lib.lidf_ray_aabb_pairs_ray_major_count(*ptrs, R, V, ws.data_ptr(), nbytes, C.byref(n), st)
+            lidf_query._raise(rc, "lidf_ray_aabb_pairs_ray_major_count")
+            P = int(n.value)
+            vox = torch.empty(P, dtype=torch.int64, device=dev)
+            ray = torch.empty(P, dtype=torch.int64, device=dev)
+            dist = torch.empty(P, 2, dtype=torch.float32, device=dev)
+            ray_start = torch.empty(R + 1, dtype=torch.int32, device=dev) if return_ray_start else None
+            rc = lib.lidf_ray_aabb_pairs_ray_major_fill(*ptrs, R, V, ws.data_ptr(), nbytes, P, vox.data_ptr(), ray.data_ptr(),
+                                                        dist.data_ptr(), ray_start.data_ptr() if return_ray_start else None, st)
+            lidf_query._raise(rc, "lidf_ray_aabb_pairs_ray_major_fill")
+        ws.record_stream(torch.cuda.current_stream(dev))
+        return (vox, ray, dist, ray_start) if return_ray_start else (vox, ray, dist)
 
 
 ray_aabb = _RayAabb()

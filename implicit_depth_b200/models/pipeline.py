@@ -49,6 +49,11 @@ class LIDFQueryMixin:
     """
 
     mlp_impl = "auto"   # "auto" | "tc_bf16x3" | "simt_fp32" | "tc_bf16x1" (see include/lidf_query.h)
+    # Order of the pair list compute_ray_aabb writes: "nonzero" = the reference's torch.nonzero order (voxel, then ray;
+    # bit-identical index tensors), "ray" = sorted by ray, then voxel -- the same pairs, emitted ray-major by the pair
+    # generator so that get_pred skips its regroup (every reader of the pair tensors in the reference is keyed by
+    # miss_ray_intersect_idx / occ_vox_intersect_idx and does not depend on their order).
+    pair_order = "nonzero"
 
     def get_embedding(self, data_dict):
         """Runs the two upstream producers exactly where the reference does (pipeline.py:370, :400-407) and stores
@@ -100,11 +105,13 @@ class LIDFQueryMixin:
         the reference are not produced -- their only reader is ``get_embedding`` (pipeline.py:345), replaced above."""
         from implicit_depth_b200.extensions.ray_aabb.jit import ray_aabb
         vox, ray, dist = ray_aabb.pairs(data_dict['miss_ray_dir'].contiguous(), data_dict['voxel_bound'].contiguous(),
-                                        data_dict['miss_bid'].int().contiguous(), data_dict['occ_vox_bid'].int().contiguous())
+                                        data_dict['miss_bid'].int().contiguous(), data_dict['occ_vox_bid'].int().contiguous(),
+                                        order=self.pair_order)
         if vox.shape[0] == 0:
             print('No miss ray and occ vox intersection pair', data_dict.get('item_path'))
             return False
-        data_dict.update({'occ_vox_intersect_idx': vox, 'miss_ray_intersect_idx': ray, 'intersect_dist': dist})
+        data_dict.update({'occ_vox_intersect_idx': vox, 'miss_ray_intersect_idx': ray, 'intersect_dist': dist,
+                          'pairs_ray_major': self.pair_order == 'ray'})
         return True
 
     def compute_pair_label(self, data_dict, gt_pos):
@@ -174,7 +181,8 @@ class LIDFQueryMixin:
                 data_dict['occ_vox_intersect_idx'].contiguous(), data_dict['miss_ray_intersect_idx'].contiguous(),
                 dist.contiguous())
         kw = dict(pcl_label_float=data_dict['pcl_label_float'].contiguous() if use_label else None,
-                  mlp_impl=self.mlp_impl, **self._query_kwargs(data_dict))
+                  mlp_impl=self.mlp_impl, pairs_ray_major=bool(data_dict.get('pairs_ray_major', False)),
+                  **self._query_kwargs(data_dict))
         needs_grad = torch.is_grad_enabled() and (
             args[0].requires_grad or args[1].requires_grad
             or any(p.requires_grad for p in self.offset_dec.parameters())

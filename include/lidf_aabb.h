@@ -48,6 +48,18 @@ int lidf_ray_aabb_pairs_fill(const float* ray_dir, const float* voxel_bound, con
                              int64_t P, int64_t* pair_vox /*[P]*/, int64_t* pair_ray /*[P]*/, float* pair_dist /*[P,2]*/,
                              lidf_stream_t stream);
 
+/* The same pairs sorted by ray, then voxel (every ray's pairs adjacent, ascending voxel id): the order the consumer of
+ * the list works in -- lidf_query_forward with LidfQueryParams::pairs_ray_major = 1 skips its regroup.  Same two-step
+ * protocol with its own workspace; step 2 can also hand out the CSR offsets ray_start [R+1] int32 (NULL to skip). */
+size_t lidf_ray_aabb_ray_major_workspace_bytes(int64_t R, int64_t V);
+int lidf_ray_aabb_pairs_ray_major_count(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                        const int32_t* voxel_bid, int64_t R, int64_t V, void* workspace,
+                                        size_t workspace_bytes, int64_t* n_pairs_host, lidf_stream_t stream);
+int lidf_ray_aabb_pairs_ray_major_fill(const float* ray_dir, const float* voxel_bound, const int32_t* ray_bid,
+                                       const int32_t* voxel_bid, int64_t R, int64_t V, void* workspace,
+                                       size_t workspace_bytes, int64_t P, int64_t* pair_vox /*[P]*/, int64_t* pair_ray /*[P]*/,
+                                       float* pair_dist /*[P,2]*/, int32_t* ray_start /*[R+1] or NULL*/, lidf_stream_t stream);
+
 /* dense drop-in: mask [V,N] int32 */
 int lidf_pcl_aabb_forward(const float* pcl_pos /*[N,3]*/, const float* voxel_bound /*[V,6]*/,
                           const int32_t* pcl_bid /*[N]*/, const int32_t* voxel_bid /*[V]*/, int64_t N, int64_t V,

@@ -33,6 +33,13 @@ size_t lidf_pointnet_workspace_bytes(int64_t N, int64_t V);
 int lidf_pointnet_forward(const LidfPointNet* w, const float* inp_feat, const int64_t* vox2point_idx, int64_t N, int64_t V,
                           float* occ_voxel_feat, void* workspace, size_t workspace_bytes, lidf_stream_t stream);
 
+/* Same call with the engine of the two 128 -> 128 per-point layers (97 % of the MACs) chosen explicitly:
+ * LIDF_MLP_AUTO / LIDF_MLP_TC_BF16X3 = tcgen05 tensor cores, split-bf16 operands with fp32 accumulation (the decoder's
+ * arithmetic, ~2^-16 relative), LIDF_MLP_SIMT_FP32 = fp32 FMA kernels.  lidf_pointnet_forward is the AUTO form. */
+int lidf_pointnet_forward_impl(const LidfPointNet* w, const float* inp_feat, const int64_t* vox2point_idx, int64_t N, int64_t V,
+                               float* occ_voxel_feat, void* workspace, size_t workspace_bytes, int32_t mlp_impl,
+                               lidf_stream_t stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LIDF_QUERY_ABI_VERSION 3
+#define LIDF_QUERY_ABI_VERSION 4
 
 /* fixed by the shipped YAMLs (train_lidf.yaml:36-57): rgb_out 32 x roi_out_bbox 2^2, pnet_out 128, imnet_gf 64 */
 #define LIDF_RGB_CH 32
@@ -120,6 +120,11 @@ typedef struct LidfQueryParams {
   size_t weight_cache_bytes;    /* packed decoder weights (k-major fp32 copies, bf16 hi|lo MMA streams, folded biases)   */
   int32_t weight_cache_valid;   /* between calls.  0: this call packs into it; 1: the ~20 packing launches are skipped   */
                                 /* (the caller vouches that no decoder tensor changed since the call that filled it).    */
+  /* ABI 4: */
+  int32_t pairs_ray_major;      /* 1: the caller vouches that pair_ray is non-decreasing (the order lidf_ray_aabb_pairs_ray_major_*
+                                 * emits: by ray, then voxel).  The voxel-major -> ray-major regroup (count / scan / scatter /
+                                 * segment sort over all P pairs) is replaced by one binary search per ray; outputs are the same
+                                 * tensors at the same pair indices.  A list that is not sorted sets bit 2 of *index_error. */
 } LidfQueryParams;
 
 /* Gradients of one decoder's parameters: fp32 device buffers with the shapes of the LidfDecoder tensors; every buffer is

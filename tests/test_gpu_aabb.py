@@ -40,6 +40,14 @@ def _check_ray(ray_dir, vb, rb, xb, want_mask, want_dist, want_pairs):
     assert vox.dtype == torch.int64 and ray.dtype == torch.int64
     assert np.array_equal(vox.cpu().numpy(), want_pairs[0]) and np.array_equal(ray.cpu().numpy(), want_pairs[1])
     assert np.array_equal(bits(pd.cpu().numpy()), bits(want_pairs[2]))
+    # ray-major list (lidf_ray_aabb_pairs_ray_major_*): the same pairs, stably re-sorted by ray (voxel stays ascending
+    # within a ray because the nonzero order is voxel-major), bit-identical distances, plus its CSR offsets
+    vox2, ray2, pd2, start = ray_aabb.pairs(*args, order="ray", return_ray_start=True)
+    o = np.argsort(want_pairs[1], kind="stable")
+    assert np.array_equal(vox2.cpu().numpy(), want_pairs[0][o]) and np.array_equal(ray2.cpu().numpy(), want_pairs[1][o])
+    assert np.array_equal(bits(pd2.cpu().numpy()), bits(want_pairs[2][o]))
+    R = ray_dir.shape[0]
+    assert start.dtype == torch.int32 and np.array_equal(start.cpu().numpy(), np.searchsorted(want_pairs[1][o], np.arange(R + 1)))
 
 
 @pytest.mark.parametrize("name", AABB_CASES)
@@ -95,6 +103,8 @@ def test_aabb_empty_inputs_and_no_hits():
         assert tuple(mask.shape) == (V, R) and tuple(dist.shape) == (V, R, 2)
         vox, ray, pd = ray_aabb.pairs(f(R, 3), f(V, 6), i(R), i(V))
         assert vox.numel() == 0 and ray.numel() == 0 and tuple(pd.shape) == (0, 2)
+        vox, ray, pd, start = ray_aabb.pairs(f(R, 3), f(V, 6), i(R), i(V), order="ray", return_ray_start=True)
+        assert vox.numel() == 0 and ray.numel() == 0 and tuple(pd.shape) == (0, 2) and int(start.abs().sum()) == 0
         assert tuple(pcl_aabb.forward(f(R, 3), f(V, 6), i(R), i(V)).shape) == (V, R)
     # rays and voxels of different images never pair up
     d = torch.tensor([[0., 0., 1.]] * 2000, device="cuda")
@@ -127,6 +137,10 @@ def test_ray_aabb_pairs_equal_nonzero_of_dense_at_config2_size():
     assert torch.equal(idx[:, 0], vox) and torch.equal(idx[:, 1], ray)
     assert torch.equal(dist[vox, ray].view(torch.int32), pd.view(torch.int32))   # pipeline.py:345, bit patterns
     assert torch.equal(rb[ray], xb[vox]) and bool((pd[:, 1] >= pd[:, 0]).all())
+    vox2, ray2, pd2, start = ray_aabb.pairs(rd, vb, rb, xb, order="ray", return_ray_start=True)      # ray-major: a stable re-sort
+    o = torch.sort(ray, stable=True).indices
+    assert torch.equal(vox2, vox[o]) and torch.equal(ray2, ray[o]) and torch.equal(pd2.view(torch.int32), pd[o].view(torch.int32))
+    assert torch.equal(start.long(), torch.searchsorted(ray2, torch.arange(rd.shape[0] + 1, device="cuda")))
     sel_v = torch.arange(0, vb.shape[0], 37, device="cuda"); sel_r = torch.arange(0, rd.shape[0], 41, device="cuda")
     om, od = A.ray_aabb_dense(rd[sel_r].cpu().numpy(), vb[sel_v].cpu().numpy(), rb[sel_r].cpu().numpy(), xb[sel_v].cpu().numpy())
     assert np.array_equal(mask[sel_v][:, sel_r].cpu().numpy(), om)
@@ -188,6 +202,22 @@ def test_pipeline_mixin_real_geometry_chain_vs_oracle():
     start = np.concatenate((vox, [0]))[dd["max_pair_id"].cpu().numpy()]
     want_end = A.pcl_end_voxel(dd["pred_pos"].cpu().numpy(), d["voxel_bound"].numpy(), d["miss_bid"].numpy(), d["occ_vox_bid"].numpy(), start)
     assert np.array_equal(end.cpu().numpy(), want_end)
+    # the same chain with the pair list emitted ray-major (pair_order = "ray": no regroup inside get_pred): per-ray results
+    # bit-identical, per-pair results a permutation, labels / end voxels follow the permuted index tensors
+    lidf.pair_order = "ray"
+    d2 = {k: (v.cuda() if isinstance(v, torch.Tensor) else v) for k, v in d.items()
+          if k not in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist")}
+    with torch.no_grad():
+        assert lidf.compute_ray_aabb(d2) is True and d2["pairs_ray_major"] is True
+        lidf.get_pred(d2, "test", 0)
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    lidf_query.check_index_errors()
+    o = torch.sort(dd["miss_ray_intersect_idx"], stable=True).indices
+    assert torch.equal(d2["miss_ray_intersect_idx"], dd["miss_ray_intersect_idx"][o]) and torch.equal(d2["occ_vox_intersect_idx"], dd["occ_vox_intersect_idx"][o])
+    assert torch.equal(d2["pred_pos"], dd["pred_pos"]) and torch.equal(d2["pred_prob_end"], dd["pred_prob_end"][o])
+    lidf.compute_pair_label(d2, gt_pos)
+    assert torch.equal(d2["pcl_label_float"], dd["pcl_label_float"][o])
+    assert torch.equal(refine.refine_end_voxel(d2, d2["pred_pos"]), end)
 
 
 # ---------------------------------------------------------------------------------------------------------------

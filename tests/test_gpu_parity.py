@@ -552,22 +552,30 @@ def test_forward_host_async_back_to_back_batches():
 
 # ---------------------------------------------------------------------------------------------------------------
 # PointNet2Stage forward (the producer of occ_voxel_feat)
+# engines of the two 128 -> 128 per-point layers: fp32 FMA, and tcgen05 with split-bf16 operands (the default)
+PN_ENGINES = [("simt_fp32", TOL_FP32), ("auto", 2e-4)]
+
+
+@pytest.mark.parametrize("engine,tol", PN_ENGINES)
 @pytest.mark.parametrize("name", ["pointnet_2000x60", "pointnet_257x3"])
-def test_pointnet_golden_reference_module_outputs(name):
+def test_pointnet_golden_reference_module_outputs(name, engine, tol):
     from test_oracle import load_pointnet
     from implicit_depth_b200.models.pointnet import PointNet2Stage
     w, inp, idx, V, ref = load_pointnet(name)
     net = PointNet2Stage(input_channels=6, output_channels=128, gf_dim=32).cuda().eval()
     net.load_state_dict(w)                                   # reference checkpoint keys
+    net.mlp_impl = engine
     with torch.no_grad():
         out = net(inp.cuda(), idx.cuda())
     assert out.shape == ref.shape
-    assert rel_err(out.cpu(), ref) < TOL_FP32
+    assert rel_err(out.cpu(), ref) < tol, rel_err(out.cpu(), ref)
 
 
+@pytest.mark.parametrize("engine,tol", PN_ENGINES)
 @pytest.mark.parametrize("N,V,sorted_idx", [(1, 1, True), (63, 5, False), (64, 64, True), (65, 2, False), (5000, 300, True),
-                                            (100000, 2048, True), (3000, 40, False), (0, 3, True)])
-def test_pointnet_vs_oracle_seeded(N, V, sorted_idx):
+                                            (100000, 2048, True), (3000, 40, False), (0, 3, True), (127, 9, True), (129, 9, False),
+                                            (128 * 149 + 5, 700, True)])
+def test_pointnet_vs_oracle_seeded(N, V, sorted_idx, engine, tol):
     from implicit_depth_b200.models.pointnet import pointnet_forward
     g = torch.Generator().manual_seed(N + V)
     w = {}
@@ -580,9 +588,13 @@ def test_pointnet_vs_oracle_seeded(N, V, sorted_idx):
     if sorted_idx:
         idx = idx.sort().values                              # long runs of equal voxel ids (the run-reduced path)
     want = O.pointnet2stage_forward(w, inp, idx, V)
-    got = pointnet_forward(_cuda(w), inp.cuda(), idx.cuda(), V)
+    got = pointnet_forward(_cuda(w), inp.cuda(), idx.cuda(), V, mlp_impl=engine)
     assert got.shape == (V, 128)
-    assert rel_err(got.cpu(), want) < TOL_FP32, rel_err(got.cpu(), want)
+    assert rel_err(got.cpu(), want) < tol, rel_err(got.cpu(), want)
+    if engine == "auto" and N:                               # the two engines agree far inside the fp32 tolerance
+        simt = pointnet_forward(_cuda(w), inp.cuda(), idx.cuda(), V, mlp_impl="simt_fp32")
+        print("pointnet tc vs simt", N, V, rel_err(got.cpu(), simt.cpu()))
+        assert rel_err(got.cpu(), simt.cpu()) < 1e-4
     if N:                                                    # voxels that own no point: relu(b) through the voxel layers only
         empty = torch.ones(V, dtype=torch.bool); empty[idx] = False
         if empty.any():
@@ -792,3 +804,43 @@ def test_graphed_forward_replays_bit_identically_and_follows_weight_updates():
     got3 = run()
     torch.cuda.synchronize()
     assert torch.equal(got3["pred_offset"], want3["pred_offset"]) and not torch.equal(want3["pred_offset"], want2["pred_offset"])
+
+
+@pytest.mark.parametrize("engine", ["auto", "simt_fp32"])
+def test_pairs_ray_major_hint_same_outputs_without_the_regroup(engine):
+    """LidfQueryParams::pairs_ray_major (ABI 4): the same pairs handed over sorted by ray (what ray_aabb.pairs(order="ray")
+    emits) take the binary-search CSR instead of the count / scan / scatter / sort regroup.  Rows reach the decoder tiles in
+    the same order either way, so every output is bit-identical under the permutation; ragged rays, rays without a pair and
+    the GT-label branch included.  A list that is not sorted is reported, not silently mis-grouped."""
+    from implicit_depth_b200.synthetic import make_inputs
+    lq = _lq()
+    d = _cuda(make_inputs(2, 24, 40, 9, V_img=48, seed=21, ragged=True))
+    g = torch.Generator().manual_seed(22)
+    off = _cuda(O.init_decoder("IEF", 385, mode="trained", generator=g))
+    prob = _cuda(O.init_decoder("IMNET", 385, mode="trained", generator=g))
+    ins = [d[k] for k in lq.INPUT_KEYS]
+    iv, ir, idist = lq.INPUT_KEYS.index("occ_vox_intersect_idx"), lq.INPUT_KEYS.index("miss_ray_intersect_idx"), lq.INPUT_KEYS.index("intersect_dist")
+    assert not bool((ins[ir][1:] >= ins[ir][:-1]).all())               # the fixture is voxel-major, like the reference's list
+    P = ins[ir].shape[0]
+    label = (torch.rand(P, generator=torch.Generator().manual_seed(3)) < 0.1).float().cuda()
+    o = torch.sort(ins[ir], stable=True).indices
+    ins2 = list(ins)
+    ins2[iv], ins2[ir], ins2[idist] = ins[iv][o].contiguous(), ins[ir][o].contiguous(), ins[idist][o].contiguous()
+    for lab in (None, label):
+        kw = dict(part_size=d["part_size"], mlp_impl=engine, want_roi_feat=True)
+        want = lq.forward(*ins, off, prob, pcl_label_float=lab, **kw)
+        lq.launch_count(reset=True)
+        lq.forward(*ins, off, prob, pcl_label_float=lab, **kw)
+        n_regroup = lq.launch_count()
+        lq.launch_count(reset=True)
+        got = lq.forward(*ins2, off, prob, pcl_label_float=None if lab is None else lab[o].contiguous(), pairs_ray_major=True,
+                         check_indices=True, **kw)
+        assert lq.launch_count() < n_regroup                           # fewer launches: no count / scan x3 / fill / sort
+        for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax"):
+            assert torch.equal(got[k], want[k][o]), k
+        assert torch.equal(got["pred_pos"], want["pred_pos"]) and torch.equal(got["roi_feat_per_ray"], want["roi_feat_per_ray"])
+        inv = torch.empty_like(o); inv[o] = torch.arange(P, device="cuda")
+        wid = want["max_pair_id"]
+        assert torch.equal(got["max_pair_id"], torch.where(wid < P, inv[wid.clamp(max=P - 1)], wid))
+    with pytest.raises(RuntimeError, match="not sorted by ray"):
+        lq.forward(*ins, off, prob, part_size=d["part_size"], mlp_impl=engine, pairs_ray_major=True, check_indices=True)

@@ -27,7 +27,7 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert sorted(os.listdir(os.path.join(REPO, "include"))) == ["lidf_aabb.h", "lidf_pointnet.h", "lidf_query.h"]
     for sym in declared:
         assert hasattr(lib, sym), sym
-    assert lib.lidf_query_abi_version() == 3
+    assert lib.lidf_query_abi_version() == 4
     assert lib.lidf_query_backward(None, None) == -1 and lib.lidf_query_backward_workspace_bytes(None) == 0
     assert lib.lidf_query_error_string(-2).decode().startswith("unsupported")
     # argument validation needs no GPU: NULL params / empty problem

@@ -1,10 +1,10 @@
 #!/bin/bash
 # One-rep A/B of the energy-experiment builds (build/dbg/lib_<tag>.so from tools/build_variants.sh): decoder-kernel time,
-# step time, SM clock.  Usage: bash tools/ab_exp.sh c3 base e1 e2 ...   ("base" = the product library)
+# step time, SM clock.  Usage: bash tools/ab_exp.sh c3 base e1 e2 ...   ("new" = the product library in csrc/)
 WL=$1; shift
 mkdir -p gpurun_out
 for tag in "$@"; do
-  if [ "$tag" = base ]; then unset LIDF_QUERY_LIB; else export LIDF_QUERY_LIB=$PWD/build/dbg/lib_$tag.so; fi
+  if [ "$tag" = new ]; then unset LIDF_QUERY_LIB; else export LIDF_QUERY_LIB=$PWD/build/dbg/lib_$tag.so; fi
   echo -n "$tag: "
   timeout 300 python bench.py --workload $WL --steps 4 --warmup 3 --no-e2e --no-cpu-baseline --no-torch-gpu-baseline 2>&1 | tail -1 | python -c "
 import sys, json
