@@ -194,6 +194,10 @@ def main():
     ap.add_argument("--engine", default="auto", choices=["auto", "simt_fp32", "tc_bf16x3", "tc_bf16x1"])
     ap.add_argument("--offdec", default="IEF", choices=["IEF", "IMNET"])
     ap.add_argument("--cpu-sample-pairs", type=int, default=1 << 19)
+    ap.add_argument("--pair-order", default="nonzero", choices=["nonzero", "ray"],
+                    help="order of the synthetic pair list: 'nonzero' = the reference's torch.nonzero order (voxel-major; "
+                         "the call regroups by ray inside the timed region: the default and the headline), 'ray' = the list "
+                         "as lidf_ray_aabb_pairs_ray_major_* emits it (sorted by ray; LidfQueryParams::pairs_ray_major: no regroup)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stage2", action="store_true",
@@ -236,6 +240,12 @@ def main():
     off, prob = make_decoders(dev, args.offdec)
     P = int(d["occ_vox_intersect_idx"].shape[0]); R = int(d["miss_ray_dir"].shape[0])
     kw = dict(part_size=d["part_size"], mlp_impl=args.engine)
+    if args.pair_order == "ray":                                   # what compute_ray_aabb hands over with pair_order = "ray"
+        o = torch.sort(d["miss_ray_intersect_idx"], stable=True).indices
+        for k in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist"):
+            d[k] = d[k][o].contiguous()
+        del o
+        kw["pairs_ray_major"] = True
     ins = [d[k] for k in lidf_query.INPUT_KEYS]
     if args.train:
         return run_train(args, d, ins, off, prob, kw, dev, rank, world, local)
@@ -384,7 +394,8 @@ def main():
                                      f"decoders {args.offdec}(n_iter 2)+IMNET, trained-like random weights",
                             engine=args.engine, cuda_graph=bool(args.cuda_graph), l2=("inputs (>3 GB/step) exceed the 126 MB L2; no explicit flush" if in_bytes > 126e6 else
                                 f"inputs ({in_bytes / 1e6:.1f} MB) fit in the 126 MB L2: a 192 MB buffer is written between steps to flush it"),
-                            pair_order="reference voxel-major (regroup inside the timed region)"),
+                            pair_order="reference voxel-major (regroup inside the timed region)" if args.pair_order == "nonzero" else
+                                       "ray-major, as lidf_ray_aabb_pairs_ray_major_* emits it (pairs_ray_major: no regroup)"),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
     progress("cpu baseline done")
     if not args.no_torch_gpu_baseline and world == 1:

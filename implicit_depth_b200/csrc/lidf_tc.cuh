@@ -1028,13 +1028,21 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
 // ------------------------------------------------------------------------------------------------ per-ray row prep
 // T[ray][512] = [roi(128) | PE(dir)(27) | 0 x 5] W_row^T + bias for both decoders (the per-ray layer-1 term) on the tensor
 // cores with the same split-bf16 arithmetic: 128 rays per tile, K = 160 (10 k-steps), N = 4 x 128 (one TMEM quarter per
-// N-chunk).  Simple tile-serial structure (operand build -> 4 x MMA chunk -> epilogue overlapping the next chunk): the
-// whole job is ~1 ms.  8 row warps (TMEM quadrant q, column half h), warp 8 = MMA issuer, warp 9 = weight loader.
+// N-chunk).  8 row warps (TMEM quadrant q, column half h), warp 8 = MMA issuer, warp 9 = weight loader.
+// Software pipeline over tiles (the kernel moves 2.5 KB per ray: HBM-bound, so the point is to keep loads, MMAs and
+// stores of neighbouring tiles in flight together):
+//   row warps : build(t + 1) into the other operand buffer  |  epilogue(t): 4 x [TMEM quarter -> + bias -> 2 KB rows to HBM]
+//   issuer    : MMAs of tile t + 1, chunk c, start as soon as epilogue(t) has drained quarter c (d_free[c])
+//   loader    : streams the 320 KB of packed weights per tile through a 4 x 8 KB ring (slot / parity from running counters)
+// Output rows leave through a per-warp shared-memory transpose tile (16-byte chunks XOR-swizzled by row: conflict-free both
+// ways) so that 8 lanes write one 128-byte row segment -- a lane storing 16 bytes into its own row touches 32 half-filled
+// sectors per instruction.
 #define RP_KSTEPS 10
 #define RP_ROW_WARPS 8
 #define RP_THREADS ((RP_ROW_WARPS + 2) * 32)
 #define RP_A_PART_BYTES (RP_KSTEPS * 4096)
-#define RP_STAGES 5
+#define RP_STAGES 4               // ring of 4 x 8 KB (one k-step per fill)
+#define RP_FILLS_PER_TILE 40
 
 struct TcRowPrepArgs {
   const float* feat;               // [rows][128] ROI feature per ray
@@ -1047,11 +1055,11 @@ struct TcRowPrepArgs {
   const int* n_list;
 };
 struct TcRowPrepSmem {
-  uint8_t w[RP_STAGES][TC_STAGE_BYTES];
-  uint8_t a[2][RP_A_PART_BYTES];     // [hi|lo][kstep(10)][kgroup(2)][128 rows][16 B]
-  float bias[512];
+  uint8_t w[RP_STAGES][TC_CHUNK_BYTES];
+  uint8_t a[2][2][RP_A_PART_BYTES];  // [tile parity][hi|lo][kstep(10)][kgroup(2)][128 rows][16 B]
+  float stage[RP_ROW_WARPS][32 * 32];   // per-warp transpose tile of the epilogue: [row][8 x 16 B, chunk ^ (row & 7)]
   uint64_t w_full[RP_STAGES], w_empty[RP_STAGES];
-  uint64_t a_ready, a_free, d_full[4], d_free[4];
+  uint64_t a_ready[2], a_free[2], d_full[4], d_free[4];
   uint32_t tmem_base;
 };
 
@@ -1074,11 +1082,9 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   TcRowPrepSmem& S = *reinterpret_cast<TcRowPrepSmem*>(smem_raw);
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-  for (int i = tid; i < 512; i += RP_THREADS) S.bias[i] = a.bias ? a.bias[i] : 0.f;
   if (tid == 0) {
     for (int i = 0; i < RP_STAGES; ++i) { tc::mbar_init(&S.w_full[i], 1); tc::mbar_init(&S.w_empty[i], 1); }
-    tc::mbar_init(&S.a_ready, RP_ROW_WARPS);
-    tc::mbar_init(&S.a_free, 1);
+    for (int i = 0; i < 2; ++i) { tc::mbar_init(&S.a_ready[i], RP_ROW_WARPS); tc::mbar_init(&S.a_free[i], 1); }
     for (int i = 0; i < 4; ++i) { tc::mbar_init(&S.d_full[i], 1); tc::mbar_init(&S.d_free[i], RP_ROW_WARPS); }
     tc::fence_barrier_init();
   }
@@ -1092,16 +1098,16 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
   const int n_my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == RP_ROW_WARPS + 1) {
-    // ---- weight loader: 20 fills of 16 KB per tile (4 N-chunks x 5), ring of 5 -> slot = fill % 5, 4 rotations / tile
+    // ---- weight loader: 40 fills of 8 KB per tile (4 N-chunks x 10 k-steps), ring of 4; slot / wrap count run over all tiles
     if (tc::elect_one()) {
+      uint32_t slot = 0, use = 0;                      // use = how many times the ring has wrapped (parity of the slot's phase)
       for (int t = 0; t < n_my_tiles; ++t) {
-#pragma unroll
-        for (int f = 0; f < 20; ++f) {
-          const int slot = f % RP_STAGES;
-          const uint32_t par = (uint32_t)((f / RP_STAGES) & 1);
-          if (t > 0 || f >= RP_STAGES) tc::mbar_wait(&S.w_empty[slot], par ^ 1u);
-          tc::mbar_arrive_expect_tx(&S.w_full[slot], TC_STAGE_BYTES);
-          tc::bulk_g2s(S.w[slot], a.wstream + (size_t)f * TC_STAGE_BYTES, TC_STAGE_BYTES, &S.w_full[slot]);
+#pragma unroll 1
+        for (int f = 0; f < RP_FILLS_PER_TILE; ++f) {
+          if (use > 0) tc::mbar_wait(&S.w_empty[slot], (use - 1u) & 1u);
+          tc::mbar_arrive_expect_tx(&S.w_full[slot], TC_CHUNK_BYTES);
+          tc::bulk_g2s(S.w[slot], a.wstream + (size_t)f * TC_CHUNK_BYTES, TC_CHUNK_BYTES, &S.w_full[slot]);
+          if (++slot == RP_STAGES) { slot = 0; ++use; }
         }
       }
     }
@@ -1110,65 +1116,69 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
     if (tc::elect_one()) {
       constexpr uint32_t idesc = tc::make_idesc(128);
       const uint64_t wd = tc::make_bdesc(tc::smem_u32(S.w[0]), 2048u, 128u);
-      const uint64_t ad = tc::make_bdesc(tc::smem_u32(S.a[0]), 2048u, 128u);
+      uint32_t slot = 0, use = 0;
       for (int t = 0; t < n_my_tiles; ++t) {
-        const uint32_t ph = (uint32_t)t & 1u;
-        tc::mbar_wait(&S.a_ready, ph);
+        const uint32_t buf = (uint32_t)t & 1u, uph = ((uint32_t)t >> 1) & 1u, ph = (uint32_t)t & 1u;
+        const uint64_t ad = tc::make_bdesc(tc::smem_u32(S.a[buf][0]), 2048u, 128u);
+        tc::mbar_wait(&S.a_ready[buf], uph);
         tc::fence_after_sync();
-#pragma unroll
+#pragma unroll 1
         for (int c = 0; c < 4; ++c) {
           if (t > 0) { tc::mbar_wait(&S.d_free[c], ph ^ 1u); tc::fence_after_sync(); }
-#pragma unroll
-          for (int j = 0; j < 5; ++j) {
-            const int f = 5 * c + j, slot = f % RP_STAGES;
-            tc::mbar_wait(&S.w_full[slot], (uint32_t)((f / RP_STAGES) & 1));
-#pragma unroll
-            for (int i = 0; i < 2; ++i) {
-              const int ks = 2 * j + i;
-              const uint64_t bhi = wd + ((uint32_t)(slot * TC_STAGE_BYTES + i * TC_CHUNK_BYTES) >> 4);
-              const uint64_t ahi = ad + ((uint32_t)(ks * 4096) >> 4);
-              tc::mma_ss(tmem + 128 * c, ahi, bhi, idesc, ks == 0 ? 0u : 1u);
-              if (NPROD == 3) {
-                tc::mma_ss(tmem + 128 * c, ahi + ((uint32_t)RP_A_PART_BYTES >> 4), bhi, idesc, 1u);
-                tc::mma_ss(tmem + 128 * c, ahi, bhi + (4096u >> 4), idesc, 1u);
-              }
+#pragma unroll 1
+          for (int ks = 0; ks < RP_KSTEPS; ++ks) {
+            tc::mbar_wait(&S.w_full[slot], use & 1u);
+            const uint64_t bhi = wd + ((uint32_t)(slot * TC_CHUNK_BYTES) >> 4);
+            const uint64_t ahi = ad + ((uint32_t)(ks * 4096) >> 4);
+            tc::mma_ss(tmem + 128 * c, ahi, bhi, idesc, ks == 0 ? 0u : 1u);
+            if (NPROD == 3) {
+              tc::mma_ss(tmem + 128 * c, ahi + ((uint32_t)RP_A_PART_BYTES >> 4), bhi, idesc, 1u);
+              tc::mma_ss(tmem + 128 * c, ahi, bhi + (4096u >> 4), idesc, 1u);
             }
             tc::commit(&S.w_empty[slot]);
+            if (++slot == RP_STAGES) { slot = 0; ++use; }
           }
           tc::commit(&S.d_full[c]);
         }
-        tc::commit(&S.a_free);
+        tc::commit(&S.a_free[buf]);
       }
     }
   } else {
-    // ---- row warps: operand build + epilogue
+    // ---- row warps: operand build (one tile ahead) + epilogue
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
-    const uint32_t a_hi = tc::smem_u32(S.a[0]), a_lo = tc::smem_u32(S.a[1]);
-    for (int t = 0; t < n_my_tiles; ++t) {
+    auto build = [&](int t) {
       const int tile = (int)blockIdx.x + t * (int)gridDim.x;
       const int64_t row0 = (int64_t)tile * 128;
-      const uint32_t ph = (uint32_t)t & 1u;
-      if (t > 0) tc::mbar_wait(&S.a_free, ph ^ 1u);
-      // feature part (k-steps 0-7): one instruction = 8 rows x one k-step, 4 lanes x 16 B per row
+      const uint32_t buf = (uint32_t)t & 1u;
+      const uint32_t a_hi = tc::smem_u32(S.a[buf][0]), a_lo = tc::smem_u32(S.a[buf][1]);
+      if (t >= 2) tc::mbar_wait(&S.a_free[buf], (((uint32_t)t >> 1) - 1u) & 1u);   // MMAs of tile t - 2 have read this buffer
+      // feature part (k-steps 0-7): one instruction = 8 rows x one k-step, 4 lanes x 16 B per row; 8 loads in flight per thread
       {
         const int r8 = lane >> 2, j4 = lane & 3;
-#pragma unroll 4
-        for (int it = warp; it < 16 * 8; it += RP_ROW_WARPS) {
-          const int rg = it >> 3, ks = it & 7;
-          const int r = 8 * rg + r8;
-          float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-          if (row0 + r < n_rows) {
-            const int64_t src = a.row_list ? (int64_t)a.row_list[row0 + r] : row0 + r;
-            v = __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)src * 128 + 16 * ks) + j4);
+#pragma unroll 1
+        for (int it0 = warp; it0 < 16 * 8; it0 += 8 * RP_ROW_WARPS) {
+          float4 v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int it = it0 + u * RP_ROW_WARPS, rg = it >> 3, ks = it & 7, r = 8 * rg + r8;
+            v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row0 + r < n_rows) {
+              const int64_t src = a.row_list ? (int64_t)a.row_list[row0 + r] : row0 + r;
+              v[u] = __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)src * 128 + 16 * ks) + j4);
+            }
           }
-          uint32_t h0, l0, h1, l1;
-          tc::split2(v.x, v.y, h0, l0);
-          tc::split2(v.z, v.w, h1, l1);
-          const uint32_t off = (uint32_t)(ks * 4096 + (j4 >> 1) * 2048 + r * 16 + 8 * (j4 & 1));
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
-          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + off), "r"(l0), "r"(l1) : "memory");
+#pragma unroll
+          for (int u = 0; u < 8; ++u) {
+            const int it = it0 + u * RP_ROW_WARPS, rg = it >> 3, ks = it & 7, r = 8 * rg + r8;
+            uint32_t h0, l0, h1, l1;
+            tc::split2(v[u].x, v[u].y, h0, l0);
+            tc::split2(v[u].z, v[u].w, h1, l1);
+            const uint32_t off = (uint32_t)(ks * 4096 + (j4 >> 1) * 2048 + r * 16 + 8 * (j4 & 1));
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_hi + off), "r"(h0), "r"(h1) : "memory");
+            asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(a_lo + off), "r"(l0), "r"(l1) : "memory");
+          }
         }
       }
       // PE(dir) part (k-steps 8, 9): Embedder order [x, sin f0 x, cos f0 x, sin f1 x, ...], f = 1, 2, 4, 8; 27 values
@@ -1205,35 +1215,54 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
       }
       tc::fence_proxy_async();
       __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&S.a_ready);
-      // epilogue: this thread owns columns [64 h, 64 h + 64) of every N-chunk of its row
-      const bool live = row0 + row < n_rows;
-      float* orow = a.out + (size_t)(live && a.row_list ? (int64_t)a.row_list[row0 + row] : row0 + row) * 512 + 64 * h;
+      if (lane == 0) tc::mbar_arrive(&S.a_ready[buf]);
+    };
+    if (n_my_tiles > 0) build(0);
+    for (int t = 0; t < n_my_tiles; ++t) {
+      if (t + 1 < n_my_tiles) build(t + 1);
+      const int tile = (int)blockIdx.x + t * (int)gridDim.x;
+      const int64_t row0 = (int64_t)tile * 128;
+      const uint32_t ph = (uint32_t)t & 1u;
+      // epilogue: this thread pulls columns [64 h, 64 h + 64) of every N-chunk of its row out of TMEM; the warp transposes
+      // them through its staging tile so that lane l stores 16 bytes of row 4 i + (l >> 3), i = 0..7 (8 lanes = 128 B of a row)
+      float* orows[8];
+      bool olive[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t rr = row0 + 32 * q + 4 * i + (lane >> 3);
+        olive[i] = rr < n_rows;
+        orows[i] = a.out + (size_t)(olive[i] && a.row_list ? (int64_t)a.row_list[rr] : rr) * 512 + 64 * h + 4 * (lane & 7);
+      }
+      float* const stg = S.stage[warp];
 #pragma unroll 1
       for (int c = 0; c < 4; ++c) {
         tc::mbar_wait(&S.d_full[c], ph);
         tc::fence_after_sync();
-#pragma unroll
-        for (int k = 0; k < 2; ++k) {
-          uint32_t r[32];
-          tc::tmem_ld32(lane_addr + 128 * c + 64 * h + 32 * k, r);
-          tc::wait_ld();
-          if (live) {
-            const float* bp = &S.bias[128 * c + 64 * h + 32 * k];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-              float4 o;
-              o.x = __uint_as_float(r[4 * i + 0]) + bp[4 * i + 0];
-              o.y = __uint_as_float(r[4 * i + 1]) + bp[4 * i + 1];
-              o.z = __uint_as_float(r[4 * i + 2]) + bp[4 * i + 2];
-              o.w = __uint_as_float(r[4 * i + 3]) + bp[4 * i + 3];
-              *reinterpret_cast<float4*>(orow + 128 * c + 32 * k + 4 * i) = o;
-            }
-          }
-        }
+        uint32_t r0[32], r1[32];
+        tc::tmem_ld32(lane_addr + 128 * c + 64 * h, r0);
+        tc::tmem_ld32(lane_addr + 128 * c + 64 * h + 32, r1);
+        tc::wait_ld();
         tc::fence_before_sync();
         __syncwarp();
-        if (lane == 0) tc::mbar_arrive(&S.d_free[c]);
+        if (lane == 0) tc::mbar_arrive(&S.d_free[c]);                          // the quarter is in registers: release it first
+#pragma unroll
+        for (int k = 0; k < 2; ++k) {
+          const uint32_t* r = k ? r1 : r0;
+#pragma unroll
+          for (int j = 0; j < 8; ++j)
+            *reinterpret_cast<uint4*>(stg + lane * 32 + 4 * (j ^ (lane & 7))) = make_uint4(r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+          __syncwarp();
+          const float4 b4 = a.bias ? __ldg(reinterpret_cast<const float4*>(a.bias + 128 * c + 64 * h + 32 * k) + (lane & 7))
+                                   : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int rr = 4 * i + (lane >> 3);
+            float4 o = *reinterpret_cast<const float4*>(stg + rr * 32 + 4 * ((lane & 7) ^ (rr & 7)));
+            o.x += b4.x; o.y += b4.y; o.z += b4.z; o.w += b4.w;
+            if (olive[i]) __stcs(reinterpret_cast<float4*>(orows[i] + 128 * c + 32 * k), o);
+          }
+          __syncwarp();                                                        // the tile is rewritten by the next round
+        }
       }
     }
   }

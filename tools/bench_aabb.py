@@ -62,6 +62,12 @@ def main():
     P = int(vox.shape[0])
     print(json.dumps(dict(op="ray_aabb.pairs", ms=ms, pairs=P, pairs_per_ray=P / R, value=same_image_tests / (ms * 1e-3),
                           unit="same-image ray-voxel tests/s", out_bytes=P * 24, **base)), flush=True)
+    ms2, (vox2, ray2, pd2) = timed(lambda: ray_aabb.pairs(rd, vb, rb, xb, order="ray"), args.steps)
+    o = torch.sort(ray, stable=True).indices
+    assert torch.equal(vox2, vox[o]) and torch.equal(ray2, ray[o]) and torch.equal(pd2.view(torch.int32), pd[o].view(torch.int32))
+    print(json.dumps(dict(op="ray_aabb.pairs(order='ray')  (ray-major list + CSR: the consumer skips its regroup)", ms=ms2, pairs=P,
+                          value=same_image_tests / (ms2 * 1e-3), unit="same-image ray-voxel tests/s", out_bytes=P * 24, **base)), flush=True)
+    del vox2, ray2, pd2, o
     dense_bytes = 12 * V * R
     if not args.no_dense and dense_bytes < 60e9:
         ms_d, (mask, dist) = timed(lambda: ray_aabb.forward(rd, vb, rb, xb), args.steps)

@@ -42,7 +42,8 @@ def main():
         return e0.elapsed_time(e1) / args.steps, out
 
     with torch.no_grad():
-        ms, out = timed(lambda: pointnet_forward(net, inp, idx, V))
+        ms, out = timed(lambda: pointnet_forward(net, inp, idx, V))                                   # tcgen05 (default)
+        ms_simt, out_simt = timed(lambda: pointnet_forward(net, inp, idx, V, mlp_impl="simt_fp32"))
         for p in net.parameters():
             p.requires_grad_(True)
         with torch.enable_grad():
@@ -53,8 +54,11 @@ def main():
         ms_t, out_t = timed(torch_chain)
     err = float((out - out_t).abs().max() / out_t.abs().max())
     macs = N * (6 * 32 + 32 * 64 + 128 * 128 * 2) + V * (64 * 64 + 128 * 128)
-    print(json.dumps(dict(op="PointNet2Stage forward", points=N, voxels=V, ms=ms, torch_ms=ms_t, speedup=ms_t / ms,
-                          tflops_fp32=2 * macs / (ms * 1e-3) / 1e12, max_rel_diff_vs_torch=err)))
+    err_s = float((out_simt - out_t).abs().max() / out_t.abs().max())
+    print(json.dumps(dict(op="PointNet2Stage forward", points=N, voxels=V, ms=ms, engine="tcgen05 split-bf16 (128->128 layers)",
+                          simt_fp32_ms=ms_simt, torch_ms=ms_t, speedup=ms_t / ms, speedup_vs_simt=ms_simt / ms,
+                          tflops_nominal=2 * macs / (ms * 1e-3) / 1e12, tflops_simt=2 * macs / (ms_simt * 1e-3) / 1e12,
+                          max_rel_diff_vs_torch=err, max_rel_diff_simt_vs_torch=err_s)))
 
 
 if __name__ == "__main__":
