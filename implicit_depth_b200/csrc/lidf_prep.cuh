@@ -271,6 +271,60 @@ __device__ __forceinline__ void roi_channel_general(const float* __restrict__ fc
   }
 }
 
+// NC channels of one ray at once (planes fc, fc + cstride, ...): the sample positions and bilinear weights depend on the ray
+// only, so they are formed once per sample and the NC x (1..4) loads of a sample are independent of each other.  Per channel
+// the accumulation order is exactly roi_channel_general's (ph, pw, iy, ix; w1 v1 + w2 v2 + w3 v3 + w4 v4) -> same bits.
+template <int NC>
+__device__ __forceinline__ void roi_channels_general(const float* __restrict__ fc, size_t cstride, int H, int W, float sw, float sh,
+                                                     float bw, float bh, int gw, int gh, float count, float (&o)[NC][4]) {
+#pragma unroll
+  for (int ph = 0; ph < 2; ++ph) {
+#pragma unroll
+    for (int pw = 0; pw < 2; ++pw) {
+      float acc[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) acc[k] = 0.f;
+      for (int iy = 0; iy < gh; ++iy) {
+        const float y = sh + ph * bh + (iy + 0.5f) * bh / (float)gh;
+        int ylo, yhi; float ly, hy; bool ydead;
+        roi_tap(y, H, ylo, yhi, ly, hy, ydead);
+        for (int ix = 0; ix < gw; ++ix) {
+          const float x = sw + pw * bw + (ix + 0.5f) * bw / (float)gw;
+          int xlo, xhi; float lx, hx; bool xdead;
+          roi_tap(x, W, xlo, xhi, lx, hx, xdead);
+          if (ydead || xdead) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) acc[k] += 0.f;
+            continue;
+          }
+          const float w1 = hy * hx, w2 = hy * lx, w3 = ly * hx, w4 = ly * lx;
+          const float* p1 = fc + (size_t)ylo * W + xlo; const float* p2 = fc + (size_t)ylo * W + xhi;
+          const float* p3 = fc + (size_t)yhi * W + xlo; const float* p4 = fc + (size_t)yhi * W + xhi;
+          float val[NC];
+#pragma unroll
+          for (int k = 0; k < NC; ++k) val[k] = w1 * __ldg(p1 + k * cstride);
+          if (w2 != 0.f) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) val[k] += w2 * __ldg(p2 + k * cstride);
+          }
+          if (w3 != 0.f) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) val[k] += w3 * __ldg(p3 + k * cstride);
+          }
+          if (w4 != 0.f) {
+#pragma unroll
+            for (int k = 0; k < NC; ++k) val[k] += w4 * __ldg(p4 + k * cstride);
+          }
+#pragma unroll
+          for (int k = 0; k < NC; ++k) acc[k] += val[k];
+        }
+      }
+#pragma unroll
+      for (int k = 0; k < NC; ++k) o[k][ph * 2 + pw] = acc[k] / count;
+    }
+  }
+}
+
 // per-ray box set-up shared by the two ROI kernels (boxes are built from integers then .float(), pipeline.py:374-381)
 struct RoiBox { float sw, sh, bw, bh, count; int gw, gh; };
 __device__ __forceinline__ RoiBox roi_box(int px, int py, int half, int H, int W) {
@@ -365,10 +419,14 @@ k_roi_align_border(const float* __restrict__ feat, int B, int H, int W, const in
     const int b = (int)lidf_clamp_idx(bid[ray], B);
     const RoiBox rb = roi_box(px, py, half, H, W);
     const size_t plane0 = (size_t)b * LIDF_RGB_CH * H * W;
-    for (int c = warp; c < LIDF_RGB_CH; c += LIDF_ROI_THREADS / 32) {
-      float o[4];
-      roi_channel_general(feat + plane0 + (size_t)c * H * W, H, W, rb.sw, rb.sh, rb.bw, rb.bh, rb.gw, rb.gh, rb.count, o);
-      *reinterpret_cast<float4*>(&s_tile[lane][c * 4]) = make_float4(o[0], o[1], o[2], o[3]);
+    {                                                                // this warp's 4 channels (warp, warp + 8, ...) together
+      constexpr int NC = LIDF_RGB_CH / (LIDF_ROI_THREADS / 32);
+      float o[NC][4];
+      roi_channels_general<NC>(feat + plane0 + (size_t)warp * H * W, (size_t)(LIDF_ROI_THREADS / 32) * H * W, H, W, rb.sw, rb.sh,
+                               rb.bw, rb.bh, rb.gw, rb.gh, rb.count, o);
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+        *reinterpret_cast<float4*>(&s_tile[lane][(warp + k * (LIDF_ROI_THREADS / 32)) * 4]) = make_float4(o[k][0], o[k][1], o[k][2], o[k][3]);
     }
     __syncthreads();
     for (int r = warp; r < 32; r += LIDF_ROI_THREADS / 32)
@@ -455,16 +513,15 @@ __global__ void __launch_bounds__(256) k_box4_tma(const __grid_constant__ CUtens
 //   soft = scatter_softmax(pred_prob_end, ray)         exp(x - max) / (sum + 1e-12)
 //   max_pair_id = scatter_max(soft | pcl_label, ray)   first maximum (lowest pair index) wins, empty ray -> P
 //   pred_pos = cat(pair_pred_pos, 0)[max_pair_id]
-// One warp per ray over the CSR built above; all reductions are warp shuffles.
+// A warp owns 4 consecutive rays.  Rays with at most 8 pairs (the reference's real regime: ~2 pairs per ray) are done by the
+// warp's four 8-lane groups at once, one pair per lane; longer rays take the whole warp, one after the other.  All reductions
+// are shuffle trees in a fixed order; for <= 8 pairs the 8-lane tree adds exactly what the 32-lane tree adds (the upper levels
+// only add zeros / compare against -inf), so both paths give the same bits.
 // ------------------------------------------------------------------------------------------------
-__global__ void k_ray_terminate(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
-                                const float* __restrict__ label, const int* __restrict__ ray_start,
-                                const int* __restrict__ perm, int64_t P, int64_t R, float* __restrict__ soft,
-                                int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos) {
-  const int64_t ray = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const int lane = threadIdx.x & 31;
-  if (ray >= R) return;
-  const int s = ray_start[ray], e = ray_start[ray + 1];
+__device__ __forceinline__ void ray_terminate_full_warp(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
+                                                        const float* __restrict__ label, const int* __restrict__ perm, int64_t P,
+                                                        int64_t ray, int s, int e, int lane, float* __restrict__ soft,
+                                                        int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos) {
   float m = -INFINITY;
   for (int i = s + lane; i < e; i += 32) m = fmaxf(m, logit[perm ? perm[i] : i]);
 #pragma unroll
@@ -492,6 +549,58 @@ __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __
   }
   if (lane == 0) max_pair_id[ray] = (e > s) ? (int64_t)best_id : P;
   if (lane < 3) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
+}
+
+__global__ void k_ray_terminate(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
+                                const float* __restrict__ label, const int* __restrict__ ray_start,
+                                const int* __restrict__ perm, int64_t P, int64_t R, float* __restrict__ soft,
+                                int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos) {
+  const int64_t ray0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
+  const int lane = threadIdx.x & 31, gi = lane >> 3, gl = lane & 7;
+  if (ray0 >= R) return;
+  const int64_t ray = ray0 + gi;
+  const bool have = ray < R;
+  const int s = have ? ray_start[ray] : 0, e = have ? ray_start[ray + 1] : 0;
+  const bool small = have && e - s <= 8;
+  {  // ---- the four 8-lane groups: rays with <= 8 pairs, lane gl holds pair s + gl
+    const bool act = small && s + gl < e;
+    const int id = act ? (perm ? perm[s + gl] : s + gl) : 0x7fffffff;
+    const float x = act ? logit[id] : -INFINITY;
+    float m = x;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float ex = act ? expf(x - m) : 0.f;
+    float sum = ex;
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float denom = sum + 1e-12f;
+    float best = -INFINITY;
+    int best_id = 0x7fffffff;
+    if (act) {
+      const float sv = ex / denom;
+      soft[id] = sv;
+      best = label ? label[id] : sv;
+      best_id = id;
+    }
+#pragma unroll
+    for (int o = 4; o > 0; o >>= 1) {
+      const float ob = __shfl_xor_sync(0xffffffffu, best, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
+      if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
+    }
+    if (small) {
+      if (gl == 0) max_pair_id[ray] = (e > s) ? (int64_t)best_id : P;
+      if (gl < 3) pred_pos[ray * 3 + gl] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + gl] : 0.f;
+    }
+  }
+  // ---- rays with more than 8 pairs: the whole warp, one ray at a time
+  unsigned longm = __ballot_sync(0xffffffffu, have && !small && gl == 0);
+  while (longm) {
+    const int src = __ffs(longm) - 1;
+    longm &= longm - 1;
+    const int ls = __shfl_sync(0xffffffffu, s, src), le = __shfl_sync(0xffffffffu, e, src);
+    ray_terminate_full_warp(logit, pair_pred_pos, label, perm, P, ray0 + (src >> 3), ls, le, lane, soft, max_pair_id, pred_pos);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------

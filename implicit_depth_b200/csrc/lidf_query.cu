@@ -291,7 +291,7 @@ extern "C" int lidf_ray_terminate(const float* logit, const int64_t* pair_ray, c
   CsrBufs c = carve_csr(b, P, R);
   int rc = build_csr(c, pair_ray, P, R, stream);
   if (rc) return rc;
-  k_ray_terminate<<<(unsigned)((R * 32 + 255) / 256), 256, 0, stream>>>(logit, pair_pred_pos, label, c.ray_start, c.perm,
+  k_ray_terminate<<<(unsigned)(((R + 3) / 4 * 32 + 255) / 256), 256, 0, stream>>>(logit, pair_pred_pos, label, c.ray_start, c.perm,
                                                                         P, R, soft, max_pair_id, pred_pos);
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
@@ -449,6 +449,7 @@ struct QueryPlan {
   CsrBufs csr;
   float* roi_feat; float* T; float* Av; float* box4; int* border_list; int* border_count;
   int* live_list; int* live_count;          // sparse regime: rays that own a pair (row prep works on these only)
+  bool roi_sparse;                          // ... and ROIAlign too (only when the per-ray ROI feature is not an output)
   SimtPack sp;
   TcBufs tc;
   size_t bytes;                             // workspace
@@ -476,11 +477,13 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base, bool sizing_c
   q->border_count = use_box ? b.take<int>(1) : nullptr;
   q->T = b.take<float>((size_t)p->R * 512);
   q->Av = b.take<float>((size_t)p->V * 512);
-  // sparse regime (fewer than 8 pairs per ray on average, no per-ray ROI output requested): per-ray work only for rays
-  // that own a pair
-  const bool sparse = allow_sparse && !p->roi_feat_per_ray && p->P < 8 * p->R && !use_box;
+  // sparse regime (fewer than 8 pairs per ray on average): per-ray work only for rays
+  // that own a pair.  The tensor-core row prep (T) always can; ROIAlign only if its output is not handed to the caller
+  // (RefineNet reads the feature of every ray) and the rays do not go through the box-sum map anyway.
+  const bool sparse = allow_sparse && p->P < 8 * p->R;
   q->live_list = sparse ? b.take<int>((size_t)(p->R > 0 ? p->R : 1)) : nullptr;
   q->live_count = sparse ? b.take<int>(1) : nullptr;
+  q->roi_sparse = sparse && !p->roi_feat_per_ray && !use_box;
   if (q->impl != LIDF_MLP_SIMT_FP32 && q->KP > TC_KPE_MAX) return LIDF_ERR_UNSUPPORTED;
   // packed weights: in the caller's cache buffer when given, else at the end of the workspace
   const bool ext = p->weight_cache != nullptr && base != nullptr;
@@ -519,7 +522,7 @@ int run_prep(const LidfQueryParams* p, QueryPlan& q, cudaStream_t st) {
   if (q.box4) {
     if ((rc = roi_align_rays_box(p->full_rgb_feat, q.box4, q.border_list, q.border_count, p->B, p->H, p->W, p->miss_img_ind,
                                  p->miss_bid, R, p->roi_inp_bbox, q.roi_feat, st))) return rc;
-  } else if (q.live_list && R > 0) {
+  } else if (q.roi_sparse && R > 0) {
     k_roi_align_rays<<<(unsigned)((R + 31) / 32), LIDF_ROI_THREADS, 0, st>>>(p->full_rgb_feat, nullptr, p->B, p->H, p->W,
                                                                               p->miss_img_ind, p->miss_bid, R, p->roi_inp_bbox / 2,
                                                                               q.roi_feat, nullptr, nullptr, q.csr.ray_start);
@@ -653,7 +656,7 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
     }
   }
   // 6. ray termination
-  k_ray_terminate<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(p->pred_prob_end, p->pair_pred_pos, p->pcl_label_float,
+  k_ray_terminate<<<(unsigned)(((R + 3) / 4 * 32 + 255) / 256), 256, 0, st>>>(p->pred_prob_end, p->pair_pred_pos, p->pcl_label_float,
                                                                      q.csr.ray_start, q.csr.perm, P, R,
                                                                      p->pred_prob_end_softmax, p->max_pair_id, p->pred_pos);
   LIDF_LAUNCH_CHECK();
