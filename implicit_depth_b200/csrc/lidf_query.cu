@@ -129,8 +129,11 @@ int check_decoder(const LidfDecoder& d, int D) {
   return LIDF_OK;
 }
 
-int resolve_impl(int mlp_impl, int* out) {
-  int impl = mlp_impl == LIDF_MLP_AUTO ? LIDF_MLP_TC_BF16X3 : mlp_impl;
+// AUTO = the tcgen05 engine where its operand layout applies (NeRF encoding with multires 8, the shipped YAMLs), else the
+// fp32 FMA engine, which takes any multires <= LIDF_MAX_MULTIRES and pos_encode off.  Both are CUDA kernels of this library;
+// an explicitly requested engine is never substituted.
+int resolve_impl(int mlp_impl, int* out, int pos_encode = 1, int multires = 8) {
+  int impl = mlp_impl == LIDF_MLP_AUTO ? ((pos_encode && multires == 8) ? LIDF_MLP_TC_BF16X3 : LIDF_MLP_SIMT_FP32) : mlp_impl;
   if (impl != LIDF_MLP_SIMT_FP32 && impl != LIDF_MLP_TC_BF16X3 && impl != LIDF_MLP_TC_BF16X1) return LIDF_ERR_ARG;
   *out = impl;
   return LIDF_OK;
@@ -458,7 +461,7 @@ struct QueryPlan {
 };
 
 int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base, bool sizing_cache_only = false, bool allow_sparse = true) {
-  int rc = resolve_impl(p->mlp_impl, &q->impl);
+  int rc = resolve_impl(p->mlp_impl, &q->impl, p->pos_encode, p->multires);
   if (rc) return rc;
   if (p->multires < 0 || p->multires > LIDF_MAX_MULTIRES || p->multires_views < 0 || p->multires_views > LIDF_MAX_MULTIRES)
     return LIDF_ERR_UNSUPPORTED;
@@ -973,7 +976,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
 namespace {
 struct RefinePlan { int impl, pe_pos, pe_dir, D, KR, KP; bool tc; float* T; float* Av; float* scratch; SimtPack sp; TcBufs tcb; size_t bytes; };
 int plan_refine(const LidfRefineParams* p, RefinePlan* q, char* base) {
-  int rc = resolve_impl(p->mlp_impl, &q->impl);
+  int rc = resolve_impl(p->mlp_impl, &q->impl, p->pos_encode, p->multires);
   if (rc) return rc;
   if (p->multires < 0 || p->multires > LIDF_MAX_MULTIRES || p->multires_views < 0 || p->multires_views > LIDF_MAX_MULTIRES)
     return LIDF_ERR_UNSUPPORTED;

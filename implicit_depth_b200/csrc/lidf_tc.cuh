@@ -1093,8 +1093,11 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
   __syncthreads();
   tc::fence_after_sync();
   const uint32_t tmem = S.tmem_base;
-  const int64_t n_rows = a.row_list ? (int64_t)*a.n_list : a.rows;
-  const int n_tiles = a.row_list ? (int)((n_rows + 127) / 128) : a.n_tiles;
+  // the row list pays only when it drops a good part of the rows: going through it costs a dependent load per row and
+  // scatters the tiles; with more than 3/4 of the rows listed the kernel walks all rows instead (CTA-uniform decision)
+  const int* const row_list = (a.row_list && (int64_t)*a.n_list * 4 < a.rows * 3) ? a.row_list : nullptr;
+  const int64_t n_rows = row_list ? (int64_t)*a.n_list : a.rows;
+  const int n_tiles = row_list ? (int)((n_rows + 127) / 128) : a.n_tiles;
   const int n_my_tiles = n_tiles > (int)blockIdx.x ? (n_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
 
   if (warp == RP_ROW_WARPS + 1) {
@@ -1165,7 +1168,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
             const int it = it0 + u * RP_ROW_WARPS, rg = it >> 3, ks = it & 7, r = 8 * rg + r8;
             v[u] = make_float4(0.f, 0.f, 0.f, 0.f);
             if (row0 + r < n_rows) {
-              const int64_t src = a.row_list ? (int64_t)a.row_list[row0 + r] : row0 + r;
+              const int64_t src = row_list ? (int64_t)row_list[row0 + r] : row0 + r;
               v[u] = __ldg(reinterpret_cast<const float4*>(a.feat + (size_t)src * 128 + 16 * ks) + j4);
             }
           }
@@ -1187,7 +1190,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
 #pragma unroll
         for (int k = 0; k < 32; ++k) x[k] = 0.f;
         if (row0 + row < n_rows) {
-          const float* dp = a.dirs + (size_t)(a.row_list ? (int64_t)a.row_list[row0 + row] : row0 + row) * 3;
+          const float* dp = a.dirs + (size_t)(row_list ? (int64_t)row_list[row0 + row] : row0 + row) * 3;
 #pragma unroll
           for (int c = 0; c < 3; ++c) {
             const float dv = dp[c];
@@ -1231,7 +1234,7 @@ __global__ void __launch_bounds__(RP_THREADS, 1) k_rowprep_tc(const __grid_const
       for (int i = 0; i < 8; ++i) {
         const int64_t rr = row0 + 32 * q + 4 * i + (lane >> 3);
         olive[i] = rr < n_rows;
-        orows[i] = a.out + (size_t)(olive[i] && a.row_list ? (int64_t)a.row_list[rr] : rr) * 512 + 64 * h + 4 * (lane & 7);
+        orows[i] = a.out + (size_t)(olive[i] && row_list ? (int64_t)row_list[rr] : rr) * 512 + 64 * h + 4 * (lane & 7);
       }
       float* const stg = S.stage[warp];
 #pragma unroll 1

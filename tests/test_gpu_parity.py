@@ -844,3 +844,50 @@ def test_pairs_ray_major_hint_same_outputs_without_the_regroup(engine):
         assert torch.equal(got["max_pair_id"], torch.where(wid < P, inv[wid.clamp(max=P - 1)], wid))
     with pytest.raises(RuntimeError, match="not sorted by ray"):
         lq.forward(*ins, off, prob, part_size=d["part_size"], mlp_impl=engine, pairs_ray_major=True, check_indices=True)
+
+
+@pytest.mark.parametrize("engine", ["simt_fp32", "auto"])
+@pytest.mark.parametrize("pos_encode,multires,multires_views,pos_type", [(True, 6, 3, "abs"), (True, 10, 4, "rel"), (False, 8, 4, "abs"),
+                                                                         (True, 0, 0, "abs")])
+def test_encodings_outside_the_shipped_yaml(engine, pos_encode, multires, multires_views, pos_type):
+    """opt.model.multires / multires_views / pos_encode other than the shipped 8 / 4 / True (reference implicit_net.py:9-57:
+    any frequency count, i = -1 -> identity): the fp32 FMA engine takes them all, and "auto" resolves to it where the
+    tcgen05 operand layout (built for multires 8) does not apply -- same library, same C ABI, no error, no CPU path."""
+    from implicit_depth_b200.synthetic import make_inputs
+    d = make_inputs(2, 20, 28, 7, V_img=32, seed=31 + multires, ragged=True)
+    cfg = dict(O.DEFAULT_CFG, pos_encode=pos_encode, multires=multires, multires_views=multires_views, intersect_pos_type=pos_type)
+    D = 256 + 2 * O.embed_out_dim(multires, pos_encode) + O.embed_out_dim(multires_views, pos_encode)
+    g = torch.Generator().manual_seed(32)
+    off = O.init_decoder("IEF", D, mode="trained", generator=g)
+    prob = O.init_decoder("IMNET", D, mode="trained", generator=g)
+    ref = O.lidf_query(d, cfg, off, prob, d["part_size"], dedup_rays=True)
+    out = _run(d, cfg, off, prob, d["part_size"], engine)
+    _compare(out, ref, d, TOL_FP32 if multires <= 8 else 2e-4)      # sin(2^9 x) in fp32: the argument's rounding is amplified
+    _check_argmax(out, ref, d, 1e-3)
+
+
+@pytest.mark.parametrize("engine", ["auto", "simt_fp32"])
+def test_pointnet_permutation_invariance_at_config5_stage2_size(engine):
+    """Size-independent property at BASELINE config 5's second-stage size (8 x 10^4 valid points + 2,457,600 predicted points,
+    2,048 voxels): a per-voxel max over per-point features does not depend on the order of the points -- every point's
+    features come out of its own operand row whatever tile it lands in, and max is exact -- so shuffling the points must
+    reproduce the output bit for bit; each voxel's feature must also equal the one computed from that voxel's points alone."""
+    from implicit_depth_b200.models.pointnet import pointnet_forward
+    N, V = 2537600, 2048
+    g = torch.Generator().manual_seed(41)
+    w = {}
+    for name, (o, i) in {"point_lin1": (32, 6), "point_lin2": (64, 32), "vox_lin1": (64, 64), "point_lin3": (128, 128),
+                         "point_lin4": (128, 128), "vox_lin2": (128, 128)}.items():
+        w[name + ".weight"] = torch.randn(o, i, generator=g) / i ** 0.5
+        w[name + ".bias"] = 0.1 * torch.randn(o, generator=g)
+    w = _cuda(w)
+    inp = torch.cat((0.3 * torch.randn(N, 3, generator=g), torch.rand(N, 3, generator=g)), 1).cuda()
+    idx = torch.randint(0, V, (N,), generator=g).sort().values.cuda()
+    a = pointnet_forward(w, inp, idx, V, mlp_impl=engine)
+    perm = torch.randperm(N, generator=g).cuda()
+    b = pointnet_forward(w, inp[perm].contiguous(), idx[perm].contiguous(), V, mlp_impl=engine)
+    assert torch.equal(a, b)
+    for v in (0, 777, V - 1):
+        sel = idx == v
+        one = pointnet_forward(w, inp[sel].contiguous(), torch.zeros(int(sel.sum()), dtype=torch.int64, device="cuda"), 1, mlp_impl=engine)
+        assert torch.equal(one[0], a[v])
