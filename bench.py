@@ -198,6 +198,7 @@ def main():
                     help="order of the synthetic pair list: 'nonzero' = the reference's torch.nonzero order (voxel-major; "
                          "the call regroups by ray inside the timed region: the default and the headline), 'ray' = the list "
                          "as lidf_ray_aabb_pairs_ray_major_* emits it (sorted by ray; LidfQueryParams::pairs_ray_major: no regroup)")
+    ap.add_argument("--no-winner-only", action="store_true", help="skip the extra winner-only-mode timing (N = 1 only)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stage2", action="store_true",
@@ -303,6 +304,26 @@ def main():
     if args.cuda_graph:                              # the library's event pair is not usable inside a captured graph
         mlp_ms = [total_ms / args.steps]
     clocks = sampler.stop() if rank == 0 else None
+    # ---- extra (never the headline): winner-only mode -- per-ray outputs only, the offset decoder on each ray's arg-max
+    # pair (LidfQueryParams::winner_only_offset; pred_pos / max_pair_id / pred_prob_end* bit-identical to the full call) ----
+    winner = None
+    if not args.no_winner_only and not args.cuda_graph and args.engine != "simt_fp32" and world == 1:
+        kw_w = dict(kw, winner_only=True)
+        for _ in range(2):
+            lidf_query.forward(*ins, off, prob, **kw_w)
+        torch.cuda.synchronize()
+        w0, w1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        w0.record()
+        for _ in range(args.steps):
+            o = lidf_query.forward(*ins, off, prob, **kw_w)
+            del o
+        w1.record()
+        torch.cuda.synchronize()
+        w_ms = w0.elapsed_time(w1) / args.steps
+        winner = dict(value=P / (w_ms * 1e-3), unit="points/s", ms_per_step=w_ms, steps=args.steps,
+                      note="NOT the headline: pred_pos / max_pair_id / pred_prob_end / pred_prob_end_softmax only (what the "
+                           "reference reads downstream of get_pred), bit-identical to the full call; the probability decoder "
+                           "runs over all P pairs, the offset decoder on one row per ray; pred_offset / pair_pred_pos are not produced")
     t = torch.tensor([total_ms], device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -397,6 +418,8 @@ def main():
                             pair_order="reference voxel-major (regroup inside the timed region)" if args.pair_order == "nonzero" else
                                        "ray-major, as lidf_ray_aabb_pairs_ray_major_* emits it (pairs_ray_major: no regroup)"),
                 clocks=clocks, e2e=e2e, gpu_launches=launches, roofline=roofline, cpu_baseline=cpu)
+    if winner is not None:
+        line["winner_only_mode"] = winner
     progress("cpu baseline done")
     if not args.no_torch_gpu_baseline and world == 1:
         tg = torch_gpu_baseline(d, off, prob, args, dev)

@@ -521,7 +521,8 @@ __global__ void __launch_bounds__(256) k_box4_tma(const __grid_constant__ CUtens
 __device__ __forceinline__ void ray_terminate_full_warp(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
                                                         const float* __restrict__ label, const int* __restrict__ perm, int64_t P,
                                                         int64_t ray, int s, int e, int lane, float* __restrict__ soft,
-                                                        int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos) {
+                                                        int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos,
+                                                        int* __restrict__ win) {
   float m = -INFINITY;
   for (int i = s + lane; i < e; i += 32) m = fmaxf(m, logit[perm ? perm[i] : i]);
 #pragma unroll
@@ -547,14 +548,16 @@ __device__ __forceinline__ void ray_terminate_full_warp(const float* __restrict_
     const int oi = __shfl_xor_sync(0xffffffffu, best_id, o);
     if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
   }
-  if (lane == 0) max_pair_id[ray] = (e > s) ? (int64_t)best_id : P;
-  if (lane < 3) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
+  if (lane == 0) { max_pair_id[ray] = (e > s) ? (int64_t)best_id : P; if (win) win[ray] = (e > s) ? best_id : -1; }
+  if (lane < 3 && pair_pred_pos) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
 }
 
+// pair_pred_pos == nullptr (winner-only mode): pred_pos is not gathered here (the offset decoder writes it for the winners
+// afterwards); win [R] receives each ray's arg-max pair, -1 for a ray without pairs.
 __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
                                 const float* __restrict__ label, const int* __restrict__ ray_start,
                                 const int* __restrict__ perm, int64_t P, int64_t R, float* __restrict__ soft,
-                                int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos) {
+                                int64_t* __restrict__ max_pair_id, float* __restrict__ pred_pos, int* __restrict__ win = nullptr) {
   const int64_t ray0 = (((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5) * 4;
   const int lane = threadIdx.x & 31, gi = lane >> 3, gl = lane & 7;
   if (ray0 >= R) return;
@@ -589,8 +592,8 @@ __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __
       if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
     }
     if (small) {
-      if (gl == 0) max_pair_id[ray] = (e > s) ? (int64_t)best_id : P;
-      if (gl < 3) pred_pos[ray * 3 + gl] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + gl] : 0.f;
+      if (gl == 0) { max_pair_id[ray] = (e > s) ? (int64_t)best_id : P; if (win) win[ray] = (e > s) ? best_id : -1; }
+      if (gl < 3 && pair_pred_pos) pred_pos[ray * 3 + gl] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + gl] : 0.f;
     }
   }
   // ---- rays with more than 8 pairs: the whole warp, one ray at a time
@@ -599,7 +602,7 @@ __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __
     const int src = __ffs(longm) - 1;
     longm &= longm - 1;
     const int ls = __shfl_sync(0xffffffffu, s, src), le = __shfl_sync(0xffffffffu, e, src);
-    ray_terminate_full_warp(logit, pair_pred_pos, label, perm, P, ray0 + (src >> 3), ls, le, lane, soft, max_pair_id, pred_pos);
+    ray_terminate_full_warp(logit, pair_pred_pos, label, perm, P, ray0 + (src >> 3), ls, le, lane, soft, max_pair_id, pred_pos, win);
   }
 }
 

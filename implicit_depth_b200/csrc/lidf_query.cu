@@ -451,6 +451,7 @@ struct QueryPlan {
   int impl, pe_pos, pe_dir, D, KR, KP;
   CsrBufs csr;
   float* roi_feat; float* T; float* Av; float* box4; int* border_list; int* border_count;
+  int* win; float* off_ray;                 // winner-only mode: each ray's arg-max pair (-1: none), its offset output
   int* live_list; int* live_count;          // sparse regime: rays that own a pair (row prep works on these only)
   bool roi_sparse;                          // ... and ROIAlign too (only when the per-ray ROI feature is not an output)
   SimtPack sp;
@@ -480,6 +481,8 @@ int plan_query(const LidfQueryParams* p, QueryPlan* q, char* base, bool sizing_c
   q->border_count = use_box ? b.take<int>(1) : nullptr;
   q->T = b.take<float>((size_t)p->R * 512);
   q->Av = b.take<float>((size_t)p->V * 512);
+  q->win = p->winner_only_offset ? b.take<int>((size_t)(p->R > 0 ? p->R : 1)) : nullptr;
+  q->off_ray = p->winner_only_offset ? b.take<float>((size_t)(p->R > 0 ? p->R : 1)) : nullptr;
   // sparse regime (fewer than 8 pairs per ray on average): per-ray work only for rays
   // that own a pair.  The tensor-core row prep (T) always can; ROIAlign only if its output is not handed to the caller
   // (RefineNet reads the feature of every ray) and the rays do not go through the box-sum map anyway.
@@ -609,13 +612,15 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
   if (p->P > 0) {
     if (!p->occ_voxel_feat || !p->voxel_bound || !p->pair_vox || !p->pair_ray) return LIDF_ERR_NULL;
     if (!p->pair_dist && !p->dense_dist) return LIDF_ERR_NULL;
-    if (!p->pred_offset || !p->pred_prob_end || !p->pair_pred_pos || !p->pred_prob_end_softmax) return LIDF_ERR_NULL;
+    if (!p->pred_prob_end || !p->pred_prob_end_softmax) return LIDF_ERR_NULL;
+    if (!p->winner_only_offset && (!p->pred_offset || !p->pair_pred_pos)) return LIDF_ERR_NULL;
   }
   if (p->roi_inp_bbox < 0) return LIDF_ERR_ARG;
   if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;   // pipeline.py:81-85
   QueryPlan q;
   int rc = plan_query(p, &q, (char*)p->workspace);
   if (rc) return rc;
+  if (p->winner_only_offset && (q.impl == LIDF_MLP_SIMT_FP32 || p->ief_iter_out)) return LIDF_ERR_UNSUPPORTED;
   if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
   if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
   if ((rc = check_decoder(p->prob_dec, q.D))) return rc;
@@ -653,10 +658,23 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
       k_mlp_simt<<<(unsigned)((P + LIDF_SIMT_BM - 1) / LIDF_SIMT_BM), LIDF_SIMT_THREADS, smem, st>>>(a);
       mlp_event(1, st);
       LIDF_LAUNCH_CHECK();
+    } else if (p->winner_only_offset) {
+      // 5'. winner-only mode: probability decoder over all pairs -> ray termination -> offset decoder on each ray's winner
+      if ((rc = tc_query_forward(p, q.tc, q.csr.perm, q.T, q.Av, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
+                                 sizeof(g_cuda_err), mlp_event, 1))) return rc;
+      k_ray_terminate<<<(unsigned)(((R + 3) / 4 * 32 + 255) / 256), 256, 0, st>>>(p->pred_prob_end, nullptr, p->pcl_label_float,
+                                                                         q.csr.ray_start, q.csr.perm, P, R,
+                                                                         p->pred_prob_end_softmax, p->max_pair_id, p->pred_pos, q.win);
+      LIDF_LAUNCH_CHECK();
+      LIDF_CUDA(cudaMemsetAsync(p->pred_pos, 0, sizeof(float) * 3 * (size_t)R, st));      // rays without a pair: zeros (pipeline.py:452)
+      return tc_query_forward(p, q.tc, q.win, q.T, q.Av, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
+                              sizeof(g_cuda_err), mlp_event, 2, q.off_ray);
     } else {
       if ((rc = tc_query_forward(p, q.tc, q.csr.perm, q.T, q.Av, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
                                  sizeof(g_cuda_err), mlp_event))) return rc;
     }
+  } else if (p->winner_only_offset) {
+    LIDF_CUDA(cudaMemsetAsync(p->pred_pos, 0, sizeof(float) * 3 * (size_t)R, st));
   }
   // 6. ray termination
   k_ray_terminate<<<(unsigned)(((R + 3) / 4 * 32 + 255) / 256), 256, 0, st>>>(p->pred_prob_end, p->pair_pred_pos, p->pcl_label_float,

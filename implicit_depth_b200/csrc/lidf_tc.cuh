@@ -462,6 +462,8 @@ struct TcArgs {
   float* pos_out;                  // pair_pred_pos [P,3]
   int n_prod;                      // bf16 products per MAC: 3 (hi*hi + lo*hi + hi*lo) or 1
   float* o_iter;                   // [n_pass[0]-1][P] or NULL: decoder 0's running IEF offset after every iteration but the last
+  int out_by_slot;                 // 1: outputs are written at the row's slot (tile * 128 + row) instead of its original pair
+                                   // index, and perm[slot] < 0 marks a slot without a row (winner-only pass: slot = ray)
 };
 
 struct TcSmem {
@@ -735,7 +737,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     auto load_meta = [&](int tile, int orig_) {
       RowMeta m{0, 0, 0, 0.f, 0.f, false};
       const int64_t s = (int64_t)tile * 128 + row;
-      if (s < a.P) {
+      if (s < a.P && orig_ >= 0) {
         m.valid = true;
         m.orig = orig_;
         // out-of-range indices are clamped (and reported by k_count_pairs / k_validate_indices), never dereferenced
@@ -749,7 +751,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     };
     // layer-1 MMA operand of one tile.  Column group 0 encodes the enter position (k-steps 0-2), 1 the leave position
     // (k-steps 3-5), 2 writes the raw xyz k-step (6) and parks the output metadata in smem.
-    auto build_a1 = [&](const RowMeta& m, int buf) {
+    auto build_a1 = [&](const RowMeta& m, int buf, int tile_) {
       float dir[3] = {0.f, 0.f, 0.f}, enter[3] = {0.f, 0.f, 0.f}, pe[3] = {0.f, 0.f, 0.f}, pl[3] = {0.f, 0.f, 0.f};
       if (m.valid) {
 #pragma unroll
@@ -796,7 +798,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         uint32_t w[16];
         tc::split16(x, w);
         st_a1(6, w);
-        S.m_orig[buf][row] = m.orig;
+        S.m_orig[buf][row] = a.out_by_slot ? (m.valid ? tile_ * 128 + row : -1) : m.orig;
 #pragma unroll
         for (int k = 0; k < 3; ++k) { S.m_geo[buf][k][row] = enter[k]; S.m_geo[buf][3 + k][row] = dir[k]; }
       }
@@ -934,9 +936,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
       const float prev = it == 0 ? (is_ief ? a.o0 : 0.f) : (d == 0 ? o_a : o_b);
       const float onew = is_ief ? prev + l4 : l4;
       if (d == 0) o_a = onew; else o_b = onew;
-      if (a.o_iter && d == 0 && g == 0 && it + 1 < npass0 && (int64_t)tile_ * 128 + row < a.P)
+      const bool row_live = (int64_t)tile_ * 128 + row < a.P && (!a.out_by_slot || S.m_orig[buf][row] >= 0);
+      if (a.o_iter && d == 0 && g == 0 && it + 1 < npass0 && row_live)
         a.o_iter[(size_t)it * a.P + S.m_orig[buf][row]] = onew;
-      if (it + 1 == (d == 0 ? npass0 : npass1) && (int64_t)tile_ * 128 + row < a.P) {
+      if (it + 1 == (d == 0 ? npass0 : npass1) && row_live) {
         const float res = lidf_final_act(onew, d == 0 ? sig0 : sig1);
         const int orig = S.m_orig[buf][row];
         if (d == 0) {
@@ -961,7 +964,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
     // next pass runs before it (its accumulator is ready earlier and the tensor pipe needs it sooner) -- unless the next
     // pass is the next IEF iteration of the same decoder, which needs E3's result: then E3 runs right after E2.
     RowMeta cur = load_meta((int)blockIdx.x, load_orig((int)blockIdx.x));
-    build_a1(cur, 0);
+    build_a1(cur, 0, (int)blockIdx.x);
     int ray = cur.ray, vox = cur.vox;
     bool valid = cur.valid;
     uint32_t gp = 0, tl = 0;
@@ -998,7 +1001,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_tc(const __grid_constant_
         // ---- operand of the next tile: its last reader (S2 of this pass) has retired once a1_free completes
         if (last && has_next) {
           tc::mbar_wait(&S.a1_free, tl & 1u);
-          build_a1(nxt, (int)((tl + 1) & 1u));
+          build_a1(nxt, (int)((tl + 1) & 1u), next_tile);
         }
         // ---- E2(p)
         epi_l2(d, ph);
@@ -1309,14 +1312,17 @@ inline int tc_launch(TcArgs& a, cudaStream_t st, int64_t* launches, char* errbuf
                      void (*mlp_event)(int, cudaStream_t));
 
 // decoders + pair_pred_pos for all P pairs; T = per-ray layer-1 term [R][512], u = IEF rank-1 vector of offset_dec
+// phase: 0 = both decoders over all P pairs; 1 = the probability decoder only (winner-only mode, first half);
+// 2 = the offset decoder over one row per ray (winner-only mode, second half): perm = win [R] (the ray's arg-max pair, -1 for
+// a ray without pairs), outputs by ray: pred_pos [R,3] directly and the offset into off_ray [R].
 inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const int* perm, const float* T, const float* Av,
                             const float* u,
                             int pe_pos, int D, int impl, cudaStream_t st, int64_t* launches, char* errbuf, size_t errlen,
-                            void (*mlp_event)(int, cudaStream_t)) {
+                            void (*mlp_event)(int, cudaStream_t), int phase = 0, float* off_ray = nullptr) {
   if (!p->pos_encode || p->multires != 8 || pe_pos != 51) return LIDF_ERR_UNSUPPORTED;   // A1 layout is built for PE(8)
   if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
   const LidfDecoder* decs[2] = {&p->offset_dec, &p->prob_dec};
-  for (int d = 0; d < 2 && !(p->weight_cache && p->weight_cache_valid); ++d) {
+  for (int d = 0; d < 2 && phase != 2 && !(p->weight_cache && p->weight_cache_valid); ++d) {
     const int ldw = D + (decs[d]->kind == LIDF_DEC_IEF ? LIDF_IEF_ENC : 0);
     k_pack_tc_weights<<<(TC_CHUNKS_PER_DEC * 2048 + 255) / 256, 256, 0, st>>>(
         decs[d]->w1, ldw, pe_pos, decs[d]->w2, decs[d]->w3, tb.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES, 0);
@@ -1338,7 +1344,14 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   a.sqrt3 = (float)sqrt(3.0); a.part = p->part_size;
   a.out[0] = p->pred_offset; a.out[1] = p->pred_prob_end; a.pos_out = p->pair_pred_pos;
   a.n_prod = impl == LIDF_MLP_TC_BF16X1 ? 1 : 3;
-  return tc_launch(a, st, launches, errbuf, errlen, mlp_event);
+  if (phase == 1) {
+    a.n_pass[0] = 0; a.o_iter = nullptr;
+  } else if (phase == 2) {
+    a.n_pass[1] = 0;
+    a.P = p->R; a.n_tiles = (int)((p->R + 127) / 128);
+    a.out_by_slot = 1; a.out[0] = off_ray; a.pos_out = p->pred_pos; a.o_iter = nullptr;
+  }
+  return tc_launch(a, st, launches, errbuf, errlen, phase == 2 ? nullptr : mlp_event);
 }
 
 // pass schedule + launch of k_mlp_tc (a.n_pass[] / a.kind[] set by the caller)

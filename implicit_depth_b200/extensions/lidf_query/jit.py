@@ -50,7 +50,7 @@ class _QueryParams(C.Structure):
                 ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("ief_iter_out", C.c_void_p), ("index_error", C.c_void_p),
                 ("weight_cache", C.c_void_p), ("weight_cache_bytes", C.c_size_t), ("weight_cache_valid", C.c_int32),
-                ("pairs_ray_major", C.c_int32)]
+                ("pairs_ray_major", C.c_int32), ("winner_only_offset", C.c_int32)]
 
 
 class _DecoderGrad(C.Structure):
@@ -585,7 +585,8 @@ class _LidfQuery:
                 n_iter: int = 2, use_sigmoid: bool = False, offset_range: Sequence[float] = (0.0, 1.0),
                 pcl_label_float: Optional[torch.Tensor] = None, mlp_impl: str = "auto",
                 want_roi_feat: bool = False, save_for_backward: bool = False,
-                check_indices: bool = False, pairs_ray_major: bool = False) -> Dict[str, torch.Tensor]:
+                check_indices: bool = False, pairs_ray_major: bool = False,
+                winner_only: bool = False) -> Dict[str, torch.Tensor]:
         """Everything LIDF.get_embedding + LIDF.get_pred compute after the ResNet / PointNet producers
         (reference src/models/pipeline.py:338-466).  ``dist`` is either the per-pair [P,2] enter/leave distances or
         the reference's dense [V,R,2] tensor.  Returns the data_dict entries of pipeline.py:460-466 (+ pred_offset).
@@ -593,7 +594,12 @@ class _LidfQuery:
         ``check_indices`` waits for the call and raises on an out-of-range index (otherwise the next call reports it).
         ``pairs_ray_major``: the caller vouches that ``miss_ray_intersect_idx`` is non-decreasing (what
         ``ray_aabb.pairs(..., order="ray")`` emits); the in-call regroup by ray is then a binary search per ray.  A list
-        that is not sorted raises like an out-of-range index (flag bit 2)."""
+        that is not sorted raises like an out-of-range index (flag bit 2).
+        ``winner_only``: for callers that read the per-ray results only (everything downstream of get_pred in the reference
+        does: compute_loss and RefineNet use pred_pos, max_pair_id, pred_prob_end, pred_prob_end_softmax; pair_pred_pos and
+        pred_offset are written to data_dict and never read).  The probability decoder runs over all pairs, the rays are
+        terminated, and the offset decoder runs on each ray's arg-max pair only -- ``pred_pos`` comes out bit-identical to the
+        full call at a third of the decoder work (64 pairs per ray).  ``pred_offset`` / ``pair_pred_pos`` are not returned."""
         capturing = torch.cuda.is_current_stream_capturing() if full_rgb_feat.is_cuda else False
         if not capturing:
             self.check_index_errors(wait=False)
@@ -607,9 +613,14 @@ class _LidfQuery:
                                pcl_label_float=pcl_label_float, mlp_impl=mlp_impl, pairs_ray_major=pairs_ray_major)
         P, R = int(p.P), int(p.R)
         f32 = dict(dtype=torch.float32, device=dev)
-        out = dict(pred_offset=torch.empty(P, 1, **f32), pred_prob_end=torch.empty(P, 1, **f32),
-                   pair_pred_pos=torch.empty(P, 3, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
+        out = dict(pred_prob_end=torch.empty(P, 1, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
                    max_pair_id=torch.empty(R, dtype=torch.int64, device=dev), pred_pos=torch.empty(R, 3, **f32))
+        if winner_only:
+            if save_for_backward:
+                raise RuntimeError("lidf_query: winner_only is an inference mode (no ief_iter for the backward)")
+            p.winner_only_offset = 1
+        else:
+            out.update(pred_offset=torch.empty(P, 1, **f32), pair_pred_pos=torch.empty(P, 3, **f32))
         if want_roi_feat:
             out["roi_feat_per_ray"] = torch.empty(R, 128, **f32)
             p.roi_feat_per_ray = out["roi_feat_per_ray"].data_ptr()
@@ -621,7 +632,8 @@ class _LidfQuery:
         p.index_error = flag.data_ptr()
         self._attach_weight_cache(p, keep, dev)
         for k in ("pred_offset", "pred_prob_end", "pair_pred_pos", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
-            setattr(p, k, out[k].data_ptr())
+            if k in out:
+                setattr(p, k, out[k].data_ptr())
         nbytes = int(self.lib.lidf_query_workspace_bytes(C.byref(p)))
         if nbytes == 0:
             raise RuntimeError("lidf_query: unsupported configuration (lidf_query_workspace_bytes returned 0)")

@@ -54,6 +54,11 @@ class LIDFQueryMixin:
     # generator so that get_pred skips its regroup (every reader of the pair tensors in the reference is keyed by
     # miss_ray_intersect_idx / occ_vox_intersect_idx and does not depend on their order).
     pair_order = "nonzero"
+    # Inference only: True = get_pred computes the per-ray results only (pred_pos, max_pair_id, pred_prob_end,
+    # pred_prob_end_softmax -- everything compute_loss and RefineNet read); the offset decoder then runs on each ray's arg-max
+    # pair instead of on all pairs.  data_dict['pair_pred_pos'] / ['pred_offset'] (written by the reference, never read) are
+    # not produced.  Same bits in every produced tensor.
+    winner_only = False
 
     def get_embedding(self, data_dict):
         """Runs the two upstream producers exactly where the reference does (pipeline.py:370, :400-407) and stores
@@ -192,17 +197,11 @@ class LIDFQueryMixin:
             # (tcgen05 dgrad / wgrad kernels); DDP sees ordinary .grad tensors on the decoder parameters
             out = lidf_query_autograd(args, self.offset_dec, self.prob_dec, kw)
         else:
-            out = lidf_query.forward(*args, self.offset_dec, self.prob_dec, want_roi_feat=True, **kw)
+            out = lidf_query.forward(*args, self.offset_dec, self.prob_dec, want_roi_feat=True,
+                                     winner_only=bool(self.winner_only) and self.mlp_impl != "simt_fp32", **kw)
         assert out['pred_pos'].shape[0] == data_dict['total_miss_sample_num']
-        data_dict.update({
-            'pair_pred_pos': out['pair_pred_pos'],
-            'max_pair_id': out['max_pair_id'],
-            'pred_prob_end': out['pred_prob_end'],
-            'pred_prob_end_softmax': out['pred_prob_end_softmax'],
-            'pred_pos': out['pred_pos'],
-            'pred_offset': out['pred_offset'],
-            'roi_feat_per_ray': out['roi_feat_per_ray'],
-        })
+        data_dict.update({k: out[k] for k in ('pair_pred_pos', 'max_pair_id', 'pred_prob_end', 'pred_prob_end_softmax', 'pred_pos',
+                                              'pred_offset', 'roi_feat_per_ray') if k in out})
 
 
 class _LidfQueryFn(torch.autograd.Function):

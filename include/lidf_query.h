@@ -125,6 +125,15 @@ typedef struct LidfQueryParams {
                                  * emits: by ray, then voxel).  The voxel-major -> ray-major regroup (count / scan / scatter /
                                  * segment sort over all P pairs) is replaced by one binary search per ray; outputs are the same
                                  * tensors at the same pair indices.  A list that is not sorted sets bit 2 of *index_error. */
+  int32_t winner_only_offset;   /* 1: "winner-only" mode for callers that read the per-ray results only.  Every reader of this
+                                 * path's outputs in the reference (compute_loss pipeline.py:468-650, RefineNet :939-944) looks at
+                                 * pred_pos, max_pair_id, pred_prob_end and pred_prob_end_softmax; pred_offset and pair_pred_pos
+                                 * are stored in data_dict (:460-466) and never read again.  In this mode the probability
+                                 * decoder runs over all P pairs, the rays are terminated, and the offset decoder runs on ONE
+                                 * row per ray -- its arg-max pair -- writing pred_pos directly: the same bits as the full
+                                 * call (a row's arithmetic does not depend on its tile), a third of the decoder work at 64
+                                 * pairs per ray.  pred_offset / pair_pred_pos are NOT written (may be NULL); needs the tcgen05
+                                 * engine and ief_iter_out == NULL. */
 } LidfQueryParams;
 
 /* Gradients of one decoder's parameters: fp32 device buffers with the shapes of the LidfDecoder tensors; every buffer is

@@ -891,3 +891,32 @@ def test_pointnet_permutation_invariance_at_config5_stage2_size(engine):
         sel = idx == v
         one = pointnet_forward(w, inp[sel].contiguous(), torch.zeros(int(sel.sum()), dtype=torch.int64, device="cuda"), 1, mlp_impl=engine)
         assert torch.equal(one[0], a[v])
+
+
+@pytest.mark.parametrize("B,H,W,N,ragged,offdec,label", [(2, 40, 56, 16, False, "IEF", False), (1, 33, 47, 9, True, "IEF", False),
+                                                        (1, 32, 32, 64, False, "IMNET", False), (2, 24, 24, 12, True, "IEF", True)])
+def test_winner_only_mode_gives_the_same_per_ray_results(B, H, W, N, ragged, offdec, label):
+    """LidfQueryParams::winner_only_offset: the probability decoder over all pairs, ray termination, then the offset decoder
+    on each ray's arg-max pair only.  Everything the reference reads downstream of get_pred (pred_pos, max_pair_id,
+    pred_prob_end, pred_prob_end_softmax) must be BIT-identical to the full call -- a row's arithmetic does not depend on
+    which tile it sits in -- incl. ragged rays, rays without a pair (zeros / P) and the GT-label arg-max branch."""
+    from implicit_depth_b200.synthetic import make_inputs
+    lq = _lq()
+    d = _cuda(make_inputs(B, H, W, N, V_img=64, seed=51 + N, ragged=ragged))
+    g = torch.Generator().manual_seed(52)
+    off = _cuda(O.init_decoder(offdec, 385, mode="trained", generator=g))
+    prob = _cuda(O.init_decoder("IMNET", 385, mode="trained", generator=g))
+    ins = [d[k] for k in lq.INPUT_KEYS]
+    P = ins[lq.INPUT_KEYS.index("occ_vox_intersect_idx")].shape[0]
+    lab = (torch.rand(P, generator=torch.Generator().manual_seed(5)) < 0.1).float().cuda() if label else None
+    kw = dict(part_size=d["part_size"], pcl_label_float=lab)
+    full = lq.forward(*ins, off, prob, **kw)
+    win = lq.forward(*ins, off, prob, winner_only=True, check_indices=True, **kw)
+    assert "pred_offset" not in win and "pair_pred_pos" not in win
+    for k in ("pred_prob_end", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
+        assert torch.equal(win[k], full[k]), k
+    if ragged:
+        empty = full["max_pair_id"] == P
+        assert bool(empty.any()) and float(win["pred_pos"][empty].abs().sum()) == 0.0
+    with pytest.raises(RuntimeError):           # needs the tcgen05 engine: loud, not silent
+        lq.forward(*ins, off, prob, winner_only=True, mlp_impl="simt_fp32", **kw)

@@ -33,6 +33,7 @@ def main():
     ap.add_argument("--batch", type=int, default=1)
     ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--pair-order", default="nonzero", choices=["nonzero", "ray"])
+    ap.add_argument("--winner-only", action="store_true")
     args = ap.parse_args()
     from bench import make_decoders
     from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
@@ -55,6 +56,7 @@ def main():
     lidf = LIDF(default_opt(), dev).to(dev).eval()
     lidf.offset_dec, lidf.prob_dec = off, prob
     lidf.pair_order = args.pair_order
+    lidf.winner_only = args.winner_only
     dd = dict(bs=B, h=H, w=W, valid_xyz=valid_xyz, valid_bid=valid_bid, miss_bid=miss_bid, miss_img_ind=miss_img_ind,
               miss_ray_dir=miss_ray_dir, full_rgb_feat=full_rgb_feat, total_miss_sample_num=miss_bid.shape[0], item_path=["scene"])
     res = {}
@@ -70,7 +72,7 @@ def main():
         res["get_pred_launches"] = lidf_query.launch_count()
         res["decoder_kernel_ms"] = lidf_query.last_mlp_ms()
     P, R, V = int(dd["occ_vox_intersect_idx"].shape[0]), int(miss_bid.shape[0]), int(dd["voxel_bound"].shape[0])
-    res.update(workload=f"{B} x {H}x{W} all-pixel rays, {n_pts} valid points/image, 9^3 grid", pair_order=args.pair_order, rays=R, voxels=V, pairs=P,
+    res.update(workload=f"{B} x {H}x{W} all-pixel rays, {n_pts} valid points/image, 9^3 grid", pair_order=args.pair_order, winner_only=args.winner_only, rays=R, voxels=V, pairs=P,
                pairs_per_ray=P / R, get_pred_points_per_s=P / (res["get_pred_ms"] * 1e-3),
                chain_ms=res["get_occ_vox_bound_ms"] + res["compute_ray_aabb_ms"] + res["pointnet_ms"] + res["get_pred_ms"])
     print(json.dumps(res))
