@@ -199,6 +199,9 @@ def main():
                          "the call regroups by ray inside the timed region: the default and the headline), 'ray' = the list "
                          "as lidf_ray_aabb_pairs_ray_major_* emits it (sorted by ray; LidfQueryParams::pairs_ray_major: no regroup)")
     ap.add_argument("--no-winner-only", action="store_true", help="skip the extra winner-only-mode timing (N = 1 only)")
+    ap.add_argument("--winner-only", action="store_true",
+                    help="--train only: forward + backward in winner-only mode (offset decoder on each ray's arg-max pair; the "
+                         "same gradients, see include/lidf_query.h); stated in config")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--stage2", action="store_true",
@@ -461,9 +464,9 @@ def run_train(args, d, ins, off, prob, kw, dev, rank, world, local):
     def step(record=False):
         e = [ev() for _ in range(4)]
         e[0].record()
-        out = lidf_query.forward(*ins, off, prob, save_for_backward=True, **kw)
+        out = lidf_query.forward(*ins, off, prob, save_for_backward=True, winner_only=args.winner_only, **kw)
         e[1].record()
-        res = lidf_query.backward(*ins, off, prob, out, g_pred_pos=g_pos, g_pred_prob_end=g_prob, **kw)
+        res = lidf_query.backward(*ins, off, prob, out, g_pred_pos=g_pos, g_pred_prob_end=g_prob, winner_only=args.winner_only, **kw)
         e[2].record()
         flat = torch.cat([res["offset_dec"][k].reshape(-1) for k in names[0]] + [res["prob_dec"][k].reshape(-1) for k in names[1]])
         if world > 1:
@@ -524,7 +527,10 @@ def run_train(args, d, ins, off, prob, kw, dev, rank, world, local):
                 config=dict(workload=f"{args.workload} train: {B} images/GPU of {H}x{W} rays x {N} pairs/ray = {P} points/GPU, "
                                      f"decoders {args.offdec}(n_iter 2)+IMNET; step = fused forward + native backward + "
                                      f"all-reduce of the {n_dec_params} decoder gradients",
-                            l2="inputs exceed the 126 MB L2; no explicit flush"),
+                            l2="inputs exceed the 126 MB L2; no explicit flush",
+                            mode=("winner-only: offset decoder forward + backward on each ray's arg-max pair (R rows), probability "
+                                  "decoder on all P pairs; gradients equal the full backward's (tests/test_gpu_backward.py)")
+                                 if args.winner_only else "full: both decoders forward + backward over all P pairs"),
                 clocks=clocks, gpu_launches=launches,
                 train=dict(forward_ms=med(t_fwd), backward_ms=med(t_bwd), allreduce_decoder_grads_ms=med(t_ar),
                            allreduce_bytes=4 * n_dec_params, allreduce_full_model_86MB_ms=ar_full,

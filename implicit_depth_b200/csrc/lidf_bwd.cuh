@@ -121,6 +121,8 @@ struct BwArgs {
   float* h1; float* h2; float* d1; float* d2; float* d3; float* pe;   // chunk-local rows; pe NULL = do not write
   int d1_accumulate;
   float* colpart;                                   // [grid][16][32][BW_COLPART], accumulated
+  int by_slot;                                      // winner-only backward of the offset decoder: rows = rays (perm = each ray's
+                                                    // arg-max pair, -1: none), g / o_in indexed by the row's slot s0 + row
 };
 
 #define BW_SLOTS 8                     // weight ring: 8 x 8 KB chunks
@@ -379,7 +381,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
     auto load_meta = [&](int tile_local) {
       RowMeta m{0, 0, 0, 0.f, 0.f, false};
       const int rl = tile_local * 128 + row;
-      if (rl < a.n_rows) {
+      if (rl < a.n_rows && a.perm[a.s0 + rl] >= 0) {
         m.valid = true;
         m.orig = a.perm[a.s0 + rl];
         m.vox = (int)lidf_clamp_idx(a.pair_vox[m.orig], a.V);      // out-of-range indices are flagged by the forward
@@ -457,8 +459,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       const bool has_next = t + 1 < n_my_tiles;
       const size_t wrow0 = (size_t)tile_local * 128 + q * 32;    // first of this warp's 32 chunk rows
       const bool valid = cur.valid;
-      const float gin = valid ? a.g[cur.orig] : 0.f;
-      const float oin = (valid && a.o_in) ? a.o_in[cur.orig] : a.o0;
+      const int64_t gidx = a.by_slot ? a.s0 + (int64_t)tile_local * 128 + row : (int64_t)cur.orig;
+      const float gin = valid ? a.g[gidx] : 0.f;
+      const float oin = (valid && a.o_in) ? a.o_in[gidx] : a.o0;
       const float delta = oin - a.o0;
       const bool rank1 = a.is_ief && a.it > 0;
       RowMeta nxt{0, 0, 0, 0.f, 0.f, false};
@@ -620,7 +623,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
         S.part[par][g][row] = fb;
         tc::bar_quadrant(q);
         if (g == 0 && valid)
-          a.g[cur.orig] = gin + (((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row]);
+          a.g[gidx] = gin + (((S.part[par][0][row] + S.part[par][1][row]) + S.part[par][2][row]) + S.part[par][3][row]);
         par ^= 1;
       }
       cur = nxt;
@@ -856,8 +859,28 @@ __global__ void k_chunk_vox_keys(const int* __restrict__ perm, const int64_t* __
                                  int64_t V, int64_t* __restrict__ keys) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n_rows) return;
-  int64_t v = pair_vox[perm[s0 + i]];
+  const int o = perm[s0 + i];
+  int64_t v = o >= 0 ? pair_vox[o] : 0;              // slot without a row (winner-only list): its delta1 row is zero
   keys[i] = v < 0 ? 0 : (v >= V ? V - 1 : v);
+}
+// winner-only backward: the offset decoder's row list (one row per ray) and its seeds, by ray
+__global__ void k_bwd_winner_rows(const int64_t* __restrict__ max_pair_id, int64_t P, int64_t R, int* __restrict__ win,
+                                  int* __restrict__ iota) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r > R) return;
+  iota[r] = (int)r;
+  if (r < R) { const int64_t m = max_pair_id[r]; win[r] = (m >= 0 && m < P) ? (int)m : -1; }
+}
+__global__ void k_bwd_seed_rays(const float* __restrict__ g_pred_pos, const float* __restrict__ ray_dir, const float* __restrict__ off_ray,
+                                const int* __restrict__ win, int64_t R, float scale, int sig0, float* __restrict__ g0r) {
+  const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= R) return;
+  float go = 0.f;
+  if (g_pred_pos && win[r] >= 0) {
+    const float dot = g_pred_pos[3 * r] * ray_dir[3 * r] + g_pred_pos[3 * r + 1] * ray_dir[3 * r + 1] + g_pred_pos[3 * r + 2] * ray_dir[3 * r + 2];
+    go = dot * scale * lidf_final_act_grad(off_ray[r], sig0);
+  }
+  g0r[r] = go;
 }
 // G_v[vox][dcol ..) += delta1 rows grouped by voxel: block = 64 consecutive positions of the voxel-sorted row list
 // (order[], seg_start[V+1]); a running sum is flushed with atomics whenever the voxel changes (segments are long, so

@@ -620,7 +620,7 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
   QueryPlan q;
   int rc = plan_query(p, &q, (char*)p->workspace);
   if (rc) return rc;
-  if (p->winner_only_offset && (q.impl == LIDF_MLP_SIMT_FP32 || p->ief_iter_out)) return LIDF_ERR_UNSUPPORTED;
+  if (p->winner_only_offset && q.impl == LIDF_MLP_SIMT_FP32) return LIDF_ERR_UNSUPPORTED;
   if (p->workspace_bytes < q.bytes) return LIDF_ERR_WORKSPACE;
   if ((rc = check_decoder(p->offset_dec, q.D))) return rc;
   if ((rc = check_decoder(p->prob_dec, q.D))) return rc;
@@ -668,7 +668,7 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
       LIDF_LAUNCH_CHECK();
       LIDF_CUDA(cudaMemsetAsync(p->pred_pos, 0, sizeof(float) * 3 * (size_t)R, st));      // rays without a pair: zeros (pipeline.py:452)
       return tc_query_forward(p, q.tc, q.win, q.T, q.Av, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
-                              sizeof(g_cuda_err), mlp_event, 2, q.off_ray);
+                              sizeof(g_cuda_err), mlp_event, 2, p->pred_offset_ray ? p->pred_offset_ray : q.off_ray);
     } else {
       if ((rc = tc_query_forward(p, q.tc, q.csr.perm, q.T, q.Av, q.sp.u[0], q.pe_pos, q.D, q.impl, st, &g_launches, g_cuda_err,
                                  sizeof(g_cuda_err), mlp_event))) return rc;
@@ -707,13 +707,16 @@ struct BwdPlan {
   float *Gr, *Gv, *pedir, *droi, *Wg;
   float* partial; size_t partial_floats; int n_cta;
   float* colpart; float* du; float* dc;
+  int* win; int* iota; float* g0r;          // winner-only backward: row list / identity CSR / seeds of the offset decoder, by ray
   size_t bytes;
 };
 
 int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
   LidfQueryParams fp = bp->fwd;
   fp.mlp_impl = LIDF_MLP_TC_BF16X3; fp.roi_feat_per_ray = nullptr; fp.weight_cache = nullptr; fp.weight_cache_valid = 0;
-  int rc = plan_query(&fp, &b->q, base, false, false);    // dense per-ray rows: the wgrad GEMMs read every ROI / T row
+  fp.winner_only_offset = 0;                      // (the forward's scratch of that mode is not needed here)
+  int rc = plan_query(&fp, &b->q, base, false, false);
+  fp.winner_only_offset = bp->fwd.winner_only_offset;    // dense per-ray rows: the wgrad GEMMs read every ROI / T row
   if (rc) return rc;
   const int64_t P = fp.P, R = fp.R, V = fp.V;
   Bump bm{base, b->q.bytes};
@@ -739,6 +742,10 @@ int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
   b->partial = bm.take<float>(b->partial_floats * b->n_cta);
   b->colpart = bm.take<float>((size_t)b->n_cta * TC_ROW_WARPS * 32 * BW_COLPART);
   b->du = bm.take<float>(256); b->dc = bm.take<float>(256);
+  const bool wo = fp.winner_only_offset != 0;
+  b->win = wo ? bm.take<int>((size_t)(R > 0 ? R : 1)) : nullptr;
+  b->iota = wo ? bm.take<int>((size_t)R + 1) : nullptr;
+  b->g0r = wo ? bm.take<float>((size_t)(R > 0 ? R : 1)) : nullptr;
   b->bytes = bm.off + 256;
   return LIDF_OK;
 }
@@ -816,8 +823,11 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
   if (p->P > 0) {
     if (!p->occ_voxel_feat || !p->voxel_bound || !p->pair_vox || !p->pair_ray) return LIDF_ERR_NULL;
     if (!p->pair_dist && !p->dense_dist) return LIDF_ERR_NULL;
-    if (!p->pred_offset || !p->pred_prob_end) return LIDF_ERR_NULL;
+    if (!p->pred_prob_end) return LIDF_ERR_NULL;
+    if (!p->winner_only_offset && !p->pred_offset) return LIDF_ERR_NULL;
+    if (p->winner_only_offset && (!p->pred_offset_ray || bp->g_pred_offset || bp->g_pair_pred_pos)) return LIDF_ERR_ARG;
   }
+  const bool wo = p->winner_only_offset != 0;
   if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;
   if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
   BwdPlan b;
@@ -880,8 +890,18 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     a.g_pair_pred_pos = bp->g_pair_pred_pos;
     a.scale = (float)((double)(p->offset_range1 - p->offset_range0) * sqrt(3.0) * (double)p->part_size);
     a.sig0 = decs[0]->use_sigmoid; a.sig1 = decs[1]->use_sigmoid; a.g0 = b.g[0]; a.g1 = b.g[1];
+    if (wo) {           // the offset decoder's seeds live by ray (below); the per-pair pass only forms the probability decoder's
+      a.g_pred_pos = nullptr; a.pred_offset = p->pred_prob_end; a.g0 = b.g[0];
+    }
     k_bwd_seed<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a);
     LIDF_LAUNCH_CHECK();
+    if (wo) {
+      k_bwd_winner_rows<<<(unsigned)((R + 1 + 255) / 256), 256, 0, st>>>(p->max_pair_id, P, R, b.win, b.iota);
+      LIDF_LAUNCH_CHECK();
+      k_bwd_seed_rays<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(bp->g_pred_pos, p->miss_ray_dir, p->pred_offset_ray, b.win, R,
+                                                                    a.scale, a.sig0, b.g0r);
+      LIDF_LAUNCH_CHECK();
+    }
   }
   k_bwd_pedir<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(p->miss_ray_dir, R, p->multires_views, p->pos_encode, b.pedir);
   LIDF_LAUNCH_CHECK();
@@ -902,21 +922,27 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     const int n_pass = ief ? dc.n_iter : 1;
     LIDF_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float) * b.partial_floats * b.n_cta, st));
     LIDF_CUDA(cudaMemsetAsync(b.colpart, 0, sizeof(float) * (size_t)b.n_cta * TC_ROW_WARPS * 32 * BW_COLPART, st));
-    for (int64_t s0 = 0; s0 < P; s0 += b.chunk_rows) {
-      const int n_rows = (int)((P - s0) < b.chunk_rows ? (P - s0) : b.chunk_rows);
+    // rows of this decoder's backward: all P pairs in ray-major order, or (winner-only mode, offset decoder) one row per ray
+    const bool by_ray = wo && d == 0;
+    const int64_t n_dom = by_ray ? R : P;
+    const int* row_perm = by_ray ? b.win : q.csr.perm;
+    const int* row_ray_start = by_ray ? b.iota : q.csr.ray_start;
+    for (int64_t s0 = 0; s0 < n_dom; s0 += b.chunk_rows) {
+      const int n_rows = (int)((n_dom - s0) < b.chunk_rows ? (n_dom - s0) : b.chunk_rows);
       const int n_tiles = (n_rows + 127) / 128;
       for (int it = n_pass - 1; it >= 0; --it) {
         BwArgs a{};
         a.P = P; a.s0 = s0; a.n_rows = n_rows; a.n_tiles = n_tiles;
-        a.perm = q.csr.perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
+        a.by_slot = by_ray ? 1 : 0;
+        a.perm = row_perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
         a.dense_dist = p->dense_dist; a.R = R; a.V = V; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
         a.rel = p->intersect_pos_rel; a.Av = q.Av; a.T = q.T; a.dcol = 256 * d;
         a.wfwd = q.tc.wstream + (size_t)d * TC_CHUNKS_PER_DEC * TC_CHUNK_BYTES;
         a.wbwd = b.wbwd + (size_t)d * BW_CHUNKS_BWD * TC_CHUNK_BYTES;
         a.u = ief ? q.sp.u[d] : nullptr; a.b2 = dc.b2; a.b3 = dc.b3; a.w4 = dc.w4;
         a.is_ief = ief ? 1 : 0; a.it = it; a.o0 = ief ? dc.init_offset : 0.f;
-        a.o_in = (ief && it > 0) ? bp->ief_iter + (size_t)(it - 1) * P : nullptr;
-        a.g = b.g[d];
+        a.o_in = (ief && it > 0) ? bp->ief_iter + (size_t)(it - 1) * n_dom : nullptr;     // [n_iter-1][P], or [..][R] by ray
+        a.g = by_ray ? b.g0r : b.g[d];
         a.h1 = b.h1; a.h2 = b.h2; a.d1 = b.d1; a.d2 = b.d2; a.d3 = b.d3;
         a.pe = it == n_pass - 1 ? b.pe : nullptr;
         a.d1_accumulate = it == n_pass - 1 ? 0 : 1;
@@ -928,9 +954,9 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
         if ((rc = launch_wgrad(b.d2, LIDF_H2, 128, b.h1, LIDF_H1, 256, 256, n_rows, part_w2, n_cta, st))) return rc;   // dW2
       }
       if ((rc = launch_wgrad(b.d1, LIDF_H1, 256, b.pe, BW_PE_LD, BW_PE_LD, BW_PE_LD, n_rows, part_w1, n_cta, st))) return rc;   // dW1[:,pos]
-      k_segsum_rays<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(b.d1, s0, n_rows, q.csr.ray_start, R, b.Gr, 256 * d);
+      k_segsum_rays<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(b.d1, s0, n_rows, row_ray_start, R, b.Gr, 256 * d);
       LIDF_LAUNCH_CHECK();
-      k_chunk_vox_keys<<<(n_rows + 255) / 256, 256, 0, st>>>(q.csr.perm, p->pair_vox, s0, n_rows, V, b.vkeys);
+      k_chunk_vox_keys<<<(n_rows + 255) / 256, 256, 0, st>>>(row_perm, p->pair_vox, s0, n_rows, V, b.vkeys);
       LIDF_LAUNCH_CHECK();
       if ((rc = build_csr(b.vcsr, b.vkeys, n_rows, V, st, false))) return rc;
       k_segsum_vox<<<(n_rows + 63) / 64, 64, 0, st>>>(b.d1, b.vcsr.perm, b.vcsr.ray_start, V, n_rows, b.Gv, 256 * d);

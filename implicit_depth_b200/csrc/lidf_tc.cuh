@@ -1349,7 +1349,7 @@ inline int tc_query_forward(const LidfQueryParams* p, const TcBufs& tb, const in
   } else if (phase == 2) {
     a.n_pass[1] = 0;
     a.P = p->R; a.n_tiles = (int)((p->R + 127) / 128);
-    a.out_by_slot = 1; a.out[0] = off_ray; a.pos_out = p->pred_pos; a.o_iter = nullptr;
+    a.out_by_slot = 1; a.out[0] = off_ray; a.pos_out = p->pred_pos;      // a.o_iter (if any) is [n_iter-1][R], by ray
   }
   return tc_launch(a, st, launches, errbuf, errlen, phase == 2 ? nullptr : mlp_event);
 }

@@ -50,7 +50,7 @@ class _QueryParams(C.Structure):
                 ("roi_feat_per_ray", C.c_void_p), ("workspace", C.c_void_p), ("workspace_bytes", C.c_size_t),
                 ("ief_iter_out", C.c_void_p), ("index_error", C.c_void_p),
                 ("weight_cache", C.c_void_p), ("weight_cache_bytes", C.c_size_t), ("weight_cache_valid", C.c_int32),
-                ("pairs_ray_major", C.c_int32), ("winner_only_offset", C.c_int32)]
+                ("pairs_ray_major", C.c_int32), ("winner_only_offset", C.c_int32), ("pred_offset_ray", C.c_void_p)]
 
 
 class _DecoderGrad(C.Structure):
@@ -616,9 +616,10 @@ class _LidfQuery:
         out = dict(pred_prob_end=torch.empty(P, 1, **f32), pred_prob_end_softmax=torch.empty(P, **f32),
                    max_pair_id=torch.empty(R, dtype=torch.int64, device=dev), pred_pos=torch.empty(R, 3, **f32))
         if winner_only:
-            if save_for_backward:
-                raise RuntimeError("lidf_query: winner_only is an inference mode (no ief_iter for the backward)")
             p.winner_only_offset = 1
+            if save_for_backward:                            # the winners' offsets, by ray: what backward(winner_only=True) reads
+                out["pred_offset_ray"] = torch.empty(R, **f32)
+                p.pred_offset_ray = out["pred_offset_ray"].data_ptr()
         else:
             out.update(pred_offset=torch.empty(P, 1, **f32), pair_pred_pos=torch.empty(P, 3, **f32))
         if want_roi_feat:
@@ -626,7 +627,7 @@ class _LidfQuery:
             p.roi_feat_per_ray = out["roi_feat_per_ray"].data_ptr()
         if save_for_backward:
             n_it = int(p.offset_dec.n_iter) if p.offset_dec.kind == 1 else 1
-            out["ief_iter"] = torch.empty(max(n_it - 1, 0), P, **f32)
+            out["ief_iter"] = torch.empty(max(n_it - 1, 0), R if winner_only else P, **f32)
             p.ief_iter_out = out["ief_iter"].data_ptr() if n_it > 1 and P > 0 else None
         flag = torch.zeros(1, dtype=torch.int32, device=dev)
         p.index_error = flag.data_ptr()
@@ -701,11 +702,14 @@ class _LidfQuery:
     def backward(self, full_rgb_feat, occ_voxel_feat, miss_ray_dir, miss_img_ind, miss_bid, voxel_bound,
                  occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, fwd_out, *,
                  g_pred_pos=None, g_pred_prob_end=None, g_pred_offset=None, g_pair_pred_pos=None,
-                 need_feat_grad: bool = True, need_vox_grad: bool = True, chunk_rows: int = 0, **kw):
+                 need_feat_grad: bool = True, need_vox_grad: bool = True, chunk_rows: int = 0, winner_only: bool = False, **kw):
         """Backward of ``forward`` (include/lidf_query.h: lidf_query_backward): what torch autograd does for the reference's
         get_embedding + get_pred under ``loss_net.backward()`` (reference src/trainers/train_lidf.py:394).  ``fwd_out`` is
         the dict ``forward(..., save_for_backward=True)`` returned; ``kw`` are the same scalar settings.  Returns
-        ``dict(full_rgb_feat=..., occ_voxel_feat=..., offset_dec={state_dict key: grad}, prob_dec={...})``."""
+        ``dict(full_rgb_feat=..., occ_voxel_feat=..., offset_dec={state_dict key: grad}, prob_dec={...})``.
+        ``winner_only``: ``fwd_out`` comes from ``forward(..., winner_only=True, save_for_backward=True)``; the offset decoder's
+        backward then runs over one row per ray (the only rows whose upstream gradient is non-zero when the loss reads
+        ``pred_pos`` and ``pred_prob_end``, as the reference's does); ``g_pred_offset`` / ``g_pair_pred_pos`` must be None."""
         dev = full_rgb_feat.device
         keep: list = []
         kw.pop("want_roi_feat", None); kw.pop("save_for_backward", None); kw.pop("check_indices", None)
@@ -714,14 +718,21 @@ class _LidfQuery:
                                     occ_vox_intersect_idx, miss_ray_intersect_idx, dist, offset_dec, prob_dec, keep, **kw)
         P, R, V = int(bp.fwd.P), int(bp.fwd.R), int(bp.fwd.V)
         f32 = dict(dtype=torch.float32, device=dev)
-        bp.fwd.pred_offset = _chk(fwd_out["pred_offset"], "pred_offset", torch.float32)
+        if winner_only:
+            if g_pred_offset is not None or g_pair_pred_pos is not None:
+                raise RuntimeError("backward(winner_only=True): pred_offset / pair_pred_pos are not outputs of that mode")
+            bp.fwd.winner_only_offset = 1
+            bp.fwd.pred_offset_ray = _chk(fwd_out["pred_offset_ray"], "pred_offset_ray", torch.float32)
+        else:
+            bp.fwd.pred_offset = _chk(fwd_out["pred_offset"], "pred_offset", torch.float32)
         bp.fwd.pred_prob_end = _chk(fwd_out["pred_prob_end"], "pred_prob_end", torch.float32)
         bp.fwd.max_pair_id = _chk(fwd_out["max_pair_id"], "max_pair_id", torch.int64)
         n_it = int(bp.fwd.offset_dec.n_iter) if bp.fwd.offset_dec.kind == 1 else 1
         if n_it > 1 and P > 0:
             it = fwd_out.get("ief_iter")
-            if it is None or tuple(it.shape) != (n_it - 1, P):
-                raise RuntimeError("backward needs fwd_out['ief_iter'] [n_iter-1, P]: call forward(save_for_backward=True)")
+            if it is None or tuple(it.shape) != (n_it - 1, R if winner_only else P):
+                raise RuntimeError("backward needs fwd_out['ief_iter'] [n_iter-1, P] ([n_iter-1, R] in winner-only mode): "
+                                   "call forward(save_for_backward=True)")
             bp.ief_iter = _chk(it, "ief_iter", torch.float32)
         for name, t, shape in (("g_pred_pos", g_pred_pos, (R, 3)), ("g_pred_prob_end", g_pred_prob_end, (P, 1)),
                                ("g_pred_offset", g_pred_offset, (P, 1)), ("g_pair_pred_pos", g_pair_pred_pos, (P, 3))):

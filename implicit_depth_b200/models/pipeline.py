@@ -54,10 +54,11 @@ class LIDFQueryMixin:
     # generator so that get_pred skips its regroup (every reader of the pair tensors in the reference is keyed by
     # miss_ray_intersect_idx / occ_vox_intersect_idx and does not depend on their order).
     pair_order = "nonzero"
-    # Inference only: True = get_pred computes the per-ray results only (pred_pos, max_pair_id, pred_prob_end,
+    # True = get_pred computes the per-ray results only (pred_pos, max_pair_id, pred_prob_end,
     # pred_prob_end_softmax -- everything compute_loss and RefineNet read); the offset decoder then runs on each ray's arg-max
     # pair instead of on all pairs.  data_dict['pair_pred_pos'] / ['pred_offset'] (written by the reference, never read) are
-    # not produced.  Same bits in every produced tensor.
+    # not produced.  Same bits in every produced tensor; in training the offset decoder's backward runs over those rows only
+    # (every other pair's upstream gradient is exactly zero in the reference's loss).
     winner_only = False
 
     def get_embedding(self, data_dict):
@@ -195,7 +196,8 @@ class LIDFQueryMixin:
         if needs_grad:
             # training: the same fused forward, recorded as ONE autograd node whose backward is lidf_query_backward
             # (tcgen05 dgrad / wgrad kernels); DDP sees ordinary .grad tensors on the decoder parameters
-            out = lidf_query_autograd(args, self.offset_dec, self.prob_dec, kw)
+            out = lidf_query_autograd(args, self.offset_dec, self.prob_dec, kw,
+                                      winner_only=bool(self.winner_only) and self.mlp_impl != "simt_fp32")
         else:
             out = lidf_query.forward(*args, self.offset_dec, self.prob_dec, want_roi_feat=True,
                                      winner_only=bool(self.winner_only) and self.mlp_impl != "simt_fp32", **kw)
@@ -214,11 +216,17 @@ class _LidfQueryFn(torch.autograd.Function):
         n_off = len(meta['off_keys'])
         off = dict(zip(meta['off_keys'], params[:n_off]))
         prob = dict(zip(meta['prob_keys'], params[n_off:]))
+        wo = bool(meta.get('winner_only', False))
         out = lidf_query.forward(full_rgb_feat, occ_voxel_feat, *meta['index_args'], off, prob, want_roi_feat=True,
-                                 save_for_backward=True, **meta['kw'])
+                                 save_for_backward=True, winner_only=wo, **meta['kw'])
         ctx.meta = meta
-        ctx.fwd_out = {k: out[k] for k in ('pred_offset', 'pred_prob_end', 'max_pair_id', 'ief_iter')}
+        ctx.fwd_out = {k: out[k] for k in ('pred_offset', 'pred_prob_end', 'max_pair_id', 'ief_iter', 'pred_offset_ray') if k in out}
         ctx.save_for_backward(full_rgb_feat, occ_voxel_feat, *params)
+        if wo:      # per-pair offset outputs do not exist in this mode: empty placeholders keep the node's signature
+            e0, e1 = out['pred_prob_end'].new_empty(0), out['pred_prob_end'].new_empty(0)
+            ctx.mark_non_differentiable(out['pred_prob_end_softmax'], out['max_pair_id'], out['roi_feat_per_ray'], e0, e1)
+            return (e0, out['pred_prob_end'], e1, out['pred_prob_end_softmax'], out['max_pair_id'], out['pred_pos'],
+                    out['roi_feat_per_ray'])
         ctx.mark_non_differentiable(out['pred_prob_end_softmax'], out['max_pair_id'], out['roi_feat_per_ray'])
         return (out['pred_offset'], out['pred_prob_end'], out['pair_pred_pos'], out['pred_prob_end_softmax'],
                 out['max_pair_id'], out['pred_pos'], out['roi_feat_per_ray'])
@@ -231,15 +239,17 @@ class _LidfQueryFn(torch.autograd.Function):
         off = dict(zip(meta['off_keys'], params[:n_off]))
         prob = dict(zip(meta['prob_keys'], params[n_off:]))
         kw = {k: v for k, v in meta['kw'].items() if k != 'pcl_label_float'}
+        wo = bool(meta.get('winner_only', False))
         res = lidf_query.backward(full_rgb_feat, occ_voxel_feat, *meta['index_args'], off, prob, ctx.fwd_out,
-                                  g_pred_pos=g_pos, g_pred_prob_end=g_prob, g_pred_offset=g_off, g_pair_pred_pos=g_pair,
+                                  g_pred_pos=g_pos, g_pred_prob_end=g_prob, g_pred_offset=None if wo else g_off,
+                                  g_pair_pred_pos=None if wo else g_pair, winner_only=wo,
                                   need_feat_grad=ctx.needs_input_grad[1], need_vox_grad=ctx.needs_input_grad[2], **kw)
         grads = [res['offset_dec'][k] for k in meta['off_keys']] + [res['prob_dec'][k] for k in meta['prob_keys']]
         grads = [g if need else None for g, need in zip(grads, ctx.needs_input_grad[3:])]
         return (None, res['full_rgb_feat'], res['occ_voxel_feat'], *grads)
 
 
-def lidf_query_autograd(args, offset_dec, prob_dec, kw):
+def lidf_query_autograd(args, offset_dec, prob_dec, kw, winner_only=False):
     """Training entry: ``args`` = the nine tensor inputs of ``lidf_query.forward`` (features first), decoders as modules.
     There is no CPU / eager fallback: the tensors must live on a CUDA device."""
     full_rgb_feat, occ_voxel_feat = args[0], args[1]
@@ -247,11 +257,15 @@ def lidf_query_autograd(args, offset_dec, prob_dec, kw):
         raise RuntimeError('lidf_query: the training path runs on the sm_100a kernels only (no CPU fallback)')
     off_sd = dict(offset_dec.named_parameters())
     prob_sd = dict(prob_dec.named_parameters())
-    meta = dict(off_keys=list(off_sd), prob_keys=list(prob_sd), index_args=tuple(a.detach() for a in args[2:]), kw=kw)
+    meta = dict(off_keys=list(off_sd), prob_keys=list(prob_sd), index_args=tuple(a.detach() for a in args[2:]), kw=kw,
+                winner_only=bool(winner_only))
     names = ('pred_offset', 'pred_prob_end', 'pair_pred_pos', 'pred_prob_end_softmax', 'max_pair_id', 'pred_pos',
              'roi_feat_per_ray')
     outs = _LidfQueryFn.apply(meta, full_rgb_feat, occ_voxel_feat, *off_sd.values(), *prob_sd.values())
-    return dict(zip(names, outs))
+    out = dict(zip(names, outs))
+    if winner_only:
+        out.pop('pred_offset'); out.pop('pair_pred_pos')
+    return out
 
 
 class LIDF(LIDFQueryMixin, nn.Module):

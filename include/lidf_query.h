@@ -133,7 +133,13 @@ typedef struct LidfQueryParams {
                                  * row per ray -- its arg-max pair -- writing pred_pos directly: the same bits as the full
                                  * call (a row's arithmetic does not depend on its tile), a third of the decoder work at 64
                                  * pairs per ray.  pred_offset / pair_pred_pos are NOT written (may be NULL); needs the tcgen05
-                                 * engine and ief_iter_out == NULL. */
+                                 * engine.  Training: ief_iter_out is then [n_iter-1][R] (by ray) and pred_offset_ray [R]
+                                 * receives the offset decoder's output of each ray's winner; lidf_query_backward, given the
+                                 * same flag and those two arrays, runs the offset decoder's backward over the R winner rows
+                                 * only (every other row's upstream gradient is exactly zero in the reference: pos_loss
+                                 * reaches the decoder through pred_pos = pair_pred_pos[max_pair_id] alone, pipeline.py:449-454);
+                                 * g_pred_offset / g_pair_pred_pos must then be NULL. */
+  float* pred_offset_ray;       /* [R] optional (winner-only mode): forward output / backward input */
 } LidfQueryParams;
 
 /* Gradients of one decoder's parameters: fp32 device buffers with the shapes of the LidfDecoder tensors; every buffer is

@@ -45,7 +45,7 @@ def _to_dev(d, keys):
     return [d[k].to(_dev()).contiguous() for k in keys]
 
 
-def _native_grads(d, cfg, off, prob, part, coef, chunk_rows=0, label=None):
+def _native_grads(d, cfg, off, prob, part, coef, chunk_rows=0, label=None, winner_only=False):
     """forward(save_for_backward) + backward through the C ABI; returns (fwd_out, grads)."""
     from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
     ins = _to_dev(d, lidf_query.INPUT_KEYS)
@@ -54,12 +54,12 @@ def _native_grads(d, cfg, off, prob, part, coef, chunk_rows=0, label=None):
     kw = dict(part_size=part, pos_encode=cfg["pos_encode"], multires=cfg["multires"], multires_views=cfg["multires_views"],
               intersect_pos_type=cfg["intersect_pos_type"], n_iter=cfg["n_iter"], use_sigmoid=cfg["use_sigmoid"],
               offset_range=cfg["offset_range"])
-    out = lidf_query.forward(*ins, offc, probc, save_for_backward=True,
+    out = lidf_query.forward(*ins, offc, probc, save_for_backward=True, winner_only=winner_only,
                              pcl_label_float=label.to(_dev()) if label is not None else None, **kw)
     g = {k: (v.to(_dev()) if v is not None else None) for k, v in coef.items()}
     res = lidf_query.backward(*ins, offc, probc, out, g_pred_pos=g.get("pred_pos"), g_pred_prob_end=g.get("pred_prob_end"),
                               g_pred_offset=g.get("pred_offset"), g_pair_pred_pos=g.get("pair_pred_pos"),
-                              chunk_rows=chunk_rows, **kw)
+                              chunk_rows=chunk_rows, winner_only=winner_only, **kw)
     torch.cuda.synchronize()
     return out, res
 
@@ -85,15 +85,18 @@ def _golden_want(z, off, prob):
                 prob_dec={k: torch.from_numpy(z[f"grad.prob_dec.{k}"]) for k in prob})
 
 
+@pytest.mark.parametrize("winner_only", [False, True])
 @pytest.mark.parametrize("name,gname", [("ief_ragged_2x24x32", "gradk_ief_ragged_2x24x32"),
                                         ("ief_rel_sigmoid_1x16x20", "gradk_ief_rel_sigmoid_1x16x20")])
-def test_backward_reproduces_reference_autograd_goldens(name, gname):
+def test_backward_reproduces_reference_autograd_goldens(name, gname, winner_only):
     """Every decoder parameter, full_rgb_feat and occ_voxel_feat against the reference's own autograd (goldens whose
-    upstream gradients avoid the pairs sitting on a leaky-ReLU kink, see the module docstring): 1e-3."""
+    upstream gradients avoid the pairs sitting on a leaky-ReLU kink, see the module docstring): 1e-3.  winner_only: the
+    same gradients with the offset decoder's forward and backward run on one row per ray (the reference's loss reaches it
+    through pred_pos = pair_pred_pos[max_pair_id] alone, so every other row's contribution is exactly zero)."""
     d, cfg, off, prob, part, ref, _ = load_golden(name)
     z = np.load(os.path.join(GOLDEN_DIR, gname + ".npz"))
     coef = dict(pred_pos=torch.from_numpy(z["c_pos"]), pred_prob_end=torch.from_numpy(z["c_prob"]))
-    out, res = _native_grads(d, cfg, off, prob, part, coef)
+    out, res = _native_grads(d, cfg, off, prob, part, coef, winner_only=winner_only)
     assert torch.equal(out["max_pair_id"].cpu(), torch.from_numpy(z["max_pair_id"]).long())
     _check(res, _golden_want(z, off, prob))
 
@@ -224,6 +227,34 @@ def test_backward_matches_oracle_autograd_on_seeded_inputs(offdec, n_iter, rel, 
     _check(res, want)
 
 
+@pytest.mark.parametrize("offdec,n_iter,rel,sigmoid,chunk", [("IEF", 2, False, False, 0), ("IEF", 2, False, False, 256),
+                                                              ("IMNET", 1, False, False, 128), ("IEF", 3, True, True, 384)])
+def test_winner_only_backward_equals_the_full_backward(offdec, n_iter, rel, sigmoid, chunk):
+    """Upstream gradients on pred_pos and pred_prob_end only (all the reference's loss produces): the winner-only backward
+    (offset decoder over R rows) must give the full backward's gradients -- the rows it skips have upstream gradient 0, so
+    the sums differ by association only -- and match the fp64 oracle's autograd; ragged rays, rays without pairs, several
+    chunks of the ray domain, IMNet / IEF n_iter 2 / 3."""
+    d, cfg, off, prob, part, g = _seeded_case(2, 20, 28, 7, 24, seed=400 + n_iter, offdec=offdec, n_iter=n_iter, rel=rel, sigmoid=sigmoid)
+    P, R = d["occ_vox_intersect_idx"].shape[0], d["miss_ray_dir"].shape[0]
+    coef = dict(pred_pos=torch.randn(R, 3, generator=g), pred_prob_end=torch.randn(P, 1, generator=g))
+    out, _ = _native_grads(d, cfg, off, prob, part, coef)
+    mp = out["max_pair_id"].cpu()
+    coef, kept = mask_coefficients(coef, kink_margin(d, cfg, off, prob), d["miss_ray_intersect_idx"], mp)
+    out_f, full = _native_grads(d, cfg, off, prob, part, coef, chunk_rows=chunk)
+    out_w, win = _native_grads(d, cfg, off, prob, part, coef, chunk_rows=chunk, winner_only=True)
+    assert torch.equal(out_w["pred_pos"], out_f["pred_pos"]) and torch.equal(out_w["max_pair_id"], out_f["max_pair_id"])
+    assert "pred_offset" not in out_w and out_w["ief_iter"].shape == (max(n_iter - 1, 0) if offdec == "IEF" else 0, R)
+    for mod in ("offset_dec", "prob_dec"):
+        for k in full[mod]:
+            assert rel_err(win[mod][k].cpu(), full[mod][k].cpu()) < 1e-4, (mod, k)
+    assert rel_err(win["full_rgb_feat"].cpu(), full["full_rgb_feat"].cpu()) < 1e-4
+    assert rel_err(win["occ_voxel_feat"].cpu(), full["occ_voxel_feat"].cpu()) < 1e-4
+    _check(win, _oracle_grads(d, cfg, off, prob, part, coef, mp))
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    with pytest.raises(RuntimeError):            # per-pair offset gradients have no place in this mode
+        _native_grads(d, cfg, off, prob, part, dict(coef, pred_offset=torch.zeros(P, 1)), winner_only=True)
+
+
 def test_backward_chunking_and_repeat_are_consistent():
     """Same gradients whether the pairs are processed in one chunk or in many; identical bits when repeated."""
     d, cfg, off, prob, part, g = _seeded_case(1, 24, 32, 6, 20, seed=77)
@@ -250,15 +281,18 @@ def test_label_branch_gradient_follows_the_label_argmax():
     out, _ = _native_grads(d, cfg, off, prob, part, coef, label=label)
     mp = out["max_pair_id"].cpu()
     coef, _ = mask_coefficients(coef, kink_margin(d, cfg, off, prob), d["miss_ray_intersect_idx"], mp)
-    out, res = _native_grads(d, cfg, off, prob, part, coef, label=label)
     want = _oracle_grads(d, cfg, off, prob, part, coef, mp)
-    _check(res, want)
-    assert float(res["prob_dec"]["linear_2.weight"].abs().max()) == 0.0      # no gradient reaches prob_dec from pred_pos
+    for wo in (False, True):
+        out, res = _native_grads(d, cfg, off, prob, part, coef, label=label, winner_only=wo)
+        assert torch.equal(out["max_pair_id"].cpu(), mp)
+        _check(res, want)
+        assert float(res["prob_dec"]["linear_2.weight"].abs().max()) == 0.0      # no gradient reaches prob_dec from pred_pos
 
 
-def test_mixin_training_step_populates_param_grads_and_matches_goldens():
+@pytest.mark.parametrize("winner_only", [False, True])
+def test_mixin_training_step_populates_param_grads_and_matches_goldens(winner_only):
     """LIDFQueryMixin.get_pred while autograd records = one autograd node over the fused kernels; .grad lands on the
-    module parameters (what DDP hooks into) and equals the reference's autograd."""
+    module parameters (what DDP hooks into) and equals the reference's autograd (also with LIDFQueryMixin.winner_only)."""
     from implicit_depth_b200.models.pipeline import LIDF, default_opt
     d, cfg, off, prob, part, ref, _ = load_golden("ief_ragged_2x24x32")
     z = np.load(os.path.join(GOLDEN_DIR, "gradk_ief_ragged_2x24x32.npz"))
@@ -271,7 +305,9 @@ def test_mixin_training_step_populates_param_grads_and_matches_goldens():
     dd["full_rgb_feat"] = dd["full_rgb_feat"].clone().requires_grad_(True)
     dd["occ_voxel_feat"] = dd["occ_voxel_feat"].clone().requires_grad_(True)
     lidf.train()
+    lidf.winner_only = winner_only
     lidf.get_pred(dd, "train", 100)
+    assert ("pair_pred_pos" in dd) == (not winner_only)
     assert dd["pred_pos"].requires_grad and dd["pred_prob_end"].requires_grad and not dd["pred_prob_end_softmax"].requires_grad
     loss = (torch.from_numpy(z["c_pos"]).to(_dev()) * dd["pred_pos"]).sum() + (torch.from_numpy(z["c_prob"]).to(_dev()) * dd["pred_prob_end"]).sum()
     assert abs(float(loss.detach()) - float(z["loss"])) < 1e-3 * max(1.0, abs(float(z["loss"])))
