@@ -549,10 +549,10 @@ __device__ __forceinline__ void ray_terminate_full_warp(const float* __restrict_
     if (ob > best || (ob == best && oi < best_id)) { best = ob; best_id = oi; }
   }
   if (lane == 0) { max_pair_id[ray] = (e > s) ? (int64_t)best_id : P; if (win) win[ray] = (e > s) ? best_id : -1; }
-  if (lane < 3 && pair_pred_pos) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
+  if (lane < 3 && !win) pred_pos[ray * 3 + lane] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + lane] : 0.f;
 }
 
-// pair_pred_pos == nullptr (winner-only mode): pred_pos is not gathered here (the offset decoder writes it for the winners
+// win != nullptr (winner-only mode): pred_pos is not gathered here (the offset decoder writes it for the winners
 // afterwards); win [R] receives each ray's arg-max pair, -1 for a ray without pairs.
 __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __restrict__ pair_pred_pos,
                                 const float* __restrict__ label, const int* __restrict__ ray_start,
@@ -593,7 +593,7 @@ __global__ void k_ray_terminate(const float* __restrict__ logit, const float* __
     }
     if (small) {
       if (gl == 0) { max_pair_id[ray] = (e > s) ? (int64_t)best_id : P; if (win) win[ray] = (e > s) ? best_id : -1; }
-      if (gl < 3 && pair_pred_pos) pred_pos[ray * 3 + gl] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + gl] : 0.f;
+      if (gl < 3 && !win) pred_pos[ray * 3 + gl] = (e > s) ? pair_pred_pos[(int64_t)best_id * 3 + gl] : 0.f;
     }
   }
   // ---- rays with more than 8 pairs: the whole warp, one ray at a time

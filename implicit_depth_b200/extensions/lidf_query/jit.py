@@ -397,6 +397,9 @@ class _LidfQuery:
         ``max_pair_id`` for RefineNet, reference pipeline.py:942); the four per-pair tensors are 24 B per query point of
         D2H that only the training losses look at.  The index arrays in ``host`` may be int32 (see ``_widen``)."""
         outputs = tuple(outputs) if outputs is not None else self.OUTPUT_KEYS
+        if kw.get("winner_only") and any(k in ("pred_offset", "pair_pred_pos") for k in outputs):
+            raise RuntimeError("forward_host(winner_only=True): pred_offset / pair_pred_pos are not produced in that mode; "
+                               "ask for outputs=('pred_pos', 'max_pair_id', ...)")
         dev = torch.device(device)
         B = int(host["full_rgb_feat"].shape[0])
         P = int(host["occ_vox_intersect_idx"].shape[0]); R = int(host["miss_ray_dir"].shape[0])

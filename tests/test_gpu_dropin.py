@@ -13,6 +13,18 @@ from oracle import ref_loader
 pytestmark = [pytest.mark.gpu, pytest.mark.skipif(ref_loader.find_ref_src() is None, reason="reference tree not available")]
 
 
+@pytest.fixture(autouse=True)
+def _same_convolutions_in_both_models():
+    """The two models run the SAME ResNet weights in two separate forward calls.  cuDNN is free to pick a different
+    convolution algorithm per call (its heuristics look at the free workspace, which depends on what ran before in the
+    process), and two algorithms differ by ~1e-7 absolute in full_rgb_feat -- enough to flip a near-tie arg-max of one ray in
+    12,288 and move its pred_pos by a voxel.  Pin the algorithm choice so that the comparison sees the replaced path only."""
+    old = (torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32)
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = True, False, False
+    yield
+    torch.backends.cudnn.deterministic, torch.backends.cudnn.benchmark, torch.backends.cudnn.allow_tf32 = old
+
+
 def _run(lidf, batch, exp_type, epoch, seed):
     torch.manual_seed(seed); np.random.seed(seed)                     # sample_valid_points / get_miss_ray draw random numbers
     return lidf(dict(batch), exp_type, epoch)
@@ -50,10 +62,12 @@ def test_reference_forward_with_mixin_matches_pure_reference(bs, mixin_methods):
     assert dd_r["pred_pos"].shape == dd_o["pred_pos"].shape == (bs * 96 * 128, 3)
     assert torch.equal(dd_r["occ_vox_intersect_idx"], dd_o["occ_vox_intersect_idx"])
     assert torch.equal(dd_r["miss_ray_intersect_idx"], dd_o["miss_ray_intersect_idx"])
-    for k in ("pred_prob_end", "pred_prob_end_softmax", "pair_pred_pos", "pred_pos"):
+    for k in ("pred_prob_end", "pred_prob_end_softmax", "pair_pred_pos"):
         assert rel_err(dd_o[k].cpu(), dd_r[k].cpu()) < 1e-3, k
-    agree = float((dd_r["max_pair_id"] == dd_o["max_pair_id"]).float().mean())
+    same = dd_r["max_pair_id"] == dd_o["max_pair_id"]           # a near-tie of two pairs' probabilities may resolve either way
+    agree = float(same.float().mean())                          # within 1e-3; pred_pos is compared where the winner agrees
     assert agree > 0.995, agree
+    assert rel_err(dd_o["pred_pos"][same].cpu(), dd_r["pred_pos"][same].cpu()) < 1e-3
     assert set(loss_r) == set(loss_o)
     for k, v in loss_r.items():
         a, b = float(loss_o[k]), float(v)

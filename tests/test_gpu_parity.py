@@ -461,6 +461,12 @@ def test_forward_host_pipeline_matches_device_call(ragged):
                                            outputs=("pred_pos", "max_pair_id"))
         assert sorted(got3) == ["max_pair_id", "pred_pos"] and h2d3 < h2d and d2h3 == got3["pred_pos"].numel() * 4 + got3["max_pair_id"].numel() * 8
         assert torch.equal(got3["pred_pos"], want["pred_pos"].cpu()) and torch.equal(got3["max_pair_id"], want["max_pair_id"].cpu())
+        got4, _, _ = lq.forward_host(host32, off, prob, "cuda", part_size=d["part_size"], min_chunk_pairs=chunk,
+                                     outputs=("pred_pos", "max_pair_id", "pred_prob_end_softmax"), winner_only=True)
+        for k in got4:                                          # winner-only mode through the host pipeline: same bits
+            assert torch.equal(got4[k], want[k].cpu()), k
+    with pytest.raises(RuntimeError, match="not produced"):
+        lq.forward_host(host32, off, prob, "cuda", part_size=d["part_size"], winner_only=True)
 
 
 def test_forward_host_falls_back_when_slices_are_not_self_contained():
