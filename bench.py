@@ -543,7 +543,9 @@ def run_train(args, d, ins, off, prob, kw, dev, rank, world, local):
                               kernel="k_mlp_tc + k_mlp_bwd_tc + k_wgrad_tc", kernel_ms=k_ms, kernel_share_of_step=k_ms / ms_per_step,
                               flop_per_point_nominal=flop_pt, peak_source=peaks["source"] + ", bf16_tflops_sustained",
                               note="nominal forward + backward FLOPs of the reference's Linear stack (3 x forward) over the "
-                                   "decoder kernel of the forward plus the backward's tcgen05 section"),
+                                   "decoder kernel of the forward plus the backward's tcgen05 section; the backward skips the offset "
+                                   "decoder's rows whose upstream gradient is exactly zero (all but one pair per ray: the loss "
+                                   "reads pred_pos and pred_prob_end only), so executed work is well below nominal"),
                 e2e=None, cpu_baseline=None)
     print(json.dumps(line), flush=True)
     if world > 1:

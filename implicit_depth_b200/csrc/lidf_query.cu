@@ -743,8 +743,8 @@ int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
   b->colpart = bm.take<float>((size_t)b->n_cta * TC_ROW_WARPS * 32 * BW_COLPART);
   b->du = bm.take<float>(256); b->dc = bm.take<float>(256);
   const bool wo = fp.winner_only_offset != 0;
-  b->win = wo ? bm.take<int>((size_t)(R > 0 ? R : 1)) : nullptr;
-  b->iota = wo ? bm.take<int>((size_t)R + 1) : nullptr;
+  b->win = bm.take<int>((size_t)(R > 0 ? R : 1));
+  b->iota = bm.take<int>((size_t)R + 1);
   b->g0r = wo ? bm.take<float>((size_t)(R > 0 ? R : 1)) : nullptr;
   b->bytes = bm.off + 256;
   return LIDF_OK;
@@ -828,6 +828,11 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     if (p->winner_only_offset && (!p->pred_offset_ray || bp->g_pred_offset || bp->g_pair_pred_pos)) return LIDF_ERR_ARG;
   }
   const bool wo = p->winner_only_offset != 0;
+  // The offset decoder's upstream gradient is non-zero on ONE pair per ray unless the caller differentiates pred_offset /
+  // pair_pred_pos themselves (the reference's loss never does: pos_loss sees pred_pos = pair_pred_pos[max_pair_id],
+  // pipeline.py:449-454,472).  Rows with a zero upstream gradient contribute exactly zero to every gradient, so the offset
+  // decoder's backward then runs over the R winner rows only -- also after a full (not winner-only) forward.
+  const bool rows_by_ray = wo || (!bp->g_pred_offset && !bp->g_pair_pred_pos);
   if (p->prob_dec.kind != LIDF_DEC_IMNET) return LIDF_ERR_UNSUPPORTED;
   if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
   BwdPlan b;
@@ -895,9 +900,11 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     }
     k_bwd_seed<<<(unsigned)((P + 255) / 256), 256, 0, st>>>(a);
     LIDF_LAUNCH_CHECK();
-    if (wo) {
+    if (rows_by_ray) {
       k_bwd_winner_rows<<<(unsigned)((R + 1 + 255) / 256), 256, 0, st>>>(p->max_pair_id, P, R, b.win, b.iota);
       LIDF_LAUNCH_CHECK();
+    }
+    if (wo) {
       k_bwd_seed_rays<<<(unsigned)((R + 255) / 256), 256, 0, st>>>(bp->g_pred_pos, p->miss_ray_dir, p->pred_offset_ray, b.win, R,
                                                                     a.scale, a.sig0, b.g0r);
       LIDF_LAUNCH_CHECK();
@@ -923,7 +930,8 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     LIDF_CUDA(cudaMemsetAsync(b.partial, 0, sizeof(float) * b.partial_floats * b.n_cta, st));
     LIDF_CUDA(cudaMemsetAsync(b.colpart, 0, sizeof(float) * (size_t)b.n_cta * TC_ROW_WARPS * 32 * BW_COLPART, st));
     // rows of this decoder's backward: all P pairs in ray-major order, or (winner-only mode, offset decoder) one row per ray
-    const bool by_ray = wo && d == 0;
+    const bool by_ray = rows_by_ray && d == 0;
+    const bool by_slot = wo && d == 0;              // seeds / saved offsets indexed by ray (winner-only forward) or by pair
     const int64_t n_dom = by_ray ? R : P;
     const int* row_perm = by_ray ? b.win : q.csr.perm;
     const int* row_ray_start = by_ray ? b.iota : q.csr.ray_start;
@@ -933,7 +941,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
       for (int it = n_pass - 1; it >= 0; --it) {
         BwArgs a{};
         a.P = P; a.s0 = s0; a.n_rows = n_rows; a.n_tiles = n_tiles;
-        a.by_slot = by_ray ? 1 : 0;
+        a.by_slot = by_slot ? 1 : 0;
         a.perm = row_perm; a.pair_vox = p->pair_vox; a.pair_ray = p->pair_ray; a.pair_dist = p->pair_dist;
         a.dense_dist = p->dense_dist; a.R = R; a.V = V; a.ray_dir = p->miss_ray_dir; a.voxel_bound = p->voxel_bound;
         a.rel = p->intersect_pos_rel; a.Av = q.Av; a.T = q.T; a.dcol = 256 * d;
@@ -941,8 +949,8 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
         a.wbwd = b.wbwd + (size_t)d * BW_CHUNKS_BWD * TC_CHUNK_BYTES;
         a.u = ief ? q.sp.u[d] : nullptr; a.b2 = dc.b2; a.b3 = dc.b3; a.w4 = dc.w4;
         a.is_ief = ief ? 1 : 0; a.it = it; a.o0 = ief ? dc.init_offset : 0.f;
-        a.o_in = (ief && it > 0) ? bp->ief_iter + (size_t)(it - 1) * n_dom : nullptr;     // [n_iter-1][P], or [..][R] by ray
-        a.g = by_ray ? b.g0r : b.g[d];
+        a.o_in = (ief && it > 0) ? bp->ief_iter + (size_t)(it - 1) * (by_slot ? R : P) : nullptr;   // [n_iter-1][P], or [..][R] by ray
+        a.g = by_slot ? b.g0r : b.g[d];
         a.h1 = b.h1; a.h2 = b.h2; a.d1 = b.d1; a.d2 = b.d2; a.d3 = b.d3;
         a.pe = it == n_pass - 1 ? b.pe : nullptr;
         a.d1_accumulate = it == n_pass - 1 ? 0 : 1;

@@ -240,8 +240,16 @@ def test_winner_only_backward_equals_the_full_backward(offdec, n_iter, rel, sigm
     out, _ = _native_grads(d, cfg, off, prob, part, coef)
     mp = out["max_pair_id"].cpu()
     coef, kept = mask_coefficients(coef, kink_margin(d, cfg, off, prob), d["miss_ray_intersect_idx"], mp)
-    out_f, full = _native_grads(d, cfg, off, prob, part, coef, chunk_rows=chunk)
+    # an explicit (all-zero) dL/d pred_offset forces the backward over ALL rows of the offset decoder; without it the full
+    # call also restricts itself to the winner rows (the only ones with a non-zero upstream gradient)
+    out_f, full = _native_grads(d, cfg, off, prob, part, dict(coef, pred_offset=torch.zeros(P, 1)), chunk_rows=chunk)
+    out_s, skip = _native_grads(d, cfg, off, prob, part, coef, chunk_rows=chunk)
     out_w, win = _native_grads(d, cfg, off, prob, part, coef, chunk_rows=chunk, winner_only=True)
+    for mod in ("offset_dec", "prob_dec"):
+        for k in full[mod]:
+            assert rel_err(skip[mod][k].cpu(), full[mod][k].cpu()) < 1e-4, (mod, k)
+    assert rel_err(skip["full_rgb_feat"].cpu(), full["full_rgb_feat"].cpu()) < 1e-4
+    assert rel_err(skip["occ_voxel_feat"].cpu(), full["occ_voxel_feat"].cpu()) < 1e-4
     assert torch.equal(out_w["pred_pos"], out_f["pred_pos"]) and torch.equal(out_w["max_pair_id"], out_f["max_pair_id"])
     assert "pred_offset" not in out_w and out_w["ief_iter"].shape == (max(n_iter - 1, 0) if offdec == "IEF" else 0, R)
     for mod in ("offset_dec", "prob_dec"):
