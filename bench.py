@@ -154,31 +154,76 @@ def cpu_reference_points_per_s(workload, offdec, budget_pairs, steps=1, warmup=0
     off = O.init_decoder(offdec, 385, mode="trained", generator=g)
     prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
     P = d["occ_vox_intersect_idx"].shape[0]
+    # The reference itself when its tree is available (baseline/_ref/src travels with the repo snapshot; /root/reference/src in
+    # the build container): the UNMODIFIED LIDF.get_embedding + LIDF.get_pred on the host cores, one call over the sample as
+    # the reference runs it (torch_scatter -> oracle/ref_loader.py's torch shim, the two producers stubbed with the
+    # sample's features).  Otherwise the oracle port of the same op chain.
+    run, kind = None, "port"
+    from oracle import ref_loader
+    if ref_loader.find_ref_src() is not None:
+        try:
+            import contextlib
+            cpu = torch.device("cpu")
+            with contextlib.redirect_stdout(sys.stderr):
+                ref, opt = ref_loader.load({"model.offdec_type": offdec})
+                lidf = ref.LIDF(opt, cpu).eval()
+            lidf.offset_dec.load_state_dict(off); lidf.prob_dec.load_state_dict(prob)
+
+            class _Fixed(torch.nn.Module):
+                def __init__(self, v):
+                    super().__init__(); self.v = v
+
+                def forward(self, *a, **kw):
+                    return self.v
+            R0, V0 = int(d["miss_ray_dir"].shape[0]), int(d["voxel_bound"].shape[0])
+            lidf.resnet_model = _Fixed(d["full_rgb_feat"]); lidf.pnet_model = _Fixed(d["occ_voxel_feat"])
+            dense = torch.zeros(V0, R0, 2)
+            dense[d["occ_vox_intersect_idx"], d["miss_ray_intersect_idx"]] = d["intersect_dist"]
+            base = dict(bs=1, h=rows, w=W, dist=dense, occ_vox_intersect_idx=d["occ_vox_intersect_idx"],
+                        miss_ray_intersect_idx=d["miss_ray_intersect_idx"], miss_ray_dir=d["miss_ray_dir"],
+                        miss_img_ind=d["miss_img_ind"], miss_bid=d["miss_bid"], voxel_bound=d["voxel_bound"],
+                        occ_vox_bid=d["occ_vox_bid"], rgb_img=torch.zeros(1, 3, rows, W), valid_rgb=torch.zeros(4, 3),
+                        valid_v_pid=torch.zeros(4, dtype=torch.long), valid_v_rel_coord=torch.zeros(4, 3),
+                        revidx=torch.zeros(4, dtype=torch.long), part_size=d["part_size"], total_miss_sample_num=R0,
+                        item_path=["synthetic"])
+
+            def run():
+                dd = dict(base)
+                lidf.get_embedding(dd)
+                lidf.get_pred(dd, "test", 0)
+                return dd["pred_pos"]
+            kind = "reference"
+            roi_name = "unmodified reference LIDF.get_embedding + get_pred (torch CPU ops, torchvision roi_align, torch_scatter shim)"
+        except Exception as e:                                                       # noqa: BLE001
+            progress(f"reference tree present but not runnable on the CPU ({type(e).__name__}: {e}); timing the port")
+            run, kind = None, "port"
+    if run is None:
+        run = lambda: O.lidf_query_chunked(d, cfg, off, prob, d["part_size"], chunk_pairs=1 << 18, roi_fn=roi_fn)
     times = []
     with torch.no_grad():
         for i in range(warmup + steps):
             t0 = time.perf_counter()
-            O.lidf_query_chunked(d, cfg, off, prob, d["part_size"], chunk_pairs=1 << 18, roi_fn=roi_fn)
+            run()
             if i >= warmup:
                 times.append(time.perf_counter() - t0)
     t = sum(times) / len(times)
     sample = f"{rows}x{W} rays x {N} pairs = {P} points of the {workload} workload, {steps} pass(es), {roi_name}"
-    return P / t, t, threads, sample, P
+    return P / t, t, threads, sample, P, kind
 
 
 def run_reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    pts, t, threads, sample, P = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs,
-                                                            steps=max(1, args.steps), warmup=min(args.warmup, 1))
+    pts, t, threads, sample, P, kind = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs,
+                                                                  steps=max(1, args.steps), warmup=min(args.warmup, 1))
     B, H, W, N = WORKLOADS[args.workload]
     line = dict(impl="reference", metric="lidf_query_points_per_sec", value=pts, unit="points/s", n_gpus=args.gpus,
                 steps=args.steps, warmup=args.warmup, ms_per_step=t * 1e3, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=f"{args.workload}: {H}x{W} rays x {N} pairs/ray, decoders {args.offdec}+IMNET "
                                      f"(bounded sample of it, see cpu_baseline.sample)"),
-                cpu_baseline=dict(value=pts, unit="points/s", cores=threads, kind="port", sample=sample, device="cpu"),
+                cpu_baseline=dict(value=pts, unit="points/s", cores=threads, kind=kind, sample=sample, device="cpu"),
                 device="cpu (host cores; the same-GPU torch arm is torch_gpu_baseline in the default line)",
                 e2e=dict(value=pts, unit="points/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0), gpu_launches=0)
     print(json.dumps(line), flush=True)
@@ -412,8 +457,8 @@ def main():
     progress("e2e done")
     cpu = None
     if not args.no_cpu_baseline and world == 1:     # the CPU baseline is an N = 1 figure (rank 0, all host cores)
-        pts, tcpu, threads, sample, _ = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs)
-        cpu = dict(value=pts, unit="points/s", cores=threads, kind="port", sample=sample, seconds=tcpu, device="cpu")
+        pts, tcpu, threads, sample, _, ckind = cpu_reference_points_per_s(args.workload, args.offdec, args.cpu_sample_pairs)
+        cpu = dict(value=pts, unit="points/s", cores=threads, kind=ckind, sample=sample, seconds=tcpu, device="cpu")
     line = dict(metric="lidf_query_points_per_sec", value=value, unit="points/s", n_gpus=world, steps=args.steps,
                 warmup=max(3, args.warmup), ms_per_step=ms_per_step, higher_is_better=True, scaling="weak",
                 vs_baseline=None, dtype="bf16x3 (split bf16 operands, fp32 accumulate)" if args.engine != "simt_fp32" else "f32",

@@ -427,6 +427,32 @@ class _LidfQuery:
             call.run_monolithic()
         return call
 
+    GEOMETRY_KEYS = ("full_rgb_feat", "occ_voxel_feat", "miss_ray_dir", "miss_img_ind", "miss_bid", "voxel_bound", "occ_vox_bid")
+
+    def forward_host_from_geometry(self, host: Dict[str, torch.Tensor], offset_dec, prob_dec, device, outputs=("pred_pos", "max_pair_id"),
+                                   **kw):
+        """The call a real pipeline makes when the pair list does not exist on the host yet (reference
+        ``compute_ray_aabb`` -> ``get_embedding`` -> ``get_pred``, pipeline.py:271-296,338-466): HOST buffers of the two feature
+        tensors, the rays and the occupied voxels' boxes (``GEOMETRY_KEYS``; ``miss_bid`` / ``occ_vox_bid`` int32 or int64) go
+        to the device, the pairs are generated THERE, ray-major (``ray_aabb.pairs(order="ray")``: no regroup in the forward),
+        and the requested outputs come back.  H2D per query point: nothing -- the 16-24 bytes per pair of index / distance
+        arrays never cross PCIe.  Returns (out_host dict incl. the device-side pair count ``n_pairs``, h2d_bytes, d2h_bytes).
+        ``max_pair_id`` indexes the ray-major list, which is also returned on request (``outputs`` may name
+        ``occ_vox_intersect_idx`` / ``miss_ray_intersect_idx`` / ``intersect_dist``)."""
+        from implicit_depth_b200.extensions.ray_aabb.jit import ray_aabb
+        dev = torch.device(device)
+        h2d = sum(host[k].numel() * host[k].element_size() for k in self.GEOMETRY_KEYS)
+        g = {k: host[k].to(dev, non_blocking=True) for k in self.GEOMETRY_KEYS}
+        vox, ray, dist = ray_aabb.pairs(g["miss_ray_dir"], g["voxel_bound"], g["miss_bid"].int(), g["occ_vox_bid"].int(), order="ray")
+        out = self.forward(g["full_rgb_feat"], g["occ_voxel_feat"], g["miss_ray_dir"], g["miss_img_ind"].long(), g["miss_bid"].long(),
+                           g["voxel_bound"], vox, ray, dist, offset_dec, prob_dec, pairs_ray_major=True, **kw)
+        out.update(occ_vox_intersect_idx=vox, miss_ray_intersect_idx=ray, intersect_dist=dist)
+        res = {k: out[k].to("cpu", non_blocking=True) for k in outputs}
+        torch.cuda.current_stream(dev).synchronize()
+        res["n_pairs"] = int(vox.shape[0])
+        d2h = sum(v.numel() * v.element_size() for k, v in res.items() if k != "n_pairs")
+        return res, h2d, d2h
+
     def _enqueue_host_pipeline(self, call: "_HostCall", splits, groups) -> None:
         """Three-stage pipeline over image groups; nothing here waits on the host."""
         host, dev, out_host, kw = call.host, call.dev, call.out_host, call.kw

@@ -379,3 +379,30 @@ def test_ray_aabb_tile_culling_is_conservative(H, W, B):
     d2 = d.copy(); d2[1500 % d.shape[0]] = np.array([0.3, -0.2, -0.9], np.float32); d2[7] = np.array([1.0, 0.0, 0.0], np.float32)
     mask2, dist2 = A.ray_aabb_dense(d2, vb, rb, xb)
     _check_ray(d2, vb, rb, xb, mask2, dist2, A.ray_aabb_pairs(d2, vb, rb, xb))
+
+
+def test_forward_host_from_geometry_equals_pairs_on_the_host():
+    """lidf_query.forward_host_from_geometry: rays + voxel boxes + features from HOST buffers, pairs generated on the device
+    (ray-major, no regroup).  Must give what forward_host gives for the same geometry's pair list shipped from the host, with
+    a fraction of the H2D bytes; the winner-only mode through it as well."""
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query as lq
+    from implicit_depth_b200.synthetic import make_inputs
+    from oracle import lidf_oracle as O
+    ray_aabb, _ = _ext()
+    d = make_inputs(2, 30, 40, 1, V_img=60, seed=93)
+    g = torch.Generator().manual_seed(94)
+    off = {k: v.cuda() for k, v in O.init_decoder("IEF", 385, mode="trained", generator=g).items()}
+    prob = {k: v.cuda() for k, v in O.init_decoder("IMNET", 385, mode="trained", generator=g).items()}
+    vox, ray, dist = ray_aabb.pairs(d["miss_ray_dir"].cuda(), d["voxel_bound"].cuda(), d["miss_bid"].int().cuda(),
+                                    d["occ_vox_bid"].int().cuda(), order="ray")
+    host = {k: d[k].pin_memory() for k in lq.GEOMETRY_KEYS}
+    hostp = dict({k: d[k].pin_memory() for k in lq.INPUT_KEYS if k in lq.GEOMETRY_KEYS},
+                 occ_vox_intersect_idx=vox.cpu().pin_memory(), miss_ray_intersect_idx=ray.cpu().pin_memory(),
+                 intersect_dist=dist.cpu().pin_memory(), occ_vox_bid=d["occ_vox_bid"])
+    want, h2d_p, _ = lq.forward_host(hostp, off, prob, "cuda", part_size=d["part_size"], outputs=("pred_pos", "max_pair_id"))
+    got, h2d_g, d2h_g = lq.forward_host_from_geometry(host, off, prob, "cuda", part_size=d["part_size"])
+    assert got["n_pairs"] == vox.shape[0] > 0 and h2d_g < h2d_p
+    assert torch.equal(got["pred_pos"], want["pred_pos"]) and torch.equal(got["max_pair_id"], want["max_pair_id"])
+    got2, _, _ = lq.forward_host_from_geometry(host, off, prob, "cuda", part_size=d["part_size"], winner_only=True,
+                                               outputs=("pred_pos", "max_pair_id", "miss_ray_intersect_idx"))
+    assert torch.equal(got2["pred_pos"], want["pred_pos"]) and torch.equal(got2["miss_ray_intersect_idx"], ray.cpu())
