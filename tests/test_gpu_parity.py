@@ -926,3 +926,12 @@ def test_winner_only_mode_gives_the_same_per_ray_results(B, H, W, N, ragged, off
         assert bool(empty.any()) and float(win["pred_pos"][empty].abs().sum()) == 0.0
     with pytest.raises(RuntimeError):           # needs the tcgen05 engine: loud, not silent
         lq.forward(*ins, off, prob, winner_only=True, mlp_impl="simt_fp32", **kw)
+    # degenerate lists: no pair at all (every ray: zeros / arg = P = 0), a single pair
+    for n in (0, 1):
+        ins_n = list(ins)
+        for k in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist"):
+            i = lq.INPUT_KEYS.index(k); ins_n[i] = ins[i][:n].contiguous()
+        f = lq.forward(*ins_n, off, prob, part_size=d["part_size"])
+        w = lq.forward(*ins_n, off, prob, part_size=d["part_size"], winner_only=True, check_indices=True)
+        for k in ("pred_prob_end", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
+            assert torch.equal(w[k], f[k]), (n, k)
