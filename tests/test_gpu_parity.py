@@ -935,3 +935,33 @@ def test_winner_only_mode_gives_the_same_per_ray_results(B, H, W, N, ragged, off
         w = lq.forward(*ins_n, off, prob, part_size=d["part_size"], winner_only=True, check_indices=True)
         for k in ("pred_prob_end", "pred_prob_end_softmax", "max_pair_id", "pred_pos"):
             assert torch.equal(w[k], f[k]), (n, k)
+
+
+@pytest.mark.parametrize("want_roi", [False, True])
+def test_row_list_path_when_most_rays_own_no_pair(want_roi):
+    """Sparse regime with fewer than 3/4 of the rays owning a pair: k_rowprep_tc walks the live-ray list (several tiles per CTA
+    at this size), ROIAlign runs on live rays only unless the per-ray feature is an output.  Two thirds of the rays lose their
+    pairs; results against the oracle on a subset of the rays, zeros / arg = P on the rays without a pair."""
+    from implicit_depth_b200.synthetic import make_inputs
+    lq = _lq()
+    d = make_inputs(2, 120, 160, 3, V_img=64, seed=61, ragged=True)           # 38,400 rays -> 300 row-prep tiles
+    keep = (d["miss_ray_intersect_idx"] % 3) == 0
+    for k in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist"):
+        d[k] = d[k][keep].contiguous()
+    P, R = d["occ_vox_intersect_idx"].shape[0], d["miss_ray_dir"].shape[0]
+    assert 0 < torch.unique(d["miss_ray_intersect_idx"]).numel() * 4 < R * 3 and P < 8 * R
+    g = torch.Generator().manual_seed(62)
+    off = O.init_decoder("IEF", 385, mode="trained", generator=g)
+    prob = O.init_decoder("IMNET", 385, mode="trained", generator=g)
+    cfg = dict(O.DEFAULT_CFG)
+    sel = torch.arange(0, R, 7)                                               # oracle on a subset of the rays (it is per-pair work)
+    m = torch.isin(d["miss_ray_intersect_idx"], sel)
+    out = _run(d, cfg, off, prob, d["part_size"], "auto", want_roi_feat=want_roi)
+    sub = dict(d)
+    for k in ("occ_vox_intersect_idx", "miss_ray_intersect_idx", "intersect_dist"):
+        sub[k] = d[k][m]
+    ref = O.lidf_query(sub, cfg, off, prob, d["part_size"], dedup_rays=True)
+    for k in ("pred_offset", "pred_prob_end", "pair_pred_pos"):
+        assert rel_err(out[k].cpu()[m], ref[k]) < TOL_TC, k
+    live = torch.zeros(R, dtype=torch.bool); live[d["miss_ray_intersect_idx"]] = True
+    assert float(out["pred_pos"].cpu()[~live].abs().sum()) == 0.0 and bool((out["max_pair_id"].cpu()[~live] == P).all())
