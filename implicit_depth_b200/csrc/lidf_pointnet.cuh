@@ -421,6 +421,10 @@ __global__ void __launch_bounds__(PNT_THREADS, 1) k_pn_stage2_tc(const float* __
       // ---- layer-4 epilogue: relu(acc + b4) -> O[channel][point] (XOR-swizzled columns: conflict-free both ways)
       tc::mbar_wait(&S.d4_full, ph);
       tc::fence_after_sync();
+      // O overlays the layer-3 operand tile.  Every warp's operand stores are ordered before this point through the mbarrier
+      // chain (a_ready -> MMAs -> d3_full -> a4_ready -> MMAs -> d4_full); the explicit barrier states that for tools that do
+      // not follow mbarriers (compute-sanitizer racecheck) at the price of one bar.sync per tile.
+      asm volatile("bar.sync 1, %0;" ::"n"(PNT_ROW_WARPS * 32) : "memory");
       {
         uint32_t r[32];
         tc::tmem_ld32(lane_addr + COL_D4 + 32 * g, r);
