@@ -118,12 +118,32 @@ struct BwArgs {
   int is_ief; int it; float o0;
   const float* o_in;                                // [P] offset fed to this iteration (original index); NULL: o0
   float* g;                                         // [P] in: dL/d o_it, out (IEF, it > 0): dL/d o_{it-1}
-  float* h1; float* h2; float* d1; float* d2; float* d3; float* pe;   // chunk-local rows; pe NULL = do not write
+  float* h1; float* h2; float* d2; float* d3;       // chunk-local, PACKED split-bf16 hand-over to k_wgrad_pk_tc (layout: bw_pk_*)
+  float* d1; float* pe;                             // chunk-local fp32 rows (delta1 has three readers); pe NULL = do not write
   int d1_accumulate;
   float* colpart;                                   // [grid][16][32][BW_COLPART], accumulated
   int by_slot;                                      // winner-only backward of the offset decoder: rows = rays (perm = each ray's
                                                     // arg-max pair, -1: none), g / o_in indexed by the row's slot s0 + row
 };
+
+// ---- packed hand-over B1 -> k_wgrad_pk_tc ("PK" layout) ------------------------------------------------------------
+// The wgrad GEMMs contract over the ROW index (K = pair), and B1 owns one row per thread.  A tensor X[rows][F] is handed
+// over already split into bf16 hi | lo and already in the shared-memory layout the MN-major UMMA descriptor wants, so that
+// the wgrad kernel only has to bulk-copy it (TMA) -- no conversion, no transpose, no register staging on either side:
+//   group G = row / 64 (one pipeline stage of the wgrad kernel), 64 F 4 bytes each:
+//     [hi: F/8 feature groups][64 rows][16 B = 8 consecutive features of that row, bf16]  then  [lo: same]
+// i.e. in UMMA terms ((8 features),(8 rows, 8 row groups)) with LBO = 128 B between 8-row core matrices and SBO = 1 KB
+// between feature groups (cute: "Major-MN, INTERLEAVE: ((1,n),(8,k)):((X,SBO),(1,LBO))" in 16-byte units).
+// Same bytes per element as fp32 (2 + 2), same arithmetic (the split is the one B1 makes for its own TMEM operands).
+#define BW_PK_ROWS 64
+#define BW_PK_FG_BYTES (BW_PK_ROWS * 16)          // one feature group: 64 rows x 16 B
+__host__ __device__ inline size_t bw_pk_group_bytes(int F) { return (size_t)BW_PK_ROWS * F * 4; }
+__host__ __device__ inline size_t bw_pk_lo_offset(int F) { return (size_t)(F / 8) * BW_PK_FG_BYTES; }
+// address of the 16-byte hi unit holding features [f0, f0 + 8) (f0 % 8 == 0) of chunk row `rl`
+__device__ __forceinline__ uint8_t* bw_pk_ptr(float* tensor, int F, int64_t rl, int f0) {
+  return reinterpret_cast<uint8_t*>(tensor) + (size_t)(rl / BW_PK_ROWS) * bw_pk_group_bytes(F) + (size_t)(f0 >> 3) * BW_PK_FG_BYTES +
+         (size_t)(rl % BW_PK_ROWS) * 16;
+}
 
 #define BW_SLOTS 8                     // weight ring: 8 x 8 KB chunks
 #define BW_STAGE_PITCH 36              // floats per row of a staging tile (32 + 4: conflict-free 128-bit accesses)
@@ -340,6 +360,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       __syncwarp();
     };
+    // packed hand-over (bw_pk_*): 16 features [f0, f0 + 16) of this lane's row, w = 8 hi words | 8 lo words as split16 makes
+    // them.  One instruction covers the warp's 32 consecutive rows x 16 B = 512 contiguous bytes: no transpose needed.
+    auto store_pk16 = [&](float* tensor, int F, int tile_local, int f0, const uint32_t* w) {
+      uint8_t* p = bw_pk_ptr(tensor, F, (int64_t)tile_local * 128 + row, f0);
+      *reinterpret_cast<uint4*>(p) = make_uint4(w[0], w[1], w[2], w[3]);
+      *reinterpret_cast<uint4*>(p + BW_PK_FG_BYTES) = make_uint4(w[4], w[5], w[6], w[7]);
+      p += bw_pk_lo_offset(F);
+      *reinterpret_cast<uint4*>(p) = make_uint4(w[8], w[9], w[10], w[11]);
+      *reinterpret_cast<uint4*>(p + BW_PK_FG_BYTES) = make_uint4(w[12], w[13], w[14], w[15]);
+    };
     auto load32 = [&](float* x, const float* gbase, int pitch) {    // global rows -> this lane's row
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
@@ -494,12 +524,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           uint32_t w[16];
           tc::split16(xo + 16 * s16, w);
           tc::tmem_st16(lane_addr + xcol + 16 * s16, w);
+          store_pk16(a.h1, LIDF_H1, tile_local, n0 + 16 * s16, w);   // the same words go to the wgrad kernel (fire and forget)
         }
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.x_done[hf]);
-        store32(xo, a.h1 + wrow0 * LIDF_H1 + n0, LIDF_H1);        // after the hand-over: the layer-2 MMAs run meanwhile
       }
       // ---- operand of the next tile (its last reader, L1 of this tile, has retired once a1_free completes)
       if (has_next) {
@@ -526,12 +556,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           uint32_t w[16];
           tc::split16(xo + 16 * s16, w);
           tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16 * s16, w);
+          store_pk16(a.h2, LIDF_H2, tile_local, 32 * g + 16 * s16, w);
         }
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.y_done);
-        store32(xo, a.h2 + wrow0 * LIDF_H2 + 32 * g, LIDF_H2);
       }
       // ---- E3: z3 -> delta3 = g w4 leaky'(z3) (this thread: columns [16 g, 16 g + 16)), in place as the D2 operand
       {
@@ -554,11 +584,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
         uint32_t w[16];
         tc::split16(d3, w);
         tc::tmem_st16(lane_addr + TC_COL_Z + 16 * g, w);
+        store_pk16(a.d3, LIDF_H3, tile_local, 16 * g, w);
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.z_done);
-        store16(d3, a.d3 + wrow0 * LIDF_H3 + 16 * g, LIDF_H3);
         acc_k0 += bw_colreduce32(red, lane);                      // lanes 0-15: db3[16 g + l], 16-31: dw4[16 g + l - 16]
         if (g == 0) acc_b4 += gin;
       }
@@ -577,12 +607,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           uint32_t w[16];
           tc::split16(d2 + 16 * s16, w);
           tc::tmem_st16(lane_addr + TC_COL_Y + 32 * g + 16 * s16, w);
+          store_pk16(a.d2, LIDF_H2, tile_local, 32 * g + 16 * s16, w);
         }
         tc::wait_st();
         tc::fence_before_sync();
         __syncwarp();
         if (lane == 0) tc::mbar_arrive(&S.y2_done);
-        store32(d2, a.d2 + wrow0 * LIDF_H2 + 32 * g, LIDF_H2);
         acc_b2 += bw_colreduce32(d2, lane);                       // db2[32 g + l]
       }
       // ---- Ed1 x 2: delta1 = (delta2 W2) leaky'(z1) -> HBM (summed over the IEF passes), du, IEF feedback
@@ -730,54 +760,63 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
   } else {
     // ---- loaders: unit = (8-row group rg, 32-feature block); A blocks first, then B blocks
     const int a_blocks = a.M / 32, b_blocks = (N + 31) / 32, n_units = (a_blocks + b_blocks) * 8;
+    // A warp's units of a stage come in rounds of three (24 independent 128-byte loads in flight before any conversion: the
+    // kernel is bound by memory-level parallelism, not by instruction issue).  The first round of stage it + 1 is issued
+    // before the hand-over of stage it, so its latency runs under the fence, the arrive and the wait for the buffer.
+    auto unit_load = [&](int64_t row0, int un, float (&x)[8]) {
+      const int blk = un >> 3, rg = un & 7;
+      const bool isA = blk < a_blocks;
+      const int f = (isA ? blk : blk - a_blocks) * 32 + lane;
+      const float* src = isA ? a.A : a.B;
+      const int ld = isA ? a.lda : a.ldb;
+      const bool fok = isA ? true : (f < a.n_valid);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const int64_t rr = row0 + 8 * rg + i;
+        x[i] = (fok && rr < a.rows) ? __ldg(src + (size_t)rr * ld + f) : 0.f;
+      }
+    };
+    auto unit_store = [&](uint32_t sa, uint32_t sb, int un, const float (&x)[8]) {
+      const int blk = un >> 3, rg = un & 7;
+      const bool isA = blk < a_blocks;
+      const int f = (isA ? blk : blk - a_blocks) * 32 + lane;
+      uint32_t h[4], l[4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) tc::split2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+      const int ks = rg >> 1, kg = rg & 1;
+      if (isA) {
+        const uint32_t base = sa + (uint32_t)((f >> 7) * 4 + ks) * 8192u + kg * 2048u + (uint32_t)(f & 127) * 16u;
+        tc::st_shared_v4(base, h[0], h[1], h[2], h[3]);
+        tc::st_shared_v4(base + 4096u, l[0], l[1], l[2], l[3]);
+      } else if (f < N) {
+        const uint32_t base = sb + ks * (uint32_t)N * 64u + kg * (uint32_t)N * 16u + (uint32_t)f * 16u;
+        tc::st_shared_v4(base, h[0], h[1], h[2], h[3]);
+        tc::st_shared_v4(base + (uint32_t)N * 32u, l[0], l[1], l[2], l[3]);
+      }
+    };
+    float x0[8], x1[8], x2[8];
+    auto round_load = [&](int64_t row0, int un) {
+      unit_load(row0, un, x0);
+      if (un + WG_LOAD_WARPS < n_units) unit_load(row0, un + WG_LOAD_WARPS, x1);
+      if (un + 2 * WG_LOAD_WARPS < n_units) unit_load(row0, un + 2 * WG_LOAD_WARPS, x2);
+    };
+    auto round_store = [&](uint32_t sa, uint32_t sb, int un) {
+      unit_store(sa, sb, un, x0);
+      if (un + WG_LOAD_WARPS < n_units) unit_store(sa, sb, un + WG_LOAD_WARPS, x1);
+      if (un + 2 * WG_LOAD_WARPS < n_units) unit_store(sa, sb, un + 2 * WG_LOAD_WARPS, x2);
+    };
+    if (n_it > 0 && warp < n_units) round_load(g0 * WG_ROWS, warp);
     for (int it = 0; it < n_it; ++it) {
       const int buf = it & 1;
       if (it >= 2) bw_wait(&S.empty[buf], (uint32_t)((it >> 1) - 1) & 1u);
       const uint32_t sa = data0 + buf * stage_bytes, sb = sa + a_bytes;
       const int64_t row0 = (g0 + it) * WG_ROWS;
-      // three units per warp in flight (24 independent 128-byte loads) before any conversion: the kernel is bound by
-      // memory-level parallelism, not by instruction issue
-      auto unit_load = [&](int un, float (&x)[8]) {
-        const int blk = un >> 3, rg = un & 7;
-        const bool isA = blk < a_blocks;
-        const int f = (isA ? blk : blk - a_blocks) * 32 + lane;
-        const float* src = isA ? a.A : a.B;
-        const int ld = isA ? a.lda : a.ldb;
-        const bool fok = isA ? true : (f < a.n_valid);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) {
-          const int64_t rr = row0 + 8 * rg + i;
-          x[i] = (fok && rr < a.rows) ? __ldg(src + (size_t)rr * ld + f) : 0.f;
-        }
-      };
-      auto unit_store = [&](int un, const float (&x)[8]) {
-        const int blk = un >> 3, rg = un & 7;
-        const bool isA = blk < a_blocks;
-        const int f = (isA ? blk : blk - a_blocks) * 32 + lane;
-        uint32_t h[4], l[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) tc::split2(x[2 * j], x[2 * j + 1], h[j], l[j]);
-        const int ks = rg >> 1, kg = rg & 1;
-        if (isA) {
-          const uint32_t base = sa + (uint32_t)((f >> 7) * 4 + ks) * 8192u + kg * 2048u + (uint32_t)(f & 127) * 16u;
-          tc::st_shared_v4(base, h[0], h[1], h[2], h[3]);
-          tc::st_shared_v4(base + 4096u, l[0], l[1], l[2], l[3]);
-        } else if (f < N) {
-          const uint32_t base = sb + ks * (uint32_t)N * 64u + kg * (uint32_t)N * 16u + (uint32_t)f * 16u;
-          tc::st_shared_v4(base, h[0], h[1], h[2], h[3]);
-          tc::st_shared_v4(base + (uint32_t)N * 32u, l[0], l[1], l[2], l[3]);
-        }
-      };
-      for (int un = warp; un < n_units; un += 3 * WG_LOAD_WARPS) {
-        float x0[8], x1[8], x2[8];
-        const bool h1 = un + WG_LOAD_WARPS < n_units, h2 = un + 2 * WG_LOAD_WARPS < n_units;
-        unit_load(un, x0);
-        if (h1) unit_load(un + WG_LOAD_WARPS, x1);
-        if (h2) unit_load(un + 2 * WG_LOAD_WARPS, x2);
-        unit_store(un, x0);
-        if (h1) unit_store(un + WG_LOAD_WARPS, x1);
-        if (h2) unit_store(un + 2 * WG_LOAD_WARPS, x2);
+      if (warp < n_units) round_store(sa, sb, warp);                          // round 0: loaded one stage ahead
+      for (int un = warp + 3 * WG_LOAD_WARPS; un < n_units; un += 3 * WG_LOAD_WARPS) {
+        round_load(row0, un);
+        round_store(sa, sb, un);
       }
+      if (it + 1 < n_it && warp < n_units) round_load(row0 + WG_ROWS, warp);
       tc::fence_proxy_async();
       __syncwarp();
       if (lane == 0) tc::mbar_arrive(&S.full[buf]);
@@ -810,6 +849,144 @@ __global__ void __launch_bounds__(WG_THREADS, 1) k_wgrad_tc(const __grid_constan
   tc::fence_before_sync();
   __syncthreads();
   if (warp == WG_LOAD_WARPS) tc::tmem_dealloc(tmem, 512);
+}
+
+// ------------------------------------------------------------------------------------------------ B2, packed operands
+// C[128][N] += sum_rows A[row][m] B[row][n] with both operands in the PK layout (above): a stage = one 64-row group of A
+// and of B, fetched by two bulk copies (TMA) straight into the MN-major operand position; 4 k-steps x 3 products per
+// stage; accumulator resident in TMEM over all of the CTA's groups; per-CTA partial slices as in k_wgrad_tc.
+//   warps 0-7 : epilogue (TMEM -> partial slice), idle until the last MMA has retired
+//   warp 8    : producer, one thread: ring of n_stages (2-4, whatever fits in shared memory)
+//   warp 9    : MMA issuer, one thread
+// The kernel moves 4 (FA + FB) bytes per row and does nothing else with them: it is bound by HBM reads.
+#define WPK_EPI_WARPS 8
+#define WPK_THREADS ((WPK_EPI_WARPS + 2) * 32)
+#define WPK_MAX_STAGES 4
+struct WgPkArgs {
+  const uint8_t* A; int FA;           // FA = 128 (M)
+  const uint8_t* B; int FB;           // FB = N, a multiple of 16, <= 256
+  int64_t groups;                     // 64-row groups (whole tiles: B1 writes every row of a tile, dead rows as zeros in delta)
+  int n_stages;
+  float* partial;                     // [grid][128 * N], accumulated
+};
+struct WgPkSmemHdr { uint64_t full[WPK_MAX_STAGES], empty[WPK_MAX_STAGES], done; uint32_t tmem_base; };
+
+namespace tc {
+__device__ __forceinline__ void bulk_g2s_a(uint32_t dst_saddr, const void* src_gmem, uint32_t bytes, uint32_t bar_saddr) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_saddr),
+               "l"(src_gmem), "r"(bytes), "r"(bar_saddr)
+               : "memory");
+}
+// instruction descriptor with BOTH operands MN-major (bits 15, 16: cute::UMMA::InstrDescriptor a_major_ / b_major_)
+__host__ __device__ constexpr uint32_t make_idesc_mn(int N) { return make_idesc(N) | (1u << 15) | (1u << 16); }
+}  // namespace tc
+
+template <int NPROD>
+__global__ void __launch_bounds__(WPK_THREADS, 1) k_wgrad_pk_tc(const __grid_constant__ WgPkArgs a) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  WgPkSmemHdr& S = *reinterpret_cast<WgPkSmemHdr*>(smem_raw);
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const int N = a.FB, NS = a.n_stages;
+  const uint32_t a_bytes = (uint32_t)bw_pk_group_bytes(a.FA), b_bytes = (uint32_t)bw_pk_group_bytes(a.FB);
+  const uint32_t stage_bytes = a_bytes + b_bytes;
+  const uint32_t data0 = tc::smem_u32(smem_raw) + 1024u;
+  if (tid == 0) {
+    for (int i = 0; i < WPK_MAX_STAGES; ++i) { tc::mbar_init(&S.full[i], 1); tc::mbar_init(&S.empty[i], 1); }
+    tc::mbar_init(&S.done, 1);
+    tc::fence_barrier_init();
+  }
+  if (warp == WPK_EPI_WARPS + 1) tc::tmem_alloc(&S.tmem_base, 512);
+  tc::fence_before_sync();
+  __syncthreads();
+  tc::fence_after_sync();
+  const uint32_t tmem = S.tmem_base;
+  const int64_t per = (a.groups + gridDim.x - 1) / gridDim.x;
+  const int64_t g0 = (int64_t)blockIdx.x * per, g1 = g0 + per < a.groups ? g0 + per : a.groups;
+  const int n_it = g1 > g0 ? (int)(g1 - g0) : 0;
+
+  if (warp == WPK_EPI_WARPS) {
+    // ---- producer
+    if (tc::elect_one()) {
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % NS;
+        if (it >= NS) bw_wait(&S.empty[s], (uint32_t)(it / NS - 1) & 1u);
+        const uint32_t bar = tc::smem_u32(&S.full[s]);
+        tc::mbar_arrive_expect_tx(&S.full[s], stage_bytes);
+        tc::bulk_g2s_a(data0 + s * stage_bytes, a.A + (size_t)(g0 + it) * a_bytes, a_bytes, bar);
+        tc::bulk_g2s_a(data0 + s * stage_bytes + a_bytes, a.B + (size_t)(g0 + it) * b_bytes, b_bytes, bar);
+      }
+    }
+  } else if (warp == WPK_EPI_WARPS + 1) {
+    // ---- MMA issuer: D[m][n] (+)= sum over 16 rows of A[row][m] B[row][n], operands MN-major
+    if (tc::elect_one() && n_it > 0) {
+      const uint32_t idesc = tc::make_idesc_mn(N);
+      const uint32_t a_lo = (uint32_t)bw_pk_lo_offset(a.FA), b_lo = (uint32_t)bw_pk_lo_offset(a.FB);
+      for (int it = 0; it < n_it; ++it) {
+        const int s = it % NS;
+        bw_wait(&S.full[s], (uint32_t)(it / NS) & 1u);
+        tc::fence_after_sync();
+        const uint32_t sa = data0 + s * stage_bytes, sb = sa + a_bytes;
+#pragma unroll 1
+        for (int ks = 0; ks < BW_PK_ROWS / 16; ++ks) {
+          // k-step = 16 rows = two 8-row core matrices 128 B apart (LBO); feature groups 1 KB apart (SBO)
+          const uint64_t ahi = tc::make_bdesc(sa + ks * 256u, 128u, (uint32_t)BW_PK_FG_BYTES);
+          const uint64_t alo = tc::make_bdesc(sa + a_lo + ks * 256u, 128u, (uint32_t)BW_PK_FG_BYTES);
+          const uint64_t bhi = tc::make_bdesc(sb + ks * 256u, 128u, (uint32_t)BW_PK_FG_BYTES);
+          const uint64_t blo = tc::make_bdesc(sb + b_lo + ks * 256u, 128u, (uint32_t)BW_PK_FG_BYTES);
+          tc::mma_ss(tmem, ahi, bhi, idesc, (it > 0 || ks > 0) ? 1u : 0u);
+          if (NPROD == 3) {
+            tc::mma_ss(tmem, alo, bhi, idesc, 1u);
+            tc::mma_ss(tmem, ahi, blo, idesc, 1u);
+          }
+        }
+        tc::commit(&S.empty[s]);
+      }
+      tc::commit(&S.done);
+    }
+  } else if (n_it > 0) {
+    // ---- epilogue: TMEM -> this CTA's partial slice (accumulated across launches)
+    bw_wait(&S.done, 0);
+    tc::fence_after_sync();
+    const int q = warp & 3, cg = warp >> 2;
+    const uint32_t lane_addr = tmem + ((uint32_t)(q * 32) << 16);
+    float* part = a.partial + (size_t)blockIdx.x * 128 * N;
+    for (int blk = cg; blk < N / 16; blk += WPK_EPI_WARPS / 4) {
+      uint32_t r[16];
+      tc::tmem_ld16(lane_addr + 16 * blk, r);
+      tc::wait_ld();
+      float* dst = part + (size_t)(q * 32 + lane) * N + 16 * blk;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        float4 o = *reinterpret_cast<float4*>(dst + 4 * i);
+        o.x += __uint_as_float(r[4 * i]); o.y += __uint_as_float(r[4 * i + 1]);
+        o.z += __uint_as_float(r[4 * i + 2]); o.w += __uint_as_float(r[4 * i + 3]);
+        *reinterpret_cast<float4*>(dst + 4 * i) = o;
+      }
+    }
+  }
+  __syncwarp();
+  tc::fence_before_sync();
+  __syncthreads();
+  if (warp == WPK_EPI_WARPS + 1) tc::tmem_dealloc(tmem, 512);
+}
+
+// fp32 rows [rows][F] -> PK layout over ceil(rows / 64) groups, rows past the end as zeros (self test of k_wgrad_pk_tc)
+__global__ void k_pk_pack_rows(const float* __restrict__ X, int64_t rows, int F, uint8_t* __restrict__ out) {
+  const int64_t idx = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;        // one thread per (padded row, feature group)
+  const int fgs = F / 8;
+  const int64_t rows_pad = (rows + BW_PK_ROWS - 1) / BW_PK_ROWS * BW_PK_ROWS;
+  if (idx >= rows_pad * fgs) return;
+  const int64_t r = idx / fgs;
+  const int fg = (int)(idx % fgs);
+  float x[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) x[k] = r < rows ? X[(size_t)r * F + 8 * fg + k] : 0.f;
+  uint32_t h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) tc::split2(x[2 * j], x[2 * j + 1], h[j], l[j]);
+  uint8_t* p = bw_pk_ptr(reinterpret_cast<float*>(out), F, r, 8 * fg);
+  *reinterpret_cast<uint4*>(p) = make_uint4(h[0], h[1], h[2], h[3]);
+  *reinterpret_cast<uint4*>(p + bw_pk_lo_offset(F)) = make_uint4(l[0], l[1], l[2], l[3]);
 }
 
 // partial slices -> gradient tensor.  mode: 0 dst[n * 128 + m] (dW3 = C^T), 1 dst[m * ldd + n] for n < n_keep (dense rows

@@ -773,6 +773,25 @@ int launch_wgrad(const float* A, int lda, int M, const float* B, int ldb, int N,
   LIDF_LAUNCH_CHECK();
   return LIDF_OK;
 }
+// same contract for operands in the packed hand-over layout (lidf_bwd.cuh: bw_pk_*): C[128][N] partial slices += A^T B over
+// `groups` 64-row groups
+int launch_wgrad_pk(const float* A, int FA, const float* B, int FB, int64_t groups, float* partial, int n_cta, cudaStream_t st) {
+  if (groups <= 0) return LIDF_OK;
+  if (FA != 128 || FB % 16 || FB < 16 || FB > 256) return LIDF_ERR_ARG;
+  WgPkArgs a{};
+  a.A = reinterpret_cast<const uint8_t*>(A); a.FA = FA; a.B = reinterpret_cast<const uint8_t*>(B); a.FB = FB;
+  a.groups = groups; a.partial = partial;
+  const size_t stage = bw_pk_group_bytes(FA) + bw_pk_group_bytes(FB);
+  int ns = (int)((227 * 1024 - 1024) / stage);
+  a.n_stages = ns > WPK_MAX_STAGES ? WPK_MAX_STAGES : ns;
+  if (a.n_stages < 2) return LIDF_ERR_ARG;
+  const size_t smem = 1024 + (size_t)a.n_stages * stage;
+  const int grid = (int)(groups < n_cta ? groups : n_cta);
+  LIDF_CUDA(cudaFuncSetAttribute(k_wgrad_pk_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  k_wgrad_pk_tc<3><<<grid, WPK_THREADS, smem, st>>>(a);
+  LIDF_LAUNCH_CHECK();
+  return LIDF_OK;
+}
 int finish_wgrad(const float* partial, int n_cta, int M, int N, int mode, float* dst, int ldd, int n_keep, int pe_pos,
                  int ones_col, float* extra, cudaStream_t st) {
   WgFinishArgs f{partial, n_cta, M, N, mode, dst, ldd, n_keep, pe_pos, ones_col, extra};
@@ -806,6 +825,30 @@ extern "C" int lidf_wgrad_selftest(const float* A, const float* B, float* C, int
   float* partial = (float*)scratch;
   LIDF_CUDA(cudaMemsetAsync(partial, 0, (size_t)148 * M * N * sizeof(float), st));
   int rc = launch_wgrad(A, M, M, B, N, N, N, rows, partial, 148, st);
+  if (rc) return rc;
+  return finish_wgrad(partial, 148, M, N, 1, C, N, N, 0, -1, nullptr, st);
+}
+
+extern "C" size_t lidf_wgrad_pk_selftest_scratch_bytes(int64_t rows, int32_t M, int32_t N) {
+  const size_t groups = (size_t)((rows + BW_PK_ROWS - 1) / BW_PK_ROWS);
+  return (size_t)148 * M * N * sizeof(float) + groups * (bw_pk_group_bytes(M) + bw_pk_group_bytes(N)) + 1024;
+}
+extern "C" int lidf_wgrad_pk_selftest(const float* A, const float* B, float* C, int64_t rows, int32_t M, int32_t N, void* scratch,
+                                      lidf_stream_t stream) {
+  if (!A || !B || !C || !scratch) return LIDF_ERR_NULL;
+  if (rows <= 0 || M != 128 || N % 16 || N < 16 || N > 256) return LIDF_ERR_ARG;
+  if (!tc_device_ok()) return LIDF_ERR_NO_SM100;
+  cudaStream_t st = stream;
+  const int64_t groups = (rows + BW_PK_ROWS - 1) / BW_PK_ROWS;
+  float* partial = (float*)scratch;
+  uint8_t* Apk = (uint8_t*)scratch + ((size_t)148 * M * N * sizeof(float) + 255) / 256 * 256;
+  uint8_t* Bpk = Apk + (size_t)groups * bw_pk_group_bytes(M);
+  LIDF_CUDA(cudaMemsetAsync(partial, 0, (size_t)148 * M * N * sizeof(float), st));
+  k_pk_pack_rows<<<(unsigned)((groups * BW_PK_ROWS * (M / 8) + 255) / 256), 256, 0, st>>>(A, rows, M, Apk);
+  LIDF_LAUNCH_CHECK();
+  k_pk_pack_rows<<<(unsigned)((groups * BW_PK_ROWS * (N / 8) + 255) / 256), 256, 0, st>>>(B, rows, N, Bpk);
+  LIDF_LAUNCH_CHECK();
+  int rc = launch_wgrad_pk((const float*)Apk, M, (const float*)Bpk, N, groups, partial, 148, st);
   if (rc) return rc;
   return finish_wgrad(partial, 148, M, N, 1, C, N, N, 0, -1, nullptr, st);
 }
@@ -958,8 +1001,9 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
         const int grid = n_tiles < n_cta ? n_tiles : n_cta;
         k_mlp_bwd_tc<3><<<grid, TC_THREADS, bw_smem, st>>>(a);
         LIDF_LAUNCH_CHECK();
-        if ((rc = launch_wgrad(b.h2, LIDF_H2, 128, b.d3, LIDF_H3, 64, 64, n_rows, part_w3, n_cta, st))) return rc;     // dW3^T
-        if ((rc = launch_wgrad(b.d2, LIDF_H2, 128, b.h1, LIDF_H1, 256, 256, n_rows, part_w2, n_cta, st))) return rc;   // dW2
+        // B1 wrote h1, h2, delta2, delta3 of all n_tiles x 128 rows in the packed layout (dead rows: delta = 0)
+        if ((rc = launch_wgrad_pk(b.h2, LIDF_H2, b.d3, LIDF_H3, 2 * (int64_t)n_tiles, part_w3, n_cta, st))) return rc;   // dW3^T
+        if ((rc = launch_wgrad_pk(b.d2, LIDF_H2, b.h1, LIDF_H1, 2 * (int64_t)n_tiles, part_w2, n_cta, st))) return rc;   // dW2
       }
       if ((rc = launch_wgrad(b.d1, LIDF_H1, 256, b.pe, BW_PE_LD, BW_PE_LD, BW_PE_LD, n_rows, part_w1, n_cta, st))) return rc;   // dW1[:,pos]
       k_segsum_rays<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(b.d1, s0, n_rows, row_ray_start, R, b.Gr, 256 * d);

@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
     "lidf_image_loss_workspace_bytes", "lidf_image_loss",
     "lidf_query_backward_workspace_bytes", "lidf_query_backward", "lidf_query_last_bwd_ms",
-    "lidf_wgrad_selftest_scratch_bytes", "lidf_wgrad_selftest",
+    "lidf_wgrad_selftest_scratch_bytes", "lidf_wgrad_selftest", "lidf_wgrad_pk_selftest_scratch_bytes", "lidf_wgrad_pk_selftest",
     "lidf_depth_metrics_workspace_bytes", "lidf_depth_metrics_rays", "lidf_depth_metrics_image",
 ]
 # include/lidf_pointnet.h (bound by models/pointnet.py)
@@ -124,6 +124,10 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_wgrad_selftest_scratch_bytes.argtypes = [C.c_int32, C.c_int32]
     lib.lidf_wgrad_selftest.restype = C.c_int
     lib.lidf_wgrad_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
+    lib.lidf_wgrad_pk_selftest_scratch_bytes.restype = C.c_size_t
+    lib.lidf_wgrad_pk_selftest_scratch_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    lib.lidf_wgrad_pk_selftest.restype = C.c_int
+    lib.lidf_wgrad_pk_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.lidf_depth_metrics_workspace_bytes.restype = C.c_size_t
     lib.lidf_depth_metrics_workspace_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
     lib.lidf_depth_metrics_rays.restype = C.c_int
@@ -803,16 +807,19 @@ class _LidfQuery:
         """Device time of the backward's tcgen05 section in the latest ``backward`` (CUDA events on the launching stream)."""
         return float(self.lib.lidf_query_last_bwd_ms())
 
-    def wgrad_selftest(self, A: torch.Tensor, B: torch.Tensor) -> torch.Tensor:
-        """C = A.T @ B through k_wgrad_tc (A [rows,M], M in {128,256}; B [rows,N], N % 16 == 0, N <= 256)."""
+    def wgrad_selftest(self, A: torch.Tensor, B: torch.Tensor, packed: bool = False) -> torch.Tensor:
+        """C = A.T @ B through k_wgrad_tc (A [rows,M], M in {128,256}; B [rows,N], N % 16 == 0, N <= 256), or with
+        ``packed`` through the backward's packed hand-over path (k_pk_pack_rows -> k_wgrad_pk_tc, M = 128)."""
         dev = A.device
         rows, M = (int(v) for v in A.shape); N = int(B.shape[1])
         out = torch.empty(M, N, dtype=torch.float32, device=dev)
-        scratch = torch.empty(int(self.lib.lidf_wgrad_selftest_scratch_bytes(M, N)), dtype=torch.uint8, device=dev)
+        nbytes = self.lib.lidf_wgrad_pk_selftest_scratch_bytes(rows, M, N) if packed else self.lib.lidf_wgrad_selftest_scratch_bytes(M, N)
+        scratch = torch.empty(int(nbytes), dtype=torch.uint8, device=dev)
+        fn = self.lib.lidf_wgrad_pk_selftest if packed else self.lib.lidf_wgrad_selftest
         with torch.cuda.device(dev):
-            rc = self.lib.lidf_wgrad_selftest(_chk(A, "A", torch.float32), _chk(B, "B", torch.float32), out.data_ptr(), rows, M, N,
-                                              scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
-        self._raise(rc, "lidf_wgrad_selftest")
+            rc = fn(_chk(A, "A", torch.float32), _chk(B, "B", torch.float32), out.data_ptr(), rows, M, N,
+                    scratch.data_ptr(), C.c_void_p(torch.cuda.current_stream(dev).cuda_stream))
+        self._raise(rc, "lidf_wgrad_pk_selftest" if packed else "lidf_wgrad_selftest")
         torch.cuda.synchronize(dev)
         return out
 

@@ -217,6 +217,11 @@ float lidf_query_last_bwd_ms(void);
 size_t lidf_wgrad_selftest_scratch_bytes(int32_t M, int32_t N);
 int lidf_wgrad_selftest(const float* A, const float* B, float* C, int64_t rows, int32_t M, int32_t N, void* scratch,
                         lidf_stream_t stream);
+/* the same product through the packed hand-over path of the backward (k_pk_pack_rows -> k_wgrad_pk_tc: operands already
+ * split into bf16 hi | lo and laid out for the MN-major UMMA descriptor, fetched by TMA bulk copies); M = 128 */
+size_t lidf_wgrad_pk_selftest_scratch_bytes(int64_t rows, int32_t M, int32_t N);
+int lidf_wgrad_pk_selftest(const float* A, const float* B, float* C, int64_t rows, int32_t M, int32_t N, void* scratch,
+                           lidf_stream_t stream);
 
 size_t lidf_refine_workspace_bytes(const LidfRefineParams* p);
 int lidf_refine_forward(const LidfRefineParams* p, lidf_stream_t stream);

@@ -41,6 +41,20 @@ def test_wgrad_kernel_matches_matmul(rows, M, N):
     assert torch.equal(C, C2)                                    # fixed reduction order: reproducible
 
 
+@pytest.mark.parametrize("rows,N", [(64, 64), (128, 256), (1000, 256), (4097, 64), (70000, 256), (70000, 64), (9600, 128)])
+def test_packed_wgrad_kernel_matches_matmul(rows, N):
+    """k_wgrad_pk_tc: the same product with operands in the backward's packed hand-over layout (bf16 hi | lo in the
+    MN-major UMMA layout, TMA bulk copies, ring of 2-4 stages); bit-identical to k_wgrad_tc when every CTA sees the same
+    rows in the same order is not required -- both are held to the fp64 product."""
+    from implicit_depth_b200.extensions.lidf_query.jit import lidf_query
+    g = torch.Generator().manual_seed(rows + N)
+    A = torch.randn(rows, 128, generator=g).to(_dev()); B = torch.randn(rows, N, generator=g).to(_dev())
+    C = lidf_query.wgrad_selftest(A, B, packed=True)
+    want = A.double().t() @ B.double()
+    assert rel_err(C.cpu(), want.cpu()) < 5e-5
+    assert torch.equal(C, lidf_query.wgrad_selftest(A, B, packed=True))
+
+
 def _to_dev(d, keys):
     return [d[k].to(_dev()).contiguous() for k in keys]
 

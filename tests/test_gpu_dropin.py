@@ -69,9 +69,15 @@ def test_reference_forward_with_mixin_matches_pure_reference(bs, mixin_methods):
     assert agree > 0.995, agree
     assert rel_err(dd_o["pred_pos"][same].cpu(), dd_r["pred_pos"][same].cpu()) < 1e-3
     assert set(loss_r) == set(loss_o)
+    # A ray whose near-tie resolved the other way (random-init decoders: the logits of a ray's pairs differ by ~1e-4, and
+    # the reference's own scatter sums are atomics-ordered, so the count varies from run to run) moves its pred_pos by up
+    # to a voxel: that changes its own term of every per-ray mean and the surface normals of its 4 neighbours (each
+    # bounded by 2).  The losses are therefore compared with 12 / R of slack per flipped ray on top of the 2e-3.
+    n_flip, n_rays = int((~same).sum()), int(same.numel())
+    print(f"drop-in bs={bs}: {n_flip} of {n_rays} rays picked the other pair of a near-tie")
     for k, v in loss_r.items():
         a, b = float(loss_o[k]), float(v)
-        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)), (k, a, b)
+        assert abs(a - b) <= 2e-3 * max(1.0, abs(b)) + 12.0 * n_flip / n_rays, (k, a, b, n_flip)
 
 
 def test_reference_training_forward_backward_with_mixin():
