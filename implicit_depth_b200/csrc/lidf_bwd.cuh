@@ -25,7 +25,7 @@
 
 #define BW_CHUNKS_BWD 20               // 4 (W3^T, N = 128, K = 64) + 8 + 8 (W2^T halves, N = 128, K = 128)
 #define BW_CHUNKS_FWD TC_CHUNKS_PER_DEC
-#define BW_PE_LD 112                   // row pitch of the stored layer-1 MMA operand (K order of tc_a1_col)
+#define BW_PE_F 128                    // feature count of the handed-over layer-1 MMA operand (K order of tc_a1_col; 112 + 16 zeros)
 #define BW_COLPART 8                   // floats per (cta, warp, lane) slot of the column-sum partials
 
 // mbarrier waits of the backward kernels: the tile-serial kernels hand over between the row warps and the MMA issuer a dozen
@@ -119,7 +119,9 @@ struct BwArgs {
   const float* o_in;                                // [P] offset fed to this iteration (original index); NULL: o0
   float* g;                                         // [P] in: dL/d o_it, out (IEF, it > 0): dL/d o_{it-1}
   float* h1; float* h2; float* d2; float* d3;       // chunk-local, PACKED split-bf16 hand-over to k_wgrad_pk_tc (layout: bw_pk_*)
-  float* d1; float* pe;                             // chunk-local fp32 rows (delta1 has three readers); pe NULL = do not write
+  float* pe;                                        // packed too (F = BW_PE_F): the layer-1 MMA operand; NULL = do not write
+  float* d1;                                        // chunk-local fp32 rows [.,256] for the ray / voxel segment sums (summed over IEF passes)
+  float* d1pk;                                      // the same sum, packed, for dW1[:,pos]; non-NULL on the last pass processed (it = 0)
   int d1_accumulate;
   float* colpart;                                   // [grid][16][32][BW_COLPART], accumulated
   int by_slot;                                      // winner-only backward of the offset decoder: rows = rays (perm = each ray's
@@ -348,18 +350,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       __syncwarp();
     };
-    auto store16 = [&](const float* x, float* gbase, int pitch) {   // 16 floats per row: 4 lanes per row, 8 rows per instruction
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-        *reinterpret_cast<float4*>(stg + lane * BW_STAGE_PITCH + 4 * i) = make_float4(x[4 * i], x[4 * i + 1], x[4 * i + 2], x[4 * i + 3]);
-      __syncwarp();
-#pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int r = 8 * j + (lane >> 2), c = 4 * (lane & 3);
-        *reinterpret_cast<float4*>(gbase + (size_t)r * pitch + c) = *reinterpret_cast<const float4*>(stg + r * BW_STAGE_PITCH + c);
-      }
-      __syncwarp();
-    };
     // packed hand-over (bw_pk_*): 16 features [f0, f0 + 16) of this lane's row, w = 8 hi words | 8 lo words as split16 makes
     // them.  One instruction covers the warp's 32 consecutive rows x 16 B = 512 contiguous bytes: no transpose needed.
     auto store_pk16 = [&](float* tensor, int F, int tile_local, int f0, const uint32_t* w) {
@@ -433,7 +423,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           pl[k] = dir[k] * m.t1 - c;
         }
       }
-      float* pewarp = a.pe ? a.pe + (size_t)(tile_local * 128 + q * 32) * BW_PE_LD : nullptr;   // row 0 of this warp's 32 rows
       if (g < 2) {
         float v[48];
 #pragma unroll
@@ -461,8 +450,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           uint32_t w[16];
           tc::split16(v + 16 * j, w);
           st_a1(3 * g + j, w);
+          if (a.pe) store_pk16(a.pe, BW_PE_F, tile_local, 16 * (3 * g + j), w);     // the same words, for dW1[:,pos]
         }
-        if (pewarp) { store32(v, pewarp + 48 * g, BW_PE_LD); store16(v + 32, pewarp + 48 * g + 32, BW_PE_LD); }
       } else if (g == 2) {
         float x[16];
 #pragma unroll
@@ -472,7 +461,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
         uint32_t w[16];
         tc::split16(x, w);
         st_a1(6, w);
-        if (pewarp) store16(x, pewarp + 96, BW_PE_LD);
+        if (a.pe) store_pk16(a.pe, BW_PE_F, tile_local, 96, w);
+      }
+      else if (a.pe) {                                            // column group 3: the zero k-step that pads K to 128
+        uint32_t w[16];
+#pragma unroll
+        for (int k = 0; k < 16; ++k) w[k] = 0u;
+        store_pk16(a.pe, BW_PE_F, tile_local, 112, w);
       }
       tc::fence_proxy_async();
       __syncwarp();
@@ -625,6 +620,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
         uint32_t r[32];
         tc::tmem_ld32(lane_addr + (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g, r);
         tc::wait_ld();
+        if (hf == 1) {                                            // X0 / X1 are in registers: layer 1 of the next tile may overwrite them
+          tc::fence_before_sync();                                // while this tile's delta1 is still being stored
+          __syncwarp();
+          if (lane == 0) tc::mbar_arrive(&S.x2_done);
+        }
         const uint32_t mk = hf == 0 ? mask1a : mask1b;
         float d1[32];
 #pragma unroll
@@ -636,8 +636,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
 #pragma unroll
           for (int e = 0; e < 32; ++e) old[e] += d1[e];
           store32(old, dwarp, LIDF_H1);
+          if (a.d1pk) {
+#pragma unroll
+            for (int s16 = 0; s16 < 2; ++s16) {
+              uint32_t w[16];
+              tc::split16(old + 16 * s16, w);
+              store_pk16(a.d1pk, LIDF_H1, tile_local, n0 + 16 * s16, w);
+            }
+          }
         } else {
           store32(d1, dwarp, LIDF_H1);
+          if (a.d1pk) {
+#pragma unroll
+            for (int s16 = 0; s16 < 2; ++s16) {
+              uint32_t w[16];
+              tc::split16(d1 + 16 * s16, w);
+              store_pk16(a.d1pk, LIDF_H1, tile_local, n0 + 16 * s16, w);
+            }
+          }
         }
         if (a.is_ief) {
 #pragma unroll
@@ -646,9 +662,6 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           if (hf == 0) acc_du0 += du; else acc_du1 += du;
         }
       }
-      tc::fence_before_sync();
-      __syncwarp();
-      if (lane == 0) tc::mbar_arrive(&S.x2_done);
       if (rank1) {                                                // dL/d o_{it-1} = dL/d o_it + u . delta1
         S.part[par][g][row] = fb;
         tc::bar_quadrant(q);
@@ -990,7 +1003,8 @@ __global__ void k_pk_pack_rows(const float* __restrict__ X, int64_t rows, int F,
 }
 
 // partial slices -> gradient tensor.  mode: 0 dst[n * 128 + m] (dW3 = C^T), 1 dst[m * ldd + n] for n < n_keep (dense rows
-// of a [M, ldd] weight starting at dst), 2 layer-1 PE columns: dst[m * ldd + tc_a1_col(n)], 3 as 1 plus column `ones_col`
+// of a [M, ldd] weight starting at dst), 2 layer-1 PE columns: dst[m * ldd + tc_a1_col(n)] (4: its transpose, dst[n * ldd +
+// tc_a1_col(m)]), 3 as 1 plus column `ones_col`
 // of C -> extra[m] (column sums through the ones column of the PE(dir) block)
 struct WgFinishArgs { const float* partial; int n_cta; int M, N; int mode; float* dst; int ldd; int n_keep; int pe_pos; int ones_col; float* extra; };
 __global__ void k_wgrad_finish(const WgFinishArgs a) {
@@ -1001,6 +1015,7 @@ __global__ void k_wgrad_finish(const WgFinishArgs a) {
   for (int c = 0; c < a.n_cta; ++c) s += a.partial[(size_t)c * a.M * a.N + idx];
   if (a.mode == 0) a.dst[(size_t)n * 128 + m] = s;
   else if (a.mode == 2) { const int col = tc_a1_col(n, a.pe_pos, 0); if (col >= 0) a.dst[(size_t)m * a.ldd + col] = s; }
+  else if (a.mode == 4) { const int col = tc_a1_col(m, a.pe_pos, 0); if (col >= 0) a.dst[(size_t)n * a.ldd + col] = s; }   // C = PE^T delta1
   else {
     if (n < a.n_keep) a.dst[(size_t)m * a.ldd + n] = s;
     if (a.mode == 3 && n == a.ones_col) a.extra[m] = s;

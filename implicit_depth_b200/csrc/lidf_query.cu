@@ -702,7 +702,7 @@ struct BwdPlan {
   uint8_t* wbwd;                 // [2][20][8 KB]
   float* g[2];                   // [P] dL/d o of the running IEF iteration, per decoder
   int64_t chunk_rows;
-  float *h1, *h2, *d1, *d2, *d3, *pe;
+  float *h1, *h2, *d1, *d1pk, *d2, *d3, *pe;
   int64_t* vkeys; CsrBufs vcsr;
   float *Gr, *Gv, *pedir, *droi, *Wg;
   float* partial; size_t partial_floats; int n_cta;
@@ -730,7 +730,8 @@ int plan_backward(const LidfQueryBackwardParams* bp, BwdPlan* b, char* base) {
   b->chunk_rows = cr;
   b->h1 = bm.take<float>((size_t)cr * LIDF_H1); b->h2 = bm.take<float>((size_t)cr * LIDF_H2);
   b->d1 = bm.take<float>((size_t)cr * LIDF_H1); b->d2 = bm.take<float>((size_t)cr * LIDF_H2);
-  b->d3 = bm.take<float>((size_t)cr * LIDF_H3); b->pe = bm.take<float>((size_t)cr * BW_PE_LD);
+  b->d3 = bm.take<float>((size_t)cr * LIDF_H3); b->pe = bm.take<float>((size_t)cr * BW_PE_F);
+  b->d1pk = bm.take<float>((size_t)cr * LIDF_H1);
   b->vkeys = bm.take<int64_t>((size_t)cr);
   b->vcsr = carve_csr(bm, cr, V > 0 ? V : 1);
   b->Gr = bm.take<float>((size_t)(R > 0 ? R : 1) * 512); b->Gv = bm.take<float>((size_t)(V > 0 ? V : 1) * 512);
@@ -964,7 +965,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
   cudaEventRecord(g_ev_bwd[0], st);
   float* part_w3 = b.partial;                                   // [n_cta][128*64]
   float* part_w2 = part_w3 + (size_t)b.n_cta * 128 * 64;        // [n_cta][128*256]
-  float* part_w1 = part_w2 + (size_t)b.n_cta * 128 * 256;       // [n_cta][256*112]
+  float* part_w1 = part_w2 + (size_t)b.n_cta * 128 * 256;       // [n_cta][128*256]  (PE^T delta1)
   for (int d = 0; d < 2; ++d) {
     const LidfDecoder& dc = *decs[d];
     const LidfDecoderGrad& gd = *grads[d];
@@ -996,6 +997,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
         a.g = by_slot ? b.g0r : b.g[d];
         a.h1 = b.h1; a.h2 = b.h2; a.d1 = b.d1; a.d2 = b.d2; a.d3 = b.d3;
         a.pe = it == n_pass - 1 ? b.pe : nullptr;
+        a.d1pk = it == 0 ? b.d1pk : nullptr;
         a.d1_accumulate = it == n_pass - 1 ? 0 : 1;
         a.colpart = b.colpart;
         const int grid = n_tiles < n_cta ? n_tiles : n_cta;
@@ -1005,7 +1007,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
         if ((rc = launch_wgrad_pk(b.h2, LIDF_H2, b.d3, LIDF_H3, 2 * (int64_t)n_tiles, part_w3, n_cta, st))) return rc;   // dW3^T
         if ((rc = launch_wgrad_pk(b.d2, LIDF_H2, b.h1, LIDF_H1, 2 * (int64_t)n_tiles, part_w2, n_cta, st))) return rc;   // dW2
       }
-      if ((rc = launch_wgrad(b.d1, LIDF_H1, 256, b.pe, BW_PE_LD, BW_PE_LD, BW_PE_LD, n_rows, part_w1, n_cta, st))) return rc;   // dW1[:,pos]
+      if ((rc = launch_wgrad_pk(b.pe, BW_PE_F, b.d1pk, LIDF_H1, 2 * (int64_t)n_tiles, part_w1, n_cta, st))) return rc;    // dW1[:,pos]^T
       k_segsum_rays<<<(unsigned)((R * 32 + 255) / 256), 256, 0, st>>>(b.d1, s0, n_rows, row_ray_start, R, b.Gr, 256 * d);
       LIDF_LAUNCH_CHECK();
       k_chunk_vox_keys<<<(n_rows + 255) / 256, 256, 0, st>>>(row_perm, p->pair_vox, s0, n_rows, V, b.vkeys);
@@ -1016,7 +1018,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
     }
     if ((rc = finish_wgrad(part_w3, n_cta, 128, 64, 0, gd.w3, 0, 0, 0, -1, nullptr, st))) return rc;
     if ((rc = finish_wgrad(part_w2, n_cta, 128, 256, 1, gd.w2, 256, 256, 0, -1, nullptr, st))) return rc;
-    if ((rc = finish_wgrad(part_w1, n_cta, 256, BW_PE_LD, 2, gd.w1, ldw[d], 0, q.pe_pos, -1, nullptr, st))) return rc;
+    if ((rc = finish_wgrad(part_w1, n_cta, 128, 256, 4, gd.w1, ldw[d], 0, q.pe_pos, -1, nullptr, st))) return rc;
     k_bwd_colpart_finish<<<1, 512, 0, st>>>(b.colpart, n_cta, gd.b2, gd.b3, gd.w4, gd.b4, ief ? b.du : nullptr);
     LIDF_LAUNCH_CHECK();
     // row-level weight gradients of layer 1 from the segment sums: dW1[:,rgb] = G_r^T roi, dW1[:,dir] = G_r^T PE(dir)
