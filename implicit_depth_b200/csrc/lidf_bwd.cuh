@@ -374,28 +374,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       __syncwarp();
     };
-    // x[lane's row][0..32) = A_v[vox][col ..) + T[ray][col ..) gathered with whole-row accesses (row indices via shuffles)
-    auto gather_sum32 = [&](float* x, int vox_, int ray_, bool valid_, int col) {
+    // Layer-1 addend A_v[vox][col ..) + T[ray][col ..) of this lane's row.  The A_v part is gathered ONE EPILOGUE AHEAD of its
+    // use: 8 lanes copy 128 B of a row with cp.async straight into the staging tile (row indices via shuffles), so the
+    // latency runs under the previous epilogue / the tail of the previous tile.  The T part is read by the lane for its own
+    // row (lanes of one ray share the address); its lines were prefetched into L2 during the previous tile.
+    const uint32_t stg_sa = tc::smem_u32(stg);
+    auto gather_issue = [&](int vox_, int col) {
 #pragma unroll
       for (int j = 0; j < 8; ++j) {
         const int r = 4 * j + tr;
-        const int vr = __shfl_sync(0xffffffffu, vox_, r), rr = __shfl_sync(0xffffffffu, ray_, r);
-        const bool ok = __shfl_sync(0xffffffffu, valid_ ? 1 : 0, r) != 0;
-        float4 s4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (ok) {
-          const float4 t4 = __ldg(reinterpret_cast<const float4*>(a.T + (size_t)rr * 512 + col + tc4));
-          const float4 a4 = __ldg(reinterpret_cast<const float4*>(a.Av + (size_t)vr * 512 + col + tc4));
-          s4 = make_float4(a4.x + t4.x, a4.y + t4.y, a4.z + t4.z, a4.w + t4.w);
-        }
-        *reinterpret_cast<float4*>(stg + r * BW_STAGE_PITCH + tc4) = s4;
+        const int vr = __shfl_sync(0xffffffffu, vox_, r);
+        tc::cp_async16(stg_sa + (uint32_t)(r * BW_STAGE_PITCH + tc4) * 4u, a.Av + (size_t)vr * 512 + col + tc4);
       }
+      tc::cp_async_commit();
+    };
+    auto gather_read = [&](float* x, int ray_, bool valid_, int col) {
+      float4 tt[8];
+      const float4* tp = reinterpret_cast<const float4*>(a.T + (size_t)ray_ * 512 + col);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) tt[i] = valid_ ? __ldg(tp + i) : make_float4(0.f, 0.f, 0.f, 0.f);
+      tc::cp_async_wait_all();
       __syncwarp();
 #pragma unroll
       for (int i = 0; i < 8; ++i) {
         const float4 v = *reinterpret_cast<const float4*>(stg + lane * BW_STAGE_PITCH + 4 * i);
-        x[4 * i] = v.x; x[4 * i + 1] = v.y; x[4 * i + 2] = v.z; x[4 * i + 3] = v.w;
+        x[4 * i] = valid_ ? v.x + tt[i].x : 0.f; x[4 * i + 1] = valid_ ? v.y + tt[i].y : 0.f;
+        x[4 * i + 2] = valid_ ? v.z + tt[i].z : 0.f; x[4 * i + 3] = valid_ ? v.w + tt[i].w : 0.f;
       }
-      __syncwarp();
+      __syncwarp();                                                // the tile may be overwritten by the next gather / store
     };
     struct RowMeta { int orig, vox, ray; float t0, t1; bool valid; };
     auto load_meta = [&](int tile_local) {
@@ -478,6 +484,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
     uint32_t par = 0;
     RowMeta cur = load_meta((int)blockIdx.x);
     build_a1(cur, (int)blockIdx.x);
+    if (n_my_tiles > 0) gather_issue(cur.vox, a.dcol + 32 * g);
     for (int t = 0; t < n_my_tiles; ++t) {
       const int tile_local = (int)blockIdx.x + t * (int)gridDim.x;
       const uint32_t ph = (uint32_t)t & 1u;
@@ -497,7 +504,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       for (int hf = 0; hf < 2; ++hf) {
         const int n0 = 128 * hf + 32 * g;
         float xo[32];
-        gather_sum32(xo, cur.vox, cur.ray, valid, a.dcol + n0);   // A_v + T, before waiting for the accumulator
+        gather_read(xo, cur.ray, valid, a.dcol + n0);             // A_v + T, before waiting for the accumulator
+        if (hf == 0) gather_issue(cur.vox, a.dcol + 128 + 32 * g);   // second half's A_v rows: in flight during this epilogue
         const uint32_t xcol = (hf ? TC_COL_X1 : TC_COL_X0) + 32 * g;
         bw_wait(&S.x_full[hf], ph);
         tc::fence_after_sync();
@@ -528,6 +536,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
       }
       // ---- operand of the next tile (its last reader, L1 of this tile, has retired once a1_free completes)
       if (has_next) {
+        if (nxt.valid)                                            // next tile's T lines -> L2 (8 lines per ray and decoder, one per lane)
+          asm volatile("prefetch.global.L2 [%0];" ::"l"(a.T + (size_t)nxt.ray * 512 + a.dcol + 32 * (row & 7)));
         bw_wait(&S.a1_free, ph);
         build_a1(nxt, tile_local + (int)gridDim.x);
       }
@@ -662,6 +672,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) k_mlp_bwd_tc(const __grid_const
           if (hf == 0) acc_du0 += du; else acc_du1 += du;
         }
       }
+      if (has_next) gather_issue(nxt.vox, a.dcol + 32 * g);       // first half of the next tile (the staging tile is free again)
       if (rank1) {                                                // dL/d o_{it-1} = dL/d o_it + u . delta1
         S.part[par][g][row] = fb;
         tc::bar_quadrant(q);
