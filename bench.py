@@ -585,7 +585,7 @@ def run_train(args, d, ins, off, prob, kw, dev, rank, world, local):
                            allreduce_bytes=4 * n_dec_params, allreduce_full_model_86MB_ms=ar_full,
                            forward_mlp_kernel_ms=med(t_mlp), backward_tc_section_ms=med(t_bwd_tc)),
                 roofline=dict(bound="tensor", achieved=achieved, peak=peak, unit="TFLOP/s", frac=achieved / peak, traffic=None,
-                              kernel="k_mlp_tc + k_mlp_bwd_tc + k_wgrad_tc", kernel_ms=k_ms, kernel_share_of_step=k_ms / ms_per_step,
+                              kernel="k_mlp_tc + k_mlp_bwd_tc + k_wgrad_pk_tc + k_wgrad_tc", kernel_ms=k_ms, kernel_share_of_step=k_ms / ms_per_step,
                               flop_per_point_nominal=flop_pt, peak_source=peaks["source"] + ", bf16_tflops_sustained",
                               note="nominal forward + backward FLOPs of the reference's Linear stack (3 x forward) over the "
                                    "decoder kernel of the forward plus the backward's tcgen05 section; the backward skips the offset "

@@ -208,7 +208,7 @@ int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream);
 
 size_t lidf_query_backward_workspace_bytes(const LidfQueryBackwardParams* p);
 int lidf_query_backward(const LidfQueryBackwardParams* p, lidf_stream_t stream);
-/* device time (ms) of the backward's tcgen05 kernels (k_mlp_bwd_tc + k_wgrad_tc launches summed) in the most recent
+/* device time (ms) of the backward's tcgen05 section (k_mlp_bwd_tc + k_wgrad_pk_tc + k_wgrad_tc launches and the segment sums between them) in the most recent
  * lidf_query_backward on the calling thread; synchronises; < 0 if none */
 float lidf_query_last_bwd_ms(void);
 
