@@ -10,12 +10,15 @@
 //   k_bwd_seed     per pair : dL/d o_last of both decoders (offset scaling, arg-max gather, final activation)
 //   k_mlp_bwd_tc   "B1", tcgen05, one decoder pass per launch over a chunk of ray-major pairs: recomputes the forward
 //                  (activations are never stored by the forward), then the two dgrad GEMMs as TS-mode MMAs with
-//                  transposed weight chunks; h1, h2, delta1..3 (and PE once) leave the SM as fp32 rows for the wgrad
-//                  kernel; bias / w4 / IEF-u gradients are column sums done with shuffles; the IEF feedback
+//                  transposed weight chunks; h1, h2, delta1..3 (and PE once) leave the SM for the wgrad kernel already
+//                  split into bf16 hi | lo and in that kernel's operand layout (bw_pk_*; delta1 also as fp32 rows for the
+//                  segment sums); bias / w4 / IEF-u gradients are column sums done with shuffles; the IEF feedback
 //                  dL/d o_{k-1} = dL/d o_k + u . delta1 is carried between the passes in a [P] array.
-//   k_wgrad_tc     "B2", tcgen05: C[M,N] += A^T B over the rows of a chunk (K = pair index), both operands split bf16
-//                  hi/lo, 3 products, accumulators resident in TMEM over all row groups of the CTA, per-CTA partial
-//                  slices reduced in a fixed order afterwards (reproducible).
+//   k_wgrad_pk_tc  "B2", tcgen05: C[128,N] += A^T B over the rows of a chunk (K = pair index), operands fetched packed by
+//                  TMA bulk copies (MN-major descriptors), 3 products, accumulator resident in TMEM over all row groups
+//                  of the CTA, per-CTA partial slices reduced in a fixed order afterwards (reproducible).
+//   k_wgrad_tc     the same product for operands that only exist as fp32 rows (the row-level terms: G_r, G_v, ROI feature,
+//                  occ_voxel_feat): loader warps convert to bf16 hi/lo into the K-major layout.
 //   k_segsum_*     G_r[ray] += delta1, G_v[vox] += delta1: the factored terms turn the two widest weight gradients into
 //                  segment sums followed by small GEMMs (dW1[:,rgb|dir] = G_r^T [roi | PE(dir)], dW1[:,vox] = G_v^T feat,
 //                  d roi = G_r W1[:,rgb], d occ_voxel_feat = G_v W1[:,vox])
@@ -196,11 +199,13 @@ __device__ __forceinline__ void bw_ts64(uint32_t tmem, uint64_t wd64, uint32_t d
   }
 }
 
-// One decoder pass, forward recompute + dgrad, tile-serial (the kernel is bound by the fp32 rows it writes, not by the
-// tensor pipe).  Same roles and TMEM plan as k_mlp_tc: Z [0,64), X0 [128,256), X1 [256,384), Y [384,512).
-// Global traffic goes through a per-warp shared-memory transpose tile: a thread owns a ROW (TMEM lane) but a coalesced
-// access wants 8 lanes per 128-byte row segment -- the first version stored 16 bytes per lane into 32 different lines per
-// instruction and sat at 70 % L1TEX throughput / 26 % of the HBM rate (profiles/r2a); two CTAs per SM did not help.
+// One decoder pass, forward recompute + dgrad, tile-serial (the kernel is a latency chain of seven epilogues and five MMA
+// phases per tile, not bound by the tensor pipe).  Same roles and TMEM plan as k_mlp_tc: Z [0,64), X0 [128,256),
+// X1 [256,384), Y [384,512).
+// Row-major fp32 traffic (the A_v / T gathers, delta1) goes through a per-warp shared-memory transpose tile: a thread owns a
+// ROW (TMEM lane) but a coalesced access wants 8 lanes per 128-byte row segment -- the first version stored 16 bytes per
+// lane into 32 different lines per instruction and sat at 70 % L1TEX throughput / 26 % of the HBM rate (profiles/r2a); two
+// CTAs per SM did not help.  The packed hand-over tensors need no transpose (see bw_pk_*).
 //   MMA order per tile : L1 -> X0, X1 | L2 -> Y | L3 -> Z | D2: delta3 (in Z) W3 -> Y | D1: delta2 (in Y) W2 -> X0, X1
 //   row warps per tile : E1 x2 (h1, mask1) | [next tile's operand] | E2 (h2, mask2) | E3 (delta3) | Ed2 (delta2) | Ed1 x2
 template <int NPROD>
