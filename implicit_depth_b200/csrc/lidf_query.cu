@@ -830,6 +830,15 @@ extern "C" int lidf_wgrad_selftest(const float* A, const float* B, float* C, int
   return finish_wgrad(partial, 148, M, N, 1, C, N, N, 0, -1, nullptr, st);
 }
 
+// Byte offset of element (row, feature) of a [rows, F] tensor in the packed hand-over layout of the backward (hi part, or lo
+// part with lo != 0); < 0 on bad arguments.  Host arithmetic only: lets a CPU test hold the layout against the canonical
+// MN-major UMMA layout the wgrad kernel's descriptors assume.
+extern "C" int64_t lidf_pk_offset_bytes(int32_t F, int64_t row, int32_t feature, int32_t lo) {
+  if (F <= 0 || F % 8 || row < 0 || feature < 0 || feature >= F) return -1;
+  return (int64_t)((size_t)(row / BW_PK_ROWS) * bw_pk_group_bytes(F) + (lo ? bw_pk_lo_offset(F) : 0) +
+                   (size_t)(feature >> 3) * BW_PK_FG_BYTES + (size_t)(row % BW_PK_ROWS) * 16 + (size_t)(feature & 7) * 2);
+}
+
 extern "C" size_t lidf_wgrad_pk_selftest_scratch_bytes(int64_t rows, int32_t M, int32_t N) {
   const size_t groups = (size_t)((rows + BW_PK_ROWS - 1) / BW_PK_ROWS);
   return (size_t)148 * M * N * sizeof(float) + groups * (bw_pk_group_bytes(M) + bw_pk_group_bytes(N)) + 1024;

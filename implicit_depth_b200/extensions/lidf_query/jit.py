@@ -83,7 +83,7 @@ EXPORTED_SYMBOLS = [
     "lidf_query_last_mlp_ms", "lidf_tc_selftest", "lidf_ray_loss_workspace_bytes", "lidf_ray_loss",
     "lidf_image_loss_workspace_bytes", "lidf_image_loss",
     "lidf_query_backward_workspace_bytes", "lidf_query_backward", "lidf_query_last_bwd_ms",
-    "lidf_wgrad_selftest_scratch_bytes", "lidf_wgrad_selftest", "lidf_wgrad_pk_selftest_scratch_bytes", "lidf_wgrad_pk_selftest",
+    "lidf_wgrad_selftest_scratch_bytes", "lidf_wgrad_selftest", "lidf_wgrad_pk_selftest_scratch_bytes", "lidf_wgrad_pk_selftest", "lidf_pk_offset_bytes",
     "lidf_depth_metrics_workspace_bytes", "lidf_depth_metrics_rays", "lidf_depth_metrics_image",
 ]
 # include/lidf_pointnet.h (bound by models/pointnet.py)
@@ -126,6 +126,8 @@ def load_library(build_if_needed: bool = True) -> C.CDLL:
     lib.lidf_wgrad_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.lidf_wgrad_pk_selftest_scratch_bytes.restype = C.c_size_t
     lib.lidf_wgrad_pk_selftest_scratch_bytes.argtypes = [C.c_int64, C.c_int32, C.c_int32]
+    lib.lidf_pk_offset_bytes.restype = C.c_int64
+    lib.lidf_pk_offset_bytes.argtypes = [C.c_int32, C.c_int64, C.c_int32, C.c_int32]
     lib.lidf_wgrad_pk_selftest.restype = C.c_int
     lib.lidf_wgrad_pk_selftest.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
     lib.lidf_depth_metrics_workspace_bytes.restype = C.c_size_t

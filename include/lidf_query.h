@@ -220,6 +220,9 @@ int lidf_wgrad_selftest(const float* A, const float* B, float* C, int64_t rows, 
 /* the same product through the packed hand-over path of the backward (k_pk_pack_rows -> k_wgrad_pk_tc: operands already
  * split into bf16 hi | lo and laid out for the MN-major UMMA descriptor, fetched by TMA bulk copies); M = 128 */
 size_t lidf_wgrad_pk_selftest_scratch_bytes(int64_t rows, int32_t M, int32_t N);
+/* byte offset of element (row, feature) of a [rows, F] tensor in that packed layout (lo != 0: the lo part); host
+ * arithmetic only, < 0 on bad arguments */
+int64_t lidf_pk_offset_bytes(int32_t F, int64_t row, int32_t feature, int32_t lo);
 int lidf_wgrad_pk_selftest(const float* A, const float* B, float* C, int64_t rows, int32_t M, int32_t N, void* scratch,
                            lidf_stream_t stream);
 

@@ -45,6 +45,37 @@ def test_library_builds_loads_and_exports_every_declared_symbol():
     assert lib.lidf_voxelize_workspace_bytes(10000, 8, 9, 9, 9) > 8 * 729 * 8 and lib.lidf_voxelize_workspace_bytes(5, 0, 9, 9, 9) == 0
 
 
+def test_packed_handover_layout_is_the_canonical_mn_major_umma_layout():
+    """The backward hands activations to the wgrad kernel in 64-row groups laid out as `[hi: F/8 feature groups][64 rows][16 B]
+    [lo: same]` (csrc/lidf_bwd.cuh: bw_pk_*).  k_wgrad_pk_tc bulk-copies a group and describes it to tcgen05.mma as a Major-MN,
+    no-swizzle operand with LBO = 128 B and SBO = 1 KB; CUTLASS documents that canonical layout, in 16-byte units, as
+    ((1,n),(8,k)) : ((X,SBO),(1,LBO)) (cute/atom/mma_traits_sm100.hpp, make_umma_desc<Major::MN>).  Restated here and held
+    against the library's own offset arithmetic, plus the properties the kernels rely on."""
+    from implicit_depth_b200.extensions.lidf_query import jit
+    lib = jit.load_library()
+    LBO, SBO, ROWS = 128, 1024, 64
+
+    def canonical(m, k):               # byte offset of element (feature m, row k) inside one group's hi (or lo) part
+        return (m // 8) * SBO + (k % 8) * 16 + (k // 8) * LBO + (m % 8) * 2
+    for F in (64, 128, 256):
+        group, lo_off = ROWS * F * 4, (F // 8) * SBO
+        for row in (0, 1, 7, 8, 63, 64, 65, 127, 1000):
+            for m in (0, 1, 7, 8, F // 2 + 3, F - 1):
+                for lo in (0, 1):
+                    want = (row // ROWS) * group + lo * lo_off + canonical(m, row % ROWS)
+                    assert lib.lidf_pk_offset_bytes(F, row, m, lo) == want, (F, row, m, lo)
+        # a warp of k_mlp_bwd_tc (32 consecutive rows, one 16-byte unit each) writes 512 contiguous bytes
+        offs = [lib.lidf_pk_offset_bytes(F, 32 + r, 8, 0) for r in range(32)]
+        assert offs == list(range(offs[0], offs[0] + 512, 16))
+        # hi and lo parts tile the group exactly: no byte is shared, none is left over
+        seen = {lib.lidf_pk_offset_bytes(F, r, m, lo) for r in range(ROWS) for m in range(0, F, 8) for lo in (0, 1)}
+        assert len(seen) == 2 * ROWS * F // 8 and min(seen) == 0 and max(seen) == group - 16
+    # one pipeline stage of each product the backward runs (A features + B features) leaves room for >= 2 stages in 227 KB
+    for fa, fb in ((128, 64), (128, 256), (128, 256)):
+        assert 2 * ROWS * (fa + fb) * 4 + 1024 <= 227 * 1024
+    assert lib.lidf_pk_offset_bytes(100, 0, 0, 0) == -1 and lib.lidf_pk_offset_bytes(128, 0, 128, 0) == -1
+
+
 def test_no_cpu_fallback_for_aabb_ops():
     from implicit_depth_b200.extensions.pcl_aabb.jit import pcl_aabb
     from implicit_depth_b200.extensions.ray_aabb.jit import ray_aabb
