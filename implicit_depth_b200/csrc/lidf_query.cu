@@ -693,8 +693,22 @@ extern "C" int lidf_query_forward(const LidfQueryParams* p, lidf_stream_t stream
 //   per decoder: wgrad finish, column sums, dW1[:,rgb|dir|vox] = G^T [roi | PE(dir) | occ_voxel_feat] (k_wgrad_tc)
 //   d roi = G_r W1[:,rgb] -> k_roi_align_backward ; d occ_voxel_feat = G_v W1[:,vox]
 // -------------------------------------------------------------------------------------------------
-static thread_local cudaEvent_t g_ev_bwd[2] = {nullptr, nullptr};
+// timing events of the backward's tcgen05 section, one pair per device ordinal like the forward's (an event belongs to the
+// device it was created on; a failed create / record only disables the timing, never the call)
+static thread_local cudaEvent_t g_ev_bwd_dev[LIDF_MAX_DEVICES][2] = {};
+static thread_local cudaEvent_t* g_ev_bwd = g_ev_bwd_dev[0];
 static thread_local bool g_ev_bwd_valid = false;
+static void bwd_event(int which, cudaStream_t st) {
+  int dev = 0;
+  if (which == 0) g_ev_bwd_valid = false;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= LIDF_MAX_DEVICES) { cudaGetLastError(); return; }
+  g_ev_bwd = g_ev_bwd_dev[dev];
+  if (!g_ev_bwd[0] && (cudaEventCreate(&g_ev_bwd[0]) != cudaSuccess || cudaEventCreate(&g_ev_bwd[1]) != cudaSuccess)) {
+    cudaGetLastError(); g_ev_bwd[0] = g_ev_bwd[1] = nullptr; return;
+  }
+  if (cudaEventRecord(g_ev_bwd[which], st) != cudaSuccess) { cudaGetLastError(); g_ev_bwd_valid = false; return; }
+  if (which == 1) g_ev_bwd_valid = true;
+}
 
 namespace {
 struct BwdPlan {
@@ -970,8 +984,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
   const int n_cta = sms < b.n_cta ? sms : b.n_cta;
   const size_t bw_smem = sizeof(BwSmem) + 1024;
   LIDF_CUDA(cudaFuncSetAttribute(k_mlp_bwd_tc<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bw_smem));
-  if (!g_ev_bwd[0]) { cudaEventCreate(&g_ev_bwd[0]); cudaEventCreate(&g_ev_bwd[1]); }
-  cudaEventRecord(g_ev_bwd[0], st);
+  bwd_event(0, st);
   float* part_w3 = b.partial;                                   // [n_cta][128*64]
   float* part_w2 = part_w3 + (size_t)b.n_cta * 128 * 64;        // [n_cta][128*256]
   float* part_w1 = part_w2 + (size_t)b.n_cta * 128 * 256;       // [n_cta][128*256]  (PE^T delta1)
@@ -1047,8 +1060,7 @@ extern "C" int lidf_query_backward(const LidfQueryBackwardParams* bp, lidf_strea
                                             gd.w_enc, gd.b_enc);
     LIDF_LAUNCH_CHECK();
   }
-  cudaEventRecord(g_ev_bwd[1], st);
-  g_ev_bwd_valid = true;
+  bwd_event(1, st);
   // feature gradients: d roi = G_r [W1_off[:,rgb]; W1_prob[:,rgb]] -> ROIAlign^T ; d occ_voxel_feat = G_v [W1[:,vox]; ...]
   const size_t gemm_smem = sizeof(float) * ((size_t)LIDF_SIMT_BM * 512 + LIDF_KC * 128);
   LIDF_CUDA(cudaFuncSetAttribute(k_bwd_rows_gemm, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)gemm_smem));
